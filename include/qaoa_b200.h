@@ -1,0 +1,120 @@
+/* qaoa_b200.h -- C ABI of the B200-native QAOA statevector engine (libqaoa_b200.so).
+ *
+ * This is the drop-in boundary for the ONE hot path of OpenQuantumComputing/QAOA that the engine
+ * replaces: the energy evaluation that the reference performs as
+ *     transpile -> assign_parameters -> backend.run -> get_counts -> problem.cost loop -> Statistic
+ * (reference qaoa/qaoa.py:516-519, 592-614, 653-661, 691-740, 912-922, 1053-1066).
+ * All entry points are extern "C", take plain pointers / sizes, return 0 on success and a non-zero
+ * code on failure (message via qaoa_last_error).  No C++ exception crosses the boundary.
+ *
+ * Ownership: the caller owns every host buffer for the duration of the call only (the engine
+ * copies); the engine owns all device memory and streams.  One handle = one host thread at a time;
+ * calls are blocking (stream-synchronised on return).
+ *
+ * Bit convention: bit i of a basis index x is qubit i and equals string[i] of the string the
+ * reference hands to Problem.cost (qaoa/qaoa.py:605-609).
+ */
+#ifndef QAOA_B200_H
+#define QAOA_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct qaoa_engine qaoa_engine_t;
+
+#define QAOA_DTYPE_C64 0
+#define QAOA_DTYPE_C128 1
+
+#define QAOA_MIXER_X 0       /* qaoa/mixers/x_mixer.py:28-35            */
+#define QAOA_MIXER_XMULTI 1  /* qaoa/mixers/x_multiangle_mixer.py:24-50 */
+#define QAOA_MIXER_XY 2      /* qaoa/mixers/xy_mixer.py:42-79           */
+#define QAOA_MIXER_GROVER 3  /* qaoa/mixers/grover_mixer.py:43-82       */
+
+#define QAOA_INIT_PLUS 0         /* qaoa/initialstates/plus_initialstate.py:19-25        */
+#define QAOA_INIT_DICKE 1        /* qaoa/initialstates/dicke_initialstate.py:23-56       */
+#define QAOA_INIT_STATEVECTOR 2  /* qaoa/initialstates/statevector_initialstate.py:19-33 */
+
+/* Creates an engine for n_qubits on CUDA device `device`.  Replaces the construction of the
+ * transpiled parameterised circuit + AerSimulator instance (qaoa/qaoa.py:204, 418-520). */
+int qaoa_create(int n_qubits, int dtype, int device, qaoa_engine_t** out);
+int qaoa_destroy(qaoa_engine_t* h);
+const char* qaoa_last_error(qaoa_engine_t* h);
+/* error text when no handle exists (failed qaoa_create) */
+const char* qaoa_global_error(void);
+
+/* Tunables / test hooks: "small_max_qubits", "keep_state", "batch_points". */
+int qaoa_set_option(qaoa_engine_t* h, const char* key, double value);
+double qaoa_get_counter(qaoa_engine_t* h, const char* key); /* "launches", "bytes_alg", ... */
+
+/* Cost diagonal = GraphProblem.cost for every basis index (qaoa/problems/graph_problem.py:152-176).
+ * u,v: relabelled edge endpoints in G.edges() order; w: weights; bits_per_node = ceil(log2 k);
+ * lut[2^bits]: colour id of the b-bit integer whose bit j is qubit v*b+j; n_nodes includes a fixed
+ * last node when fixed_node != 0 (fix_one_node, graph_problem.py:148-149), whose colour id is
+ * fixed_colour. */
+int qaoa_set_cost_maxkcut(qaoa_engine_t* h, int n_nodes, int n_edges, const int32_t* u,
+                          const int32_t* v, const double* w, int bits_per_node, const uint8_t* lut,
+                          int fixed_node, int fixed_colour);
+/* cost(x) = -(x^T Q x + c^T x + b)  (qaoa/problems/qubo_problem.py:101-108); Q row-major n*n. */
+int qaoa_set_cost_qubo(qaoa_engine_t* h, int n, const double* Q, const double* c, double b);
+/* Escape hatch for an arbitrary Problem.cost: host array of 2^n doubles. */
+int qaoa_set_cost_diagonal(qaoa_engine_t* h, const double* diag);
+/* Reads cost(x) for x in [offset, offset+count) back to the host. */
+int qaoa_read_cost_diagonal(qaoa_engine_t* h, size_t offset, size_t count, double* out);
+/* min / max of cost over all x (device reduction; Problem.computeMinMaxCosts, base_problem.py:121-134). */
+int qaoa_cost_minmax(qaoa_engine_t* h, double* out_min, double* out_max);
+
+/* pairs: XY topology as (q0,q1) pairs in application order; trotter_steps: qaoa/qaoa.py:494-503.
+ * For GROVER, sub_kind/sub_k/sub_vec describe |s> = U_S|0> like qaoa_set_initial. */
+int qaoa_set_mixer(qaoa_engine_t* h, int kind, const int32_t* pairs, int n_pairs, int trotter_steps,
+                   int sub_kind, int sub_k, const double* sub_vec);
+/* vec: 2^n complex128 amplitudes (re,im interleaved), little-endian index; only for STATEVECTOR. */
+int qaoa_set_initial(qaoa_engine_t* h, int kind, int k, const double* vec);
+
+/* One energy evaluation (replaces QAOA.loss / _eval_cost, qaoa/qaoa.py:885-935, 1029-1066).
+ * angles: the reference's flat layout [(gamma_d, beta_d[0..n_beta-1]) for d in 0..p-1]
+ * (qaoa/qaoa.py:937-990; n_init = 0 for every supported initial state).
+ * out[5] = { E[cost], E[cost^2], min cost over support, max cost over support, norm }. */
+int qaoa_energy(qaoa_engine_t* h, int p, const double* angles, int n_angles, double* out);
+/* B evaluations in one call (replaces the batch branch of sample_cost_landscape,
+ * qaoa/qaoa.py:630-662).  angles: B * n_angles doubles; out: B * 5 doubles. */
+int qaoa_energy_batch(qaoa_engine_t* h, int p, const double* angles, int n_angles, int B, double* out);
+
+/* Same as qaoa_energy_batch but angles / out are DEVICE-resident host-visible?  No: they are
+ * pinned-host or pageable host pointers as well; this variant only skips the final device->host
+ * copy of results and leaves them in the engine (used by bench.py's HBM-resident timing). */
+int qaoa_energy_batch_resident(qaoa_engine_t* h, int p, const double* angles, int n_angles, int B);
+int qaoa_fetch_results(qaoa_engine_t* h, int B, double* out);
+
+/* Final state of the last qaoa_energy call made with option keep_state=1 (true amplitudes,
+ * complex128 interleaved).  Test / debugging aid; 2^n * 16 bytes on the host. */
+int qaoa_read_statevector(qaoa_engine_t* h, double* out);
+/* Draws `shots` basis indices from |psi|^2 of the kept state (replaces backend.run(shots=...) in
+ * QAOA.hist, qaoa/qaoa.py:1134-1172). */
+int qaoa_sample(qaoa_engine_t* h, int shots, uint64_t seed, uint64_t* out_idx);
+
+/* ---- sharded (multi-GPU) operation: one engine per rank, state split on the top log2(world)
+ * qubits; the host (torch.distributed / NCCL) performs the exchanges between segments. ---------- */
+int qaoa_shard_config(qaoa_engine_t* h, int rank, int world);
+void* qaoa_state_ptr(qaoa_engine_t* h);
+void* qaoa_state2_ptr(qaoa_engine_t* h);
+size_t qaoa_state_bytes(qaoa_engine_t* h);
+int qaoa_shard_begin(qaoa_engine_t* h, int p, const double* angles, int n_angles);
+/* Runs local segment `seg` (0..p); after segment s < p the caller must perform the global<->local
+ * qubit swap (all-to-all) from state_ptr into state2_ptr and call qaoa_shard_swap_done. */
+int qaoa_shard_segment(qaoa_engine_t* h, int seg);
+int qaoa_shard_swap_done(qaoa_engine_t* h);
+/* local partial sums {S0,S1,S2,kmin,kmax}; the caller all-reduces (sum,sum,sum,min,max) and calls
+ * qaoa_shard_finish to decode them into out[5]. */
+int qaoa_shard_partials(qaoa_engine_t* h, double* out5);
+int qaoa_shard_finish(qaoa_engine_t* h, const double* reduced5, double* out);
+/* CUDA IPC plumbing for the fused gather pass (peer reads over NVLink). */
+int qaoa_ipc_export(qaoa_engine_t* h, int which, unsigned char* handle64);
+int qaoa_ipc_import(qaoa_engine_t* h, int peer_rank, int which, const unsigned char* handle64);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,1005 @@
+// Host side of libqaoa_b200.so: pass planner, parameter lowering and the C ABI (include/qaoa_b200.h).
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/qaoa_b200.h"
+#include "common.cuh"
+#include "kernels_misc.cuh"
+#include "tile_kernel.cuh"
+
+namespace {
+
+std::string g_global_error;
+
+#define CUDA_OK(call)                                                                       \
+  do {                                                                                      \
+    cudaError_t _e = (call);                                                                \
+    if (_e != cudaSuccess) {                                                                \
+      char _b[512];                                                                         \
+      snprintf(_b, sizeof(_b), "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e),      \
+               __FILE__, __LINE__);                                                         \
+      throw std::string(_b);                                                                \
+    }                                                                                       \
+  } while (0)
+
+struct Fail {
+  std::string msg;
+};
+[[noreturn]] void fail(const std::string& m) { throw std::string(m); }
+
+// ------------------------------------------------------------------------------------------
+// tile plan
+// ------------------------------------------------------------------------------------------
+struct RoundSpec {
+  int ebit[5];   // element bit handled by each register slot, -1 = slot idle
+  int layer;     // 0-based layer index
+};
+struct PhaseSpec {
+  int layer;     // 0-based layer whose gamma is applied (sigma of layer-1 is folded in)
+  int shape;
+  int frame;
+};
+struct PlanPass {
+  TilePass tp;
+  std::vector<RoundSpec> rounds;
+  std::vector<PhaseSpec> phases;
+  bool has_reduce = false;
+  int reduce_shape = 0, reduce_frame = 0;
+  size_t params_offset = 0;  // doubles, per point block
+};
+struct Shape {
+  int pos[TILE_BITS];
+  std::vector<int> freepos;
+};
+struct Plan {
+  int p = 0;
+  std::vector<Shape> shapes;
+  std::vector<PlanPass> passes;
+  size_t params_per_point = 0;  // doubles over all passes
+};
+
+struct Engine {
+  int n = 0, dtype = 0, device = 0;
+  int qshift = 0, E = 0;     // element bits
+  size_t N = 0;              // basis states
+  size_t amp_bytes = 8;
+  cudaStream_t stream = nullptr;
+
+  // state storage: `state_points` consecutive registers
+  void* state = nullptr;
+  size_t state_points = 0;
+
+  // cost
+  DiagInfo dinfo{DIAG_NONE, 0.0, 1.0};
+  void* diag = nullptr;
+  std::map<std::pair<int, int>, void*> streams;  // (shape, frame) -> permuted diagonal
+
+  // mixer / init
+  int mixer = MIXER_X;
+  std::vector<int> pairs;
+  int* d_pairs = nullptr;
+  int trotter = 1;
+  StateGen init{INIT_PLUS, 0, 1.0, nullptr};
+  StateGen sub{INIT_PLUS, 0, 1.0, nullptr};
+  void* init_vec = nullptr;
+  void* sub_vec = nullptr;
+
+  // plans
+  std::map<int, Plan> plans;
+
+  // options
+  int small_max_qubits = -1;  // -1: default by dtype
+  int keep_state = 0;
+  int batch_points = 0;       // 0: auto
+  size_t batch_bytes = (size_t)16 << 30;
+
+  // scratch
+  double* d_params = nullptr; size_t params_cap = 0;
+  double* h_params = nullptr; size_t hparams_cap = 0;
+  double* d_partials = nullptr; size_t partials_cap = 0;
+  double* d_out = nullptr; size_t out_cap = 0;
+  double* h_out = nullptr; size_t hout_cap = 0;
+  void* d_tables = nullptr; size_t tables_cap = 0;
+  double* d_gamsig = nullptr; size_t gamsig_cap = 0;
+  double* d_coefdot = nullptr;
+  double* d_angles = nullptr; size_t angles_cap = 0;
+
+  // bookkeeping of the last evaluation (for read_statevector)
+  std::vector<int> last_z;
+  int last_gsign = 1;
+  double last_scale = 1.0;
+  bool last_valid = false;
+  int last_path = 0;  // 0 small/elementwise (plain S frame), 1 tile
+
+  double launches = 0;
+  double bytes_alg = 0;
+  std::string err;
+
+  int small_max() const {
+    if (small_max_qubits >= 0) return small_max_qubits;
+    return dtype == QAOA_DTYPE_C64 ? 13 : 12;
+  }
+};
+
+template <typename T>
+void ensure(T*& p, size_t& cap, size_t need_bytes, bool pinned_host = false) {
+  if (cap >= need_bytes && p) return;
+  if (p) {
+    if (pinned_host) cudaFreeHost(p); else cudaFree(p);
+    p = nullptr;
+  }
+  size_t nb = std::max(need_bytes, (size_t)4096);
+  if (pinned_host) CUDA_OK(cudaMallocHost((void**)&p, nb));
+  else CUDA_OK(cudaMalloc((void**)&p, nb));
+  cap = nb;
+}
+
+void ensure_state(Engine* h, size_t points) {
+  if (h->state && h->state_points >= points) return;
+  if (h->state) { cudaFree(h->state); h->state = nullptr; }
+  CUDA_OK(cudaMalloc(&h->state, h->N * h->amp_bytes * points));
+  h->state_points = points;
+}
+
+void free_streams(Engine* h) {
+  for (auto& kv : h->streams) cudaFree(kv.second);
+  h->streams.clear();
+}
+
+void invalidate(Engine* h) {
+  h->plans.clear();
+  h->last_valid = false;
+}
+
+int grid_for(size_t N, int threads) {
+  size_t b = (N + threads - 1) / threads;
+  return (int)std::min<size_t>(b, 148 * 16);
+}
+
+// ------------------------------------------------------------------------------------------
+// planner: which 14 element bits each pass tiles over, and the op program of each pass
+// ------------------------------------------------------------------------------------------
+// register-resident tile-local bits for (frame, sub):  sub 0 = frame proper, sub 1 = after WT
+void reg_bits(int frame, int sub, int out[5]) {
+  if (sub == 1) { for (int i = 0; i < 5; i++) out[i] = 1 + i; return; }
+  out[0] = 0;
+  for (int i = 0; i < 4; i++) out[1 + i] = (frame == 0 ? 10 : 6) + i;
+}
+
+Plan build_plan(Engine* h, int p) {
+  Plan pl;
+  pl.p = p;
+  const int E = h->E, qs = h->qshift;
+  if (E < TILE_BITS) fail("tile path needs at least 14 element bits");
+  const int nH = E - 4;
+  const int m = std::max(1, (nH + 9) / 10);
+  for (int i = 0; i < m; i++) {
+    std::vector<int> bits = {0, 1, 2, 3};
+    int lo = 4 + 10 * i, hi = std::min(E, lo + 10);
+    std::vector<int> own;
+    for (int b = lo; b < hi; b++) own.push_back(b);
+    int padb = lo - 1;
+    while ((int)own.size() < 10) { own.push_back(padb); padb--; }
+    for (int b : own) bits.push_back(b);
+    std::sort(bits.begin(), bits.end());
+    Shape s;
+    for (int j = 0; j < TILE_BITS; j++) s.pos[j] = bits[j];
+    for (int b = 0; b < E; b++)
+      if (!std::binary_search(bits.begin(), bits.end(), b)) s.freepos.push_back(b);
+    pl.shapes.push_back(s);
+  }
+  const int nq = h->n;
+  std::vector<std::vector<char>> done(p, std::vector<char>(E, 0));
+  auto layer_complete = [&](int d) {
+    for (int b = qs; b < E; b++) if (!done[d][b]) return false;
+    return true;
+  };
+  (void)nq;
+  int cur = 0;
+  bool phase_pending = true;
+  bool first = true;
+  bool finished = false;
+  const bool load_first = (h->init.kind == INIT_STATEVECTOR);
+  int guard = 0;
+  while (!finished) {
+    if (++guard > 100000) fail("planner did not terminate");
+    // choose the shape with most unmixed qubits in the current layer
+    int best = 0, bestc = -1;
+    for (int s = 0; s < m; s++) {
+      int c = 0;
+      for (int j = 0; j < TILE_BITS; j++) {
+        int b = pl.shapes[s].pos[j];
+        if (b >= qs && !done[cur][b]) c++;
+      }
+      if (c > bestc) { bestc = c; best = s; }
+    }
+    const Shape& sh = pl.shapes[best];
+    PlanPass pp;
+    memset(&pp.tp, 0, sizeof(TilePass));
+    TilePass& tp = pp.tp;
+    for (int j = 0; j < TILE_BITS; j++) tp.pos[j] = sh.pos[j];
+    tp.nfree = (int)sh.freepos.size();
+    for (int j = 0; j < tp.nfree; j++) tp.freepos[j] = sh.freepos[j];
+    tp.qshift = qs;
+    tp.init_kind = h->init.kind;
+    tp.dicke_k = h->init.k;
+    tp.init_amp = h->init.amp;
+    int frame = 0, sub = 0;
+    auto push = [&](int type, int fr, int arg) {
+      if (tp.nops >= TILE_MAX_OPS) fail("tile pass program overflow");
+      tp.ops[tp.nops].type = (int16_t)type;
+      tp.ops[tp.nops].frame = (int16_t)fr;
+      tp.ops[tp.nops].arg = arg;
+      tp.nops++;
+    };
+    auto to_main = [&]() { if (sub == 1) { push(TOP_BT, 0, 0); frame ^= 1; sub = 0; } };
+    if (first && !load_first) push(TOP_INIT, frame, 0); else push(TOP_LOAD, frame, 0);
+    first = false;
+    bool reduced = false;
+    while (true) {
+      // room check: a full layer needs <= 1 phase + 3 rounds + 3 transposes, plus the tail
+      const bool room = tp.nops + 12 <= TILE_MAX_OPS && (int)pp.phases.size() + 2 <= TILE_MAX_PHASES;
+      if (phase_pending) {
+        if (!room) break;
+        to_main();
+        PhaseSpec ps{cur, best, frame};
+        push(TOP_PHASE, frame, (int)pp.phases.size());
+        pp.phases.push_back(ps);
+        phase_pending = false;
+      }
+      // qubits of this tile still unmixed in layer `cur`
+      std::vector<char> need(TILE_BITS, 0);
+      int nneed = 0;
+      for (int j = 0; j < TILE_BITS; j++) {
+        int b = sh.pos[j];
+        if (b >= qs && !done[cur][b]) { need[j] = 1; nneed++; }
+      }
+      if (nneed == 0) break;
+      if (!room) break;
+      while (nneed > 0) {
+        int rb[5];
+        reg_bits(frame, sub, rb);
+        RoundSpec rs;
+        rs.layer = cur;
+        bool any = false;
+        for (int s = 0; s < 5; s++) {
+          rs.ebit[s] = -1;
+          if (need[rb[s]]) {
+            rs.ebit[s] = sh.pos[rb[s]];
+            need[rb[s]] = 0;
+            nneed--;
+            done[cur][sh.pos[rb[s]]] = 1;
+            any = true;
+          }
+        }
+        if (any) { push(TOP_ROUND, 0, (int)pp.rounds.size()); pp.rounds.push_back(rs); }
+        if (nneed > 0) {
+          if (sub == 0) { push(TOP_WT, 0, 0); sub = 1; }
+          else { push(TOP_BT, 0, 0); frame ^= 1; sub = 0; }
+        }
+      }
+      if (layer_complete(cur)) {
+        if (cur == p - 1) {
+          to_main();
+          pp.has_reduce = true;
+          pp.reduce_shape = best;
+          pp.reduce_frame = frame;
+          push(TOP_REDUCE, frame, (int)pp.phases.size());
+          reduced = true;
+          finished = true;
+          break;
+        }
+        cur++;
+        phase_pending = true;
+        continue;
+      }
+      break;
+    }
+    to_main();
+    if (!reduced || h->keep_state) push(TOP_STORE, frame, 0);
+    tp.nrounds = (int)pp.rounds.size();
+    tp.nphases = (int)pp.phases.size();
+    tp.params_stride = tp.nrounds * TILE_ROUND_DOUBLES + 2 * tp.nphases + 1;
+    for (int j = 0; j < tp.nphases; j++) tp.table_id[j] = pp.phases[j].layer;
+    pp.params_offset = pl.params_per_point;
+    pl.params_per_point += tp.params_stride;
+    pl.passes.push_back(pp);
+  }
+  return pl;
+}
+
+void* get_stream(Engine* h, const Plan& pl, int shape, int frame) {
+  auto key = std::make_pair(shape, frame);
+  auto it = h->streams.find(key);
+  if (it != h->streams.end()) return it->second;
+  const int vb = diag_value_bytes(h->dinfo.kind);
+  void* s = nullptr;
+  CUDA_OK(cudaMalloc(&s, h->N * vb));
+  TilePass tp;
+  memset(&tp, 0, sizeof(tp));
+  const Shape& sh = pl.shapes[shape];
+  for (int j = 0; j < TILE_BITS; j++) tp.pos[j] = sh.pos[j];
+  tp.nfree = (int)sh.freepos.size();
+  for (int j = 0; j < tp.nfree; j++) tp.freepos[j] = sh.freepos[j];
+  tp.qshift = h->qshift;
+  const unsigned ntiles = 1u << (h->E - TILE_BITS);
+  const int namp = h->dtype == QAOA_DTYPE_C64 ? 32 : 16;
+  if (vb == 1) make_stream_kernel<1><<<ntiles, TILE_THREADS, 0, h->stream>>>(tp, frame, namp, (const unsigned char*)h->diag, (unsigned char*)s);
+  else if (vb == 4) make_stream_kernel<4><<<ntiles, TILE_THREADS, 0, h->stream>>>(tp, frame, namp, (const unsigned char*)h->diag, (unsigned char*)s);
+  else make_stream_kernel<8><<<ntiles, TILE_THREADS, 0, h->stream>>>(tp, frame, namp, (const unsigned char*)h->diag, (unsigned char*)s);
+  CUDA_OK(cudaGetLastError());
+  h->launches += 1;
+  h->streams[key] = s;
+  return s;
+}
+
+Plan& get_plan(Engine* h, int p) {
+  auto it = h->plans.find(p);
+  if (it != h->plans.end()) return it->second;
+  Plan pl = build_plan(h, p);
+  // attach the diagonal streams
+  for (auto& pp : pl.passes) {
+    for (size_t j = 0; j < pp.phases.size(); j++)
+      pp.tp.streams[j] = get_stream(h, pl, pp.phases[j].shape, pp.phases[j].frame);
+    if (pp.has_reduce) pp.tp.streams[pp.phases.size()] = get_stream(h, pl, pp.reduce_shape, pp.reduce_frame);
+  }
+  h->plans[p] = pl;
+  return h->plans[p];
+}
+
+// beta of qubit q in layer d for one point (reference flat layout, qaoa/qaoa.py:937-990)
+inline double beta_of(const Engine* h, const double* ang, int d, int q) {
+  const int nb = h->mixer == MIXER_XMULTI ? h->n : 1;
+  const int per = 1 + nb;
+  return ang[d * per + 1 + (nb == 1 ? 0 : q)];
+}
+inline double gamma_of(const Engine* h, const double* ang, int d) {
+  const int nb = h->mixer == MIXER_XMULTI ? h->n : 1;
+  return ang[d * (1 + nb)];
+}
+
+// Lowers one point's angles into the per-pass parameter block; returns sigma bookkeeping.
+void fill_point_params(Engine* h, const Plan& pl, const double* ang, double* dst /*params_per_point*/,
+                       double* gamsig /*2*p or null*/, std::vector<int>* zout, int* gsign_out,
+                       double* final_scale_out) {
+  const int p = pl.p;
+  std::vector<int> z(h->n, 0);
+  int gsign = 1;
+  std::vector<double> sigma(p, 1.0);
+  // first sweep: coefficients and the scale of every layer (program order == per-qubit layer order)
+  for (const auto& pp : pl.passes) {
+    double* base = dst + pp.params_offset;
+    for (size_t i = 0; i < pp.rounds.size(); i++) {
+      const RoundSpec& rs = pp.rounds[i];
+      double* rp = base + i * TILE_ROUND_DOUBLES;
+      unsigned long long fl = 0;
+      for (int s = 0; s < 5; s++) {
+        rp[2 * s] = 0.0;
+        rp[2 * s + 1] = 0.0;
+        if (rs.ebit[s] < 0) continue;
+        const int q = rs.ebit[s] - h->qshift;
+        const double beta = beta_of(h, ang, rs.layer, q);
+        const double c = cos(beta), sn = sin(beta);
+        fl |= 1ull << s;
+        if (fabs(c) >= fabs(sn)) {
+          const double t = sn / c;
+          const double tau = z[q] ? -t : t;
+          rp[2 * s] = tau;
+          rp[2 * s + 1] = -tau;
+          sigma[rs.layer] *= c;
+        } else {
+          const double tp = -c / sn;
+          fl |= 1ull << (8 + s);
+          sigma[rs.layer] *= sn;
+          if (!z[q]) { rp[2 * s] = -tp; rp[2 * s + 1] = tp; z[q] = 1; }
+          else { rp[2 * s] = tp; rp[2 * s + 1] = -tp; z[q] = 0; gsign = -gsign; }
+        }
+      }
+      long long bits = (long long)fl;
+      double fd;
+      memcpy(&fd, &bits, 8);
+      rp[10] = fd;
+    }
+  }
+  for (const auto& pp : pl.passes) {
+    double* ph = dst + pp.params_offset + pp.rounds.size() * TILE_ROUND_DOUBLES;
+    for (size_t j = 0; j < pp.phases.size(); j++) {
+      const int d = pp.phases[j].layer;
+      ph[2 * j] = gamma_of(h, ang, d);
+      ph[2 * j + 1] = d == 0 ? 1.0 : sigma[d - 1];
+    }
+    ph[2 * pp.phases.size()] = sigma[p - 1] * sigma[p - 1];
+  }
+  if (gamsig)
+    for (int d = 0; d < p; d++) {
+      gamsig[2 * d] = gamma_of(h, ang, d);
+      gamsig[2 * d + 1] = d == 0 ? 1.0 : sigma[d - 1];
+    }
+  if (zout) *zout = z;
+  if (gsign_out) *gsign_out = gsign;
+  if (final_scale_out) *final_scale_out = sigma[p - 1];
+}
+
+// tile path for a chunk of points [b0, b0+Bc)
+void run_tile_chunk(Engine* h, Plan& pl, const double* angles, int n_angles, int Bc, double* d_out_chunk,
+                    bool record_last) {
+  const int p = pl.p;
+  const unsigned ntiles = 1u << (h->E - TILE_BITS);
+  const size_t ppp = pl.params_per_point;
+  ensure(h->h_params, h->hparams_cap, (ppp * Bc + 2 * p * Bc) * sizeof(double), true);
+  ensure(h->d_params, h->params_cap, ppp * Bc * sizeof(double));
+  ensure(h->d_gamsig, h->gamsig_cap, (size_t)2 * p * Bc * sizeof(double));
+  ensure(h->d_partials, h->partials_cap, (size_t)ntiles * Bc * 5 * sizeof(double));
+  // host layout: pass-major so every pass sees a dense [Bc][stride] block
+  std::vector<double> tmp(ppp);
+  double* hgs = h->h_params + ppp * Bc;
+  for (int b = 0; b < Bc; b++) {
+    std::vector<int> z;
+    int gs = 1;
+    double fsc = 1.0;
+    fill_point_params(h, pl, angles + (size_t)b * n_angles, tmp.data(), hgs + (size_t)2 * p * b, &z, &gs, &fsc);
+    size_t pass_base = 0;
+    for (const auto& pp : pl.passes) {
+      memcpy(h->h_params + pass_base + (size_t)b * pp.tp.params_stride, tmp.data() + pp.params_offset,
+             pp.tp.params_stride * sizeof(double));
+      pass_base += (size_t)pp.tp.params_stride * Bc;
+    }
+    if (record_last && b == Bc - 1) {
+      h->last_z = z; h->last_gsign = gs; h->last_scale = fsc; h->last_valid = true; h->last_path = 1;
+    }
+  }
+  CUDA_OK(cudaMemcpyAsync(h->d_params, h->h_params, ppp * Bc * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  const bool c64 = h->dtype == QAOA_DTYPE_C64;
+  if (h->dinfo.kind == DIAG_U8) {
+    CUDA_OK(cudaMemcpyAsync(h->d_gamsig, hgs, (size_t)2 * p * Bc * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    const size_t tb = (size_t)p * Bc * 256 * (c64 ? 8 : 16);
+    ensure(h->d_tables, h->tables_cap, tb);
+    if (c64) build_tables_kernel<float, float2><<<p * Bc, 256, 0, h->stream>>>(h->d_gamsig, h->dinfo.c0, h->dinfo.delta, (float2*)h->d_tables);
+    else build_tables_kernel<double, double2><<<p * Bc, 256, 0, h->stream>>>(h->d_gamsig, h->dinfo.c0, h->dinfo.delta, (double2*)h->d_tables);
+    h->launches += 1;
+  }
+  if (h->init.kind == INIT_STATEVECTOR) {
+    for (int b = 0; b < Bc; b++)
+      CUDA_OK(cudaMemcpyAsync((char*)h->state + (size_t)b * h->N * h->amp_bytes, h->init_vec, h->N * h->amp_bytes,
+                              cudaMemcpyDeviceToDevice, h->stream));
+  }
+  const size_t point_stride_elems = h->N << h->qshift;
+  size_t pass_base = 0;
+  for (auto& pp : pl.passes) {
+    // tables_per_point = p : patched through a copy of the launch (kernel arg)
+    const int smem = TILE_EXCH_BYTES + 4096 + 16 * 5 * 8;
+    dim3 grid(ntiles, Bc);
+    if (c64) {
+      static bool set = false;
+      if (!set) { CUDA_OK(cudaFuncSetAttribute(tile_pass_kernel<float2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); set = true; }
+      tile_pass_kernel<float2><<<grid, TILE_THREADS, smem, h->stream>>>(pp.tp, (float2*)h->state, point_stride_elems,
+          h->d_params + pass_base, h->d_tables, p, h->dinfo, h->d_partials);
+    } else {
+      static bool set = false;
+      if (!set) { CUDA_OK(cudaFuncSetAttribute(tile_pass_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); set = true; }
+      tile_pass_kernel<double><<<grid, TILE_THREADS, smem, h->stream>>>(pp.tp, (double*)h->state, point_stride_elems,
+          h->d_params + pass_base, h->d_tables, p, h->dinfo, h->d_partials);
+    }
+    CUDA_OK(cudaGetLastError());
+    h->launches += 1;
+    bool reads = pp.tp.ops[0].type == TOP_LOAD, writes = pp.tp.ops[pp.tp.nops - 1].type == TOP_STORE;
+    h->bytes_alg += (double)Bc * (double)h->N * h->amp_bytes * ((reads ? 1 : 0) + (writes ? 1 : 0));
+    h->bytes_alg += (double)Bc * (double)h->N * diag_value_bytes(h->dinfo.kind) * (pp.phases.size() + (pp.has_reduce ? 1 : 0));
+    pass_base += (size_t)pp.tp.params_stride * Bc;
+  }
+  finalize_kernel<<<Bc, 256, 0, h->stream>>>(h->d_partials, (int)ntiles, h->dinfo, d_out_chunk);
+  CUDA_OK(cudaGetLastError());
+  h->launches += 1;
+}
+
+// small fused path for a chunk
+void run_small_chunk(Engine* h, int p, const double* angles, int n_angles, int Bc, double* d_out_chunk) {
+  ensure(h->d_angles, h->angles_cap, (size_t)Bc * n_angles * sizeof(double));
+  CUDA_OK(cudaMemcpyAsync(h->d_angles, angles, (size_t)Bc * n_angles * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  SmallDesc D;
+  D.n = h->n; D.p = p; D.mixer = h->mixer;
+  D.n_beta = h->mixer == MIXER_XMULTI ? h->n : 1;
+  D.n_pairs = (int)h->pairs.size() / 2;
+  D.trotter = h->trotter;
+  D.write_state = h->keep_state;
+  D.init = h->init; D.sub = h->sub;
+  if (h->keep_state) ensure_state(h, Bc);
+  const int smem = (int)(h->N * h->amp_bytes);
+  if (h->dtype == QAOA_DTYPE_C64) {
+    CUDA_OK(cudaFuncSetAttribute(small_fused_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(smem, 1024)));
+    small_fused_kernel<float><<<Bc, 512, smem, h->stream>>>(D, h->d_pairs, h->d_angles, n_angles, h->diag, h->dinfo,
+                                                            (float*)h->state, d_out_chunk);
+  } else {
+    CUDA_OK(cudaFuncSetAttribute(small_fused_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(smem, 1024)));
+    small_fused_kernel<double><<<Bc, 512, smem, h->stream>>>(D, h->d_pairs, h->d_angles, n_angles, h->diag, h->dinfo,
+                                                             (double*)h->state, d_out_chunk);
+  }
+  CUDA_OK(cudaGetLastError());
+  h->launches += 1;
+  h->last_valid = true; h->last_path = 0; h->last_scale = 1.0; h->last_gsign = 1;
+  h->last_z.assign(h->n, 0);
+}
+
+template <typename real>
+void run_elementwise_point(Engine* h, int p, const double* ang, double* d_out_point) {
+  ensure_state(h, 1);
+  const int threads = 256;
+  const int grid = grid_for(h->N, threads);
+  ensure(h->d_partials, h->partials_cap, (size_t)grid * 5 * sizeof(double) * 2);
+  if (!h->d_coefdot) CUDA_OK(cudaMalloc((void**)&h->d_coefdot, 2 * sizeof(double)));
+  double* part_dot = h->d_partials;
+  double* part_red = h->d_partials + (size_t)grid * 5;
+  real* st = (real*)h->state;
+  const double sweep = (double)h->N * h->amp_bytes;
+  const double dsz = (double)h->N * diag_value_bytes(h->dinfo.kind);
+  auto ew = [&](int flags, double gamma) {
+    elementwise_pass_kernel<real><<<grid, threads, 0, h->stream>>>(st, h->N, flags, h->init, h->sub, h->d_coefdot, gamma,
+                                                                  h->diag, h->dinfo, part_dot, part_red);
+    CUDA_OK(cudaGetLastError());
+    h->launches += 1;
+    h->bytes_alg += ((flags & EW_INIT) ? 0 : sweep) + ((flags & EW_STORE) ? sweep : 0) +
+                    ((flags & (EW_PHASE | EW_REDUCE)) ? dsz : 0);
+  };
+  if (h->mixer == MIXER_GROVER) {
+    for (int d = 0; d < p; d++) {
+      int fl = (d == 0 ? EW_INIT : EW_AXPY) | EW_PHASE | EW_DOT | EW_STORE;
+      ew(fl, ang[2 * d]);
+      grover_dot_finalize_kernel<<<1, 1024, 0, h->stream>>>(part_dot, grid, ang[2 * d + 1], h->d_coefdot);
+      CUDA_OK(cudaGetLastError());
+      h->launches += 1;
+    }
+    ew(EW_AXPY | EW_REDUCE | (h->keep_state ? EW_STORE : 0), 0.0);
+  } else {  // XY
+    const int np = (int)h->pairs.size() / 2;
+    for (int d = 0; d < p; d++) {
+      ew((d == 0 ? EW_INIT : 0) | EW_PHASE | EW_STORE, ang[2 * d]);
+      const double a = 0.25 * ang[2 * d + 1] / h->trotter;
+      const double c = cos(a), s = sin(a);
+      const int g4 = grid_for(h->N / 4, threads);
+      for (int rep = 0; rep < h->trotter; rep++)
+        for (int e = 0; e < np; e++) {
+          xy_gate_kernel<real><<<g4, threads, 0, h->stream>>>(st, h->N, h->pairs[2 * e], h->pairs[2 * e + 1], c, s);
+          CUDA_OK(cudaGetLastError());
+          h->launches += 1;
+          h->bytes_alg += sweep;  // touches half the register, read + write
+        }
+    }
+    ew(EW_REDUCE, 0.0);
+  }
+  finalize_raw_kernel<<<1, 1024, 0, h->stream>>>(part_red, grid, d_out_point);
+  CUDA_OK(cudaGetLastError());
+  h->launches += 1;
+  h->last_valid = true; h->last_path = 0; h->last_scale = 1.0; h->last_gsign = 1;
+  h->last_z.assign(h->n, 0);
+}
+
+void check_ready(Engine* h, int p, int n_angles) {
+  if (h->dinfo.kind == DIAG_NONE) fail("no cost function set");
+  if (p < 1) fail("depth p must be >= 1");
+  const int nb = h->mixer == MIXER_XMULTI ? h->n : 1;
+  if (n_angles != p * (1 + nb)) {
+    char b[160];
+    snprintf(b, sizeof(b), "expected %d angles for p=%d (n_beta=%d), got %d", p * (1 + nb), p, nb, n_angles);
+    fail(b);
+  }
+  if ((h->mixer == MIXER_XY) && h->pairs.empty()) fail("XY mixer without pairs");
+}
+
+void energy_batch_impl(Engine* h, int p, const double* angles, int n_angles, int B) {
+  check_ready(h, p, n_angles);
+  CUDA_OK(cudaSetDevice(h->device));
+  ensure(h->d_out, h->out_cap, (size_t)B * 5 * sizeof(double));
+  const bool small = h->n <= h->small_max();
+  if (small) {
+    int done = 0;
+    while (done < B) {
+      int Bc = std::min(B - done, h->keep_state ? 1 : 65535);
+      run_small_chunk(h, p, angles + (size_t)done * n_angles, n_angles, Bc, h->d_out + (size_t)done * 5);
+      if (Bc < B - done) CUDA_OK(cudaStreamSynchronize(h->stream));  // d_angles reuse
+      done += Bc;
+    }
+    return;
+  }
+  if (h->mixer == MIXER_X || h->mixer == MIXER_XMULTI) {
+    Plan& pl = get_plan(h, p);
+    size_t per_point = h->N * h->amp_bytes;
+    int Bmax = h->batch_points > 0 ? h->batch_points : (int)std::max<size_t>(1, std::min<size_t>(64, h->batch_bytes / per_point));
+    Bmax = std::min(Bmax, 65535);
+    ensure_state(h, std::min(B, Bmax));
+    int done = 0;
+    while (done < B) {
+      int Bc = std::min(B - done, Bmax);
+      run_tile_chunk(h, pl, angles + (size_t)done * n_angles, n_angles, Bc, h->d_out + (size_t)done * 5, done + Bc == B);
+      done += Bc;
+      if (done < B) CUDA_OK(cudaStreamSynchronize(h->stream));  // pinned param buffer reuse
+    }
+    return;
+  }
+  for (int b = 0; b < B; b++) {
+    if (h->dtype == QAOA_DTYPE_C64) run_elementwise_point<float>(h, p, angles + (size_t)b * n_angles, h->d_out + (size_t)b * 5);
+    else run_elementwise_point<double>(h, p, angles + (size_t)b * n_angles, h->d_out + (size_t)b * 5);
+  }
+}
+
+void set_diag_common(Engine* h, int kind, double c0, double delta) {
+  if (h->diag) { cudaFree(h->diag); h->diag = nullptr; }
+  free_streams(h);
+  invalidate(h);
+  h->dinfo.kind = kind;
+  h->dinfo.c0 = kind == DIAG_F64 ? 0.0 : c0;
+  h->dinfo.delta = kind == DIAG_F64 ? 1.0 : delta;
+  CUDA_OK(cudaMalloc(&h->diag, h->N * diag_value_bytes(kind)));
+}
+
+// choose the diagonal representation from value bounds
+void choose_kind(Engine* h, double lo, double hi, bool integer_valued, int* kind, double* c0, double* delta) {
+  if (integer_valued && hi - lo <= 255.0) { *kind = DIAG_U8; *c0 = lo; *delta = 1.0; return; }
+  if (h->dtype == QAOA_DTYPE_C128) { *kind = DIAG_F64; *c0 = 0; *delta = 1; return; }
+  *kind = DIAG_U32FX;
+  *c0 = lo;
+  if (integer_valued && hi - lo < 4294967295.0) *delta = 1.0;
+  else *delta = (hi > lo) ? (hi - lo) / 4294967295.0 : 1.0;
+}
+
+StateGen make_gen(Engine* h, int kind, int k, const double* vec, void** devvec) {
+  StateGen g;
+  g.kind = kind; g.k = k; g.vec = nullptr; g.amp = 1.0;
+  if (*devvec) { cudaFree(*devvec); *devvec = nullptr; }
+  if (kind == INIT_PLUS) g.amp = pow(2.0, -0.5 * h->n);
+  else if (kind == INIT_DICKE) {
+    if (k < 0 || k > h->n) fail("Dicke weight out of range");
+    double lc = lgamma(h->n + 1.0) - lgamma(k + 1.0) - lgamma(h->n - k + 1.0);
+    g.amp = exp(-0.5 * lc);
+  } else if (kind == INIT_STATEVECTOR) {
+    if (!vec) fail("statevector pointer is null");
+    CUDA_OK(cudaMalloc(devvec, h->N * h->amp_bytes));
+    if (h->dtype == QAOA_DTYPE_C128) {
+      CUDA_OK(cudaMemcpy(*devvec, vec, h->N * 16, cudaMemcpyHostToDevice));
+      to_sframe_kernel<double><<<grid_for(h->N, 256), 256, 0, h->stream>>>((double*)*devvec, h->N);
+    } else {
+      std::vector<float> tmp(h->N * 2);
+      for (size_t i = 0; i < h->N * 2; i++) tmp[i] = (float)vec[i];
+      CUDA_OK(cudaMemcpy(*devvec, tmp.data(), h->N * 8, cudaMemcpyHostToDevice));
+      to_sframe_kernel<float><<<grid_for(h->N, 256), 256, 0, h->stream>>>((float*)*devvec, h->N);
+    }
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    g.vec = *devvec;
+  } else fail("unknown state kind");
+  return g;
+}
+
+}  // namespace
+
+struct qaoa_engine : Engine {};
+
+#define API_BEGIN(h)            \
+  if (!(h)) return 1;           \
+  try {                         \
+    cudaSetDevice((h)->device);
+#define API_END(h)                  \
+  }                                 \
+  catch (const std::string& e) {    \
+    (h)->err = e;                   \
+    return 2;                       \
+  }                                 \
+  catch (...) {                     \
+    (h)->err = "unknown error";     \
+    return 3;                       \
+  }                                 \
+  return 0;
+
+extern "C" {
+
+const char* qaoa_global_error(void) { return g_global_error.c_str(); }
+
+int qaoa_create(int n_qubits, int dtype, int device, qaoa_engine_t** out) {
+  if (!out) return 1;
+  *out = nullptr;
+  try {
+    if (n_qubits < 1 || n_qubits > QAOA_MAX_QUBITS - 1) fail("n_qubits out of range [1, 39]");
+    if (dtype != QAOA_DTYPE_C64 && dtype != QAOA_DTYPE_C128) fail("dtype must be 0 (complex64) or 1 (complex128)");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) fail(std::string("no CUDA device available: ") + cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) fail("device index out of range");
+    CUDA_OK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) fail("this engine requires an sm_100a (B200) device");
+    qaoa_engine* h = new qaoa_engine();
+    h->n = n_qubits; h->dtype = dtype; h->device = device;
+    h->qshift = dtype == QAOA_DTYPE_C128 ? 1 : 0;
+    h->E = n_qubits + h->qshift;
+    h->N = (size_t)1 << n_qubits;
+    h->amp_bytes = dtype == QAOA_DTYPE_C128 ? 16 : 8;
+    CUDA_OK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    h->init = make_gen(h, INIT_PLUS, 0, nullptr, &h->init_vec);
+    h->sub = h->init;
+    *out = h;
+  } catch (const std::string& e) {
+    g_global_error = e;
+    return 2;
+  }
+  return 0;
+}
+
+int qaoa_destroy(qaoa_engine_t* h) {
+  if (!h) return 1;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  free_streams(h);
+  void* bufs[] = {h->state, h->diag, h->d_pairs, h->init_vec, h->sub_vec, h->d_params, h->d_partials, h->d_out,
+                  h->d_tables, h->d_gamsig, h->d_coefdot, h->d_angles};
+  for (void* b : bufs) if (b) cudaFree(b);
+  if (h->h_params) cudaFreeHost(h->h_params);
+  if (h->h_out) cudaFreeHost(h->h_out);
+  cudaStreamDestroy(h->stream);
+  delete h;
+  return 0;
+}
+
+const char* qaoa_last_error(qaoa_engine_t* h) { return h ? h->err.c_str() : "null handle"; }
+
+int qaoa_set_option(qaoa_engine_t* h, const char* key, double value) {
+  API_BEGIN(h)
+  std::string k(key ? key : "");
+  if (k == "small_max_qubits") {
+    int lim = h->dtype == QAOA_DTYPE_C64 ? 14 : 13;
+    h->small_max_qubits = std::min((int)value, lim);
+  } else if (k == "keep_state") { h->keep_state = value != 0; invalidate(h); }
+  else if (k == "batch_points") h->batch_points = (int)value;
+  else if (k == "batch_bytes") h->batch_bytes = (size_t)value;
+  else fail("unknown option: " + k);
+  API_END(h)
+}
+
+double qaoa_get_counter(qaoa_engine_t* h, const char* key) {
+  if (!h || !key) return -1.0;
+  std::string k(key);
+  if (k == "launches") return h->launches;
+  if (k == "bytes_alg") return h->bytes_alg;
+  if (k == "diag_kind") return h->dinfo.kind;
+  if (k == "reset") { h->launches = 0; h->bytes_alg = 0; return 0; }
+  if (k == "n_passes") { double s = 0; for (auto& kv : h->plans) s = (double)kv.second.passes.size(); return s; }
+  return -1.0;
+}
+
+int qaoa_set_cost_maxkcut(qaoa_engine_t* h, int n_nodes, int n_edges, const int32_t* u, const int32_t* v,
+                          const double* w, int bits_per_node, const uint8_t* lut, int fixed_node, int fixed_colour) {
+  API_BEGIN(h)
+  if (bits_per_node < 1 || bits_per_node > 3) fail("bits_per_node must be 1..3");
+  const int n_free = n_nodes - (fixed_node ? 1 : 0);
+  if (n_free * bits_per_node != h->n) fail("n_nodes * bits_per_node does not match the engine's qubit count");
+  if (n_edges < 0 || (n_edges > 0 && (!u || !v || !w || !lut))) fail("null edge arrays");
+  double pos = 0, neg = 0;
+  bool integer = true;
+  for (int e = 0; e < n_edges; e++) {
+    if (u[e] < 0 || u[e] >= n_nodes || v[e] < 0 || v[e] >= n_nodes) fail("edge endpoint out of range");
+    if (w[e] >= 0) pos += w[e]; else neg += w[e];
+    if (w[e] != floor(w[e]) || fabs(w[e]) > 1e9) integer = false;
+  }
+  int kind; double c0, delta;
+  choose_kind(h, neg, pos, integer, &kind, &c0, &delta);
+  set_diag_common(h, kind, c0, delta);
+  MaxKCutDev D;
+  memset(&D, 0, sizeof(D));
+  D.n_edges = n_edges; D.bits = bits_per_node; D.n_free = n_free; D.fixed_colour = fixed_colour;
+  for (int i = 0; i < (1 << bits_per_node); i++) D.lut[i] = lut[i];
+  int *du, *dv, *dwi; double* dw;
+  std::vector<int> wi(std::max(n_edges, 1));
+  // the U8 path stores cost - c0 with c0 = sum of the negative weights
+  for (int e = 0; e < n_edges; e++) wi[e] = integer ? (int)w[e] : 0;
+  CUDA_OK(cudaMalloc((void**)&du, std::max(n_edges, 1) * 4));
+  CUDA_OK(cudaMalloc((void**)&dv, std::max(n_edges, 1) * 4));
+  CUDA_OK(cudaMalloc((void**)&dwi, std::max(n_edges, 1) * 4));
+  CUDA_OK(cudaMalloc((void**)&dw, std::max(n_edges, 1) * 8));
+  CUDA_OK(cudaMemcpy(du, u, n_edges * 4, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(dv, v, n_edges * 4, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(dwi, wi.data(), n_edges * 4, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(dw, w, n_edges * 8, cudaMemcpyHostToDevice));
+  D.eu = du; D.ev = dv; D.ewi = dwi; D.ew = dw;
+  DiagInfo gi = h->dinfo;
+  gen_maxkcut_kernel<<<grid_for(h->N, 256), 256, 0, h->stream>>>(D, h->N, gi, h->diag);
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  h->launches += 1;
+  cudaFree(du); cudaFree(dv); cudaFree(dwi); cudaFree(dw);
+  API_END(h)
+}
+
+int qaoa_set_cost_qubo(qaoa_engine_t* h, int n, const double* Q, const double* c, double b) {
+  API_BEGIN(h)
+  if (n != h->n) fail("QUBO size does not match the engine's qubit count");
+  if (!Q) fail("Q is null");
+  std::vector<double> d(n), M((size_t)n * n, 0.0);
+  double lo = b, hi = b;  // bounds of f = x^T Q x + c^T x + b
+  bool integer = (b == floor(b));
+  for (int i = 0; i < n; i++) {
+    d[i] = Q[(size_t)i * n + i] + (c ? c[i] : 0.0);
+    if (d[i] > 0) hi += d[i]; else lo += d[i];
+    if (d[i] != floor(d[i])) integer = false;
+    for (int j = 0; j < i; j++) {
+      double m = Q[(size_t)i * n + j] + Q[(size_t)j * n + i];
+      M[(size_t)i * n + j] = m;
+      if (m > 0) hi += m; else lo += m;
+      if (m != floor(m)) integer = false;
+    }
+  }
+  if (fabs(lo) > 1e9 || fabs(hi) > 1e9) integer = false;
+  int kind; double c0, delta;
+  choose_kind(h, -hi, -lo, integer, &kind, &c0, &delta);
+  set_diag_common(h, kind, c0, delta);
+  double *dd, *dM;
+  CUDA_OK(cudaMalloc((void**)&dd, n * 8));
+  CUDA_OK(cudaMalloc((void**)&dM, (size_t)n * n * 8));
+  CUDA_OK(cudaMemcpy(dd, d.data(), n * 8, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(dM, M.data(), (size_t)n * n * 8, cudaMemcpyHostToDevice));
+  const int smem = (n + n * n) * 8;
+  gen_qubo_kernel<<<grid_for(h->N, 256), 256, smem, h->stream>>>(n, dd, dM, b, h->N, h->dinfo, h->diag);
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  h->launches += 1;
+  cudaFree(dd); cudaFree(dM);
+  API_END(h)
+}
+
+int qaoa_set_cost_diagonal(qaoa_engine_t* h, const double* diag) {
+  API_BEGIN(h)
+  if (!diag) fail("diag is null");
+  double lo = 1e300, hi = -1e300;
+  bool integer = true;
+  for (size_t i = 0; i < h->N; i++) {
+    lo = std::min(lo, diag[i]); hi = std::max(hi, diag[i]);
+    if (diag[i] != floor(diag[i])) integer = false;
+  }
+  int kind; double c0, delta;
+  choose_kind(h, lo, hi, integer, &kind, &c0, &delta);
+  set_diag_common(h, kind, c0, delta);
+  const size_t chunk = (size_t)1 << 24;
+  double* tmp;
+  CUDA_OK(cudaMalloc((void**)&tmp, std::min(chunk, h->N) * 8));
+  for (size_t off = 0; off < h->N; off += chunk) {
+    size_t cnt = std::min(chunk, h->N - off);
+    CUDA_OK(cudaMemcpy(tmp, diag + off, cnt * 8, cudaMemcpyHostToDevice));
+    quantise_diag_kernel<<<grid_for(cnt, 256), 256, 0, h->stream>>>(tmp, cnt, off, h->dinfo, h->diag);
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    h->launches += 1;
+  }
+  cudaFree(tmp);
+  API_END(h)
+}
+
+int qaoa_read_cost_diagonal(qaoa_engine_t* h, size_t offset, size_t count, double* out) {
+  API_BEGIN(h)
+  if (h->dinfo.kind == DIAG_NONE) fail("no cost function set");
+  if (offset + count > h->N) fail("range outside the diagonal");
+  const size_t chunk = (size_t)1 << 24;
+  double* tmp;
+  CUDA_OK(cudaMalloc((void**)&tmp, std::min(chunk, std::max<size_t>(count, 1)) * 8));
+  for (size_t o = 0; o < count; o += chunk) {
+    size_t cnt = std::min(chunk, count - o);
+    read_diag_kernel<<<grid_for(cnt, 256), 256, 0, h->stream>>>(h->diag, h->dinfo, offset + o, cnt, tmp);
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaMemcpyAsync(out + o, tmp, cnt * 8, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    h->launches += 1;
+  }
+  cudaFree(tmp);
+  API_END(h)
+}
+
+int qaoa_cost_minmax(qaoa_engine_t* h, double* out_min, double* out_max) {
+  API_BEGIN(h)
+  if (h->dinfo.kind == DIAG_NONE) fail("no cost function set");
+  const int grid = grid_for(h->N, 256);
+  ensure(h->d_partials, h->partials_cap, (size_t)grid * 2 * sizeof(double));
+  diag_minmax_kernel<<<grid, 256, 0, h->stream>>>(h->diag, h->dinfo, h->N, h->d_partials);
+  CUDA_OK(cudaGetLastError());
+  std::vector<double> hp((size_t)grid * 2);
+  CUDA_OK(cudaMemcpyAsync(hp.data(), h->d_partials, hp.size() * 8, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  h->launches += 1;
+  double lo = 1e300, hi = -1e300;
+  for (int i = 0; i < grid; i++) { lo = std::min(lo, hp[2 * i]); hi = std::max(hi, hp[2 * i + 1]); }
+  if (out_min) *out_min = lo;
+  if (out_max) *out_max = hi;
+  API_END(h)
+}
+
+int qaoa_set_mixer(qaoa_engine_t* h, int kind, const int32_t* pairs, int n_pairs, int trotter_steps,
+                   int sub_kind, int sub_k, const double* sub_vec) {
+  API_BEGIN(h)
+  if (kind < MIXER_X || kind > MIXER_GROVER) fail("unknown mixer kind");
+  if (trotter_steps < 1) fail("trotter_steps must be >= 1");
+  invalidate(h);
+  h->mixer = kind;
+  h->trotter = trotter_steps;
+  h->pairs.clear();
+  if (h->d_pairs) { cudaFree(h->d_pairs); h->d_pairs = nullptr; }
+  if (kind == MIXER_XY) {
+    if (n_pairs < 1 || !pairs) fail("XY mixer needs at least one pair");
+    for (int i = 0; i < 2 * n_pairs; i++) {
+      if (pairs[i] < 0 || pairs[i] >= h->n) fail("XY pair index out of range");
+      h->pairs.push_back(pairs[i]);
+    }
+    for (int i = 0; i < n_pairs; i++) if (pairs[2 * i] == pairs[2 * i + 1]) fail("XY pair with identical qubits");
+    CUDA_OK(cudaMalloc((void**)&h->d_pairs, h->pairs.size() * 4));
+    CUDA_OK(cudaMemcpy(h->d_pairs, h->pairs.data(), h->pairs.size() * 4, cudaMemcpyHostToDevice));
+  }
+  if (kind == MIXER_GROVER) h->sub = make_gen(h, sub_kind, sub_k, sub_vec, &h->sub_vec);
+  API_END(h)
+}
+
+int qaoa_set_initial(qaoa_engine_t* h, int kind, int k, const double* vec) {
+  API_BEGIN(h)
+  invalidate(h);
+  h->init = make_gen(h, kind, k, vec, &h->init_vec);
+  API_END(h)
+}
+
+int qaoa_energy_batch_resident(qaoa_engine_t* h, int p, const double* angles, int n_angles, int B) {
+  API_BEGIN(h)
+  if (B < 1 || !angles) fail("empty batch");
+  energy_batch_impl(h, p, angles, n_angles, B);
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  API_END(h)
+}
+
+int qaoa_fetch_results(qaoa_engine_t* h, int B, double* out) {
+  API_BEGIN(h)
+  if (!h->d_out || (size_t)B * 5 * sizeof(double) > h->out_cap) fail("no results to fetch");
+  CUDA_OK(cudaMemcpyAsync(out, h->d_out, (size_t)B * 5 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  API_END(h)
+}
+
+int qaoa_energy_batch(qaoa_engine_t* h, int p, const double* angles, int n_angles, int B, double* out) {
+  API_BEGIN(h)
+  if (B < 1 || !angles || !out) fail("empty batch");
+  energy_batch_impl(h, p, angles, n_angles, B);
+  CUDA_OK(cudaMemcpyAsync(out, h->d_out, (size_t)B * 5 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  API_END(h)
+}
+
+int qaoa_energy(qaoa_engine_t* h, int p, const double* angles, int n_angles, double* out) {
+  return qaoa_energy_batch(h, p, angles, n_angles, 1, out);
+}
+
+int qaoa_read_statevector(qaoa_engine_t* h, double* out) {
+  API_BEGIN(h)
+  if (!h->keep_state || !h->last_valid || !h->state) fail("no kept state: set option keep_state=1 and evaluate first");
+  const size_t N = h->N;
+  std::vector<double> re(N), im(N);
+  if (h->dtype == QAOA_DTYPE_C128) {
+    std::vector<double> tmp(2 * N);
+    CUDA_OK(cudaMemcpy(tmp.data(), h->state, N * 16, cudaMemcpyDeviceToHost));
+    for (size_t x = 0; x < N; x++) { re[x] = tmp[2 * x]; im[x] = tmp[2 * x + 1]; }
+  } else {
+    std::vector<float> tmp(2 * N);
+    CUDA_OK(cudaMemcpy(tmp.data(), h->state, N * 8, cudaMemcpyDeviceToHost));
+    for (size_t x = 0; x < N; x++) { re[x] = tmp[2 * x]; im[x] = tmp[2 * x + 1]; }
+  }
+  unsigned long long zm = 0;
+  for (int q = 0; q < h->n; q++) if (h->last_z[q]) zm |= 1ull << q;
+  for (size_t x = 0; x < N; x++) {
+    double r = re[x] * h->last_scale * h->last_gsign, m = im[x] * h->last_scale * h->last_gsign;
+    if (__builtin_popcountll(x & zm) & 1) { r = -r; m = -m; }
+    int k = (4 - (__builtin_popcountll(x) & 3)) & 3;  // multiply by (-i)^popc = i^(-popc)
+    double rr = r, mm = m;
+    if (k == 1) { rr = -m; mm = r; } else if (k == 2) { rr = -r; mm = -m; } else if (k == 3) { rr = m; mm = -r; }
+    out[2 * x] = rr;
+    out[2 * x + 1] = mm;
+  }
+  API_END(h)
+}
+
+}  // extern "C"

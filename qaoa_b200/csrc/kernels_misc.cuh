@@ -1,0 +1,448 @@
+// Cost-diagonal generators, the single-CTA fused kernel for small registers, the element-wise
+// Grover / XY passes and the small helper kernels (phase tables, partial-sum finalisation).
+#pragma once
+#include "common.cuh"
+
+// ============================================================================================
+// cost-diagonal generators (natural index order)
+// ============================================================================================
+// Replaces GraphProblem.cost (reference qaoa/problems/graph_problem.py:152-176) evaluated for
+// every basis index.  lut[] maps the b-bit integer (bit j = qubit v*b+j) to a colour id; the host
+// builds it from the reference's string tables (maxkcut_binary_powertwo.py:111-142,
+// maxkcut_binary_fullH.py:119-192).  Nodes >= n_free carry the fixed colour (fix_one_node).
+struct MaxKCutDev {
+  int n_edges;
+  const int* eu;
+  const int* ev;
+  const double* ew;   // weights as given
+  const int* ewi;     // integer weights (valid when integer path is used)
+  int bits;
+  int n_free;
+  int fixed_colour;
+  unsigned char lut[8];
+};
+
+__device__ __forceinline__ int node_colour(const MaxKCutDev& D, unsigned long long x, int v) {
+  if (v >= D.n_free) return D.fixed_colour;
+  return D.lut[(x >> (v * D.bits)) & ((1u << D.bits) - 1u)];
+}
+
+__global__ void gen_maxkcut_kernel(MaxKCutDev D, size_t N, DiagInfo info, void* out) {
+  for (size_t x = blockIdx.x * (size_t)blockDim.x + threadIdx.x; x < N; x += (size_t)gridDim.x * blockDim.x) {
+    if (info.kind == DIAG_U8) {
+      int s = 0;
+      for (int e = 0; e < D.n_edges; e++) {
+        int cu = node_colour(D, x, __ldg(D.eu + e)), cv = node_colour(D, x, __ldg(D.ev + e));
+        s += (cu != cv) ? __ldg(D.ewi + e) : 0;
+      }
+      ((uint8_t*)out)[x] = (uint8_t)(s - (int)llrint(info.c0));
+    } else {
+      double s = 0.0;
+      for (int e = 0; e < D.n_edges; e++) {
+        int cu = node_colour(D, x, __ldg(D.eu + e)), cv = node_colour(D, x, __ldg(D.ev + e));
+        s += (cu != cv) ? __ldg(D.ew + e) : 0.0;   // same edge order as the reference's sum()
+      }
+      if (info.kind == DIAG_U32FX) ((uint32_t*)out)[x] = (uint32_t)llrint((s - info.c0) / info.delta);
+      else ((double*)out)[x] = s;
+    }
+  }
+}
+
+// Replaces QUBO.qubo_cost (qubo_problem.py:101-108): cost = -(x^T Q x + c^T x + b).
+// d[i] = Q_ii + c_i ; M[i*n+j] = Q_ij + Q_ji for j < i (host-prepared).
+__global__ void gen_qubo_kernel(int n, const double* __restrict__ d, const double* __restrict__ M,
+                                double b, size_t N, DiagInfo info, void* out) {
+  extern __shared__ double sm[];
+  double* sd = sm;
+  double* sM = sm + n;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) sd[i] = d[i];
+  for (int i = threadIdx.x; i < n * n; i += blockDim.x) sM[i] = M[i];
+  __syncthreads();
+  for (size_t x = blockIdx.x * (size_t)blockDim.x + threadIdx.x; x < N; x += (size_t)gridDim.x * blockDim.x) {
+    double f = b;
+    unsigned long long rem = x;
+    while (rem) {
+      int i = 63 - __clzll((long long)rem);
+      rem &= ~(1ull << i);
+      double row = sd[i];
+      unsigned long long r2 = rem;  // bits j < i that are set
+      while (r2) {
+        int j = 63 - __clzll((long long)r2);
+        r2 &= ~(1ull << j);
+        row += sM[i * n + j];
+      }
+      f += row;
+    }
+    double cost = -f;
+    if (info.kind == DIAG_U8) ((uint8_t*)out)[x] = (uint8_t)llrint((cost - info.c0) / info.delta);
+    else if (info.kind == DIAG_U32FX) ((uint32_t*)out)[x] = (uint32_t)llrint((cost - info.c0) / info.delta);
+    else ((double*)out)[x] = cost;
+  }
+}
+
+// host-provided diagonal (escape hatch): quantise a chunk of doubles
+__global__ void quantise_diag_kernel(const double* __restrict__ src, size_t count, size_t offset,
+                                     DiagInfo info, void* out) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) {
+    double c = src[i];
+    size_t x = offset + i;
+    if (info.kind == DIAG_U8) ((uint8_t*)out)[x] = (uint8_t)llrint((c - info.c0) / info.delta);
+    else if (info.kind == DIAG_U32FX) ((uint32_t*)out)[x] = (uint32_t)llrint((c - info.c0) / info.delta);
+    else ((double*)out)[x] = c;
+  }
+}
+
+__global__ void read_diag_kernel(const void* diag, DiagInfo info, size_t offset, size_t count, double* out) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = diag_decode(info, diag, offset + i);
+}
+
+// min / max of the diagonal (computeMinMaxCosts, base_problem.py:121-134, without the Python loop)
+__global__ void diag_minmax_kernel(const void* diag, DiagInfo info, size_t N, double* partials) {
+  __shared__ double red[32 * 5];
+  double v[5] = {0, 0, 0, 1e300, -1e300};
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < N; i += (size_t)gridDim.x * blockDim.x) {
+    double c = diag_decode(info, diag, i);
+    v[3] = fmin(v[3], c);
+    v[4] = fmax(v[4], c);
+  }
+  block_reduce5(v, red);
+  if (threadIdx.x == 0) { partials[blockIdx.x * 2] = v[3]; partials[blockIdx.x * 2 + 1] = v[4]; }
+}
+
+// ============================================================================================
+// phase tables and result finalisation
+// ============================================================================================
+// table[t][k] = sigma_t * exp(i gamma_t (c0 + delta k)),  k = 0..255
+template <typename real, typename cplx>
+__global__ void build_tables_kernel(const double* __restrict__ gam_sig, double c0, double delta, cplx* out) {
+  const int t = blockIdx.x, k = threadIdx.x;
+  const double gamma = gam_sig[2 * t], sigma = gam_sig[2 * t + 1];
+  double s, c;
+  sincos(gamma * (c0 + delta * (double)k), &s, &c);
+  cplx r;
+  r.x = (real)(sigma * c);
+  r.y = (real)(sigma * s);
+  out[(size_t)t * 256 + k] = r;
+}
+
+// out[point] = {E[cost], E[cost^2], min, max, norm}; partials hold {S0, S1, S2, kmin, kmax} with
+// cost = c0 + delta * k.  Fixed summation order => run-to-run reproducible.
+__global__ void finalize_kernel(const double* __restrict__ partials, int ntiles, DiagInfo info, double* out) {
+  __shared__ double red[32 * 5];
+  const double* p = partials + (size_t)blockIdx.x * ntiles * 5;
+  double v[5] = {0, 0, 0, 1e300, -1e300};
+  for (int i = threadIdx.x; i < ntiles; i += blockDim.x) {
+    v[0] += p[i * 5 + 0];
+    v[1] += p[i * 5 + 1];
+    v[2] += p[i * 5 + 2];
+    v[3] = fmin(v[3], p[i * 5 + 3]);
+    v[4] = fmax(v[4], p[i * 5 + 4]);
+  }
+  block_reduce5(v, red);
+  if (threadIdx.x == 0) {
+    const double c0 = info.kind == DIAG_F64 ? 0.0 : info.c0, dl = info.kind == DIAG_F64 ? 1.0 : info.delta;
+    const double m1 = v[1] / v[0], m2 = v[2] / v[0];
+    double* o = out + (size_t)blockIdx.x * 5;
+    o[0] = c0 + dl * m1;
+    o[1] = c0 * c0 + 2.0 * c0 * dl * m1 + dl * dl * m2;
+    double lo = c0 + dl * v[3], hi = c0 + dl * v[4];
+    o[2] = fmin(lo, hi);
+    o[3] = fmax(lo, hi);
+    o[4] = v[0];
+  }
+}
+
+// ============================================================================================
+// initial / Grover reference states in the S frame
+// ============================================================================================
+struct StateGen {
+  int kind;       // INIT_PLUS / INIT_DICKE / INIT_STATEVECTOR
+  int k;          // Dicke weight
+  double amp;     // 2^{-n/2} or C(n,k)^{-1/2}
+  const void* vec;  // S-frame vector for INIT_STATEVECTOR (same element type as the state)
+};
+
+template <typename real>
+__device__ __forceinline__ void gen_amp(const StateGen& g, size_t x, real& re, real& im) {
+  if (g.kind == INIT_STATEVECTOR) {
+    re = ((const real*)g.vec)[2 * x];
+    im = ((const real*)g.vec)[2 * x + 1];
+    return;
+  }
+  int pc = __popcll((unsigned long long)x);
+  re = (real)g.amp;
+  im = (real)0;
+  if (g.kind == INIT_DICKE && pc != g.k) re = (real)0;
+  mul_i_pow(re, im, pc);
+}
+
+// psi~(x) = i^popc(x) psi(x)   (in place, natural order, interleaved re/im)
+template <typename real>
+__global__ void to_sframe_kernel(real* st, size_t N) {
+  for (size_t x = blockIdx.x * (size_t)blockDim.x + threadIdx.x; x < N; x += (size_t)gridDim.x * blockDim.x) {
+    real re = st[2 * x], im = st[2 * x + 1];
+    mul_i_pow(re, im, __popcll((unsigned long long)x));
+    st[2 * x] = re;
+    st[2 * x + 1] = im;
+  }
+}
+
+// ============================================================================================
+// single-CTA fused kernel: whole circuit for n <= 14 (complex64) / 13 (complex128) in shared memory
+// ============================================================================================
+struct SmallDesc {
+  int n;
+  int p;
+  int mixer;       // MixerKind
+  int n_beta;      // parameters per layer for the mixer (1 or n)
+  int n_pairs;     // XY
+  int trotter;     // XY only (X and Grover are invariant under trotterisation)
+  int write_state; // store the final S-frame state to global memory
+  StateGen init;
+  StateGen sub;    // Grover |s>
+};
+
+template <typename real>
+__global__ void __launch_bounds__(512, 1)
+small_fused_kernel(SmallDesc D, const int* __restrict__ pairs, const double* __restrict__ angles,
+                   int angles_stride, const void* __restrict__ diag, DiagInfo info,
+                   real* __restrict__ state_out, double* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  real* ps = reinterpret_cast<real*>(smem_raw);  // interleaved re, im
+  __shared__ double red[16 * 5];
+  __shared__ double dotsh[2];
+  const int n = D.n;
+  const size_t N = (size_t)1 << n;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const double* ang = angles + (size_t)blockIdx.x * angles_stride;
+  const int per = 1 + D.n_beta;
+
+  for (size_t x = tid; x < N; x += nt) {
+    real re, im;
+    gen_amp<real>(D.init, x, re, im);
+    ps[2 * x] = re;
+    ps[2 * x + 1] = im;
+  }
+  __syncthreads();
+
+  for (int d = 0; d < D.p; d++) {
+    const double gamma = ang[d * per];
+    // phase separator  e^{+i gamma cost(x)}   (sign: qaoa/utils/validation.py:43)
+    for (size_t x = tid; x < N; x += nt) {
+      double s, c;
+      sincos(gamma * diag_decode(info, diag, x), &s, &c);
+      real re = ps[2 * x], im = ps[2 * x + 1];
+      ps[2 * x] = re * (real)c - im * (real)s;
+      ps[2 * x + 1] = re * (real)s + im * (real)c;
+    }
+    __syncthreads();
+    if (D.mixer == MIXER_X || D.mixer == MIXER_XMULTI) {
+      for (int q = 0; q < n; q++) {
+        const double beta = ang[d * per + 1 + (D.n_beta == 1 ? 0 : q)];
+        double sd, cd;
+        sincos(beta, &sd, &cd);
+        const real c = (real)cd, s = (real)sd;
+        const size_t bit = (size_t)1 << q;
+        for (size_t i = tid; i < N / 2; i += nt) {
+          size_t x0 = ((i >> q) << (q + 1)) | (i & (bit - 1));
+          size_t x1 = x0 | bit;
+          real ar = ps[2 * x0], ai = ps[2 * x0 + 1], br = ps[2 * x1], bi = ps[2 * x1 + 1];
+          ps[2 * x0] = c * ar + s * br;   // S frame: real rotation [[c, s], [-s, c]]
+          ps[2 * x0 + 1] = c * ai + s * bi;
+          ps[2 * x1] = c * br - s * ar;
+          ps[2 * x1 + 1] = c * bi - s * ai;
+        }
+        __syncthreads();
+      }
+    } else if (D.mixer == MIXER_XY) {
+      // XXPlusYYGate(0.5 beta): rotation by beta/4 on span{|01>,|10>} (xy_mixer.py:54-56), in order
+      const double beta = ang[d * per + 1] / D.trotter;
+      double sd, cd;
+      sincos(0.25 * beta, &sd, &cd);
+      const real c = (real)cd, s = (real)sd;
+      for (int rep = 0; rep < D.trotter; rep++) {
+        for (int e = 0; e < D.n_pairs; e++) {
+          const int q0 = pairs[2 * e], q1 = pairs[2 * e + 1];
+          const int lo = q0 < q1 ? q0 : q1, hi = q0 < q1 ? q1 : q0;
+          for (size_t i = tid; i < N / 4; i += nt) {
+            size_t t = ((i >> lo) << (lo + 1)) | (i & (((size_t)1 << lo) - 1));
+            size_t base = ((t >> hi) << (hi + 1)) | (t & (((size_t)1 << hi) - 1));
+            size_t xa = base | ((size_t)1 << q0), xb = base | ((size_t)1 << q1);
+            real ar = ps[2 * xa], ai = ps[2 * xa + 1], br = ps[2 * xb], bi = ps[2 * xb + 1];
+            // a' = c a - i s b ; b' = -i s a + c b
+            ps[2 * xa] = c * ar + s * bi;
+            ps[2 * xa + 1] = c * ai - s * br;
+            ps[2 * xb] = c * br + s * ai;
+            ps[2 * xb + 1] = c * bi - s * ar;
+          }
+          __syncthreads();
+        }
+      }
+    } else {  // MIXER_GROVER:  psi += (e^{-i beta} - 1) <s|psi> s   (grover_mixer.py:43-82)
+      const double beta = ang[d * per + 1];
+      double v[5] = {0, 0, 0, 1e300, -1e300};
+      for (size_t x = tid; x < N; x += nt) {
+        real sr, si;
+        gen_amp<real>(D.sub, x, sr, si);
+        double re = ps[2 * x], im = ps[2 * x + 1];
+        v[0] += (double)sr * re + (double)si * im;   // conj(s) * psi
+        v[1] += (double)sr * im - (double)si * re;
+      }
+      block_reduce5(v, red);
+      if (tid == 0) { dotsh[0] = v[0]; dotsh[1] = v[1]; }
+      __syncthreads();
+      double sb, cb;
+      sincos(beta, &sb, &cb);
+      const double kr = cb - 1.0, ki = -sb;
+      const double fr = kr * dotsh[0] - ki * dotsh[1], fi = kr * dotsh[1] + ki * dotsh[0];
+      for (size_t x = tid; x < N; x += nt) {
+        real sr, si;
+        gen_amp<real>(D.sub, x, sr, si);
+        ps[2 * x] += (real)(fr * sr - fi * si);
+        ps[2 * x + 1] += (real)(fr * si + fi * sr);
+      }
+      __syncthreads();
+    }
+  }
+
+  double v[5] = {0, 0, 0, 1e300, -1e300};
+  for (size_t x = tid; x < N; x += nt) {
+    double re = ps[2 * x], im = ps[2 * x + 1];
+    double pr = re * re + im * im;
+    double c = diag_decode(info, diag, x);
+    v[0] += pr;
+    v[1] += pr * c;
+    v[2] += pr * c * c;
+    if (pr > 0.0) { v[3] = fmin(v[3], c); v[4] = fmax(v[4], c); }
+    if (D.write_state) {
+      state_out[2 * x] = (real)re;
+      state_out[2 * x + 1] = (real)im;
+    }
+  }
+  block_reduce5(v, red);
+  if (tid == 0) {
+    double* o = out + (size_t)blockIdx.x * 5;
+    o[0] = v[1] / v[0];
+    o[1] = v[2] / v[0];
+    o[2] = v[3];
+    o[3] = v[4];
+    o[4] = v[0];
+  }
+}
+
+// ============================================================================================
+// element-wise passes for large registers: Grover mixer and XY mixer (natural order, S frame)
+// ============================================================================================
+enum EwFlags : int {
+  EW_INIT = 1, EW_AXPY = 2, EW_PHASE = 4, EW_DOT = 8, EW_REDUCE = 16, EW_STORE = 32
+};
+
+// One sweep:  v = init|load ; v += coefdot * s ; v *= e^{i gamma c} ; dot += conj(s) v ; stats ; store
+// partial layout per block: {dot_re, dot_im, -, -, -} (EW_DOT) or {S0,S1,S2,min,max} (EW_REDUCE)
+template <typename real>
+__global__ void __launch_bounds__(256)
+elementwise_pass_kernel(real* __restrict__ st, size_t N, int flags, StateGen init, StateGen sub,
+                        const double* __restrict__ coefdot, double gamma, const void* __restrict__ diag,
+                        DiagInfo info, double* __restrict__ part_dot, double* __restrict__ part_red) {
+  __shared__ double red[8 * 5];
+  double fr = 0.0, fi = 0.0;
+  if (flags & EW_AXPY) { fr = coefdot[0]; fi = coefdot[1]; }
+  double dv[5] = {0, 0, 0, 1e300, -1e300};
+  double rv[5] = {0, 0, 0, 1e300, -1e300};
+  for (size_t x = blockIdx.x * (size_t)blockDim.x + threadIdx.x; x < N; x += (size_t)gridDim.x * blockDim.x) {
+    real re, im;
+    if (flags & EW_INIT) gen_amp<real>(init, x, re, im);
+    else { re = st[2 * x]; im = st[2 * x + 1]; }
+    real sr = 0, si = 0;
+    if (flags & (EW_AXPY | EW_DOT)) gen_amp<real>(sub, x, sr, si);
+    if (flags & EW_AXPY) {
+      re += (real)(fr * sr - fi * si);
+      im += (real)(fr * si + fi * sr);
+    }
+    double c = 0.0;
+    if (flags & (EW_PHASE | EW_REDUCE)) c = diag_decode(info, diag, x);
+    if (flags & EW_PHASE) {
+      double s, co;
+      sincos(gamma * c, &s, &co);
+      real r2 = re * (real)co - im * (real)s;
+      im = re * (real)s + im * (real)co;
+      re = r2;
+    }
+    if (flags & EW_DOT) {
+      dv[0] += (double)sr * re + (double)si * im;
+      dv[1] += (double)sr * im - (double)si * re;
+    }
+    if (flags & EW_REDUCE) {
+      double pr = (double)re * re + (double)im * im;
+      rv[0] += pr;
+      rv[1] += pr * c;
+      rv[2] += pr * c * c;
+      if (pr > 0.0) { rv[3] = fmin(rv[3], c); rv[4] = fmax(rv[4], c); }
+    }
+    if (flags & EW_STORE) { st[2 * x] = re; st[2 * x + 1] = im; }
+  }
+  if (flags & EW_DOT) {
+    block_reduce5(dv, red);
+    if (threadIdx.x == 0) { part_dot[blockIdx.x * 2] = dv[0]; part_dot[blockIdx.x * 2 + 1] = dv[1]; }
+  }
+  if (flags & EW_REDUCE) {
+    block_reduce5(rv, red);
+    if (threadIdx.x == 0)
+      for (int i = 0; i < 5; i++) part_red[blockIdx.x * 5 + i] = rv[i];
+  }
+}
+
+// coefdot = (e^{-i beta} - 1) * sum(partials)     (single block, fixed order)
+__global__ void grover_dot_finalize_kernel(const double* __restrict__ part, int nparts, double beta, double* coefdot) {
+  __shared__ double red[32 * 5];
+  double v[5] = {0, 0, 0, 1e300, -1e300};
+  for (int i = threadIdx.x; i < nparts; i += blockDim.x) { v[0] += part[2 * i]; v[1] += part[2 * i + 1]; }
+  block_reduce5(v, red);
+  if (threadIdx.x == 0) {
+    double sb, cb;
+    sincos(beta, &sb, &cb);
+    const double kr = cb - 1.0, ki = -sb;
+    coefdot[0] = kr * v[0] - ki * v[1];
+    coefdot[1] = kr * v[1] + ki * v[0];
+  }
+}
+
+// raw-sum variant of finalize for the element-wise path (cost values are already decoded)
+__global__ void finalize_raw_kernel(const double* __restrict__ partials, int nparts, double* out) {
+  __shared__ double red[32 * 5];
+  double v[5] = {0, 0, 0, 1e300, -1e300};
+  for (int i = threadIdx.x; i < nparts; i += blockDim.x) {
+    v[0] += partials[i * 5 + 0];
+    v[1] += partials[i * 5 + 1];
+    v[2] += partials[i * 5 + 2];
+    v[3] = fmin(v[3], partials[i * 5 + 3]);
+    v[4] = fmax(v[4], partials[i * 5 + 4]);
+  }
+  block_reduce5(v, red);
+  if (threadIdx.x == 0) {
+    out[0] = v[1] / v[0];
+    out[1] = v[2] / v[0];
+    out[2] = v[3];
+    out[3] = v[4];
+    out[4] = v[0];
+  }
+}
+
+// one XY gate on qubits (q0, q1) over the whole register: rotation by `ang` on span{|01>,|10>}
+template <typename real>
+__global__ void __launch_bounds__(256)
+xy_gate_kernel(real* __restrict__ st, size_t N, int q0, int q1, double cd, double sd) {
+  const real c = (real)cd, s = (real)sd;
+  const int lo = q0 < q1 ? q0 : q1, hi = q0 < q1 ? q1 : q0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < N / 4; i += (size_t)gridDim.x * blockDim.x) {
+    size_t t = ((i >> lo) << (lo + 1)) | (i & (((size_t)1 << lo) - 1));
+    size_t base = ((t >> hi) << (hi + 1)) | (t & (((size_t)1 << hi) - 1));
+    size_t xa = base | ((size_t)1 << q0), xb = base | ((size_t)1 << q1);
+    real ar = st[2 * xa], ai = st[2 * xa + 1], br = st[2 * xb], bi = st[2 * xb + 1];
+    st[2 * xa] = c * ar + s * bi;
+    st[2 * xa + 1] = c * ai - s * br;
+    st[2 * xb] = c * br + s * ai;
+    st[2 * xb + 1] = c * bi - s * ar;
+  }
+}

@@ -1,0 +1,3 @@
+from .statistic import Statistic, ExactStatistic
+from .graphutils import GraphHandler
+from .optimizers import COBYLA, NELDER_MEAD, L_BFGS_B, SPSA

@@ -1,0 +1,216 @@
+"""GPU parity: CUDA engine (through the C ABI) vs the numpy oracle on identical inputs.
+
+Tolerances (BASELINE.json north_star): cost diagonals bit-exact for integer weights;
+energies 1e-9 relative in complex128, 1e-4 relative in complex64.
+"""
+import numpy as np
+import pytest
+
+from oracle import qaoa_oracle as orc
+import parity_helpers as H
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"complex64": 1e-4, "complex128": 1e-9}
+
+
+def _engine(n, dtype):
+    from qaoa_b200 import engine as eng
+    return eng, eng.Engine(n, dtype=dtype)
+
+
+def _check(out, spec, angles, dtype, what=""):
+    e, e2, mn, mx = orc.energy(spec, angles)
+    tol = TOL[dtype]
+    assert H.rel_err(out[0], e) < tol, (what, out, e)
+    assert H.rel_err(out[1], e2) < 2 * tol, (what, out, e2)
+    assert abs(out[2] - mn) <= 1e-6 * max(1, abs(mn)) and abs(out[3] - mx) <= 1e-6 * max(1, abs(mx)), (what, out, mn, mx)
+    assert abs(out[4] - 1.0) < (1e-4 if dtype == "complex64" else 1e-11), (what, out)
+
+
+@pytest.mark.parametrize("dtype", ["complex64", "complex128"])
+@pytest.mark.parametrize("n", [4, 8, 12])
+def test_small_x_mixer_maxcut(n, dtype):
+    eng, E = _engine(n, dtype)
+    edges, colors, table = H.regular_maxcut(n)
+    lut, _ = H.lut_from_table(table, 1)
+    E.set_cost_maxkcut(n, edges, 1, lut)
+    diag = H.maxcut_diag(n, edges, colors, table)
+    assert np.array_equal(E.read_cost_diagonal(), diag.astype(np.float64))  # bit-exact
+    spec = orc.Spec(n, diag)
+    rng = np.random.default_rng(1234)
+    for p in (1, 2, 3):
+        ang = rng.uniform(0, 2 * np.pi, size=2 * p)
+        _check(E.energy(ang), spec, ang, dtype, "p=%d" % p)
+
+
+def test_readme_known_answers():
+    """README graph (n=8, seed 42) energies."""
+    eng, E = _engine(8, "complex128")
+    edges, colors, table = H.regular_maxcut(8)
+    lut, _ = H.lut_from_table(table, 1)
+    E.set_cost_maxkcut(8, edges, 1, lut)
+    assert abs(-E.energy([0.3, 0.2])[0] - (-7.124615209734253)) < 1e-9
+    assert abs(-E.energy([0.4, 0.6, 0.7, 0.35, 0.9, 0.15])[0] - (-8.995719311366326)) < 1e-9
+
+
+@pytest.mark.parametrize("dtype", ["complex64", "complex128"])
+@pytest.mark.parametrize("n", [14, 15, 18, 20])
+def test_tile_x_mixer_maxcut(n, dtype):
+    eng, E = _engine(n, dtype)
+    edges, colors, table = H.regular_maxcut(n)
+    lut, _ = H.lut_from_table(table, 1)
+    E.set_cost_maxkcut(n, edges, 1, lut)
+    diag = H.maxcut_diag(n, edges, colors, table)
+    assert np.array_equal(E.read_cost_diagonal(), diag.astype(np.float64))
+    spec = orc.Spec(n, diag)
+    rng = np.random.default_rng(99 + n)
+    for p in (1, 2, 3, 5):
+        ang = rng.uniform(0, 2 * np.pi, size=2 * p)
+        _check(E.energy(ang), spec, ang, dtype, "n=%d p=%d" % (n, p))
+
+
+@pytest.mark.parametrize("dtype", ["complex64", "complex128"])
+def test_tile_vs_small_same_n(dtype):
+    """n where both code paths exist: force each and compare with the oracle."""
+    n = 14 if dtype == "complex64" else 13
+    edges, colors, table = H.regular_maxcut(n if n % 2 == 0 else n + 1)
+    edges = [(u, v, w) for (u, v, w) in edges if u < n and v < n]
+    diag = np.zeros(1 << n)
+    x = np.arange(1 << n)
+    for (u, v, w) in edges:
+        diag += (((x >> u) ^ (x >> v)) & 1) * w
+    spec = orc.Spec(n, diag)
+    ang = np.array([0.37, 1.21, 2.2, 0.45, 1.1, 2.9])
+    ref = orc.energy(spec, ang)
+    outs = []
+    for small_max in (n, n - 1):
+        eng, E = _engine(n, dtype)
+        E.set_option("small_max_qubits", small_max)
+        E.set_cost_diagonal(diag)
+        out = E.energy(ang)
+        outs.append(out)
+        assert H.rel_err(out[0], ref[0]) < TOL[dtype]
+    assert H.rel_err(outs[0][0], outs[1][0]) < TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", ["complex64", "complex128"])
+@pytest.mark.parametrize("n", [10, 16])
+def test_multiangle_x(n, dtype):
+    eng, E = _engine(n, dtype)
+    Q, c, b = H.random_qubo(n)
+    E.set_cost_qubo(Q, c, b)
+    diag = orc.qubo_diag(Q, c, b)
+    got = E.read_cost_diagonal()
+    scale = np.abs(diag).max()
+    assert np.abs(got - diag).max() <= (1e-12 if dtype == "complex128" else 2e-9) * scale
+    E.set_mixer(eng.MIXER_XMULTI)
+    spec = orc.Spec(n, diag, mixer=("xmulti",))
+    rng = np.random.default_rng(5)
+    for p in (1, 3):
+        ang = rng.uniform(0, 2 * np.pi, size=p * (1 + n))
+        ang[::(1 + n)] *= 0.05  # gamma range sensible for costs O(100)
+        _check(E.energy(ang), spec, ang, dtype, "xmulti p=%d" % p)
+
+
+@pytest.mark.parametrize("dtype", ["complex64", "complex128"])
+@pytest.mark.parametrize("n,k", [(8, 3), (16, 5)])
+def test_grover_dicke(n, k, dtype):
+    eng, E = _engine(n, dtype)
+    Q, c, b = H.random_qubo(n, seed=7)
+    E.set_cost_qubo(Q, c, b)
+    diag = orc.qubo_diag(Q, c, b)
+    E.set_initial(eng.INIT_DICKE, k)
+    E.set_mixer(eng.MIXER_GROVER, sub_kind=eng.INIT_DICKE, sub_k=k)
+    s = orc.dicke_state(n, k)
+    spec = orc.Spec(n, diag, mixer=("grover", s), init=s)
+    rng = np.random.default_rng(11)
+    for p in (1, 3):
+        ang = rng.uniform(0, 2 * np.pi, size=2 * p)
+        ang[::2] *= 0.05
+        _check(E.energy(ang), spec, ang, dtype, "grover p=%d" % p)
+
+
+@pytest.mark.parametrize("dtype", ["complex64", "complex128"])
+@pytest.mark.parametrize("n,k,case", [(8, 3, "ring"), (15, 4, "chain"), (16, 5, "ring")])
+def test_xy_dicke(n, k, case, dtype):
+    eng, E = _engine(n, dtype)
+    Q, c, b = H.random_qubo(n, seed=3)
+    E.set_cost_qubo(Q, c, b)
+    diag = orc.qubo_diag(Q, c, b)
+    pairs = orc.xy_pairs(n, case)
+    E.set_initial(eng.INIT_DICKE, k)
+    E.set_mixer(eng.MIXER_XY, pairs=pairs, trotter=2)
+    spec = orc.Spec(n, diag, mixer=("xy", pairs), init=orc.dicke_state(n, k), trotter=2)
+    rng = np.random.default_rng(21)
+    for p in (1, 2):
+        ang = rng.uniform(0, 2 * np.pi, size=2 * p)
+        ang[::2] *= 0.05
+        _check(E.energy(ang), spec, ang, dtype, "xy p=%d" % p)
+
+
+@pytest.mark.parametrize("dtype", ["complex64", "complex128"])
+@pytest.mark.parametrize("n", [9, 15])
+def test_statevector_init(n, dtype):
+    eng, E = _engine(n, dtype)
+    edges, colors, table = H.regular_maxcut(n + (n % 2))
+    edges = [(u, v, w) for (u, v, w) in edges if u < n and v < n]
+    x = np.arange(1 << n)
+    diag = np.zeros(1 << n)
+    for (u, v, w) in edges:
+        diag += (((x >> u) ^ (x >> v)) & 1) * w
+    E.set_cost_diagonal(diag)
+    rng = np.random.default_rng(8)
+    vec = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
+    vec /= np.linalg.norm(vec)
+    E.set_initial(eng.INIT_STATEVECTOR, vec=vec)
+    spec = orc.Spec(n, diag, init=vec)
+    ang = np.array([0.7, 0.3, 1.9, 2.4])
+    _check(E.energy(ang), spec, ang, dtype, "statevector")
+
+
+@pytest.mark.parametrize("dtype", ["complex64", "complex128"])
+def test_kept_state_matches_oracle(dtype):
+    n = 15
+    eng, E = _engine(n, dtype)
+    edges, colors, table = H.regular_maxcut(n + 1)
+    edges = [(u, v, w) for (u, v, w) in edges if u < n and v < n]
+    x = np.arange(1 << n)
+    diag = np.zeros(1 << n)
+    for (u, v, w) in edges:
+        diag += (((x >> u) ^ (x >> v)) & 1) * w
+    E.set_cost_diagonal(diag)
+    E.set_option("keep_state", 1)
+    ang = np.array([0.7, 2.3, 1.9, 0.4, 0.2, 1.3])   # betas on both sides of |tan| = 1
+    E.energy(ang)
+    psi = E.read_statevector()
+    ref = orc.evolve(orc.Spec(n, diag), ang)
+    # global phase is not physical
+    ph = np.vdot(ref, psi)
+    ph /= abs(ph)
+    assert np.abs(psi - ph * ref).max() < (2e-6 if dtype == "complex64" else 1e-13)
+
+
+def test_batch_landscape_matches_oracle():
+    n = 14
+    eng, E = _engine(n, "complex64")
+    edges, colors, table = H.regular_maxcut(n)
+    lut, _ = H.lut_from_table(table, 1)
+    E.set_cost_maxkcut(n, edges, 1, lut)
+    diag = H.maxcut_diag(n, edges, colors, table)
+    spec = orc.Spec(n, diag)
+    gam = np.linspace(0, 2 * np.pi, 5, endpoint=False)
+    bet = np.linspace(0, 2 * np.pi, 4, endpoint=False)
+    ang = np.array([[g, b] for b in bet for g in gam])
+    out = E.energy_batch(ang)
+    for i, a in enumerate(ang):
+        e = orc.energy(spec, a)[0]
+        assert H.rel_err(out[i, 0], e) < 1e-4
+
+
+def test_errors_are_reported():
+    eng, E = _engine(6, "complex64")
+    with pytest.raises(eng.EngineError):
+        E.energy([0.1, 0.2])  # no cost set
+    with pytest.raises(eng.EngineError):
+        E.set_cost_qubo(np.eye(5))
