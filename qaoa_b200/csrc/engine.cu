@@ -45,13 +45,16 @@ struct PhaseSpec {
   int shape;
   int frame;
 };
+enum ProgId { PROG_GENERIC = 0, PROG_FIRST_INIT, PROG_FIRST_LOAD, PROG_INTERIOR, PROG_BOUNDARY, PROG_FINAL };
 struct PlanPass {
   TilePass tp;
   std::vector<RoundSpec> rounds;
   std::vector<PhaseSpec> phases;
   bool has_reduce = false;
   int reduce_shape = 0, reduce_frame = 0;
-  size_t params_offset = 0;  // doubles, per point block
+  size_t tau_offset = 0;  // reals, per point block
+  size_t phs_offset = 0;  // doubles, per point block
+  int prog = PROG_GENERIC;
 };
 struct Shape {
   int pos[TILE_BITS];
@@ -61,7 +64,8 @@ struct Plan {
   int p = 0;
   std::vector<Shape> shapes;
   std::vector<PlanPass> passes;
-  size_t params_per_point = 0;  // doubles over all passes
+  size_t tau_per_point = 0;  // reals over all passes
+  size_t phs_per_point = 0;  // doubles over all passes
 };
 
 struct Engine {
@@ -100,8 +104,9 @@ struct Engine {
   size_t batch_bytes = (size_t)16 << 30;
 
   // scratch
-  double* d_params = nullptr; size_t params_cap = 0;
+  double* d_params = nullptr; size_t params_cap = 0;   // [tau block (real)][phs block (double)]
   double* h_params = nullptr; size_t hparams_cap = 0;
+  int force_generic = 0;
   double* d_partials = nullptr; size_t partials_cap = 0;
   double* d_out = nullptr; size_t out_cap = 0;
   double* h_out = nullptr; size_t hout_cap = 0;
@@ -118,6 +123,7 @@ struct Engine {
   int last_path = 0;  // 0 small/elementwise (plain S frame), 1 tile
 
   double launches = 0;
+  double prog_launches = 0;
   double bytes_alg = 0;
   std::string err;
 
@@ -194,13 +200,11 @@ Plan build_plan(Engine* h, int p) {
       if (!std::binary_search(bits.begin(), bits.end(), b)) s.freepos.push_back(b);
     pl.shapes.push_back(s);
   }
-  const int nq = h->n;
   std::vector<std::vector<char>> done(p, std::vector<char>(E, 0));
   auto layer_complete = [&](int d) {
     for (int b = qs; b < E; b++) if (!done[d][b]) return false;
     return true;
   };
-  (void)nq;
   int cur = 0;
   bool phase_pending = true;
   bool first = true;
@@ -230,67 +234,66 @@ Plan build_plan(Engine* h, int p) {
     tp.init_kind = h->init.kind;
     tp.dicke_k = h->init.k;
     tp.init_amp = h->init.amp;
-    int frame = 0, sub = 0;
-    auto push = [&](int type, int fr, int arg) {
+    int frame = 0;
+    auto push = [&](int type, int fr, int arg, int mask) {
       if (tp.nops >= TILE_MAX_OPS) fail("tile pass program overflow");
       tp.ops[tp.nops].type = (int16_t)type;
       tp.ops[tp.nops].frame = (int16_t)fr;
-      tp.ops[tp.nops].arg = arg;
+      tp.ops[tp.nops].arg = (int16_t)arg;
+      tp.ops[tp.nops].mask = (int16_t)mask;
       tp.nops++;
     };
-    auto to_main = [&]() { if (sub == 1) { push(TOP_BT, 0, 0); frame ^= 1; sub = 0; } };
-    if (first && !load_first) push(TOP_INIT, frame, 0); else push(TOP_LOAD, frame, 0);
+    if (first && !load_first) push(TOP_INIT, frame, 0, 0); else push(TOP_LOAD, frame, 0, 0);
     first = false;
     bool reduced = false;
     while (true) {
-      // room check: a full layer needs <= 1 phase + 3 rounds + 3 transposes, plus the tail
-      const bool room = tp.nops + 12 <= TILE_MAX_OPS && (int)pp.phases.size() + 2 <= TILE_MAX_PHASES;
+      // room check: one more layer segment needs <= 1 phase + 5 cover steps, plus the tail
+      const bool room = tp.nops + 9 <= TILE_MAX_OPS && (int)pp.phases.size() + 2 <= TILE_MAX_PHASES;
+      if (!room) break;
+      // qubits of this tile still unmixed in layer `cur` (with a pending phase: all of them)
+      std::vector<char> need(TILE_BITS, 0);
+      int nneed = 0;
+      bool need_low = false;
+      for (int j = 0; j < TILE_BITS; j++) {
+        int b = sh.pos[j];
+        if (b >= qs && !done[cur][b]) { need[j] = 1; nneed++; if (j < 4) need_low = true; }
+      }
+      if (nneed == 0) break;
       if (phase_pending) {
-        if (!room) break;
-        to_main();
         PhaseSpec ps{cur, best, frame};
-        push(TOP_PHASE, frame, (int)pp.phases.size());
+        push(TOP_PHASE, frame, (int)pp.phases.size(), 0);
         pp.phases.push_back(ps);
         phase_pending = false;
       }
-      // qubits of this tile still unmixed in layer `cur`
-      std::vector<char> need(TILE_BITS, 0);
-      int nneed = 0;
-      for (int j = 0; j < TILE_BITS; j++) {
-        int b = sh.pos[j];
-        if (b >= qs && !done[cur][b]) { need[j] = 1; nneed++; }
-      }
-      if (nneed == 0) break;
-      if (!room) break;
-      while (nneed > 0) {
+      // canonical cover: R WT R BT R, full (all 14 bits) or high (upper 10 bits)
+      const int masks_full[3] = {M_ALL, M_ALL, M_HI4}, masks_high[3] = {M_HI4, M_TOP2, M_HI4};
+      const int* masks = need_low ? masks_full : masks_high;
+      for (int step = 0; step < 3; step++) {
         int rb[5];
-        reg_bits(frame, sub, rb);
+        reg_bits(frame, step == 1 ? 1 : 0, rb);
         RoundSpec rs;
         rs.layer = cur;
-        bool any = false;
         for (int s = 0; s < 5; s++) {
           rs.ebit[s] = -1;
-          if (need[rb[s]]) {
+          if (((masks[step] >> s) & 1) && need[rb[s]]) {
             rs.ebit[s] = sh.pos[rb[s]];
             need[rb[s]] = 0;
             nneed--;
             done[cur][sh.pos[rb[s]]] = 1;
-            any = true;
           }
         }
-        if (any) { push(TOP_ROUND, 0, (int)pp.rounds.size()); pp.rounds.push_back(rs); }
-        if (nneed > 0) {
-          if (sub == 0) { push(TOP_WT, 0, 0); sub = 1; }
-          else { push(TOP_BT, 0, 0); frame ^= 1; sub = 0; }
-        }
+        push(TOP_ROUND, 0, (int)pp.rounds.size(), masks[step]);
+        pp.rounds.push_back(rs);
+        if (step == 0) push(TOP_WT, 0, 0, 0);
+        if (step == 1) { push(TOP_BT, 0, 0, 0); frame ^= 1; }
       }
+      if (nneed != 0) fail("planner: cover left qubits unmixed");
       if (layer_complete(cur)) {
         if (cur == p - 1) {
-          to_main();
           pp.has_reduce = true;
           pp.reduce_shape = best;
           pp.reduce_frame = frame;
-          push(TOP_REDUCE, frame, (int)pp.phases.size());
+          push(TOP_REDUCE, frame, (int)pp.phases.size(), 0);
           reduced = true;
           finished = true;
           break;
@@ -301,14 +304,23 @@ Plan build_plan(Engine* h, int p) {
       }
       break;
     }
-    to_main();
-    if (!reduced || h->keep_state) push(TOP_STORE, frame, 0);
+    if (tp.nops == 1 && !reduced) fail("planner: empty pass");
+    if (!reduced || h->keep_state) push(TOP_STORE, frame, 0, 0);
     tp.nrounds = (int)pp.rounds.size();
     tp.nphases = (int)pp.phases.size();
-    tp.params_stride = tp.nrounds * TILE_ROUND_DOUBLES + 2 * tp.nphases + 1;
+    tp.tau_stride = tp.nrounds * TILE_ROUND_REALS;
+    tp.phs_stride = 2 * tp.nphases + 1;
     for (int j = 0; j < tp.nphases; j++) tp.table_id[j] = pp.phases[j].layer;
-    pp.params_offset = pl.params_per_point;
-    pl.params_per_point += tp.params_stride;
+    pp.tau_offset = pl.tau_per_point;
+    pp.phs_offset = pl.phs_per_point;
+    pl.tau_per_point += tp.tau_stride;
+    pl.phs_per_point += tp.phs_stride;
+    pp.prog = PROG_GENERIC;
+    if (prog_matches<ProgFirstInit>(tp)) pp.prog = PROG_FIRST_INIT;
+    else if (prog_matches<ProgFirstLoad>(tp)) pp.prog = PROG_FIRST_LOAD;
+    else if (prog_matches<ProgInterior>(tp)) pp.prog = PROG_INTERIOR;
+    else if (prog_matches<ProgBoundary>(tp)) pp.prog = PROG_BOUNDARY;
+    else if (prog_matches<ProgFinal>(tp)) pp.prog = PROG_FINAL;
     pl.passes.push_back(pp);
   }
   return pl;
@@ -364,66 +376,100 @@ inline double gamma_of(const Engine* h, const double* ang, int d) {
   return ang[d * (1 + nb)];
 }
 
-// Lowers one point's angles into the per-pass parameter block; returns sigma bookkeeping.
-void fill_point_params(Engine* h, const Plan& pl, const double* ang, double* dst /*params_per_point*/,
-                       double* gamsig /*2*p or null*/, std::vector<int>* zout, int* gsign_out,
-                       double* final_scale_out) {
+// largest |tan beta| handled in the normal (lifted) form: bounds the per-layer growth so that the
+// pre-shrunk amplitudes stay inside the normal exponent range of the state's real type
+inline double tmax_normal_form(const Engine* h) {
+  const double budget = h->dtype == QAOA_DTYPE_C64 ? 340.0 : 1800.0;  // 2 * log2 range allowed per layer
+  return sqrt(pow(2.0, std::min(budget / h->n, 1000.0)) - 1.0);
+}
+
+// Lowers one point's angles into round coefficients (tau: doubles here, narrowed by the caller) and
+// phase parameters.  Returns false in *all_normal if any slot needs the cot form.
+void fill_point_params(Engine* h, const Plan& pl, const double* ang, double* tau /*tau_per_point*/,
+                       double* phs /*phs_per_point*/, double* gamsig /*2*p or null*/,
+                       std::vector<char>* pass_all_normal, double* final_scale_out) {
   const int p = pl.p;
-  std::vector<int> z(h->n, 0);
-  int gsign = 1;
-  std::vector<double> sigma(p, 1.0);
-  // first sweep: coefficients and the scale of every layer (program order == per-qubit layer order)
-  for (const auto& pp : pl.passes) {
-    double* base = dst + pp.params_offset;
+  std::vector<double> logS(p, 0.0);   // log |prod scale| per layer
+  std::vector<int> sgnS(p, 1);
+  const double tmax = tmax_normal_form(h);
+  if (pass_all_normal) pass_all_normal->assign(pl.passes.size(), 1);
+  for (size_t ip = 0; ip < pl.passes.size(); ip++) {
+    const auto& pp = pl.passes[ip];
+    double* base = tau + pp.tau_offset;
     for (size_t i = 0; i < pp.rounds.size(); i++) {
       const RoundSpec& rs = pp.rounds[i];
-      double* rp = base + i * TILE_ROUND_DOUBLES;
-      unsigned long long fl = 0;
+      double* rp = base + i * TILE_ROUND_REALS;
+      for (int k = 0; k < TILE_ROUND_REALS; k++) rp[k] = 0.0;
+      int forms = 0;
       for (int s = 0; s < 5; s++) {
-        rp[2 * s] = 0.0;
-        rp[2 * s + 1] = 0.0;
         if (rs.ebit[s] < 0) continue;
         const int q = rs.ebit[s] - h->qshift;
         const double beta = beta_of(h, ang, rs.layer, q);
         const double c = cos(beta), sn = sin(beta);
-        fl |= 1ull << s;
-        if (fabs(c) >= fabs(sn)) {
+        if (fabs(sn) <= tmax * fabs(c)) {   // normal form: c * [[1, t], [-t, 1]]
           const double t = sn / c;
-          const double tau = z[q] ? -t : t;
-          rp[2 * s] = tau;
-          rp[2 * s + 1] = -tau;
-          sigma[rs.layer] *= c;
-        } else {
-          const double tp = -c / sn;
-          fl |= 1ull << (8 + s);
-          sigma[rs.layer] *= sn;
-          if (!z[q]) { rp[2 * s] = -tp; rp[2 * s + 1] = tp; z[q] = 1; }
-          else { rp[2 * s] = tp; rp[2 * s + 1] = -tp; z[q] = 0; gsign = -gsign; }
+          rp[s] = t;
+          rp[5 + s] = -t;
+          logS[rs.layer] += log(fabs(c));
+          if (c < 0) sgnS[rs.layer] = -sgnS[rs.layer];
+        } else {                            // cot form: s * [[u, 1], [-1, u]]
+          const double u = c / sn;
+          rp[s] = u;
+          rp[5 + s] = u;
+          forms |= 1 << s;
+          logS[rs.layer] += log(fabs(sn));
+          if (sn < 0) sgnS[rs.layer] = -sgnS[rs.layer];
+          if (pass_all_normal) (*pass_all_normal)[ip] = 0;
         }
       }
-      long long bits = (long long)fl;
-      double fd;
-      memcpy(&fd, &bits, 8);
-      rp[10] = fd;
+      rp[10] = (double)forms;
     }
   }
+  // split every layer's scale S_d into pre_d (applied with the layer's own phase) and post_d
+  std::vector<double> pre(p), post(p);
+  for (int d = 0; d < p; d++) {
+    pre[d] = exp(0.5 * logS[d]);
+    post[d] = sgnS[d] * exp(0.5 * logS[d]);
+  }
+  auto mult_of = [&](int d) { return (d == 0 ? 1.0 : post[d - 1]) * pre[d]; };
   for (const auto& pp : pl.passes) {
-    double* ph = dst + pp.params_offset + pp.rounds.size() * TILE_ROUND_DOUBLES;
+    double* ph = phs + pp.phs_offset;
     for (size_t j = 0; j < pp.phases.size(); j++) {
       const int d = pp.phases[j].layer;
       ph[2 * j] = gamma_of(h, ang, d);
-      ph[2 * j + 1] = d == 0 ? 1.0 : sigma[d - 1];
+      ph[2 * j + 1] = mult_of(d);
     }
-    ph[2 * pp.phases.size()] = sigma[p - 1] * sigma[p - 1];
+    ph[2 * pp.phases.size()] = post[p - 1];
   }
   if (gamsig)
     for (int d = 0; d < p; d++) {
       gamsig[2 * d] = gamma_of(h, ang, d);
-      gamsig[2 * d + 1] = d == 0 ? 1.0 : sigma[d - 1];
+      gamsig[2 * d + 1] = mult_of(d);
     }
-  if (zout) *zout = z;
-  if (gsign_out) *gsign_out = gsign;
-  if (final_scale_out) *final_scale_out = sigma[p - 1];
+  if (final_scale_out) *final_scale_out = post[p - 1];
+}
+
+template <typename Elem>
+void launch_pass(Engine* h, const PlanPass& pp, bool use_prog, dim3 grid, size_t point_stride_elems,
+                 const void* d_tau, const double* d_phs, int tables_per_point) {
+  typedef typename ElemTraits<Elem>::real real;
+  const int smem = TILE_SMEM_BYTES;
+  auto go = [&](auto kernel) {
+    CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    kernel<<<grid, TILE_THREADS, smem, h->stream>>>(pp.tp, (Elem*)h->state, point_stride_elems, (const real*)d_tau,
+                                                    d_phs, h->d_tables, tables_per_point, h->dinfo, h->d_partials);
+  };
+  const int prog = use_prog ? pp.prog : PROG_GENERIC;
+  const bool u8 = h->dinfo.kind == DIAG_U8;
+  switch (prog) {
+    case PROG_FIRST_INIT: if (u8) go(tile_prog_kernel<Elem, ProgFirstInit, DIAG_U8>); else go(tile_prog_kernel<Elem, ProgFirstInit, 0>); break;
+    case PROG_FIRST_LOAD: if (u8) go(tile_prog_kernel<Elem, ProgFirstLoad, DIAG_U8>); else go(tile_prog_kernel<Elem, ProgFirstLoad, 0>); break;
+    case PROG_INTERIOR: go(tile_prog_kernel<Elem, ProgInterior, DIAG_U8>); break;
+    case PROG_BOUNDARY: if (u8) go(tile_prog_kernel<Elem, ProgBoundary, DIAG_U8>); else go(tile_prog_kernel<Elem, ProgBoundary, 0>); break;
+    case PROG_FINAL: if (u8) go(tile_prog_kernel<Elem, ProgFinal, DIAG_U8>); else go(tile_prog_kernel<Elem, ProgFinal, 0>); break;
+    default: go(tile_pass_kernel<Elem>); break;
+  }
+  CUDA_OK(cudaGetLastError());
 }
 
 // tile path for a chunk of points [b0, b0+Bc)
@@ -431,37 +477,54 @@ void run_tile_chunk(Engine* h, Plan& pl, const double* angles, int n_angles, int
                     bool record_last) {
   const int p = pl.p;
   const unsigned ntiles = 1u << (h->E - TILE_BITS);
-  const size_t ppp = pl.params_per_point;
-  ensure(h->h_params, h->hparams_cap, (ppp * Bc + 2 * p * Bc) * sizeof(double), true);
-  ensure(h->d_params, h->params_cap, ppp * Bc * sizeof(double));
-  ensure(h->d_gamsig, h->gamsig_cap, (size_t)2 * p * Bc * sizeof(double));
+  const bool c64 = h->dtype == QAOA_DTYPE_C64;
+  const size_t rsz = c64 ? 4 : 8;
+  const size_t tpp = pl.tau_per_point, ppp = pl.phs_per_point;
+  // host block: [tau (real) pass-major][pad][phs (double) pass-major][gamsig]
+  const size_t tau_bytes = (tpp * Bc * rsz + 15) / 16 * 16;
+  const size_t phs_bytes = ppp * Bc * 8;
+  const size_t gs_bytes = (size_t)2 * p * Bc * 8;
+  ensure(h->h_params, h->hparams_cap, tau_bytes + phs_bytes + gs_bytes, true);
+  ensure(h->d_params, h->params_cap, tau_bytes + phs_bytes);
+  ensure(h->d_gamsig, h->gamsig_cap, gs_bytes);
   ensure(h->d_partials, h->partials_cap, (size_t)ntiles * Bc * 5 * sizeof(double));
-  // host layout: pass-major so every pass sees a dense [Bc][stride] block
-  std::vector<double> tmp(ppp);
-  double* hgs = h->h_params + ppp * Bc;
+  unsigned char* hb = (unsigned char*)h->h_params;
+  double* h_phs = (double*)(hb + tau_bytes);
+  double* hgs = (double*)(hb + tau_bytes + phs_bytes);
+  std::vector<double> tau_tmp(tpp), phs_tmp(ppp);
+  std::vector<char> all_normal(pl.passes.size(), 1), an;
   for (int b = 0; b < Bc; b++) {
-    std::vector<int> z;
-    int gs = 1;
     double fsc = 1.0;
-    fill_point_params(h, pl, angles + (size_t)b * n_angles, tmp.data(), hgs + (size_t)2 * p * b, &z, &gs, &fsc);
-    size_t pass_base = 0;
-    for (const auto& pp : pl.passes) {
-      memcpy(h->h_params + pass_base + (size_t)b * pp.tp.params_stride, tmp.data() + pp.params_offset,
-             pp.tp.params_stride * sizeof(double));
-      pass_base += (size_t)pp.tp.params_stride * Bc;
+    fill_point_params(h, pl, angles + (size_t)b * n_angles, tau_tmp.data(), phs_tmp.data(), hgs + (size_t)2 * p * b,
+                      &an, &fsc);
+    size_t tbase = 0, pbase = 0;
+    for (size_t ip = 0; ip < pl.passes.size(); ip++) {
+      const auto& pp = pl.passes[ip];
+      if (!an[ip]) all_normal[ip] = 0;
+      const size_t ts = pp.tp.tau_stride, ps = pp.tp.phs_stride;
+      if (c64) {
+        float* dst = (float*)hb + tbase + (size_t)b * ts;
+        for (size_t k = 0; k < ts; k++) dst[k] = (float)tau_tmp[pp.tau_offset + k];
+      } else {
+        memcpy((double*)hb + tbase + (size_t)b * ts, tau_tmp.data() + pp.tau_offset, ts * 8);
+      }
+      memcpy(h_phs + pbase + (size_t)b * ps, phs_tmp.data() + pp.phs_offset, ps * 8);
+      tbase += ts * Bc;
+      pbase += ps * Bc;
     }
     if (record_last && b == Bc - 1) {
-      h->last_z = z; h->last_gsign = gs; h->last_scale = fsc; h->last_valid = true; h->last_path = 1;
+      h->last_z.assign(h->n, 0); h->last_gsign = 1; h->last_scale = fsc; h->last_valid = true; h->last_path = 1;
     }
   }
-  CUDA_OK(cudaMemcpyAsync(h->d_params, h->h_params, ppp * Bc * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-  const bool c64 = h->dtype == QAOA_DTYPE_C64;
+  unsigned char* db = (unsigned char*)h->d_params;
+  CUDA_OK(cudaMemcpyAsync(db, hb, tau_bytes + phs_bytes, cudaMemcpyHostToDevice, h->stream));
   if (h->dinfo.kind == DIAG_U8) {
-    CUDA_OK(cudaMemcpyAsync(h->d_gamsig, hgs, (size_t)2 * p * Bc * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CUDA_OK(cudaMemcpyAsync(h->d_gamsig, hgs, gs_bytes, cudaMemcpyHostToDevice, h->stream));
     const size_t tb = (size_t)p * Bc * 256 * (c64 ? 8 : 16);
     ensure(h->d_tables, h->tables_cap, tb);
     if (c64) build_tables_kernel<float, float2><<<p * Bc, 256, 0, h->stream>>>(h->d_gamsig, h->dinfo.c0, h->dinfo.delta, (float2*)h->d_tables);
     else build_tables_kernel<double, double2><<<p * Bc, 256, 0, h->stream>>>(h->d_gamsig, h->dinfo.c0, h->dinfo.delta, (double2*)h->d_tables);
+    CUDA_OK(cudaGetLastError());
     h->launches += 1;
   }
   if (h->init.kind == INIT_STATEVECTOR) {
@@ -470,28 +533,22 @@ void run_tile_chunk(Engine* h, Plan& pl, const double* angles, int n_angles, int
                               cudaMemcpyDeviceToDevice, h->stream));
   }
   const size_t point_stride_elems = h->N << h->qshift;
-  size_t pass_base = 0;
-  for (auto& pp : pl.passes) {
-    // tables_per_point = p : patched through a copy of the launch (kernel arg)
-    const int smem = TILE_EXCH_BYTES + 4096 + 16 * 5 * 8;
+  size_t tbase = 0, pbase = 0;
+  for (size_t ip = 0; ip < pl.passes.size(); ip++) {
+    auto& pp = pl.passes[ip];
     dim3 grid(ntiles, Bc);
-    if (c64) {
-      static bool set = false;
-      if (!set) { CUDA_OK(cudaFuncSetAttribute(tile_pass_kernel<float2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); set = true; }
-      tile_pass_kernel<float2><<<grid, TILE_THREADS, smem, h->stream>>>(pp.tp, (float2*)h->state, point_stride_elems,
-          h->d_params + pass_base, h->d_tables, p, h->dinfo, h->d_partials);
-    } else {
-      static bool set = false;
-      if (!set) { CUDA_OK(cudaFuncSetAttribute(tile_pass_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); set = true; }
-      tile_pass_kernel<double><<<grid, TILE_THREADS, smem, h->stream>>>(pp.tp, (double*)h->state, point_stride_elems,
-          h->d_params + pass_base, h->d_tables, p, h->dinfo, h->d_partials);
-    }
-    CUDA_OK(cudaGetLastError());
+    const bool use_prog = all_normal[ip] && !h->force_generic;
+    const void* d_tau = db + tbase * rsz;
+    const double* d_phs = (const double*)(db + tau_bytes) + pbase;
+    if (c64) launch_pass<float2>(h, pp, use_prog, grid, point_stride_elems, d_tau, d_phs, p);
+    else launch_pass<double>(h, pp, use_prog, grid, point_stride_elems, d_tau, d_phs, p);
     h->launches += 1;
+    if (use_prog && pp.prog != PROG_GENERIC) h->prog_launches += 1;
     bool reads = pp.tp.ops[0].type == TOP_LOAD, writes = pp.tp.ops[pp.tp.nops - 1].type == TOP_STORE;
     h->bytes_alg += (double)Bc * (double)h->N * h->amp_bytes * ((reads ? 1 : 0) + (writes ? 1 : 0));
     h->bytes_alg += (double)Bc * (double)h->N * diag_value_bytes(h->dinfo.kind) * (pp.phases.size() + (pp.has_reduce ? 1 : 0));
-    pass_base += (size_t)pp.tp.params_stride * Bc;
+    tbase += (size_t)pp.tp.tau_stride * Bc;
+    pbase += (size_t)pp.tp.phs_stride * Bc;
   }
   finalize_kernel<<<Bc, 256, 0, h->stream>>>(h->d_partials, (int)ntiles, h->dinfo, d_out_chunk);
   CUDA_OK(cudaGetLastError());
@@ -756,6 +813,7 @@ int qaoa_set_option(qaoa_engine_t* h, const char* key, double value) {
   } else if (k == "keep_state") { h->keep_state = value != 0; invalidate(h); }
   else if (k == "batch_points") h->batch_points = (int)value;
   else if (k == "batch_bytes") h->batch_bytes = (size_t)value;
+  else if (k == "force_generic") h->force_generic = value != 0;
   else fail("unknown option: " + k);
   API_END(h)
 }
@@ -764,9 +822,10 @@ double qaoa_get_counter(qaoa_engine_t* h, const char* key) {
   if (!h || !key) return -1.0;
   std::string k(key);
   if (k == "launches") return h->launches;
+  if (k == "prog_launches") return h->prog_launches;
   if (k == "bytes_alg") return h->bytes_alg;
   if (k == "diag_kind") return h->dinfo.kind;
-  if (k == "reset") { h->launches = 0; h->bytes_alg = 0; return 0; }
+  if (k == "reset") { h->launches = 0; h->prog_launches = 0; h->bytes_alg = 0; return 0; }
   if (k == "n_passes") { double s = 0; for (auto& kv : h->plans) s = (double)kv.second.passes.size(); return s; }
   return -1.0;
 }

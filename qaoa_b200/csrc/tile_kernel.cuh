@@ -1,24 +1,31 @@
-// Register-tiled QAOA pass kernel for sm_100a.
+// Register-tiled QAOA pass kernels for sm_100a.
 //
 // One CTA (512 threads) owns a tile of 2^14 state ELEMENTS (8 bytes each: a complex64 amplitude,
 // or one double of a complex128 amplitude) held entirely in registers, 32 per thread.  A tile is
 // the set of elements whose index differs only in 14 chosen "tile bits" pos[0..13] (pos[0]=0,
 // pos[0..3] are the 4 lowest element bits so that every global access is a full 128-byte line).
-// The kernel interprets a short per-pass program (TilePass::ops) whose steps are
+// A pass is a short program of steps:
 //     LOAD / INIT   : fill the registers (coalesced 128-bit loads, or generate |+> / Dicke in place)
-//     PHASE         : psi(x) *= sigma * exp(i gamma cost(x))      (phase separator, fused)
+//     PHASE         : psi(x) *= m * exp(i gamma cost(x))      (phase separator, fused; m = scale owed)
 //     ROUND         : X-mixer butterflies on the 5 tile bits that are register-resident right now
 //     WT / BT       : warp-local / block-wide transposes through shared memory that rotate which
 //                     tile bits are register-resident (frames A -> A' -> B -> B' -> A ...)
 //     STORE / REDUCE: write back, or fuse the <cost>, <cost^2>, min, max reduction and skip the write
 //
+// Two kernels execute such programs:
+//   * tile_prog_kernel<Elem, Prog>: the program is a COMPILE-TIME constant, the whole pass is
+//     straight-line code (free register renaming, no per-step dispatch) -- used for the four
+//     canonical passes FIRST / INTERIOR / BOUNDARY / FINAL that make up every large evaluation;
+//   * tile_pass_kernel<Elem>: interprets TilePass::ops at run time -- fallback for irregular passes
+//     (several layers in one pass at small n, keep_state, mixed butterfly forms).
+//
 // Butterflies use the unnormalised "lifted" rotation: in the S frame the mixer on one qubit is
 // c*[[1,t],[-t,1]] (t = tan beta), i.e. ONE fused multiply-add per amplitude (FFMA2 on the packed
-// (re,im) pair for complex64, DFMA for complex128).  The per-layer scale prod(c) is folded into the
-// next layer's phase multiply (sigma) and finally into the reduction scale, so it costs nothing.
-// For |tan beta| > 1 the host switches to the swapped form (rotation by beta -+ pi/2 composed with
-// a swap) and tracks the resulting sign flips (pending Z) itself; the kernel only sees two signed
-// coefficients and a swap flag per register slot.
+// (re,im) pair for complex64, DFMA for complex128).  The per-layer scale prod(c) is split into a
+// pre-shrink folded into the SAME layer's phase multiply and a post factor folded into the NEXT
+// phase multiply / the reduction, so it costs nothing and keeps fp32 inside its exponent range.
+// Near beta = pi/2 (|t| huge) the host selects the "cot form" s*[[u,1],[-1,u]] (u = cot beta) per
+// register slot; passes containing such slots run on the interpreter kernel.
 #pragma once
 #include "common.cuh"
 
@@ -27,8 +34,9 @@ constexpr int TILE_ELEMS = 1 << TILE_BITS;
 constexpr int TILE_THREADS = 512;
 constexpr int TILE_MAX_OPS = 64;
 constexpr int TILE_MAX_PHASES = 16;
-constexpr int TILE_ROUND_DOUBLES = 11;  // 5 x (tau1, tau2) + flags
+constexpr int TILE_ROUND_REALS = 12;  // k1[5], k2[5], form mask, pad
 constexpr int TILE_EXCH_BYTES = TILE_ELEMS * 8;
+constexpr int TILE_SMEM_BYTES = TILE_EXCH_BYTES + 4096 + 16 * 5 * 8;
 
 enum TileOpType : int {
   TOP_LOAD = 1, TOP_STORE = 2, TOP_INIT = 3, TOP_PHASE = 4,
@@ -38,7 +46,8 @@ enum TileOpType : int {
 struct TileOp {
   int16_t type;
   int16_t frame;  // 0 = A, 1 = B   (LOAD/STORE/INIT/PHASE/REDUCE)
-  int32_t arg;    // ROUND: round index; PHASE/REDUCE: phase slot index
+  int16_t arg;    // ROUND: round index; PHASE/REDUCE: phase slot index
+  int16_t mask;   // ROUND: register slots compiled in (canonical programs)
 };
 
 struct TilePass {
@@ -53,7 +62,8 @@ struct TilePass {
   double init_amp;
   int nrounds;
   int nphases;
-  int params_stride;                    // doubles per point
+  int tau_stride;                       // reals per point  (nrounds * TILE_ROUND_REALS)
+  int phs_stride;                       // doubles per point (2 * nphases + 1)
   const void* streams[TILE_MAX_PHASES]; // permuted cost-diagonal stream per phase slot
   int table_id[TILE_MAX_PHASES];        // index of the 256-entry phase table (U8 mode)
 };
@@ -77,6 +87,8 @@ __device__ __forceinline__ float2 efma(float t, float2 b, float2 a) {
   return __ffma2_rn(make_float2(t, t), b, a);
 }
 __device__ __forceinline__ double efma(double t, double b, double a) { return fma(t, b, a); }
+__device__ __forceinline__ float2 eneg(float2 a) { return make_float2(-a.x, -a.y); }
+__device__ __forceinline__ double eneg(double a) { return -a; }
 
 __device__ __forceinline__ void load16(const float2* p, float2& a, float2& b) {
   float4 t = *reinterpret_cast<const float4*>(p);
@@ -132,72 +144,117 @@ __device__ __forceinline__ size_t stream_chunk(unsigned tile, int warp, int lane
   return (((size_t)tile * 16 + warp) * nchunks + j) * 32 + lane;
 }
 
+// ---- per-thread context -------------------------------------------------------------------
+template <typename Elem>
+struct Ctx {
+  typedef typename ElemTraits<Elem>::real real;
+  typedef typename ElemTraits<Elem>::cplx cplx;
+  const TilePass* P;
+  Elem* state;
+  const real* tau;     // this point's round coefficients
+  const double* phs;   // this point's (gamma, mult) pairs followed by the reduction scale
+  const void* tables;
+  int tables_per_point;
+  DiagInfo dinfo;
+  double* partials;
+  unsigned tile, point;
+  int warp, lane;
+  size_t base;
+  unsigned char* smem;
+  // hoisted shared-memory byte addresses (see warp_transpose / block_transpose)
+  unsigned wt_st, wt_ld, bt_st, bt_ld;
+};
+
+template <typename Elem>
+__device__ __forceinline__ void ctx_smem_setup(Ctx<Elem>& c) {
+  const unsigned lane = c.lane, warp = c.warp;
+  // warp transpose: write chunk (16 B) index lane*16 + (q ^ (lane&15)); read chunk r*16 + ((lane>>1)^(r&15))
+  c.wt_st = warp * 8192u + lane * 256u;          // ^ ((q ^ (lane&15)) << 4), folded below
+  c.wt_st ^= (lane & 15u) << 4;
+  c.wt_ld = warp * 8192u + (lane & 1u) * 8u;
+  c.wt_ld ^= (lane >> 1) << 4;
+  // block transpose: write element (warp,lane,r) at chunk (r + 32 warp + 512 (lane>>1)) ^ ((lane>>1)&7)
+  const unsigned hi = lane >> 1;
+  c.bt_st = (32u * warp + 512u * hi) * 16u + (lane & 1u) * 8u;
+  c.bt_st ^= (hi & 7u) << 4;
+  // read chunk (lane + 32 q + 512 warp) ^ (warp & 7)
+  c.bt_ld = ((lane ^ (warp & 7u)) + 512u * warp) * 16u;
+}
+
 // ---- transposes ---------------------------------------------------------------------------
 // warp-local: (lane l, reg r) -> (lane r, reg l); XOR-swizzled 16-byte chunks, conflict free.
 template <typename Elem>
-__device__ __forceinline__ void warp_transpose(Elem (&v)[32], Elem* exch, int warp, int lane) {
-  Elem* base = exch + warp * 1024;
+__device__ __forceinline__ void warp_transpose(const Ctx<Elem>& c, Elem (&v)[32]) {
   __syncwarp();
 #pragma unroll
-  for (int q = 0; q < 16; q++) {
-    int chunk = lane * 16 + (q ^ (lane & 15));
-    store16(base + chunk * 2, v[2 * q], v[2 * q + 1]);
-  }
+  for (int q = 0; q < 16; q++)
+    store16(reinterpret_cast<Elem*>(c.smem + (c.wt_st ^ (unsigned)(q << 4))), v[2 * q], v[2 * q + 1]);
   __syncwarp();
 #pragma unroll
-  for (int r = 0; r < 32; r++) {
-    int chunk = r * 16 + ((lane >> 1) ^ (r & 15));
-    v[r] = base[chunk * 2 + (lane & 1)];
-  }
+  for (int r = 0; r < 32; r++)
+    v[r] = *reinterpret_cast<const Elem*>(c.smem + (c.wt_ld ^ (unsigned)((r & 15) << 4)) + r * 256);
 }
 
 // block-wide: (warp w, lane l, reg r) -> (warp l>>1, lane r, reg (l&1)|(w<<1)).
 template <typename Elem>
-__device__ __forceinline__ void block_transpose(Elem (&v)[32], Elem* exch, int warp, int lane) {
-  __syncthreads();
-  {
-    const int hi = lane >> 1, half = lane & 1;
-    const int ubase = 32 * warp + 512 * hi;
-#pragma unroll
-    for (int r = 0; r < 32; r++) {
-      int u = (ubase + r) ^ (hi & 7);
-      exch[2 * u + half] = v[r];
-    }
-  }
+__device__ __forceinline__ void block_transpose(const Ctx<Elem>& c, Elem (&v)[32]) {
   __syncthreads();
 #pragma unroll
-  for (int q = 0; q < 16; q++) {
-    int u = (lane + 32 * q + 512 * warp) ^ (warp & 7);
-    load16(exch + 2 * u, v[2 * q], v[2 * q + 1]);
-  }
+  for (int r = 0; r < 32; r++)
+    *reinterpret_cast<Elem*>(c.smem + (c.bt_st ^ (unsigned)((r & 7) << 4)) + (r >> 3) * 128) = v[r];
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < 16; q++)
+    load16(reinterpret_cast<const Elem*>(c.smem + c.bt_ld + q * 512), v[2 * q], v[2 * q + 1]);
 }
 
 // ---- butterflies --------------------------------------------------------------------------
-template <typename Elem>
-__device__ __forceinline__ void do_round(Elem (&v)[32], const double* __restrict__ rp) {
+// canonical (straight-line) round: normal form only, slots selected at compile time
+template <typename Elem, int MASK>
+__device__ __forceinline__ void round_static(const Ctx<Elem>& c, Elem (&v)[32], int round) {
   typedef typename ElemTraits<Elem>::real real;
-  const unsigned long long fl = (unsigned long long)__double_as_longlong(__ldg(rp + 10));
+  const real* rp = c.tau + round * TILE_ROUND_REALS;
 #pragma unroll
   for (int s = 0; s < 5; s++) {
-    if ((fl >> s) & 1ull) {
-      const real t1 = (real)__ldg(rp + 2 * s), t2 = (real)__ldg(rp + 2 * s + 1);
-      if ((fl >> (8 + s)) & 1ull) {
+    if (MASK & (1 << s)) {
+      const real t = __ldg(rp + s);
 #pragma unroll
-        for (int i = 0; i < 32; i++) {
-          if (!(i & (1 << s))) {
-            Elem a = v[i], b = v[i | (1 << s)];
-            v[i] = efma(t1, a, b);
-            v[i | (1 << s)] = efma(t2, b, a);
-          }
+      for (int i = 0; i < 32; i++) {
+        if (!(i & (1 << s))) {
+          Elem a = v[i], b = v[i | (1 << s)];
+          v[i] = efma(t, b, a);
+          v[i | (1 << s)] = efma(-t, a, b);
         }
-      } else {
+      }
+    }
+  }
+}
+
+// interpreter round: per-slot form, idle slots skipped
+template <typename Elem>
+__device__ __forceinline__ void round_dynamic(const Ctx<Elem>& c, Elem (&v)[32], int round) {
+  typedef typename ElemTraits<Elem>::real real;
+  const real* rp = c.tau + round * TILE_ROUND_REALS;
+  const int forms = (int)__ldg(rp + 10);
 #pragma unroll
-        for (int i = 0; i < 32; i++) {
-          if (!(i & (1 << s))) {
-            Elem a = v[i], b = v[i | (1 << s)];
-            v[i] = efma(t1, b, a);
-            v[i | (1 << s)] = efma(t2, a, b);
-          }
+  for (int s = 0; s < 5; s++) {
+    const real k1 = __ldg(rp + s), k2 = __ldg(rp + 5 + s);
+    if ((forms >> s) & 1) {  // cot form: a' = k1 a + b ; b' = k2 b - a
+#pragma unroll
+      for (int i = 0; i < 32; i++) {
+        if (!(i & (1 << s))) {
+          Elem a = v[i], b = v[i | (1 << s)];
+          v[i] = efma(k1, a, b);
+          v[i | (1 << s)] = efma(k2, b, eneg(a));
+        }
+      }
+    } else if (k1 != (real)0 || k2 != (real)0) {  // normal form: a' = a + k1 b ; b' = b + k2 a
+#pragma unroll
+      for (int i = 0; i < 32; i++) {
+        if (!(i & (1 << s))) {
+          Elem a = v[i], b = v[i | (1 << s)];
+          v[i] = efma(k1, b, a);
+          v[i | (1 << s)] = efma(k2, a, b);
         }
       }
     }
@@ -227,8 +284,7 @@ __device__ __forceinline__ void phase_sincos(double turns, double& s, double& c)
   sincospi(2.0 * fr, &s, &c);
 }
 
-// Loads this thread's NAMP diagonal values (as raw integer k for U8/U32FX, as double for F64).
-// kd[a] = value such that cost = c0 + delta * kd (F64: c0 = 0, delta = 1).
+// Visits this thread's NAMP diagonal values (raw integer k for U8/U32FX, double for F64).
 template <int NAMP, typename F>
 __device__ __forceinline__ void for_each_diag(const void* stream, int kind, unsigned tile, int warp,
                                               int lane, F&& f) {
@@ -260,137 +316,272 @@ __device__ __forceinline__ void for_each_diag(const void* stream, int kind, unsi
   }
 }
 
-// ---- the pass kernel ----------------------------------------------------------------------
+// ---- the steps ----------------------------------------------------------------------------
 template <typename Elem>
-__global__ void __launch_bounds__(TILE_THREADS, 1)
-tile_pass_kernel(const __grid_constant__ TilePass P, Elem* __restrict__ state, size_t point_stride,
-                 const double* __restrict__ params, const void* __restrict__ tables,
-                 int tables_per_point, DiagInfo dinfo, double* __restrict__ partials) {
+__device__ __forceinline__ void op_load(const Ctx<Elem>& c, Elem (&v)[32], int frame) {
+  TileAddr ad = tile_addr(*c.P, c.base, frame, c.warp, c.lane);
+  const Elem* p = c.state + ad.e0;
+#pragma unroll
+  for (int q = 0; q < 16; q++) load16(p + reg_off(ad, q), v[2 * q], v[2 * q + 1]);
+}
+
+template <typename Elem>
+__device__ __forceinline__ void op_store(const Ctx<Elem>& c, Elem (&v)[32], int frame) {
+  TileAddr ad = tile_addr(*c.P, c.base, frame, c.warp, c.lane);
+  Elem* p = c.state + ad.e0;
+#pragma unroll
+  for (int q = 0; q < 16; q++) store16(p + reg_off(ad, q), v[2 * q], v[2 * q + 1]);
+}
+
+template <typename Elem>
+__device__ __forceinline__ void op_init(const Ctx<Elem>& c, Elem (&v)[32], int frame) {
+  typedef typename ElemTraits<Elem>::real real;
+  constexpr int NAMP = ElemTraits<Elem>::NAMP;
+  const TilePass& P = *c.P;
+  TileAddr ad = tile_addr(P, c.base, frame, c.warp, c.lane);
+  const real A = (real)P.init_amp;
+  const int pc0 = __popcll((unsigned long long)(ad.e0 >> P.qshift));
+#pragma unroll
+  for (int a = 0; a < NAMP; a++) {
+    // tile bits are distinct element bits: popcount(x) = popcount(thread part) + popcount(reg part)
+    const int regbits = ElemTraits<Elem>::IS_C64 ? a : (a << 1);
+    const int pc = pc0 + __popc(regbits >> P.qshift);
+    real re = A, im = (real)0;
+    if (P.init_kind == INIT_DICKE && pc != P.dicke_k) re = (real)0;
+    mul_i_pow(re, im, pc);
+    amp_set(v, a, re, im);
+  }
+}
+
+template <typename Elem, int DK>
+__device__ __forceinline__ void op_phase(const Ctx<Elem>& c, Elem (&v)[32], int slot) {
   typedef typename ElemTraits<Elem>::real real;
   typedef typename ElemTraits<Elem>::cplx cplx;
   constexpr int NAMP = ElemTraits<Elem>::NAMP;
+  const TilePass& P = *c.P;
+  const double gamma = __ldg(c.phs + 2 * slot), mult = __ldg(c.phs + 2 * slot + 1);
+  if (DK == DIAG_U8 || (DK == 0 && c.dinfo.kind == DIAG_U8)) {
+    cplx* tab = reinterpret_cast<cplx*>(c.smem + TILE_EXCH_BYTES);
+    __syncthreads();
+    if (threadIdx.x < 256) {
+      const cplx* t = reinterpret_cast<const cplx*>(c.tables) +
+                      ((size_t)c.point * c.tables_per_point + P.table_id[slot]) * 256;
+      tab[threadIdx.x] = t[threadIdx.x];
+    }
+    __syncthreads();
+    for_each_diag<NAMP>(P.streams[slot], DIAG_U8, c.tile, c.warp, c.lane, [&](int a, unsigned k, double) {
+      cplx ph = tab[k];
+      real re, im;
+      amp_get(v, a, re, im);
+      amp_set(v, a, re * ph.x - im * ph.y, re * ph.y + im * ph.x);
+    });
+  } else if (DK == 0) {
+    const double inv2pi = 0.15915494309189533576888;
+    const double g0 = gamma * c.dinfo.c0 * inv2pi, gd = gamma * c.dinfo.delta * inv2pi;
+    const real sg = (real)mult;
+    const int kind = c.dinfo.kind;
+    for_each_diag<NAMP>(P.streams[slot], kind, c.tile, c.warp, c.lane, [&](int a, unsigned k, double cd) {
+      double turns = kind == DIAG_U32FX ? fma((double)k, gd, g0) : fma(cd, gd, g0);
+      real s, co;
+      phase_sincos(turns, s, co);
+      s *= sg;
+      co *= sg;
+      real re, im;
+      amp_get(v, a, re, im);
+      amp_set(v, a, re * co - im * s, re * s + im * co);
+    });
+  }
+}
 
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  Elem* exch = reinterpret_cast<Elem*>(smem_raw);
-  cplx* tab = reinterpret_cast<cplx*>(smem_raw + TILE_EXCH_BYTES);             // 256 entries
-  double* red = reinterpret_cast<double*>(smem_raw + TILE_EXCH_BYTES + 4096);  // 16*5 doubles
+template <typename Elem, int DK>
+__device__ __forceinline__ void op_reduce(const Ctx<Elem>& c, Elem (&v)[32], int slot) {
+  typedef typename ElemTraits<Elem>::real real;
+  constexpr int NAMP = ElemTraits<Elem>::NAMP;
+  const TilePass& P = *c.P;
+  const real post = (real)__ldg(c.phs + 2 * P.nphases);  // scale still owed by the last layer
+  real s0 = 0, s1 = 0, s2 = 0;
+  double kmin = 1e300, kmax = -1e300;
+  const int kind = DK == DIAG_U8 ? (int)DIAG_U8 : c.dinfo.kind;
+  for_each_diag<NAMP>(P.streams[slot], kind, c.tile, c.warp, c.lane, [&](int a, unsigned k, double cd) {
+    real re, im;
+    amp_get(v, a, re, im);
+    re *= post;
+    im *= post;
+    real p = re * re + im * im;
+    real kv = kind == DIAG_F64 ? (real)cd : (real)k;
+    double kdv = kind == DIAG_F64 ? cd : (double)k;
+    s0 += p;
+    s1 = fma(p, kv, s1);
+    s2 = fma(p * kv, kv, s2);
+    if (p > (real)0) { kmin = fmin(kmin, kdv); kmax = fmax(kmax, kdv); }
+  });
+  double r5[5] = {(double)s0, (double)s1, (double)s2, kmin, kmax};
+  block_reduce5(r5, reinterpret_cast<double*>(c.smem + TILE_EXCH_BYTES + 4096));
+  if (threadIdx.x == 0) {
+    double* o = c.partials + ((size_t)c.point * gridDim.x + c.tile) * 5;
+#pragma unroll
+    for (int i = 0; i < 5; i++) o[i] = r5[i];
+  }
+}
 
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const unsigned tile = blockIdx.x;
-  const unsigned point = blockIdx.y;
-  state += (size_t)point * point_stride;
-  const double* pp = params + (size_t)point * P.params_stride;
-  const double* phase_pp = pp + P.nrounds * TILE_ROUND_DOUBLES;
-  const size_t base = tile_base(P, tile);
+template <typename Elem>
+__device__ __forceinline__ void ctx_init(Ctx<Elem>& c, const TilePass& P, Elem* state, size_t point_stride,
+                                         const typename ElemTraits<Elem>::real* tau, const double* phs,
+                                         const void* tables, int tables_per_point, const DiagInfo& dinfo,
+                                         double* partials, unsigned char* smem) {
+  c.P = &P;
+  c.lane = threadIdx.x & 31;
+  c.warp = threadIdx.x >> 5;
+  c.tile = blockIdx.x;
+  c.point = blockIdx.y;
+  c.state = state + (size_t)c.point * point_stride;
+  c.tau = tau + (size_t)c.point * P.tau_stride;
+  c.phs = phs + (size_t)c.point * P.phs_stride;
+  c.tables = tables;
+  c.tables_per_point = tables_per_point;
+  c.dinfo = dinfo;
+  c.partials = partials;
+  c.base = tile_base(P, c.tile);
+  c.smem = smem;
+  ctx_smem_setup(c);
+}
 
+// ---- interpreter kernel -------------------------------------------------------------------
+template <typename Elem>
+__global__ void __launch_bounds__(TILE_THREADS, 1)
+tile_pass_kernel(const __grid_constant__ TilePass P, Elem* __restrict__ state, size_t point_stride,
+                 const typename ElemTraits<Elem>::real* __restrict__ tau, const double* __restrict__ phs,
+                 const void* __restrict__ tables, int tables_per_point, DiagInfo dinfo,
+                 double* __restrict__ partials) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  Ctx<Elem> c;
+  ctx_init<Elem>(c, P, state, point_stride, tau, phs, tables, tables_per_point, dinfo, partials, smem_raw);
   Elem v[32];
-
+  TileOp op = P.ops[0];
   for (int io = 0; io < P.nops; io++) {
-    const TileOp op = P.ops[io];
-    switch (op.type) {
-      case TOP_LOAD: {
-        TileAddr ad = tile_addr(P, base, op.frame, warp, lane);
-#pragma unroll
-        for (int q = 0; q < 16; q++) load16(state + ad.e0 + reg_off(ad, q), v[2 * q], v[2 * q + 1]);
-      } break;
-      case TOP_STORE: {
-        TileAddr ad = tile_addr(P, base, op.frame, warp, lane);
-#pragma unroll
-        for (int q = 0; q < 16; q++) store16(state + ad.e0 + reg_off(ad, q), v[2 * q], v[2 * q + 1]);
-      } break;
-      case TOP_INIT: {
-        TileAddr ad = tile_addr(P, base, op.frame, warp, lane);
-        const real A = (real)P.init_amp;
-#pragma unroll
-        for (int a = 0; a < NAMP; a++) {
-          // amplitude a of this thread: complex64 -> register a; complex128 -> registers 2a, 2a+1
-          const int q = ElemTraits<Elem>::IS_C64 ? (a >> 1) : a;
-          size_t e = ad.e0 + reg_off(ad, q) + (ElemTraits<Elem>::IS_C64 ? (a & 1) : 0);
-          unsigned long long x = (unsigned long long)(e >> P.qshift);
-          int pc = __popcll(x);
-          real re = A, im = (real)0;
-          if (P.init_kind == INIT_DICKE && pc != P.dicke_k) re = (real)0;
-          mul_i_pow(re, im, pc);
-          amp_set(v, a, re, im);
-        }
-      } break;
-      case TOP_PHASE: {
-        const int slot = op.arg;
-        const double gamma = __ldg(phase_pp + 2 * slot), sigma = __ldg(phase_pp + 2 * slot + 1);
-        if (dinfo.kind == DIAG_U8) {
-          __syncthreads();
-          if (threadIdx.x < 256) {
-            const cplx* t = reinterpret_cast<const cplx*>(tables) +
-                            ((size_t)point * tables_per_point + P.table_id[slot]) * 256;
-            tab[threadIdx.x] = t[threadIdx.x];
-          }
-          __syncthreads();
-          for_each_diag<NAMP>(P.streams[slot], DIAG_U8, tile, warp, lane,
-                              [&](int a, unsigned k, double) {
-                                cplx ph = tab[k];
-                                real re, im;
-                                amp_get(v, a, re, im);
-                                amp_set(v, a, re * ph.x - im * ph.y, re * ph.y + im * ph.x);
-                              });
-        } else {
-          const double inv2pi = 0.15915494309189533576888;
-          const double g0 = gamma * dinfo.c0 * inv2pi, gd = gamma * dinfo.delta * inv2pi;
-          const real sg = (real)sigma;
-          for_each_diag<NAMP>(P.streams[slot], dinfo.kind, tile, warp, lane,
-                              [&](int a, unsigned k, double cd) {
-                                double turns = dinfo.kind == DIAG_U32FX ? fma((double)k, gd, g0)
-                                                                        : fma(cd, gd, g0);
-                                real s, c;
-                                phase_sincos(turns, s, c);
-                                s *= sg; c *= sg;
-                                real re, im;
-                                amp_get(v, a, re, im);
-                                amp_set(v, a, re * c - im * s, re * s + im * c);
-                              });
-        }
-      } break;
-      case TOP_ROUND:
-        do_round<Elem>(v, pp + op.arg * TILE_ROUND_DOUBLES);
-        break;
-      case TOP_WT:
-        warp_transpose<Elem>(v, exch, warp, lane);
-        break;
-      case TOP_BT:
-        block_transpose<Elem>(v, exch, warp, lane);
-        break;
-      case TOP_REDUCE: {
-        const int slot = op.arg;
-        const double scale = __ldg(phase_pp + 2 * P.nphases);  // red_scale follows the phase params
-        real s0 = 0, s1 = 0, s2 = 0;
-        double kmin = 1e300, kmax = -1e300;
-        for_each_diag<NAMP>(P.streams[slot], dinfo.kind, tile, warp, lane,
-                            [&](int a, unsigned k, double cd) {
-                              real re, im;
-                              amp_get(v, a, re, im);
-                              real p = re * re + im * im;
-                              real kv = dinfo.kind == DIAG_F64 ? (real)cd : (real)k;
-                              double kdv = dinfo.kind == DIAG_F64 ? cd : (double)k;
-                              s0 += p;
-                              s1 = fma(p, kv, s1);
-                              s2 = fma(p * kv, kv, s2);
-                              if (p > (real)0) { kmin = fmin(kmin, kdv); kmax = fmax(kmax, kdv); }
-                            });
-        double r5[5] = {(double)s0 * scale, (double)s1 * scale, (double)s2 * scale, kmin, kmax};
-        block_reduce5(r5, red);
-        if (threadIdx.x == 0) {
-          double* o = partials + ((size_t)point * gridDim.x + tile) * 5;
-#pragma unroll
-          for (int i = 0; i < 5; i++) o[i] = r5[i];
-        }
-      } break;
-      default:
-        break;
+    const TileOp cur = op;
+    if (io + 1 < P.nops) op = P.ops[io + 1];  // fetch the next step early (constant-bank latency)
+    switch (cur.type) {
+      case TOP_LOAD: op_load<Elem>(c, v, cur.frame); break;
+      case TOP_STORE: op_store<Elem>(c, v, cur.frame); break;
+      case TOP_INIT: op_init<Elem>(c, v, cur.frame); break;
+      case TOP_PHASE: op_phase<Elem, 0>(c, v, cur.arg); break;
+      case TOP_ROUND: round_dynamic<Elem>(c, v, cur.arg); break;
+      case TOP_WT: warp_transpose<Elem>(c, v); break;
+      case TOP_BT: block_transpose<Elem>(c, v); break;
+      case TOP_REDUCE: op_reduce<Elem, 0>(c, v, cur.arg); break;
+      default: break;
     }
   }
 }
 
+// ---- compile-time programs ----------------------------------------------------------------
+struct COp {
+  int type, frame, arg, mask;
+};
+
+constexpr int M_ALL = 0x1f, M_HI4 = 0x1e, M_TOP2 = 0x18;
+
+// full cover of all 14 tile bits starting in frame F (ends in frame F^1)
+//   R(all) WT R(all) BT R(hi4)
+// high cover of the 10 upper tile bits:  R(hi4) WT R(top2) BT R(hi4)
+struct ProgFirstInit {  // |+>/Dicke generated in registers, phase 1, full layer-1 cover of the tile
+  static constexpr int N = 8;
+  static constexpr COp op(int i) {
+    constexpr COp o[N] = {{TOP_INIT, 0, 0, 0}, {TOP_PHASE, 0, 0, 0}, {TOP_ROUND, 0, 0, M_ALL}, {TOP_WT, 0, 0, 0},
+                          {TOP_ROUND, 0, 1, M_ALL}, {TOP_BT, 0, 0, 0}, {TOP_ROUND, 0, 2, M_HI4}, {TOP_STORE, 1, 0, 0}};
+    return o[i];
+  }
+};
+struct ProgFirstLoad {
+  static constexpr int N = 8;
+  static constexpr COp op(int i) {
+    constexpr COp o[N] = {{TOP_LOAD, 0, 0, 0}, {TOP_PHASE, 0, 0, 0}, {TOP_ROUND, 0, 0, M_ALL}, {TOP_WT, 0, 0, 0},
+                          {TOP_ROUND, 0, 1, M_ALL}, {TOP_BT, 0, 0, 0}, {TOP_ROUND, 0, 2, M_HI4}, {TOP_STORE, 1, 0, 0}};
+    return o[i];
+  }
+};
+struct ProgInterior {
+  static constexpr int N = 7;
+  static constexpr COp op(int i) {
+    constexpr COp o[N] = {{TOP_LOAD, 0, 0, 0}, {TOP_ROUND, 0, 0, M_HI4}, {TOP_WT, 0, 0, 0}, {TOP_ROUND, 0, 1, M_TOP2},
+                          {TOP_BT, 0, 0, 0}, {TOP_ROUND, 0, 2, M_HI4}, {TOP_STORE, 1, 0, 0}};
+    return o[i];
+  }
+};
+struct ProgBoundary {
+  static constexpr int N = 13;
+  static constexpr COp op(int i) {
+    constexpr COp o[N] = {{TOP_LOAD, 0, 0, 0}, {TOP_ROUND, 0, 0, M_HI4}, {TOP_WT, 0, 0, 0}, {TOP_ROUND, 0, 1, M_TOP2},
+                          {TOP_BT, 0, 0, 0}, {TOP_ROUND, 0, 2, M_HI4}, {TOP_PHASE, 1, 0, 0}, {TOP_ROUND, 0, 3, M_ALL},
+                          {TOP_WT, 0, 0, 0}, {TOP_ROUND, 0, 4, M_ALL}, {TOP_BT, 0, 0, 0}, {TOP_ROUND, 0, 5, M_HI4},
+                          {TOP_STORE, 0, 0, 0}};
+    return o[i];
+  }
+};
+struct ProgFinal {
+  static constexpr int N = 7;
+  static constexpr COp op(int i) {
+    constexpr COp o[N] = {{TOP_LOAD, 0, 0, 0}, {TOP_ROUND, 0, 0, M_HI4}, {TOP_WT, 0, 0, 0}, {TOP_ROUND, 0, 1, M_TOP2},
+                          {TOP_BT, 0, 0, 0}, {TOP_ROUND, 0, 2, M_HI4}, {TOP_REDUCE, 1, 0, 0}};
+    return o[i];
+  }
+};
+
+template <typename Elem, typename Prog, int DK, int I>
+struct ProgExec {
+  static __device__ __forceinline__ void run(const Ctx<Elem>& c, Elem (&v)[32]) {
+    if constexpr (I < Prog::N) {
+      constexpr COp op = Prog::op(I);
+      if constexpr (op.type == TOP_LOAD) op_load<Elem>(c, v, op.frame);
+      else if constexpr (op.type == TOP_STORE) op_store<Elem>(c, v, op.frame);
+      else if constexpr (op.type == TOP_INIT) op_init<Elem>(c, v, op.frame);
+      else if constexpr (op.type == TOP_PHASE) op_phase<Elem, DK>(c, v, op.arg);
+      else if constexpr (op.type == TOP_ROUND) {
+        // complex128: register slot 0 of frames A/B is the re/im bit, never a qubit
+        round_static<Elem, op.mask>(c, v, op.arg);
+      }
+      else if constexpr (op.type == TOP_WT) warp_transpose<Elem>(c, v);
+      else if constexpr (op.type == TOP_BT) block_transpose<Elem>(c, v);
+      else if constexpr (op.type == TOP_REDUCE) op_reduce<Elem, DK>(c, v, op.arg);
+      ProgExec<Elem, Prog, DK, I + 1>::run(c, v);
+    }
+  }
+};
+
+template <typename Elem, typename Prog, int DK>
+__global__ void __launch_bounds__(TILE_THREADS, 1)
+tile_prog_kernel(const __grid_constant__ TilePass P, Elem* __restrict__ state, size_t point_stride,
+                 const typename ElemTraits<Elem>::real* __restrict__ tau, const double* __restrict__ phs,
+                 const void* __restrict__ tables, int tables_per_point, DiagInfo dinfo,
+                 double* __restrict__ partials) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  Ctx<Elem> c;
+  ctx_init<Elem>(c, P, state, point_stride, tau, phs, tables, tables_per_point, dinfo, partials, smem_raw);
+  Elem v[32];
+  ProgExec<Elem, Prog, DK, 0>::run(c, v);
+}
+
+// host-side: does a planned pass match a compiled program exactly?
+template <typename Prog>
+inline bool prog_matches(const TilePass& tp) {
+  if (tp.nops != Prog::N) return false;
+  for (int i = 0; i < Prog::N; i++) {
+    const COp o = Prog::op(i);
+    if (tp.ops[i].type != o.type) return false;
+    if (o.type == TOP_ROUND) {
+      if (tp.ops[i].arg != o.arg || tp.ops[i].mask != o.mask) return false;
+    } else if (o.type == TOP_PHASE || o.type == TOP_REDUCE) {
+      if (tp.ops[i].arg != o.arg || tp.ops[i].frame != o.frame) return false;
+    } else if (o.type == TOP_LOAD || o.type == TOP_STORE || o.type == TOP_INIT) {
+      if (tp.ops[i].frame != o.frame) return false;
+    }
+  }
+  return true;
+}
+
 // Builds one permuted diagonal stream: stream[(tile, warp, chunk, lane, i)] = diag[x(tile,warp,lane,amp)]
-// using exactly the addressing of the pass kernel (same helper functions).
+// using exactly the addressing of the pass kernels (same helper functions).
 template <int VALBYTES>
 __global__ void make_stream_kernel(const __grid_constant__ TilePass P, int frame, int namp,
                                    const unsigned char* __restrict__ diag,
@@ -401,14 +592,17 @@ __global__ void make_stream_kernel(const __grid_constant__ TilePass P, int frame
   TileAddr ad = tile_addr(P, base, frame, warp, lane);
   constexpr int V = 16 / VALBYTES;
   const int nchunks = namp / V;
-  for (int a = 0; a < namp; a++) {
-    // amplitude a -> register index: complex64: r = a (q = a>>1, low bit a&1); complex128: q = a
-    int q = (namp == 32) ? (a >> 1) : a;
-    size_t e = ad.e0 + reg_off(ad, q) + ((namp == 32) ? (a & 1) : 0);
-    size_t x = e >> P.qshift;
-    size_t dst = (stream_chunk(tile, warp, lane, nchunks, a / V) * V + (a % V)) * VALBYTES;
-    const unsigned char* src = diag + x * VALBYTES;
+  for (int j = 0; j < nchunks; j++) {
+    __align__(16) unsigned char buf[16];
+    for (int i = 0; i < V; i++) {
+      const int a = j * V + i;
+      // amplitude a -> register pair q: complex64: q = a>>1 with low bit a&1; complex128: q = a
+      const int q = (namp == 32) ? (a >> 1) : a;
+      const size_t e = ad.e0 + reg_off(ad, q) + ((namp == 32) ? (a & 1) : 0);
+      const unsigned char* src = diag + (e >> P.qshift) * VALBYTES;
 #pragma unroll
-    for (int b = 0; b < VALBYTES; b++) stream[dst + b] = src[b];
+      for (int b = 0; b < VALBYTES; b++) buf[i * VALBYTES + b] = src[b];
+    }
+    reinterpret_cast<uint4*>(stream)[stream_chunk(tile, warp, lane, nchunks, j)] = *reinterpret_cast<uint4*>(buf);
   }
 }

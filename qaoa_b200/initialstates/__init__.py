@@ -1,0 +1,4 @@
+from .base_initialstate import InitialState
+from .plus_initialstate import Plus
+from .dicke_initialstate import Dicke
+from .statevector_initialstate import StateVector

@@ -1,0 +1,5 @@
+from .base_mixer import Mixer
+from .xy_mixer import XY
+from .x_mixer import X
+from .x_multiangle_mixer import XMultiAngle
+from .grover_mixer import Grover

@@ -1,0 +1,487 @@
+"""QAOA driver with the reference's public API, evaluated on the B200 engine.
+
+``QAOA(problem=..., mixer=..., initialstate=...)``, ``sample_cost_landscape()``,
+``optimize(depth)``, ``get_Exp/get_Var/get_gamma/get_beta/get_angles`` keep the signatures and
+semantics of the reference driver (reference qaoa/qaoa.py:157-1218).  What changes is the
+evaluation path: where the reference builds, transpiles and binds a qiskit circuit, runs it on
+qiskit-aer for ``shots`` samples and averages ``problem.cost`` over the counts
+(qaoa/qaoa.py:418-520, 592-614, 653-661, 691-740, 912-922), this class lowers the three
+components onto a device-resident statevector engine once and asks it for the EXACT moments
+``E[cost]``, ``E[cost^2]``, ``min``, ``max`` of the final state.
+
+Semantics in the exact engine:
+  * ``Exp = -E[cost]`` (cvar = 1) is the shots -> infinity limit of the reference's estimate;
+  * ``Var`` is the population variance (the reference's S/(W-1) is undefined without samples);
+  * ``BestCost/WorstCost`` are -max/-min of the cost over the support of |psi|^2;
+  * ``noisemodel``, ``precision``, ``memorysize > 0``, ``flip``, ``post``, QNSPSA and foreign
+    ``backend`` objects cannot be honoured by an exact statevector engine and are REJECTED
+    (NotImplementedError) — nothing is ever routed to a CPU simulator.
+"""
+
+from __future__ import annotations
+
+import logging
+import time
+
+import numpy as np
+
+from qaoa_b200.initialstates import InitialState
+from qaoa_b200.mixers import Mixer
+from qaoa_b200.problems import Problem
+from qaoa_b200.utils import COBYLA, ExactStatistic
+
+LOG = logging.getLogger(__name__)
+
+
+class B200Backend:
+    """Stands where the reference keeps its qiskit backend (``backend.name``,
+    ``backend.configuration().local`` are the only members the reference reads,
+    qaoa/qaoa.py:564 and qaoa/utils/qaoaIO.py:255)."""
+
+    name = "b200_statevector"
+
+    def __init__(self, device=0, dtype="complex128"):
+        self.device = device
+        self.dtype = dtype
+
+    class _Conf:
+        local = True
+
+    def configuration(self):
+        return self._Conf()
+
+
+class OptResult:
+    """Per-depth optimisation record (same fields as reference qaoa/qaoa.py:30-154)."""
+
+    def __init__(self, depth):
+        self.depth = depth
+        self.angles = []
+        self.Exp = []
+        self.Var = []
+        self.WorstCost = []
+        self.BestCost = []
+        self.BestSols = []
+        self.shots = []
+        self.index_Exp_min = -1
+        self.opt_time = -1.0
+
+    def add_iteration(self, angles, stat, shots):
+        self.angles.append(angles)
+        self.Exp.append(-stat.get_CVaR())
+        self.Var.append(stat.get_Variance())
+        self.BestCost.append(-stat.get_max())
+        self.WorstCost.append(-stat.get_min())
+        self.BestSols.append(stat.get_max_sols())
+        self.shots.append(shots)
+
+    def compute_best_index(self):
+        self.index_Exp_min = int(np.argmin(self.Exp))
+
+    def get_best_Exp(self):
+        return self.Exp[self.index_Exp_min]
+
+    def get_best_Var(self):
+        return self.Var[self.index_Exp_min]
+
+    def get_best_angles(self):
+        return self.angles[self.index_Exp_min]
+
+    def num_fval(self):
+        return len(self.Exp)
+
+    def num_shots(self):
+        return sum(self.shots)
+
+    def get_best_solution(self):
+        lowest = np.min(self.BestCost)
+        sols = []
+        for i in np.where(np.asarray(self.BestCost) == lowest)[0]:
+            sols.extend(self.BestSols[i])
+        return np.unique(sols), lowest
+
+
+def _reject(what):
+    raise NotImplementedError(
+        what + " cannot be honoured by the exact B200 statevector engine and is rejected "
+        "(the engine never falls back to a sampling/CPU simulator)"
+    )
+
+
+class QAOA:
+    def __init__(
+        self,
+        problem,
+        mixer,
+        initialstate,
+        backend=None,
+        noisemodel=None,
+        optimizer=None,
+        precision=None,
+        shots=1024,
+        cvar=1,
+        memorysize=-1,
+        interpolate=True,
+        flip=False,
+        post=False,
+        number_trottersteps_mixer=1,
+        sequential=False,
+        dtype=None,
+        device=0,
+    ) -> None:
+        assert issubclass(type(problem), Problem)
+        assert issubclass(type(mixer), Mixer)
+        assert issubclass(type(initialstate), InitialState)
+
+        if backend is None:
+            backend = B200Backend(device=device, dtype=dtype or "complex128")
+        if not isinstance(backend, B200Backend):
+            _reject("backend=%r" % (backend,))
+        if dtype is not None:
+            backend.dtype = dtype
+        if noisemodel is not None:
+            _reject("noisemodel")
+        if precision is not None:
+            _reject("precision (shot-adaptive estimation)")
+        if memorysize is not None and memorysize > 0:
+            _reject("memorysize > 0 (per-shot memory)")
+        if flip:
+            _reject("flip=True (bit-flip boosting needs sampled histograms)")
+        if post:
+            _reject("post=True (classical post-processing of sampled histograms)")
+        if getattr(problem, "N_ancilla_qubits", 0):
+            _reject("problems with ancilla qubits")
+        if not (0 < cvar <= 1):
+            raise ValueError("cvar must be in (0, 1]")
+        if cvar < 1:
+            _reject("cvar < 1")
+
+        self.problem = problem
+        self.mixer = mixer
+        self.initialstate = initialstate
+        self.initialstate.setNumQubits(self.problem.N_qubits)
+        self.mixer.setNumQubits(self.problem.N_qubits)
+
+        self.parameterized_circuit = None
+        self.parameterized_circuit_depth = 0
+        self.parametrized_circuit_depth = 0  # the reference writes this spelling (qaoa.py:520)
+
+        self.backend = backend
+        self.optimizer = [COBYLA, {}] if optimizer is None else optimizer
+        if getattr(self.optimizer[0], "__name__", "") == "QNSPSA":
+            _reject("QNSPSA (needs circuit fidelities)")
+        self.noisemodel = None
+        self.shots = shots
+        self.precision = None
+        self.stat = ExactStatistic(cvar=cvar)
+        self.cvar = cvar
+        self.memorysize = memorysize
+        self.memory = False
+        self.interpolate = interpolate
+        self.sequential = sequential
+        self.usebarrier = False
+        self.isQNSPSA = False
+
+        self.current_depth = 0
+        self.gamma_params = None
+        self.beta_params = None
+        self.init_params = None
+        self.n_gamma = 1
+        self.n_beta = 1
+        self.n_init = 0
+
+        self.Exp_sampled_p1 = None
+        self.landscape_p1_angles = {}
+        self.Var_sampled_p1 = None
+        self.MaxCost_sampled_p1 = None
+        self.MinCost_sampled_p1 = None
+
+        self.optimization_results = {}
+        self.memory_lists = []
+        self.flip = False
+        self.bitflips = []
+        self.post = False
+        self.Exp_post_processed = None
+        self.Var_post_processed = None
+        self.samplecount_hists = {}
+        self.last_hist = {}
+        self.number_trottersteps_mixer = number_trottersteps_mixer
+
+        self._engine = None
+
+    # ------------------------------------------------------------------ engine plumbing
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        state["_engine"] = None  # device handles are re-created lazily after unpickling
+        return state
+
+    def _get_engine(self):
+        """Builds the device plan (what createParameterizedCircuit + transpile were, qaoa.py:418-520)."""
+        if self._engine is None:
+            from qaoa_b200.engine import Engine
+
+            if self.problem.get_num_parameters() != 1:
+                _reject("problems with more than one gamma per layer")
+            if self.initialstate.get_num_parameters() != 0:
+                _reject("parameterised initial states")
+            eng = Engine(self.problem.N_qubits, dtype=self.backend.dtype, device=self.backend.device)
+            self.problem.lower_cost(eng)
+            self.initialstate.lower_initial(eng)
+            self.mixer.lower_mixer(eng, trotter=self.number_trottersteps_mixer)
+            self._engine = eng
+        return self._engine
+
+    def _evaluate(self, angle_rows):
+        """(B, n_angles) flat angle vectors -> (B, 5) = E, E2, min, max, norm."""
+        rows = np.atleast_2d(np.asarray(angle_rows, dtype=np.float64))
+        return self._get_engine().energy_batch(rows)
+
+    # ------------------------------------------------------------------ accessors
+    def exp_landscape(self):
+        return self.Exp_sampled_p1
+
+    def var_landscape(self):
+        return self.Var_sampled_p1
+
+    def get_Exp(self, depth=None):
+        if not depth:
+            return [self.optimization_results[d].get_best_Exp() for d in range(1, self.current_depth + 1)]
+        if depth > self.current_depth + 1:
+            raise ValueError
+        return self.optimization_results[depth].get_best_Exp()
+
+    def get_Var(self, depth):
+        if depth > self.current_depth + 1:
+            raise ValueError
+        return self.optimization_results[depth].get_best_Var()
+
+    def get_beta(self, depth):
+        if depth > self.current_depth + 1:
+            raise ValueError
+        return self.optimization_results[depth].get_best_angles()[1::2]
+
+    def get_gamma(self, depth):
+        if depth > self.current_depth + 1:
+            raise ValueError
+        return self.optimization_results[depth].get_best_angles()[::2]
+
+    def get_angles(self, depth):
+        if depth > self.current_depth + 1:
+            raise ValueError
+        return self.optimization_results[depth].get_best_angles()
+
+    def get_memory_lists(self):
+        return self.memory_lists
+
+    # ------------------------------------------------------------------ plan ("circuit")
+    def createParameterizedCircuit(self, depth):
+        """Fixes the parameter layout for ``depth`` layers.  No circuit is built: the engine applies
+        init -> [phase(gamma_d) -> mixer(beta_d)] x depth directly on the statevector."""
+        self.problem.create_circuit()
+        self.mixer.create_circuit()
+        self.initialstate.create_circuit()
+        self.n_gamma = self.problem.get_num_parameters()
+        self.n_beta = self.mixer.get_num_parameters()
+        self.n_init = self.initialstate.get_num_parameters()
+        self.gamma_params = [["gamma_{}_{}".format(d, i) for i in range(self.n_gamma)] for d in range(depth)]
+        self.beta_params = [["beta_{}_{}".format(d, i) for i in range(self.n_beta)] for d in range(depth)]
+        self.init_params = ["init_{}".format(i) for i in range(self.n_init)]
+        self.parameterized_circuit_depth = depth
+        self.parametrized_circuit_depth = depth
+        self._get_engine()
+
+    def getParametersToBind(self, angles, depth, asList=False):
+        """Name -> value view of the flat angle vector (layout of reference qaoa.py:937-990)."""
+        per_layer = self.n_gamma + self.n_beta
+        assert len(angles) == self.n_init + depth * per_layer
+        wrap = (lambda v: [v]) if asList else (lambda v: v)
+        bound = {}
+        for i in range(self.n_init):
+            bound["init_{}".format(i)] = wrap(angles[i])
+        at = self.n_init
+        for d in range(depth):
+            for i in range(self.n_gamma):
+                bound["gamma_{}_{}".format(d, i)] = wrap(angles[at + i])
+            at += self.n_gamma
+            for i in range(self.n_beta):
+                bound["beta_{}_{}".format(d, i)] = wrap(angles[at + i])
+            at += self.n_beta
+        return bound
+
+    # ------------------------------------------------------------------ landscape
+    def _grid(self, angles):
+        g, b = angles["gamma"], angles["beta"]
+        return (np.linspace(g[0], g[1], g[2], endpoint=False), np.linspace(b[0], b[1], b[2], endpoint=False))
+
+    def _vanilla_rows(self, gamma_grid, beta_grid, prefix=()):
+        """All grid points in the symmetric subspace, beta-major like the reference loops
+        (qaoa.py:637-649): every gamma of the layer = grid gamma, every beta = grid beta."""
+        prefix = list(prefix)
+        rows = [
+            prefix + [g] * self.n_gamma + [b] * self.n_beta
+            for b in beta_grid
+            for g in gamma_grid
+        ]
+        return np.asarray(rows, dtype=np.float64)
+
+    def sample_cost_landscape(self, angles={"gamma": [0, 2 * np.pi, 20], "beta": [0, 2 * np.pi, 20]}):
+        """p = 1 landscape on the (gamma, beta) grid: all points go to the device in one batched call
+        (the reference's batch branch, qaoa.py:630-662; ``sequential`` gives identical numbers here)."""
+        self.landscape_p1_angles = angles
+        LOG.info("Calculating energy landscape for depth p=1...")
+        if not self.backend.configuration().local:
+            raise NotImplementedError
+        self.createParameterizedCircuit(1)
+        self.gamma_grid, self.beta_grid = self._grid(angles)
+        rows = self._vanilla_rows(self.gamma_grid, self.beta_grid, prefix=[0.0] * self.n_init)
+        LOG.info("Executing sample_cost_landscape")
+        LOG.info("circuits: %d", len(rows))
+        res = self._evaluate(rows)
+        shape = (angles["beta"][2], angles["gamma"][2])
+        self.Exp_sampled_p1 = -res[:, 0].reshape(shape)
+        self.Var_sampled_p1 = np.maximum(res[:, 1] - res[:, 0] ** 2, 0.0).reshape(shape)
+        self.MaxCost_sampled_p1 = -res[:, 3].reshape(shape)
+        self.MinCost_sampled_p1 = -res[:, 2].reshape(shape)
+        self.last_hist = {}
+        LOG.info("Calculating Energy landscape done")
+
+    @staticmethod
+    def _argmin_first(values):
+        """np.argmin with a deterministic tie-break: landscapes of symmetric problems have exactly
+        degenerate minima (16-fold for MaxCut on [0, 2pi)^2) that differ only by rounding noise, so
+        values are quantised to 1e-9 of the landscape's scale before the first minimum is taken."""
+        v = np.asarray(values, dtype=np.float64)
+        scale = max(np.max(np.abs(v)), 1e-300)
+        q = np.round(v / (1e-9 * scale))
+        return int(np.argmin(q, axis=None))
+
+    # ------------------------------------------------------------------ optimisation
+    def optimize(self, depth, angles={"gamma": [0, 2 * np.pi, 20], "beta": [0, 2 * np.pi, 20]}):
+        """Depth-by-depth local optimisation (control flow of reference qaoa.py:742-856)."""
+        while self.current_depth < depth:
+            n_gamma = self.problem.get_num_parameters()
+            n_beta = self.mixer.get_num_parameters()
+            n_init = self.initialstate.get_num_parameters()
+            t0 = time.perf_counter()
+            if self.current_depth == 0:
+                if self.Exp_sampled_p1 is None:
+                    self.sample_cost_landscape(angles=angles)
+                flat = self._argmin_first(self.Exp_sampled_p1)
+                ib, ig = np.unravel_index(flat, self.Exp_sampled_p1.shape)
+                angles0 = np.array([0.0] * n_init + [self.gamma_grid[ig]] * n_gamma + [self.beta_grid[ib]] * n_beta)
+            else:
+                best = self.get_angles(self.current_depth)
+                angles0 = self.interp(best) if self.interpolate else self._grid_search_layer(best, angles)
+
+            target = self.current_depth + 1
+            self.optimization_results[target] = OptResult(target)
+            self.createParameterizedCircuit(int((len(angles0) - n_init) / (n_gamma + n_beta)))
+            res = self.local_opt(angles0)
+            self.samplecount_hists[target] = self.last_hist
+            self.optimization_results[target].compute_best_index()
+            self.optimization_results[target].opt_time = time.perf_counter() - t0
+            LOG.info("cost(depth %d = %s", target, res.fun)
+            self.current_depth += 1
+
+    def local_opt(self, angles0):
+        opt = self.optimizer[0](**self.optimizer[1])
+        return opt.minimize(self.loss, x0=angles0)
+
+    def loss(self, angles):
+        """One energy evaluation, recorded in the current depth's OptResult (reference qaoa.py:885-935)."""
+        if not self.backend.configuration().local:
+            raise NotImplementedError
+        angles = np.asarray(angles, dtype=np.float64)
+        assert len(angles) == self.n_init + self.parametrized_circuit_depth * (self.n_gamma + self.n_beta)
+        e, e2, cmin, cmax, _norm = self._evaluate(angles[self.n_init:])[0]
+        self.stat.reset()
+        self.stat.set_exact(e, e2, cmin, cmax)
+        self.optimization_results[self.current_depth + 1].add_iteration(angles.copy(), self.stat, self.shots)
+        return -self.stat.get_CVaR()
+
+    def interp(self, angles):
+        """INTERP warm start p -> p+1, independently for every parameter index (reference
+        qaoa.py:992-1027, https://doi.org/10.1103/PhysRevX.10.021067)."""
+        per_layer = self.n_gamma + self.n_beta
+        depth = (len(angles) - self.n_init) // per_layer
+        head = np.asarray(angles[: self.n_init], dtype=np.float64)
+        old = np.asarray(angles[self.n_init:], dtype=np.float64).reshape(depth, per_layer)
+        padded = np.zeros((depth + 2, per_layer))
+        padded[1:-1] = old
+        w = np.arange(depth + 1, dtype=np.float64)[:, None]
+        new = w / depth * padded[:-1] + (depth - w) / depth * padded[1:]
+        return np.concatenate([head, new.reshape(-1)])
+
+    def _eval_cost(self, angle_array):
+        """Unrecorded evaluation (reference qaoa.py:1029-1066)."""
+        if not self.backend.configuration().local:
+            raise NotImplementedError
+        angle_array = np.asarray(angle_array, dtype=np.float64)
+        e, e2, cmin, cmax, _ = self._evaluate(angle_array[self.n_init:])[0]
+        self.stat.reset()
+        self.stat.set_exact(e, e2, cmin, cmax)
+        return -self.stat.get_CVaR()
+
+    def _grid_search_layer(self, prev_angles, angles):
+        """Warm start for depth p from a 2-D grid over the NEW layer with layers 1..p-1 locked
+        (reference qaoa.py:1068-1132).  The whole grid is one batched device call; the first
+        strictly smallest value wins, as in the reference's sequential scan."""
+        per_layer = self.n_gamma + self.n_beta
+        new_depth = (len(prev_angles) - self.n_init) // per_layer + 1
+        self.createParameterizedCircuit(new_depth)
+        gamma_grid, beta_grid = self._grid(angles)
+        LOG.info("Layer grid search at depth %d: %dx%d points", new_depth, len(gamma_grid), len(beta_grid))
+        rows = self._vanilla_rows(gamma_grid, beta_grid, prefix=list(np.asarray(prev_angles, dtype=np.float64)))
+        res = self._evaluate(rows[:, self.n_init:])
+        costs = -res[:, 0]
+        k = int(np.argmin(costs))
+        LOG.info("Layer grid search done, best cost: %.6f", -costs[k])
+        return rows[k].copy()
+
+    def hist(self, angles, shots):
+        """Sampled histogram {bit-string (string[i] = qubit i): count} of the state at ``angles``
+        (reference qaoa.py:1134-1172), drawn on the device from |psi|^2."""
+        n_gamma = self.problem.get_num_parameters()
+        n_beta = self.mixer.get_num_parameters()
+        n_init = self.initialstate.get_num_parameters()
+        depth = int((len(angles) - n_init) / (n_gamma + n_beta))
+        self.createParameterizedCircuit(depth)
+        eng = self._get_engine()
+        idx = eng.sample(np.asarray(angles, dtype=np.float64)[n_init:], int(shots))
+        n = self.problem.N_qubits
+        out = {}
+        values, counts = np.unique(idx, return_counts=True)
+        for x, c in zip(values.tolist(), counts.tolist()):
+            out["".join("1" if (x >> i) & 1 else "0" for i in range(n))] = int(c)
+        return out
+
+    def random_init(self, gamma_bounds, beta_bounds, depth):
+        gam = np.random.uniform(gamma_bounds[0], gamma_bounds[1], size=depth)
+        bet = np.random.uniform(beta_bounds[0], beta_bounds[1], size=depth)
+        out = np.empty(2 * depth, dtype=gam.dtype)
+        out[0::2], out[1::2] = gam, bet
+        return out
+
+    def get_optimal_solutions(self):
+        sols, costs = [], []
+        for d in self.optimization_results:
+            s, c = self.optimization_results[d].get_best_solution()
+            sols.append(s)
+            costs.append(c)
+        keep = np.where(np.asarray(costs) == np.min(costs))[0]
+        return np.unique([x for i in keep for x in sols[i]])
+
+    def validate_circuit(self, t=1, flip=True, atol=1e-8, rtol=1e-8):
+        """The reference compares the circuit's diagonal with exp(i t cost) (validation.py:16-79).
+        Here the phase separator IS that diagonal; what can be validated is that the device
+        diagonal equals ``problem.cost`` for every bit-string."""
+        n = self.problem.N_qubits
+        if n > 16:
+            raise ValueError("validate_circuit is a brute-force check for <= 16 qubits")
+        dev = self._get_engine().read_cost_diagonal()
+        host = np.array([
+            self.problem.cost("".join("1" if (x >> i) & 1 else "0" for i in range(n))) for x in range(1 << n)
+        ], dtype=np.float64)
+        err = float(np.max(np.abs(dev - host)))
+        ok = err <= atol + rtol * float(np.max(np.abs(host)))
+        return ok, {"n_qubits": n, "max_cost_error": err}

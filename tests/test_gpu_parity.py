@@ -214,3 +214,43 @@ def test_errors_are_reported():
         E.energy([0.1, 0.2])  # no cost set
     with pytest.raises(eng.EngineError):
         E.set_cost_qubo(np.eye(5))
+
+
+@pytest.mark.parametrize("dtype", ["complex64", "complex128"])
+def test_canonical_programs_vs_interpreter_vs_oracle(dtype):
+    """n=24: the specialised straight-line pass kernels and the interpreter kernel must agree
+    with each other and with the oracle (p=1: FIRST+FINAL; p=3: FIRST, INTERIOR/BOUNDARY, FINAL)."""
+    n = 24
+    eng, E = _engine(n, dtype)
+    edges, colors, table = H.regular_maxcut(n)
+    lut, _ = H.lut_from_table(table, 1)
+    E.set_cost_maxkcut(n, edges, 1, lut)
+    diag = H.maxcut_diag(n, edges, colors, table)
+    spec = orc.Spec(n, diag)
+    rng = np.random.default_rng(2024)
+    for p in (1, 3):
+        ang = rng.uniform(0, 2 * np.pi, size=2 * p)
+        ang[1::2] = rng.uniform(-1.2, 1.2, size=p)      # keep |tan beta| moderate: normal form
+        E.set_option("force_generic", 0)
+        E.counter("reset")
+        a = E.energy(ang)
+        assert E.counter("prog_launches") >= 2, "specialised kernels were not used"
+        E.set_option("force_generic", 1)
+        b = E.energy(ang)
+        ref = orc.energy(spec, ang)
+        assert H.rel_err(a[0], ref[0]) < TOL[dtype] and H.rel_err(b[0], ref[0]) < TOL[dtype], (a, b, ref)
+        assert H.rel_err(a[0], b[0]) < TOL[dtype] * 0.1
+
+
+@pytest.mark.parametrize("dtype", ["complex64", "complex128"])
+def test_beta_at_and_near_half_pi(dtype):
+    """|tan beta| huge or infinite: the host must switch to the cot form (interpreter kernel)."""
+    n = 16
+    eng, E = _engine(n, dtype)
+    edges, colors, table = H.regular_maxcut(n)
+    lut, _ = H.lut_from_table(table, 1)
+    E.set_cost_maxkcut(n, edges, 1, lut)
+    spec = orc.Spec(n, H.maxcut_diag(n, edges, colors, table))
+    for betas in ([np.pi / 2, 0.3], [np.pi / 2 - 1e-9, 3 * np.pi / 2], [1.5, 1.6], [0.0, np.pi]):
+        ang = np.array([0.8, betas[0], 0.35, betas[1]])
+        _check(E.energy(ang), spec, ang, dtype, "betas=%r" % (betas,))
