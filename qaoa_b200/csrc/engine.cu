@@ -107,6 +107,8 @@ struct Engine {
   double* d_params = nullptr; size_t params_cap = 0;   // [tau block (real)][phs block (double)]
   double* h_params = nullptr; size_t hparams_cap = 0;
   int force_generic = 0;
+  int prefetch_dist = 0;     // extra L2 prefetch distance in tiles (0 = off)
+  int persistent_ctas = 148; // CTAs of the persistent pass kernels (one per SM)
   double* d_partials = nullptr; size_t partials_cap = 0;
   double* d_out = nullptr; size_t out_cap = 0;
   double* h_out = nullptr; size_t hout_cap = 0;
@@ -450,24 +452,39 @@ void fill_point_params(Engine* h, const Plan& pl, const double* ang, double* tau
 }
 
 template <typename Elem>
-void launch_pass(Engine* h, const PlanPass& pp, bool use_prog, dim3 grid, size_t point_stride_elems,
+void launch_pass(Engine* h, const PlanPass& pp, bool use_prog, unsigned ntiles, int B, size_t point_stride_elems,
                  const void* d_tau, const double* d_phs, int tables_per_point) {
   typedef typename ElemTraits<Elem>::real real;
-  const int smem = TILE_SMEM_BYTES;
-  auto go = [&](auto kernel) {
-    CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    kernel<<<grid, TILE_THREADS, smem, h->stream>>>(pp.tp, (Elem*)h->state, point_stride_elems, (const real*)d_tau,
-                                                    d_phs, h->d_tables, tables_per_point, h->dinfo, h->d_partials);
-  };
+  TilePass tp = pp.tp;
+  tp.ntiles = ntiles;
+  tp.prefetch_dist = h->prefetch_dist;
   const int prog = use_prog ? pp.prog : PROG_GENERIC;
   const bool u8 = h->dinfo.kind == DIAG_U8;
+  // interpreter: one CTA per (tile, point); programs: persistent CTAs walking the linear index
+  auto go_generic = [&]() {
+    auto kernel = tile_pass_kernel<Elem>;
+    CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES));
+    tp.prefetch_dist = 0;
+    // interpreter walks tiles of ONE point per launch row; use a flat grid over (point, tile)
+    dim3 grid((unsigned)std::min<unsigned long long>((unsigned long long)ntiles * B, 0x7fffffffull));
+    kernel<<<grid, TILE_THREADS, TILE_SMEM_BYTES, h->stream>>>(tp, (Elem*)h->state, point_stride_elems, (const real*)d_tau,
+                                                               d_phs, h->d_tables, tables_per_point, h->dinfo, h->d_partials);
+  };
+  auto go = [&](auto kernel) {
+    CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES_STAGED));
+    const unsigned long long total = (unsigned long long)ntiles * B;
+    dim3 grid((unsigned)std::min<unsigned long long>(total, (unsigned long long)h->persistent_ctas));
+    kernel<<<grid, TILE_THREADS, TILE_SMEM_BYTES_STAGED, h->stream>>>(tp, (Elem*)h->state, point_stride_elems,
+                                                                      (const real*)d_tau, d_phs, h->d_tables,
+                                                                      tables_per_point, h->dinfo, h->d_partials, (unsigned)B);
+  };
   switch (prog) {
     case PROG_FIRST_INIT: if (u8) go(tile_prog_kernel<Elem, ProgFirstInit, DIAG_U8>); else go(tile_prog_kernel<Elem, ProgFirstInit, 0>); break;
     case PROG_FIRST_LOAD: if (u8) go(tile_prog_kernel<Elem, ProgFirstLoad, DIAG_U8>); else go(tile_prog_kernel<Elem, ProgFirstLoad, 0>); break;
     case PROG_INTERIOR: go(tile_prog_kernel<Elem, ProgInterior, DIAG_U8>); break;
     case PROG_BOUNDARY: if (u8) go(tile_prog_kernel<Elem, ProgBoundary, DIAG_U8>); else go(tile_prog_kernel<Elem, ProgBoundary, 0>); break;
     case PROG_FINAL: if (u8) go(tile_prog_kernel<Elem, ProgFinal, DIAG_U8>); else go(tile_prog_kernel<Elem, ProgFinal, 0>); break;
-    default: go(tile_pass_kernel<Elem>); break;
+    default: go_generic(); break;
   }
   CUDA_OK(cudaGetLastError());
 }
@@ -536,12 +553,11 @@ void run_tile_chunk(Engine* h, Plan& pl, const double* angles, int n_angles, int
   size_t tbase = 0, pbase = 0;
   for (size_t ip = 0; ip < pl.passes.size(); ip++) {
     auto& pp = pl.passes[ip];
-    dim3 grid(ntiles, Bc);
     const bool use_prog = all_normal[ip] && !h->force_generic;
     const void* d_tau = db + tbase * rsz;
     const double* d_phs = (const double*)(db + tau_bytes) + pbase;
-    if (c64) launch_pass<float2>(h, pp, use_prog, grid, point_stride_elems, d_tau, d_phs, p);
-    else launch_pass<double>(h, pp, use_prog, grid, point_stride_elems, d_tau, d_phs, p);
+    if (c64) launch_pass<float2>(h, pp, use_prog, ntiles, Bc, point_stride_elems, d_tau, d_phs, p);
+    else launch_pass<double>(h, pp, use_prog, ntiles, Bc, point_stride_elems, d_tau, d_phs, p);
     h->launches += 1;
     if (use_prog && pp.prog != PROG_GENERIC) h->prog_launches += 1;
     bool reads = pp.tp.ops[0].type == TOP_LOAD, writes = pp.tp.ops[pp.tp.nops - 1].type == TOP_STORE;
@@ -771,6 +787,7 @@ int qaoa_create(int n_qubits, int dtype, int device, qaoa_engine_t** out) {
     CUDA_OK(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10) fail("this engine requires an sm_100a (B200) device");
     qaoa_engine* h = new qaoa_engine();
+    h->persistent_ctas = prop.multiProcessorCount;
     h->n = n_qubits; h->dtype = dtype; h->device = device;
     h->qshift = dtype == QAOA_DTYPE_C128 ? 1 : 0;
     h->E = n_qubits + h->qshift;
@@ -814,6 +831,8 @@ int qaoa_set_option(qaoa_engine_t* h, const char* key, double value) {
   else if (k == "batch_points") h->batch_points = (int)value;
   else if (k == "batch_bytes") h->batch_bytes = (size_t)value;
   else if (k == "force_generic") h->force_generic = value != 0;
+  else if (k == "prefetch_dist") h->prefetch_dist = (int)value;
+  else if (k == "persistent_ctas") h->persistent_ctas = std::max(1, (int)value);
   else fail("unknown option: " + k);
   API_END(h)
 }
@@ -1058,6 +1077,83 @@ int qaoa_read_statevector(qaoa_engine_t* h, double* out) {
     out[2 * x] = rr;
     out[2 * x + 1] = mm;
   }
+  API_END(h)
+}
+
+// Test / profiling hook: runs an arbitrary step program on tiles over {0..3} U [hb, hb+10) with the
+// interpreter kernel and returns the mean CUDA-event time per launch.  ops = (type, frame, mask)
+// triples; PHASE / REDUCE are not allowed here (they need diagonal streams).
+int qaoa_debug_tile_program(qaoa_engine_t* h, int hb, const int32_t* ops, int nops, int reps, double tau_val,
+                            double* ms_out) {
+  API_BEGIN(h)
+  if (h->E < TILE_BITS) fail("register too small for the tile path");
+  // hb >= 100 encodes c = hb / 100 low bits and a window start hb % 100 for the other 14 - c bits
+  int clow = 4;
+  if (hb >= 100) { clow = hb / 100; hb = hb % 100; }
+  if (hb < clow || hb + (14 - clow) > h->E) fail("high-bit window out of range");
+  if (nops < 1 || nops > TILE_MAX_OPS) fail("bad program length");
+  ensure_state(h, 1);
+  TilePass tp;
+  memset(&tp, 0, sizeof(tp));
+  for (int j = 0; j < clow; j++) tp.pos[j] = j;
+  for (int j = 0; j < 14 - clow; j++) tp.pos[clow + j] = hb + j;
+  for (int b = clow; b < h->E; b++) if (b < hb || b >= hb + (14 - clow)) tp.freepos[tp.nfree++] = b;
+  tp.qshift = h->qshift;
+  tp.init_kind = INIT_PLUS;
+  tp.init_amp = pow(2.0, -0.5 * h->n);
+  int nr = 0;
+  for (int i = 0; i < nops; i++) {
+    const int ty = ops[3 * i];
+    if (ty == TOP_PHASE || ty == TOP_REDUCE) fail("PHASE/REDUCE not supported by the debug hook");
+    tp.ops[i].type = (int16_t)ty;
+    tp.ops[i].frame = (int16_t)ops[3 * i + 1];
+    tp.ops[i].mask = (int16_t)ops[3 * i + 2];
+    tp.ops[i].arg = (int16_t)(ty == TOP_ROUND ? nr++ : 0);
+  }
+  tp.nops = nops;
+  tp.nrounds = nr;
+  tp.tau_stride = nr * TILE_ROUND_REALS;
+  tp.phs_stride = 1;
+  tp.prefetch_dist = h->prefetch_dist;
+  const bool c64 = h->dtype == QAOA_DTYPE_C64;
+  const size_t rsz = c64 ? 4 : 8;
+  std::vector<unsigned char> hb_(std::max<size_t>(16, (size_t)tp.tau_stride * rsz + 16), 0);
+  for (int r = 0; r < nr; r++)
+    for (int s2 = 0; s2 < 5; s2++) {
+      // only slots in the step's mask are active
+      int mask = 0, seen = 0;
+      for (int i = 0; i < nops; i++) if (ops[3 * i] == TOP_ROUND) { if (seen == r) mask = ops[3 * i + 2]; seen++; }
+      const double k1 = ((mask >> s2) & 1) ? tau_val : 0.0;
+      if (c64) { ((float*)hb_.data())[r * TILE_ROUND_REALS + s2] = (float)k1; ((float*)hb_.data())[r * TILE_ROUND_REALS + 5 + s2] = (float)-k1; }
+      else { ((double*)hb_.data())[r * TILE_ROUND_REALS + s2] = k1; ((double*)hb_.data())[r * TILE_ROUND_REALS + 5 + s2] = -k1; }
+    }
+  ensure(h->d_params, h->params_cap, hb_.size() + 64);
+  CUDA_OK(cudaMemcpy(h->d_params, hb_.data(), hb_.size(), cudaMemcpyHostToDevice));
+  double one = 1.0;
+  CUDA_OK(cudaMemcpy((char*)h->d_params + hb_.size(), &one, 8, cudaMemcpyHostToDevice));
+  ensure(h->d_partials, h->partials_cap, 4096);
+  const unsigned ntiles = 1u << (h->E - TILE_BITS);
+  PlanPass pp;
+  pp.tp = tp;
+  cudaEvent_t e0, e1;
+  CUDA_OK(cudaEventCreate(&e0));
+  CUDA_OK(cudaEventCreate(&e1));
+  auto once = [&]() {
+    if (c64) launch_pass<float2>(h, pp, false, ntiles, 1, h->N << h->qshift, h->d_params, (const double*)((char*)h->d_params + hb_.size()), 1);
+    else launch_pass<double>(h, pp, false, ntiles, 1, h->N << h->qshift, h->d_params, (const double*)((char*)h->d_params + hb_.size()), 1);
+  };
+  once();
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  CUDA_OK(cudaEventRecord(e0, h->stream));
+  for (int r = 0; r < reps; r++) once();
+  CUDA_OK(cudaEventRecord(e1, h->stream));
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  float ms = 0;
+  CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (ms_out) *ms_out = ms / reps;
+  h->launches += reps + 1;
   API_END(h)
 }
 

@@ -37,6 +37,10 @@ constexpr int TILE_MAX_PHASES = 16;
 constexpr int TILE_ROUND_REALS = 12;  // k1[5], k2[5], form mask, pad
 constexpr int TILE_EXCH_BYTES = TILE_ELEMS * 8;
 constexpr int TILE_SMEM_BYTES = TILE_EXCH_BYTES + 4096 + 16 * 5 * 8;
+// persistent kernels additionally stage TILE_STAGE_PAIRS of the 16 register pairs of the NEXT tile
+constexpr int TILE_STAGE_PAIRS = 11;
+constexpr int TILE_STAGE_OFFSET = TILE_EXCH_BYTES + 4096 + 1024;
+constexpr int TILE_SMEM_BYTES_STAGED = TILE_STAGE_OFFSET + TILE_STAGE_PAIRS * TILE_THREADS * 16;
 
 enum TileOpType : int {
   TOP_LOAD = 1, TOP_STORE = 2, TOP_INIT = 3, TOP_PHASE = 4,
@@ -64,6 +68,8 @@ struct TilePass {
   int nphases;
   int tau_stride;                       // reals per point  (nrounds * TILE_ROUND_REALS)
   int phs_stride;                       // doubles per point (2 * nphases + 1)
+  int prefetch_dist;                    // tiles ahead whose lines are pulled into L2 (0 = off)
+  unsigned ntiles;                      // tiles per point
   const void* streams[TILE_MAX_PHASES]; // permuted cost-diagonal stream per phase slot
   int table_id[TILE_MAX_PHASES];        // index of the 256-entry phase table (U8 mode)
 };
@@ -158,6 +164,12 @@ struct Ctx {
   DiagInfo dinfo;
   double* partials;
   unsigned tile, point;
+  unsigned ntiles;
+  unsigned long long id, total, stride;   // persistent kernels: linear (point, tile) index walk
+  Elem* state0;
+  const real* tau0;
+  const double* phs0;
+  size_t point_stride;
   int warp, lane;
   size_t base;
   unsigned char* smem;
@@ -325,6 +337,28 @@ __device__ __forceinline__ void op_load(const Ctx<Elem>& c, Elem (&v)[32], int f
   for (int q = 0; q < 16; q++) load16(p + reg_off(ad, q), v[2 * q], v[2 * q + 1]);
 }
 
+// Pulls the 1024 128-byte rows of a LATER tile (the one the next CTA scheduled on this SM will most
+// likely own) from HBM into L2, so that its loads overlap this tile's arithmetic.  One CTA per SM
+// cannot overlap its own load and compute phases; the L2 (126 MB) is the staging buffer instead.
+template <typename Elem>
+__device__ __forceinline__ void prefetch_later_tile(const Ctx<Elem>& c) {
+  const TilePass& P = *c.P;
+  if (P.prefetch_dist <= 0) return;
+  const unsigned long long id = c.id + (unsigned)P.prefetch_dist;
+  if (id >= c.total) return;
+  const unsigned ntile = (unsigned)(id % c.ntiles), npoint = (unsigned)(id / c.ntiles);
+  const size_t nbase = tile_base(P, ntile);
+  const Elem* st = c.state0 + (size_t)npoint * c.point_stride;
+#pragma unroll
+  for (int k = 0; k < 2; k++) {
+    const unsigned row = threadIdx.x + k * TILE_THREADS;  // 10 bits: tile-local bits 4..13
+    size_t e = nbase;
+#pragma unroll
+    for (int j = 0; j < 10; j++) e += (size_t)((row >> j) & 1u) << P.pos[4 + j];
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(st + e));
+  }
+}
+
 template <typename Elem>
 __device__ __forceinline__ void op_store(const Ctx<Elem>& c, Elem (&v)[32], int frame) {
   TileAddr ad = tile_addr(*c.P, c.base, frame, c.warp, c.lane);
@@ -418,32 +452,84 @@ __device__ __forceinline__ void op_reduce(const Ctx<Elem>& c, Elem (&v)[32], int
   double r5[5] = {(double)s0, (double)s1, (double)s2, kmin, kmax};
   block_reduce5(r5, reinterpret_cast<double*>(c.smem + TILE_EXCH_BYTES + 4096));
   if (threadIdx.x == 0) {
-    double* o = c.partials + ((size_t)c.point * gridDim.x + c.tile) * 5;
+    double* o = c.partials + ((size_t)c.point * c.ntiles + c.tile) * 5;
 #pragma unroll
     for (int i = 0; i < 5; i++) o[i] = r5[i];
   }
 }
 
 template <typename Elem>
+__device__ __forceinline__ void ctx_set_tile(Ctx<Elem>& c, unsigned long long id) {
+  const TilePass& P = *c.P;
+  c.id = id;
+  c.tile = (unsigned)(id % c.ntiles);
+  c.point = (unsigned)(id / c.ntiles);
+  c.state = c.state0 + (size_t)c.point * c.point_stride;
+  c.tau = c.tau0 + (size_t)c.point * P.tau_stride;
+  c.phs = c.phs0 + (size_t)c.point * P.phs_stride;
+  c.base = tile_base(P, c.tile);
+}
+
+template <typename Elem>
 __device__ __forceinline__ void ctx_init(Ctx<Elem>& c, const TilePass& P, Elem* state, size_t point_stride,
                                          const typename ElemTraits<Elem>::real* tau, const double* phs,
                                          const void* tables, int tables_per_point, const DiagInfo& dinfo,
-                                         double* partials, unsigned char* smem) {
+                                         double* partials, unsigned char* smem, unsigned long long total) {
   c.P = &P;
   c.lane = threadIdx.x & 31;
   c.warp = threadIdx.x >> 5;
-  c.tile = blockIdx.x;
-  c.point = blockIdx.y;
-  c.state = state + (size_t)c.point * point_stride;
-  c.tau = tau + (size_t)c.point * P.tau_stride;
-  c.phs = phs + (size_t)c.point * P.phs_stride;
+  c.ntiles = P.ntiles;
+  c.total = total;
+  c.stride = gridDim.x;
+  c.state0 = state;
+  c.tau0 = tau;
+  c.phs0 = phs;
+  c.point_stride = point_stride;
   c.tables = tables;
   c.tables_per_point = tables_per_point;
   c.dinfo = dinfo;
   c.partials = partials;
-  c.base = tile_base(P, c.tile);
   c.smem = smem;
   ctx_smem_setup(c);
+  ctx_set_tile(c, blockIdx.x);
+}
+
+// ---- staged (software-pipelined) loads for the persistent kernels ---------------------------
+__device__ __forceinline__ void cp_async16(unsigned smem_addr, const void* g) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// issue the asynchronous copies of register pairs 0..TILE_STAGE_PAIRS-1 of tile `id` into this
+// thread's private staging slots
+template <typename Elem>
+__device__ __forceinline__ void stage_issue(const Ctx<Elem>& c, unsigned long long id, int frame) {
+  if (id < c.total) {
+    const TilePass& P = *c.P;
+    const unsigned ntile = (unsigned)(id % c.ntiles), npoint = (unsigned)(id / c.ntiles);
+    TileAddr ad = tile_addr(P, tile_base(P, ntile), frame, c.warp, c.lane);
+    const Elem* p = c.state0 + (size_t)npoint * c.point_stride + ad.e0;
+    const unsigned slot0 = (unsigned)__cvta_generic_to_shared(c.smem + TILE_STAGE_OFFSET) + threadIdx.x * 16u;
+#pragma unroll
+    for (int q = 0; q < TILE_STAGE_PAIRS; q++) cp_async16(slot0 + q * (TILE_THREADS * 16), p + reg_off(ad, q));
+  }
+  cp_async_commit();
+}
+
+// persistent-kernel load: pairs >= TILE_STAGE_PAIRS straight from global memory, the others from
+// the staging slots filled during the previous tile; then the next tile's staging is issued.
+template <typename Elem>
+__device__ __forceinline__ void op_load_staged(const Ctx<Elem>& c, Elem (&v)[32], int frame) {
+  TileAddr ad = tile_addr(*c.P, c.base, frame, c.warp, c.lane);
+  const Elem* p = c.state + ad.e0;
+#pragma unroll
+  for (int q = TILE_STAGE_PAIRS; q < 16; q++) load16(p + reg_off(ad, q), v[2 * q], v[2 * q + 1]);
+  cp_async_wait_all();
+  const Elem* slot0 = reinterpret_cast<const Elem*>(c.smem + TILE_STAGE_OFFSET + threadIdx.x * 16);
+#pragma unroll
+  for (int q = 0; q < TILE_STAGE_PAIRS; q++) load16(slot0 + q * (TILE_THREADS * 2), v[2 * q], v[2 * q + 1]);
+  stage_issue<Elem>(c, c.id + c.stride, frame);
 }
 
 // ---- interpreter kernel -------------------------------------------------------------------
@@ -455,14 +541,15 @@ tile_pass_kernel(const __grid_constant__ TilePass P, Elem* __restrict__ state, s
                  double* __restrict__ partials) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   Ctx<Elem> c;
-  ctx_init<Elem>(c, P, state, point_stride, tau, phs, tables, tables_per_point, dinfo, partials, smem_raw);
+  ctx_init<Elem>(c, P, state, point_stride, tau, phs, tables, tables_per_point, dinfo, partials, smem_raw,
+                 (unsigned long long)gridDim.x);
   Elem v[32];
   TileOp op = P.ops[0];
   for (int io = 0; io < P.nops; io++) {
     const TileOp cur = op;
     if (io + 1 < P.nops) op = P.ops[io + 1];  // fetch the next step early (constant-bank latency)
     switch (cur.type) {
-      case TOP_LOAD: op_load<Elem>(c, v, cur.frame); break;
+      case TOP_LOAD: op_load<Elem>(c, v, cur.frame); prefetch_later_tile<Elem>(c); break;
       case TOP_STORE: op_store<Elem>(c, v, cur.frame); break;
       case TOP_INIT: op_init<Elem>(c, v, cur.frame); break;
       case TOP_PHASE: op_phase<Elem, 0>(c, v, cur.arg); break;
@@ -533,7 +620,7 @@ struct ProgExec {
   static __device__ __forceinline__ void run(const Ctx<Elem>& c, Elem (&v)[32]) {
     if constexpr (I < Prog::N) {
       constexpr COp op = Prog::op(I);
-      if constexpr (op.type == TOP_LOAD) op_load<Elem>(c, v, op.frame);
+      if constexpr (op.type == TOP_LOAD) { op_load_staged<Elem>(c, v, op.frame); prefetch_later_tile<Elem>(c); }
       else if constexpr (op.type == TOP_STORE) op_store<Elem>(c, v, op.frame);
       else if constexpr (op.type == TOP_INIT) op_init<Elem>(c, v, op.frame);
       else if constexpr (op.type == TOP_PHASE) op_phase<Elem, DK>(c, v, op.arg);
@@ -554,12 +641,18 @@ __global__ void __launch_bounds__(TILE_THREADS, 1)
 tile_prog_kernel(const __grid_constant__ TilePass P, Elem* __restrict__ state, size_t point_stride,
                  const typename ElemTraits<Elem>::real* __restrict__ tau, const double* __restrict__ phs,
                  const void* __restrict__ tables, int tables_per_point, DiagInfo dinfo,
-                 double* __restrict__ partials) {
+                 double* __restrict__ partials, unsigned n_points) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   Ctx<Elem> c;
-  ctx_init<Elem>(c, P, state, point_stride, tau, phs, tables, tables_per_point, dinfo, partials, smem_raw);
+  const unsigned long long total = (unsigned long long)P.ntiles * n_points;
+  ctx_init<Elem>(c, P, state, point_stride, tau, phs, tables, tables_per_point, dinfo, partials, smem_raw, total);
+  constexpr COp first = Prog::op(0);
+  if constexpr (first.type == TOP_LOAD) stage_issue<Elem>(c, blockIdx.x, first.frame);
   Elem v[32];
-  ProgExec<Elem, Prog, DK, 0>::run(c, v);
+  for (unsigned long long id = blockIdx.x; id < total; id += gridDim.x) {
+    ctx_set_tile(c, id);
+    ProgExec<Elem, Prog, DK, 0>::run(c, v);
+  }
 }
 
 // host-side: does a planned pass match a compiled program exactly?

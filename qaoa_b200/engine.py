@@ -76,6 +76,8 @@ def load_library():
             ctypes.c_int, [H, ctypes.c_int, _c_double_p, ctypes.c_int, ctypes.c_int]),
         "qaoa_fetch_results": (ctypes.c_int, [H, ctypes.c_int, _c_double_p]),
         "qaoa_read_statevector": (ctypes.c_int, [H, _c_double_p]),
+        "qaoa_debug_tile_program": (
+            ctypes.c_int, [H, ctypes.c_int, _c_int32_p, ctypes.c_int, ctypes.c_int, ctypes.c_double, _c_double_p]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -217,3 +219,11 @@ class Engine:
         out = np.empty(2 << self.n_qubits, dtype=np.float64)
         self._check(self._lib.qaoa_read_statevector(self._h, _dptr(out)))
         return out.view(np.complex128)
+
+    def debug_tile_program(self, hb, ops, reps=5, tau=0.1):
+        """Profiling hook: mean ms per launch of an arbitrary (type, frame, mask) step program."""
+        arr = np.ascontiguousarray(ops, dtype=np.int32).reshape(-1)
+        ms = ctypes.c_double()
+        self._check(self._lib.qaoa_debug_tile_program(self._h, int(hb), arr.ctypes.data_as(_c_int32_p), arr.size // 3,
+                                                      int(reps), float(tau), ctypes.byref(ms)))
+        return ms.value
