@@ -109,6 +109,7 @@ struct Engine {
   int force_generic = 0;
   int prefetch_dist = 0;     // extra L2 prefetch distance in tiles (0 = off)
   int persistent_ctas = 148; // CTAs of the persistent pass kernels (one per SM)
+  int low_bits = 0;          // 0: automatic choice between 4 and 5 low tile bits
   double* d_partials = nullptr; size_t partials_cap = 0;
   double* d_out = nullptr; size_t out_cap = 0;
   double* h_out = nullptr; size_t hout_cap = 0;
@@ -185,15 +186,23 @@ Plan build_plan(Engine* h, int p) {
   pl.p = p;
   const int E = h->E, qs = h->qshift;
   if (E < TILE_BITS) fail("tile path needs at least 14 element bits");
-  const int nH = E - 4;
-  const int m = std::max(1, (nH + 9) / 10);
+  // c low bits ride along in every tile (rows of 2^c * 8 bytes).  256-byte rows (c = 5) run at full
+  // DRAM speed at every stride, 128-byte rows lose ~15 % at the largest strides; use c = 5 whenever it
+  // does not cost an extra pass per layer.
+  const int m4 = std::max(1, (E - 4 + 9) / 10), m5 = std::max(1, (E - 5 + 8) / 9);
+  int clow = (m5 == m4 && E >= 15) ? 5 : 4;
+  if (h->low_bits == 4 || h->low_bits == 5) clow = h->low_bits;
+  const int hper = TILE_BITS - clow;
+  const int nH = E - clow;
+  const int m = std::max(1, (nH + hper - 1) / hper);
   for (int i = 0; i < m; i++) {
-    std::vector<int> bits = {0, 1, 2, 3};
-    int lo = 4 + 10 * i, hi = std::min(E, lo + 10);
+    std::vector<int> bits;
+    for (int b = 0; b < clow; b++) bits.push_back(b);
+    int lo = clow + hper * i, hi = std::min(E, lo + hper);
     std::vector<int> own;
     for (int b = lo; b < hi; b++) own.push_back(b);
     int padb = lo - 1;
-    while ((int)own.size() < 10) { own.push_back(padb); padb--; }
+    while ((int)own.size() < hper) { own.push_back(padb); padb--; }
     for (int b : own) bits.push_back(b);
     std::sort(bits.begin(), bits.end());
     Shape s;
@@ -259,6 +268,7 @@ Plan build_plan(Engine* h, int p) {
       for (int j = 0; j < TILE_BITS; j++) {
         int b = sh.pos[j];
         if (b >= qs && !done[cur][b]) { need[j] = 1; nneed++; if (j < 4) need_low = true; }
+        // (with 5 low bits, tile bit 4 is reached by the high cover's lane round as well)
       }
       if (nneed == 0) break;
       if (phase_pending) {
@@ -833,6 +843,7 @@ int qaoa_set_option(qaoa_engine_t* h, const char* key, double value) {
   else if (k == "force_generic") h->force_generic = value != 0;
   else if (k == "prefetch_dist") h->prefetch_dist = (int)value;
   else if (k == "persistent_ctas") h->persistent_ctas = std::max(1, (int)value);
+  else if (k == "low_bits") { h->low_bits = (int)value; free_streams(h); invalidate(h); }
   else fail("unknown option: " + k);
   API_END(h)
 }

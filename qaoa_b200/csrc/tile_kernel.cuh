@@ -125,19 +125,28 @@ __device__ __forceinline__ size_t tile_base(const TilePass& P, unsigned tile) {
   return base;
 }
 
-__device__ __forceinline__ TileAddr tile_addr(const TilePass& P, size_t base, int frame, int warp, int lane) {
-  TileAddr a;
-  size_t e = base;
+// element offset contributed by this thread's lane and warp bits in the given frame
+__device__ __forceinline__ size_t thread_off(const TilePass& P, int frame, int warp, int lane) {
+  size_t e = 0;
 #pragma unroll
   for (int j = 0; j < 5; j++) e += (size_t)((lane >> j) & 1) << P.pos[1 + j];
-  const int wofs = frame == 0 ? 6 : 10, rofs = frame == 0 ? 10 : 6;
+  const int wofs = frame == 0 ? 6 : 10;
 #pragma unroll
-  for (int j = 0; j < 4; j++) {
-    e += (size_t)((warp >> j) & 1) << P.pos[wofs + j];
-    a.roff[j] = (size_t)1 << P.pos[rofs + j];
-  }
-  a.e0 = e;
+  for (int j = 0; j < 4; j++) e += (size_t)((warp >> j) & 1) << P.pos[wofs + j];
+  return e;
+}
+
+__device__ __forceinline__ TileAddr tile_addr_off(const TilePass& P, size_t base, int frame, size_t thr) {
+  TileAddr a;
+  const int rofs = frame == 0 ? 10 : 6;
+#pragma unroll
+  for (int j = 0; j < 4; j++) a.roff[j] = (size_t)1 << P.pos[rofs + j];
+  a.e0 = base + thr;
   return a;
+}
+
+__device__ __forceinline__ TileAddr tile_addr(const TilePass& P, size_t base, int frame, int warp, int lane) {
+  return tile_addr_off(P, base, frame, thread_off(P, frame, warp, lane));
 }
 
 __device__ __forceinline__ size_t reg_off(const TileAddr& a, int q) {
@@ -175,6 +184,7 @@ struct Ctx {
   unsigned char* smem;
   // hoisted shared-memory byte addresses (see warp_transpose / block_transpose)
   unsigned wt_st, wt_ld, bt_st, bt_ld;
+  size_t thr[2];   // hoisted per-thread element offsets for frames A and B
 };
 
 template <typename Elem>
@@ -191,6 +201,8 @@ __device__ __forceinline__ void ctx_smem_setup(Ctx<Elem>& c) {
   c.bt_st ^= (hi & 7u) << 4;
   // read chunk (lane + 32 q + 512 warp) ^ (warp & 7)
   c.bt_ld = ((lane ^ (warp & 7u)) + 512u * warp) * 16u;
+  c.thr[0] = thread_off(*c.P, 0, c.warp, c.lane);
+  c.thr[1] = thread_off(*c.P, 1, c.warp, c.lane);
 }
 
 // ---- transposes ---------------------------------------------------------------------------
@@ -331,7 +343,7 @@ __device__ __forceinline__ void for_each_diag(const void* stream, int kind, unsi
 // ---- the steps ----------------------------------------------------------------------------
 template <typename Elem>
 __device__ __forceinline__ void op_load(const Ctx<Elem>& c, Elem (&v)[32], int frame) {
-  TileAddr ad = tile_addr(*c.P, c.base, frame, c.warp, c.lane);
+  TileAddr ad = tile_addr_off(*c.P, c.base, frame, c.thr[frame]);
   const Elem* p = c.state + ad.e0;
 #pragma unroll
   for (int q = 0; q < 16; q++) load16(p + reg_off(ad, q), v[2 * q], v[2 * q + 1]);
@@ -361,7 +373,7 @@ __device__ __forceinline__ void prefetch_later_tile(const Ctx<Elem>& c) {
 
 template <typename Elem>
 __device__ __forceinline__ void op_store(const Ctx<Elem>& c, Elem (&v)[32], int frame) {
-  TileAddr ad = tile_addr(*c.P, c.base, frame, c.warp, c.lane);
+  TileAddr ad = tile_addr_off(*c.P, c.base, frame, c.thr[frame]);
   Elem* p = c.state + ad.e0;
 #pragma unroll
   for (int q = 0; q < 16; q++) store16(p + reg_off(ad, q), v[2 * q], v[2 * q + 1]);
@@ -372,7 +384,7 @@ __device__ __forceinline__ void op_init(const Ctx<Elem>& c, Elem (&v)[32], int f
   typedef typename ElemTraits<Elem>::real real;
   constexpr int NAMP = ElemTraits<Elem>::NAMP;
   const TilePass& P = *c.P;
-  TileAddr ad = tile_addr(P, c.base, frame, c.warp, c.lane);
+  TileAddr ad = tile_addr_off(P, c.base, frame, c.thr[frame]);
   const real A = (real)P.init_amp;
   const int pc0 = __popcll((unsigned long long)(ad.e0 >> P.qshift));
 #pragma unroll
@@ -501,35 +513,44 @@ __device__ __forceinline__ void cp_async16(unsigned smem_addr, const void* g) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-// issue the asynchronous copies of register pairs 0..TILE_STAGE_PAIRS-1 of tile `id` into this
-// thread's private staging slots
-template <typename Elem>
+// Asynchronous copies of register pairs [Q0, Q1) of tile `id` into this thread's private slots.
+// Pairs < TILE_STAGE_PAIRS live in the dedicated staging area ("early" group, issued right after the
+// current tile has been pulled into registers); the remaining pairs use the first 40 KB of the
+// exchange buffer ("late" group, issued once the tile's last transpose is done with that buffer).
+template <typename Elem, int Q0, int Q1>
 __device__ __forceinline__ void stage_issue(const Ctx<Elem>& c, unsigned long long id, int frame) {
   if (id < c.total) {
     const TilePass& P = *c.P;
     const unsigned ntile = (unsigned)(id % c.ntiles), npoint = (unsigned)(id / c.ntiles);
-    TileAddr ad = tile_addr(P, tile_base(P, ntile), frame, c.warp, c.lane);
+    TileAddr ad = tile_addr_off(P, tile_base(P, ntile), frame, c.thr[frame]);
     const Elem* p = c.state0 + (size_t)npoint * c.point_stride + ad.e0;
-    const unsigned slot0 = (unsigned)__cvta_generic_to_shared(c.smem + TILE_STAGE_OFFSET) + threadIdx.x * 16u;
+    const unsigned sb = (unsigned)__cvta_generic_to_shared(c.smem);
+    const unsigned early = sb + TILE_STAGE_OFFSET + threadIdx.x * 16u;
+    // late slots sit inside the OWNING warp's 8 KB transpose region, so the only writers that can
+    // touch them before they are consumed are the warp's own (program-ordered) transposes
+    const unsigned late = sb + c.warp * 8192u + c.lane * 16u;
 #pragma unroll
-    for (int q = 0; q < TILE_STAGE_PAIRS; q++) cp_async16(slot0 + q * (TILE_THREADS * 16), p + reg_off(ad, q));
+    for (int q = Q0; q < Q1; q++) {
+      const unsigned dst = q < TILE_STAGE_PAIRS ? early + q * (TILE_THREADS * 16) : late + (q - TILE_STAGE_PAIRS) * 512;
+      cp_async16(dst, p + reg_off(ad, q));
+    }
   }
   cp_async_commit();
 }
 
-// persistent-kernel load: pairs >= TILE_STAGE_PAIRS straight from global memory, the others from
-// the staging slots filled during the previous tile; then the next tile's staging is issued.
+// persistent-kernel load: every register pair comes from the slots filled during the previous tile
 template <typename Elem>
 __device__ __forceinline__ void op_load_staged(const Ctx<Elem>& c, Elem (&v)[32], int frame) {
-  TileAddr ad = tile_addr(*c.P, c.base, frame, c.warp, c.lane);
-  const Elem* p = c.state + ad.e0;
-#pragma unroll
-  for (int q = TILE_STAGE_PAIRS; q < 16; q++) load16(p + reg_off(ad, q), v[2 * q], v[2 * q + 1]);
   cp_async_wait_all();
-  const Elem* slot0 = reinterpret_cast<const Elem*>(c.smem + TILE_STAGE_OFFSET + threadIdx.x * 16);
+  const unsigned char* early = c.smem + TILE_STAGE_OFFSET + threadIdx.x * 16;
+  const unsigned char* late = c.smem + c.warp * 8192 + c.lane * 16;
 #pragma unroll
-  for (int q = 0; q < TILE_STAGE_PAIRS; q++) load16(slot0 + q * (TILE_THREADS * 2), v[2 * q], v[2 * q + 1]);
-  stage_issue<Elem>(c, c.id + c.stride, frame);
+  for (int q = 0; q < 16; q++) {
+    const unsigned char* src = q < TILE_STAGE_PAIRS ? early + q * (TILE_THREADS * 16) : late + (q - TILE_STAGE_PAIRS) * 512;
+    load16(reinterpret_cast<const Elem*>(src), v[2 * q], v[2 * q + 1]);
+  }
+  __syncwarp();
+  stage_issue<Elem, 0, TILE_STAGE_PAIRS>(c, c.id + c.stride, frame);
 }
 
 // ---- interpreter kernel -------------------------------------------------------------------
@@ -573,6 +594,7 @@ constexpr int M_ALL = 0x1f, M_HI4 = 0x1e, M_TOP2 = 0x18;
 //   R(all) WT R(all) BT R(hi4)
 // high cover of the 10 upper tile bits:  R(hi4) WT R(top2) BT R(hi4)
 struct ProgFirstInit {  // |+>/Dicke generated in registers, phase 1, full layer-1 cover of the tile
+  static constexpr int last_bt() { int k = -1; for (int i = 0; i < N; i++) if (op(i).type == TOP_BT) k = i; return k; }
   static constexpr int N = 8;
   static constexpr COp op(int i) {
     constexpr COp o[N] = {{TOP_INIT, 0, 0, 0}, {TOP_PHASE, 0, 0, 0}, {TOP_ROUND, 0, 0, M_ALL}, {TOP_WT, 0, 0, 0},
@@ -581,6 +603,7 @@ struct ProgFirstInit {  // |+>/Dicke generated in registers, phase 1, full layer
   }
 };
 struct ProgFirstLoad {
+  static constexpr int last_bt() { int k = -1; for (int i = 0; i < N; i++) if (op(i).type == TOP_BT) k = i; return k; }
   static constexpr int N = 8;
   static constexpr COp op(int i) {
     constexpr COp o[N] = {{TOP_LOAD, 0, 0, 0}, {TOP_PHASE, 0, 0, 0}, {TOP_ROUND, 0, 0, M_ALL}, {TOP_WT, 0, 0, 0},
@@ -589,6 +612,7 @@ struct ProgFirstLoad {
   }
 };
 struct ProgInterior {
+  static constexpr int last_bt() { int k = -1; for (int i = 0; i < N; i++) if (op(i).type == TOP_BT) k = i; return k; }
   static constexpr int N = 7;
   static constexpr COp op(int i) {
     constexpr COp o[N] = {{TOP_LOAD, 0, 0, 0}, {TOP_ROUND, 0, 0, M_HI4}, {TOP_WT, 0, 0, 0}, {TOP_ROUND, 0, 1, M_TOP2},
@@ -597,6 +621,7 @@ struct ProgInterior {
   }
 };
 struct ProgBoundary {
+  static constexpr int last_bt() { int k = -1; for (int i = 0; i < N; i++) if (op(i).type == TOP_BT) k = i; return k; }
   static constexpr int N = 13;
   static constexpr COp op(int i) {
     constexpr COp o[N] = {{TOP_LOAD, 0, 0, 0}, {TOP_ROUND, 0, 0, M_HI4}, {TOP_WT, 0, 0, 0}, {TOP_ROUND, 0, 1, M_TOP2},
@@ -607,6 +632,7 @@ struct ProgBoundary {
   }
 };
 struct ProgFinal {
+  static constexpr int last_bt() { int k = -1; for (int i = 0; i < N; i++) if (op(i).type == TOP_BT) k = i; return k; }
   static constexpr int N = 7;
   static constexpr COp op(int i) {
     constexpr COp o[N] = {{TOP_LOAD, 0, 0, 0}, {TOP_ROUND, 0, 0, M_HI4}, {TOP_WT, 0, 0, 0}, {TOP_ROUND, 0, 1, M_TOP2},
@@ -629,7 +655,13 @@ struct ProgExec {
         round_static<Elem, op.mask>(c, v, op.arg);
       }
       else if constexpr (op.type == TOP_WT) warp_transpose<Elem>(c, v);
-      else if constexpr (op.type == TOP_BT) block_transpose<Elem>(c, v);
+      else if constexpr (op.type == TOP_BT) {
+        block_transpose<Elem>(c, v);
+        if constexpr (Prog::op(0).type == TOP_LOAD && I == Prog::last_bt()) {
+          __syncthreads();  // every warp has read its share of the exchange buffer
+          stage_issue<Elem, TILE_STAGE_PAIRS, 16>(c, c.id + c.stride, Prog::op(0).frame);
+        }
+      }
       else if constexpr (op.type == TOP_REDUCE) op_reduce<Elem, DK>(c, v, op.arg);
       ProgExec<Elem, Prog, DK, I + 1>::run(c, v);
     }
@@ -647,7 +679,10 @@ tile_prog_kernel(const __grid_constant__ TilePass P, Elem* __restrict__ state, s
   const unsigned long long total = (unsigned long long)P.ntiles * n_points;
   ctx_init<Elem>(c, P, state, point_stride, tau, phs, tables, tables_per_point, dinfo, partials, smem_raw, total);
   constexpr COp first = Prog::op(0);
-  if constexpr (first.type == TOP_LOAD) stage_issue<Elem>(c, blockIdx.x, first.frame);
+  if constexpr (first.type == TOP_LOAD) {
+    stage_issue<Elem, 0, TILE_STAGE_PAIRS>(c, blockIdx.x, first.frame);
+    stage_issue<Elem, TILE_STAGE_PAIRS, 16>(c, blockIdx.x, first.frame);
+  }
   Elem v[32];
   for (unsigned long long id = blockIdx.x; id < total; id += gridDim.x) {
     ctx_set_tile(c, id);
