@@ -1,0 +1,263 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 QAOA engine (contract in the task statement).
+
+Workload (BASELINE.json metric "ms per QAOA energy eval (MaxCut n=32,p=5)"): MaxCut on
+nx.random_regular_graph(3, n, seed=42), X mixer, |+> initial state, depth p=5, complex64
+statevector.  One step = one energy evaluation <gamma,beta|H_P|gamma,beta>.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--n 32] [--p 5] [--impl reference]
+
+N = 1 : n = 32 on one B200 (32 GiB state, far larger than the 126 MB L2: nothing to flush).
+N > 1 : launched under torchrun, one rank per GPU; WEAK scaling: every rank evaluates the same
+        n = 32 register with its own angle vector (independent replicas: the landscape/optimizer
+        workloads of the reference shard over evaluations with no data-path collective).  The
+        sharded single-state path (n = 33..36) is reported by scripts/bench_sharded.py.
+--impl reference : times the CPU restatement of the reference path (oracle/c/qaoa_ref.c, OpenMP over
+        the host cores) on a bounded sample (smaller n) and scales it to the workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "ms_per_energy_eval_maxcut_n32_p5"
+UNIT = "ms"
+
+
+def workload(n):
+    import networkx as nx
+    from qaoa_b200.utils.graphutils import GraphHandler
+
+    G = nx.random_regular_graph(3, n, seed=42)
+    gh = GraphHandler(G, check_isomorphism=False)
+    return gh.edge_list()
+
+
+def angles_for(p, seed):
+    return np.random.default_rng(seed).uniform(0, 2 * np.pi, size=2 * p)
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.stop_flag = False
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [x.strip() for x in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [nm for i, nm in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
+                "samples": len(sm)}
+
+
+def run_reference(args, rank):
+    """CPU arm: oracle/c/qaoa_ref.c on the host cores, bounded sample, scaled to the workload."""
+    if rank != 0:
+        return
+    from oracle import c_oracle
+
+    c_oracle.build()
+    ns = args.cpu_n
+    edges = workload(ns)
+    diag = c_oracle.maxcut_diag(ns, edges)
+    ang = angles_for(args.p, 1234)
+    for _ in range(max(1, min(args.warmup, 1))):
+        c_oracle.energy(ns, diag, ang, "complex64")
+    ts = []
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        c_oracle.energy(ns, diag, ang, "complex64")
+        ts.append(time.perf_counter() - t0)
+    ms_sample = 1e3 * sum(ts) / len(ts)
+    scale = (2.0 ** args.n * args.n) / (2.0 ** ns * ns)   # work ~ 2^n amplitudes x (n + 1) sweeps per layer
+    value = ms_sample * scale
+    cores = c_oracle.num_threads()
+    sample = ("n=%d (1/%d of the amplitudes), p=%d, complex64, %.1f ms/eval measured, scaled by 2^n*n to n=%d "
+              "(n=%d needs 2 x 32 GiB of host memory)" % (ns, 2 ** (args.n - ns), args.p, ms_sample, args.n, args.n))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_sample, "higher_is_better": False, "scaling": "weak",
+        "vs_baseline": None, "dtype": "c64", "data": "synthetic",
+        "config": {"workload": "MaxCut 3-regular n=%d seed=42, X mixer, Plus, p=%d, complex64" % (args.n, args.p),
+                   "reference_arm": "CPU restatement of the reference path (qiskit-aer itself is not installable: "
+                                    "no network); OpenMP over %d host threads" % cores},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--n", type=int, default=32)
+    ap.add_argument("--p", type=int, default=5)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--cpu-n", type=int, default=26, dest="cpu_n")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from qaoa_b200 import engine as eng
+
+    n, p = args.n, args.p
+    edges = workload(n)
+    E = eng.Engine(n, "complex64", device=local_rank)
+    E.set_cost_maxkcut(n, edges, 1, np.array([0, 1], dtype=np.uint8))
+    ang = angles_for(p, 1234 + rank)
+    E.set_option("time_passes", 1)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident metric: CUDA-event time of the evaluation's kernels -------------------
+    for _ in range(args.warmup):
+        E.energy(ang)
+    E.counter("reset")
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    dev_ms = []
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        E.energy_batch_resident(ang[None, :])
+        dev_ms.append(E.counter("last_device_ms"))
+    barrier()
+    wall_resident = time.perf_counter() - t0
+    launches = E.counter("launches")
+    pass_stats = {i: (E.counter("pass_ms_%d" % i), E.counter("pass_count_%d" % i), E.counter("pass_bytes_%d" % i))
+                  for i in range(6)}
+    out = E.fetch_results(1)[0]
+
+    # ---- end to end through the public API: host angles in, host result out ----------------------
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res = E.energy(ang)
+    barrier()
+    wall_e2e = time.perf_counter() - t0
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    ms_dev = float(np.mean(dev_ms))
+    ms_e2e = 1e3 * wall_e2e / args.steps
+    if world > 1:
+        t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_dev, ms_e2e = float(t[0]), float(t[1])
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        names = {0: "tile_pass_kernel (interpreter)", 1: "tile_prog_kernel<ProgFirstInit>", 2: "tile_prog_kernel<ProgFirstLoad>",
+                 3: "tile_prog_kernel<ProgInterior>", 4: "tile_prog_kernel<ProgBoundary>", 5: "tile_prog_kernel<ProgFinal>"}
+        dom = max(pass_stats, key=lambda i: pass_stats[i][0])
+        d_ms, d_cnt, d_bytes = pass_stats[dom]
+        achieved = (d_bytes / d_cnt) / (d_ms / d_cnt * 1e-3) / 1e9 if d_cnt else 0.0
+        total_pass_ms = sum(v[0] for v in pass_stats.values())
+        total_bytes = sum(v[2] for v in pass_stats.values())
+        # the survey's pass model: s * 2^n * (2 p P - 2), P = ceil((n-4)/10)
+        P = max(1, -(-(n - 4) // 10))
+        survey_bytes = 8.0 * 2.0 ** n * (2 * p * P - 2)
+        line = {
+            "metric": METRIC, "value": ms_dev, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_dev, "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
+            "dtype": "c64", "data": "synthetic",
+            "config": {"workload": "MaxCut 3-regular n=%d seed=42, X mixer, Plus, p=%d, complex64; 1 step = 1 energy "
+                                   "evaluation; replicas per GPU when n_gpus > 1" % (n, p),
+                       "l2": "state is %d GiB >> 126 MB L2, no flush needed" % (8 * 2 ** n >> 30),
+                       "energy": float(-out[0]), "norm": float(out[4])},
+            "e2e": {"value": ms_e2e, "unit": UNIT, "h2d_bytes_per_step": int(ang.nbytes), "d2h_bytes_per_step": 40,
+                    "api": "qaoa_energy (C ABI via ctypes): host angle vector in, host {E,E2,min,max,norm} out"},
+            "gpu_launches": int(launches),
+            "clocks": sampler.summary(),
+            "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
+                         "launches_timed": int(d_cnt), "ms_per_launch": d_ms / d_cnt if d_cnt else None,
+                         "kernel_share_of_step": d_ms / total_pass_ms if total_pass_ms else None,
+                         "whole_eval_actual_gbs": total_bytes / (total_pass_ms * 1e-3) / 1e9 if total_pass_ms else None,
+                         "survey_model_bytes_per_eval": survey_bytes,
+                         "survey_model_gbs": survey_bytes / (ms_dev * 1e-3) / 1e9,
+                         "survey_model_frac_of_8TBps": survey_bytes / (ms_dev * 1e-3) / 8e12},
+            "passes": {names[i]: {"ms_total": v[0], "launches": int(v[1])} for i, v in pass_stats.items() if v[1]},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            from oracle import c_oracle
+            try:
+                c_oracle.build()
+                ns = args.cpu_n
+                cdiag = c_oracle.maxcut_diag(ns, workload(ns))
+                c_oracle.energy(ns, cdiag, ang, "complex64")
+                t0 = time.perf_counter()
+                reps = 3
+                for _ in range(reps):
+                    c_oracle.energy(ns, cdiag, ang, "complex64")
+                ms_s = 1e3 * (time.perf_counter() - t0) / reps
+                scale = (2.0 ** n * n) / (2.0 ** ns * ns)
+                line["cpu_baseline"] = {
+                    "value": ms_s * scale, "unit": UNIT, "cores": c_oracle.num_threads(), "kind": "port",
+                    "sample": "n=%d p=%d complex64: %.1f ms/eval measured on the host cores, scaled by 2^n*n to n=%d"
+                              % (ns, p, ms_s, n)}
+            except Exception as exc:  # noqa: BLE001
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % exc}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

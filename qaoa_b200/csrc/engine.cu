@@ -2,6 +2,7 @@
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <map>
@@ -128,6 +129,14 @@ struct Engine {
   double launches = 0;
   double prog_launches = 0;
   double bytes_alg = 0;
+  // optional CUDA-event timing of every pass launch, accumulated per program id
+  int time_passes = 0;
+  double pass_ms[8] = {0}, pass_count[8] = {0}, pass_bytes[8] = {0};
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
+  struct PendingEv { int prog; size_t idx; double bytes; };
+  std::vector<PendingEv> ev_pending;
+  double last_device_ms = 0;
+  cudaEvent_t ev_call0 = nullptr, ev_call1 = nullptr;
   std::string err;
 
   int small_max() const {
@@ -566,13 +575,29 @@ void run_tile_chunk(Engine* h, Plan& pl, const double* angles, int n_angles, int
     const bool use_prog = all_normal[ip] && !h->force_generic;
     const void* d_tau = db + tbase * rsz;
     const double* d_phs = (const double*)(db + tau_bytes) + pbase;
+    bool reads = pp.tp.ops[0].type == TOP_LOAD, writes = pp.tp.ops[pp.tp.nops - 1].type == TOP_STORE;
+    const double pass_bytes = (double)Bc * (double)h->N * h->amp_bytes * ((reads ? 1 : 0) + (writes ? 1 : 0)) +
+        (double)Bc * (double)h->N * diag_value_bytes(h->dinfo.kind) * (pp.phases.size() + (pp.has_reduce ? 1 : 0));
+    size_t evi = 0;
+    if (h->time_passes) {
+      evi = h->ev_pending.size();
+      while (h->ev_pool.size() <= evi) {
+        cudaEvent_t a, b;
+        CUDA_OK(cudaEventCreate(&a));
+        CUDA_OK(cudaEventCreate(&b));
+        h->ev_pool.push_back({a, b});
+      }
+      CUDA_OK(cudaEventRecord(h->ev_pool[evi].first, h->stream));
+    }
     if (c64) launch_pass<float2>(h, pp, use_prog, ntiles, Bc, point_stride_elems, d_tau, d_phs, p);
     else launch_pass<double>(h, pp, use_prog, ntiles, Bc, point_stride_elems, d_tau, d_phs, p);
+    if (h->time_passes) {
+      CUDA_OK(cudaEventRecord(h->ev_pool[evi].second, h->stream));
+      h->ev_pending.push_back({use_prog ? pp.prog : (int)PROG_GENERIC, evi, pass_bytes});
+    }
     h->launches += 1;
     if (use_prog && pp.prog != PROG_GENERIC) h->prog_launches += 1;
-    bool reads = pp.tp.ops[0].type == TOP_LOAD, writes = pp.tp.ops[pp.tp.nops - 1].type == TOP_STORE;
-    h->bytes_alg += (double)Bc * (double)h->N * h->amp_bytes * ((reads ? 1 : 0) + (writes ? 1 : 0));
-    h->bytes_alg += (double)Bc * (double)h->N * diag_value_bytes(h->dinfo.kind) * (pp.phases.size() + (pp.has_reduce ? 1 : 0));
+    h->bytes_alg += pass_bytes;
     tbase += (size_t)pp.tp.tau_stride * Bc;
     pbase += (size_t)pp.tp.phs_stride * Bc;
   }
@@ -674,9 +699,35 @@ void check_ready(Engine* h, int p, int n_angles) {
   if ((h->mixer == MIXER_XY) && h->pairs.empty()) fail("XY mixer without pairs");
 }
 
+void energy_batch_body(Engine* h, int p, const double* angles, int n_angles, int B);
+
+// collects the per-pass event timings once the stream has drained
+void harvest_events(Engine* h) {
+  for (auto& pe : h->ev_pending) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, h->ev_pool[pe.idx].first, h->ev_pool[pe.idx].second) == cudaSuccess) {
+      h->pass_ms[pe.prog] += ms;
+      h->pass_count[pe.prog] += 1;
+      h->pass_bytes[pe.prog] += pe.bytes;
+    }
+  }
+  h->ev_pending.clear();
+  float ms = 0;
+  if (h->ev_call0 && cudaEventElapsedTime(&ms, h->ev_call0, h->ev_call1) == cudaSuccess) h->last_device_ms = ms;
+}
+
 void energy_batch_impl(Engine* h, int p, const double* angles, int n_angles, int B) {
   check_ready(h, p, n_angles);
   CUDA_OK(cudaSetDevice(h->device));
+  if (!h->ev_call0) { CUDA_OK(cudaEventCreate(&h->ev_call0)); CUDA_OK(cudaEventCreate(&h->ev_call1)); }
+  // make sure plans / streams exist before the timed region starts
+  if (h->n > h->small_max() && (h->mixer == MIXER_X || h->mixer == MIXER_XMULTI)) get_plan(h, p);
+  CUDA_OK(cudaEventRecord(h->ev_call0, h->stream));
+  energy_batch_body(h, p, angles, n_angles, B);
+  CUDA_OK(cudaEventRecord(h->ev_call1, h->stream));
+}
+
+void energy_batch_body(Engine* h, int p, const double* angles, int n_angles, int B) {
   ensure(h->d_out, h->out_cap, (size_t)B * 5 * sizeof(double));
   const bool small = h->n <= h->small_max();
   if (small) {
@@ -843,6 +894,7 @@ int qaoa_set_option(qaoa_engine_t* h, const char* key, double value) {
   else if (k == "force_generic") h->force_generic = value != 0;
   else if (k == "prefetch_dist") h->prefetch_dist = (int)value;
   else if (k == "persistent_ctas") h->persistent_ctas = std::max(1, (int)value);
+  else if (k == "time_passes") h->time_passes = value != 0;
   else if (k == "low_bits") { h->low_bits = (int)value; free_streams(h); invalidate(h); }
   else fail("unknown option: " + k);
   API_END(h)
@@ -855,7 +907,15 @@ double qaoa_get_counter(qaoa_engine_t* h, const char* key) {
   if (k == "prog_launches") return h->prog_launches;
   if (k == "bytes_alg") return h->bytes_alg;
   if (k == "diag_kind") return h->dinfo.kind;
-  if (k == "reset") { h->launches = 0; h->prog_launches = 0; h->bytes_alg = 0; return 0; }
+  if (k == "reset") {
+    h->launches = 0; h->prog_launches = 0; h->bytes_alg = 0;
+    for (int i = 0; i < 8; i++) { h->pass_ms[i] = 0; h->pass_count[i] = 0; h->pass_bytes[i] = 0; }
+    return 0;
+  }
+  if (k == "last_device_ms") return h->last_device_ms;
+  if (k.rfind("pass_ms_", 0) == 0) { int i = atoi(k.c_str() + 8); return (i >= 0 && i < 8) ? h->pass_ms[i] : -1.0; }
+  if (k.rfind("pass_count_", 0) == 0) { int i = atoi(k.c_str() + 11); return (i >= 0 && i < 8) ? h->pass_count[i] : -1.0; }
+  if (k.rfind("pass_bytes_", 0) == 0) { int i = atoi(k.c_str() + 11); return (i >= 0 && i < 8) ? h->pass_bytes[i] : -1.0; }
   if (k == "n_passes") { double s = 0; for (auto& kv : h->plans) s = (double)kv.second.passes.size(); return s; }
   return -1.0;
 }
@@ -1039,6 +1099,7 @@ int qaoa_energy_batch_resident(qaoa_engine_t* h, int p, const double* angles, in
   if (B < 1 || !angles) fail("empty batch");
   energy_batch_impl(h, p, angles, n_angles, B);
   CUDA_OK(cudaStreamSynchronize(h->stream));
+  harvest_events(h);
   API_END(h)
 }
 
@@ -1056,6 +1117,7 @@ int qaoa_energy_batch(qaoa_engine_t* h, int p, const double* angles, int n_angle
   energy_batch_impl(h, p, angles, n_angles, B);
   CUDA_OK(cudaMemcpyAsync(out, h->d_out, (size_t)B * 5 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CUDA_OK(cudaStreamSynchronize(h->stream));
+  harvest_events(h);
   API_END(h)
 }
 
