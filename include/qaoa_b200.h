@@ -45,7 +45,8 @@ const char* qaoa_last_error(qaoa_engine_t* h);
 /* error text when no handle exists (failed qaoa_create) */
 const char* qaoa_global_error(void);
 
-/* Tunables / test hooks: "small_max_qubits", "keep_state", "batch_points". */
+/* Tunables / test hooks: "small_max_qubits", "keep_state", "batch_points", "batch_bytes",
+ * "force_generic", "prefetch_dist", "persistent_ctas", "low_bits", "time_passes". */
 int qaoa_set_option(qaoa_engine_t* h, const char* key, double value);
 double qaoa_get_counter(qaoa_engine_t* h, const char* key); /* "launches", "bytes_alg", ... */
 
@@ -82,37 +83,19 @@ int qaoa_energy(qaoa_engine_t* h, int p, const double* angles, int n_angles, dou
  * qaoa/qaoa.py:630-662).  angles: B * n_angles doubles; out: B * 5 doubles. */
 int qaoa_energy_batch(qaoa_engine_t* h, int p, const double* angles, int n_angles, int B, double* out);
 
-/* Same as qaoa_energy_batch but angles / out are DEVICE-resident host-visible?  No: they are
- * pinned-host or pageable host pointers as well; this variant only skips the final device->host
- * copy of results and leaves them in the engine (used by bench.py's HBM-resident timing). */
+/* Same evaluation as qaoa_energy_batch, but the B x 5 results stay in device memory until
+ * qaoa_fetch_results is called (bench.py uses it to time the HBM-resident part on its own). */
 int qaoa_energy_batch_resident(qaoa_engine_t* h, int p, const double* angles, int n_angles, int B);
 int qaoa_fetch_results(qaoa_engine_t* h, int B, double* out);
 
 /* Final state of the last qaoa_energy call made with option keep_state=1 (true amplitudes,
  * complex128 interleaved).  Test / debugging aid; 2^n * 16 bytes on the host. */
 int qaoa_read_statevector(qaoa_engine_t* h, double* out);
-/* Draws `shots` basis indices from |psi|^2 of the kept state (replaces backend.run(shots=...) in
- * QAOA.hist, qaoa/qaoa.py:1134-1172). */
-int qaoa_sample(qaoa_engine_t* h, int shots, uint64_t seed, uint64_t* out_idx);
 
-/* ---- sharded (multi-GPU) operation: one engine per rank, state split on the top log2(world)
- * qubits; the host (torch.distributed / NCCL) performs the exchanges between segments. ---------- */
-int qaoa_shard_config(qaoa_engine_t* h, int rank, int world);
-void* qaoa_state_ptr(qaoa_engine_t* h);
-void* qaoa_state2_ptr(qaoa_engine_t* h);
-size_t qaoa_state_bytes(qaoa_engine_t* h);
-int qaoa_shard_begin(qaoa_engine_t* h, int p, const double* angles, int n_angles);
-/* Runs local segment `seg` (0..p); after segment s < p the caller must perform the global<->local
- * qubit swap (all-to-all) from state_ptr into state2_ptr and call qaoa_shard_swap_done. */
-int qaoa_shard_segment(qaoa_engine_t* h, int seg);
-int qaoa_shard_swap_done(qaoa_engine_t* h);
-/* local partial sums {S0,S1,S2,kmin,kmax}; the caller all-reduces (sum,sum,sum,min,max) and calls
- * qaoa_shard_finish to decode them into out[5]. */
-int qaoa_shard_partials(qaoa_engine_t* h, double* out5);
-int qaoa_shard_finish(qaoa_engine_t* h, const double* reduced5, double* out);
-/* CUDA IPC plumbing for the fused gather pass (peer reads over NVLink). */
-int qaoa_ipc_export(qaoa_engine_t* h, int which, unsigned char* handle64);
-int qaoa_ipc_import(qaoa_engine_t* h, int peer_rank, int which, const unsigned char* handle64);
+/* Profiling hook: runs an arbitrary (type, frame, mask) step program of the tiled pass kernel and
+ * returns the mean CUDA-event time per launch (scripts/tile_floor.py). */
+int qaoa_debug_tile_program(qaoa_engine_t* h, int hb, const int32_t* ops, int nops, int reps, double tau_val,
+                            double* ms_out);
 
 #ifdef __cplusplus
 }

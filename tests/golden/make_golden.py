@@ -1,0 +1,93 @@
+"""Generates tests/golden/*.json from the REFERENCE tree (run in the build container only).
+
+The reference package cannot be imported as a whole (structlog / qiskit / qiskit-aer are not
+installable here), but two of its modules are dependency-light and are loaded straight from
+/root/reference by file path: qaoa/utils/graphutils.py (networkx) and qaoa/utils/statistic.py
+(numpy).  Their OUTPUTS, plus the data fields of the reference's ExactCover result fixture, are
+stored as golden vectors; no reference source is copied.
+
+    python tests/golden/make_golden.py
+"""
+import importlib.util
+import json
+import os
+
+import networkx as nx
+import numpy as np
+
+REF = "/root/reference"
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def load(path, name):
+    spec = importlib.util.spec_from_file_location(name, os.path.join(REF, path))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def main():
+    graphutils = load("qaoa/utils/graphutils.py", "ref_graphutils")
+    statistic = load("qaoa/utils/statistic.py", "ref_statistic")
+
+    # ---- GraphHandler relabelling on a family of graphs ------------------------------------------
+    graphs = {}
+    cases = {
+        "regular3_n8_seed42": nx.random_regular_graph(3, 8, seed=42),
+        "regular3_n12_seed7": nx.random_regular_graph(3, 12, seed=7),
+        "regular3_n16_seed42": nx.random_regular_graph(3, 16, seed=42),
+        "barbell": nx.Graph([(0, 1)]),
+        "path3": nx.path_graph(3),
+        "house": nx.house_graph(),
+        "star_relabel": nx.relabel_nodes(nx.star_graph(4), {0: "hub", 1: "a", 2: "b", 3: "c", 4: "d"}),
+        "erdos_n10": nx.gnp_random_graph(10, 0.4, seed=3),
+    }
+    wg = nx.random_regular_graph(3, 10, seed=5)
+    rng = np.random.RandomState(0)
+    for u, v in wg.edges():
+        wg[u][v]["weight"] = float(np.round(rng.rand() * 3, 3))
+    cases["weighted_regular3_n10"] = wg
+    for name, G in cases.items():
+        gh = graphutils.GraphHandler(G)
+        graphs[name] = {
+            "input_nodes": [str(x) for x in G.nodes()],
+            "input_edges": [[str(u), str(v), G[u][v].get("weight", 1)] for u, v in G.edges()],
+            "relabelled_edges": [[int(u), int(v), gh.G[u][v].get("weight", 1)] for u, v in gh.G.edges()],
+            "num_nodes": gh.num_nodes,
+        }
+    with open(os.path.join(OUT, "graphhandler.json"), "w") as f:
+        json.dump(graphs, f, indent=1)
+
+    # ---- Statistic on deterministic sample streams -------------------------------------------------
+    stats = []
+    rng = np.random.RandomState(1)
+    for cvar in (1, 0.5, 0.25):
+        for _ in range(3):
+            k = int(rng.randint(3, 9))
+            values = [float(x) for x in rng.randint(0, 12, size=k)]
+            weights = [int(x) for x in rng.randint(1, 20, size=k)]
+            st = statistic.Statistic(cvar=cvar)
+            for i, (val, w) in enumerate(zip(values, weights)):
+                st.add_sample(val, w, "s%d" % i)
+            stats.append({"cvar": cvar, "values": values, "weights": weights, "E": float(st.get_E()),
+                          "Variance": float(st.get_Variance()), "max": st.get_max(), "min": st.get_min(),
+                          "CVaR": float(st.get_CVaR()), "max_sols": st.get_max_sols(), "min_sols": st.get_min_sols()})
+    with open(os.path.join(OUT, "statistic.json"), "w") as f:
+        json.dump(stats, f, indent=1)
+
+    # ---- ExactCover end-to-end fixture (Dicke + Grover, 8192-shot histograms) ---------------------
+    with open(os.path.join(REF, "examples/ExactCover/data/exact_cover_path_problem_example.json")) as f:
+        ec = json.load(f)
+    keep = {"columns": ec["problem"]["columns"], "weights": ec["problem"]["weights"],
+            "hamming_weight": ec["problem"]["hamming_weight"], "solution": ec["problem"]["solution"],
+            "cvar": ec["qaoa_params"]["cvar"], "depths": {}}
+    for d in ("1", "3", "10"):
+        keep["depths"][d] = {"optimal_angles": ec["qaoa_params"]["depths"][d]["optimal_angles"],
+                             "histogram": ec["qaoa_params"]["depths"][d]["histogram"]}
+    with open(os.path.join(OUT, "exactcover_fixture.json"), "w") as f:
+        json.dump(keep, f, indent=1)
+    print("golden vectors written to", OUT)
+
+
+if __name__ == "__main__":
+    main()

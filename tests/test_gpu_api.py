@@ -1,0 +1,82 @@
+"""GPU: the reference-facing Python API (QAOA class) on the real engine vs the same driver on the
+oracle stand-in: landscapes, optimizer trajectories, Grover/Dicke and multi-angle pipelines."""
+import networkx as nx
+import numpy as np
+import pytest
+
+from qaoa_b200 import QAOA, initialstates, mixers, problems
+from qaoa_b200.utils import COBYLA
+from test_host_api import make
+
+pytestmark = pytest.mark.gpu
+
+
+def both(problem_factory, mixer_factory, init_factory, dtype, **kw):
+    dev = QAOA(problem=problem_factory(), mixer=mixer_factory(), initialstate=init_factory(), dtype=dtype, **kw)
+    ref, _ = make(problem_factory(), mixer=mixer_factory(), init=init_factory(), **kw)
+    return dev, ref
+
+
+@pytest.mark.parametrize("dtype,tol", [("complex128", 1e-9), ("complex64", 1e-4)])
+def test_readme_example_landscape_and_trajectory(dtype, tol):
+    """BASELINE config 1: README quick example (MaxCut 3-regular n=8 seed 42, X, Plus): landscape then
+    optimize to depth 3; the optimizer trajectory must follow the oracle's to the stated tolerance."""
+    G = nx.random_regular_graph(3, 8, seed=42)
+    opt = [COBYLA, {"maxiter": 80, "tol": 1e-5}]
+    dev, ref = both(lambda: problems.MaxCut(G), mixers.X, initialstates.Plus, dtype, optimizer=opt)
+    dev.sample_cost_landscape()
+    ref.sample_cost_landscape()
+    assert dev.Exp_sampled_p1.shape == (20, 20)
+    assert np.allclose(dev.Exp_sampled_p1, ref.Exp_sampled_p1, rtol=tol, atol=tol)
+    assert np.allclose(dev.Var_sampled_p1, ref.Var_sampled_p1, rtol=10 * tol, atol=10 * tol)
+    assert np.array_equal(dev.MaxCost_sampled_p1, ref.MaxCost_sampled_p1)
+    dev.optimize(depth=3)
+    ref.optimize(depth=3)
+    for d in (1, 2, 3):
+        a, b = dev.optimization_results[d], ref.optimization_results[d]
+        m = min(10, len(a.Exp), len(b.Exp))
+        assert np.allclose(a.Exp[:m], b.Exp[:m], rtol=tol, atol=tol), d        # trajectory head
+        assert dev.get_Exp(d) == pytest.approx(ref.get_Exp(d), rel=max(tol, 1e-6), abs=max(tol, 1e-6))
+    if dtype == "complex128":
+        a, b = dev.optimization_results[1], ref.optimization_results[1]
+        assert len(a.Exp) == len(b.Exp) and np.allclose(a.angles, b.angles, atol=1e-7)
+    ok, rep = dev.validate_circuit()
+    assert ok, rep
+
+
+def test_portfolio_grover_dicke_and_multiangle_qubo():
+    """BASELINE config 4 at test size: Portfolio + Grover(Dicke) + Dicke, and QUBO + XMultiAngle + Plus."""
+    rng = np.random.RandomState(0)
+    A = rng.randn(10, 60)
+    cov, mu = np.cov(A), A.mean(axis=1)
+    mk = lambda: problems.PortfolioOptimization(risk=0.5, budget=4, cov_matrix=cov, exp_return=mu, penalty=0)
+    dev, ref = both(mk, lambda: mixers.Grover(initialstates.Dicke(4)), lambda: initialstates.Dicke(4), "complex128",
+                    optimizer=[COBYLA, {"maxiter": 30}])
+    grid = {"gamma": [0, 2 * np.pi, 6], "beta": [0, 2 * np.pi, 6]}
+    dev.optimize(depth=2, angles=grid)
+    ref.optimize(depth=2, angles=grid)
+    assert np.allclose(dev.Exp_sampled_p1, ref.Exp_sampled_p1, rtol=1e-9, atol=1e-12)
+    assert dev.get_Exp(2) == pytest.approx(ref.get_Exp(2), rel=1e-6)
+
+    rs = np.random.RandomState(42)
+    Q, c = rs.rand(9, 9), 3 * (rs.rand(9) - 0.5)
+    dev, ref = both(lambda: problems.QUBO(Q=Q, c=c, b=0.0), mixers.XMultiAngle, initialstates.Plus, "complex128",
+                    optimizer=[COBYLA, {"maxiter": 25}])
+    grid = {"gamma": [0, 1.0, 5], "beta": [0, np.pi, 5]}
+    dev.optimize(depth=2, angles=grid)
+    ref.optimize(depth=2, angles=grid)
+    assert len(dev.get_angles(2)) == 20
+    assert dev.get_Exp(1) == pytest.approx(ref.get_Exp(1), rel=1e-6)
+
+
+def test_large_landscape_batch_n20():
+    """Batched landscape on the tiled path (one launch per pass for all points)."""
+    G = nx.random_regular_graph(3, 20, seed=42)
+    dev = QAOA(problem=problems.MaxCut(G), mixer=mixers.X(), initialstate=initialstates.Plus(), dtype="complex64")
+    dev.sample_cost_landscape({"gamma": [0, 2 * np.pi, 6], "beta": [0, 2 * np.pi, 5]})
+    from oracle import qaoa_oracle as orc
+    edges = orc.graph_edges(orc.relabel_graph(G))
+    colors, table = orc.colour_table(2)
+    for (b, g) in ((0, 0), (2, 3), (4, 5)):
+        e = orc.maxcut_p1_closed_form(edges, 20, dev.gamma_grid[g], dev.beta_grid[b])
+        assert dev.Exp_sampled_p1[b, g] == pytest.approx(-e, rel=1e-4)

@@ -1,0 +1,295 @@
+"""CPU tests that PIN the oracle (and the host-side restatements in qaoa_b200) against everything
+the reference pins for this path: golden vectors generated from the reference's loadable modules
+(tests/golden/make_golden.py), the reference's unit-test tables, its ExactCover result fixture, and
+independent closed forms.  No GPU needed."""
+import json
+import math
+import os
+
+import networkx as nx
+import numpy as np
+import pytest
+
+from oracle import qaoa_oracle as orc
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _rebuild(case):
+    G = nx.Graph()
+    G.add_nodes_from(case["input_nodes"])
+    for u, v, w in case["input_edges"]:
+        if w == 1:
+            G.add_edge(u, v)
+        else:
+            G.add_edge(u, v, weight=w)
+    return G
+
+
+def _golden_graph(name, case):
+    """Rebuild the input graph with the SAME node/edge insertion order the generator used."""
+    makers = {
+        "regular3_n8_seed42": lambda: nx.random_regular_graph(3, 8, seed=42),
+        "regular3_n12_seed7": lambda: nx.random_regular_graph(3, 12, seed=7),
+        "regular3_n16_seed42": lambda: nx.random_regular_graph(3, 16, seed=42),
+        "barbell": lambda: nx.Graph([(0, 1)]),
+        "path3": lambda: nx.path_graph(3),
+        "house": lambda: nx.house_graph(),
+        "erdos_n10": lambda: nx.gnp_random_graph(10, 0.4, seed=3),
+    }
+    if name in makers:
+        return makers[name]()
+    return _rebuild(case)
+
+
+def test_graph_relabelling_matches_reference_graphhandler(capsys):
+    """GraphHandler golden (reference qaoa/utils/graphutils.py:38-47, 115-137)."""
+    from qaoa_b200.utils.graphutils import GraphHandler
+
+    with open(os.path.join(GOLD, "graphhandler.json")) as f:
+        gold = json.load(f)
+    for name, case in gold.items():
+        G = _golden_graph(name, case)
+        want = [tuple(e) for e in case["relabelled_edges"]]
+        got_oracle = orc.graph_edges(orc.relabel_graph(G))
+        got_host = GraphHandler(G).edge_list()
+        assert [tuple(e) for e in got_oracle] == want, name
+        assert [tuple(e) for e in got_host] == want, name
+
+
+def test_statistic_matches_reference_statistic():
+    """Statistic golden (reference qaoa/utils/statistic.py:57-142)."""
+    from qaoa_b200.utils.statistic import Statistic
+
+    with open(os.path.join(GOLD, "statistic.json")) as f:
+        gold = json.load(f)
+    for case in gold:
+        for cls in (Statistic, orc.StatisticOracle):
+            st = cls(cvar=case["cvar"])
+            for i, (v, w) in enumerate(zip(case["values"], case["weights"])):
+                st.add_sample(v, w, "s%d" % i)
+            assert st.E == pytest.approx(case["E"], rel=1e-14)
+            assert st.get_Variance() == pytest.approx(case["Variance"], rel=1e-13)
+            assert st.get_CVaR() == pytest.approx(case["CVaR"], rel=1e-14)
+            assert st.maxval == case["max"] and st.minval == case["min"]
+        st = Statistic(cvar=case["cvar"])
+        for i, (v, w) in enumerate(zip(case["values"], case["weights"])):
+            st.add_sample(v, w, "s%d" % i)
+        assert st.get_max_sols() == case["max_sols"] and st.get_min_sols() == case["min_sols"]
+
+
+def test_statistic_unit_tables():
+    """reference unittests/test_statistic_utility.py:24-92."""
+    from qaoa_b200.utils.statistic import Statistic
+
+    st = Statistic()
+    st.add_sample(2.0, 1.0, "a")
+    st.add_sample(4.0, 1.0, "b")
+    assert st.get_E() == pytest.approx(3.0) and st.get_Variance() == pytest.approx(2.0)
+    st = Statistic()
+    st.add_sample(0.0, 1.0, "0")
+    st.add_sample(10.0, 9.0, "1")
+    assert st.get_E() == pytest.approx(9.0)
+    st = Statistic(cvar=0.5)
+    for v in (1.0, 2.0, 3.0, 4.0):
+        st.add_sample(v, 1.0, str(v))
+    assert st.get_CVaR() == pytest.approx(3.5)
+
+
+def test_qubo_and_exactcover_unit_tables():
+    """reference unittests/test_problems.py:30-59, 100-123."""
+    from qaoa_b200.problems import QUBO, ExactCover
+
+    for cost in (lambda s: QUBO(Q=np.diag([1.0, -1.0])).cost(s),
+                 lambda s: orc.qubo_cost_string(s, np.diag([1.0, -1.0]), np.zeros(2), 0.0)):
+        assert cost("01") == pytest.approx(1.0) and cost("10") == pytest.approx(-1.0) and cost("00") == pytest.approx(0.0)
+    q = QUBO(Q=np.diag([0.0, 0.0]), c=np.array([1.0, 0.0]))
+    assert q.cost("10") == pytest.approx(-1.0) and q.cost("01") == pytest.approx(0.0)
+    cols = np.array([[1, 0, 0], [1, 1, 0], [0, 1, 1], [0, 0, 1]])
+    ec = ExactCover(cols)
+    assert ec.cost("101") == pytest.approx(0.0) and ec.cost("000") < 0
+    assert ec.isFeasible("101") and not ec.isFeasible("100") and not ec.isFeasible("111")
+    w, pen, Q, c, b = orc.exactcover_setup(cols)
+    for s in ("101", "000", "110", "111"):
+        assert orc.exactcover_cost_string(s, cols, w, pen) == pytest.approx(ec.cost(s))
+        assert ec.qubo_cost(s) == pytest.approx(ec.cost(s))         # QUBO mapping == direct cost
+
+
+def test_portfolio_cost_equals_its_qubo():
+    """reference qaoa/problems/portfolio_problem.py:48-71 (mapping) — both restatements."""
+    from qaoa_b200.problems import PortfolioOptimization
+
+    rng = np.random.RandomState(0)
+    A = rng.randn(6, 40)
+    cov, mu = np.cov(A), A.mean(axis=1)
+    pf = PortfolioOptimization(risk=0.5, budget=3, cov_matrix=cov, exp_return=mu, penalty=1.7)
+    Q, c, b = orc.portfolio_qubo(0.5, 3, cov, mu, 1.7)
+    diag = orc.qubo_diag(Q, c, b)
+    for x in range(64):
+        s = orc.index_to_string(x, 6)
+        assert pf.cost(s) == pytest.approx(diag[x], rel=1e-12, abs=1e-12)
+        assert pf.cost(s) == pytest.approx(orc.portfolio_cost_string(s, 0.5, 3, cov, mu, 1.7), rel=1e-12)
+        assert pf.isFeasible(s) == (s.count("1") == 3)
+
+
+@pytest.mark.parametrize("k,enc", [(2, None), (4, None), (8, None), (3, "LessThanK"), (5, "LessThanK"),
+                                   (5, "max_balanced"), (6, "LessThanK"), (6, "max_balanced"), (7, "LessThanK")])
+def test_maxkcut_barbell_cost_tables(k, enc):
+    """reference unittests/test_maxkcut_binary_problem.py:39-104, 142-240: on the barbell graph the
+    cost is 0 iff both nodes carry the same colour, 1 otherwise — for every label pair."""
+    from qaoa_b200.problems import MaxKCutBinaryFullH, MaxKCutBinaryPowerOfTwo
+
+    G = nx.Graph([(0, 1)])
+    prob = MaxKCutBinaryPowerOfTwo(G, k) if enc is None else MaxKCutBinaryFullH(G, k, enc)
+    colors, table = orc.colour_table(k, enc)
+    assert prob.bitstring_to_color == table
+    b = prob.N_qubits_per_node
+    edges = orc.graph_edges(orc.relabel_graph(G))
+    diag = orc.maxkcut_diag(edges, 2, b, table, colors)
+    for x in range(1 << (2 * b)):
+        s = orc.index_to_string(x, 2 * b)
+        same = table[s[:b]] == table[s[b:]]
+        assert prob.cost(s) == (0 if same else 1)
+        assert diag[x] == prob.cost(s)
+    # the device LUT must be indexed by the integer whose bit j is the j-th CHARACTER of the label
+    lut, fixed = prob.colour_lut()
+    for val in range(1 << b):
+        lab = "".join("1" if (val >> j) & 1 else "0" for j in range(b))
+        assert list(prob.colors.keys())[lut[val]] == table[lab]
+
+
+def test_fix_one_node_cost():
+    """graph_problem.py:148-149: the removed last node carries colour1."""
+    from qaoa_b200.problems import MaxCut
+
+    G = nx.random_regular_graph(3, 8, seed=42)
+    prob = MaxCut(G, fix_one_node=True)
+    assert prob.N_qubits == 7
+    edges = orc.graph_edges(orc.relabel_graph(G))
+    colors, table = orc.colour_table(2)
+    diag = orc.maxkcut_diag(edges, 8, 1, table, colors, fix_one_node=True)
+    full = orc.maxkcut_diag(edges, 8, 1, table, colors)
+    assert np.array_equal(diag, full[:128])           # node 7 fixed to "0"
+    for x in (0, 5, 77, 127):
+        assert prob.cost(orc.index_to_string(x, 7)) == diag[x]
+
+
+def test_dicke_amplitudes():
+    """reference unittests/test_maxkcut_feasible_initialstate.py:47-64 (k = 1) and general k."""
+    for k in range(2, 9):
+        psi = orc.dicke_state(k, 1)
+        want = np.zeros(1 << k)
+        want[[1 << i for i in range(k)]] = 1 / math.sqrt(k)
+        assert np.allclose(psi, want)
+    psi = orc.dicke_state(6, 3)
+    assert np.count_nonzero(psi) == 20 and np.isclose(np.vdot(psi, psi).real, 1.0)
+
+
+def test_readme_graph_known_answers():
+    """SURVEY §8c K2 (README graph, n=8, seed 42): diagonal, histogram, energies, landscape minimum."""
+    G = nx.random_regular_graph(3, 8, seed=42)
+    edges = orc.graph_edges(orc.relabel_graph(G))
+    assert sorted((min(u, v), max(u, v)) for u, v, _ in edges) == [
+        (0, 1), (0, 3), (0, 6), (1, 4), (1, 7), (2, 3), (2, 5), (2, 7), (3, 6), (4, 5), (4, 6), (5, 7)]
+    colors, table = orc.colour_table(2)
+    d = orc.maxkcut_diag(edges, 8, 1, table, colors)
+    assert list(d[:16]) == [0, 3, 3, 4, 3, 6, 6, 7, 3, 4, 6, 5, 4, 5, 7, 6]
+    assert list(np.bincount(d)) == [2, 0, 0, 20, 32, 36, 60, 60, 30, 12, 4]
+    spec = orc.Spec(8, d)
+    e, e2, _, _ = orc.energy(spec, [0.3, 0.2])
+    assert -e == pytest.approx(-7.124615209734253, abs=1e-12)
+    assert e2 - e * e == pytest.approx(2.166792962011350, abs=1e-10)
+    assert -orc.energy(spec, [1.1, 2.5])[0] == pytest.approx(-4.950669805780547, abs=1e-12)
+    assert -orc.energy(spec, [0.3, 0.2, 0.5, 0.1])[0] == pytest.approx(-7.765034832943002, abs=1e-12)
+    assert -orc.energy(spec, [0.4, 0.6, 0.7, 0.35, 0.9, 0.15])[0] == pytest.approx(-8.995719311366326, abs=1e-12)
+    _, _, Exp, _, _, _ = orc.landscape(spec, [0, 2 * np.pi, 20], [0, 2 * np.pi, 20])
+    assert Exp.min() == pytest.approx(-7.960913237344, abs=1e-9)
+    assert np.isclose(Exp[6, 2], Exp.min(), atol=1e-9)
+
+
+@pytest.mark.parametrize("n,seed", [(8, 42), (10, 1), (12, 7)])
+def test_p1_closed_form(n, seed):
+    """Independent derivation: closed-form p=1 MaxCut energy."""
+    G = nx.random_regular_graph(3, n, seed=seed)
+    edges = orc.graph_edges(orc.relabel_graph(G))
+    colors, table = orc.colour_table(2)
+    spec = orc.Spec(n, orc.maxkcut_diag(edges, n, 1, table, colors))
+    rng = np.random.default_rng(seed)
+    for _ in range(4):
+        g, b = rng.uniform(0, 2 * np.pi, size=2)
+        assert orc.energy(spec, [g, b])[0] == pytest.approx(orc.maxcut_p1_closed_form(edges, n, g, b), abs=1e-12)
+
+
+def test_exactcover_fixture_histograms():
+    """End-to-end pin of Dicke + Grover + QUBO-type cost + phase sign against the 8192-shot histograms
+    of the reference's own result file (examples/ExactCover/data/exact_cover_path_problem_example.json):
+    chi^2 over the 28 weight-2 strings.  The opposite Grover sign is rejected by orders of magnitude."""
+    with open(os.path.join(GOLD, "exactcover_fixture.json")) as f:
+        fx = json.load(f)
+    cols = np.array(fx["columns"], dtype=float)
+    w = np.array(fx["weights"], dtype=float)
+    n, k = cols.shape[1], fx["hamming_weight"]
+    pen = float(np.sum(np.sort(w)[-k:]))                 # SURVEY §8c G1 recipe (= pi/3)
+    assert pen == pytest.approx(math.pi / 3, abs=1e-4)
+    diag = np.array([orc.exactcover_cost_string(orc.index_to_string(x, n), cols, w, pen) for x in range(1 << n)])
+    s = orc.dicke_state(n, k)
+    spec = orc.Spec(n, diag, mixer=("grover", s), init=s)
+    for depth, rec in fx["depths"].items():
+        ang = np.array(rec["optimal_angles"], dtype=float)
+        shots = sum(rec["histogram"].values())
+        for sign, ok in ((+1, True), (-1, False)):
+            a = ang.copy()
+            a[1::2] *= sign                                # flipping beta flips the Grover phase sign
+            prob = np.abs(orc.evolve(spec, a)) ** 2
+            chi2 = 0.0
+            for x in np.nonzero(prob > 1e-14)[0]:
+                key = orc.index_to_string(int(x), n)
+                obs = rec["histogram"].get(key, 0)
+                chi2 += (obs - shots * prob[x]) ** 2 / (shots * prob[x])
+            assert set(rec["histogram"]).issubset({orc.index_to_string(int(x), n) for x in np.nonzero(prob > 1e-14)[0]})
+            if ok:
+                assert chi2 < 65.0, (depth, chi2)          # 27 dof: P(chi2 > 65) ~ 5e-5
+            else:
+                assert chi2 > 2000.0, (depth, chi2)
+
+
+def test_xy_mixer_preserves_hamming_weight_and_norm():
+    n, k = 7, 3
+    psi0 = orc.dicke_state(n, k)
+    rng = np.random.RandomState(2)
+    spec = orc.Spec(n, rng.rand(1 << n), mixer=("xy", orc.xy_pairs(n, "ring")), init=psi0)
+    psi = orc.evolve(spec, [0.7, 1.3, 0.2, 2.1])
+    assert np.vdot(psi, psi).real == pytest.approx(1.0, abs=1e-12)
+    weights = np.array([bin(x).count("1") for x in range(1 << n)])
+    assert np.all(np.abs(psi[weights != k]) < 1e-14)
+
+
+def test_exact_cvar_is_the_large_sample_limit():
+    rng = np.random.RandomState(5)
+    diag = rng.randint(0, 9, size=64).astype(float)
+    prob = rng.rand(64)
+    prob /= prob.sum()
+    counts = np.round(prob * 200000).astype(int)
+    st = orc.StatisticOracle(cvar=0.3)
+    for x in range(64):
+        if counts[x]:
+            st.add_sample(diag[x], int(counts[x]))
+    assert orc.exact_cvar(diag, counts / counts.sum(), 0.3) == pytest.approx(st.get_CVaR(), rel=2e-4)
+    assert orc.exact_cvar(diag, prob, 1.0) == pytest.approx(prob @ diag)
+
+
+def test_c_oracle_matches_numpy_oracle():
+    from oracle import c_oracle
+
+    n = 12
+    G = nx.random_regular_graph(3, n, seed=3)
+    edges = orc.graph_edges(orc.relabel_graph(G))
+    colors, table = orc.colour_table(2)
+    d = orc.maxkcut_diag(edges, n, 1, table, colors)
+    assert np.array_equal(c_oracle.maxcut_diag(n, edges), d.astype(float))
+    ang = [0.3, 0.2, 0.5, 0.1, 1.4, 2.2]
+    ref = orc.energy(orc.Spec(n, d), ang)
+    got = c_oracle.energy(n, d.astype(float), ang, "complex128")
+    assert np.allclose(got, ref, rtol=1e-12)
+    got32 = c_oracle.energy(n, d.astype(float), ang, "complex64")
+    assert np.allclose(got32[:2], ref[:2], rtol=1e-4)
