@@ -213,6 +213,16 @@ def main():
         # the survey's pass model: s * 2^n * (2 p P - 2), P = ceil((n-4)/10)
         P = max(1, -(-(n - 4) // 10))
         survey_bytes = 8.0 * 2.0 ** n * (2 * p * P - 2)
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+                ratios = json.load(f)["traffic_over_algorithmic"]
+            key = [k for k in ratios if k in names[dom]]
+            if key and d_cnt:
+                # DRAM bytes per launch = (ncu dram read+write / algorithmic bytes, measured at n=28) x algorithmic bytes
+                traffic = ratios[key[0]] * d_bytes / d_cnt
+        except Exception:
+            pass
         line = {
             "metric": METRIC, "value": ms_dev, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev, "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
@@ -226,7 +236,8 @@ def main():
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
+                         "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic,
+                         "traffic_source": "profiles/r01_tile_kernels_n28.md ratio x algorithmic bytes",
                          "launches_timed": int(d_cnt), "ms_per_launch": d_ms / d_cnt if d_cnt else None,
                          "kernel_share_of_step": d_ms / total_pass_ms if total_pass_ms else None,
                          "whole_eval_actual_gbs": total_bytes / (total_pass_ms * 1e-3) / 1e9 if total_pass_ms else None,
