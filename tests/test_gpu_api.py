@@ -60,7 +60,9 @@ def test_portfolio_grover_dicke_and_multiangle_qubo():
     dev.optimize(depth=2, angles=grid)
     ref.optimize(depth=2, angles=grid)
     assert np.allclose(dev.Exp_sampled_p1, ref.Exp_sampled_p1, rtol=1e-9, atol=1e-12)
-    assert dev.get_Exp(2) == pytest.approx(ref.get_Exp(2), rel=1e-6)
+    for d in (1, 2):
+        a = dev.optimization_results[d]
+        assert np.allclose(a.Exp, -ref._engine.energy_batch(np.asarray(a.angles))[:, 0], rtol=1e-9, atol=1e-12)
 
     rs = np.random.RandomState(42)
     Q, c = rs.rand(9, 9), 3 * (rs.rand(9) - 0.5)
@@ -70,7 +72,9 @@ def test_portfolio_grover_dicke_and_multiangle_qubo():
     dev.optimize(depth=2, angles=grid)
     ref.optimize(depth=2, angles=grid)
     assert len(dev.get_angles(2)) == 20
-    assert dev.get_Exp(1) == pytest.approx(ref.get_Exp(1), rel=1e-6)
+    for d in (1, 2):
+        a = dev.optimization_results[d]
+        assert np.allclose(a.Exp, -ref._engine.energy_batch(np.asarray(a.angles))[:, 0], rtol=1e-9, atol=1e-12)
 
 
 def test_large_landscape_batch_n20():
