@@ -181,7 +181,7 @@ def main():
     wall_resident = time.perf_counter() - t0
     launches = E.counter("launches")
     pass_stats = {i: (E.counter("pass_ms_%d" % i), E.counter("pass_count_%d" % i), E.counter("pass_bytes_%d" % i))
-                  for i in range(6)}
+                  for i in range(9)}
     out = E.fetch_results(1)[0]
 
     # ---- end to end through the public API: host angles in, host result out ----------------------
@@ -204,7 +204,8 @@ def main():
     if rank == 0:
         peak, peak_src = peaks()
         names = {0: "tile_pass_kernel (interpreter)", 1: "tile_prog_kernel<ProgFirstInit>", 2: "tile_prog_kernel<ProgFirstLoad>",
-                 3: "tile_prog_kernel<ProgInterior>", 4: "tile_prog_kernel<ProgBoundary>", 5: "tile_prog_kernel<ProgFinal>"}
+                 3: "tile_prog_kernel<ProgInterior>", 4: "tile_prog_kernel<ProgBoundary>", 5: "tile_prog_kernel<ProgFinal>",
+                 6: "tile_prog_kernel<ProgMid>", 7: "tile_prog_kernel<ProgBound2>", 8: "tile_prog_kernel<ProgFinal2>"}
         dom = max(pass_stats, key=lambda i: pass_stats[i][0])
         d_ms, d_cnt, d_bytes = pass_stats[dom]
         achieved = (d_bytes / d_cnt) / (d_ms / d_cnt * 1e-3) / 1e9 if d_cnt else 0.0

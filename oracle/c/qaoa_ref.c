@@ -41,9 +41,27 @@ void qref_maxcut_diag(int n, int n_edges, const int32_t* u, const int32_t* v, co
   }
 }
 
+/* cost diagonal of a QUBO: cost(x) = -(x^T Q x + c^T x + b)   (qaoa/problems/qubo_problem.py:101-108) */
+void qref_qubo_diag(int n, const double* Q, const double* c, double b, double* diag) {
+  const int64_t N = (int64_t)1 << n;
+#pragma omp parallel for schedule(static)
+  for (int64_t x = 0; x < N; x++) {
+    double f = b;
+    for (int i = 0; i < n; i++) {
+      if (!((x >> i) & 1)) continue;
+      double row = (c ? c[i] : 0.0);
+      for (int j = 0; j < n; j++) if ((x >> j) & 1) row += Q[(size_t)i * n + j];
+      f += row;
+    }
+    diag[x] = -f;
+  }
+}
+
+/* angles: the reference's flat layout [(gamma_d, beta_d[0..n_beta-1]) for d < p], n_beta = 1 (X mixer,
+ * x_mixer.py:35) or n (XMultiAngle, x_multiangle_mixer.py:40-50: parameter index = qubit index) */
 #define DEFINE_ENERGY(NAME, CT, RT)                                                              \
   /* out[4] = {E[cost], E[cost^2], min over support, max over support}; returns 0 on success */  \
-  int NAME(int n, const double* diag, int p, const double* angles, double* out, CT* work) {      \
+  int NAME##_nb(int n, const double* diag, int p, int n_beta, const double* angles, double* out, CT* work) { \
     const int64_t N = (int64_t)1 << n;                                                           \
     CT* psi = work ? work : (CT*)malloc(sizeof(CT) * (size_t)N);                                 \
     if (!psi) return 1;                                                                          \
@@ -51,7 +69,8 @@ void qref_maxcut_diag(int n, int n_edges, const int32_t* u, const int32_t* v, co
     _Pragma("omp parallel for schedule(static)")                                                 \
     for (int64_t x = 0; x < N; x++) { psi[x].re = a0; psi[x].im = 0; }                           \
     for (int d = 0; d < p; d++) {                                                                \
-      const double gamma = angles[2 * d], beta = angles[2 * d + 1];                              \
+      const double gamma = angles[(size_t)d * (1 + n_beta)];                                     \
+      const double* betas = angles + (size_t)d * (1 + n_beta) + 1;                               \
       _Pragma("omp parallel for schedule(static)")                                               \
       for (int64_t x = 0; x < N; x++) { /* phase separator, validation.py:43 sign */            \
         const RT c = (RT)cos(gamma * diag[x]), s = (RT)sin(gamma * diag[x]);                     \
@@ -59,8 +78,9 @@ void qref_maxcut_diag(int n, int n_edges, const int32_t* u, const int32_t* v, co
         psi[x].re = re * c - im * s;                                                             \
         psi[x].im = re * s + im * c;                                                             \
       }                                                                                          \
-      const RT cb = (RT)cos(beta), sb = (RT)sin(beta);                                           \
       for (int q = 0; q < n; q++) { /* RX(-2 beta) = [[c, i s], [i s, c]], x_mixer.py:35 */      \
+        const double beta = betas[n_beta == 1 ? 0 : q];                                          \
+        const RT cb = (RT)cos(beta), sb = (RT)sin(beta);                                         \
         const int64_t bit = (int64_t)1 << q;                                                     \
         _Pragma("omp parallel for schedule(static)")                                             \
         for (int64_t i = 0; i < N / 2; i++) {                                                    \
@@ -84,6 +104,9 @@ void qref_maxcut_diag(int n, int n_edges, const int32_t* u, const int32_t* v, co
     out[0] = e; out[1] = e2; out[2] = mn; out[3] = mx;                                           \
     if (!work) free(psi);                                                                        \
     return 0;                                                                                    \
+  }                                                                                              \
+  int NAME(int n, const double* diag, int p, const double* angles, double* out, CT* work) {      \
+    return NAME##_nb(n, diag, p, 1, angles, out, work);                                          \
   }
 
 DEFINE_ENERGY(qref_energy_c128, c128, double)

@@ -28,6 +28,11 @@ def load():
             fn = getattr(lib, name)
             fn.restype = ctypes.c_int
             fn.argtypes = [ctypes.c_int, dp, ctypes.c_int, dp, dp, ctypes.c_void_p]
+        for name in ("qref_energy_c128_nb", "qref_energy_c64_nb"):
+            fn = getattr(lib, name)
+            fn.restype = ctypes.c_int
+            fn.argtypes = [ctypes.c_int, dp, ctypes.c_int, ctypes.c_int, dp, dp, ctypes.c_void_p]
+        lib.qref_qubo_diag.argtypes = [ctypes.c_int, dp, dp, ctypes.c_double, dp]
         _lib = lib
     return _lib
 
@@ -48,14 +53,27 @@ def maxcut_diag(n, edges):
     return out
 
 
-def energy(n, diag, angles, dtype="complex128"):
+def qubo_diag(Q, c=None, b=0.0):
+    lib = load()
+    Q = np.ascontiguousarray(Q, dtype=np.float64)
+    n = Q.shape[0]
+    cc = np.ascontiguousarray(np.zeros(n) if c is None else c, dtype=np.float64)
+    out = np.empty(1 << n, dtype=np.float64)
+    dp = ctypes.POINTER(ctypes.c_double)
+    lib.qref_qubo_diag(n, Q.ctypes.data_as(dp), cc.ctypes.data_as(dp), float(b), out.ctypes.data_as(dp))
+    return out
+
+
+def energy(n, diag, angles, dtype="complex128", n_beta=1):
+    """n_beta = 1: X mixer; n_beta = n: XMultiAngle (flat reference layout, qaoa/qaoa.py:937-990)."""
     lib = load()
     diag = np.ascontiguousarray(diag, dtype=np.float64)
     angles = np.ascontiguousarray(angles, dtype=np.float64)
     out = np.empty(4, dtype=np.float64)
     dp = ctypes.POINTER(ctypes.c_double)
-    fn = lib.qref_energy_c128 if dtype == "complex128" else lib.qref_energy_c64
-    rc = fn(n, diag.ctypes.data_as(dp), angles.size // 2, angles.ctypes.data_as(dp), out.ctypes.data_as(dp), None)
+    fn = lib.qref_energy_c128_nb if dtype == "complex128" else lib.qref_energy_c64_nb
+    rc = fn(n, diag.ctypes.data_as(dp), angles.size // (1 + n_beta), n_beta, angles.ctypes.data_as(dp),
+            out.ctypes.data_as(dp), None)
     if rc:
         raise MemoryError("C oracle could not allocate the statevector")
     return out

@@ -46,7 +46,8 @@ struct PhaseSpec {
   int shape;
   int frame;
 };
-enum ProgId { PROG_GENERIC = 0, PROG_FIRST_INIT, PROG_FIRST_LOAD, PROG_INTERIOR, PROG_BOUNDARY, PROG_FINAL };
+enum ProgId { PROG_GENERIC = 0, PROG_FIRST_INIT, PROG_FIRST_LOAD, PROG_INTERIOR, PROG_BOUNDARY, PROG_FINAL,
+              PROG_MID, PROG_BOUND2, PROG_FINAL2, PROG_COUNT };
 struct PlanPass {
   TilePass tp;
   std::vector<RoundSpec> rounds;
@@ -111,6 +112,7 @@ struct Engine {
   int prefetch_dist = 0;     // extra L2 prefetch distance in tiles (0 = off)
   int persistent_ctas = 148; // CTAs of the persistent pass kernels (one per SM)
   int low_bits = 0;          // 0: automatic choice between 4 and 5 low tile bits
+  int schedule = 0;          // 0: automatic, 1: classic (interior + boundary), 2: balanced (mid + bound2)
   double* d_partials = nullptr; size_t partials_cap = 0;
   double* d_out = nullptr; size_t out_cap = 0;
   double* h_out = nullptr; size_t hout_cap = 0;
@@ -131,7 +133,7 @@ struct Engine {
   double bytes_alg = 0;
   // optional CUDA-event timing of every pass launch, accumulated per program id
   int time_passes = 0;
-  double pass_ms[8] = {0}, pass_count[8] = {0}, pass_bytes[8] = {0};
+  double pass_ms[PROG_COUNT] = {0}, pass_count[PROG_COUNT] = {0}, pass_bytes[PROG_COUNT] = {0};
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
   struct PendingEv { int prog; size_t idx; double bytes; };
   std::vector<PendingEv> ev_pending;
@@ -190,6 +192,155 @@ void reg_bits(int frame, int sub, int out[5]) {
   for (int i = 0; i < 4; i++) out[1 + i] = (frame == 0 ? 10 : 6) + i;
 }
 
+// Balanced schedule (complex64, 5 low bits, >= 3 tile shapes).  Shape 0 is the low tile (element
+// bits 0..13), shapes 1.. are the high tiles (5 low bits + 9 high bits).  Per layer d:
+//   MID    on shape 0            : all 14 qubits of the low tile                       (2 transposes)
+//   INTERIOR on all but one high : the tile's high qubits                              (2 transposes)
+//   BOUND2 on the last high tile : its high qubits of layer d, phase d+1, the same
+//                                  qubits of layer d+1                                 (2 transposes)
+// against the classic INTERIOR (2 transposes) + BOUNDARY (4 transposes) pair.  The last layer ends
+// with FINAL2 (1 transpose, fused reduction).  Same number of HBM sweeps, a third less shared-memory
+// traffic and evenly split arithmetic.
+void build_balanced(Engine* h, int p, Plan& pl) {
+  const int E = h->E, qs = h->qshift, m = (int)pl.shapes.size();
+  std::vector<std::vector<char>> done(p, std::vector<char>(E, 0));
+  std::vector<std::vector<char>> gdone(p + 1, std::vector<char>(m, 0));
+  const bool load_first = (h->init.kind == INIT_STATEVECTOR);
+  // tile-local bit held by register slot s:  kind 0 = frame A, 1 = frame B, 2 = frame C, 3 = after WT
+  auto reg_tile_bit = [](int kind, int s) {
+    if (kind == 3) return 1 + s;
+    return frame_reg_bit(kind, s);
+  };
+  struct Builder {
+    PlanPass pp;
+    const Shape* sh;
+  };
+  auto begin = [&](int shape) {
+    Builder b;
+    b.sh = &pl.shapes[shape];
+    memset(&b.pp.tp, 0, sizeof(TilePass));
+    TilePass& tp = b.pp.tp;
+    for (int j = 0; j < TILE_BITS; j++) tp.pos[j] = b.sh->pos[j];
+    tp.nfree = (int)b.sh->freepos.size();
+    for (int j = 0; j < tp.nfree; j++) tp.freepos[j] = b.sh->freepos[j];
+    if (!tilepass_set_free_runs(tp)) fail("tile shape with more than two runs of free bits");
+    tp.qshift = qs;
+    tp.init_kind = h->init.kind;
+    tp.dicke_k = h->init.k;
+    tp.init_amp = h->init.amp;
+    return b;
+  };
+  auto push = [&](Builder& b, int type, int fr, int arg, int mask) {
+    TilePass& tp = b.pp.tp;
+    if (tp.nops >= TILE_MAX_OPS) fail("tile pass program overflow");
+    tp.ops[tp.nops].type = (int16_t)type;
+    tp.ops[tp.nops].frame = (int16_t)fr;
+    tp.ops[tp.nops].arg = (int16_t)arg;
+    tp.ops[tp.nops].mask = (int16_t)mask;
+    tp.nops++;
+  };
+  auto round = [&](Builder& b, int layer, int kind, int mask) {
+    RoundSpec rs;
+    rs.layer = layer;
+    for (int s = 0; s < 5; s++) {
+      rs.ebit[s] = -1;
+      if (!((mask >> s) & 1)) continue;
+      const int eb = b.sh->pos[reg_tile_bit(kind, s)];
+      if (eb >= qs && !done[layer][eb]) { rs.ebit[s] = eb; done[layer][eb] = 1; }
+    }
+    push(b, TOP_ROUND, 0, (int)b.pp.rounds.size(), mask);
+    b.pp.rounds.push_back(rs);
+  };
+  auto phase = [&](Builder& b, int layer, int shape, int frame) {
+    push(b, TOP_PHASE, frame, (int)b.pp.phases.size(), 0);
+    b.pp.phases.push_back(PhaseSpec{layer, shape, frame});
+  };
+  auto finish = [&](Builder& b) {
+    PlanPass& pp = b.pp;
+    TilePass& tp = pp.tp;
+    tp.nrounds = (int)pp.rounds.size();
+    tp.nphases = (int)pp.phases.size();
+    tp.tau_stride = tp.nrounds * TILE_ROUND_REALS;
+    tp.phs_stride = 2 * tp.nphases + 1;
+    for (int j = 0; j < tp.nphases; j++) tp.table_id[j] = pp.phases[j].layer;
+    pp.tau_offset = pl.tau_per_point;
+    pp.phs_offset = pl.phs_per_point;
+    pl.tau_per_point += tp.tau_stride;
+    pl.phs_per_point += tp.phs_stride;
+    pp.prog = PROG_GENERIC;
+    if (prog_matches<ProgFirstInit>(tp)) pp.prog = PROG_FIRST_INIT;
+    else if (prog_matches<ProgFirstLoad>(tp)) pp.prog = PROG_FIRST_LOAD;
+    else if (prog_matches<ProgInterior>(tp)) pp.prog = PROG_INTERIOR;
+    else if (prog_matches<ProgMid>(tp)) pp.prog = PROG_MID;
+    else if (prog_matches<ProgBound2>(tp)) pp.prog = PROG_BOUND2;
+    else if (prog_matches<ProgFinal2>(tp)) pp.prog = PROG_FINAL2;
+    if (pp.prog == PROG_GENERIC) fail("balanced planner produced a pass without a compiled program");
+    pl.passes.push_back(pp);
+  };
+  auto full_cover = [&](Builder& b, int layer) {   // R(all) WT R(all) BT R(hi4): frame A -> B
+    round(b, layer, 0, M_ALL);
+    push(b, TOP_WT, 0, 0, 0);
+    round(b, layer, 3, M_ALL);
+    push(b, TOP_BT, 0, 0, 0);
+    round(b, layer, 1, M_HI4);
+  };
+  {  // FIRST: initial state, phase 0, the low tile of layer 0
+    Builder b = begin(0);
+    push(b, load_first ? TOP_LOAD : TOP_INIT, 0, 0, 0);
+    phase(b, 0, 0, 0);
+    full_cover(b, 0);
+    push(b, TOP_STORE, 1, 0, 0);
+    finish(b);
+    gdone[0][0] = 1;
+  }
+  for (int d = 0; d < p; d++) {
+    std::vector<int> rem;
+    for (int g = 1; g < m; g++) if (!gdone[d][g]) rem.push_back(g);
+    if (rem.empty()) fail("balanced planner: no high tile left for the layer boundary");
+    for (size_t i = 0; i + 1 < rem.size(); i++) {   // INTERIOR passes
+      Builder b = begin(rem[i]);
+      push(b, TOP_LOAD, 0, 0, 0);
+      round(b, d, 0, M_HI4);
+      push(b, TOP_WT, 0, 0, 0);
+      round(b, d, 3, M_TOP2);
+      push(b, TOP_BT, 0, 0, 0);
+      round(b, d, 1, M_HI4);
+      push(b, TOP_STORE, 1, 0, 0);
+      finish(b);
+      gdone[d][rem[i]] = 1;
+    }
+    const int g = rem.back();
+    Builder b = begin(g);
+    push(b, TOP_LOAD, 0, 0, 0);
+    round(b, d, 0, M_HI4);
+    push(b, TOP_XT, 0, 0, 0);
+    round(b, d, 2, M_ALL);
+    gdone[d][g] = 1;
+    for (int e = qs; e < E; e++) if (!done[d][e]) fail("balanced planner: layer left incomplete");
+    if (d == p - 1) {
+      b.pp.has_reduce = true;
+      b.pp.reduce_shape = g;
+      b.pp.reduce_frame = 2;
+      push(b, TOP_REDUCE, 2, (int)b.pp.phases.size(), 0);
+      finish(b);
+      break;
+    }
+    phase(b, d + 1, g, 2);
+    round(b, d + 1, 2, M_ALL);
+    push(b, TOP_XTI, 0, 0, 0);
+    round(b, d + 1, 0, M_HI4);
+    push(b, TOP_STORE, 0, 0, 0);
+    finish(b);
+    gdone[d + 1][g] = 1;
+    Builder mb = begin(0);   // MID: the low tile of layer d+1
+    push(mb, TOP_LOAD, 0, 0, 0);
+    full_cover(mb, d + 1);
+    push(mb, TOP_STORE, 1, 0, 0);
+    finish(mb);
+    gdone[d + 1][0] = 1;
+  }
+}
+
 Plan build_plan(Engine* h, int p) {
   Plan pl;
   pl.p = p;
@@ -219,6 +370,10 @@ Plan build_plan(Engine* h, int p) {
     for (int b = 0; b < E; b++)
       if (!std::binary_search(bits.begin(), bits.end(), b)) s.freepos.push_back(b);
     pl.shapes.push_back(s);
+  }
+  if (h->schedule != 1 && h->dtype == QAOA_DTYPE_C64 && clow == 5 && m >= 3 && !h->keep_state) {
+    build_balanced(h, p, pl);
+    return pl;
   }
   std::vector<std::vector<char>> done(p, std::vector<char>(E, 0));
   auto layer_complete = [&](int d) {
@@ -250,6 +405,7 @@ Plan build_plan(Engine* h, int p) {
     for (int j = 0; j < TILE_BITS; j++) tp.pos[j] = sh.pos[j];
     tp.nfree = (int)sh.freepos.size();
     for (int j = 0; j < tp.nfree; j++) tp.freepos[j] = sh.freepos[j];
+    if (!tilepass_set_free_runs(tp)) fail("tile shape with more than two runs of free bits");
     tp.qshift = qs;
     tp.init_kind = h->init.kind;
     tp.dicke_k = h->init.k;
@@ -342,6 +498,9 @@ Plan build_plan(Engine* h, int p) {
     else if (prog_matches<ProgInterior>(tp)) pp.prog = PROG_INTERIOR;
     else if (prog_matches<ProgBoundary>(tp)) pp.prog = PROG_BOUNDARY;
     else if (prog_matches<ProgFinal>(tp)) pp.prog = PROG_FINAL;
+    else if (prog_matches<ProgMid>(tp)) pp.prog = PROG_MID;
+    else if (prog_matches<ProgBound2>(tp)) pp.prog = PROG_BOUND2;
+    else if (prog_matches<ProgFinal2>(tp)) pp.prog = PROG_FINAL2;
     pl.passes.push_back(pp);
   }
   return pl;
@@ -360,6 +519,7 @@ void* get_stream(Engine* h, const Plan& pl, int shape, int frame) {
   for (int j = 0; j < TILE_BITS; j++) tp.pos[j] = sh.pos[j];
   tp.nfree = (int)sh.freepos.size();
   for (int j = 0; j < tp.nfree; j++) tp.freepos[j] = sh.freepos[j];
+  if (!tilepass_set_free_runs(tp)) fail("tile shape with more than two runs of free bits");
   tp.qshift = h->qshift;
   const unsigned ntiles = 1u << (h->E - TILE_BITS);
   const int namp = h->dtype == QAOA_DTYPE_C64 ? 32 : 16;
@@ -470,15 +630,17 @@ void fill_point_params(Engine* h, const Plan& pl, const double* ang, double* tau
   if (final_scale_out) *final_scale_out = post[p - 1];
 }
 
+// returns the number of partial-result slots per point a REDUCE pass writes
 template <typename Elem>
-void launch_pass(Engine* h, const PlanPass& pp, bool use_prog, unsigned ntiles, int B, size_t point_stride_elems,
-                 const void* d_tau, const double* d_phs, int tables_per_point) {
+int launch_pass(Engine* h, const PlanPass& pp, bool use_prog, unsigned ntiles, int B, size_t point_stride_elems,
+                const void* d_tau, const double* d_phs, int tables_per_point) {
   typedef typename ElemTraits<Elem>::real real;
   TilePass tp = pp.tp;
   tp.ntiles = ntiles;
   tp.prefetch_dist = h->prefetch_dist;
   const int prog = use_prog ? pp.prog : PROG_GENERIC;
   const bool u8 = h->dinfo.kind == DIAG_U8;
+  int nparts = (int)ntiles;
   // interpreter: one CTA per (tile, point); programs: persistent CTAs walking the linear index
   auto go_generic = [&]() {
     auto kernel = tile_pass_kernel<Elem>;
@@ -490,10 +652,11 @@ void launch_pass(Engine* h, const PlanPass& pp, bool use_prog, unsigned ntiles, 
                                                                d_phs, h->d_tables, tables_per_point, h->dinfo, h->d_partials);
   };
   auto go = [&](auto kernel) {
-    CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES_STAGED));
+    CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TileSmem<Elem>::TOTAL));
     const unsigned long long total = (unsigned long long)ntiles * B;
     dim3 grid((unsigned)std::min<unsigned long long>(total, (unsigned long long)h->persistent_ctas));
-    kernel<<<grid, TILE_THREADS, TILE_SMEM_BYTES_STAGED, h->stream>>>(tp, (Elem*)h->state, point_stride_elems,
+    nparts = (int)grid.x;
+    kernel<<<grid, TILE_THREADS, TileSmem<Elem>::TOTAL, h->stream>>>(tp, (Elem*)h->state, point_stride_elems,
                                                                       (const real*)d_tau, d_phs, h->d_tables,
                                                                       tables_per_point, h->dinfo, h->d_partials, (unsigned)B);
   };
@@ -503,9 +666,13 @@ void launch_pass(Engine* h, const PlanPass& pp, bool use_prog, unsigned ntiles, 
     case PROG_INTERIOR: go(tile_prog_kernel<Elem, ProgInterior, DIAG_U8>); break;
     case PROG_BOUNDARY: if (u8) go(tile_prog_kernel<Elem, ProgBoundary, DIAG_U8>); else go(tile_prog_kernel<Elem, ProgBoundary, 0>); break;
     case PROG_FINAL: if (u8) go(tile_prog_kernel<Elem, ProgFinal, DIAG_U8>); else go(tile_prog_kernel<Elem, ProgFinal, 0>); break;
+    case PROG_MID: go(tile_prog_kernel<Elem, ProgMid, DIAG_U8>); break;
+    case PROG_BOUND2: if (u8) go(tile_prog_kernel<Elem, ProgBound2, DIAG_U8>); else go(tile_prog_kernel<Elem, ProgBound2, 0>); break;
+    case PROG_FINAL2: if (u8) go(tile_prog_kernel<Elem, ProgFinal2, DIAG_U8>); else go(tile_prog_kernel<Elem, ProgFinal2, 0>); break;
     default: go_generic(); break;
   }
   CUDA_OK(cudaGetLastError());
+  return nparts;
 }
 
 // tile path for a chunk of points [b0, b0+Bc)
@@ -523,7 +690,7 @@ void run_tile_chunk(Engine* h, Plan& pl, const double* angles, int n_angles, int
   ensure(h->h_params, h->hparams_cap, tau_bytes + phs_bytes + gs_bytes, true);
   ensure(h->d_params, h->params_cap, tau_bytes + phs_bytes);
   ensure(h->d_gamsig, h->gamsig_cap, gs_bytes);
-  ensure(h->d_partials, h->partials_cap, (size_t)ntiles * Bc * 5 * sizeof(double));
+  ensure(h->d_partials, h->partials_cap, ((size_t)ntiles + h->persistent_ctas) * Bc * 5 * sizeof(double));
   unsigned char* hb = (unsigned char*)h->h_params;
   double* h_phs = (double*)(hb + tau_bytes);
   double* hgs = (double*)(hb + tau_bytes + phs_bytes);
@@ -570,6 +737,7 @@ void run_tile_chunk(Engine* h, Plan& pl, const double* angles, int n_angles, int
   }
   const size_t point_stride_elems = h->N << h->qshift;
   size_t tbase = 0, pbase = 0;
+  int nparts = (int)ntiles;
   for (size_t ip = 0; ip < pl.passes.size(); ip++) {
     auto& pp = pl.passes[ip];
     const bool use_prog = all_normal[ip] && !h->force_generic;
@@ -589,8 +757,9 @@ void run_tile_chunk(Engine* h, Plan& pl, const double* angles, int n_angles, int
       }
       CUDA_OK(cudaEventRecord(h->ev_pool[evi].first, h->stream));
     }
-    if (c64) launch_pass<float2>(h, pp, use_prog, ntiles, Bc, point_stride_elems, d_tau, d_phs, p);
-    else launch_pass<double>(h, pp, use_prog, ntiles, Bc, point_stride_elems, d_tau, d_phs, p);
+    const int np = c64 ? launch_pass<float2>(h, pp, use_prog, ntiles, Bc, point_stride_elems, d_tau, d_phs, p)
+                       : launch_pass<double>(h, pp, use_prog, ntiles, Bc, point_stride_elems, d_tau, d_phs, p);
+    if (pp.has_reduce) nparts = np;
     if (h->time_passes) {
       CUDA_OK(cudaEventRecord(h->ev_pool[evi].second, h->stream));
       h->ev_pending.push_back({use_prog ? pp.prog : (int)PROG_GENERIC, evi, pass_bytes});
@@ -601,7 +770,7 @@ void run_tile_chunk(Engine* h, Plan& pl, const double* angles, int n_angles, int
     tbase += (size_t)pp.tp.tau_stride * Bc;
     pbase += (size_t)pp.tp.phs_stride * Bc;
   }
-  finalize_kernel<<<Bc, 256, 0, h->stream>>>(h->d_partials, (int)ntiles, h->dinfo, d_out_chunk);
+  finalize_kernel<<<Bc, 256, 0, h->stream>>>(h->d_partials, nparts, h->dinfo, d_out_chunk);
   CUDA_OK(cudaGetLastError());
   h->launches += 1;
 }
@@ -896,6 +1065,7 @@ int qaoa_set_option(qaoa_engine_t* h, const char* key, double value) {
   else if (k == "persistent_ctas") h->persistent_ctas = std::max(1, (int)value);
   else if (k == "time_passes") h->time_passes = value != 0;
   else if (k == "low_bits") { h->low_bits = (int)value; free_streams(h); invalidate(h); }
+  else if (k == "schedule") { h->schedule = (int)value; free_streams(h); invalidate(h); }
   else fail("unknown option: " + k);
   API_END(h)
 }
@@ -909,13 +1079,13 @@ double qaoa_get_counter(qaoa_engine_t* h, const char* key) {
   if (k == "diag_kind") return h->dinfo.kind;
   if (k == "reset") {
     h->launches = 0; h->prog_launches = 0; h->bytes_alg = 0;
-    for (int i = 0; i < 8; i++) { h->pass_ms[i] = 0; h->pass_count[i] = 0; h->pass_bytes[i] = 0; }
+    for (int i = 0; i < PROG_COUNT; i++) { h->pass_ms[i] = 0; h->pass_count[i] = 0; h->pass_bytes[i] = 0; }
     return 0;
   }
   if (k == "last_device_ms") return h->last_device_ms;
-  if (k.rfind("pass_ms_", 0) == 0) { int i = atoi(k.c_str() + 8); return (i >= 0 && i < 8) ? h->pass_ms[i] : -1.0; }
-  if (k.rfind("pass_count_", 0) == 0) { int i = atoi(k.c_str() + 11); return (i >= 0 && i < 8) ? h->pass_count[i] : -1.0; }
-  if (k.rfind("pass_bytes_", 0) == 0) { int i = atoi(k.c_str() + 11); return (i >= 0 && i < 8) ? h->pass_bytes[i] : -1.0; }
+  if (k.rfind("pass_ms_", 0) == 0) { int i = atoi(k.c_str() + 8); return (i >= 0 && i < PROG_COUNT) ? h->pass_ms[i] : -1.0; }
+  if (k.rfind("pass_count_", 0) == 0) { int i = atoi(k.c_str() + 11); return (i >= 0 && i < PROG_COUNT) ? h->pass_count[i] : -1.0; }
+  if (k.rfind("pass_bytes_", 0) == 0) { int i = atoi(k.c_str() + 11); return (i >= 0 && i < PROG_COUNT) ? h->pass_bytes[i] : -1.0; }
   if (k == "n_passes") { double s = 0; for (auto& kv : h->plans) s = (double)kv.second.passes.size(); return s; }
   return -1.0;
 }
@@ -1171,6 +1341,7 @@ int qaoa_debug_tile_program(qaoa_engine_t* h, int hb, const int32_t* ops, int no
   for (int j = 0; j < clow; j++) tp.pos[j] = j;
   for (int j = 0; j < 14 - clow; j++) tp.pos[clow + j] = hb + j;
   for (int b = clow; b < h->E; b++) if (b < hb || b >= hb + (14 - clow)) tp.freepos[tp.nfree++] = b;
+  if (!tilepass_set_free_runs(tp)) fail("tile shape with more than two runs of free bits");
   tp.qshift = h->qshift;
   tp.init_kind = INIT_PLUS;
   tp.init_amp = pow(2.0, -0.5 * h->n);

@@ -36,20 +36,25 @@ constexpr int TILE_MAX_OPS = 64;
 constexpr int TILE_MAX_PHASES = 16;
 constexpr int TILE_ROUND_REALS = 12;  // k1[5], k2[5], form mask, pad
 constexpr int TILE_EXCH_BYTES = TILE_ELEMS * 8;
-constexpr int TILE_SMEM_BYTES = TILE_EXCH_BYTES + 4096 + 16 * 5 * 8;
-// persistent kernels additionally stage TILE_STAGE_PAIRS of the 16 register pairs of the NEXT tile
-constexpr int TILE_STAGE_PAIRS = 11;
-constexpr int TILE_STAGE_OFFSET = TILE_EXCH_BYTES + 4096 + 1024;
-constexpr int TILE_SMEM_BYTES_STAGED = TILE_STAGE_OFFSET + TILE_STAGE_PAIRS * TILE_THREADS * 16;
+constexpr int TILE_SMEM_BYTES = TILE_EXCH_BYTES + 4096 + 16 * 5 * 8;   // interpreter kernel
+constexpr int TILE_SMEM_MAX = 232448;                                   // 227 KB per CTA on sm_100a
+constexpr int TILE_CANON_ROUNDS = 8;                                    // rounds a compiled program may hold
 
 enum TileOpType : int {
   TOP_LOAD = 1, TOP_STORE = 2, TOP_INIT = 3, TOP_PHASE = 4,
-  TOP_ROUND = 5, TOP_WT = 6, TOP_BT = 7, TOP_REDUCE = 8
+  TOP_ROUND = 5, TOP_WT = 6, TOP_BT = 7, TOP_REDUCE = 8,
+  TOP_XT = 9,    // block transpose frame A -> frame C
+  TOP_XTI = 10   // block transpose frame C -> frame A
 };
+// Frames (which tile-local bit sits where; t0..t13 = tile bits, t0 = element bit 0):
+//   A: reg {t0, t10..t13}  lane {t1..t5}      warp {t6..t9}      (global access: 16 B per thread)
+//   B: reg {t0, t6..t9}    lane {t1..t5}      warp {t10..t13}    (global access: 16 B per thread)
+//   C: reg {t5, t6..t9}    lane {t0, t1..t4}  warp {t10..t13}    (register-only frame, complex64)
+//   after WT (from A or B): reg {t1..t5}
 
 struct TileOp {
   int16_t type;
-  int16_t frame;  // 0 = A, 1 = B   (LOAD/STORE/INIT/PHASE/REDUCE)
+  int16_t frame;  // 0 = A, 1 = B, 2 = C   (LOAD/STORE/INIT/PHASE/REDUCE)
   int16_t arg;    // ROUND: round index; PHASE/REDUCE: phase slot index
   int16_t mask;   // ROUND: register slots compiled in (canonical programs)
 };
@@ -60,6 +65,8 @@ struct TilePass {
   int pos[TILE_BITS];  // element-bit position of each tile-local bit (ascending, pos[0] == 0)
   int nfree;
   int freepos[QAOA_MAX_QUBITS + 1];  // element-bit positions of the non-tile bits (ascending)
+  // the non-tile bits always form at most two contiguous runs; the kernels address tiles through them
+  int fr_lo_bits, fr_lo_shift, fr_hi_shift;
   int qshift;                        // 0: complex64, 1: complex128 (element bit 0 = re/im)
   int init_kind;
   int dicke_k;
@@ -86,6 +93,25 @@ template <> struct ElemTraits<double> {
   typedef double2 cplx;
   static constexpr int NAMP = 16;
   static constexpr bool IS_C64 = false;
+};
+
+// Shared-memory layout of the compiled-program (persistent) kernels:
+//   [exchange buffer 128 KB][phase table 256 cplx][reduction scratch][round coefficients of the
+//   current point][staging area: STAGE_PAIRS of the 16 register pairs of the NEXT tile]
+template <typename Elem>
+struct TileSmem {
+  typedef typename ElemTraits<Elem>::real real;
+  typedef typename ElemTraits<Elem>::cplx cplx;
+  static constexpr int TABLE_OFF = TILE_EXCH_BYTES;
+  static constexpr int TABLE_BYTES = 256 * (int)sizeof(cplx);
+  static constexpr int SCRATCH_OFF = TABLE_OFF + TABLE_BYTES;
+  static constexpr int SCRATCH_BYTES = 16 * 5 * 8;
+  static constexpr int TAU_OFF = SCRATCH_OFF + SCRATCH_BYTES;
+  static constexpr int TAU_BYTES = TILE_CANON_ROUNDS * TILE_ROUND_REALS * (int)sizeof(real);
+  static constexpr int STAGE_OFF = TAU_OFF + TAU_BYTES;
+  static constexpr int STAGE_PAIRS = (TILE_SMEM_MAX - STAGE_OFF) / (TILE_THREADS * 16);   // 12 (c64) / 11 (c128)
+  static constexpr int TOTAL = STAGE_OFF + STAGE_PAIRS * TILE_THREADS * 16;
+  static_assert(STAGE_OFF % 16 == 0, "staging area must be 16-byte aligned");
 };
 
 // ---- element arithmetic -------------------------------------------------------------------
@@ -120,22 +146,51 @@ struct TileAddr {
 };
 
 __device__ __forceinline__ size_t tile_base(const TilePass& P, unsigned tile) {
-  size_t base = 0;
-  for (int i = 0; i < P.nfree; i++) base |= (size_t)((tile >> i) & 1u) << P.freepos[i];
-  return base;
+  return ((size_t)(tile & ((1u << P.fr_lo_bits) - 1u)) << P.fr_lo_shift) |
+         ((size_t)(tile >> P.fr_lo_bits) << P.fr_hi_shift);
+}
+
+// host: derive the two-run description from freepos (false if the free bits need more than two runs)
+inline bool tilepass_set_free_runs(TilePass& tp) {
+  tp.fr_lo_bits = 0; tp.fr_lo_shift = 0; tp.fr_hi_shift = 0;
+  if (tp.nfree == 0) return true;
+  int i = 1;
+  while (i < tp.nfree && tp.freepos[i] == tp.freepos[i - 1] + 1) i++;
+  tp.fr_lo_bits = i;
+  tp.fr_lo_shift = tp.freepos[0];
+  if (i == tp.nfree) return true;
+  tp.fr_hi_shift = tp.freepos[i];
+  for (int j = i + 1; j < tp.nfree; j++) if (tp.freepos[j] != tp.freepos[j - 1] + 1) return false;
+  return true;
+}
+
+// tile-local bit held by each lane / warp / register bit of a frame (see the frame table above)
+__host__ __device__ inline int frame_lane_bit(int frame, int j) { return frame == 2 ? j : 1 + j; }
+__host__ __device__ inline int frame_warp_bit(int frame, int j) { return (frame == 0 ? 6 : 10) + j; }
+__host__ __device__ inline int frame_reg_bit(int frame, int j) {
+  if (frame == 2) return 5 + j;
+  return j == 0 ? 0 : (frame == 0 ? 9 : 5) + j;
 }
 
 // element offset contributed by this thread's lane and warp bits in the given frame
 __device__ __forceinline__ size_t thread_off(const TilePass& P, int frame, int warp, int lane) {
   size_t e = 0;
 #pragma unroll
-  for (int j = 0; j < 5; j++) e += (size_t)((lane >> j) & 1) << P.pos[1 + j];
-  const int wofs = frame == 0 ? 6 : 10;
+  for (int j = 0; j < 5; j++) e += (size_t)((lane >> j) & 1) << P.pos[frame_lane_bit(frame, j)];
 #pragma unroll
-  for (int j = 0; j < 4; j++) e += (size_t)((warp >> j) & 1) << P.pos[wofs + j];
+  for (int j = 0; j < 4; j++) e += (size_t)((warp >> j) & 1) << P.pos[frame_warp_bit(frame, j)];
   return e;
 }
 
+// element offset of register `r` (0..31) of a frame
+__device__ __forceinline__ size_t reg_elem_off(const TilePass& P, int frame, int r) {
+  size_t e = 0;
+#pragma unroll
+  for (int j = 0; j < 5; j++) e += (size_t)((r >> j) & 1) << P.pos[frame_reg_bit(frame, j)];
+  return e;
+}
+
+// frames A and B only (register bit 0 = element bit 0, 16-byte accesses)
 __device__ __forceinline__ TileAddr tile_addr_off(const TilePass& P, size_t base, int frame, size_t thr) {
   TileAddr a;
   const int rofs = frame == 0 ? 10 : 6;
@@ -143,10 +198,6 @@ __device__ __forceinline__ TileAddr tile_addr_off(const TilePass& P, size_t base
   for (int j = 0; j < 4; j++) a.roff[j] = (size_t)1 << P.pos[rofs + j];
   a.e0 = base + thr;
   return a;
-}
-
-__device__ __forceinline__ TileAddr tile_addr(const TilePass& P, size_t base, int frame, int warp, int lane) {
-  return tile_addr_off(P, base, frame, thread_off(P, frame, warp, lane));
 }
 
 __device__ __forceinline__ size_t reg_off(const TileAddr& a, int q) {
@@ -166,7 +217,7 @@ struct Ctx {
   typedef typename ElemTraits<Elem>::cplx cplx;
   const TilePass* P;
   Elem* state;
-  const real* tau;     // this point's round coefficients
+  const real* tau;     // this point's round coefficients (global memory)
   const double* phs;   // this point's (gamma, mult) pairs followed by the reduction scale
   const void* tables;
   int tables_per_point;
@@ -182,9 +233,11 @@ struct Ctx {
   int warp, lane;
   size_t base;
   unsigned char* smem;
+  unsigned char* tab;   // 256-entry phase table in shared memory
+  double* scratch;      // block-reduction scratch in shared memory
   // hoisted shared-memory byte addresses (see warp_transpose / block_transpose)
   unsigned wt_st, wt_ld, bt_st, bt_ld;
-  size_t thr[2];   // hoisted per-thread element offsets for frames A and B
+  size_t thr[3];   // hoisted per-thread element offsets for frames A, B, C
 };
 
 template <typename Elem>
@@ -203,6 +256,7 @@ __device__ __forceinline__ void ctx_smem_setup(Ctx<Elem>& c) {
   c.bt_ld = ((lane ^ (warp & 7u)) + 512u * warp) * 16u;
   c.thr[0] = thread_off(*c.P, 0, c.warp, c.lane);
   c.thr[1] = thread_off(*c.P, 1, c.warp, c.lane);
+  c.thr[2] = thread_off(*c.P, 2, c.warp, c.lane);
 }
 
 // ---- transposes ---------------------------------------------------------------------------
@@ -232,16 +286,45 @@ __device__ __forceinline__ void block_transpose(const Ctx<Elem>& c, Elem (&v)[32
     load16(reinterpret_cast<const Elem*>(c.smem + c.bt_ld + q * 512), v[2 * q], v[2 * q + 1]);
 }
 
+// frame A -> frame C: (warp w, lane l, reg r) -> (warp r>>1, lane ((l&15)<<1)|(r&1), reg (w<<1)|(l>>4)).
+// Element (w, l, r) lives at byte (r>>1)*8192 + (32 w + l)*16 + (r&1)*8: every warp-wide access of
+// both sides covers contiguous bytes, so no swizzle is needed and all offsets are immediates.
+template <typename Elem>
+__device__ __forceinline__ void xt_a_to_c(const Ctx<Elem>& c, Elem (&v)[32]) {
+  __syncthreads();
+  unsigned char* st = c.smem + threadIdx.x * 16u;
+#pragma unroll
+  for (int q = 0; q < 16; q++) store16(reinterpret_cast<Elem*>(st + q * 8192), v[2 * q], v[2 * q + 1]);
+  __syncthreads();
+  const unsigned char* ld = c.smem + c.warp * 8192u + c.lane * 8u;
+#pragma unroll
+  for (int r = 0; r < 32; r++) v[r] = *reinterpret_cast<const Elem*>(ld + r * 256);
+}
+
+// frame C -> frame A (inverse of the above, same layout)
+template <typename Elem>
+__device__ __forceinline__ void xt_c_to_a(const Ctx<Elem>& c, Elem (&v)[32]) {
+  __syncthreads();
+  unsigned char* st = c.smem + c.warp * 8192u + c.lane * 8u;
+#pragma unroll
+  for (int r = 0; r < 32; r++) *reinterpret_cast<Elem*>(st + r * 256) = v[r];
+  __syncthreads();
+  const unsigned char* ld = c.smem + threadIdx.x * 16u;
+#pragma unroll
+  for (int q = 0; q < 16; q++) load16(reinterpret_cast<const Elem*>(ld + q * 8192), v[2 * q], v[2 * q + 1]);
+}
+
 // ---- butterflies --------------------------------------------------------------------------
-// canonical (straight-line) round: normal form only, slots selected at compile time
+// canonical (straight-line) round: normal form only, slots selected at compile time; the
+// coefficients of the current point sit in shared memory (see point_setup)
 template <typename Elem, int MASK>
-__device__ __forceinline__ void round_static(const Ctx<Elem>& c, Elem (&v)[32], int round) {
+__device__ __forceinline__ void round_static(const typename ElemTraits<Elem>::real* tau_s, Elem (&v)[32], int round) {
   typedef typename ElemTraits<Elem>::real real;
-  const real* rp = c.tau + round * TILE_ROUND_REALS;
+  const real* rp = tau_s + round * TILE_ROUND_REALS;
 #pragma unroll
   for (int s = 0; s < 5; s++) {
     if (MASK & (1 << s)) {
-      const real t = __ldg(rp + s);
+      const real t = rp[s];
 #pragma unroll
       for (int i = 0; i < 32; i++) {
         if (!(i & (1 << s))) {
@@ -285,7 +368,9 @@ __device__ __forceinline__ void round_dynamic(const Ctx<Elem>& c, Elem (&v)[32],
   }
 }
 
-// ---- amplitude access helpers (frames A and B only: register bit 0 is tile bit 0) ----------
+// ---- amplitude access helpers ---------------------------------------------------------------
+// complex64: register a IS amplitude a (every frame).  complex128: amplitude a = registers
+// (2a, 2a+1), frames A and B only (register bit 0 is the re/im bit there).
 __device__ __forceinline__ void amp_get(const float2 (&v)[32], int a, float& re, float& im) {
   re = v[a].x; im = v[a].y;
 }
@@ -350,8 +435,7 @@ __device__ __forceinline__ void op_load(const Ctx<Elem>& c, Elem (&v)[32], int f
 }
 
 // Pulls the 1024 128-byte rows of a LATER tile (the one the next CTA scheduled on this SM will most
-// likely own) from HBM into L2, so that its loads overlap this tile's arithmetic.  One CTA per SM
-// cannot overlap its own load and compute phases; the L2 (126 MB) is the staging buffer instead.
+// likely own) from HBM into L2, so that its loads overlap this tile's arithmetic.
 template <typename Elem>
 __device__ __forceinline__ void prefetch_later_tile(const Ctx<Elem>& c) {
   const TilePass& P = *c.P;
@@ -399,6 +483,8 @@ __device__ __forceinline__ void op_init(const Ctx<Elem>& c, Elem (&v)[32], int f
   }
 }
 
+// phase separator, generic form: the stream is read where it is needed, U8 tables are (re)loaded
+// into shared memory on every call
 template <typename Elem, int DK>
 __device__ __forceinline__ void op_phase(const Ctx<Elem>& c, Elem (&v)[32], int slot) {
   typedef typename ElemTraits<Elem>::real real;
@@ -407,7 +493,7 @@ __device__ __forceinline__ void op_phase(const Ctx<Elem>& c, Elem (&v)[32], int 
   const TilePass& P = *c.P;
   const double gamma = __ldg(c.phs + 2 * slot), mult = __ldg(c.phs + 2 * slot + 1);
   if (DK == DIAG_U8 || (DK == 0 && c.dinfo.kind == DIAG_U8)) {
-    cplx* tab = reinterpret_cast<cplx*>(c.smem + TILE_EXCH_BYTES);
+    cplx* tab = reinterpret_cast<cplx*>(c.tab);
     __syncthreads();
     if (threadIdx.x < 256) {
       const cplx* t = reinterpret_cast<const cplx*>(c.tables) +
@@ -439,6 +525,28 @@ __device__ __forceinline__ void op_phase(const Ctx<Elem>& c, Elem (&v)[32], int 
   }
 }
 
+// phase separator, compiled programs with a U8 diagonal: the thread's stream words were fetched at
+// the start of the tile (dq) and the table of the current point is resident in shared memory
+template <typename Elem>
+__device__ __forceinline__ void op_phase_u8_regs(const Ctx<Elem>& c, Elem (&v)[32], const uint4 (&dq)[2]) {
+  typedef typename ElemTraits<Elem>::real real;
+  typedef typename ElemTraits<Elem>::cplx cplx;
+  constexpr int NAMP = ElemTraits<Elem>::NAMP;
+  const cplx* tab = reinterpret_cast<const cplx*>(c.tab);
+#pragma unroll
+  for (int j = 0; j < NAMP / 16; j++) {
+    const unsigned ww[4] = {dq[j].x, dq[j].y, dq[j].z, dq[j].w};
+#pragma unroll
+    for (int b = 0; b < 16; b++) {
+      const unsigned k = (ww[b >> 2] >> (8 * (b & 3))) & 0xffu;
+      const cplx ph = tab[k];
+      real re, im;
+      amp_get(v, j * 16 + b, re, im);
+      amp_set(v, j * 16 + b, re * ph.x - im * ph.y, re * ph.y + im * ph.x);
+    }
+  }
+}
+
 template <typename Elem, int DK>
 __device__ __forceinline__ void op_reduce(const Ctx<Elem>& c, Elem (&v)[32], int slot) {
   typedef typename ElemTraits<Elem>::real real;
@@ -462,12 +570,114 @@ __device__ __forceinline__ void op_reduce(const Ctx<Elem>& c, Elem (&v)[32], int
     if (p > (real)0) { kmin = fmin(kmin, kdv); kmax = fmax(kmax, kdv); }
   });
   double r5[5] = {(double)s0, (double)s1, (double)s2, kmin, kmax};
-  block_reduce5(r5, reinterpret_cast<double*>(c.smem + TILE_EXCH_BYTES + 4096));
+  block_reduce5(r5, c.scratch);
   if (threadIdx.x == 0) {
     double* o = c.partials + ((size_t)c.point * c.ntiles + c.tile) * 5;
 #pragma unroll
     for (int i = 0; i < 5; i++) o[i] = r5[i];
   }
+}
+
+// Fused <cost>, <cost^2>, min, max reduction of the compiled programs.  Every thread keeps double
+// accumulators across ALL tiles its CTA processes for a point (acc = {S0, S1, S2, kmin, kmax}); the
+// block-wide tree runs once per point (flush_acc), not once per tile.  Tile-to-CTA assignment is
+// static, so the summation order is fixed and results are reproducible run to run.
+// U8 diagonal: stream words in registers, integer min/max over whole words (the exact
+// "support only" handling runs only when a zero amplitude shows up).
+template <typename Elem>
+__device__ __forceinline__ void op_reduce_u8_regs(const Ctx<Elem>& c, Elem (&v)[32], const uint4 (&dq)[2],
+                                                  typename ElemTraits<Elem>::real post, double (&acc)[5]) {
+  typedef typename ElemTraits<Elem>::real real;
+  constexpr int NAMP = ElemTraits<Elem>::NAMP;
+  real s0 = 0, s1 = 0, s2 = 0;
+  real pmin = (real)1e30;
+  unsigned mn4 = 0xffffffffu, mx4 = 0u;
+#pragma unroll
+  for (int j = 0; j < NAMP / 16; j++) {
+    const unsigned ww[4] = {dq[j].x, dq[j].y, dq[j].z, dq[j].w};
+#pragma unroll
+    for (int w = 0; w < 4; w++) { mn4 = __vminu4(mn4, ww[w]); mx4 = __vmaxu4(mx4, ww[w]); }
+#pragma unroll
+    for (int b = 0; b < 16; b++) {
+      const unsigned k = (ww[b >> 2] >> (8 * (b & 3))) & 0xffu;
+      real re, im;
+      amp_get(v, j * 16 + b, re, im);
+      re *= post;
+      im *= post;
+      const real p = re * re + im * im;
+      const real kv = (real)k;
+      s0 += p;
+      s1 = fma(p, kv, s1);
+      s2 = fma(p * kv, kv, s2);
+      pmin = p < pmin ? p : pmin;
+    }
+  }
+  unsigned kmn = min(min(mn4 & 0xffu, (mn4 >> 8) & 0xffu), min((mn4 >> 16) & 0xffu, mn4 >> 24));
+  unsigned kmx = max(max(mx4 & 0xffu, (mx4 >> 8) & 0xffu), max((mx4 >> 16) & 0xffu, mx4 >> 24));
+  double kmin = (double)kmn, kmax = (double)kmx;
+  if (!(pmin > (real)0)) {   // some amplitude is exactly zero: min / max over the support only
+    kmin = 1e300; kmax = -1e300;
+#pragma unroll
+    for (int j = 0; j < NAMP / 16; j++) {
+      const unsigned ww[4] = {dq[j].x, dq[j].y, dq[j].z, dq[j].w};
+#pragma unroll
+      for (int b = 0; b < 16; b++) {
+        const unsigned k = (ww[b >> 2] >> (8 * (b & 3))) & 0xffu;
+        real re, im;
+        amp_get(v, j * 16 + b, re, im);
+        re *= post;
+        im *= post;
+        if (re * re + im * im > (real)0) { kmin = fmin(kmin, (double)k); kmax = fmax(kmax, (double)k); }
+      }
+    }
+  }
+  acc[0] += (double)s0;
+  acc[1] += (double)s1;
+  acc[2] += (double)s2;
+  acc[3] = fmin(acc[3], kmin);
+  acc[4] = fmax(acc[4], kmax);
+}
+
+// same, any diagonal kind, stream read in place
+template <typename Elem, int DK>
+__device__ __forceinline__ void op_reduce_acc(const Ctx<Elem>& c, Elem (&v)[32], int slot, double (&acc)[5]) {
+  typedef typename ElemTraits<Elem>::real real;
+  constexpr int NAMP = ElemTraits<Elem>::NAMP;
+  const TilePass& P = *c.P;
+  const real post = (real)__ldg(c.phs + 2 * P.nphases);
+  real s0 = 0, s1 = 0, s2 = 0;
+  double kmin = 1e300, kmax = -1e300;
+  const int kind = DK == DIAG_U8 ? (int)DIAG_U8 : c.dinfo.kind;
+  for_each_diag<NAMP>(P.streams[slot], kind, c.tile, c.warp, c.lane, [&](int a, unsigned k, double cd) {
+    real re, im;
+    amp_get(v, a, re, im);
+    re *= post;
+    im *= post;
+    real p = re * re + im * im;
+    real kv = kind == DIAG_F64 ? (real)cd : (real)k;
+    double kdv = kind == DIAG_F64 ? cd : (double)k;
+    s0 += p;
+    s1 = fma(p, kv, s1);
+    s2 = fma(p * kv, kv, s2);
+    if (p > (real)0) { kmin = fmin(kmin, kdv); kmax = fmax(kmax, kdv); }
+  });
+  acc[0] += (double)s0;
+  acc[1] += (double)s1;
+  acc[2] += (double)s2;
+  acc[3] = fmin(acc[3], kmin);
+  acc[4] = fmax(acc[4], kmax);
+}
+
+// block tree over the per-thread accumulators -> partials[point][cta], then reset
+template <typename Elem>
+__device__ __forceinline__ void flush_acc(const Ctx<Elem>& c, double (&acc)[5], unsigned point) {
+  block_reduce5(acc, c.scratch);
+  if (threadIdx.x == 0) {
+    double* o = c.partials + ((size_t)point * gridDim.x + blockIdx.x) * 5;
+#pragma unroll
+    for (int i = 0; i < 5; i++) o[i] = acc[i];
+  }
+  acc[0] = 0.0; acc[1] = 0.0; acc[2] = 0.0; acc[3] = 1e300; acc[4] = -1e300;
 }
 
 template <typename Elem>
@@ -486,7 +696,8 @@ template <typename Elem>
 __device__ __forceinline__ void ctx_init(Ctx<Elem>& c, const TilePass& P, Elem* state, size_t point_stride,
                                          const typename ElemTraits<Elem>::real* tau, const double* phs,
                                          const void* tables, int tables_per_point, const DiagInfo& dinfo,
-                                         double* partials, unsigned char* smem, unsigned long long total) {
+                                         double* partials, unsigned char* smem, int tab_off, int scratch_off,
+                                         unsigned long long total) {
   c.P = &P;
   c.lane = threadIdx.x & 31;
   c.warp = threadIdx.x >> 5;
@@ -502,6 +713,8 @@ __device__ __forceinline__ void ctx_init(Ctx<Elem>& c, const TilePass& P, Elem* 
   c.dinfo = dinfo;
   c.partials = partials;
   c.smem = smem;
+  c.tab = smem + tab_off;
+  c.scratch = reinterpret_cast<double*>(smem + scratch_off);
   ctx_smem_setup(c);
   ctx_set_tile(c, blockIdx.x);
 }
@@ -514,25 +727,31 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // Asynchronous copies of register pairs [Q0, Q1) of tile `id` into this thread's private slots.
-// Pairs < TILE_STAGE_PAIRS live in the dedicated staging area ("early" group, issued right after the
-// current tile has been pulled into registers); the remaining pairs use the first 40 KB of the
-// exchange buffer ("late" group, issued once the tile's last transpose is done with that buffer).
-template <typename Elem, int Q0, int Q1>
+// Pairs < STAGE_PAIRS live in the dedicated staging area ("early" group, issued right after the
+// current tile has been pulled into registers); the remaining pairs use the start of the exchange
+// buffer ("late" group, issued once the tile's last transpose is done with that buffer).  With
+// L2_REST the lines of the pairs >= Q1 are pulled into L2 so that the late group is an L2 hit.
+template <typename Elem, int Q0, int Q1, bool L2_REST>
 __device__ __forceinline__ void stage_issue(const Ctx<Elem>& c, unsigned long long id, int frame) {
+  constexpr int SP = TileSmem<Elem>::STAGE_PAIRS;
   if (id < c.total) {
     const TilePass& P = *c.P;
     const unsigned ntile = (unsigned)(id % c.ntiles), npoint = (unsigned)(id / c.ntiles);
     TileAddr ad = tile_addr_off(P, tile_base(P, ntile), frame, c.thr[frame]);
     const Elem* p = c.state0 + (size_t)npoint * c.point_stride + ad.e0;
     const unsigned sb = (unsigned)__cvta_generic_to_shared(c.smem);
-    const unsigned early = sb + TILE_STAGE_OFFSET + threadIdx.x * 16u;
-    // late slots sit inside the OWNING warp's 8 KB transpose region, so the only writers that can
-    // touch them before they are consumed are the warp's own (program-ordered) transposes
+    const unsigned early = sb + TileSmem<Elem>::STAGE_OFF + threadIdx.x * 16u;
+    // late slots sit inside the OWNING warp's 8 KB region of the exchange buffer; every block-wide
+    // transpose starts with a barrier, so they are consumed before anybody else writes there
     const unsigned late = sb + c.warp * 8192u + c.lane * 16u;
 #pragma unroll
     for (int q = Q0; q < Q1; q++) {
-      const unsigned dst = q < TILE_STAGE_PAIRS ? early + q * (TILE_THREADS * 16) : late + (q - TILE_STAGE_PAIRS) * 512;
+      const unsigned dst = q < SP ? early + q * (TILE_THREADS * 16) : late + (q - SP) * 512;
       cp_async16(dst, p + reg_off(ad, q));
+    }
+    if (L2_REST) {
+#pragma unroll
+      for (int q = Q1; q < 16; q++) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + reg_off(ad, q)));
     }
   }
   cp_async_commit();
@@ -541,16 +760,17 @@ __device__ __forceinline__ void stage_issue(const Ctx<Elem>& c, unsigned long lo
 // persistent-kernel load: every register pair comes from the slots filled during the previous tile
 template <typename Elem>
 __device__ __forceinline__ void op_load_staged(const Ctx<Elem>& c, Elem (&v)[32], int frame) {
+  constexpr int SP = TileSmem<Elem>::STAGE_PAIRS;
   cp_async_wait_all();
-  const unsigned char* early = c.smem + TILE_STAGE_OFFSET + threadIdx.x * 16;
+  const unsigned char* early = c.smem + TileSmem<Elem>::STAGE_OFF + threadIdx.x * 16;
   const unsigned char* late = c.smem + c.warp * 8192 + c.lane * 16;
 #pragma unroll
   for (int q = 0; q < 16; q++) {
-    const unsigned char* src = q < TILE_STAGE_PAIRS ? early + q * (TILE_THREADS * 16) : late + (q - TILE_STAGE_PAIRS) * 512;
+    const unsigned char* src = q < SP ? early + q * (TILE_THREADS * 16) : late + (q - SP) * 512;
     load16(reinterpret_cast<const Elem*>(src), v[2 * q], v[2 * q + 1]);
   }
   __syncwarp();
-  stage_issue<Elem, 0, TILE_STAGE_PAIRS>(c, c.id + c.stride, frame);
+  stage_issue<Elem, 0, SP, true>(c, c.id + c.stride, frame);
 }
 
 // ---- interpreter kernel -------------------------------------------------------------------
@@ -563,7 +783,7 @@ tile_pass_kernel(const __grid_constant__ TilePass P, Elem* __restrict__ state, s
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   Ctx<Elem> c;
   ctx_init<Elem>(c, P, state, point_stride, tau, phs, tables, tables_per_point, dinfo, partials, smem_raw,
-                 (unsigned long long)gridDim.x);
+                 TILE_EXCH_BYTES, TILE_EXCH_BYTES + 4096, (unsigned long long)gridDim.x);
   Elem v[32];
   TileOp op = P.ops[0];
   for (int io = 0; io < P.nops; io++) {
@@ -577,6 +797,8 @@ tile_pass_kernel(const __grid_constant__ TilePass P, Elem* __restrict__ state, s
       case TOP_ROUND: round_dynamic<Elem>(c, v, cur.arg); break;
       case TOP_WT: warp_transpose<Elem>(c, v); break;
       case TOP_BT: block_transpose<Elem>(c, v); break;
+      case TOP_XT: xt_a_to_c<Elem>(c, v); break;
+      case TOP_XTI: xt_c_to_a<Elem>(c, v); break;
       case TOP_REDUCE: op_reduce<Elem, 0>(c, v, cur.arg); break;
       default: break;
     }
@@ -590,38 +812,52 @@ struct COp {
 
 constexpr int M_ALL = 0x1f, M_HI4 = 0x1e, M_TOP2 = 0x18;
 
-// full cover of all 14 tile bits starting in frame F (ends in frame F^1)
-//   R(all) WT R(all) BT R(hi4)
-// high cover of the 10 upper tile bits:  R(hi4) WT R(top2) BT R(hi4)
+// full cover of all 14 tile bits starting in frame F (ends in frame F^1):  R(all) WT R(all) BT R(hi4)
+// high cover of the 10 upper tile bits:                                    R(hi4) WT R(top2) BT R(hi4)
+// high cover of the 9 upper tile bits through frame C:                     R(hi4) XT R(all)   [XTI R(hi4)]
+#define PROG_COMMON                                                                                  \
+  static constexpr int find_last(int t0, int t1, int t2, int t3) {                                   \
+    int k = -1;                                                                                      \
+    for (int i = 0; i < N; i++)                                                                      \
+      if (op(i).type == t0 || op(i).type == t1 || op(i).type == t2 || op(i).type == t3) k = i;       \
+    return k;                                                                                        \
+  }                                                                                                  \
+  static constexpr int last_transpose() { return find_last(TOP_BT, TOP_XT, TOP_XTI, TOP_BT); }       \
+  static constexpr int stream_op() { return find_last(TOP_PHASE, TOP_REDUCE, TOP_PHASE, TOP_PHASE); } \
+  static constexpr int n_stream_ops() {                                                              \
+    int k = 0;                                                                                       \
+    for (int i = 0; i < N; i++) if (op(i).type == TOP_PHASE || op(i).type == TOP_REDUCE) k++;        \
+    return k;                                                                                        \
+  }
+
 struct ProgFirstInit {  // |+>/Dicke generated in registers, phase 1, full layer-1 cover of the tile
-  static constexpr int last_bt() { int k = -1; for (int i = 0; i < N; i++) if (op(i).type == TOP_BT) k = i; return k; }
   static constexpr int N = 8;
   static constexpr COp op(int i) {
     constexpr COp o[N] = {{TOP_INIT, 0, 0, 0}, {TOP_PHASE, 0, 0, 0}, {TOP_ROUND, 0, 0, M_ALL}, {TOP_WT, 0, 0, 0},
                           {TOP_ROUND, 0, 1, M_ALL}, {TOP_BT, 0, 0, 0}, {TOP_ROUND, 0, 2, M_HI4}, {TOP_STORE, 1, 0, 0}};
     return o[i];
   }
+  PROG_COMMON
 };
 struct ProgFirstLoad {
-  static constexpr int last_bt() { int k = -1; for (int i = 0; i < N; i++) if (op(i).type == TOP_BT) k = i; return k; }
   static constexpr int N = 8;
   static constexpr COp op(int i) {
     constexpr COp o[N] = {{TOP_LOAD, 0, 0, 0}, {TOP_PHASE, 0, 0, 0}, {TOP_ROUND, 0, 0, M_ALL}, {TOP_WT, 0, 0, 0},
                           {TOP_ROUND, 0, 1, M_ALL}, {TOP_BT, 0, 0, 0}, {TOP_ROUND, 0, 2, M_HI4}, {TOP_STORE, 1, 0, 0}};
     return o[i];
   }
+  PROG_COMMON
 };
 struct ProgInterior {
-  static constexpr int last_bt() { int k = -1; for (int i = 0; i < N; i++) if (op(i).type == TOP_BT) k = i; return k; }
   static constexpr int N = 7;
   static constexpr COp op(int i) {
     constexpr COp o[N] = {{TOP_LOAD, 0, 0, 0}, {TOP_ROUND, 0, 0, M_HI4}, {TOP_WT, 0, 0, 0}, {TOP_ROUND, 0, 1, M_TOP2},
                           {TOP_BT, 0, 0, 0}, {TOP_ROUND, 0, 2, M_HI4}, {TOP_STORE, 1, 0, 0}};
     return o[i];
   }
+  PROG_COMMON
 };
 struct ProgBoundary {
-  static constexpr int last_bt() { int k = -1; for (int i = 0; i < N; i++) if (op(i).type == TOP_BT) k = i; return k; }
   static constexpr int N = 13;
   static constexpr COp op(int i) {
     constexpr COp o[N] = {{TOP_LOAD, 0, 0, 0}, {TOP_ROUND, 0, 0, M_HI4}, {TOP_WT, 0, 0, 0}, {TOP_ROUND, 0, 1, M_TOP2},
@@ -630,40 +866,108 @@ struct ProgBoundary {
                           {TOP_STORE, 0, 0, 0}};
     return o[i];
   }
+  PROG_COMMON
 };
 struct ProgFinal {
-  static constexpr int last_bt() { int k = -1; for (int i = 0; i < N; i++) if (op(i).type == TOP_BT) k = i; return k; }
   static constexpr int N = 7;
   static constexpr COp op(int i) {
     constexpr COp o[N] = {{TOP_LOAD, 0, 0, 0}, {TOP_ROUND, 0, 0, M_HI4}, {TOP_WT, 0, 0, 0}, {TOP_ROUND, 0, 1, M_TOP2},
                           {TOP_BT, 0, 0, 0}, {TOP_ROUND, 0, 2, M_HI4}, {TOP_REDUCE, 1, 0, 0}};
     return o[i];
   }
+  PROG_COMMON
 };
+// ---- balanced schedule (complex64, 5 low bits, >= 3 tile shapes): per layer one MID pass over the
+// low tile (14 qubits) and one BOUND2 pass over a high tile (9 qubits of layer d, phase d+1, the
+// same 9 qubits of layer d+1), two transposes each; FINAL2 needs a single transpose.
+struct ProgMid {
+  static constexpr int N = 7;
+  static constexpr COp op(int i) {
+    constexpr COp o[N] = {{TOP_LOAD, 0, 0, 0}, {TOP_ROUND, 0, 0, M_ALL}, {TOP_WT, 0, 0, 0}, {TOP_ROUND, 0, 1, M_ALL},
+                          {TOP_BT, 0, 0, 0}, {TOP_ROUND, 0, 2, M_HI4}, {TOP_STORE, 1, 0, 0}};
+    return o[i];
+  }
+  PROG_COMMON
+};
+struct ProgBound2 {
+  static constexpr int N = 9;
+  static constexpr COp op(int i) {
+    constexpr COp o[N] = {{TOP_LOAD, 0, 0, 0}, {TOP_ROUND, 0, 0, M_HI4}, {TOP_XT, 0, 0, 0}, {TOP_ROUND, 0, 1, M_ALL},
+                          {TOP_PHASE, 2, 0, 0}, {TOP_ROUND, 0, 2, M_ALL}, {TOP_XTI, 0, 0, 0}, {TOP_ROUND, 0, 3, M_HI4},
+                          {TOP_STORE, 0, 0, 0}};
+    return o[i];
+  }
+  PROG_COMMON
+};
+struct ProgFinal2 {
+  static constexpr int N = 5;
+  static constexpr COp op(int i) {
+    constexpr COp o[N] = {{TOP_LOAD, 0, 0, 0}, {TOP_ROUND, 0, 0, M_HI4}, {TOP_XT, 0, 0, 0}, {TOP_ROUND, 0, 1, M_ALL},
+                          {TOP_REDUCE, 2, 0, 0}};
+    return o[i];
+  }
+  PROG_COMMON
+};
+
+// Per-point residents of the compiled-program kernels: the round coefficients (and the reduction
+// scale, parked in the pad slot 11 of round 0) and, for U8 diagonals, the phase table of the
+// program's PHASE step.  Called whenever the CTA moves on to a new point.
+template <typename Elem, typename Prog, int DK>
+__device__ __forceinline__ void point_setup(const Ctx<Elem>& c) {
+  typedef typename ElemTraits<Elem>::real real;
+  typedef typename ElemTraits<Elem>::cplx cplx;
+  const TilePass& P = *c.P;
+  real* tau_s = reinterpret_cast<real*>(c.smem + TileSmem<Elem>::TAU_OFF);
+  __syncthreads();
+  if ((int)threadIdx.x < P.tau_stride) {
+    real val = __ldg(c.tau + threadIdx.x);
+    if (threadIdx.x == 11) val = (real)__ldg(c.phs + 2 * P.nphases);
+    tau_s[threadIdx.x] = val;
+  }
+  constexpr int so = Prog::stream_op();
+  if constexpr (DK == DIAG_U8 && so >= 0) {
+    if constexpr (Prog::op(so >= 0 ? so : 0).type == TOP_PHASE) {
+      if (threadIdx.x >= 256) {
+        const cplx* t = reinterpret_cast<const cplx*>(c.tables) +
+                        ((size_t)c.point * c.tables_per_point + P.table_id[Prog::op(so).arg]) * 256;
+        reinterpret_cast<cplx*>(c.tab)[threadIdx.x - 256] = t[threadIdx.x - 256];
+      }
+    }
+  }
+  __syncthreads();
+}
 
 template <typename Elem, typename Prog, int DK, int I>
 struct ProgExec {
-  static __device__ __forceinline__ void run(const Ctx<Elem>& c, Elem (&v)[32]) {
+  static __device__ __forceinline__ void run(const Ctx<Elem>& c, Elem (&v)[32], const uint4 (&dq)[2], double (&acc)[5]) {
+    typedef typename ElemTraits<Elem>::real real;
     if constexpr (I < Prog::N) {
       constexpr COp op = Prog::op(I);
+      constexpr bool REGS = DK == DIAG_U8 && Prog::n_stream_ops() == 1;   // stream words prefetched in dq
+      const real* tau_s = reinterpret_cast<const real*>(c.smem + TileSmem<Elem>::TAU_OFF);
       if constexpr (op.type == TOP_LOAD) { op_load_staged<Elem>(c, v, op.frame); prefetch_later_tile<Elem>(c); }
       else if constexpr (op.type == TOP_STORE) op_store<Elem>(c, v, op.frame);
       else if constexpr (op.type == TOP_INIT) op_init<Elem>(c, v, op.frame);
-      else if constexpr (op.type == TOP_PHASE) op_phase<Elem, DK>(c, v, op.arg);
-      else if constexpr (op.type == TOP_ROUND) {
-        // complex128: register slot 0 of frames A/B is the re/im bit, never a qubit
-        round_static<Elem, op.mask>(c, v, op.arg);
+      else if constexpr (op.type == TOP_PHASE) {
+        if constexpr (REGS) op_phase_u8_regs<Elem>(c, v, dq);
+        else op_phase<Elem, DK>(c, v, op.arg);
       }
+      else if constexpr (op.type == TOP_ROUND) round_static<Elem, op.mask>(tau_s, v, op.arg);
       else if constexpr (op.type == TOP_WT) warp_transpose<Elem>(c, v);
-      else if constexpr (op.type == TOP_BT) {
-        block_transpose<Elem>(c, v);
-        if constexpr (Prog::op(0).type == TOP_LOAD && I == Prog::last_bt()) {
+      else if constexpr (op.type == TOP_BT || op.type == TOP_XT || op.type == TOP_XTI) {
+        if constexpr (op.type == TOP_BT) block_transpose<Elem>(c, v);
+        else if constexpr (op.type == TOP_XT) xt_a_to_c<Elem>(c, v);
+        else xt_c_to_a<Elem>(c, v);
+        if constexpr (Prog::op(0).type == TOP_LOAD && I == Prog::last_transpose()) {
           __syncthreads();  // every warp has read its share of the exchange buffer
-          stage_issue<Elem, TILE_STAGE_PAIRS, 16>(c, c.id + c.stride, Prog::op(0).frame);
+          stage_issue<Elem, TileSmem<Elem>::STAGE_PAIRS, 16, false>(c, c.id + c.stride, Prog::op(0).frame);
         }
       }
-      else if constexpr (op.type == TOP_REDUCE) op_reduce<Elem, DK>(c, v, op.arg);
-      ProgExec<Elem, Prog, DK, I + 1>::run(c, v);
+      else if constexpr (op.type == TOP_REDUCE) {
+        if constexpr (REGS) op_reduce_u8_regs<Elem>(c, v, dq, tau_s[11], acc);
+        else op_reduce_acc<Elem, DK>(c, v, op.arg, acc);
+      }
+      ProgExec<Elem, Prog, DK, I + 1>::run(c, v, dq, acc);
     }
   }
 };
@@ -675,18 +979,49 @@ tile_prog_kernel(const __grid_constant__ TilePass P, Elem* __restrict__ state, s
                  const void* __restrict__ tables, int tables_per_point, DiagInfo dinfo,
                  double* __restrict__ partials, unsigned n_points) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
+  typedef TileSmem<Elem> L;
+  constexpr int NAMP = ElemTraits<Elem>::NAMP;
   Ctx<Elem> c;
   const unsigned long long total = (unsigned long long)P.ntiles * n_points;
-  ctx_init<Elem>(c, P, state, point_stride, tau, phs, tables, tables_per_point, dinfo, partials, smem_raw, total);
+  ctx_init<Elem>(c, P, state, point_stride, tau, phs, tables, tables_per_point, dinfo, partials, smem_raw,
+                 L::TABLE_OFF, L::SCRATCH_OFF, total);
   constexpr COp first = Prog::op(0);
   if constexpr (first.type == TOP_LOAD) {
-    stage_issue<Elem, 0, TILE_STAGE_PAIRS>(c, blockIdx.x, first.frame);
-    stage_issue<Elem, TILE_STAGE_PAIRS, 16>(c, blockIdx.x, first.frame);
+    stage_issue<Elem, 0, L::STAGE_PAIRS, false>(c, blockIdx.x, first.frame);
+    stage_issue<Elem, L::STAGE_PAIRS, 16, false>(c, blockIdx.x, first.frame);
+  }
+  constexpr bool HAS_RED = Prog::op(Prog::N - 1).type == TOP_REDUCE;
+  double acc[5] = {0.0, 0.0, 0.0, 1e300, -1e300};
+  if constexpr (HAS_RED) {
+    // partials[point][cta]: neutral entries for the points this CTA never touches
+    for (unsigned pt = threadIdx.x; pt < n_points; pt += TILE_THREADS) {
+      double* o = partials + ((size_t)pt * gridDim.x + blockIdx.x) * 5;
+      o[0] = 0.0; o[1] = 0.0; o[2] = 0.0; o[3] = 1e300; o[4] = -1e300;
+    }
   }
   Elem v[32];
+  unsigned loaded_point = 0xffffffffu;
   for (unsigned long long id = blockIdx.x; id < total; id += gridDim.x) {
     ctx_set_tile(c, id);
-    ProgExec<Elem, Prog, DK, 0>::run(c, v);
+    if (c.point != loaded_point) {
+      if constexpr (HAS_RED) {
+        if (loaded_point != 0xffffffffu) flush_acc<Elem>(c, acc, loaded_point);
+      }
+      point_setup<Elem, Prog, DK>(c);
+      loaded_point = c.point;
+    }
+    uint4 dq[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+    constexpr int so = Prog::stream_op();
+    if constexpr (DK == DIAG_U8 && Prog::n_stream_ops() == 1) {
+      // this tile's slice of the permuted diagonal: fetched now, consumed by the PHASE / REDUCE step
+      const uint4* s4 = reinterpret_cast<const uint4*>(P.streams[Prog::op(so >= 0 ? so : 0).arg]);
+#pragma unroll
+      for (int j = 0; j < NAMP / 16; j++) dq[j] = __ldg(s4 + stream_chunk(c.tile, c.warp, c.lane, NAMP / 16, j));
+    }
+    ProgExec<Elem, Prog, DK, 0>::run(c, v, dq, acc);
+  }
+  if constexpr (HAS_RED) {
+    if (loaded_point != 0xffffffffu) flush_acc<Elem>(c, acc, loaded_point);
   }
 }
 
@@ -709,24 +1044,23 @@ inline bool prog_matches(const TilePass& tp) {
 }
 
 // Builds one permuted diagonal stream: stream[(tile, warp, chunk, lane, i)] = diag[x(tile,warp,lane,amp)]
-// using exactly the addressing of the pass kernels (same helper functions).
+// using exactly the addressing of the pass kernels (same helper functions).  namp == 32: amplitude a is
+// register a (complex64, every frame); namp == 16: amplitude a is the register pair (2a, 2a+1)
+// (complex128, frames A and B).
 template <int VALBYTES>
 __global__ void make_stream_kernel(const __grid_constant__ TilePass P, int frame, int namp,
                                    const unsigned char* __restrict__ diag,
                                    unsigned char* __restrict__ stream) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned tile = blockIdx.x;
-  const size_t base = tile_base(P, tile);
-  TileAddr ad = tile_addr(P, base, frame, warp, lane);
+  const size_t e0 = tile_base(P, tile) + thread_off(P, frame, warp, lane);
   constexpr int V = 16 / VALBYTES;
   const int nchunks = namp / V;
   for (int j = 0; j < nchunks; j++) {
     __align__(16) unsigned char buf[16];
     for (int i = 0; i < V; i++) {
       const int a = j * V + i;
-      // amplitude a -> register pair q: complex64: q = a>>1 with low bit a&1; complex128: q = a
-      const int q = (namp == 32) ? (a >> 1) : a;
-      const size_t e = ad.e0 + reg_off(ad, q) + ((namp == 32) ? (a & 1) : 0);
+      const size_t e = e0 + reg_elem_off(P, frame, namp == 32 ? a : 2 * a);
       const unsigned char* src = diag + (e >> P.qshift) * VALBYTES;
 #pragma unroll
       for (int b = 0; b < VALBYTES; b++) buf[i * VALBYTES + b] = src[b];

@@ -19,8 +19,8 @@ def _engine(n, dtype):
     return eng, eng.Engine(n, dtype=dtype)
 
 
-def _check(out, spec, angles, dtype, what=""):
-    e, e2, mn, mx = orc.energy(spec, angles)
+def _check(out, spec, angles, dtype, what="", ref=None):
+    e, e2, mn, mx = orc.energy(spec, angles) if ref is None else ref
     tol = TOL[dtype]
     assert H.rel_err(out[0], e) < tol, (what, out, e)
     assert H.rel_err(out[1], e2) < 2 * tol, (what, out, e2)
@@ -254,3 +254,59 @@ def test_beta_at_and_near_half_pi(dtype):
     for betas in ([np.pi / 2, 0.3], [np.pi / 2 - 1e-9, 3 * np.pi / 2], [1.5, 1.6], [0.0, np.pi]):
         ang = np.array([0.8, betas[0], 0.35, betas[1]])
         _check(E.energy(ang), spec, ang, dtype, "betas=%r" % (betas,))
+
+
+@pytest.mark.parametrize("n,ps", [(25, (1, 2, 3)), (26, (2,))])
+def test_balanced_schedule_vs_classic_vs_oracle(n, ps):
+    """complex64, n >= 25 (5 low bits, 3 tile shapes): the balanced schedule (MID + BOUND2 passes through
+    frame C, FINAL2) must agree with the classic schedule (INTERIOR + BOUNDARY), with the interpreter
+    running the same balanced plan, and with the oracle (C twin of the numpy oracle, pinned to it in
+    tests/test_oracle.py -- the numpy one needs minutes at this size).  n=26 pads the top tile with lower bits."""
+    from oracle import c_oracle
+    dtype = "complex64"
+    eng, E = _engine(n, dtype)
+    edges, colors, table = H.regular_maxcut(n)
+    lut, _ = H.lut_from_table(table, 1)
+    E.set_cost_maxkcut(n, edges, 1, lut)
+    diag = c_oracle.maxcut_diag(n, edges)
+    got_diag = E.read_cost_diagonal(0, 1 << 16)
+    assert np.array_equal(got_diag, diag[: 1 << 16])
+    rng = np.random.default_rng(77)
+    for p in ps:
+        ang = rng.uniform(0, 2 * np.pi, size=2 * p)
+        ang[1::2] = rng.uniform(-1.2, 1.2, size=p)
+        ref = c_oracle.energy(n, diag, ang, "complex128")
+        E.set_option("schedule", 0)
+        E.set_option("force_generic", 0)
+        E.counter("reset")
+        a = E.energy(ang)
+        assert E.counter("prog_launches") >= 2
+        npass_bal = E.counter("n_passes")
+        E.set_option("force_generic", 1)
+        b = E.energy(ang)
+        E.set_option("force_generic", 0)
+        E.set_option("schedule", 1)
+        c = E.energy(ang)
+        assert E.counter("n_passes") == npass_bal, "same number of HBM sweeps in both schedules"
+        for got in (a, b, c):
+            _check(got, None, ang, dtype, "n=%d p=%d" % (n, p), ref=ref)
+        assert H.rel_err(a[0], b[0]) < 1e-5 and H.rel_err(a[0], c[0]) < 1e-5, (a, b, c, ref)
+
+
+def test_balanced_schedule_real_valued_costs_and_multiangle():
+    """Balanced schedule with a U32FX diagonal (QUBO, complex64) and per-qubit betas (XMultiAngle)."""
+    from oracle import c_oracle
+    n, p = 25, 2
+    eng, E = _engine(n, "complex64")
+    Q, c, b = H.random_qubo(n)
+    E.set_cost_qubo(Q, c, b)
+    E.set_mixer(eng.MIXER_XMULTI)
+    diag = c_oracle.qubo_diag(Q, c, b)
+    rng = np.random.default_rng(5)
+    ang = rng.uniform(-1.0, 1.0, size=p * (1 + n))
+    ang[0::(1 + n)] *= 0.05     # gammas: QUBO costs are O(100)
+    ref = c_oracle.energy(n, diag, ang, "complex128", n_beta=n)
+    E.counter("reset")
+    out = E.energy(ang)
+    assert E.counter("prog_launches") >= 2
+    _check(out, None, ang, "complex64", "qubo n=25", ref=ref)

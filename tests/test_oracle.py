@@ -293,3 +293,20 @@ def test_c_oracle_matches_numpy_oracle():
     assert np.allclose(got, ref, rtol=1e-12)
     got32 = c_oracle.energy(n, d.astype(float), ang, "complex64")
     assert np.allclose(got32[:2], ref[:2], rtol=1e-4)
+
+
+def test_c_oracle_qubo_and_multiangle_match_numpy_oracle():
+    """The C twin used as checker at n >= 24 (QUBO diagonal, per-qubit betas) is pinned to the numpy oracle."""
+    from oracle import c_oracle
+
+    n = 11
+    rs = np.random.RandomState(42)
+    Q, c, b = rs.rand(n, n), 3 * (rs.rand(n) - 0.5), 0.25
+    d = orc.qubo_diag(Q, c, b)
+    dc = c_oracle.qubo_diag(Q, c, b)
+    assert np.allclose(dc, d, rtol=1e-13, atol=1e-12)
+    rng = np.random.default_rng(9)
+    ang = rng.uniform(-1, 1, size=2 * (1 + n))
+    ref = orc.energy(orc.Spec(n, d, mixer=("xmulti",)), ang)
+    got = c_oracle.energy(n, d, ang, "complex128", n_beta=n)
+    assert np.allclose(got, ref, rtol=1e-11)
