@@ -46,7 +46,7 @@ const char* qaoa_last_error(qaoa_engine_t* h);
 const char* qaoa_global_error(void);
 
 /* Tunables / test hooks: "small_max_qubits", "keep_state", "batch_points", "batch_bytes",
- * "force_generic", "prefetch_dist", "persistent_ctas", "low_bits", "time_passes". */
+ * "force_generic", "prefetch_dist", "persistent_ctas", "low_bits", "schedule", "time_passes". */
 int qaoa_set_option(qaoa_engine_t* h, const char* key, double value);
 double qaoa_get_counter(qaoa_engine_t* h, const char* key); /* "launches", "bytes_alg", ... */
 
@@ -91,6 +91,37 @@ int qaoa_fetch_results(qaoa_engine_t* h, int B, double* out);
 /* Final state of the last qaoa_energy call made with option keep_state=1 (true amplitudes,
  * complex128 interleaved).  Test / debugging aid; 2^n * 16 bytes on the host. */
 int qaoa_read_statevector(qaoa_engine_t* h, double* out);
+
+/* ---- Sharded registers: one engine per GPU (one process per GPU), the register split on its top
+ * log2(world) qubits; rank r holds the basis indices [r * 2^(n - log2 world), (r+1) * 2^(n - log2 world)).
+ * There is nothing to replace in the reference (it has no multi-device path);
+ * the boundary mirrors qaoa_energy: same angle layout, same result semantics.
+ *
+ * Mixer gates on the top ("global") qubits are executed by CROSS passes: ordinary tile passes whose
+ * tile contains the rank bits, so that their loads and stores go to the peers' HBM over NVLink
+ * (peer memory) -- the exchange is fused into the pass, there is no separate swap or staging buffer.
+ * The caller provides the peers' buffers, either as CUDA IPC handles (one process per GPU) or as raw
+ * device pointers (several engines inside one process), and separates passes with a barrier across
+ * ranks whenever qaoa_shard_pass_is_cross says so for the pass before or after it:
+ *
+ *   qaoa_create_sharded on every rank; qaoa_set_cost_* / qaoa_set_mixer / qaoa_set_initial
+ *   exchange qaoa_shard_export(which=0 state, 1 cost diagonal) handles -> qaoa_shard_import; barrier
+ *   qaoa_shard_begin(p, angles) -> n_passes
+ *   for i < n_passes: [barrier if pass i or pass i-1 is cross]  qaoa_shard_run_pass(i); qaoa_shard_sync
+ *   qaoa_shard_finish(out5) -> this rank's {sum p, sum p c, sum p c^2, min c, max c};
+ *   combine over ranks with (sum, sum, sum, min, max): E[c] = S1/S0, E[c^2] = S2/S0, norm = S0.
+ * Supported: X / multi-angle X mixers, Plus / Dicke initial states, every cost generator. */
+int qaoa_create_sharded(int n_qubits, int dtype, int device, int rank, int world, qaoa_engine_t** out);
+int qaoa_shard_info(qaoa_engine_t* h, int* rank, int* world, int* local_qubits);
+int qaoa_shard_local_ptr(qaoa_engine_t* h, int which, void** out);
+int qaoa_shard_set_peers(qaoa_engine_t* h, int which, void* const* ptrs);
+int qaoa_shard_export(qaoa_engine_t* h, int which, unsigned char* handle64);
+int qaoa_shard_import(qaoa_engine_t* h, int which, const unsigned char* handles);
+int qaoa_shard_begin(qaoa_engine_t* h, int p, const double* angles, int n_angles, int* n_passes);
+int qaoa_shard_pass_is_cross(qaoa_engine_t* h, int pass); /* 1 / 0, -1 on error */
+int qaoa_shard_run_pass(qaoa_engine_t* h, int pass);
+int qaoa_shard_sync(qaoa_engine_t* h);
+int qaoa_shard_finish(qaoa_engine_t* h, double* out5);
 
 /* Profiling hook: runs an arbitrary (type, frame, mask) step program of the tiled pass kernel and
  * returns the mean CUDA-event time per launch (scripts/tile_floor.py). */

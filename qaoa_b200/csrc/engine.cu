@@ -57,10 +57,12 @@ struct PlanPass {
   size_t tau_offset = 0;  // reals, per point block
   size_t phs_offset = 0;  // doubles, per point block
   int prog = PROG_GENERIC;
+  bool cross = false;
 };
 struct Shape {
   int pos[TILE_BITS];
   std::vector<int> freepos;
+  bool cross = false;   // contains element bits owned by other ranks (sharded registers)
 };
 struct Plan {
   int p = 0;
@@ -72,8 +74,16 @@ struct Plan {
 
 struct Engine {
   int n = 0, dtype = 0, device = 0;
-  int qshift = 0, E = 0;     // element bits
-  size_t N = 0;              // basis states
+  int qshift = 0, E = 0;     // element bits of the WHOLE register
+  size_t N = 0;              // basis states held by THIS engine (2^n, or 2^(n - gbits) when sharded)
+  // sharding: the register is split on its top gbits qubits over world = 2^gbits engines
+  int rank = 0, world = 1, gbits = 0;
+  int El = 0;                // element bits of the local shard (E - gbits)
+  size_t x0 = 0;             // first basis index of the local shard
+  void* peer_state[QAOA_MAX_RANKS] = {nullptr};
+  void* peer_diag[QAOA_MAX_RANKS] = {nullptr};
+  bool peer_state_ipc[QAOA_MAX_RANKS] = {false}, peer_diag_ipc[QAOA_MAX_RANKS] = {false};
+  bool peers_state_set = false, peers_diag_set = false;
   size_t amp_bytes = 8;
   cudaStream_t stream = nullptr;
 
@@ -128,6 +138,16 @@ struct Engine {
   bool last_valid = false;
   int last_path = 0;  // 0 small/elementwise (plain S frame), 1 tile
 
+  // context of the evaluation in flight (pass-by-pass execution)
+  struct EvalCtx {
+    Plan* pl = nullptr;
+    int Bc = 0;
+    size_t tau_bytes = 0;
+    std::vector<char> all_normal;
+    std::vector<size_t> tbase, pbase;
+    int nparts = 0;
+  } ev;
+
   double launches = 0;
   double prog_launches = 0;
   double bytes_alg = 0;
@@ -139,6 +159,7 @@ struct Engine {
   std::vector<PendingEv> ev_pending;
   double last_device_ms = 0;
   cudaEvent_t ev_call0 = nullptr, ev_call1 = nullptr;
+  bool ev_call_recorded = false;
   std::string err;
 
   int small_max() const {
@@ -167,6 +188,18 @@ void ensure_state(Engine* h, size_t points) {
   h->state_points = points;
 }
 
+// forget the peer pointers of the state (which = 0) or the cost diagonal (which = 1)
+void close_peers(Engine* h, int which) {
+  void** ptrs = which == 0 ? h->peer_state : h->peer_diag;
+  bool* ipc = which == 0 ? h->peer_state_ipc : h->peer_diag_ipc;
+  for (int r = 0; r < QAOA_MAX_RANKS; r++) {
+    if (ptrs[r] && ipc[r]) cudaIpcCloseMemHandle(ptrs[r]);
+    ptrs[r] = nullptr;
+    ipc[r] = false;
+  }
+  if (which == 0) h->peers_state_set = false; else h->peers_diag_set = false;
+}
+
 void free_streams(Engine* h) {
   for (auto& kv : h->streams) cudaFree(kv.second);
   h->streams.clear();
@@ -175,6 +208,27 @@ void free_streams(Engine* h) {
 void invalidate(Engine* h) {
   h->plans.clear();
   h->last_valid = false;
+}
+
+// sharding fields of a pass descriptor (see TilePass)
+void shard_fill(const Engine* h, TilePass& tp, bool cross) {
+  tp.shard_bits = h->world > 1 ? h->El : 0;
+  tp.rank_popc = __builtin_popcount((unsigned)h->rank);
+  tp.tile0 = 0;
+  if (h->world > 1) {
+    // tiles enumerate LOCAL free bits only (a cross tile has the rank bits among its tile bits, any
+    // other tile lives entirely inside the local shard)
+    int nf = 0;
+    for (int j = 0; j < tp.nfree; j++) if (tp.freepos[j] < h->El) tp.freepos[nf++] = tp.freepos[j];
+    tp.nfree = nf;
+    if (!tilepass_set_free_runs(tp)) fail("tile shape with more than two runs of free bits");
+    if (nf != h->El - (cross ? TILE_BITS - h->gbits : TILE_BITS)) fail("sharded tile shape straddles the shard boundary");
+  }
+  if (cross) {
+    if (!h->peers_state_set) fail("sharded engine: peer state pointers have not been set");
+    tp.tile0 = (unsigned)h->rank << (h->El - TILE_BITS);
+    for (int r = 0; r < h->world; r++) { tp.peers[r] = h->peer_state[r]; tp.dpeers[r] = h->peer_diag[r]; }
+  }
 }
 
 int grid_for(size_t N, int threads) {
@@ -218,6 +272,7 @@ void build_balanced(Engine* h, int p, Plan& pl) {
   auto begin = [&](int shape) {
     Builder b;
     b.sh = &pl.shapes[shape];
+    b.pp.cross = b.sh->cross;
     memset(&b.pp.tp, 0, sizeof(TilePass));
     TilePass& tp = b.pp.tp;
     for (int j = 0; j < TILE_BITS; j++) tp.pos[j] = b.sh->pos[j];
@@ -359,6 +414,7 @@ Plan build_plan(Engine* h, int p) {
     std::vector<int> bits;
     for (int b = 0; b < clow; b++) bits.push_back(b);
     int lo = clow + hper * i, hi = std::min(E, lo + hper);
+    if (h->world > 1 && i < m - 1) hi = std::min(hi, h->El);   // only the top tile may hold rank bits
     std::vector<int> own;
     for (int b = lo; b < hi; b++) own.push_back(b);
     int padb = lo - 1;
@@ -369,7 +425,12 @@ Plan build_plan(Engine* h, int p) {
     for (int j = 0; j < TILE_BITS; j++) s.pos[j] = bits[j];
     for (int b = 0; b < E; b++)
       if (!std::binary_search(bits.begin(), bits.end(), b)) s.freepos.push_back(b);
+    s.cross = h->world > 1 && bits.back() >= h->El;
     pl.shapes.push_back(s);
+  }
+  if (h->world > 1) {
+    if (m < 2 || pl.shapes[0].cross) fail("sharded engine: the local shard must hold at least 14 element bits");
+    for (int i = 0; i < m; i++) if (pl.shapes[i].cross != (i == m - 1)) fail("sharded engine: unexpected cross tile");
   }
   if (h->schedule != 1 && h->dtype == QAOA_DTYPE_C64 && clow == 5 && m >= 3 && !h->keep_state) {
     build_balanced(h, p, pl);
@@ -400,6 +461,7 @@ Plan build_plan(Engine* h, int p) {
     }
     const Shape& sh = pl.shapes[best];
     PlanPass pp;
+    pp.cross = sh.cross;
     memset(&pp.tp, 0, sizeof(TilePass));
     TilePass& tp = pp.tp;
     for (int j = 0; j < TILE_BITS; j++) tp.pos[j] = sh.pos[j];
@@ -521,11 +583,15 @@ void* get_stream(Engine* h, const Plan& pl, int shape, int frame) {
   for (int j = 0; j < tp.nfree; j++) tp.freepos[j] = sh.freepos[j];
   if (!tilepass_set_free_runs(tp)) fail("tile shape with more than two runs of free bits");
   tp.qshift = h->qshift;
-  const unsigned ntiles = 1u << (h->E - TILE_BITS);
+  const int cross = sh.cross ? 1 : 0;
+  if (cross && !h->peers_diag_set) fail("sharded engine: peer cost-diagonal pointers have not been set");
+  shard_fill(h, tp, sh.cross);
+  const unsigned ntiles = 1u << (h->El - TILE_BITS);
   const int namp = h->dtype == QAOA_DTYPE_C64 ? 32 : 16;
-  if (vb == 1) make_stream_kernel<1><<<ntiles, TILE_THREADS, 0, h->stream>>>(tp, frame, namp, (const unsigned char*)h->diag, (unsigned char*)s);
-  else if (vb == 4) make_stream_kernel<4><<<ntiles, TILE_THREADS, 0, h->stream>>>(tp, frame, namp, (const unsigned char*)h->diag, (unsigned char*)s);
-  else make_stream_kernel<8><<<ntiles, TILE_THREADS, 0, h->stream>>>(tp, frame, namp, (const unsigned char*)h->diag, (unsigned char*)s);
+  if (frame == 2 && namp != 32) fail("frame C streams exist for complex64 only");
+  if (vb == 1) make_stream_kernel<1><<<ntiles, TILE_THREADS, 0, h->stream>>>(tp, frame, namp, cross, (const unsigned char*)h->diag, (unsigned char*)s);
+  else if (vb == 4) make_stream_kernel<4><<<ntiles, TILE_THREADS, 0, h->stream>>>(tp, frame, namp, cross, (const unsigned char*)h->diag, (unsigned char*)s);
+  else make_stream_kernel<8><<<ntiles, TILE_THREADS, 0, h->stream>>>(tp, frame, namp, cross, (const unsigned char*)h->diag, (unsigned char*)s);
   CUDA_OK(cudaGetLastError());
   h->launches += 1;
   h->streams[key] = s;
@@ -638,12 +704,16 @@ int launch_pass(Engine* h, const PlanPass& pp, bool use_prog, unsigned ntiles, i
   TilePass tp = pp.tp;
   tp.ntiles = ntiles;
   tp.prefetch_dist = h->prefetch_dist;
-  const int prog = use_prog ? pp.prog : PROG_GENERIC;
+  shard_fill(h, tp, pp.cross);
+  int prog = use_prog ? pp.prog : PROG_GENERIC;
+  const bool cross = pp.cross;
+  // cross passes have compiled programs for the high-tile passes of the balanced schedule only
+  if (cross && prog != PROG_INTERIOR && prog != PROG_BOUND2 && prog != PROG_FINAL2) prog = PROG_GENERIC;
   const bool u8 = h->dinfo.kind == DIAG_U8;
   int nparts = (int)ntiles;
   // interpreter: one CTA per (tile, point); programs: persistent CTAs walking the linear index
   auto go_generic = [&]() {
-    auto kernel = tile_pass_kernel<Elem>;
+    auto kernel = cross ? tile_pass_kernel<Elem, true> : tile_pass_kernel<Elem, false>;
     CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES));
     tp.prefetch_dist = 0;
     // interpreter walks tiles of ONE point per launch row; use a flat grid over (point, tile)
@@ -661,14 +731,22 @@ int launch_pass(Engine* h, const PlanPass& pp, bool use_prog, unsigned ntiles, i
                                                                       tables_per_point, h->dinfo, h->d_partials, (unsigned)B);
   };
   switch (prog) {
-    case PROG_FIRST_INIT: if (u8) go(tile_prog_kernel<Elem, ProgFirstInit, DIAG_U8>); else go(tile_prog_kernel<Elem, ProgFirstInit, 0>); break;
-    case PROG_FIRST_LOAD: if (u8) go(tile_prog_kernel<Elem, ProgFirstLoad, DIAG_U8>); else go(tile_prog_kernel<Elem, ProgFirstLoad, 0>); break;
-    case PROG_INTERIOR: go(tile_prog_kernel<Elem, ProgInterior, DIAG_U8>); break;
-    case PROG_BOUNDARY: if (u8) go(tile_prog_kernel<Elem, ProgBoundary, DIAG_U8>); else go(tile_prog_kernel<Elem, ProgBoundary, 0>); break;
-    case PROG_FINAL: if (u8) go(tile_prog_kernel<Elem, ProgFinal, DIAG_U8>); else go(tile_prog_kernel<Elem, ProgFinal, 0>); break;
-    case PROG_MID: go(tile_prog_kernel<Elem, ProgMid, DIAG_U8>); break;
-    case PROG_BOUND2: if (u8) go(tile_prog_kernel<Elem, ProgBound2, DIAG_U8>); else go(tile_prog_kernel<Elem, ProgBound2, 0>); break;
-    case PROG_FINAL2: if (u8) go(tile_prog_kernel<Elem, ProgFinal2, DIAG_U8>); else go(tile_prog_kernel<Elem, ProgFinal2, 0>); break;
+    case PROG_FIRST_INIT: if (u8) go(tile_prog_kernel<Elem, ProgFirstInit, DIAG_U8, false>); else go(tile_prog_kernel<Elem, ProgFirstInit, 0, false>); break;
+    case PROG_FIRST_LOAD: if (u8) go(tile_prog_kernel<Elem, ProgFirstLoad, DIAG_U8, false>); else go(tile_prog_kernel<Elem, ProgFirstLoad, 0, false>); break;
+    case PROG_INTERIOR:
+      if (cross) go(tile_prog_kernel<Elem, ProgInterior, DIAG_U8, true>); else go(tile_prog_kernel<Elem, ProgInterior, DIAG_U8, false>);
+      break;
+    case PROG_BOUNDARY: if (u8) go(tile_prog_kernel<Elem, ProgBoundary, DIAG_U8, false>); else go(tile_prog_kernel<Elem, ProgBoundary, 0, false>); break;
+    case PROG_FINAL: if (u8) go(tile_prog_kernel<Elem, ProgFinal, DIAG_U8, false>); else go(tile_prog_kernel<Elem, ProgFinal, 0, false>); break;
+    case PROG_MID: go(tile_prog_kernel<Elem, ProgMid, DIAG_U8, false>); break;
+    case PROG_BOUND2:
+      if (cross) { if (u8) go(tile_prog_kernel<Elem, ProgBound2, DIAG_U8, true>); else go(tile_prog_kernel<Elem, ProgBound2, 0, true>); }
+      else { if (u8) go(tile_prog_kernel<Elem, ProgBound2, DIAG_U8, false>); else go(tile_prog_kernel<Elem, ProgBound2, 0, false>); }
+      break;
+    case PROG_FINAL2:
+      if (cross) { if (u8) go(tile_prog_kernel<Elem, ProgFinal2, DIAG_U8, true>); else go(tile_prog_kernel<Elem, ProgFinal2, 0, true>); }
+      else { if (u8) go(tile_prog_kernel<Elem, ProgFinal2, DIAG_U8, false>); else go(tile_prog_kernel<Elem, ProgFinal2, 0, false>); }
+      break;
     default: go_generic(); break;
   }
   CUDA_OK(cudaGetLastError());
@@ -676,10 +754,12 @@ int launch_pass(Engine* h, const PlanPass& pp, bool use_prog, unsigned ntiles, i
 }
 
 // tile path for a chunk of points [b0, b0+Bc)
-void run_tile_chunk(Engine* h, Plan& pl, const double* angles, int n_angles, int Bc, double* d_out_chunk,
-                    bool record_last) {
+// ---- tile path, executed pass by pass -----------------------------------------------------
+// tile_prepare lowers the angles of Bc points and uploads them (+ phase tables); tile_launch_pass
+// launches pass ip; tile_finalize turns the partial sums into {E, E2, min, max, norm} per point.
+void tile_prepare(Engine* h, Plan& pl, const double* angles, int n_angles, int Bc, bool record_last) {
   const int p = pl.p;
-  const unsigned ntiles = 1u << (h->E - TILE_BITS);
+  const unsigned ntiles = 1u << (h->El - TILE_BITS);
   const bool c64 = h->dtype == QAOA_DTYPE_C64;
   const size_t rsz = c64 ? 4 : 8;
   const size_t tpp = pl.tau_per_point, ppp = pl.phs_per_point;
@@ -695,7 +775,15 @@ void run_tile_chunk(Engine* h, Plan& pl, const double* angles, int n_angles, int
   double* h_phs = (double*)(hb + tau_bytes);
   double* hgs = (double*)(hb + tau_bytes + phs_bytes);
   std::vector<double> tau_tmp(tpp), phs_tmp(ppp);
-  std::vector<char> all_normal(pl.passes.size(), 1), an;
+  std::vector<char> an;
+  Engine::EvalCtx& ev = h->ev;
+  ev.pl = &pl;
+  ev.Bc = Bc;
+  ev.tau_bytes = tau_bytes;
+  ev.all_normal.assign(pl.passes.size(), 1);
+  ev.tbase.assign(pl.passes.size(), 0);
+  ev.pbase.assign(pl.passes.size(), 0);
+  ev.nparts = (int)ntiles;
   for (int b = 0; b < Bc; b++) {
     double fsc = 1.0;
     fill_point_params(h, pl, angles + (size_t)b * n_angles, tau_tmp.data(), phs_tmp.data(), hgs + (size_t)2 * p * b,
@@ -703,7 +791,7 @@ void run_tile_chunk(Engine* h, Plan& pl, const double* angles, int n_angles, int
     size_t tbase = 0, pbase = 0;
     for (size_t ip = 0; ip < pl.passes.size(); ip++) {
       const auto& pp = pl.passes[ip];
-      if (!an[ip]) all_normal[ip] = 0;
+      if (!an[ip]) ev.all_normal[ip] = 0;
       const size_t ts = pp.tp.tau_stride, ps = pp.tp.phs_stride;
       if (c64) {
         float* dst = (float*)hb + tbase + (size_t)b * ts;
@@ -712,6 +800,8 @@ void run_tile_chunk(Engine* h, Plan& pl, const double* angles, int n_angles, int
         memcpy((double*)hb + tbase + (size_t)b * ts, tau_tmp.data() + pp.tau_offset, ts * 8);
       }
       memcpy(h_phs + pbase + (size_t)b * ps, phs_tmp.data() + pp.phs_offset, ps * 8);
+      ev.tbase[ip] = tbase;
+      ev.pbase[ip] = pbase;
       tbase += ts * Bc;
       pbase += ps * Bc;
     }
@@ -735,44 +825,62 @@ void run_tile_chunk(Engine* h, Plan& pl, const double* angles, int n_angles, int
       CUDA_OK(cudaMemcpyAsync((char*)h->state + (size_t)b * h->N * h->amp_bytes, h->init_vec, h->N * h->amp_bytes,
                               cudaMemcpyDeviceToDevice, h->stream));
   }
+}
+
+void tile_launch_pass(Engine* h, size_t ip) {
+  Engine::EvalCtx& ev = h->ev;
+  if (!ev.pl || ip >= ev.pl->passes.size()) fail("no evaluation in flight / pass index out of range");
+  Plan& pl = *ev.pl;
+  const int p = pl.p, Bc = ev.Bc;
+  const unsigned ntiles = 1u << (h->El - TILE_BITS);
+  const bool c64 = h->dtype == QAOA_DTYPE_C64;
+  const size_t rsz = c64 ? 4 : 8;
+  unsigned char* db = (unsigned char*)h->d_params;
   const size_t point_stride_elems = h->N << h->qshift;
-  size_t tbase = 0, pbase = 0;
-  int nparts = (int)ntiles;
-  for (size_t ip = 0; ip < pl.passes.size(); ip++) {
-    auto& pp = pl.passes[ip];
-    const bool use_prog = all_normal[ip] && !h->force_generic;
-    const void* d_tau = db + tbase * rsz;
-    const double* d_phs = (const double*)(db + tau_bytes) + pbase;
-    bool reads = pp.tp.ops[0].type == TOP_LOAD, writes = pp.tp.ops[pp.tp.nops - 1].type == TOP_STORE;
-    const double pass_bytes = (double)Bc * (double)h->N * h->amp_bytes * ((reads ? 1 : 0) + (writes ? 1 : 0)) +
-        (double)Bc * (double)h->N * diag_value_bytes(h->dinfo.kind) * (pp.phases.size() + (pp.has_reduce ? 1 : 0));
-    size_t evi = 0;
-    if (h->time_passes) {
-      evi = h->ev_pending.size();
-      while (h->ev_pool.size() <= evi) {
-        cudaEvent_t a, b;
-        CUDA_OK(cudaEventCreate(&a));
-        CUDA_OK(cudaEventCreate(&b));
-        h->ev_pool.push_back({a, b});
-      }
-      CUDA_OK(cudaEventRecord(h->ev_pool[evi].first, h->stream));
+  auto& pp = pl.passes[ip];
+  const bool use_prog = ev.all_normal[ip] && !h->force_generic;
+  const void* d_tau = db + ev.tbase[ip] * rsz;
+  const double* d_phs = (const double*)(db + ev.tau_bytes) + ev.pbase[ip];
+  bool reads = pp.tp.ops[0].type == TOP_LOAD, writes = pp.tp.ops[pp.tp.nops - 1].type == TOP_STORE;
+  const double pass_bytes = (double)Bc * (double)h->N * h->amp_bytes * ((reads ? 1 : 0) + (writes ? 1 : 0)) +
+      (double)Bc * (double)h->N * diag_value_bytes(h->dinfo.kind) * (pp.phases.size() + (pp.has_reduce ? 1 : 0));
+  size_t evi = 0;
+  if (h->time_passes) {
+    evi = h->ev_pending.size();
+    while (h->ev_pool.size() <= evi) {
+      cudaEvent_t a, b;
+      CUDA_OK(cudaEventCreate(&a));
+      CUDA_OK(cudaEventCreate(&b));
+      h->ev_pool.push_back({a, b});
     }
-    const int np = c64 ? launch_pass<float2>(h, pp, use_prog, ntiles, Bc, point_stride_elems, d_tau, d_phs, p)
-                       : launch_pass<double>(h, pp, use_prog, ntiles, Bc, point_stride_elems, d_tau, d_phs, p);
-    if (pp.has_reduce) nparts = np;
-    if (h->time_passes) {
-      CUDA_OK(cudaEventRecord(h->ev_pool[evi].second, h->stream));
-      h->ev_pending.push_back({use_prog ? pp.prog : (int)PROG_GENERIC, evi, pass_bytes});
-    }
-    h->launches += 1;
-    if (use_prog && pp.prog != PROG_GENERIC) h->prog_launches += 1;
-    h->bytes_alg += pass_bytes;
-    tbase += (size_t)pp.tp.tau_stride * Bc;
-    pbase += (size_t)pp.tp.phs_stride * Bc;
+    CUDA_OK(cudaEventRecord(h->ev_pool[evi].first, h->stream));
   }
-  finalize_kernel<<<Bc, 256, 0, h->stream>>>(h->d_partials, nparts, h->dinfo, d_out_chunk);
+  const int np = c64 ? launch_pass<float2>(h, pp, use_prog, ntiles, Bc, point_stride_elems, d_tau, d_phs, p)
+                     : launch_pass<double>(h, pp, use_prog, ntiles, Bc, point_stride_elems, d_tau, d_phs, p);
+  if (pp.has_reduce) ev.nparts = np;
+  if (h->time_passes) {
+    CUDA_OK(cudaEventRecord(h->ev_pool[evi].second, h->stream));
+    h->ev_pending.push_back({use_prog ? pp.prog : (int)PROG_GENERIC, evi, pass_bytes});
+  }
+  h->launches += 1;
+  if (use_prog && pp.prog != PROG_GENERIC) h->prog_launches += 1;
+  h->bytes_alg += pass_bytes;
+}
+
+void tile_finalize(Engine* h, double* d_out_chunk, bool raw) {
+  Engine::EvalCtx& ev = h->ev;
+  if (raw) finalize_sums_kernel<<<ev.Bc, 256, 0, h->stream>>>(h->d_partials, ev.nparts, h->dinfo, d_out_chunk);
+  else finalize_kernel<<<ev.Bc, 256, 0, h->stream>>>(h->d_partials, ev.nparts, h->dinfo, d_out_chunk);
   CUDA_OK(cudaGetLastError());
   h->launches += 1;
+}
+
+// tile path for a chunk of points [b0, b0+Bc)
+void run_tile_chunk(Engine* h, Plan& pl, const double* angles, int n_angles, int Bc, double* d_out_chunk,
+                    bool record_last) {
+  tile_prepare(h, pl, angles, n_angles, Bc, record_last);
+  for (size_t ip = 0; ip < pl.passes.size(); ip++) tile_launch_pass(h, ip);
+  tile_finalize(h, d_out_chunk, false);
 }
 
 // small fused path for a chunk
@@ -882,10 +990,15 @@ void harvest_events(Engine* h) {
   }
   h->ev_pending.clear();
   float ms = 0;
-  if (h->ev_call0 && cudaEventElapsedTime(&ms, h->ev_call0, h->ev_call1) == cudaSuccess) h->last_device_ms = ms;
+  if (h->ev_call_recorded) {
+    if (cudaEventElapsedTime(&ms, h->ev_call0, h->ev_call1) == cudaSuccess) h->last_device_ms = ms;
+    else cudaGetLastError();
+    h->ev_call_recorded = false;
+  }
 }
 
 void energy_batch_impl(Engine* h, int p, const double* angles, int n_angles, int B) {
+  if (h->world > 1) fail("sharded engine: use qaoa_shard_begin / qaoa_shard_run_pass / qaoa_shard_finish");
   check_ready(h, p, n_angles);
   CUDA_OK(cudaSetDevice(h->device));
   if (!h->ev_call0) { CUDA_OK(cudaEventCreate(&h->ev_call0)); CUDA_OK(cudaEventCreate(&h->ev_call1)); }
@@ -894,6 +1007,7 @@ void energy_batch_impl(Engine* h, int p, const double* angles, int n_angles, int
   CUDA_OK(cudaEventRecord(h->ev_call0, h->stream));
   energy_batch_body(h, p, angles, n_angles, B);
   CUDA_OK(cudaEventRecord(h->ev_call1, h->stream));
+  h->ev_call_recorded = true;
 }
 
 void energy_batch_body(Engine* h, int p, const double* angles, int n_angles, int B) {
@@ -931,6 +1045,7 @@ void energy_batch_body(Engine* h, int p, const double* angles, int n_angles, int
 }
 
 void set_diag_common(Engine* h, int kind, double c0, double delta) {
+  close_peers(h, 1);
   if (h->diag) { cudaFree(h->diag); h->diag = nullptr; }
   free_streams(h);
   invalidate(h);
@@ -1003,10 +1118,20 @@ extern "C" {
 const char* qaoa_global_error(void) { return g_global_error.c_str(); }
 
 int qaoa_create(int n_qubits, int dtype, int device, qaoa_engine_t** out) {
+  return qaoa_create_sharded(n_qubits, dtype, device, 0, 1, out);
+}
+
+int qaoa_create_sharded(int n_qubits, int dtype, int device, int rank, int world, qaoa_engine_t** out) {
   if (!out) return 1;
   *out = nullptr;
   try {
     if (n_qubits < 1 || n_qubits > QAOA_MAX_QUBITS - 1) fail("n_qubits out of range [1, 39]");
+    int gbits = 0;
+    while ((1 << gbits) < world) gbits++;
+    if (world < 1 || world > QAOA_MAX_RANKS || (1 << gbits) != world) fail("world must be 1, 2, 4 or 8");
+    if (rank < 0 || rank >= world) fail("rank out of range");
+    if (world > 1 && n_qubits - gbits + (dtype == QAOA_DTYPE_C128 ? 1 : 0) < TILE_BITS + 1)
+      fail("sharded engine: every shard must hold more than 14 element bits");
     if (dtype != QAOA_DTYPE_C64 && dtype != QAOA_DTYPE_C128) fail("dtype must be 0 (complex64) or 1 (complex128)");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -1021,11 +1146,15 @@ int qaoa_create(int n_qubits, int dtype, int device, qaoa_engine_t** out) {
     h->n = n_qubits; h->dtype = dtype; h->device = device;
     h->qshift = dtype == QAOA_DTYPE_C128 ? 1 : 0;
     h->E = n_qubits + h->qshift;
-    h->N = (size_t)1 << n_qubits;
+    h->rank = rank; h->world = world; h->gbits = gbits;
+    h->El = h->E - gbits;
+    h->N = (size_t)1 << (n_qubits - gbits);
+    h->x0 = (size_t)rank << (n_qubits - gbits);
     h->amp_bytes = dtype == QAOA_DTYPE_C128 ? 16 : 8;
     CUDA_OK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     h->init = make_gen(h, INIT_PLUS, 0, nullptr, &h->init_vec);
     h->sub = h->init;
+    if (world > 1) ensure_state(h, 1);   // peers map it before the first evaluation
     *out = h;
   } catch (const std::string& e) {
     g_global_error = e;
@@ -1038,6 +1167,8 @@ int qaoa_destroy(qaoa_engine_t* h) {
   if (!h) return 1;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
+  close_peers(h, 0);
+  close_peers(h, 1);
   free_streams(h);
   void* bufs[] = {h->state, h->diag, h->d_pairs, h->init_vec, h->sub_vec, h->d_params, h->d_partials, h->d_out,
                   h->d_tables, h->d_gamsig, h->d_coefdot, h->d_angles};
@@ -1125,7 +1256,7 @@ int qaoa_set_cost_maxkcut(qaoa_engine_t* h, int n_nodes, int n_edges, const int3
   CUDA_OK(cudaMemcpy(dw, w, n_edges * 8, cudaMemcpyHostToDevice));
   D.eu = du; D.ev = dv; D.ewi = dwi; D.ew = dw;
   DiagInfo gi = h->dinfo;
-  gen_maxkcut_kernel<<<grid_for(h->N, 256), 256, 0, h->stream>>>(D, h->N, gi, h->diag);
+  gen_maxkcut_kernel<<<grid_for(h->N, 256), 256, 0, h->stream>>>(D, h->N, h->x0, gi, h->diag);
   CUDA_OK(cudaGetLastError());
   CUDA_OK(cudaStreamSynchronize(h->stream));
   h->launches += 1;
@@ -1161,7 +1292,7 @@ int qaoa_set_cost_qubo(qaoa_engine_t* h, int n, const double* Q, const double* c
   CUDA_OK(cudaMemcpy(dd, d.data(), n * 8, cudaMemcpyHostToDevice));
   CUDA_OK(cudaMemcpy(dM, M.data(), (size_t)n * n * 8, cudaMemcpyHostToDevice));
   const int smem = (n + n * n) * 8;
-  gen_qubo_kernel<<<grid_for(h->N, 256), 256, smem, h->stream>>>(n, dd, dM, b, h->N, h->dinfo, h->diag);
+  gen_qubo_kernel<<<grid_for(h->N, 256), 256, smem, h->stream>>>(n, dd, dM, b, h->N, h->x0, h->dinfo, h->diag);
   CUDA_OK(cudaGetLastError());
   CUDA_OK(cudaStreamSynchronize(h->stream));
   h->launches += 1;
@@ -1172,6 +1303,7 @@ int qaoa_set_cost_qubo(qaoa_engine_t* h, int n, const double* Q, const double* c
 int qaoa_set_cost_diagonal(qaoa_engine_t* h, const double* diag) {
   API_BEGIN(h)
   if (!diag) fail("diag is null");
+  if (h->world > 1) fail("sharded engine: host-provided cost diagonals are not supported");
   double lo = 1e300, hi = -1e300;
   bool integer = true;
   for (size_t i = 0; i < h->N; i++) {
@@ -1237,6 +1369,7 @@ int qaoa_set_mixer(qaoa_engine_t* h, int kind, const int32_t* pairs, int n_pairs
                    int sub_kind, int sub_k, const double* sub_vec) {
   API_BEGIN(h)
   if (kind < MIXER_X || kind > MIXER_GROVER) fail("unknown mixer kind");
+  if (h->world > 1 && kind != MIXER_X && kind != MIXER_XMULTI) fail("sharded engine: only the X and multi-angle X mixers are supported");
   if (trotter_steps < 1) fail("trotter_steps must be >= 1");
   invalidate(h);
   h->mixer = kind;
@@ -1259,6 +1392,7 @@ int qaoa_set_mixer(qaoa_engine_t* h, int kind, const int32_t* pairs, int n_pairs
 
 int qaoa_set_initial(qaoa_engine_t* h, int kind, int k, const double* vec) {
   API_BEGIN(h)
+  if (h->world > 1 && kind == INIT_STATEVECTOR) fail("sharded engine: StateVector initial states are not supported");
   invalidate(h);
   h->init = make_gen(h, kind, k, vec, &h->init_vec);
   API_END(h)
@@ -1323,6 +1457,130 @@ int qaoa_read_statevector(qaoa_engine_t* h, double* out) {
   API_END(h)
 }
 
+// ---- sharded registers ----------------------------------------------------------------------
+int qaoa_shard_info(qaoa_engine_t* h, int* rank, int* world, int* local_qubits) {
+  API_BEGIN(h)
+  if (rank) *rank = h->rank;
+  if (world) *world = h->world;
+  if (local_qubits) *local_qubits = h->n - h->gbits;
+  API_END(h)
+}
+
+static void* shard_local_buffer(Engine* h, int which) {
+  if (which == 0) { ensure_state(h, 1); return h->state; }
+  if (which == 1) { if (!h->diag) fail("no cost function set"); return h->diag; }
+  fail("which must be 0 (state) or 1 (cost diagonal)");
+}
+
+int qaoa_shard_local_ptr(qaoa_engine_t* h, int which, void** out) {
+  API_BEGIN(h)
+  if (!out) fail("null output");
+  *out = shard_local_buffer(h, which);
+  API_END(h)
+}
+
+int qaoa_shard_set_peers(qaoa_engine_t* h, int which, void* const* ptrs) {
+  API_BEGIN(h)
+  if (h->world < 2) fail("not a sharded engine");
+  void* mine = shard_local_buffer(h, which);
+  close_peers(h, which);
+  void** dst = which == 0 ? h->peer_state : h->peer_diag;
+  for (int r = 0; r < h->world; r++) {
+    if (!ptrs || !ptrs[r]) fail("null peer pointer");
+    dst[r] = r == h->rank ? mine : ptrs[r];
+    if (r != h->rank) {   // same-process peers on another GPU: map their memory into this device
+      cudaPointerAttributes at;
+      CUDA_OK(cudaPointerGetAttributes(&at, ptrs[r]));
+      if (at.type == cudaMemoryTypeDevice && at.device != h->device) {
+        int can = 0;
+        CUDA_OK(cudaDeviceCanAccessPeer(&can, h->device, at.device));
+        if (!can) fail("peer GPU memory is not accessible from this device (no NVLink / P2P)");
+        cudaError_t e = cudaDeviceEnablePeerAccess(at.device, 0);
+        if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+        else CUDA_OK(e);
+      }
+    }
+  }
+  if (which == 0) h->peers_state_set = true; else { h->peers_diag_set = true; free_streams(h); invalidate(h); }
+  API_END(h)
+}
+
+int qaoa_shard_export(qaoa_engine_t* h, int which, unsigned char* handle64) {
+  API_BEGIN(h)
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is expected to be 64 bytes");
+  if (!handle64) fail("null handle buffer");
+  cudaIpcMemHandle_t hd;
+  CUDA_OK(cudaIpcGetMemHandle(&hd, shard_local_buffer(h, which)));
+  memcpy(handle64, &hd, 64);
+  API_END(h)
+}
+
+int qaoa_shard_import(qaoa_engine_t* h, int which, const unsigned char* handles) {
+  API_BEGIN(h)
+  if (h->world < 2) fail("not a sharded engine");
+  if (!handles) fail("null handle buffer");
+  void* mine = shard_local_buffer(h, which);
+  close_peers(h, which);
+  void** dst = which == 0 ? h->peer_state : h->peer_diag;
+  bool* ipc = which == 0 ? h->peer_state_ipc : h->peer_diag_ipc;
+  for (int r = 0; r < h->world; r++) {
+    if (r == h->rank) { dst[r] = mine; continue; }
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, handles + (size_t)r * 64, 64);
+    void* ptr = nullptr;
+    CUDA_OK(cudaIpcOpenMemHandle(&ptr, hd, cudaIpcMemLazyEnablePeerAccess));
+    dst[r] = ptr;
+    ipc[r] = true;
+  }
+  if (which == 0) h->peers_state_set = true; else { h->peers_diag_set = true; free_streams(h); invalidate(h); }
+  API_END(h)
+}
+
+int qaoa_shard_begin(qaoa_engine_t* h, int p, const double* angles, int n_angles, int* n_passes) {
+  API_BEGIN(h)
+  if (h->world < 2) fail("not a sharded engine");
+  if (!angles) fail("null angles");
+  check_ready(h, p, n_angles);
+  if (h->keep_state) fail("sharded engine: keep_state is not supported");
+  if (!h->peers_state_set || !h->peers_diag_set) fail("sharded engine: peer pointers have not been set");
+  Plan& pl = get_plan(h, p);
+  ensure_state(h, 1);
+  tile_prepare(h, pl, angles, n_angles, 1, false);
+  if (n_passes) *n_passes = (int)pl.passes.size();
+  API_END(h)
+}
+
+int qaoa_shard_pass_is_cross(qaoa_engine_t* h, int pass) {
+  if (!h || !h->ev.pl || pass < 0 || pass >= (int)h->ev.pl->passes.size()) return -1;
+  return h->ev.pl->passes[pass].cross ? 1 : 0;
+}
+
+int qaoa_shard_run_pass(qaoa_engine_t* h, int pass) {
+  API_BEGIN(h)
+  if (h->world < 2) fail("not a sharded engine");
+  tile_launch_pass(h, (size_t)pass);
+  API_END(h)
+}
+
+int qaoa_shard_sync(qaoa_engine_t* h) {
+  API_BEGIN(h)
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  harvest_events(h);
+  API_END(h)
+}
+
+int qaoa_shard_finish(qaoa_engine_t* h, double* out5) {
+  API_BEGIN(h)
+  if (h->world < 2) fail("not a sharded engine");
+  if (!out5) fail("null output");
+  ensure(h->d_out, h->out_cap, 5 * sizeof(double));
+  tile_finalize(h, h->d_out, true);
+  CUDA_OK(cudaMemcpyAsync(out5, h->d_out, 5 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  harvest_events(h);
+  API_END(h)
+}
+
 // Test / profiling hook: runs an arbitrary step program on tiles over {0..3} U [hb, hb+10) with the
 // interpreter kernel and returns the mean CUDA-event time per launch.  ops = (type, frame, mask)
 // triples; PHASE / REDUCE are not allowed here (they need diagonal streams).
@@ -1376,7 +1634,7 @@ int qaoa_debug_tile_program(qaoa_engine_t* h, int hb, const int32_t* ops, int no
   double one = 1.0;
   CUDA_OK(cudaMemcpy((char*)h->d_params + hb_.size(), &one, 8, cudaMemcpyHostToDevice));
   ensure(h->d_partials, h->partials_cap, 4096);
-  const unsigned ntiles = 1u << (h->E - TILE_BITS);
+  const unsigned ntiles = 1u << (h->El - TILE_BITS);
   PlanPass pp;
   pp.tp = tp;
   cudaEvent_t e0, e1;

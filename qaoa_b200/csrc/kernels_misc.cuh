@@ -27,23 +27,25 @@ __device__ __forceinline__ int node_colour(const MaxKCutDev& D, unsigned long lo
   return D.lut[(x >> (v * D.bits)) & ((1u << D.bits) - 1u)];
 }
 
-__global__ void gen_maxkcut_kernel(MaxKCutDev D, size_t N, DiagInfo info, void* out) {
-  for (size_t x = blockIdx.x * (size_t)blockDim.x + threadIdx.x; x < N; x += (size_t)gridDim.x * blockDim.x) {
+// x0: first basis index of the slice this engine holds (sharded registers; 0 otherwise)
+__global__ void gen_maxkcut_kernel(MaxKCutDev D, size_t N, size_t x0, DiagInfo info, void* out) {
+  for (size_t xl = blockIdx.x * (size_t)blockDim.x + threadIdx.x; xl < N; xl += (size_t)gridDim.x * blockDim.x) {
+    const size_t x = x0 + xl;
     if (info.kind == DIAG_U8) {
       int s = 0;
       for (int e = 0; e < D.n_edges; e++) {
         int cu = node_colour(D, x, __ldg(D.eu + e)), cv = node_colour(D, x, __ldg(D.ev + e));
         s += (cu != cv) ? __ldg(D.ewi + e) : 0;
       }
-      ((uint8_t*)out)[x] = (uint8_t)(s - (int)llrint(info.c0));
+      ((uint8_t*)out)[xl] = (uint8_t)(s - (int)llrint(info.c0));
     } else {
       double s = 0.0;
       for (int e = 0; e < D.n_edges; e++) {
         int cu = node_colour(D, x, __ldg(D.eu + e)), cv = node_colour(D, x, __ldg(D.ev + e));
         s += (cu != cv) ? __ldg(D.ew + e) : 0.0;   // same edge order as the reference's sum()
       }
-      if (info.kind == DIAG_U32FX) ((uint32_t*)out)[x] = (uint32_t)llrint((s - info.c0) / info.delta);
-      else ((double*)out)[x] = s;
+      if (info.kind == DIAG_U32FX) ((uint32_t*)out)[xl] = (uint32_t)llrint((s - info.c0) / info.delta);
+      else ((double*)out)[xl] = s;
     }
   }
 }
@@ -51,16 +53,16 @@ __global__ void gen_maxkcut_kernel(MaxKCutDev D, size_t N, DiagInfo info, void* 
 // Replaces QUBO.qubo_cost (qubo_problem.py:101-108): cost = -(x^T Q x + c^T x + b).
 // d[i] = Q_ii + c_i ; M[i*n+j] = Q_ij + Q_ji for j < i (host-prepared).
 __global__ void gen_qubo_kernel(int n, const double* __restrict__ d, const double* __restrict__ M,
-                                double b, size_t N, DiagInfo info, void* out) {
+                                double b, size_t N, size_t x0, DiagInfo info, void* out) {
   extern __shared__ double sm[];
   double* sd = sm;
   double* sM = sm + n;
   for (int i = threadIdx.x; i < n; i += blockDim.x) sd[i] = d[i];
   for (int i = threadIdx.x; i < n * n; i += blockDim.x) sM[i] = M[i];
   __syncthreads();
-  for (size_t x = blockIdx.x * (size_t)blockDim.x + threadIdx.x; x < N; x += (size_t)gridDim.x * blockDim.x) {
+  for (size_t xl = blockIdx.x * (size_t)blockDim.x + threadIdx.x; xl < N; xl += (size_t)gridDim.x * blockDim.x) {
     double f = b;
-    unsigned long long rem = x;
+    unsigned long long rem = x0 + xl;
     while (rem) {
       int i = 63 - __clzll((long long)rem);
       rem &= ~(1ull << i);
@@ -74,9 +76,9 @@ __global__ void gen_qubo_kernel(int n, const double* __restrict__ d, const doubl
       f += row;
     }
     double cost = -f;
-    if (info.kind == DIAG_U8) ((uint8_t*)out)[x] = (uint8_t)llrint((cost - info.c0) / info.delta);
-    else if (info.kind == DIAG_U32FX) ((uint32_t*)out)[x] = (uint32_t)llrint((cost - info.c0) / info.delta);
-    else ((double*)out)[x] = cost;
+    if (info.kind == DIAG_U8) ((uint8_t*)out)[xl] = (uint8_t)llrint((cost - info.c0) / info.delta);
+    else if (info.kind == DIAG_U32FX) ((uint32_t*)out)[xl] = (uint32_t)llrint((cost - info.c0) / info.delta);
+    else ((double*)out)[xl] = cost;
   }
 }
 
@@ -150,6 +152,32 @@ __global__ void finalize_kernel(const double* __restrict__ partials, int ntiles,
     o[2] = fmin(lo, hi);
     o[3] = fmax(lo, hi);
     o[4] = v[0];
+  }
+}
+
+// Sharded registers: this rank's share of the sums in TRUE cost units, to be combined across ranks
+// (sum, sum, sum, min, max):  out[point] = {sum p, sum p c, sum p c^2, min c, max c}.
+__global__ void finalize_sums_kernel(const double* __restrict__ partials, int nparts, DiagInfo info, double* out) {
+  __shared__ double red[32 * 5];
+  const double* p = partials + (size_t)blockIdx.x * nparts * 5;
+  double v[5] = {0, 0, 0, 1e300, -1e300};
+  for (int i = threadIdx.x; i < nparts; i += blockDim.x) {
+    v[0] += p[i * 5 + 0];
+    v[1] += p[i * 5 + 1];
+    v[2] += p[i * 5 + 2];
+    v[3] = fmin(v[3], p[i * 5 + 3]);
+    v[4] = fmax(v[4], p[i * 5 + 4]);
+  }
+  block_reduce5(v, red);
+  if (threadIdx.x == 0) {
+    const double c0 = info.kind == DIAG_F64 ? 0.0 : info.c0, dl = info.kind == DIAG_F64 ? 1.0 : info.delta;
+    double* o = out + (size_t)blockIdx.x * 5;
+    o[0] = v[0];
+    o[1] = c0 * v[0] + dl * v[1];
+    o[2] = c0 * c0 * v[0] + 2.0 * c0 * dl * v[1] + dl * dl * v[2];
+    const double lo = c0 + dl * v[3], hi = c0 + dl * v[4];
+    o[3] = v[3] > 1e299 ? 1e300 : fmin(lo, hi);
+    o[4] = v[4] < -1e299 ? -1e300 : fmax(lo, hi);
   }
 }
 

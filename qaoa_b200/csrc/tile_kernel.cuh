@@ -34,6 +34,7 @@ constexpr int TILE_ELEMS = 1 << TILE_BITS;
 constexpr int TILE_THREADS = 512;
 constexpr int TILE_MAX_OPS = 64;
 constexpr int TILE_MAX_PHASES = 16;
+#define QAOA_MAX_RANKS 8
 constexpr int TILE_ROUND_REALS = 12;  // k1[5], k2[5], form mask, pad
 constexpr int TILE_EXCH_BYTES = TILE_ELEMS * 8;
 constexpr int TILE_SMEM_BYTES = TILE_EXCH_BYTES + 4096 + 16 * 5 * 8;   // interpreter kernel
@@ -79,6 +80,15 @@ struct TilePass {
   unsigned ntiles;                      // tiles per point
   const void* streams[TILE_MAX_PHASES]; // permuted cost-diagonal stream per phase slot
   int table_id[TILE_MAX_PHASES];        // index of the 256-entry phase table (U8 mode)
+  // Sharded registers (one engine per GPU, the register split on its top qubits): element bits >=
+  // shard_bits select the owning rank.  A pass whose tile contains those bits is a CROSS pass: its
+  // tile ids are global (this rank owns [tile0, tile0 + ntiles)) and every access goes through the
+  // peer table (NVLink peer memory); all other passes see only the local shard.
+  int shard_bits;                       // element bits per shard (0: not sharded)
+  int rank_popc;                        // popcount of this rank's index (initial-state generation)
+  unsigned tile0;
+  void* peers[QAOA_MAX_RANKS];          // state base of every rank
+  const void* dpeers[QAOA_MAX_RANKS];   // cost-diagonal base of every rank (stream construction)
 };
 
 template <typename Elem> struct ElemTraits;
@@ -148,6 +158,15 @@ struct TileAddr {
 __device__ __forceinline__ size_t tile_base(const TilePass& P, unsigned tile) {
   return ((size_t)(tile & ((1u << P.fr_lo_bits) - 1u)) << P.fr_lo_shift) |
          ((size_t)(tile >> P.fr_lo_bits) << P.fr_hi_shift);
+}
+
+// element index -> pointer.  CROSS passes translate through the peer table (one point only).
+template <bool CROSS, typename Elem>
+__device__ __forceinline__ Elem* eptr(const TilePass& P, Elem* point_base, size_t e) {
+  if constexpr (CROSS)
+    return reinterpret_cast<Elem*>(P.peers[e >> P.shard_bits]) + (e & (((size_t)1 << P.shard_bits) - 1));
+  else
+    return point_base + e;
 }
 
 // host: derive the two-run description from freepos (false if the free bits need more than two runs)
@@ -426,12 +445,12 @@ __device__ __forceinline__ void for_each_diag(const void* stream, int kind, unsi
 }
 
 // ---- the steps ----------------------------------------------------------------------------
-template <typename Elem>
+template <typename Elem, bool CROSS>
 __device__ __forceinline__ void op_load(const Ctx<Elem>& c, Elem (&v)[32], int frame) {
   TileAddr ad = tile_addr_off(*c.P, c.base, frame, c.thr[frame]);
-  const Elem* p = c.state + ad.e0;
 #pragma unroll
-  for (int q = 0; q < 16; q++) load16(p + reg_off(ad, q), v[2 * q], v[2 * q + 1]);
+  for (int q = 0; q < 16; q++)
+    load16(eptr<CROSS, Elem>(*c.P, c.state, ad.e0 + reg_off(ad, q)), v[2 * q], v[2 * q + 1]);
 }
 
 // Pulls the 1024 128-byte rows of a LATER tile (the one the next CTA scheduled on this SM will most
@@ -439,7 +458,7 @@ __device__ __forceinline__ void op_load(const Ctx<Elem>& c, Elem (&v)[32], int f
 template <typename Elem>
 __device__ __forceinline__ void prefetch_later_tile(const Ctx<Elem>& c) {
   const TilePass& P = *c.P;
-  if (P.prefetch_dist <= 0) return;
+  if (P.prefetch_dist <= 0 || P.shard_bits != 0) return;
   const unsigned long long id = c.id + (unsigned)P.prefetch_dist;
   if (id >= c.total) return;
   const unsigned ntile = (unsigned)(id % c.ntiles), npoint = (unsigned)(id / c.ntiles);
@@ -455,12 +474,12 @@ __device__ __forceinline__ void prefetch_later_tile(const Ctx<Elem>& c) {
   }
 }
 
-template <typename Elem>
+template <typename Elem, bool CROSS>
 __device__ __forceinline__ void op_store(const Ctx<Elem>& c, Elem (&v)[32], int frame) {
   TileAddr ad = tile_addr_off(*c.P, c.base, frame, c.thr[frame]);
-  Elem* p = c.state + ad.e0;
 #pragma unroll
-  for (int q = 0; q < 16; q++) store16(p + reg_off(ad, q), v[2 * q], v[2 * q + 1]);
+  for (int q = 0; q < 16; q++)
+    store16(eptr<CROSS, Elem>(*c.P, c.state, ad.e0 + reg_off(ad, q)), v[2 * q], v[2 * q + 1]);
 }
 
 template <typename Elem>
@@ -470,7 +489,7 @@ __device__ __forceinline__ void op_init(const Ctx<Elem>& c, Elem (&v)[32], int f
   const TilePass& P = *c.P;
   TileAddr ad = tile_addr_off(P, c.base, frame, c.thr[frame]);
   const real A = (real)P.init_amp;
-  const int pc0 = __popcll((unsigned long long)(ad.e0 >> P.qshift));
+  const int pc0 = __popcll((unsigned long long)(ad.e0 >> P.qshift)) + P.rank_popc;
 #pragma unroll
   for (int a = 0; a < NAMP; a++) {
     // tile bits are distinct element bits: popcount(x) = popcount(thread part) + popcount(reg part)
@@ -689,8 +708,9 @@ __device__ __forceinline__ void ctx_set_tile(Ctx<Elem>& c, unsigned long long id
   c.state = c.state0 + (size_t)c.point * c.point_stride;
   c.tau = c.tau0 + (size_t)c.point * P.tau_stride;
   c.phs = c.phs0 + (size_t)c.point * P.phs_stride;
-  c.base = tile_base(P, c.tile);
+  c.base = tile_base(P, c.tile + P.tile0);
 }
+
 
 template <typename Elem>
 __device__ __forceinline__ void ctx_init(Ctx<Elem>& c, const TilePass& P, Elem* state, size_t point_stride,
@@ -731,14 +751,14 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // current tile has been pulled into registers); the remaining pairs use the start of the exchange
 // buffer ("late" group, issued once the tile's last transpose is done with that buffer).  With
 // L2_REST the lines of the pairs >= Q1 are pulled into L2 so that the late group is an L2 hit.
-template <typename Elem, int Q0, int Q1, bool L2_REST>
+template <typename Elem, int Q0, int Q1, bool L2_REST, bool CROSS>
 __device__ __forceinline__ void stage_issue(const Ctx<Elem>& c, unsigned long long id, int frame) {
   constexpr int SP = TileSmem<Elem>::STAGE_PAIRS;
   if (id < c.total) {
     const TilePass& P = *c.P;
     const unsigned ntile = (unsigned)(id % c.ntiles), npoint = (unsigned)(id / c.ntiles);
-    TileAddr ad = tile_addr_off(P, tile_base(P, ntile), frame, c.thr[frame]);
-    const Elem* p = c.state0 + (size_t)npoint * c.point_stride + ad.e0;
+    TileAddr ad = tile_addr_off(P, tile_base(P, ntile + P.tile0), frame, c.thr[frame]);
+    Elem* pb = c.state0 + (size_t)npoint * c.point_stride;
     const unsigned sb = (unsigned)__cvta_generic_to_shared(c.smem);
     const unsigned early = sb + TileSmem<Elem>::STAGE_OFF + threadIdx.x * 16u;
     // late slots sit inside the OWNING warp's 8 KB region of the exchange buffer; every block-wide
@@ -747,18 +767,18 @@ __device__ __forceinline__ void stage_issue(const Ctx<Elem>& c, unsigned long lo
 #pragma unroll
     for (int q = Q0; q < Q1; q++) {
       const unsigned dst = q < SP ? early + q * (TILE_THREADS * 16) : late + (q - SP) * 512;
-      cp_async16(dst, p + reg_off(ad, q));
+      cp_async16(dst, eptr<CROSS, Elem>(P, pb, ad.e0 + reg_off(ad, q)));
     }
-    if (L2_REST) {
+    if (L2_REST && !CROSS) {   // (peer lines bypass the local L2)
 #pragma unroll
-      for (int q = Q1; q < 16; q++) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + reg_off(ad, q)));
+      for (int q = Q1; q < 16; q++) asm volatile("prefetch.global.L2 [%0];" ::"l"(pb + ad.e0 + reg_off(ad, q)));
     }
   }
   cp_async_commit();
 }
 
 // persistent-kernel load: every register pair comes from the slots filled during the previous tile
-template <typename Elem>
+template <typename Elem, bool CROSS>
 __device__ __forceinline__ void op_load_staged(const Ctx<Elem>& c, Elem (&v)[32], int frame) {
   constexpr int SP = TileSmem<Elem>::STAGE_PAIRS;
   cp_async_wait_all();
@@ -770,11 +790,11 @@ __device__ __forceinline__ void op_load_staged(const Ctx<Elem>& c, Elem (&v)[32]
     load16(reinterpret_cast<const Elem*>(src), v[2 * q], v[2 * q + 1]);
   }
   __syncwarp();
-  stage_issue<Elem, 0, SP, true>(c, c.id + c.stride, frame);
+  stage_issue<Elem, 0, SP, true, CROSS>(c, c.id + c.stride, frame);
 }
 
 // ---- interpreter kernel -------------------------------------------------------------------
-template <typename Elem>
+template <typename Elem, bool CROSS>
 __global__ void __launch_bounds__(TILE_THREADS, 1)
 tile_pass_kernel(const __grid_constant__ TilePass P, Elem* __restrict__ state, size_t point_stride,
                  const typename ElemTraits<Elem>::real* __restrict__ tau, const double* __restrict__ phs,
@@ -790,8 +810,8 @@ tile_pass_kernel(const __grid_constant__ TilePass P, Elem* __restrict__ state, s
     const TileOp cur = op;
     if (io + 1 < P.nops) op = P.ops[io + 1];  // fetch the next step early (constant-bank latency)
     switch (cur.type) {
-      case TOP_LOAD: op_load<Elem>(c, v, cur.frame); prefetch_later_tile<Elem>(c); break;
-      case TOP_STORE: op_store<Elem>(c, v, cur.frame); break;
+      case TOP_LOAD: op_load<Elem, CROSS>(c, v, cur.frame); prefetch_later_tile<Elem>(c); break;
+      case TOP_STORE: op_store<Elem, CROSS>(c, v, cur.frame); break;
       case TOP_INIT: op_init<Elem>(c, v, cur.frame); break;
       case TOP_PHASE: op_phase<Elem, 0>(c, v, cur.arg); break;
       case TOP_ROUND: round_dynamic<Elem>(c, v, cur.arg); break;
@@ -937,7 +957,7 @@ __device__ __forceinline__ void point_setup(const Ctx<Elem>& c) {
   __syncthreads();
 }
 
-template <typename Elem, typename Prog, int DK, int I>
+template <typename Elem, typename Prog, int DK, bool CROSS, int I>
 struct ProgExec {
   static __device__ __forceinline__ void run(const Ctx<Elem>& c, Elem (&v)[32], const uint4 (&dq)[2], double (&acc)[5]) {
     typedef typename ElemTraits<Elem>::real real;
@@ -945,8 +965,8 @@ struct ProgExec {
       constexpr COp op = Prog::op(I);
       constexpr bool REGS = DK == DIAG_U8 && Prog::n_stream_ops() == 1;   // stream words prefetched in dq
       const real* tau_s = reinterpret_cast<const real*>(c.smem + TileSmem<Elem>::TAU_OFF);
-      if constexpr (op.type == TOP_LOAD) { op_load_staged<Elem>(c, v, op.frame); prefetch_later_tile<Elem>(c); }
-      else if constexpr (op.type == TOP_STORE) op_store<Elem>(c, v, op.frame);
+      if constexpr (op.type == TOP_LOAD) { op_load_staged<Elem, CROSS>(c, v, op.frame); prefetch_later_tile<Elem>(c); }
+      else if constexpr (op.type == TOP_STORE) op_store<Elem, CROSS>(c, v, op.frame);
       else if constexpr (op.type == TOP_INIT) op_init<Elem>(c, v, op.frame);
       else if constexpr (op.type == TOP_PHASE) {
         if constexpr (REGS) op_phase_u8_regs<Elem>(c, v, dq);
@@ -960,19 +980,19 @@ struct ProgExec {
         else xt_c_to_a<Elem>(c, v);
         if constexpr (Prog::op(0).type == TOP_LOAD && I == Prog::last_transpose()) {
           __syncthreads();  // every warp has read its share of the exchange buffer
-          stage_issue<Elem, TileSmem<Elem>::STAGE_PAIRS, 16, false>(c, c.id + c.stride, Prog::op(0).frame);
+          stage_issue<Elem, TileSmem<Elem>::STAGE_PAIRS, 16, false, CROSS>(c, c.id + c.stride, Prog::op(0).frame);
         }
       }
       else if constexpr (op.type == TOP_REDUCE) {
         if constexpr (REGS) op_reduce_u8_regs<Elem>(c, v, dq, tau_s[11], acc);
         else op_reduce_acc<Elem, DK>(c, v, op.arg, acc);
       }
-      ProgExec<Elem, Prog, DK, I + 1>::run(c, v, dq, acc);
+      ProgExec<Elem, Prog, DK, CROSS, I + 1>::run(c, v, dq, acc);
     }
   }
 };
 
-template <typename Elem, typename Prog, int DK>
+template <typename Elem, typename Prog, int DK, bool CROSS>
 __global__ void __launch_bounds__(TILE_THREADS, 1)
 tile_prog_kernel(const __grid_constant__ TilePass P, Elem* __restrict__ state, size_t point_stride,
                  const typename ElemTraits<Elem>::real* __restrict__ tau, const double* __restrict__ phs,
@@ -987,8 +1007,8 @@ tile_prog_kernel(const __grid_constant__ TilePass P, Elem* __restrict__ state, s
                  L::TABLE_OFF, L::SCRATCH_OFF, total);
   constexpr COp first = Prog::op(0);
   if constexpr (first.type == TOP_LOAD) {
-    stage_issue<Elem, 0, L::STAGE_PAIRS, false>(c, blockIdx.x, first.frame);
-    stage_issue<Elem, L::STAGE_PAIRS, 16, false>(c, blockIdx.x, first.frame);
+    stage_issue<Elem, 0, L::STAGE_PAIRS, false, CROSS>(c, blockIdx.x, first.frame);
+    stage_issue<Elem, L::STAGE_PAIRS, 16, false, CROSS>(c, blockIdx.x, first.frame);
   }
   constexpr bool HAS_RED = Prog::op(Prog::N - 1).type == TOP_REDUCE;
   double acc[5] = {0.0, 0.0, 0.0, 1e300, -1e300};
@@ -1018,7 +1038,7 @@ tile_prog_kernel(const __grid_constant__ TilePass P, Elem* __restrict__ state, s
 #pragma unroll
       for (int j = 0; j < NAMP / 16; j++) dq[j] = __ldg(s4 + stream_chunk(c.tile, c.warp, c.lane, NAMP / 16, j));
     }
-    ProgExec<Elem, Prog, DK, 0>::run(c, v, dq, acc);
+    ProgExec<Elem, Prog, DK, CROSS, 0>::run(c, v, dq, acc);
   }
   if constexpr (HAS_RED) {
     if (loaded_point != 0xffffffffu) flush_acc<Elem>(c, acc, loaded_point);
@@ -1048,12 +1068,12 @@ inline bool prog_matches(const TilePass& tp) {
 // register a (complex64, every frame); namp == 16: amplitude a is the register pair (2a, 2a+1)
 // (complex128, frames A and B).
 template <int VALBYTES>
-__global__ void make_stream_kernel(const __grid_constant__ TilePass P, int frame, int namp,
+__global__ void make_stream_kernel(const __grid_constant__ TilePass P, int frame, int namp, int cross,
                                    const unsigned char* __restrict__ diag,
                                    unsigned char* __restrict__ stream) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned tile = blockIdx.x;
-  const size_t e0 = tile_base(P, tile) + thread_off(P, frame, warp, lane);
+  const size_t e0 = tile_base(P, tile + P.tile0) + thread_off(P, frame, warp, lane);
   constexpr int V = 16 / VALBYTES;
   const int nchunks = namp / V;
   for (int j = 0; j < nchunks; j++) {
@@ -1061,7 +1081,11 @@ __global__ void make_stream_kernel(const __grid_constant__ TilePass P, int frame
     for (int i = 0; i < V; i++) {
       const int a = j * V + i;
       const size_t e = e0 + reg_elem_off(P, frame, namp == 32 ? a : 2 * a);
-      const unsigned char* src = diag + (e >> P.qshift) * VALBYTES;
+      const size_t x = e >> P.qshift;   // amplitude index (global in a cross pass)
+      const int abits = P.shard_bits - P.qshift;
+      const unsigned char* src = cross
+          ? reinterpret_cast<const unsigned char*>(P.dpeers[x >> abits]) + (x & (((size_t)1 << abits) - 1)) * VALBYTES
+          : diag + x * VALBYTES;
 #pragma unroll
       for (int b = 0; b < VALBYTES; b++) buf[i * VALBYTES + b] = src[b];
     }

@@ -78,6 +78,20 @@ def load_library():
         "qaoa_read_statevector": (ctypes.c_int, [H, _c_double_p]),
         "qaoa_debug_tile_program": (
             ctypes.c_int, [H, ctypes.c_int, _c_int32_p, ctypes.c_int, ctypes.c_int, ctypes.c_double, _c_double_p]),
+        # sharded registers (one engine per GPU)
+        "qaoa_create_sharded": (
+            ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(H)]),
+        "qaoa_shard_info": (ctypes.c_int, [H, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int),
+                                           ctypes.POINTER(ctypes.c_int)]),
+        "qaoa_shard_local_ptr": (ctypes.c_int, [H, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]),
+        "qaoa_shard_set_peers": (ctypes.c_int, [H, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]),
+        "qaoa_shard_export": (ctypes.c_int, [H, ctypes.c_int, ctypes.c_char_p]),
+        "qaoa_shard_import": (ctypes.c_int, [H, ctypes.c_int, ctypes.c_char_p]),
+        "qaoa_shard_begin": (ctypes.c_int, [H, ctypes.c_int, _c_double_p, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]),
+        "qaoa_shard_pass_is_cross": (ctypes.c_int, [H, ctypes.c_int]),
+        "qaoa_shard_run_pass": (ctypes.c_int, [H, ctypes.c_int]),
+        "qaoa_shard_sync": (ctypes.c_int, [H]),
+        "qaoa_shard_finish": (ctypes.c_int, [H, _c_double_p]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -94,16 +108,19 @@ def _dptr(a):
 class Engine:
     """One device-resident QAOA register of ``n_qubits`` qubits on ``cuda:device``."""
 
-    def __init__(self, n_qubits, dtype="complex64", device=0):
+    def __init__(self, n_qubits, dtype="complex64", device=0, rank=0, world=1):
         self._lib = load_library()
         self._h = ctypes.c_void_p()
         self.n_qubits = int(n_qubits)
         self.dtype = {"complex64": DTYPE_C64, "complex128": DTYPE_C128, DTYPE_C64: DTYPE_C64,
                       DTYPE_C128: DTYPE_C128}[dtype]
         self.n_beta = 1
-        rc = self._lib.qaoa_create(self.n_qubits, self.dtype, int(device), ctypes.byref(self._h))
+        self.rank, self.world = int(rank), int(world)
+        rc = self._lib.qaoa_create_sharded(self.n_qubits, self.dtype, int(device), self.rank, self.world,
+                                           ctypes.byref(self._h))
         if rc != 0:
             raise EngineError(self._lib.qaoa_global_error().decode())
+        self.local_qubits = self.n_qubits - (self.world.bit_length() - 1)
 
     # -- plumbing ---------------------------------------------------------
     def _check(self, rc):
@@ -150,7 +167,8 @@ class Engine:
         self._check(self._lib.qaoa_set_cost_diagonal(self._h, _dptr(diag)))
 
     def read_cost_diagonal(self, offset=0, count=None):
-        count = (1 << self.n_qubits) - offset if count is None else count
+        """cost(x) for x in [offset, offset+count); a sharded engine indexes its own slice from 0."""
+        count = (1 << self.local_qubits) - offset if count is None else count
         out = np.empty(count, dtype=np.float64)
         self._check(self._lib.qaoa_read_cost_diagonal(self._h, offset, count, _dptr(out)))
         return out
@@ -219,6 +237,53 @@ class Engine:
         out = np.empty(2 << self.n_qubits, dtype=np.float64)
         self._check(self._lib.qaoa_read_statevector(self._h, _dptr(out)))
         return out.view(np.complex128)
+
+    # -- sharded registers: one engine per GPU (include/qaoa_b200.h, "Sharded registers") -------------
+    def shard_local_ptr(self, which):
+        out = ctypes.c_void_p()
+        self._check(self._lib.qaoa_shard_local_ptr(self._h, int(which), ctypes.byref(out)))
+        return out.value
+
+    def shard_set_peers(self, which, ptrs):
+        arr = (ctypes.c_void_p * self.world)(*[ctypes.c_void_p(p) for p in ptrs])
+        self._check(self._lib.qaoa_shard_set_peers(self._h, int(which), arr))
+
+    def shard_export(self, which):
+        buf = ctypes.create_string_buffer(64)
+        self._check(self._lib.qaoa_shard_export(self._h, int(which), buf))
+        return buf.raw
+
+    def shard_import(self, which, handles):
+        blob = b"".join(handles)
+        assert len(blob) == 64 * self.world
+        self._check(self._lib.qaoa_shard_import(self._h, int(which), blob))
+
+    def shard_begin(self, angles):
+        angles = np.ascontiguousarray(angles, dtype=np.float64).reshape(-1)
+        per = 1 + self.n_beta
+        if angles.size == 0 or angles.size % per:
+            raise ValueError("angle vector length %d is not a multiple of %d" % (angles.size, per))
+        n_passes = ctypes.c_int()
+        self._check(self._lib.qaoa_shard_begin(self._h, angles.size // per, _dptr(angles), angles.size,
+                                               ctypes.byref(n_passes)))
+        return n_passes.value
+
+    def shard_pass_is_cross(self, i):
+        rc = self._lib.qaoa_shard_pass_is_cross(self._h, int(i))
+        if rc < 0:
+            raise EngineError("no evaluation in flight or pass index out of range")
+        return bool(rc)
+
+    def shard_run_pass(self, i):
+        self._check(self._lib.qaoa_shard_run_pass(self._h, int(i)))
+
+    def shard_sync(self):
+        self._check(self._lib.qaoa_shard_sync(self._h))
+
+    def shard_finish(self):
+        out = np.empty(5, dtype=np.float64)
+        self._check(self._lib.qaoa_shard_finish(self._h, _dptr(out)))
+        return out
 
     def debug_tile_program(self, hb, ops, reps=5, tau=0.1):
         """Profiling hook: mean ms per launch of an arbitrary (type, frame, mask) step program."""

@@ -1,0 +1,195 @@
+"""One QAOA register sharded over several B200s (include/qaoa_b200.h "Sharded registers").
+
+The register is split on its top log2(world) qubits, one shard per GPU.  Mixer gates on those
+"global" qubits are executed by CROSS passes -- ordinary tile passes of the engine whose tile
+contains the rank bits, so their loads and stores travel over NVLink to the peers' HBM.  Nothing is
+swapped or staged: the exchange is fused into the pass.  This module is the host-side plumbing:
+
+* :class:`DistShardedEngine` -- one process per GPU under ``torch.distributed`` (NCCL or gloo): CUDA IPC
+  handles are exchanged with ``all_gather_object``, passes that touch peer memory are bracketed by
+  ``dist.barrier()``, the five partial sums are combined with a scalar all-reduce.
+* :class:`LocalShardGroup` -- every rank's engine inside ONE process (one or several GPUs); used to
+  check the sharded kernels on a single GPU: passes of different ranks only ever run back to back.
+
+Both expose the :class:`qaoa_b200.engine.Engine` surface the problem / mixer / initial-state lowering
+uses (``set_cost_*``, ``set_mixer``, ``set_initial``, ``energy``, ``energy_batch``), so ``QAOA`` can sit
+on top of either.  The reference has no multi-device path.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from qaoa_b200 import engine as _eng
+
+
+def combine_partials(parts):
+    """parts: (world, 5) rows {sum p, sum p c, sum p c^2, min c, max c} -> (E, E2, min, max, norm)."""
+    parts = np.asarray(parts, dtype=np.float64).reshape(-1, 5)
+    s0, s1, s2 = parts[:, 0].sum(), parts[:, 1].sum(), parts[:, 2].sum()
+    return np.array([s1 / s0, s2 / s0, parts[:, 3].min(), parts[:, 4].max(), s0])
+
+
+def needs_barrier(cross_flags, i):
+    """A barrier across ranks separates pass i from pass i-1 whenever either of them touches peer memory."""
+    return bool(cross_flags[i] or (i > 0 and cross_flags[i - 1]))
+
+
+class _ShardedSurface:
+    """Engine-like methods shared by the two drivers (fan a call out to the local engine(s))."""
+
+    n_beta = 1
+
+    def _engines(self):
+        raise NotImplementedError
+
+    def _diag_changed(self):
+        raise NotImplementedError
+
+    def set_option(self, key, value):
+        for e in self._engines():
+            e.set_option(key, value)
+
+    def set_cost_maxkcut(self, *a, **k):
+        for e in self._engines():
+            e.set_cost_maxkcut(*a, **k)
+        self._diag_changed()
+
+    def set_cost_qubo(self, *a, **k):
+        for e in self._engines():
+            e.set_cost_qubo(*a, **k)
+        self._diag_changed()
+
+    def set_cost_diagonal(self, diag):
+        raise _eng.EngineError("sharded engine: host-provided cost diagonals are not supported")
+
+    def set_mixer(self, kind, *a, **k):
+        for e in self._engines():
+            e.set_mixer(kind, *a, **k)
+        self.n_beta = self._engines()[0].n_beta
+
+    def set_initial(self, kind, *a, **k):
+        for e in self._engines():
+            e.set_initial(kind, *a, **k)
+
+    def energy_batch(self, angles):
+        angles = np.atleast_2d(np.asarray(angles, dtype=np.float64))
+        return np.stack([self.energy(row) for row in angles])
+
+
+class LocalShardGroup(_ShardedSurface):
+    """All ``world`` ranks inside this process (``devices[r]`` = CUDA device of rank r, default all 0)."""
+
+    def __init__(self, n_qubits, world, dtype="complex64", devices=None, engine_factory=None):
+        devices = [0] * world if devices is None else list(devices)
+        make = engine_factory or (lambda r: _eng.Engine(n_qubits, dtype=dtype, device=devices[r], rank=r, world=world))
+        self.n_qubits, self.world = int(n_qubits), int(world)
+        self.engines = [make(r) for r in range(world)]
+        ptrs = [e.shard_local_ptr(0) for e in self.engines]
+        for e in self.engines:
+            e.shard_set_peers(0, ptrs)
+        self.last_cross_flags = []
+
+    def _engines(self):
+        return self.engines
+
+    def _diag_changed(self):
+        ptrs = [e.shard_local_ptr(1) for e in self.engines]
+        for e in self.engines:
+            e.shard_set_peers(1, ptrs)
+
+    def _sync_all(self):
+        for e in self.engines:
+            e.shard_sync()
+
+    def read_cost_diagonal(self):
+        return np.concatenate([e.read_cost_diagonal() for e in self.engines])
+
+    def energy(self, angles):
+        counts = [e.shard_begin(angles) for e in self.engines]
+        assert len(set(counts)) == 1
+        self._sync_all()   # (first call: the diagonal streams of every rank are built from peer memory)
+        flags = [self.engines[0].shard_pass_is_cross(i) for i in range(counts[0])]
+        self.last_cross_flags = flags
+        for i in range(counts[0]):
+            if needs_barrier(flags, i):
+                self._sync_all()
+            for e in self.engines:
+                e.shard_run_pass(i)
+        return combine_partials([e.shard_finish() for e in self.engines])
+
+    def close(self):
+        for e in self.engines:
+            e.close()
+
+
+class DistShardedEngine(_ShardedSurface):
+    """This process' shard of a register spread over ``torch.distributed`` ranks (one process per GPU)."""
+
+    def __init__(self, n_qubits, dtype="complex64", device=None, group=None, engine_factory=None):
+        import torch.distributed as dist
+
+        self._dist = dist
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        if device is None and engine_factory is None:
+            import torch
+            device = torch.cuda.current_device()
+        make = engine_factory or (lambda r, w: _eng.Engine(n_qubits, dtype=dtype, device=device, rank=r, world=w))
+        self.n_qubits = int(n_qubits)
+        self.eng = make(self.rank, self.world)
+        self.barriers = 0
+        self._exchange(0)
+
+    def _engines(self):
+        return [self.eng]
+
+    def _barrier(self):
+        self.barriers += 1
+        self._dist.barrier(group=self.group)
+
+    def _exchange(self, which):
+        """every rank maps every other rank's buffer (state: which=0, cost diagonal: which=1)"""
+        mine = self.eng.shard_export(which)
+        handles = [None] * self.world
+        self._dist.all_gather_object(handles, mine, group=self.group)
+        self.eng.shard_import(which, handles)
+        self.eng.shard_sync()
+        self._barrier()
+
+    def _diag_changed(self):
+        self._exchange(1)
+
+    def read_cost_diagonal(self):
+        return self.eng.read_cost_diagonal()
+
+    def _all_reduce(self, part):
+        import torch
+
+        dist = self._dist
+        backend = dist.get_backend(self.group)
+        dev = "cuda" if backend == "nccl" else "cpu"
+        sums = torch.tensor(part[:3], dtype=torch.float64, device=dev)
+        lo = torch.tensor(part[3:4], dtype=torch.float64, device=dev)
+        hi = torch.tensor(part[4:5], dtype=torch.float64, device=dev)
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=self.group)
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=self.group)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=self.group)
+        s = sums.cpu().numpy()
+        return np.array([s[1] / s[0], s[2] / s[0], float(lo.cpu()[0]), float(hi.cpu()[0]), s[0]])
+
+    def energy(self, angles):
+        """(E[cost], E[cost^2], min, max, norm) of the WHOLE register; identical on every rank."""
+        eng = self.eng
+        n_passes = eng.shard_begin(angles)
+        flags = [eng.shard_pass_is_cross(i) for i in range(n_passes)]
+        for i in range(n_passes):
+            if needs_barrier(flags, i):
+                eng.shard_sync()
+                self._barrier()
+            eng.shard_run_pass(i)
+        # the all-reduce doubles as the barrier that keeps the next evaluation's first pass from
+        # overwriting a shard some peer is still reading in its last (cross) pass
+        return self._all_reduce(eng.shard_finish())
+
+    def close(self):
+        self.eng.close()

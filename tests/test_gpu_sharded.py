@@ -1,0 +1,91 @@
+"""GPU: the sharded register with every rank's engine inside ONE process on ONE GPU.
+
+The cross passes address the peers' shards through the same peer table a multi-GPU run uses (here the
+"peers" are other buffers of the same device), and passes of different ranks never overlap unless the
+protocol allows it -- so this checks the sharded kernels, the planner and the reduction without
+needing several GPUs.  The multi-process path (CUDA IPC + torch.distributed) is exercised by
+scripts/run_sharded.py on a multi-GPU box and by tests/test_sharded_protocol.py (gloo, CPU)."""
+import numpy as np
+import pytest
+
+import parity_helpers as H
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"complex64": 1e-4, "complex128": 1e-9}
+
+
+def _setup(n, world, dtype):
+    from oracle import c_oracle
+    from qaoa_b200 import engine as eng
+    from qaoa_b200.sharded import LocalShardGroup
+
+    edges, colors, table = H.regular_maxcut(n)
+    lut, _ = H.lut_from_table(table, 1)
+    grp = LocalShardGroup(n, world, dtype=dtype)
+    grp.set_cost_maxkcut(n, edges, 1, lut)
+    diag = c_oracle.maxcut_diag(n, edges)
+    return eng, grp, c_oracle, diag, edges, lut
+
+
+@pytest.mark.parametrize("n,world,dtype", [(24, 2, "complex64"), (25, 4, "complex64"), (26, 8, "complex64"),
+                                           (23, 2, "complex128"), (20, 4, "complex64")])
+def test_sharded_energy_matches_oracle_and_single_engine(n, world, dtype):
+    eng, grp, c_oracle, diag, edges, lut = _setup(n, world, dtype)
+    assert np.array_equal(grp.read_cost_diagonal(), diag), "sharded cost diagonal is not bit-exact"
+    single = eng.Engine(n, dtype=dtype)
+    single.set_cost_maxkcut(n, edges, 1, lut)
+    rng = np.random.default_rng(11)
+    for p in (1, 2, 3):
+        ang = rng.uniform(0, 2 * np.pi, size=2 * p)
+        ang[1::2] = rng.uniform(-1.2, 1.2, size=p)
+        ref = c_oracle.energy(n, diag, ang, "complex128")
+        got = grp.energy(ang)
+        one = single.energy(ang)
+        assert any(grp.last_cross_flags), "no pass touched peer memory"
+        tol = TOL[dtype]
+        assert H.rel_err(got[0], ref[0]) < tol and H.rel_err(got[1], ref[1]) < 2 * tol, (p, got, ref)
+        assert got[2] == ref[2] and got[3] == ref[3]
+        assert abs(got[4] - 1) < (1e-4 if dtype == "complex64" else 1e-11)
+        assert H.rel_err(got[0], one[0]) < tol * 0.1, (got, one)
+    grp.close()
+
+
+def test_sharded_multiangle_dicke_and_cot_form():
+    """Per-qubit betas follow the logical qubit across the shard boundary; Dicke initial state generated
+    per shard with the global popcount; beta = pi/2 exercises the interpreter's cross variant."""
+    from oracle import c_oracle
+    from oracle import qaoa_oracle as orc
+    from qaoa_b200 import engine as eng
+    from qaoa_b200.sharded import LocalShardGroup
+
+    n, world = 20, 4
+    Q, c, b = H.random_qubo(n)
+    grp = LocalShardGroup(n, world, dtype="complex128")
+    grp.set_cost_qubo(Q, c, b)
+    grp.set_mixer(eng.MIXER_XMULTI)
+    diag = c_oracle.qubo_diag(Q, c, b)
+    assert np.abs(grp.read_cost_diagonal() - diag).max() <= 1e-12 * np.abs(diag).max()
+    rng = np.random.default_rng(3)
+    ang = rng.uniform(-1.0, 1.0, size=2 * (1 + n))
+    ang[0::(1 + n)] *= 0.05
+    ang[1 + n - 1] = np.pi / 2          # top (global) qubit, layer 0: cot form
+    ref = c_oracle.energy(n, diag, ang, "complex128", n_beta=n)
+    got = grp.energy(ang)
+    assert H.rel_err(got[0], ref[0]) < 1e-9 and H.rel_err(got[1], ref[1]) < 2e-9, (got, ref)
+    grp.close()
+
+    n, world, k = 18, 2, 7
+    edges, colors, table = H.regular_maxcut(n)
+    lut, _ = H.lut_from_table(table, 1)
+    grp = LocalShardGroup(n, world, dtype="complex128")
+    grp.set_cost_maxkcut(n, edges, 1, lut)
+    grp.set_initial(eng.INIT_DICKE, k)
+    diag = H.maxcut_diag(n, edges, colors, table)
+    spec = orc.Spec(n, diag, init=orc.dicke_state(n, k))
+    ang = np.array([0.4, 0.3, 0.7, -0.5])
+    ref = orc.energy(spec, ang)
+    got = grp.energy(ang)
+    assert H.rel_err(got[0], ref[0]) < 1e-9, (got, ref)
+    assert got[2] == ref[2] and got[3] == ref[3]
+    grp.close()

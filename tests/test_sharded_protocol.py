@@ -1,0 +1,195 @@
+"""CPU, world_size 2 (gloo): the host-side protocol of the sharded register (qaoa_b200/sharded.py).
+
+DistShardedEngine is run over a stand-in for the CUDA engine that keeps each rank's shard in POSIX
+shared memory -- the CPU analogue of the CUDA-IPC peer mapping -- and implements the same pass protocol
+(shard_begin / shard_pass_is_cross / shard_run_pass / shard_finish) in numpy: local passes touch the own
+shard only, cross passes read and write the peers' shards.  The stand-in checks, at the start of every
+pass, that the barriers the protocol requires have actually happened (rank 1 is slowed down so that a
+missing barrier is caught), and the combined result must equal the oracle's energy."""
+import os
+import socket
+import time
+from multiprocessing import shared_memory
+
+import numpy as np
+import pytest
+
+from oracle import qaoa_oracle as orc
+import parity_helpers as H
+
+
+class ShmShardEngine:
+    """numpy stand-in with the shard_* surface of qaoa_b200.engine.Engine (complex128)."""
+
+    def __init__(self, n, rank, world, diag, slow=0.0):
+        self.n, self.rank, self.world = n, rank, world
+        self.g = world.bit_length() - 1
+        self.nl = n - self.g
+        self.n_beta = 1
+        self.diag = np.asarray(diag, dtype=np.float64)
+        self.slow = slow
+        # shared segment: [done_pass (int64), pad, shard (2^nl complex128)]
+        self.shm = shared_memory.SharedMemory(create=True, size=64 + (16 << self.nl))
+        self.peers = {rank: self.shm}
+        self._view(rank)[0][0] = -1
+
+    def _view(self, r):
+        buf = self.peers[r].buf
+        return np.ndarray((1,), dtype=np.int64, buffer=buf, offset=0), \
+            np.ndarray((1 << self.nl,), dtype=np.complex128, buffer=buf, offset=64)
+
+    # -- peer mapping ---------------------------------------------------------------------------
+    def shard_export(self, which):
+        return self.shm.name.encode().ljust(64, b"\0") if which == 0 else b"\0" * 64
+
+    def shard_import(self, which, handles):
+        if which != 0:
+            return
+        for r, hd in enumerate(handles):
+            if r != self.rank:
+                self.peers[r] = shared_memory.SharedMemory(name=hd.rstrip(b"\0").decode())
+
+    def shard_sync(self):
+        pass
+
+    def set_cost(self):
+        pass
+
+    # -- pass protocol ----------------------------------------------------------------------------
+    def shard_begin(self, angles):
+        self.ang = np.asarray(angles, dtype=np.float64)
+        p = self.ang.size // 2
+        self.passes = []
+        for d in range(p):
+            self.passes += [("local", d), ("cross", d)]
+        self._view(self.rank)[0][0] = -1
+        return len(self.passes)
+
+    def shard_pass_is_cross(self, i):
+        return self.passes[i][0] == "cross"
+
+    def _check_barrier(self, i):
+        from qaoa_b200.sharded import needs_barrier
+
+        flags = [k == "cross" for k, _ in self.passes]
+        if needs_barrier(flags, i):
+            for r in self.peers:
+                done = int(self._view(r)[0][0])
+                assert done >= i - 1, "rank %d started pass %d while rank %d had only finished pass %d" % (
+                    self.rank, i, r, done)
+
+    def shard_run_pass(self, i):
+        kind, d = self.passes[i]
+        self._check_barrier(i)
+        if self.slow:
+            time.sleep(self.slow)
+        gamma, beta = self.ang[2 * d], self.ang[2 * d + 1]
+        c, s = np.cos(beta), np.sin(beta)
+        _, mine = self._view(self.rank)
+        if kind == "local":
+            if d == 0:
+                mine[:] = 2.0 ** (-0.5 * self.n)
+            lo = self.rank << self.nl
+            mine *= np.exp(1j * gamma * self.diag[lo: lo + (1 << self.nl)])
+            psi = mine.reshape([2] * self.nl)
+            for q in range(self.nl):   # RX(-2 beta) = [[c, i s], [i s, c]] on local qubit q (axis nl-1-q)
+                ax = self.nl - 1 - q
+                a, b = np.take(psi, 0, axis=ax).copy(), np.take(psi, 1, axis=ax).copy()
+                idx0 = [slice(None)] * self.nl
+                idx1 = [slice(None)] * self.nl
+                idx0[ax], idx1[ax] = 0, 1
+                psi[tuple(idx0)] = c * a + 1j * s * b
+                psi[tuple(idx1)] = 1j * s * a + c * b
+        else:
+            # this rank's share of the cross tiles: the slice of LOCAL indices [rank/world, (rank+1)/world)
+            # of EVERY shard; the global qubits are the rank index bits
+            w = (1 << self.nl) // self.world
+            sl = slice(self.rank * w, (self.rank + 1) * w)
+            shards = [self._view(r)[1] for r in range(self.world)]
+            block = np.stack([sh[sl] for sh in shards])          # (world, w): axis 0 = global qubits
+            block = block.reshape([2] * self.g + [w])
+            for q in range(self.g):
+                ax = self.g - 1 - q
+                a, b = np.take(block, 0, axis=ax).copy(), np.take(block, 1, axis=ax).copy()
+                idx0 = [slice(None)] * (self.g + 1)
+                idx1 = [slice(None)] * (self.g + 1)
+                idx0[ax], idx1[ax] = 0, 1
+                block[tuple(idx0)] = c * a + 1j * s * b
+                block[tuple(idx1)] = 1j * s * a + c * b
+            block = block.reshape(self.world, w)
+            if i == len(self.passes) - 1:
+                # like the engine's FINAL pass: reduce the tiles this rank processed, store nothing
+                d = np.stack([self.diag[(r << self.nl) + sl.start: (r << self.nl) + sl.stop] for r in range(self.world)])
+                pr = np.abs(block) ** 2
+                sup = pr > 0
+                self.partial = np.array([pr.sum(), (pr * d).sum(), (pr * d * d).sum(), d[sup].min(), d[sup].max()])
+            else:
+                for r in range(self.world):
+                    shards[r][sl] = block[r]
+        self._view(self.rank)[0][0] = i
+
+    def shard_finish(self):
+        return self.partial
+
+    def close(self):
+        for r, sh in self.peers.items():
+            sh.close()
+        self.shm.unlink()
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, n, out_dir):
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from qaoa_b200 import sharded
+
+        edges, colors, table = H.regular_maxcut(n)
+        diag = H.maxcut_diag(n, edges, colors, table)
+        eng = sharded.DistShardedEngine(
+            n, engine_factory=lambda r, w: ShmShardEngine(n, r, w, diag, slow=0.05 if r == 1 else 0.0))
+        ang = np.array([0.3, 0.2, 0.5, 0.1, 1.4, -0.7])
+        status, got = "ok", None
+        try:
+            got = eng.energy(ang)
+        except AssertionError as exc:
+            status = "violation: %s" % exc
+        ref = np.array(orc.energy(orc.Spec(n, diag), ang))
+        np.save(os.path.join(out_dir, "r%d.npy" % rank), np.concatenate([[1.0 if status == "ok" else 0.0],
+                                                                          got if got is not None else np.zeros(5), ref]))
+        assert eng.barriers >= 2 * (ang.size // 2)
+        dist.barrier()
+        eng.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2])
+def test_dist_sharded_protocol_gloo(world, tmp_path):
+    import torch.multiprocessing as mp
+
+    n = 10
+    mp.spawn(_worker, args=(world, _free_port(), n, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        row = np.load(tmp_path / ("r%d.npy" % r))
+        assert row[0] == 1.0
+        got, ref = row[1:6], row[6:10]
+        assert np.allclose(got[:4], ref, rtol=1e-12), (r, got, ref)
+        assert abs(got[4] - 1.0) < 1e-12
+
+
+def test_combine_partials_and_barrier_rule():
+    from qaoa_b200.sharded import combine_partials, needs_barrier
+
+    parts = [[0.25, 1.0, 5.0, 1.0, 4.0], [0.75, 2.0, 7.0, 0.0, 3.0]]
+    out = combine_partials(parts)
+    assert np.allclose(out, [3.0, 12.0, 0.0, 4.0, 1.0])
+    flags = [False, False, True, False, False, True]
+    assert [needs_barrier(flags, i) for i in range(6)] == [False, False, True, True, False, True]
