@@ -47,7 +47,7 @@ struct PhaseSpec {
   int frame;
 };
 enum ProgId { PROG_GENERIC = 0, PROG_FIRST_INIT, PROG_FIRST_LOAD, PROG_INTERIOR, PROG_BOUNDARY, PROG_FINAL,
-              PROG_MID, PROG_BOUND2, PROG_FINAL2, PROG_COUNT };
+              PROG_MID, PROG_BOUND2, PROG_FINAL2, PROG_BOUNDX, PROG_FINALX, PROG_COUNT };
 struct PlanPass {
   TilePass tp;
   std::vector<RoundSpec> rounds;
@@ -329,6 +329,8 @@ void build_balanced(Engine* h, int p, Plan& pl) {
     else if (prog_matches<ProgMid>(tp)) pp.prog = PROG_MID;
     else if (prog_matches<ProgBound2>(tp)) pp.prog = PROG_BOUND2;
     else if (prog_matches<ProgFinal2>(tp)) pp.prog = PROG_FINAL2;
+    else if (prog_matches<ProgBoundX>(tp)) pp.prog = PROG_BOUNDX;
+    else if (prog_matches<ProgFinalX>(tp)) pp.prog = PROG_FINALX;
     if (pp.prog == PROG_GENERIC) fail("balanced planner produced a pass without a compiled program");
     pl.passes.push_back(pp);
   };
@@ -366,23 +368,28 @@ void build_balanced(Engine* h, int p, Plan& pl) {
     }
     const int g = rem.back();
     Builder b = begin(g);
+    const bool xs = b.sh->cross;   // cross shape: only the rank bits (register bits of frame A) are left
     push(b, TOP_LOAD, 0, 0, 0);
     round(b, d, 0, M_HI4);
-    push(b, TOP_XT, 0, 0, 0);
-    round(b, d, 2, M_ALL);
+    if (!xs) {
+      push(b, TOP_XT, 0, 0, 0);
+      round(b, d, 2, M_ALL);
+    }
     gdone[d][g] = 1;
     for (int e = qs; e < E; e++) if (!done[d][e]) fail("balanced planner: layer left incomplete");
     if (d == p - 1) {
       b.pp.has_reduce = true;
       b.pp.reduce_shape = g;
-      b.pp.reduce_frame = 2;
-      push(b, TOP_REDUCE, 2, (int)b.pp.phases.size(), 0);
+      b.pp.reduce_frame = xs ? 0 : 2;
+      push(b, TOP_REDUCE, xs ? 0 : 2, (int)b.pp.phases.size(), 0);
       finish(b);
       break;
     }
-    phase(b, d + 1, g, 2);
-    round(b, d + 1, 2, M_ALL);
-    push(b, TOP_XTI, 0, 0, 0);
+    phase(b, d + 1, g, xs ? 0 : 2);
+    if (!xs) {
+      round(b, d + 1, 2, M_ALL);
+      push(b, TOP_XTI, 0, 0, 0);
+    }
     round(b, d + 1, 0, M_HI4);
     push(b, TOP_STORE, 0, 0, 0);
     finish(b);
@@ -404,17 +411,19 @@ Plan build_plan(Engine* h, int p) {
   // c low bits ride along in every tile (rows of 2^c * 8 bytes).  256-byte rows (c = 5) run at full
   // DRAM speed at every stride, 128-byte rows lose ~15 % at the largest strides; use c = 5 whenever it
   // does not cost an extra pass per layer.
-  const int m4 = std::max(1, (E - 4 + 9) / 10), m5 = std::max(1, (E - 5 + 8) / 9);
-  int clow = (m5 == m4 && E >= 15) ? 5 : 4;
+  // Sharded registers: the local shapes tile the El bits of the shard exactly like an unsharded
+  // register of that size; the rank bits get a shape of their own (appended below).
+  const int EL = h->El;
+  const int m4 = std::max(1, (EL - 4 + 9) / 10), m5 = std::max(1, (EL - 5 + 8) / 9);
+  int clow = (m5 == m4 && EL >= 15) ? 5 : 4;
   if (h->low_bits == 4 || h->low_bits == 5) clow = h->low_bits;
   const int hper = TILE_BITS - clow;
-  const int nH = E - clow;
-  const int m = std::max(1, (nH + hper - 1) / hper);
-  for (int i = 0; i < m; i++) {
+  const int nH = EL - clow;
+  const int m_local = std::max(1, (nH + hper - 1) / hper);
+  for (int i = 0; i < m_local; i++) {
     std::vector<int> bits;
     for (int b = 0; b < clow; b++) bits.push_back(b);
-    int lo = clow + hper * i, hi = std::min(E, lo + hper);
-    if (h->world > 1 && i < m - 1) hi = std::min(hi, h->El);   // only the top tile may hold rank bits
+    int lo = clow + hper * i, hi = std::min(EL, lo + hper);
     std::vector<int> own;
     for (int b = lo; b < hi; b++) own.push_back(b);
     int padb = lo - 1;
@@ -425,13 +434,22 @@ Plan build_plan(Engine* h, int p) {
     for (int j = 0; j < TILE_BITS; j++) s.pos[j] = bits[j];
     for (int b = 0; b < E; b++)
       if (!std::binary_search(bits.begin(), bits.end(), b)) s.freepos.push_back(b);
-    s.cross = h->world > 1 && bits.back() >= h->El;
+    s.cross = false;
     pl.shapes.push_back(s);
   }
   if (h->world > 1) {
-    if (m < 2 || pl.shapes[0].cross) fail("sharded engine: the local shard must hold at least 14 element bits");
-    for (int i = 0; i < m; i++) if (pl.shapes[i].cross != (i == m - 1)) fail("sharded engine: unexpected cross tile");
+    // CROSS shape: the 14 - gbits lowest element bits + the rank bits.  On every rank a tile is then
+    // ONE contiguous run of 2^(14-gbits) elements (64 KB at 2 ranks, 16 KB at 8): peer traffic is
+    // sequential, which is what NVLink and the peer TLBs want (tiles made of 256-byte rows 128 MB
+    // apart ran at < 200 GB/s per direction at n = 33).
+    Shape s;
+    for (int j = 0; j < TILE_BITS - h->gbits; j++) s.pos[j] = j;
+    for (int j = 0; j < h->gbits; j++) s.pos[TILE_BITS - h->gbits + j] = EL + j;
+    for (int b = TILE_BITS - h->gbits; b < EL; b++) s.freepos.push_back(b);
+    s.cross = true;
+    pl.shapes.push_back(s);
   }
+  const int m = (int)pl.shapes.size();
   if (h->schedule != 1 && h->dtype == QAOA_DTYPE_C64 && clow == 5 && m >= 3 && !h->keep_state) {
     build_balanced(h, p, pl);
     return pl;
@@ -708,7 +726,8 @@ int launch_pass(Engine* h, const PlanPass& pp, bool use_prog, unsigned ntiles, i
   int prog = use_prog ? pp.prog : PROG_GENERIC;
   const bool cross = pp.cross;
   // cross passes have compiled programs for the high-tile passes of the balanced schedule only
-  if (cross && prog != PROG_INTERIOR && prog != PROG_BOUND2 && prog != PROG_FINAL2) prog = PROG_GENERIC;
+  if (cross && prog != PROG_BOUNDX && prog != PROG_FINALX) prog = PROG_GENERIC;
+  if (!cross && (prog == PROG_BOUNDX || prog == PROG_FINALX)) prog = PROG_GENERIC;
   const bool u8 = h->dinfo.kind == DIAG_U8;
   int nparts = (int)ntiles;
   // interpreter: one CTA per (tile, point); programs: persistent CTAs walking the linear index
@@ -733,20 +752,14 @@ int launch_pass(Engine* h, const PlanPass& pp, bool use_prog, unsigned ntiles, i
   switch (prog) {
     case PROG_FIRST_INIT: if (u8) go(tile_prog_kernel<Elem, ProgFirstInit, DIAG_U8, false>); else go(tile_prog_kernel<Elem, ProgFirstInit, 0, false>); break;
     case PROG_FIRST_LOAD: if (u8) go(tile_prog_kernel<Elem, ProgFirstLoad, DIAG_U8, false>); else go(tile_prog_kernel<Elem, ProgFirstLoad, 0, false>); break;
-    case PROG_INTERIOR:
-      if (cross) go(tile_prog_kernel<Elem, ProgInterior, DIAG_U8, true>); else go(tile_prog_kernel<Elem, ProgInterior, DIAG_U8, false>);
-      break;
+    case PROG_INTERIOR: go(tile_prog_kernel<Elem, ProgInterior, DIAG_U8, false>); break;
     case PROG_BOUNDARY: if (u8) go(tile_prog_kernel<Elem, ProgBoundary, DIAG_U8, false>); else go(tile_prog_kernel<Elem, ProgBoundary, 0, false>); break;
     case PROG_FINAL: if (u8) go(tile_prog_kernel<Elem, ProgFinal, DIAG_U8, false>); else go(tile_prog_kernel<Elem, ProgFinal, 0, false>); break;
     case PROG_MID: go(tile_prog_kernel<Elem, ProgMid, DIAG_U8, false>); break;
-    case PROG_BOUND2:
-      if (cross) { if (u8) go(tile_prog_kernel<Elem, ProgBound2, DIAG_U8, true>); else go(tile_prog_kernel<Elem, ProgBound2, 0, true>); }
-      else { if (u8) go(tile_prog_kernel<Elem, ProgBound2, DIAG_U8, false>); else go(tile_prog_kernel<Elem, ProgBound2, 0, false>); }
-      break;
-    case PROG_FINAL2:
-      if (cross) { if (u8) go(tile_prog_kernel<Elem, ProgFinal2, DIAG_U8, true>); else go(tile_prog_kernel<Elem, ProgFinal2, 0, true>); }
-      else { if (u8) go(tile_prog_kernel<Elem, ProgFinal2, DIAG_U8, false>); else go(tile_prog_kernel<Elem, ProgFinal2, 0, false>); }
-      break;
+    case PROG_BOUND2: if (u8) go(tile_prog_kernel<Elem, ProgBound2, DIAG_U8, false>); else go(tile_prog_kernel<Elem, ProgBound2, 0, false>); break;
+    case PROG_FINAL2: if (u8) go(tile_prog_kernel<Elem, ProgFinal2, DIAG_U8, false>); else go(tile_prog_kernel<Elem, ProgFinal2, 0, false>); break;
+    case PROG_BOUNDX: if (u8) go(tile_prog_kernel<Elem, ProgBoundX, DIAG_U8, true>); else go(tile_prog_kernel<Elem, ProgBoundX, 0, true>); break;
+    case PROG_FINALX: if (u8) go(tile_prog_kernel<Elem, ProgFinalX, DIAG_U8, true>); else go(tile_prog_kernel<Elem, ProgFinalX, 0, true>); break;
     default: go_generic(); break;
   }
   CUDA_OK(cudaGetLastError());

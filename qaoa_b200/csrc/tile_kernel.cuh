@@ -929,6 +929,26 @@ struct ProgFinal2 {
   PROG_COMMON
 };
 
+// ---- cross shape of a sharded register (low 14 - g element bits + the g rank bits): the only qubits
+// left to mix are the rank bits, which are register bits of frame A -- no transposes at all.
+struct ProgBoundX {   // rank qubits of layer d, phase d+1, rank qubits of layer d+1
+  static constexpr int N = 5;
+  static constexpr COp op(int i) {
+    constexpr COp o[N] = {{TOP_LOAD, 0, 0, 0}, {TOP_ROUND, 0, 0, M_HI4}, {TOP_PHASE, 0, 0, 0}, {TOP_ROUND, 0, 1, M_HI4},
+                          {TOP_STORE, 0, 0, 0}};
+    return o[i];
+  }
+  PROG_COMMON
+};
+struct ProgFinalX {   // rank qubits of the last layer, fused reduction
+  static constexpr int N = 3;
+  static constexpr COp op(int i) {
+    constexpr COp o[N] = {{TOP_LOAD, 0, 0, 0}, {TOP_ROUND, 0, 0, M_HI4}, {TOP_REDUCE, 0, 0, 0}};
+    return o[i];
+  }
+  PROG_COMMON
+};
+
 // Per-point residents of the compiled-program kernels: the round coefficients (and the reduction
 // scale, parked in the pad slot 11 of round 0) and, for U8 diagonals, the phase table of the
 // program's PHASE step.  Called whenever the CTA moves on to a new point.
@@ -965,7 +985,12 @@ struct ProgExec {
       constexpr COp op = Prog::op(I);
       constexpr bool REGS = DK == DIAG_U8 && Prog::n_stream_ops() == 1;   // stream words prefetched in dq
       const real* tau_s = reinterpret_cast<const real*>(c.smem + TileSmem<Elem>::TAU_OFF);
-      if constexpr (op.type == TOP_LOAD) { op_load_staged<Elem, CROSS>(c, v, op.frame); prefetch_later_tile<Elem>(c); }
+      if constexpr (op.type == TOP_LOAD) {
+        op_load_staged<Elem, CROSS>(c, v, op.frame);
+        if constexpr (Prog::last_transpose() < 0)   // the exchange buffer is never used: stage the rest right away
+          stage_issue<Elem, TileSmem<Elem>::STAGE_PAIRS, 16, false, CROSS>(c, c.id + c.stride, op.frame);
+        prefetch_later_tile<Elem>(c);
+      }
       else if constexpr (op.type == TOP_STORE) op_store<Elem, CROSS>(c, v, op.frame);
       else if constexpr (op.type == TOP_INIT) op_init<Elem>(c, v, op.frame);
       else if constexpr (op.type == TOP_PHASE) {
