@@ -8,10 +8,11 @@ statevector.  One step = one energy evaluation <gamma,beta|H_P|gamma,beta>.
   python bench.py [--gpus N] [--steps K] [--warmup W] [--n 32] [--p 5] [--impl reference]
 
 N = 1 : n = 32 on one B200 (32 GiB state, far larger than the 126 MB L2: nothing to flush).
-N > 1 : launched under torchrun, one rank per GPU; WEAK scaling: every rank evaluates the same
-        n = 32 register with its own angle vector (independent replicas: the landscape/optimizer
-        workloads of the reference shard over evaluations with no data-path collective).  The
-        sharded single-state path (n = 33..36) is reported by scripts/bench_sharded.py.
+N > 1 : launched under torchrun, one rank per GPU; WEAK scaling of ONE register sharded on its top
+        log2(N) qubits: n = 32 + log2(N) (32 GiB shard per GPU, as at N = 1); mixer gates on the global
+        qubits run as cross passes over NVLink peer memory, the energy is a scalar all-reduce.  The
+        line also carries "replicas": every rank evaluating its own n = 32 register (the landscape /
+        optimizer workloads shard over evaluations with no data-path collective).
 --impl reference : times the CPU restatement of the reference path (oracle/c/qaoa_ref.c, OpenMP over
         the host cores) on a bounded sample (smaller n) and scales it to the workload.
 """
@@ -36,7 +37,7 @@ def workload(n):
     import networkx as nx
     from qaoa_b200.utils.graphutils import GraphHandler
 
-    G = nx.random_regular_graph(3, n, seed=42)
+    G = nx.random_regular_graph(3 if n % 2 == 0 else 4, n, seed=42)   # odd n: no 3-regular graph exists
     gh = GraphHandler(G, check_isomorphism=False)
     return gh.edge_list()
 
@@ -94,6 +95,8 @@ def run_reference(args, rank):
 
     c_oracle.build()
     ns = args.cpu_n
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    args.n = args.n + (world.bit_length() - 1)     # same workload as the b200 arm at this GPU count
     edges = workload(ns)
     diag = c_oracle.maxcut_diag(ns, edges)
     ang = angles_for(args.p, 1234)
@@ -123,6 +126,95 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+def landscape_leg(device):
+    """BASELINE config 2: MaxCut 3-regular n=24, X mixer, p=1, 100x100 (gamma, beta) grid through the public
+    QAOA.sample_cost_landscape call (host grid in, four host arrays out)."""
+    import networkx as nx
+    from qaoa_b200 import QAOA, initialstates, mixers, problems
+
+    n, g = 24, 100
+    G = nx.random_regular_graph(3, n, seed=42)
+    q = QAOA(problem=problems.MaxCut(G), mixer=mixers.X(), initialstate=initialstates.Plus(), dtype="complex64",
+             device=device)
+    q.sample_cost_landscape({"gamma": [0, 2 * np.pi, 8], "beta": [0, 2 * np.pi, 8]})   # warm-up: plan, streams
+    grid = {"gamma": [0, 2 * np.pi, g], "beta": [0, 2 * np.pi, g]}
+    t0 = time.perf_counter()
+    q.sample_cost_landscape(grid)
+    dt = time.perf_counter() - t0
+    bytes_per_point = 2 * (8.0 + 1.0) * 2.0 ** n    # FIRST writes the state, FINAL reads it, one diagonal byte each
+    return {"workload": "MaxCut 3-regular n=%d seed=42, X, Plus, p=1, %dx%d grid, complex64" % (n, g, g),
+            "points_per_s": g * g / dt, "seconds": dt, "min_exp": float(q.Exp_sampled_p1.min()),
+            "algorithmic_gb_per_point": bytes_per_point / 1e9,
+            "achieved_gbs": bytes_per_point * g * g / dt / 1e9}
+
+
+def run_sharded(args, rank, world, local_rank, dist, torch):
+    """N > 1: ONE register of n + log2(N) qubits sharded over the N GPUs (weak scaling, 2^n amplitudes per GPU)."""
+    from qaoa_b200.sharded import DistShardedEngine
+
+    gb = world.bit_length() - 1
+    n, p = args.n + gb, args.p
+    edges = workload(n)
+    E = DistShardedEngine(n, dtype="complex64", device=local_rank)
+    E.set_cost_maxkcut(n, edges, 1, np.array([0, 1], dtype=np.uint8))
+    E.set_option("time_passes", 1)
+    ang = angles_for(p, 1234)
+    for _ in range(args.warmup):
+        out = E.energy(ang)
+    E.eng.counter("reset")
+    dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = E.energy(ang)
+    torch.cuda.synchronize()
+    dist.barrier()
+    ms_e2e = 1e3 * (time.perf_counter() - t0) / args.steps
+    names = ["interpreter", "FirstInit", "FirstLoad", "Interior", "Boundary", "Final", "Mid", "Bound2", "Final2",
+             "BoundX", "FinalX"]
+    stats = {nm: (E.eng.counter("pass_ms_%d" % i), E.eng.counter("pass_count_%d" % i), E.eng.counter("pass_bytes_%d" % i))
+             for i, nm in enumerate(names)}
+    ms_dev = sum(v[0] for v in stats.values()) / args.steps
+    launches = E.eng.counter("launches") / args.steps
+    t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_dev, ms_e2e = float(t[0]), float(t[1])
+    peak, peak_src = peaks()
+    local = {k: v for k, v in stats.items() if v[1] and k not in ("BoundX", "FinalX")}
+    dom = max(local, key=lambda k: local[k][0])
+    d_ms, d_cnt, d_bytes = local[dom]
+    achieved = (d_bytes / d_cnt) / (d_ms / d_cnt * 1e-3) / 1e9
+    shard_bytes = 8.0 * 2.0 ** (n - gb)
+    cross = {}
+    if stats["BoundX"][1]:
+        ms = stats["BoundX"][0] / stats["BoundX"][1]
+        # a read-modify-write cross pass moves (1 - 1/N) of the shard over NVLink in EACH direction twice (loads + stores)
+        per_dir = 2.0 * (1.0 - 1.0 / world) * shard_bytes
+        cross = {"kernel": "tile_prog_kernel<ProgBoundX>", "ms_per_launch": ms, "launches_per_eval": stats["BoundX"][1] / args.steps,
+                 "bytes_per_direction_per_launch": per_dir, "achieved_gbs_per_direction": per_dir / (ms * 1e-3) / 1e9,
+                 "reference_gbs_per_direction": 770.0, "reference_source": "B200_PROFILING.md measured peer copy"}
+    E.close()
+    return {
+        "value": ms_dev, "ms_per_step": ms_dev, "n_gpus": world, "scaling": "weak",
+        "config": {"workload": "MaxCut %d-regular n=%d seed=42, X mixer, Plus, p=%d, complex64, ONE register sharded on its top "
+                               "%d qubits over %d GPUs (2^%d amplitudes = %d GiB per GPU); 1 step = 1 energy evaluation"
+                               % (3 if n % 2 == 0 else 4, n, p, gb, world, n - gb, int(shard_bytes) >> 30),
+                   "l2": "shard is %d GiB >> 126 MB L2, no flush needed" % (int(shard_bytes) >> 30),
+                   "energy": float(-out[0]), "norm": float(out[4]),
+                   "value_is": "sum of the CUDA-event times of the pass kernels of one evaluation, max over ranks",
+                   "e2e_is": "wall time per evaluation through DistShardedEngine.energy (host angles in, host result out, "
+                             "barriers and the scalar all-reduce included), max over ranks"},
+        "e2e": {"value": ms_e2e, "unit": UNIT, "h2d_bytes_per_step": int(ang.nbytes) + 4096, "d2h_bytes_per_step": 40,
+                "api": "qaoa_shard_begin / qaoa_shard_run_pass / qaoa_shard_finish (C ABI via ctypes) under torch.distributed"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": "tile_prog_kernel<Prog%s>" % dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "peak_source": peak_src, "traffic": None, "launches_timed": int(d_cnt),
+                     "ms_per_launch": d_ms / d_cnt, "note": "dominant LOCAL (HBM-bound) pass on rank 0; the cross passes are NVLink-bound, see nvlink"},
+        "nvlink": cross,
+        "passes": {k: {"ms_total": v[0], "launches": int(v[1])} for k, v in stats.items() if v[1]},
+    }
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -133,6 +225,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--cpu-n", type=int, default=26, dest="cpu_n")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-landscape", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
 
@@ -154,6 +247,9 @@ def main():
     from qaoa_b200 import engine as eng
 
     n, p = args.n, args.p
+    sharded = None
+    if world > 1:
+        sharded = run_sharded(args, rank, world, local_rank, dist, torch)
     edges = workload(n)
     E = eng.Engine(n, "complex64", device=local_rank)
     E.set_cost_maxkcut(n, edges, 1, np.array([0, 1], dtype=np.uint8))
@@ -181,7 +277,7 @@ def main():
     wall_resident = time.perf_counter() - t0
     launches = E.counter("launches")
     pass_stats = {i: (E.counter("pass_ms_%d" % i), E.counter("pass_count_%d" % i), E.counter("pass_bytes_%d" % i))
-                  for i in range(9)}
+                  for i in range(11)}
     out = E.fetch_results(1)[0]
 
     # ---- end to end through the public API: host angles in, host result out ----------------------
@@ -205,7 +301,8 @@ def main():
         peak, peak_src = peaks()
         names = {0: "tile_pass_kernel (interpreter)", 1: "tile_prog_kernel<ProgFirstInit>", 2: "tile_prog_kernel<ProgFirstLoad>",
                  3: "tile_prog_kernel<ProgInterior>", 4: "tile_prog_kernel<ProgBoundary>", 5: "tile_prog_kernel<ProgFinal>",
-                 6: "tile_prog_kernel<ProgMid>", 7: "tile_prog_kernel<ProgBound2>", 8: "tile_prog_kernel<ProgFinal2>"}
+                 6: "tile_prog_kernel<ProgMid>", 7: "tile_prog_kernel<ProgBound2>", 8: "tile_prog_kernel<ProgFinal2>",
+                 9: "tile_prog_kernel<ProgBoundX>", 10: "tile_prog_kernel<ProgFinalX>"}
         dom = max(pass_stats, key=lambda i: pass_stats[i][0])
         d_ms, d_cnt, d_bytes = pass_stats[dom]
         achieved = (d_bytes / d_cnt) / (d_ms / d_cnt * 1e-3) / 1e9 if d_cnt else 0.0
@@ -247,6 +344,16 @@ def main():
                          "survey_model_frac_of_8TBps": survey_bytes / (ms_dev * 1e-3) / 8e12},
             "passes": {names[i]: {"ms_total": v[0], "launches": int(v[1])} for i, v in pass_stats.items() if v[1]},
         }
+        if world == 1 and not args.no_landscape:
+            line["landscape"] = landscape_leg(local_rank)
+        if sharded is not None:
+            # headline at N > 1: the sharded register; the per-GPU replica numbers move to "replicas"
+            line["replicas"] = {"ms_per_eval_per_gpu": ms_dev, "evals_per_s_total": 1e3 * world / ms_dev,
+                                "e2e_ms_per_eval_per_gpu": ms_e2e, "n": n,
+                                "note": "every rank evaluates its own n=%d register, no data-path collective" % n}
+            line["roofline_replica"] = line.pop("roofline")
+            line["passes_replica"] = line.pop("passes")
+            line.update(sharded)
         if not args.no_cpu_baseline and world == 1:
             from oracle import c_oracle
             try:

@@ -566,6 +566,35 @@ __device__ __forceinline__ void op_phase_u8_regs(const Ctx<Elem>& c, Elem (&v)[3
   }
 }
 
+// |+> generation fused with the first phase separator (compiled FIRST pass, U8 diagonal):
+//   psi~(x) = i^popc(x) * A * m * e^{i gamma c(x)}  =  tab4[popc(x) & 3][k(x)],
+// four rotated copies of the phase table sit in the (otherwise unused) staging area, so an amplitude
+// costs one byte extract and one shared-memory load.
+template <typename Elem>
+__device__ __forceinline__ void op_init_phase_plus(const Ctx<Elem>& c, Elem (&v)[32], const uint4 (&dq)[2]) {
+  typedef typename ElemTraits<Elem>::real real;
+  typedef typename ElemTraits<Elem>::cplx cplx;
+  constexpr int NAMP = ElemTraits<Elem>::NAMP;
+  const TilePass& P = *c.P;
+  const size_t e0 = c.base + c.thr[0];
+  const int pc0 = __popcll((unsigned long long)(e0 >> P.qshift)) + P.rank_popc;
+  const cplx* tab4 = reinterpret_cast<const cplx*>(c.smem + TileSmem<Elem>::STAGE_OFF);
+  const cplx* tb[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) tb[j] = tab4 + ((pc0 + j) & 3) * 256;
+#pragma unroll
+  for (int j = 0; j < NAMP / 16; j++) {
+    const unsigned ww[4] = {dq[j].x, dq[j].y, dq[j].z, dq[j].w};
+#pragma unroll
+    for (int b = 0; b < 16; b++) {
+      const int a = j * 16 + b;
+      const unsigned k = (ww[b >> 2] >> (8 * (b & 3))) & 0xffu;
+      const cplx ph = tb[__builtin_popcount(a) & 3][k];   // amplitude index bits are distinct element bits
+      amp_set(v, a, (real)ph.x, (real)ph.y);
+    }
+  }
+}
+
 template <typename Elem, int DK>
 __device__ __forceinline__ void op_reduce(const Ctx<Elem>& c, Elem (&v)[32], int slot) {
   typedef typename ElemTraits<Elem>::real real;
@@ -967,10 +996,21 @@ __device__ __forceinline__ void point_setup(const Ctx<Elem>& c) {
   constexpr int so = Prog::stream_op();
   if constexpr (DK == DIAG_U8 && so >= 0) {
     if constexpr (Prog::op(so >= 0 ? so : 0).type == TOP_PHASE) {
-      if (threadIdx.x >= 256) {
-        const cplx* t = reinterpret_cast<const cplx*>(c.tables) +
-                        ((size_t)c.point * c.tables_per_point + P.table_id[Prog::op(so).arg]) * 256;
-        reinterpret_cast<cplx*>(c.tab)[threadIdx.x - 256] = t[threadIdx.x - 256];
+      const cplx* t = reinterpret_cast<const cplx*>(c.tables) +
+                      ((size_t)c.point * c.tables_per_point + P.table_id[Prog::op(so).arg]) * 256;
+      if (threadIdx.x >= 256) reinterpret_cast<cplx*>(c.tab)[threadIdx.x - 256] = t[threadIdx.x - 256];
+      if constexpr (Prog::op(0).type == TOP_INIT) {
+        if (P.init_kind == INIT_PLUS) {   // tab4[r][k] = i^r * A * table[k]  (see op_init_phase_plus)
+          cplx* tab4 = reinterpret_cast<cplx*>(c.smem + TileSmem<Elem>::STAGE_OFF);
+          const real A = (real)P.init_amp;
+          for (int i = threadIdx.x; i < 1024; i += TILE_THREADS) {
+            const cplx ph = t[i & 255];
+            real re = A * ph.x, im = A * ph.y;
+            mul_i_pow(re, im, i >> 8);
+            cplx o; o.x = re; o.y = im;
+            tab4[i] = o;
+          }
+        }
       }
     }
   }
@@ -992,9 +1032,17 @@ struct ProgExec {
         prefetch_later_tile<Elem>(c);
       }
       else if constexpr (op.type == TOP_STORE) op_store<Elem, CROSS>(c, v, op.frame);
-      else if constexpr (op.type == TOP_INIT) op_init<Elem>(c, v, op.frame);
+      else if constexpr (op.type == TOP_INIT) {
+        if constexpr (REGS && Prog::op(I + 1 < Prog::N ? I + 1 : I).type == TOP_PHASE) {
+          if (c.P->init_kind == INIT_PLUS) op_init_phase_plus<Elem>(c, v, dq);   // phase fused in
+          else op_init<Elem>(c, v, op.frame);
+        } else op_init<Elem>(c, v, op.frame);
+      }
       else if constexpr (op.type == TOP_PHASE) {
-        if constexpr (REGS) op_phase_u8_regs<Elem>(c, v, dq);
+        if constexpr (REGS) {
+          constexpr bool after_init = I > 0 && Prog::op(I > 0 ? I - 1 : 0).type == TOP_INIT;
+          if (!(after_init && c.P->init_kind == INIT_PLUS)) op_phase_u8_regs<Elem>(c, v, dq);
+        }
         else op_phase<Elem, DK>(c, v, op.arg);
       }
       else if constexpr (op.type == TOP_ROUND) round_static<Elem, op.mask>(tau_s, v, op.arg);
