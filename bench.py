@@ -94,6 +94,7 @@ def run_reference(args, rank):
     from oracle import c_oracle
 
     c_oracle.build()
+    c_oracle.use_all_cores()
     ns = args.cpu_n
     world = int(os.environ.get("WORLD_SIZE", "1"))
     args.n = args.n + (world.bit_length() - 1)     # same workload as the b200 arm at this GPU count
@@ -117,7 +118,8 @@ def run_reference(args, rank):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_sample, "higher_is_better": False, "scaling": "weak",
         "vs_baseline": None, "dtype": "c64", "data": "synthetic",
-        "config": {"workload": "MaxCut 3-regular n=%d seed=42, X mixer, Plus, p=%d, complex64" % (args.n, args.p),
+        "config": {"workload": "MaxCut %d-regular n=%d seed=42, X mixer, Plus, p=%d, complex64"
+                               % (3 if args.n % 2 == 0 else 4, args.n, args.p),
                    "reference_arm": "CPU restatement of the reference path (qiskit-aer itself is not installable: "
                                     "no network); OpenMP over %d host threads" % cores},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
@@ -358,6 +360,7 @@ def main():
             from oracle import c_oracle
             try:
                 c_oracle.build()
+                c_oracle.use_all_cores()
                 ns = args.cpu_n
                 cdiag = c_oracle.maxcut_diag(ns, workload(ns))
                 c_oracle.energy(ns, cdiag, ang, "complex64")

@@ -30,6 +30,15 @@ int qref_num_threads(void) {
 #endif
 }
 
+/* launchers such as torchrun export OMP_NUM_THREADS=1; the CPU baseline wants every host core */
+void qref_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 /* cost diagonal for unweighted/weighted MaxCut: cost(x) = sum_e w_e [x_u != x_v] */
 void qref_maxcut_diag(int n, int n_edges, const int32_t* u, const int32_t* v, const double* w, double* diag) {
   const int64_t N = (int64_t)1 << n;

@@ -23,6 +23,7 @@ def load():
         dp = ctypes.POINTER(ctypes.c_double)
         ip = ctypes.POINTER(ctypes.c_int32)
         lib.qref_num_threads.restype = ctypes.c_int
+        lib.qref_set_num_threads.argtypes = [ctypes.c_int]
         lib.qref_maxcut_diag.argtypes = [ctypes.c_int, ctypes.c_int, ip, ip, dp, dp]
         for name in ("qref_energy_c128", "qref_energy_c64"):
             fn = getattr(lib, name)
@@ -39,6 +40,17 @@ def load():
 
 def num_threads():
     return load().qref_num_threads()
+
+
+def use_all_cores():
+    """Launchers such as torchrun export OMP_NUM_THREADS=1; the timed CPU baseline uses every core it may."""
+    import os
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    load().qref_set_num_threads(int(n))
+    return num_threads()
 
 
 def maxcut_diag(n, edges):
