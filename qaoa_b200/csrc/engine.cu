@@ -47,7 +47,7 @@ struct PhaseSpec {
   int frame;
 };
 enum ProgId { PROG_GENERIC = 0, PROG_FIRST_INIT, PROG_FIRST_LOAD, PROG_INTERIOR, PROG_BOUNDARY, PROG_FINAL,
-              PROG_MID, PROG_BOUND2, PROG_FINAL2, PROG_BOUNDX, PROG_FINALX, PROG_COUNT };
+              PROG_MID, PROG_BOUND2, PROG_FINAL2, PROG_BOUNDX, PROG_FINALX, PROG_BOUND2L4, PROG_FINAL2L4, PROG_COUNT };
 struct PlanPass {
   TilePass tp;
   std::vector<RoundSpec> rounds;
@@ -260,11 +260,12 @@ void build_balanced(Engine* h, int p, Plan& pl) {
   std::vector<std::vector<char>> done(p, std::vector<char>(E, 0));
   std::vector<std::vector<char>> gdone(p + 1, std::vector<char>(m, 0));
   const bool load_first = (h->init.kind == INIT_STATEVECTOR);
-  // tile-local bit held by register slot s:  kind 0 = frame A, 1 = frame B, 2 = frame C, 3 = after WT
+  // tile-local bit held by register slot s:  kind 0..4 = frames A, B, C, A4, C4;  kind 5 = after WT
   auto reg_tile_bit = [](int kind, int s) {
-    if (kind == 3) return 1 + s;
+    if (kind == 5) return 1 + s;
     return frame_reg_bit(kind, s);
   };
+  const bool low4 = pl.shapes[m > 1 ? 1 : 0].pos[4] != 4;   // high tiles carry 4 low bits
   struct Builder {
     PlanPass pp;
     const Shape* sh;
@@ -331,13 +332,15 @@ void build_balanced(Engine* h, int p, Plan& pl) {
     else if (prog_matches<ProgFinal2>(tp)) pp.prog = PROG_FINAL2;
     else if (prog_matches<ProgBoundX>(tp)) pp.prog = PROG_BOUNDX;
     else if (prog_matches<ProgFinalX>(tp)) pp.prog = PROG_FINALX;
+    else if (prog_matches<ProgBound2L4>(tp)) pp.prog = PROG_BOUND2L4;
+    else if (prog_matches<ProgFinal2L4>(tp)) pp.prog = PROG_FINAL2L4;
     if (pp.prog == PROG_GENERIC) fail("balanced planner produced a pass without a compiled program");
     pl.passes.push_back(pp);
   };
   auto full_cover = [&](Builder& b, int layer) {   // R(all) WT R(all) BT R(hi4): frame A -> B
     round(b, layer, 0, M_ALL);
     push(b, TOP_WT, 0, 0, 0);
-    round(b, layer, 3, M_ALL);
+    round(b, layer, 5, M_ALL);
     push(b, TOP_BT, 0, 0, 0);
     round(b, layer, 1, M_HI4);
   };
@@ -359,7 +362,7 @@ void build_balanced(Engine* h, int p, Plan& pl) {
       push(b, TOP_LOAD, 0, 0, 0);
       round(b, d, 0, M_HI4);
       push(b, TOP_WT, 0, 0, 0);
-      round(b, d, 3, M_TOP2);
+      round(b, d, 5, M_TOP2);
       push(b, TOP_BT, 0, 0, 0);
       round(b, d, 1, M_HI4);
       push(b, TOP_STORE, 1, 0, 0);
@@ -369,29 +372,31 @@ void build_balanced(Engine* h, int p, Plan& pl) {
     const int g = rem.back();
     Builder b = begin(g);
     const bool xs = b.sh->cross;   // cross shape: only the rank bits (register bits of frame A) are left
-    push(b, TOP_LOAD, 0, 0, 0);
-    round(b, d, 0, M_HI4);
+    const bool l4 = low4 && !xs;   // 4 low bits: frames A4 / C4, five qubits per round
+    const int fio = l4 ? 3 : 0, fmid = xs ? 0 : (l4 ? 4 : 2);
+    push(b, TOP_LOAD, fio, 0, 0);
+    round(b, d, fio, l4 ? M_ALL : M_HI4);
     if (!xs) {
       push(b, TOP_XT, 0, 0, 0);
-      round(b, d, 2, M_ALL);
+      round(b, d, fmid, M_ALL);
     }
     gdone[d][g] = 1;
     for (int e = qs; e < E; e++) if (!done[d][e]) fail("balanced planner: layer left incomplete");
     if (d == p - 1) {
       b.pp.has_reduce = true;
       b.pp.reduce_shape = g;
-      b.pp.reduce_frame = xs ? 0 : 2;
-      push(b, TOP_REDUCE, xs ? 0 : 2, (int)b.pp.phases.size(), 0);
+      b.pp.reduce_frame = fmid;
+      push(b, TOP_REDUCE, fmid, (int)b.pp.phases.size(), 0);
       finish(b);
       break;
     }
-    phase(b, d + 1, g, xs ? 0 : 2);
+    phase(b, d + 1, g, fmid);
     if (!xs) {
-      round(b, d + 1, 2, M_ALL);
+      round(b, d + 1, fmid, M_ALL);
       push(b, TOP_XTI, 0, 0, 0);
     }
-    round(b, d + 1, 0, M_HI4);
-    push(b, TOP_STORE, 0, 0, 0);
+    round(b, d + 1, fio, l4 ? M_ALL : M_HI4);
+    push(b, TOP_STORE, fio, 0, 0);
     finish(b);
     gdone[d + 1][g] = 1;
     Builder mb = begin(0);   // MID: the low tile of layer d+1
@@ -450,7 +455,7 @@ Plan build_plan(Engine* h, int p) {
     pl.shapes.push_back(s);
   }
   const int m = (int)pl.shapes.size();
-  if (h->schedule != 1 && h->dtype == QAOA_DTYPE_C64 && clow == 5 && m >= 3 && !h->keep_state) {
+  if (h->schedule != 1 && h->dtype == QAOA_DTYPE_C64 && m >= 3 && !h->keep_state) {
     build_balanced(h, p, pl);
     return pl;
   }
@@ -606,7 +611,7 @@ void* get_stream(Engine* h, const Plan& pl, int shape, int frame) {
   shard_fill(h, tp, sh.cross);
   const unsigned ntiles = 1u << (h->El - TILE_BITS);
   const int namp = h->dtype == QAOA_DTYPE_C64 ? 32 : 16;
-  if (frame == 2 && namp != 32) fail("frame C streams exist for complex64 only");
+  if (frame >= 2 && namp != 32) fail("frame C / C4 streams exist for complex64 only");
   if (vb == 1) make_stream_kernel<1><<<ntiles, TILE_THREADS, 0, h->stream>>>(tp, frame, namp, cross, (const unsigned char*)h->diag, (unsigned char*)s);
   else if (vb == 4) make_stream_kernel<4><<<ntiles, TILE_THREADS, 0, h->stream>>>(tp, frame, namp, cross, (const unsigned char*)h->diag, (unsigned char*)s);
   else make_stream_kernel<8><<<ntiles, TILE_THREADS, 0, h->stream>>>(tp, frame, namp, cross, (const unsigned char*)h->diag, (unsigned char*)s);
@@ -758,6 +763,8 @@ int launch_pass(Engine* h, const PlanPass& pp, bool use_prog, unsigned ntiles, i
     case PROG_MID: go(tile_prog_kernel<Elem, ProgMid, DIAG_U8, false>); break;
     case PROG_BOUND2: if (u8) go(tile_prog_kernel<Elem, ProgBound2, DIAG_U8, false>); else go(tile_prog_kernel<Elem, ProgBound2, 0, false>); break;
     case PROG_FINAL2: if (u8) go(tile_prog_kernel<Elem, ProgFinal2, DIAG_U8, false>); else go(tile_prog_kernel<Elem, ProgFinal2, 0, false>); break;
+    case PROG_BOUND2L4: if (u8) go(tile_prog_kernel<Elem, ProgBound2L4, DIAG_U8, false>); else go(tile_prog_kernel<Elem, ProgBound2L4, 0, false>); break;
+    case PROG_FINAL2L4: if (u8) go(tile_prog_kernel<Elem, ProgFinal2L4, DIAG_U8, false>); else go(tile_prog_kernel<Elem, ProgFinal2L4, 0, false>); break;
     case PROG_BOUNDX: if (u8) go(tile_prog_kernel<Elem, ProgBoundX, DIAG_U8, true>); else go(tile_prog_kernel<Elem, ProgBoundX, 0, true>); break;
     case PROG_FINALX: if (u8) go(tile_prog_kernel<Elem, ProgFinalX, DIAG_U8, true>); else go(tile_prog_kernel<Elem, ProgFinalX, 0, true>); break;
     default: go_generic(); break;

@@ -52,10 +52,13 @@ enum TileOpType : int {
 //   B: reg {t0, t6..t9}    lane {t1..t5}      warp {t10..t13}    (global access: 16 B per thread)
 //   C: reg {t5, t6..t9}    lane {t0, t1..t4}  warp {t10..t13}    (register-only frame, complex64)
 //   after WT (from A or B): reg {t1..t5}
+// Tiles with 4 low bits (t0..t3 low, t4..t13 high) use two more frames for their high-bit passes:
+//   A4 (3): reg {t9, t10..t13}  lane {t0..t3, t4}  warp {t5..t8}  (global access: 8 B per thread, 128-byte rows)
+//   C4 (4): reg {t4, t5..t8}    lane {t9, t0..t3}  warp {t10..t13} (register-only; A4 <-> C4 is the XT / XTI transpose)
 
 struct TileOp {
   int16_t type;
-  int16_t frame;  // 0 = A, 1 = B, 2 = C   (LOAD/STORE/INIT/PHASE/REDUCE)
+  int16_t frame;  // 0 = A, 1 = B, 2 = C, 3 = A4, 4 = C4   (LOAD/STORE/INIT/PHASE/REDUCE)
   int16_t arg;    // ROUND: round index; PHASE/REDUCE: phase slot index
   int16_t mask;   // ROUND: register slots compiled in (canonical programs)
 };
@@ -184,10 +187,18 @@ inline bool tilepass_set_free_runs(TilePass& tp) {
 }
 
 // tile-local bit held by each lane / warp / register bit of a frame (see the frame table above)
-__host__ __device__ inline int frame_lane_bit(int frame, int j) { return frame == 2 ? j : 1 + j; }
-__host__ __device__ inline int frame_warp_bit(int frame, int j) { return (frame == 0 ? 6 : 10) + j; }
+__host__ __device__ inline int frame_lane_bit(int frame, int j) {
+  if (frame == 2 || frame == 3) return j;
+  if (frame == 4) return j == 0 ? 9 : j - 1;
+  return 1 + j;
+}
+__host__ __device__ inline int frame_warp_bit(int frame, int j) {
+  return (frame == 0 ? 6 : (frame == 3 ? 5 : 10)) + j;
+}
 __host__ __device__ inline int frame_reg_bit(int frame, int j) {
   if (frame == 2) return 5 + j;
+  if (frame == 3) return 9 + j;
+  if (frame == 4) return 4 + j;
   return j == 0 ? 0 : (frame == 0 ? 9 : 5) + j;
 }
 
@@ -256,7 +267,7 @@ struct Ctx {
   double* scratch;      // block-reduction scratch in shared memory
   // hoisted shared-memory byte addresses (see warp_transpose / block_transpose)
   unsigned wt_st, wt_ld, bt_st, bt_ld;
-  size_t thr[3];   // hoisted per-thread element offsets for frames A, B, C
+  size_t thr[5];   // hoisted per-thread element offsets for frames A, B, C, A4, C4
 };
 
 template <typename Elem>
@@ -276,6 +287,8 @@ __device__ __forceinline__ void ctx_smem_setup(Ctx<Elem>& c) {
   c.thr[0] = thread_off(*c.P, 0, c.warp, c.lane);
   c.thr[1] = thread_off(*c.P, 1, c.warp, c.lane);
   c.thr[2] = thread_off(*c.P, 2, c.warp, c.lane);
+  c.thr[3] = thread_off(*c.P, 3, c.warp, c.lane);
+  c.thr[4] = thread_off(*c.P, 4, c.warp, c.lane);
 }
 
 // ---- transposes ---------------------------------------------------------------------------
@@ -480,6 +493,39 @@ __device__ __forceinline__ void op_store(const Ctx<Elem>& c, Elem (&v)[32], int 
 #pragma unroll
   for (int q = 0; q < 16; q++)
     store16(eptr<CROSS, Elem>(*c.P, c.state, ad.e0 + reg_off(ad, q)), v[2 * q], v[2 * q + 1]);
+}
+
+// frame A4: every register is one 8-byte element of its own 128-byte row
+template <typename Elem, bool CROSS>
+__device__ __forceinline__ void op_load8(const Ctx<Elem>& c, Elem (&v)[32]) {
+  const TilePass& P = *c.P;
+  const size_t e0 = c.base + c.thr[3];
+  size_t ro[5];
+#pragma unroll
+  for (int j = 0; j < 5; j++) ro[j] = (size_t)1 << P.pos[frame_reg_bit(3, j)];
+#pragma unroll
+  for (int r = 0; r < 32; r++) {
+    size_t e = e0;
+#pragma unroll
+    for (int j = 0; j < 5; j++) if (r & (1 << j)) e += ro[j];
+    v[r] = *eptr<CROSS, Elem>(P, c.state, e);
+  }
+}
+
+template <typename Elem, bool CROSS>
+__device__ __forceinline__ void op_store8(const Ctx<Elem>& c, Elem (&v)[32]) {
+  const TilePass& P = *c.P;
+  const size_t e0 = c.base + c.thr[3];
+  size_t ro[5];
+#pragma unroll
+  for (int j = 0; j < 5; j++) ro[j] = (size_t)1 << P.pos[frame_reg_bit(3, j)];
+#pragma unroll
+  for (int r = 0; r < 32; r++) {
+    size_t e = e0;
+#pragma unroll
+    for (int j = 0; j < 5; j++) if (r & (1 << j)) e += ro[j];
+    *eptr<CROSS, Elem>(P, c.state, e) = v[r];
+  }
 }
 
 template <typename Elem>
@@ -806,6 +852,48 @@ __device__ __forceinline__ void stage_issue(const Ctx<Elem>& c, unsigned long lo
   cp_async_commit();
 }
 
+__device__ __forceinline__ void cp_async8(unsigned smem_addr, const void* g) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_addr), "l"(g) : "memory");
+}
+
+// frame A4 variant: register pair q = registers (2q, 2q+1) = two 8-byte elements of different rows,
+// staged side by side in the same 16-byte slot the A / B frames use
+template <typename Elem, int Q0, int Q1, bool L2_REST, bool CROSS>
+__device__ __forceinline__ void stage_issue8(const Ctx<Elem>& c, unsigned long long id) {
+  constexpr int SP = TileSmem<Elem>::STAGE_PAIRS;
+  if (id < c.total) {
+    const TilePass& P = *c.P;
+    const unsigned ntile = (unsigned)(id % c.ntiles), npoint = (unsigned)(id / c.ntiles);
+    const size_t e0 = tile_base(P, ntile + P.tile0) + c.thr[3];
+    size_t ro[5];
+#pragma unroll
+    for (int j = 0; j < 5; j++) ro[j] = (size_t)1 << P.pos[frame_reg_bit(3, j)];
+    Elem* pb = c.state0 + (size_t)npoint * c.point_stride;
+    const unsigned sb = (unsigned)__cvta_generic_to_shared(c.smem);
+    const unsigned early = sb + TileSmem<Elem>::STAGE_OFF + threadIdx.x * 16u;
+    const unsigned late = sb + c.warp * 8192u + c.lane * 16u;
+#pragma unroll
+    for (int r = 2 * Q0; r < 2 * Q1; r++) {
+      const int q = r >> 1;
+      size_t e = e0;
+#pragma unroll
+      for (int j = 0; j < 5; j++) if (r & (1 << j)) e += ro[j];
+      const unsigned dst = (q < SP ? early + q * (TILE_THREADS * 16) : late + (q - SP) * 512) + (r & 1) * 8;
+      cp_async8(dst, eptr<CROSS, Elem>(P, pb, e));
+    }
+    if (L2_REST && !CROSS) {
+#pragma unroll
+      for (int r = 2 * Q1; r < 32; r++) {
+        size_t e = e0;
+#pragma unroll
+        for (int j = 0; j < 5; j++) if (r & (1 << j)) e += ro[j];
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(pb + e));
+      }
+    }
+  }
+  cp_async_commit();
+}
+
 // persistent-kernel load: every register pair comes from the slots filled during the previous tile
 template <typename Elem, bool CROSS>
 __device__ __forceinline__ void op_load_staged(const Ctx<Elem>& c, Elem (&v)[32], int frame) {
@@ -819,7 +907,8 @@ __device__ __forceinline__ void op_load_staged(const Ctx<Elem>& c, Elem (&v)[32]
     load16(reinterpret_cast<const Elem*>(src), v[2 * q], v[2 * q + 1]);
   }
   __syncwarp();
-  stage_issue<Elem, 0, SP, true, CROSS>(c, c.id + c.stride, frame);
+  if (frame == 3) stage_issue8<Elem, 0, SP, true, CROSS>(c, c.id + c.stride);
+  else stage_issue<Elem, 0, SP, true, CROSS>(c, c.id + c.stride, frame);
 }
 
 // ---- interpreter kernel -------------------------------------------------------------------
@@ -839,8 +928,13 @@ tile_pass_kernel(const __grid_constant__ TilePass P, Elem* __restrict__ state, s
     const TileOp cur = op;
     if (io + 1 < P.nops) op = P.ops[io + 1];  // fetch the next step early (constant-bank latency)
     switch (cur.type) {
-      case TOP_LOAD: op_load<Elem, CROSS>(c, v, cur.frame); prefetch_later_tile<Elem>(c); break;
-      case TOP_STORE: op_store<Elem, CROSS>(c, v, cur.frame); break;
+      case TOP_LOAD:
+        if (cur.frame == 3) op_load8<Elem, CROSS>(c, v); else op_load<Elem, CROSS>(c, v, cur.frame);
+        prefetch_later_tile<Elem>(c);
+        break;
+      case TOP_STORE:
+        if (cur.frame == 3) op_store8<Elem, CROSS>(c, v); else op_store<Elem, CROSS>(c, v, cur.frame);
+        break;
       case TOP_INIT: op_init<Elem>(c, v, cur.frame); break;
       case TOP_PHASE: op_phase<Elem, 0>(c, v, cur.arg); break;
       case TOP_ROUND: round_dynamic<Elem>(c, v, cur.arg); break;
@@ -958,6 +1052,27 @@ struct ProgFinal2 {
   PROG_COMMON
 };
 
+// balanced schedule for tiles with 4 low bits: the 10 high tile bits split 5 + 5 over frames A4 / C4
+struct ProgBound2L4 {
+  static constexpr int N = 9;
+  static constexpr COp op(int i) {
+    constexpr COp o[N] = {{TOP_LOAD, 3, 0, 0}, {TOP_ROUND, 0, 0, M_ALL}, {TOP_XT, 0, 0, 0}, {TOP_ROUND, 0, 1, M_ALL},
+                          {TOP_PHASE, 4, 0, 0}, {TOP_ROUND, 0, 2, M_ALL}, {TOP_XTI, 0, 0, 0}, {TOP_ROUND, 0, 3, M_ALL},
+                          {TOP_STORE, 3, 0, 0}};
+    return o[i];
+  }
+  PROG_COMMON
+};
+struct ProgFinal2L4 {
+  static constexpr int N = 5;
+  static constexpr COp op(int i) {
+    constexpr COp o[N] = {{TOP_LOAD, 3, 0, 0}, {TOP_ROUND, 0, 0, M_ALL}, {TOP_XT, 0, 0, 0}, {TOP_ROUND, 0, 1, M_ALL},
+                          {TOP_REDUCE, 4, 0, 0}};
+    return o[i];
+  }
+  PROG_COMMON
+};
+
 // ---- cross shape of a sharded register (low 14 - g element bits + the g rank bits): the only qubits
 // left to mix are the rank bits, which are register bits of frame A -- no transposes at all.
 struct ProgBoundX {   // rank qubits of layer d, phase d+1, rank qubits of layer d+1
@@ -1027,11 +1142,16 @@ struct ProgExec {
       const real* tau_s = reinterpret_cast<const real*>(c.smem + TileSmem<Elem>::TAU_OFF);
       if constexpr (op.type == TOP_LOAD) {
         op_load_staged<Elem, CROSS>(c, v, op.frame);
-        if constexpr (Prog::last_transpose() < 0)   // the exchange buffer is never used: stage the rest right away
-          stage_issue<Elem, TileSmem<Elem>::STAGE_PAIRS, 16, false, CROSS>(c, c.id + c.stride, op.frame);
+        if constexpr (Prog::last_transpose() < 0) {  // the exchange buffer is never used: stage the rest right away
+          if constexpr (op.frame == 3) stage_issue8<Elem, TileSmem<Elem>::STAGE_PAIRS, 16, false, CROSS>(c, c.id + c.stride);
+          else stage_issue<Elem, TileSmem<Elem>::STAGE_PAIRS, 16, false, CROSS>(c, c.id + c.stride, op.frame);
+        }
         prefetch_later_tile<Elem>(c);
       }
-      else if constexpr (op.type == TOP_STORE) op_store<Elem, CROSS>(c, v, op.frame);
+      else if constexpr (op.type == TOP_STORE) {
+        if constexpr (op.frame == 3) op_store8<Elem, CROSS>(c, v);
+        else op_store<Elem, CROSS>(c, v, op.frame);
+      }
       else if constexpr (op.type == TOP_INIT) {
         if constexpr (REGS && Prog::op(I + 1 < Prog::N ? I + 1 : I).type == TOP_PHASE) {
           if (c.P->init_kind == INIT_PLUS) op_init_phase_plus<Elem>(c, v, dq);   // phase fused in
@@ -1053,7 +1173,8 @@ struct ProgExec {
         else xt_c_to_a<Elem>(c, v);
         if constexpr (Prog::op(0).type == TOP_LOAD && I == Prog::last_transpose()) {
           __syncthreads();  // every warp has read its share of the exchange buffer
-          stage_issue<Elem, TileSmem<Elem>::STAGE_PAIRS, 16, false, CROSS>(c, c.id + c.stride, Prog::op(0).frame);
+          if constexpr (Prog::op(0).frame == 3) stage_issue8<Elem, TileSmem<Elem>::STAGE_PAIRS, 16, false, CROSS>(c, c.id + c.stride);
+          else stage_issue<Elem, TileSmem<Elem>::STAGE_PAIRS, 16, false, CROSS>(c, c.id + c.stride, Prog::op(0).frame);
         }
       }
       else if constexpr (op.type == TOP_REDUCE) {
@@ -1080,8 +1201,13 @@ tile_prog_kernel(const __grid_constant__ TilePass P, Elem* __restrict__ state, s
                  L::TABLE_OFF, L::SCRATCH_OFF, total);
   constexpr COp first = Prog::op(0);
   if constexpr (first.type == TOP_LOAD) {
-    stage_issue<Elem, 0, L::STAGE_PAIRS, false, CROSS>(c, blockIdx.x, first.frame);
-    stage_issue<Elem, L::STAGE_PAIRS, 16, false, CROSS>(c, blockIdx.x, first.frame);
+    if constexpr (first.frame == 3) {
+      stage_issue8<Elem, 0, L::STAGE_PAIRS, false, CROSS>(c, blockIdx.x);
+      stage_issue8<Elem, L::STAGE_PAIRS, 16, false, CROSS>(c, blockIdx.x);
+    } else {
+      stage_issue<Elem, 0, L::STAGE_PAIRS, false, CROSS>(c, blockIdx.x, first.frame);
+      stage_issue<Elem, L::STAGE_PAIRS, 16, false, CROSS>(c, blockIdx.x, first.frame);
+    }
   }
   constexpr bool HAS_RED = Prog::op(Prog::N - 1).type == TOP_REDUCE;
   double acc[5] = {0.0, 0.0, 0.0, 1e300, -1e300};

@@ -256,15 +256,18 @@ def test_beta_at_and_near_half_pi(dtype):
         _check(E.energy(ang), spec, ang, dtype, "betas=%r" % (betas,))
 
 
-@pytest.mark.parametrize("n,ps", [(25, (1, 2, 3)), (26, (2,))])
-def test_balanced_schedule_vs_classic_vs_oracle(n, ps):
+@pytest.mark.parametrize("n,ps,low_bits", [(25, (1, 2, 3), 0), (26, (2,), 0), (25, (1, 3), 4), (26, (2,), 4)])
+def test_balanced_schedule_vs_classic_vs_oracle(n, ps, low_bits):
     """complex64, n >= 25 (5 low bits, 3 tile shapes): the balanced schedule (MID + BOUND2 passes through
     frame C, FINAL2) must agree with the classic schedule (INTERIOR + BOUNDARY), with the interpreter
     running the same balanced plan, and with the oracle (C twin of the numpy oracle, pinned to it in
-    tests/test_oracle.py -- the numpy one needs minutes at this size).  n=26 pads the top tile with lower bits."""
+    tests/test_oracle.py -- the numpy one needs minutes at this size).  n=26 pads the top tile with lower bits.
+    low_bits=4 forces the tile shapes n = 33 / 34 use (BOUND2L4 / FINAL2L4 programs)."""
     from oracle import c_oracle
     dtype = "complex64"
     eng, E = _engine(n, dtype)
+    if low_bits:   # 4 low bits (what n = 33, 34 choose): high-tile passes run in frames A4 / C4 with 8-byte accesses
+        E.set_option("low_bits", low_bits)
     edges, colors, table = H.regular_maxcut(n)
     lut, _ = H.lut_from_table(table, 1)
     E.set_cost_maxkcut(n, edges, 1, lut)
