@@ -173,7 +173,7 @@ def run_sharded(args, rank, world, local_rank, dist, torch):
     dist.barrier()
     ms_e2e = 1e3 * (time.perf_counter() - t0) / args.steps
     names = ["interpreter", "FirstInit", "FirstLoad", "Interior", "Boundary", "Final", "Mid", "Bound2", "Final2",
-             "BoundX", "FinalX"]
+             "BoundX", "FinalX", "Bound2L4", "Final2L4"]
     stats = {nm: (E.eng.counter("pass_ms_%d" % i), E.eng.counter("pass_count_%d" % i), E.eng.counter("pass_bytes_%d" % i))
              for i, nm in enumerate(names)}
     ms_dev = sum(v[0] for v in stats.values()) / args.steps
@@ -279,7 +279,7 @@ def main():
     wall_resident = time.perf_counter() - t0
     launches = E.counter("launches")
     pass_stats = {i: (E.counter("pass_ms_%d" % i), E.counter("pass_count_%d" % i), E.counter("pass_bytes_%d" % i))
-                  for i in range(11)}
+                  for i in range(13)}
     out = E.fetch_results(1)[0]
 
     # ---- end to end through the public API: host angles in, host result out ----------------------
@@ -304,7 +304,8 @@ def main():
         names = {0: "tile_pass_kernel (interpreter)", 1: "tile_prog_kernel<ProgFirstInit>", 2: "tile_prog_kernel<ProgFirstLoad>",
                  3: "tile_prog_kernel<ProgInterior>", 4: "tile_prog_kernel<ProgBoundary>", 5: "tile_prog_kernel<ProgFinal>",
                  6: "tile_prog_kernel<ProgMid>", 7: "tile_prog_kernel<ProgBound2>", 8: "tile_prog_kernel<ProgFinal2>",
-                 9: "tile_prog_kernel<ProgBoundX>", 10: "tile_prog_kernel<ProgFinalX>"}
+                 9: "tile_prog_kernel<ProgBoundX>", 10: "tile_prog_kernel<ProgFinalX>",
+                 11: "tile_prog_kernel<ProgBound2L4>", 12: "tile_prog_kernel<ProgFinal2L4>"}
         dom = max(pass_stats, key=lambda i: pass_stats[i][0])
         d_ms, d_cnt, d_bytes = pass_stats[dom]
         achieved = (d_bytes / d_cnt) / (d_ms / d_cnt * 1e-3) / 1e9 if d_cnt else 0.0

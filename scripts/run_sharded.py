@@ -62,7 +62,7 @@ def main():
     torch.cuda.synchronize()
     dist.barrier()
     ms = 1e3 * (time.perf_counter() - t0) / args.reps
-    names = ["interpreter", "FirstInit", "FirstLoad", "Interior", "Boundary", "Final", "Mid", "Bound2", "Final2", "BoundX", "FinalX"]
+    names = ["interpreter", "FirstInit", "FirstLoad", "Interior", "Boundary", "Final", "Mid", "Bound2", "Final2", "BoundX", "FinalX", "Bound2L4", "Final2L4"]
     passes = {}
     for i, nm in enumerate(names):
         cnt = E.eng.counter("pass_count_%d" % i)
