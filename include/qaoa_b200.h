@@ -92,6 +92,16 @@ int qaoa_fetch_results(qaoa_engine_t* h, int B, double* out);
  * complex128 interleaved).  Test / debugging aid; 2^n * 16 bytes on the host. */
 int qaoa_read_statevector(qaoa_engine_t* h, double* out);
 
+/* Draws `shots` basis indices from |psi(angles)|^2: replaces backend.run(shots=...) + get_counts of
+ * QAOA.hist (qaoa/qaoa.py:1134-1172).  u[shots]: uniform numbers in [0,1) from the caller's seeded
+ * generator (inverse-CDF sampling, deterministic for given u); out_idx[i] = basis index of shot i. */
+int qaoa_sample(qaoa_engine_t* h, int p, const double* angles, int n_angles, int shots, const double* u,
+                uint64_t* out_idx);
+/* P(cost = *c0 + *delta * k), k < 256, over the final state (integer-valued costs with range <= 255).
+ * The shots -> infinity limit of the sorted sample list behind Statistic.get_CVaR (statistic.py:132-142). */
+int qaoa_cost_distribution(qaoa_engine_t* h, int p, const double* angles, int n_angles, double* probs256,
+                           double* c0, double* delta);
+
 /* ---- Sharded registers: one engine per GPU (one process per GPU), the register split on its top
  * log2(world) qubits; rank r holds the basis indices [r * 2^(n - log2 world), (r+1) * 2^(n - log2 world)).
  * There is nothing to replace in the reference (it has no multi-device path);

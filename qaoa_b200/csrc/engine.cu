@@ -1477,6 +1477,100 @@ int qaoa_read_statevector(qaoa_engine_t* h, double* out) {
   API_END(h)
 }
 
+// ---- sampling / cost distribution of the final state -------------------------------------------
+// evaluates `angles` with the final state kept in HBM (natural index order, S frame; |psi|^2 is what matters)
+static void eval_keeping_state(Engine* h, int p, const double* angles, int n_angles) {
+  if (h->world > 1) fail("sharded engine: sampling and cost distributions are not supported");
+  if (!angles) fail("null angles");
+  const int old = h->keep_state;
+  if (!old) { h->keep_state = 1; invalidate(h); }
+  try {
+    energy_batch_impl(h, p, angles, n_angles, 1);
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    harvest_events(h);
+  } catch (...) {
+    if (!old) { h->keep_state = 0; invalidate(h); }
+    throw;
+  }
+  if (!old) { h->keep_state = 0; invalidate(h); }
+  if (!h->state) fail("final state was not kept");
+}
+
+int qaoa_sample(qaoa_engine_t* h, int p, const double* angles, int n_angles, int shots, const double* u,
+                uint64_t* out_idx) {
+  API_BEGIN(h)
+  if (shots < 1 || !u || !out_idx) fail("empty sample request");
+  eval_keeping_state(h, p, angles, n_angles);
+  const int chunk_log2 = std::min(h->n, 16);
+  const size_t nchunks = (h->N + ((size_t)1 << chunk_log2) - 1) >> chunk_log2;
+  double* d_sums;
+  CUDA_OK(cudaMalloc((void**)&d_sums, nchunks * 8));
+  if (h->dtype == QAOA_DTYPE_C64) chunk_prob_kernel<float><<<(unsigned)nchunks, 256, 0, h->stream>>>((const float*)h->state, h->N, chunk_log2, d_sums);
+  else chunk_prob_kernel<double><<<(unsigned)nchunks, 256, 0, h->stream>>>((const double*)h->state, h->N, chunk_log2, d_sums);
+  CUDA_OK(cudaGetLastError());
+  std::vector<double> cum(nchunks);
+  CUDA_OK(cudaMemcpyAsync(cum.data(), d_sums, nchunks * 8, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  for (size_t i = 1; i < nchunks; i++) cum[i] += cum[i - 1];
+  const double total = cum[nchunks - 1];
+  if (!(total > 0.0)) fail("state has zero norm");
+  std::vector<unsigned> chunk_of(shots);
+  std::vector<double> resid(shots);
+  for (int i = 0; i < shots; i++) {
+    double t = std::min(std::max(u[i], 0.0), 1.0) * total;
+    size_t c = std::upper_bound(cum.begin(), cum.end(), t) - cum.begin();
+    if (c >= nchunks) c = nchunks - 1;
+    while (c > 0 && cum[c] - cum[c - 1] <= 0.0) c--;   // never land in an empty chunk
+    chunk_of[i] = (unsigned)c;
+    resid[i] = t - (c ? cum[c - 1] : 0.0);
+  }
+  unsigned* d_chunk; double* d_resid; unsigned long long* d_out;
+  CUDA_OK(cudaMalloc((void**)&d_chunk, (size_t)shots * 4));
+  CUDA_OK(cudaMalloc((void**)&d_resid, (size_t)shots * 8));
+  CUDA_OK(cudaMalloc((void**)&d_out, (size_t)shots * 8));
+  CUDA_OK(cudaMemcpyAsync(d_chunk, chunk_of.data(), (size_t)shots * 4, cudaMemcpyHostToDevice, h->stream));
+  CUDA_OK(cudaMemcpyAsync(d_resid, resid.data(), (size_t)shots * 8, cudaMemcpyHostToDevice, h->stream));
+  if (h->dtype == QAOA_DTYPE_C64) sample_locate_kernel<float><<<shots, 256, 0, h->stream>>>((const float*)h->state, h->N, chunk_log2, d_chunk, d_resid, d_out);
+  else sample_locate_kernel<double><<<shots, 256, 0, h->stream>>>((const double*)h->state, h->N, chunk_log2, d_chunk, d_resid, d_out);
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaMemcpyAsync(out_idx, d_out, (size_t)shots * 8, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  h->launches += 2;
+  cudaFree(d_sums); cudaFree(d_chunk); cudaFree(d_resid); cudaFree(d_out);
+  API_END(h)
+}
+
+int qaoa_cost_distribution(qaoa_engine_t* h, int p, const double* angles, int n_angles, double* probs256,
+                           double* c0, double* delta) {
+  API_BEGIN(h)
+  if (!probs256) fail("null output");
+  if (h->dinfo.kind != DIAG_U8) fail("cost distribution needs integer-valued costs with a range <= 255");
+  eval_keeping_state(h, p, angles, n_angles);
+  const int grid = grid_for(h->N, 256);
+  double* d_part;
+  CUDA_OK(cudaMalloc((void**)&d_part, (size_t)grid * 256 * 8));
+  if (h->dtype == QAOA_DTYPE_C64) cost_hist_kernel<float><<<grid, 256, 0, h->stream>>>((const float*)h->state, (const uint8_t*)h->diag, h->N, d_part);
+  else cost_hist_kernel<double><<<grid, 256, 0, h->stream>>>((const double*)h->state, (const uint8_t*)h->diag, h->N, d_part);
+  CUDA_OK(cudaGetLastError());
+  std::vector<double> part((size_t)grid * 256);
+  CUDA_OK(cudaMemcpyAsync(part.data(), d_part, part.size() * 8, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  double tot = 0.0;
+  for (int k = 0; k < 256; k++) {
+    double s = 0.0;
+    for (int b = 0; b < grid; b++) s += part[(size_t)b * 256 + k];
+    probs256[k] = s;
+    tot += s;
+  }
+  if (!(tot > 0.0)) fail("state has zero norm");
+  for (int k = 0; k < 256; k++) probs256[k] /= tot;
+  if (c0) *c0 = h->dinfo.c0;
+  if (delta) *delta = h->dinfo.delta;
+  h->launches += 1;
+  cudaFree(d_part);
+  API_END(h)
+}
+
 // ---- sharded registers ----------------------------------------------------------------------
 int qaoa_shard_info(qaoa_engine_t* h, int* rank, int* world, int* local_qubits) {
   API_BEGIN(h)

@@ -474,3 +474,87 @@ xy_gate_kernel(real* __restrict__ st, size_t N, int q0, int q1, double cd, doubl
     st[2 * xb + 1] = c * bi - s * ar;
   }
 }
+
+// ============================================================================================
+// sampling from |psi|^2 and the distribution of cost values (kept state, natural order)
+// ============================================================================================
+// Replaces backend.run(shots=...) + get_counts of QAOA.hist (reference qaoa/qaoa.py:1134-1172): the
+// engine draws basis indices by inverse-CDF search.  Stage 1: probability mass of every chunk of
+// 2^chunk_log2 amplitudes; the host turns the caller's uniform numbers into (chunk, residual mass)
+// pairs; stage 2: one block per shot walks its chunk.  Deterministic for given uniform numbers.
+template <typename real>
+__global__ void __launch_bounds__(256)
+chunk_prob_kernel(const real* __restrict__ st, size_t N, int chunk_log2, double* __restrict__ sums) {
+  __shared__ double red[8 * 5];
+  const size_t lo = (size_t)blockIdx.x << chunk_log2;
+  const size_t hi = lo + ((size_t)1 << chunk_log2) < N ? lo + ((size_t)1 << chunk_log2) : N;
+  double v[5] = {0, 0, 0, 1e300, -1e300};
+  for (size_t x = lo + threadIdx.x; x < hi; x += blockDim.x) {
+    const double re = st[2 * x], im = st[2 * x + 1];
+    v[0] += re * re + im * im;
+  }
+  block_reduce5(v, red);
+  if (threadIdx.x == 0) sums[blockIdx.x] = v[0];
+}
+
+template <typename real>
+__global__ void __launch_bounds__(256)
+sample_locate_kernel(const real* __restrict__ st, size_t N, int chunk_log2, const unsigned* __restrict__ chunk_of,
+                     const double* __restrict__ resid, unsigned long long* __restrict__ out) {
+  __shared__ double ssum[256];
+  __shared__ int found;
+  const int shot = blockIdx.x, tid = threadIdx.x;
+  const size_t lo = (size_t)chunk_of[shot] << chunk_log2;
+  const size_t hi = lo + ((size_t)1 << chunk_log2) < N ? lo + ((size_t)1 << chunk_log2) : N;
+  const size_t len = hi - lo, per = (len + 255) / 256;
+  const size_t a = lo + per * tid < hi ? lo + per * tid : hi;
+  const size_t b = a + per < hi ? a + per : hi;
+  double s = 0.0;
+  for (size_t x = a; x < b; x++) {
+    const double re = st[2 * x], im = st[2 * x + 1];
+    s += re * re + im * im;
+  }
+  ssum[tid] = s;
+  if (tid == 0) found = 0;
+  __syncthreads();
+  double prefix = 0.0;
+  for (int i = 0; i < tid; i++) prefix += ssum[i];
+  const double r = resid[shot];
+  if (s > 0.0 && prefix <= r && r < prefix + s) {
+    double run = prefix;
+    size_t pick = b - 1;
+    for (size_t x = a; x < b; x++) {
+      const double re = st[2 * x], im = st[2 * x + 1];
+      run += re * re + im * im;
+      if (run > r) { pick = x; break; }
+    }
+    out[shot] = (unsigned long long)pick;
+    found = 1;
+  }
+  __syncthreads();
+  if (!found && tid == 0) {   // rounding pushed r to the chunk's end: the last amplitude with mass
+    size_t pick = lo;
+    for (size_t x = hi; x-- > lo;) {
+      const double re = st[2 * x], im = st[2 * x + 1];
+      if (re * re + im * im > 0.0) { pick = x; break; }
+    }
+    out[shot] = (unsigned long long)pick;
+  }
+}
+
+// P(cost = c0 + delta k), k < 256, of the kept state (U8 diagonals): partial[block][256].
+// Gives the exact CVaR (reference statistic.py:132-142 in the shots -> infinity limit) and Var.
+template <typename real>
+__global__ void __launch_bounds__(256)
+cost_hist_kernel(const real* __restrict__ st, const uint8_t* __restrict__ diag, size_t N, double* __restrict__ partial) {
+  __shared__ double bins[256];
+  bins[threadIdx.x] = 0.0;
+  __syncthreads();
+  for (size_t x = blockIdx.x * (size_t)blockDim.x + threadIdx.x; x < N; x += (size_t)gridDim.x * blockDim.x) {
+    const double re = st[2 * x], im = st[2 * x + 1];
+    const double p = re * re + im * im;
+    if (p > 0.0) atomicAdd(&bins[diag[x]], p);
+  }
+  __syncthreads();
+  partial[(size_t)blockIdx.x * 256 + threadIdx.x] = bins[threadIdx.x];
+}

@@ -678,38 +678,71 @@ __device__ __forceinline__ void op_reduce(const Ctx<Elem>& c, Elem (&v)[32], int
 // static, so the summation order is fixed and results are reproducible run to run.
 // U8 diagonal: stream words in registers, integer min/max over whole words (the exact
 // "support only" handling runs only when a zero amplitude shows up).
+// (float)(byte b of w) without the conversion pipe: build 2^23 + k with one byte permute, subtract 2^23
+__device__ __forceinline__ float byte_to_float(unsigned w, int b) {
+  return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650 | b)) - 8388608.0f;
+}
+
+// Amplitudes enter UNSCALED (the scale still owed by the last layer, `post`, is <= 1 in magnitude, so
+// the stored values are the larger ones: no underflow is introduced); the sums are scaled by post^2
+// once per tile in double precision.
 template <typename Elem>
 __device__ __forceinline__ void op_reduce_u8_regs(const Ctx<Elem>& c, Elem (&v)[32], const uint4 (&dq)[2],
                                                   typename ElemTraits<Elem>::real post, double (&acc)[5]) {
   typedef typename ElemTraits<Elem>::real real;
   constexpr int NAMP = ElemTraits<Elem>::NAMP;
-  real s0 = 0, s1 = 0, s2 = 0;
-  real pmin = (real)1e30;
   unsigned mn4 = 0xffffffffu, mx4 = 0u;
+  double kmin, kmax;
+  bool has_zero;
+  double t0, t1, t2;
+  if constexpr (ElemTraits<Elem>::IS_C64) {
+    float2 s0 = make_float2(0.f, 0.f), s1 = s0, s2 = s0;   // two interleaved accumulator lanes (FFMA2)
+    float pmin = 1e30f;
 #pragma unroll
-  for (int j = 0; j < NAMP / 16; j++) {
-    const unsigned ww[4] = {dq[j].x, dq[j].y, dq[j].z, dq[j].w};
+    for (int j = 0; j < 2; j++) {
+      const unsigned ww[4] = {dq[j].x, dq[j].y, dq[j].z, dq[j].w};
+#pragma unroll
+      for (int w = 0; w < 4; w++) { mn4 = __vminu4(mn4, ww[w]); mx4 = __vmaxu4(mx4, ww[w]); }
+#pragma unroll
+      for (int b = 0; b < 16; b += 2) {
+        const float2 va = v[j * 16 + b], vb = v[j * 16 + b + 1];
+        const float2 p2 = make_float2(fmaf(va.x, va.x, va.y * va.y), fmaf(vb.x, vb.x, vb.y * vb.y));
+        const float2 k2 = make_float2(byte_to_float(ww[b >> 2], b & 3), byte_to_float(ww[(b + 1) >> 2], (b + 1) & 3));
+        const float2 pk = __fmul2_rn(p2, k2);
+        s0 = __fadd2_rn(s0, p2);
+        s1 = __fadd2_rn(s1, pk);
+        s2 = __ffma2_rn(pk, k2, s2);
+        pmin = fminf(pmin, fminf(p2.x, p2.y));
+      }
+    }
+    t0 = (double)s0.x + (double)s0.y;
+    t1 = (double)s1.x + (double)s1.y;
+    t2 = (double)s2.x + (double)s2.y;
+    has_zero = !(pmin > 0.f);
+  } else {
+    real s0 = 0, s1 = 0, s2 = 0, pmin = (real)1e300;
+    const unsigned ww[4] = {dq[0].x, dq[0].y, dq[0].z, dq[0].w};
 #pragma unroll
     for (int w = 0; w < 4; w++) { mn4 = __vminu4(mn4, ww[w]); mx4 = __vmaxu4(mx4, ww[w]); }
 #pragma unroll
-    for (int b = 0; b < 16; b++) {
-      const unsigned k = (ww[b >> 2] >> (8 * (b & 3))) & 0xffu;
+    for (int b = 0; b < NAMP; b++) {
       real re, im;
-      amp_get(v, j * 16 + b, re, im);
-      re *= post;
-      im *= post;
+      amp_get(v, b, re, im);
       const real p = re * re + im * im;
-      const real kv = (real)k;
+      const real kv = (real)((ww[b >> 2] >> (8 * (b & 3))) & 0xffu);
       s0 += p;
       s1 = fma(p, kv, s1);
       s2 = fma(p * kv, kv, s2);
       pmin = p < pmin ? p : pmin;
     }
+    t0 = s0; t1 = s1; t2 = s2;
+    has_zero = !(pmin > (real)0);
   }
-  unsigned kmn = min(min(mn4 & 0xffu, (mn4 >> 8) & 0xffu), min((mn4 >> 16) & 0xffu, mn4 >> 24));
-  unsigned kmx = max(max(mx4 & 0xffu, (mx4 >> 8) & 0xffu), max((mx4 >> 16) & 0xffu, mx4 >> 24));
-  double kmin = (double)kmn, kmax = (double)kmx;
-  if (!(pmin > (real)0)) {   // some amplitude is exactly zero: min / max over the support only
+  const unsigned kmn = min(min(mn4 & 0xffu, (mn4 >> 8) & 0xffu), min((mn4 >> 16) & 0xffu, mn4 >> 24));
+  const unsigned kmx = max(max(mx4 & 0xffu, (mx4 >> 8) & 0xffu), max((mx4 >> 16) & 0xffu, mx4 >> 24));
+  kmin = (double)kmn;
+  kmax = (double)kmx;
+  if (has_zero) {   // some amplitude is exactly zero: min / max over the support only
     kmin = 1e300; kmax = -1e300;
 #pragma unroll
     for (int j = 0; j < NAMP / 16; j++) {
@@ -719,15 +752,14 @@ __device__ __forceinline__ void op_reduce_u8_regs(const Ctx<Elem>& c, Elem (&v)[
         const unsigned k = (ww[b >> 2] >> (8 * (b & 3))) & 0xffu;
         real re, im;
         amp_get(v, j * 16 + b, re, im);
-        re *= post;
-        im *= post;
         if (re * re + im * im > (real)0) { kmin = fmin(kmin, (double)k); kmax = fmax(kmax, (double)k); }
       }
     }
   }
-  acc[0] += (double)s0;
-  acc[1] += (double)s1;
-  acc[2] += (double)s2;
+  const double sc = (double)post * (double)post;
+  acc[0] += sc * t0;
+  acc[1] += sc * t1;
+  acc[2] += sc * t2;
   acc[3] = fmin(acc[3], kmin);
   acc[4] = fmax(acc[4], kmax);
 }
@@ -1218,9 +1250,27 @@ tile_prog_kernel(const __grid_constant__ TilePass P, Elem* __restrict__ state, s
       o[0] = 0.0; o[1] = 0.0; o[2] = 0.0; o[3] = 1e300; o[4] = -1e300;
     }
   }
+  // Passes that generate the state (no LOAD) consume their diagonal words first thing in a tile: stage
+  // the NEXT tile's words in shared memory (double-buffered, behind the rotated tables) so that the
+  // DRAM latency of the stream is off the critical path as well.
+  constexpr bool DQ_SMEM = DK == DIAG_U8 && Prog::n_stream_ops() == 1 && Prog::op(0).type == TOP_INIT;
+  constexpr int DQ_OFF = L::STAGE_OFF + 4 * L::TABLE_BYTES;
+  auto dq_issue = [&](unsigned long long id, int buf) {
+    if (id < total) {
+      const unsigned t = (unsigned)(id % c.ntiles);
+      const uint4* s4 = reinterpret_cast<const uint4*>(P.streams[Prog::op(Prog::stream_op() >= 0 ? Prog::stream_op() : 0).arg]);
+      const unsigned sb = (unsigned)__cvta_generic_to_shared(smem_raw) + DQ_OFF + buf * (TILE_THREADS * 32) + threadIdx.x * 16u;
+#pragma unroll
+      for (int j = 0; j < NAMP / 16; j++)
+        cp_async16(sb + j * (TILE_THREADS * 16), s4 + stream_chunk(t, c.warp, c.lane, NAMP / 16, j));
+    }
+    cp_async_commit();
+  };
+  if constexpr (DQ_SMEM) dq_issue(blockIdx.x, 0);
   Elem v[32];
   unsigned loaded_point = 0xffffffffu;
-  for (unsigned long long id = blockIdx.x; id < total; id += gridDim.x) {
+  int it = 0;
+  for (unsigned long long id = blockIdx.x; id < total; id += gridDim.x, it ^= 1) {
     ctx_set_tile(c, id);
     if (c.point != loaded_point) {
       if constexpr (HAS_RED) {
@@ -1231,7 +1281,13 @@ tile_prog_kernel(const __grid_constant__ TilePass P, Elem* __restrict__ state, s
     }
     uint4 dq[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
     constexpr int so = Prog::stream_op();
-    if constexpr (DK == DIAG_U8 && Prog::n_stream_ops() == 1) {
+    if constexpr (DQ_SMEM) {
+      cp_async_wait_all();
+      const unsigned char* src = smem_raw + DQ_OFF + it * (TILE_THREADS * 32) + threadIdx.x * 16;
+#pragma unroll
+      for (int j = 0; j < NAMP / 16; j++) dq[j] = *reinterpret_cast<const uint4*>(src + j * (TILE_THREADS * 16));
+      dq_issue(id + gridDim.x, it ^ 1);
+    } else if constexpr (DK == DIAG_U8 && Prog::n_stream_ops() == 1) {
       // this tile's slice of the permuted diagonal: fetched now, consumed by the PHASE / REDUCE step
       const uint4* s4 = reinterpret_cast<const uint4*>(P.streams[Prog::op(so >= 0 ? so : 0).arg]);
 #pragma unroll
