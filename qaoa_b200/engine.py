@@ -78,6 +78,9 @@ def load_library():
         "qaoa_read_statevector": (ctypes.c_int, [H, _c_double_p]),
         "qaoa_debug_tile_program": (
             ctypes.c_int, [H, ctypes.c_int, _c_int32_p, ctypes.c_int, ctypes.c_int, ctypes.c_double, _c_double_p]),
+        "qaoa_sample": (ctypes.c_int, [H, ctypes.c_int, _c_double_p, ctypes.c_int, ctypes.c_int, _c_double_p, _c_uint64_p]),
+        "qaoa_cost_distribution": (ctypes.c_int, [H, ctypes.c_int, _c_double_p, ctypes.c_int, _c_double_p,
+                                                  _c_double_p, _c_double_p]),
         # sharded registers (one engine per GPU)
         "qaoa_create_sharded": (
             ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(H)]),
@@ -237,6 +240,34 @@ class Engine:
         out = np.empty(2 << self.n_qubits, dtype=np.float64)
         self._check(self._lib.qaoa_read_statevector(self._h, _dptr(out)))
         return out.view(np.complex128)
+
+    # -- sampling / cost distribution of the final state -------------------------------------------------
+    def _angles(self, angles):
+        angles = np.ascontiguousarray(angles, dtype=np.float64).reshape(-1)
+        per = 1 + self.n_beta
+        if angles.size == 0 or angles.size % per:
+            raise ValueError("angle vector length %d is not a multiple of %d" % (angles.size, per))
+        return angles, angles.size // per
+
+    def sample(self, angles, shots, seed=None):
+        """``shots`` basis indices drawn from |psi(angles)|^2 (replaces backend.run(shots) + get_counts,
+        reference qaoa/qaoa.py:1157-1172).  Bit i of an index is qubit i."""
+        angles, p = self._angles(angles)
+        u = np.ascontiguousarray(np.random.default_rng(seed).random(int(shots)), dtype=np.float64)
+        out = np.empty(int(shots), dtype=np.uint64)
+        self._check(self._lib.qaoa_sample(self._h, p, _dptr(angles), angles.size, int(shots), _dptr(u),
+                                          out.ctypes.data_as(_c_uint64_p)))
+        return out
+
+    def cost_distribution(self, angles):
+        """(cost values, probabilities) of the final state; integer-valued costs with range <= 255 only."""
+        angles, p = self._angles(angles)
+        probs = np.empty(256, dtype=np.float64)
+        c0, delta = ctypes.c_double(), ctypes.c_double()
+        self._check(self._lib.qaoa_cost_distribution(self._h, p, _dptr(angles), angles.size, _dptr(probs),
+                                                     ctypes.byref(c0), ctypes.byref(delta)))
+        keep = probs > 0
+        return (c0.value + delta.value * np.arange(256))[keep], probs[keep]
 
     # -- sharded registers: one engine per GPU (include/qaoa_b200.h, "Sharded registers") -------------
     def shard_local_ptr(self, which):

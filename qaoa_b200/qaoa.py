@@ -153,8 +153,6 @@ class QAOA:
             _reject("problems with ancilla qubits")
         if not (0 < cvar <= 1):
             raise ValueError("cvar must be in (0, 1]")
-        if cvar < 1:
-            _reject("cvar < 1")
 
         self.problem = problem
         self.mixer = mixer
@@ -232,9 +230,26 @@ class QAOA:
         return self._engine
 
     def _evaluate(self, angle_rows):
-        """(B, n_angles) flat angle vectors -> (B, 5) = E, E2, min, max, norm."""
+        """(B, n_angles) flat angle vectors -> (B, 6) = E, E2, min, max, norm, CVaR.
+
+        CVaR (= E when cvar == 1) is the shots -> infinity limit of the reference's
+        ``Statistic.get_CVaR`` (qaoa/utils/statistic.py:132-142): the mean of the best (largest-cost)
+        ``cvar`` fraction of the distribution, computed from the device's cost-value distribution."""
         rows = np.atleast_2d(np.asarray(angle_rows, dtype=np.float64))
-        return self._get_engine().energy_batch(rows)
+        eng = self._get_engine()
+        res = eng.energy_batch(rows)
+        if self.cvar < 1:
+            cv = np.array([self._exact_cvar(*eng.cost_distribution(r)) for r in rows])
+        else:
+            cv = res[:, 0]
+        return np.column_stack([res, cv])
+
+    def _exact_cvar(self, costs, probs):
+        order = np.argsort(-costs, kind="stable")
+        c, p = costs[order], probs[order]
+        cum = np.cumsum(p)
+        take = np.clip(self.cvar - (cum - p), 0.0, p)
+        return float(take @ c) / self.cvar
 
     # ------------------------------------------------------------------ accessors
     def exp_landscape(self):
@@ -338,7 +353,7 @@ class QAOA:
         LOG.info("circuits: %d", len(rows))
         res = self._evaluate(rows)
         shape = (angles["beta"][2], angles["gamma"][2])
-        self.Exp_sampled_p1 = -res[:, 0].reshape(shape)
+        self.Exp_sampled_p1 = -res[:, 5].reshape(shape)
         self.Var_sampled_p1 = np.maximum(res[:, 1] - res[:, 0] ** 2, 0.0).reshape(shape)
         self.MaxCost_sampled_p1 = -res[:, 3].reshape(shape)
         self.MinCost_sampled_p1 = -res[:, 2].reshape(shape)
@@ -393,9 +408,9 @@ class QAOA:
             raise NotImplementedError
         angles = np.asarray(angles, dtype=np.float64)
         assert len(angles) == self.n_init + self.parametrized_circuit_depth * (self.n_gamma + self.n_beta)
-        e, e2, cmin, cmax, _norm = self._evaluate(angles[self.n_init:])[0]
+        e, e2, cmin, cmax, _norm, cv = self._evaluate(angles[self.n_init:])[0]
         self.stat.reset()
-        self.stat.set_exact(e, e2, cmin, cmax)
+        self.stat.set_exact(e, e2, cmin, cmax, cvar_value=cv)
         self.optimization_results[self.current_depth + 1].add_iteration(angles.copy(), self.stat, self.shots)
         return -self.stat.get_CVaR()
 
@@ -417,9 +432,9 @@ class QAOA:
         if not self.backend.configuration().local:
             raise NotImplementedError
         angle_array = np.asarray(angle_array, dtype=np.float64)
-        e, e2, cmin, cmax, _ = self._evaluate(angle_array[self.n_init:])[0]
+        e, e2, cmin, cmax, _, cv = self._evaluate(angle_array[self.n_init:])[0]
         self.stat.reset()
-        self.stat.set_exact(e, e2, cmin, cmax)
+        self.stat.set_exact(e, e2, cmin, cmax, cvar_value=cv)
         return -self.stat.get_CVaR()
 
     def _grid_search_layer(self, prev_angles, angles):
@@ -433,7 +448,7 @@ class QAOA:
         LOG.info("Layer grid search at depth %d: %dx%d points", new_depth, len(gamma_grid), len(beta_grid))
         rows = self._vanilla_rows(gamma_grid, beta_grid, prefix=list(np.asarray(prev_angles, dtype=np.float64)))
         res = self._evaluate(rows[:, self.n_init:])
-        costs = -res[:, 0]
+        costs = -res[:, 5]
         k = int(np.argmin(costs))
         LOG.info("Layer grid search done, best cost: %.6f", -costs[k])
         return rows[k].copy()

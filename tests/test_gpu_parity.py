@@ -313,3 +313,35 @@ def test_balanced_schedule_real_valued_costs_and_multiangle():
     out = E.energy(ang)
     assert E.counter("prog_launches") >= 2
     _check(out, None, ang, "complex64", "qubo n=25", ref=ref)
+
+
+@pytest.mark.parametrize("n,dtype", [(10, "complex128"), (10, "complex64"), (18, "complex64"), (15, "complex128")])
+def test_cost_distribution_and_sampler(n, dtype):
+    """qaoa_cost_distribution (exact CVaR input) and qaoa_sample (QAOA.hist) against the oracle's final state:
+    single-CTA path (n=10) and tiled path with the state kept in HBM (n=15, 18)."""
+    eng, E = _engine(n, dtype)
+    edges, colors, table = H.regular_maxcut(n)
+    lut, _ = H.lut_from_table(table, 1)
+    E.set_cost_maxkcut(n, edges, 1, lut)
+    diag = H.maxcut_diag(n, edges, colors, table)
+    spec = orc.Spec(n, diag)
+    ang = np.array([0.45, 0.3, 0.7, -0.4])
+    prob = np.abs(orc.evolve(spec, ang)) ** 2
+    vals, pr = E.cost_distribution(ang)
+    ref = np.array([prob[diag == v].sum() for v in vals])
+    tol = 1e-10 if dtype == "complex128" else 2e-5
+    assert set(vals) <= set(np.unique(diag)) and abs(pr.sum() - 1) < 1e-12
+    assert np.abs(pr - ref).max() < tol, np.abs(pr - ref).max()
+    assert orc.exact_cvar(diag, prob, 0.25) == pytest.approx(
+        float(np.clip(0.25 - (np.cumsum(pr[::-1]) - pr[::-1]), 0, pr[::-1]) @ vals[::-1]) / 0.25, rel=10 * tol)
+    # sampler: deterministic for a seed, and distributed like |psi|^2 (chi-square over cost classes)
+    shots = 40000
+    idx = E.sample(ang, shots, seed=7)
+    assert np.array_equal(idx, E.sample(ang, shots, seed=7))
+    assert idx.max() < (1 << n) and prob[idx.astype(np.int64)].min() > 0
+    counts = np.array([(diag[idx.astype(np.int64)] == v).sum() for v in vals], dtype=float)
+    keep = ref * shots > 5
+    chi2 = (((counts - ref * shots) ** 2) / (ref * shots))[keep].sum()
+    assert chi2 < 3 * keep.sum() + 20, (chi2, keep.sum())
+    # evaluation afterwards is unaffected (keep_state was switched on only for the duration of the call)
+    _check(E.energy(ang), spec, ang, dtype, "after sampling")

@@ -65,6 +65,21 @@ class OracleEngine:
                  eng.INIT_STATEVECTOR: lambda: np.asarray(sub_vec, dtype=complex)}[sub_kind]()
             self.mixer = ("grover", s)
 
+    def _prob(self, row):
+        spec = orc.Spec(self.n_qubits, self.diag, mixer=self.mixer, init=self.init, trotter=self.trotter)
+        pr = np.abs(orc.evolve(spec, np.asarray(row, dtype=float))) ** 2
+        return pr / pr.sum()
+
+    def cost_distribution(self, row):
+        pr = self._prob(row)
+        vals = np.unique(self.diag)
+        return vals, np.array([pr[self.diag == v].sum() for v in vals])
+
+    def sample(self, row, shots, seed=None):
+        cum = np.cumsum(self._prob(row))
+        u = np.random.default_rng(seed).random(int(shots))
+        return np.minimum(np.searchsorted(cum, u * cum[-1], side="right"), len(cum) - 1).astype(np.uint64)
+
     def energy_batch(self, rows):
         spec = orc.Spec(self.n_qubits, self.diag, mixer=self.mixer, init=self.init, trotter=self.trotter)
         out = np.empty((len(rows), 5))
@@ -208,7 +223,7 @@ def test_unsupported_features_are_rejected_not_rerouted():
     G = nx.random_regular_graph(3, 4, seed=1)
     P, X, I = problems.MaxCut(G), mixers.X(), initialstates.Plus()
     for kw in ({"noisemodel": object()}, {"precision": 0.1}, {"memorysize": 10}, {"flip": True}, {"post": True},
-               {"backend": object()}, {"cvar": 0.5}):
+               {"backend": object()}):
         with pytest.raises(NotImplementedError):
             QAOA(problem=P, mixer=X, initialstate=I, **kw)
     with pytest.raises(AssertionError):
@@ -266,3 +281,29 @@ def test_optimizer_protocol_accepts_user_classes():
     q, _ = readme_qaoa(optimizer=[OneStep, {"scale": 1.0}])
     q.optimize(depth=1, angles={"gamma": [0, 2 * np.pi, 5], "beta": [0, 2 * np.pi, 5]})
     assert q.optimization_results[1].num_fval() == 1
+
+
+def test_exact_cvar_and_hist():
+    """cvar < 1: loss = -CVaR in the shots -> infinity limit of the reference's sorted-sample rule
+    (statistic.py:132-142); hist(): sampled bit-strings with string[i] = qubit i (qaoa.py:1166-1171)."""
+    q, fake = readme_qaoa(cvar=0.3)
+    q.createParameterizedCircuit(1)
+    q.optimization_results[1] = OptResult(1)
+    ang = np.array([0.3, 0.2])
+    got = q.loss(ang)
+    pr = fake._prob(ang)
+    assert got == pytest.approx(-orc.exact_cvar(fake.diag, pr, 0.3), rel=1e-12)
+    assert got < -(pr @ fake.diag)          # the best 30 % beat the mean
+    q.sample_cost_landscape({"gamma": [0, 1, 3], "beta": [0, 1, 3]})
+    assert q.Exp_sampled_p1[1, 1] == pytest.approx(
+        -orc.exact_cvar(fake.diag, fake._prob([q.gamma_grid[1], q.beta_grid[1]]), 0.3))
+
+    q, fake = readme_qaoa()
+    h = q.hist(np.array([0.61, 0.39]), 4000)
+    assert sum(h.values()) == 4000 and all(len(k) == 8 for k in h)
+    pr = fake._prob([0.61, 0.39])
+    top = max(h, key=h.get)
+    x = sum(1 << i for i, ch in enumerate(top) if ch == "1")
+    assert pr[x] > 0.5 * pr.max()           # the most frequent string is (one of) the most probable
+    emp = sum(cnt * fake.diag[sum(1 << i for i, ch in enumerate(k) if ch == "1")] for k, cnt in h.items()) / 4000
+    assert emp == pytest.approx(pr @ fake.diag, abs=0.15)
