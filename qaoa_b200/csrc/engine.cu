@@ -588,6 +588,48 @@ Plan build_plan(Engine* h, int p) {
     else if (prog_matches<ProgFinal2>(tp)) pp.prog = PROG_FINAL2;
     pl.passes.push_back(pp);
   }
+  // complex64: a last pass of the classic FINAL form (high cover through WT + BT, fused reduction)
+  // becomes the one-transpose FINAL2 / FINAL2L4 form (p = 1 landscapes at 2-shape sizes: FIRST + this)
+  if (h->dtype == QAOA_DTYPE_C64 && !h->keep_state && !pl.passes.empty() && pl.passes.back().prog == PROG_FINAL &&
+      !pl.passes.back().cross) {
+    PlanPass& pp = pl.passes.back();
+    TilePass& tp = pp.tp;
+    std::vector<char> want(E, 0);
+    int layer = p - 1;
+    for (const auto& rs : pp.rounds) { layer = rs.layer; for (int k = 0; k < 5; k++) if (rs.ebit[k] >= 0) want[rs.ebit[k]] = 1; }
+    const bool l4 = clow == 4;
+    const int fio = l4 ? 3 : 0, fmid = l4 ? 4 : 2;
+    pl.tau_per_point -= tp.tau_stride;
+    pp.rounds.clear();
+    tp.nops = 0;
+    auto push = [&](int type, int fr, int arg, int mask) {
+      tp.ops[tp.nops].type = (int16_t)type; tp.ops[tp.nops].frame = (int16_t)fr;
+      tp.ops[tp.nops].arg = (int16_t)arg; tp.ops[tp.nops].mask = (int16_t)mask; tp.nops++;
+    };
+    auto round = [&](int frame, int mask) {
+      RoundSpec rs;
+      rs.layer = layer;
+      for (int k = 0; k < 5; k++) {
+        rs.ebit[k] = -1;
+        const int eb = tp.pos[frame_reg_bit(frame, k)];
+        if (((mask >> k) & 1) && want[eb]) { rs.ebit[k] = eb; want[eb] = 0; }
+      }
+      push(TOP_ROUND, 0, (int)pp.rounds.size(), mask);
+      pp.rounds.push_back(rs);
+    };
+    push(TOP_LOAD, fio, 0, 0);
+    round(fio, l4 ? M_ALL : M_HI4);
+    push(TOP_XT, 0, 0, 0);
+    round(fmid, M_ALL);
+    for (int b = 0; b < E; b++) if (want[b]) fail("planner: FINAL2 rewrite left qubits unmixed");
+    pp.reduce_frame = fmid;
+    push(TOP_REDUCE, fmid, 0, 0);
+    tp.nrounds = (int)pp.rounds.size();
+    tp.tau_stride = tp.nrounds * TILE_ROUND_REALS;
+    pl.tau_per_point += tp.tau_stride;
+    pp.prog = l4 ? PROG_FINAL2L4 : PROG_FINAL2;
+    if (!(l4 ? prog_matches<ProgFinal2L4>(tp) : prog_matches<ProgFinal2>(tp))) fail("planner: FINAL2 rewrite mismatch");
+  }
   return pl;
 }
 

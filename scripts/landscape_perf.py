@@ -13,3 +13,18 @@ for bp in [int(a) for a in sys.argv[3:]] or [0]:
     q._get_engine().set_option("batch_points", bp)
     t0 = time.time(); q.sample_cost_landscape(grid); dt = time.time() - t0
     print("n=%d %dx%d grid batch_points=%d: %.3f s -> %.0f points/s (min Exp %.6f)" % (n, g, g, bp, dt, g * g / dt, q.Exp_sampled_p1.min()), flush=True)
+eng = q._get_engine()
+eng.set_option("time_passes", 1)
+eng.counter("reset")
+t0 = time.time(); q.sample_cost_landscape(grid); dt = time.time() - t0
+names = ["interpreter", "FirstInit", "FirstLoad", "Interior", "Boundary", "Final", "Mid", "Bound2", "Final2", "BoundX", "FinalX", "Bound2L4", "Final2L4"]
+for i, nm in enumerate(names):
+    c = eng.counter("pass_count_%d" % i)
+    if c:
+        ms = eng.counter("pass_ms_%d" % i)
+        print("  %-10s launches %4d  total %8.2f ms  per point %6.2f us  %6.0f GB/s" % (nm, c, ms, 1e3 * ms / (g * g), eng.counter("pass_bytes_%d" % i) / ms / 1e6))
+print("  wall %.3f s; launches %d" % (dt, eng.counter("launches")))
+for sched in (1,):
+    eng.set_option("schedule", sched)
+    t0 = time.time(); q.sample_cost_landscape(grid); dt = time.time() - t0
+    print("schedule=%d: %.3f s -> %.0f points/s" % (sched, dt, g * g / dt))
