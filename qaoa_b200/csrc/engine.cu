@@ -982,6 +982,7 @@ void run_elementwise_point(Engine* h, int p, const double* ang, double* d_out_po
   if (!h->d_coefdot) CUDA_OK(cudaMalloc((void**)&h->d_coefdot, 2 * sizeof(double)));
   double* part_dot = h->d_partials;
   double* part_red = h->d_partials + (size_t)grid * 5;
+  int grid_red = grid;
   real* st = (real*)h->state;
   const double sweep = (double)h->N * h->amp_bytes;
   const double dsz = (double)h->N * diag_value_bytes(h->dinfo.kind);
@@ -1002,24 +1003,89 @@ void run_elementwise_point(Engine* h, int p, const double* ang, double* d_out_po
       h->launches += 1;
     }
     ew(EW_AXPY | EW_REDUCE | (h->keep_state ? EW_STORE : 0), 0.0);
-  } else {  // XY
+  } else if (h->n < (h->dtype == QAOA_DTYPE_C64 ? 13 : 12)) {  // XY on a register smaller than a tile: one sweep per gate
     const int np = (int)h->pairs.size() / 2;
     for (int d = 0; d < p; d++) {
       ew((d == 0 ? EW_INIT : 0) | EW_PHASE | EW_STORE, ang[2 * d]);
       const double a = 0.25 * ang[2 * d + 1] / h->trotter;
-      const double c = cos(a), s = sin(a);
       const int g4 = grid_for(h->N / 4, threads);
       for (int rep = 0; rep < h->trotter; rep++)
         for (int e = 0; e < np; e++) {
-          xy_gate_kernel<real><<<g4, threads, 0, h->stream>>>(st, h->N, h->pairs[2 * e], h->pairs[2 * e + 1], c, s);
+          xy_gate_kernel<real><<<g4, threads, 0, h->stream>>>(st, h->N, h->pairs[2 * e], h->pairs[2 * e + 1], cos(a), sin(a));
           CUDA_OK(cudaGetLastError());
           h->launches += 1;
-          h->bytes_alg += sweep;  // touches half the register, read + write
+          h->bytes_alg += sweep;
         }
     }
     ew(EW_REDUCE, 0.0);
+  } else {  // XY: ordered gate list, tiled (see xy_tile_kernel)
+    const int np = (int)h->pairs.size() / 2;
+    const bool c64 = h->dtype == QAOA_DTYPE_C64;
+    const int tb = c64 ? 13 : 12, clow = c64 ? 5 : 4;
+    std::vector<std::pair<int, int>> gates;
+    for (int rep = 0; rep < h->trotter; rep++)
+      for (int e = 0; e < np; e++) gates.push_back({h->pairs[2 * e], h->pairs[2 * e + 1]});
+    // greedy cover: the longest run of consecutive gates whose qubits fit into one tile
+    std::vector<XYTilePass> layer;
+    size_t idx = 0;
+    while (idx < gates.size()) {
+      std::vector<int> extra;
+      auto in_tile = [&](int q) { return q < clow || std::find(extra.begin(), extra.end(), q) != extra.end(); };
+      std::vector<std::pair<int, int>> mine;
+      while (idx < gates.size() && (int)mine.size() < XY_MAX_GATES) {
+        std::vector<int> need;
+        if (!in_tile(gates[idx].first)) need.push_back(gates[idx].first);
+        if (!in_tile(gates[idx].second) && gates[idx].second != gates[idx].first) need.push_back(gates[idx].second);
+        if ((int)(extra.size() + need.size()) > tb - clow) break;
+        for (int q : need) extra.push_back(q);
+        mine.push_back(gates[idx]);
+        idx++;
+      }
+      if (mine.empty()) fail("XY planner: a gate does not fit into a tile");
+      for (int q = clow; (int)extra.size() < tb - clow && q < h->n; q++) if (!in_tile(q)) extra.push_back(q);
+      XYTilePass P;
+      memset(&P, 0, sizeof(P));
+      P.tb = tb;
+      std::vector<int> bits;
+      for (int q = 0; q < clow; q++) bits.push_back(q);
+      for (int q : extra) bits.push_back(q);
+      std::sort(bits.begin(), bits.end());
+      for (int k = 0; k < tb; k++) P.pos[k] = bits[k];
+      for (int q = 0; q < h->n; q++) if (!std::binary_search(bits.begin(), bits.end(), q)) P.freepos[P.nfree++] = q;
+      P.ngates = (int)mine.size();
+      for (int k = 0; k < P.ngates; k++) {
+        P.gi[k] = (unsigned char)(std::lower_bound(bits.begin(), bits.end(), mine[k].first) - bits.begin());
+        P.gj[k] = (unsigned char)(std::lower_bound(bits.begin(), bits.end(), mine[k].second) - bits.begin());
+      }
+      layer.push_back(P);
+    }
+    const size_t ntiles = h->N >> tb;
+    const int smem = (int)(((size_t)1 << tb) * h->amp_bytes);
+    auto kernel = xy_tile_kernel<real, sizeof(real) == 4 ? 13 : 12>;
+    CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int xgrid = (int)std::min<size_t>(ntiles, (size_t)h->persistent_ctas * 2);   // 64 KB + 64 registers: two CTAs per SM
+    ensure(h->d_partials, h->partials_cap, (size_t)std::max(grid, xgrid) * 5 * sizeof(double) * 2);
+    part_red = h->d_partials;
+    for (int d = 0; d < p; d++) {
+      const double a = 0.25 * ang[2 * d + 1] / h->trotter;
+      for (size_t k = 0; k < layer.size(); k++) {
+        XYTilePass P = layer[k];
+        const bool last = d == p - 1 && k + 1 == layer.size();
+        P.flags = (k == 0 ? EW_PHASE : 0) | (d == 0 && k == 0 ? EW_INIT : 0) | (last ? EW_REDUCE : EW_STORE) |
+                  (last && h->keep_state ? EW_STORE : 0);
+        P.gamma = ang[2 * d];
+        P.cd = cos(a);
+        P.sd = sin(a);
+        kernel<<<xgrid, 512, smem, h->stream>>>(P, st, ntiles, h->init, h->diag, h->dinfo, part_red);
+        CUDA_OK(cudaGetLastError());
+        h->launches += 1;
+        h->bytes_alg += ((P.flags & EW_INIT) ? 0 : sweep) + ((P.flags & EW_STORE) ? sweep : 0) +
+                        ((P.flags & (EW_PHASE | EW_REDUCE)) ? dsz : 0);
+      }
+    }
+    grid_red = xgrid;
   }
-  finalize_raw_kernel<<<1, 1024, 0, h->stream>>>(part_red, grid, d_out_point);
+  finalize_raw_kernel<<<1, 1024, 0, h->stream>>>(part_red, grid_red, d_out_point);
   CUDA_OK(cudaGetLastError());
   h->launches += 1;
   h->last_valid = true; h->last_path = 0; h->last_scale = 1.0; h->last_gsign = 1;

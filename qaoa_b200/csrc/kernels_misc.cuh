@@ -391,10 +391,19 @@ elementwise_pass_kernel(real* __restrict__ st, size_t N, int flags, StateGen ini
     double c = 0.0;
     if (flags & (EW_PHASE | EW_REDUCE)) c = diag_decode(info, diag, x);
     if (flags & EW_PHASE) {
-      double s, co;
-      sincos(gamma * c, &s, &co);
-      real r2 = re * (real)co - im * (real)s;
-      im = re * (real)s + im * (real)co;
+      real s, co;
+      if (sizeof(real) == 4) {   // range reduction in double (turns), sine / cosine in single precision
+        const double turns = gamma * 0.15915494309189533576888 * c;
+        float sf, cf;
+        sincospif(2.0f * (float)(turns - rint(turns)), &sf, &cf);
+        s = (real)sf; co = (real)cf;
+      } else {
+        double sd, cd;
+        sincos(gamma * c, &sd, &cd);
+        s = (real)sd; co = (real)cd;
+      }
+      real r2 = re * co - im * s;
+      im = re * s + im * co;
       re = r2;
     }
     if (flags & EW_DOT) {
@@ -472,6 +481,150 @@ xy_gate_kernel(real* __restrict__ st, size_t N, int q0, int q1, double cd, doubl
     st[2 * xa + 1] = c * ai - s * br;
     st[2 * xb] = c * br + s * ai;
     st[2 * xb + 1] = c * bi - s * ar;
+  }
+}
+
+// ============================================================================================
+// XY mixer at large n: shared-memory tiles, many gates per sweep
+// ============================================================================================
+// One CTA owns a tile of 2^tb amplitudes (64 KB: tb = 13 complex64 / 12 complex128; three CTAs per SM)
+// gathered from the c lowest amplitude bits (256-byte rows) plus tb - c arbitrary higher bits, applies an
+// ORDERED run of XY gates whose qubits all lie inside the tile (reference xy_mixer.py:42-79: the pairs do
+// not commute, order is semantics) and writes the tile back -- a chain of 8 gates costs one sweep instead
+// of eight.  The phase separator is fused into the first pass of a layer, |D^n_k> / |+> generation into
+// the very first pass, the statistics into the very last one.
+constexpr int XY_MAX_GATES = 64;
+constexpr int XY_MAX_TILE_BITS = 13;
+struct XYTilePass {
+  int tb;                             // tile amplitude bits
+  int pos[XY_MAX_TILE_BITS];          // amplitude-bit position of each tile-local bit (ascending)
+  int nfree;
+  int freepos[QAOA_MAX_QUBITS];       // positions of the other bits (ascending)
+  int ngates;
+  unsigned char gi[XY_MAX_GATES], gj[XY_MAX_GATES];   // tile-local bits of (q0, q1), application order
+  int flags;                          // EW_INIT / EW_PHASE / EW_REDUCE / EW_STORE
+  double gamma, cd, sd;               // phase angle; cos / sin of the gate angle beta / 4 / trotter
+};
+
+template <typename real> struct Real2;
+template <> struct Real2<float> { typedef float2 type; };
+template <> struct Real2<double> { typedef double2 type; };
+
+// shared-memory index swizzle of the XY tiles: bits 4 and 5 are folded onto the low four bits so that the
+// pair accesses of a chain gate on tile bits (k, k+1) -- consecutive lanes skip those two bits -- spread
+// over all banks for every k (and for the ring closure (tb-1, 0)); plain consecutive accesses stay conflict free
+__device__ __forceinline__ size_t xy_swz(size_t e) { return e ^ (((e >> 4) & 1) * 5) ^ (((e >> 5) & 1) * 10); }
+
+// offset contributed by the upper tile bits of element tid + 512 k (k is a compile-time constant at every
+// use: the sum lives in uniform registers)
+template <int TB>
+__device__ __forceinline__ size_t xy_off_k(const XYTilePass& P, int k) {
+  size_t o = 0;
+#pragma unroll
+  for (int b = 9; b < TB; b++) o += (size_t)((k >> (b - 9)) & 1) << P.pos[b];
+  return o;
+}
+
+template <typename real, int TB>
+__global__ void __launch_bounds__(512, 2)
+xy_tile_kernel(const __grid_constant__ XYTilePass P, real* __restrict__ st, size_t ntiles, StateGen init,
+               const void* __restrict__ diag, DiagInfo info, double* __restrict__ part_red) {
+  extern __shared__ __align__(16) unsigned char xy_smem[];
+  typedef typename Real2<real>::type real2;
+  real2* ps = reinterpret_cast<real2*>(xy_smem);
+  __shared__ double red[16 * 5];
+  const int tid = threadIdx.x;
+  constexpr size_t T = (size_t)1 << TB;
+  constexpr int PER = (int)(T / 512);   // elements per thread: all loads of a tile are issued before the first use
+  real2* st2 = reinterpret_cast<real2*>(st);
+  const real c = (real)P.cd, s = (real)P.sd;
+  // element e = tid + 512 k: the thread's 9 low tile bits are fixed, k supplies the upper ones
+  size_t off_t = 0;
+#pragma unroll
+  for (int b = 0; b < 9; b++) off_t += (size_t)((tid >> b) & 1) << P.pos[b];
+  constexpr int CH = PER < 8 ? PER : 8;   // loads in flight per thread
+  double rv[5] = {0, 0, 0, 1e300, -1e300};
+  for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    size_t base = 0;
+    for (int i = 0; i < P.nfree; i++) base |= (size_t)((tile >> i) & 1) << P.freepos[i];
+#pragma unroll
+    for (int k0 = 0; k0 < PER; k0 += CH) {
+    real2 in[CH];
+    if (!(P.flags & EW_INIT)) {
+#pragma unroll
+      for (int k = 0; k < CH; k++) in[k] = st2[base + off_t + xy_off_k<TB>(P, k0 + k)];
+    }
+#pragma unroll
+    for (int kk = 0; kk < CH; kk++) {
+      const int k = k0 + kk;
+      const size_t e = tid + 512 * (size_t)k;
+      const size_t x = base + off_t + xy_off_k<TB>(P, k);
+      real re, im;
+      if (P.flags & EW_INIT) gen_amp<real>(init, x, re, im);
+      else { re = in[kk].x; im = in[kk].y; }
+      if (P.flags & EW_PHASE) {
+        const double cst = diag_decode(info, diag, x);
+        real sn, co;
+        if (sizeof(real) == 4) {
+          const double turns = P.gamma * 0.15915494309189533576888 * cst;
+          float sf, cf;
+          sincospif(2.0f * (float)(turns - rint(turns)), &sf, &cf);
+          sn = (real)sf; co = (real)cf;
+        } else {
+          double sd2, cd2;
+          sincos(P.gamma * cst, &sd2, &cd2);
+          sn = (real)sd2; co = (real)cd2;
+        }
+        const real r2 = re * co - im * sn;
+        im = re * sn + im * co;
+        re = r2;
+      }
+      real2 o; o.x = re; o.y = im;
+      ps[xy_swz(e)] = o;
+    }
+    }
+    __syncthreads();
+    for (int g = 0; g < P.ngates; g++) {
+      const int i = P.gi[g], j = P.gj[g];
+      const int lo = i < j ? i : j, hi = i < j ? j : i;
+      for (size_t t = tid; t < T / 4; t += 512) {
+        size_t u = ((t >> lo) << (lo + 1)) | (t & (((size_t)1 << lo) - 1));
+        size_t b0 = ((u >> hi) << (hi + 1)) | (u & (((size_t)1 << hi) - 1));
+        const size_t xa = xy_swz(b0 | ((size_t)1 << i)), xb = xy_swz(b0 | ((size_t)1 << j));
+        const real2 a = ps[xa], b = ps[xb];
+        // a' = c a - i s b ; b' = -i s a + c b   (XXPlusYYGate(beta/2) on span{|01>,|10>})
+        real2 na, nb;
+        na.x = c * a.x + s * b.y;
+        na.y = c * a.y - s * b.x;
+        nb.x = c * b.x + s * a.y;
+        nb.y = c * b.y - s * a.x;
+        ps[xa] = na;
+        ps[xb] = nb;
+      }
+      __syncthreads();
+    }
+#pragma unroll
+    for (int k = 0; k < PER; k++) {
+      const size_t e = tid + 512 * (size_t)k;
+      const size_t x = base + off_t + xy_off_k<TB>(P, k);
+      const real2 o = ps[xy_swz(e)];
+      const real re = o.x, im = o.y;
+      if (P.flags & EW_REDUCE) {
+        const double pr = (double)re * re + (double)im * im;
+        const double cst = diag_decode(info, diag, x);
+        rv[0] += pr;
+        rv[1] += pr * cst;
+        rv[2] += pr * cst * cst;
+        if (pr > 0.0) { rv[3] = fmin(rv[3], cst); rv[4] = fmax(rv[4], cst); }
+      }
+      if (P.flags & EW_STORE) st2[x] = o;
+    }
+    __syncthreads();
+  }
+  if (P.flags & EW_REDUCE) {
+    block_reduce5(rv, red);
+    if (tid == 0)
+      for (int i = 0; i < 5; i++) part_red[blockIdx.x * 5 + i] = rv[i];
   }
 }
 
