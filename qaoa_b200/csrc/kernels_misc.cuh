@@ -362,6 +362,10 @@ small_fused_kernel(SmallDesc D, const int* __restrict__ pairs, const double* __r
 // ============================================================================================
 // element-wise passes for large registers: Grover mixer and XY mixer (natural order, S frame)
 // ============================================================================================
+template <typename real> struct Real2;
+template <> struct Real2<float> { typedef float2 type; };
+template <> struct Real2<double> { typedef double2 type; };
+
 enum EwFlags : int {
   EW_INIT = 1, EW_AXPY = 2, EW_PHASE = 4, EW_DOT = 8, EW_REDUCE = 16, EW_STORE = 32
 };
@@ -378,10 +382,23 @@ elementwise_pass_kernel(real* __restrict__ st, size_t N, int flags, StateGen ini
   if (flags & EW_AXPY) { fr = coefdot[0]; fi = coefdot[1]; }
   double dv[5] = {0, 0, 0, 1e300, -1e300};
   double rv[5] = {0, 0, 0, 1e300, -1e300};
-  for (size_t x = blockIdx.x * (size_t)blockDim.x + threadIdx.x; x < N; x += (size_t)gridDim.x * blockDim.x) {
+  // four elements per thread and iteration, loads first: enough bytes in flight to cover the DRAM latency
+  typedef typename Real2<real>::type real2;
+  const real2* st2 = reinterpret_cast<const real2*>(st);
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t x0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x; x0 < N; x0 += 4 * stride) {
+    real2 in[4];
+    if (!(flags & EW_INIT)) {
+#pragma unroll
+      for (int k = 0; k < 4; k++) if (x0 + k * stride < N) in[k] = st2[x0 + k * stride];
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+    const size_t x = x0 + k * stride;
+    if (x >= N) break;
     real re, im;
     if (flags & EW_INIT) gen_amp<real>(init, x, re, im);
-    else { re = st[2 * x]; im = st[2 * x + 1]; }
+    else { re = in[k].x; im = in[k].y; }
     real sr = 0, si = 0;
     if (flags & (EW_AXPY | EW_DOT)) gen_amp<real>(sub, x, sr, si);
     if (flags & EW_AXPY) {
@@ -418,6 +435,7 @@ elementwise_pass_kernel(real* __restrict__ st, size_t N, int flags, StateGen ini
       if (pr > 0.0) { rv[3] = fmin(rv[3], c); rv[4] = fmax(rv[4], c); }
     }
     if (flags & EW_STORE) { st[2 * x] = re; st[2 * x + 1] = im; }
+    }
   }
   if (flags & EW_DOT) {
     block_reduce5(dv, red);
@@ -505,10 +523,6 @@ struct XYTilePass {
   int flags;                          // EW_INIT / EW_PHASE / EW_REDUCE / EW_STORE
   double gamma, cd, sd;               // phase angle; cos / sin of the gate angle beta / 4 / trotter
 };
-
-template <typename real> struct Real2;
-template <> struct Real2<float> { typedef float2 type; };
-template <> struct Real2<double> { typedef double2 type; };
 
 // shared-memory index swizzle of the XY tiles: bits 4 and 5 are folded onto the low four bits so that the
 // pair accesses of a chain gate on tile bits (k, k+1) -- consecutive lanes skip those two bits -- spread

@@ -3,3 +3,4 @@ from .xy_mixer import XY
 from .x_mixer import X
 from .x_multiangle_mixer import XMultiAngle
 from .grover_mixer import Grover
+from .x_orbit_mixer import XOrbit

@@ -38,6 +38,10 @@ class Mixer(MixerBase):
     def get_num_parameters(self):
         return 1
 
+    def engine_betas(self, betas):
+        """this layer's mixer parameters -> the angles the device mixer takes (identity unless parameters are shared)"""
+        return list(betas)
+
     def lower_mixer(self, engine, trotter=1):
         raise NotImplementedError(
             "%s cannot be lowered onto the B200 engine (only X, XMultiAngle, XY and Grover are supported; "

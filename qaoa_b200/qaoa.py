@@ -237,6 +237,14 @@ class QAOA:
         ``cvar`` fraction of the distribution, computed from the device's cost-value distribution."""
         rows = np.atleast_2d(np.asarray(angle_rows, dtype=np.float64))
         eng = self._get_engine()
+        n_gamma, n_beta = self.problem.get_num_parameters(), self.mixer.get_num_parameters()
+        if type(self.mixer).engine_betas is not Mixer.engine_betas:
+            # shared mixer parameters (XOrbit): expand every layer's betas to what the device mixer takes
+            per = n_gamma + n_beta
+            rows = np.asarray([
+                np.concatenate([np.concatenate([r[d * per: d * per + n_gamma],
+                                                self.mixer.engine_betas(r[d * per + n_gamma: (d + 1) * per])])
+                                for d in range(len(r) // per)]) for r in rows], dtype=np.float64)
         res = eng.energy_batch(rows)
         if self.cvar < 1:
             cv = np.array([self._exact_cvar(*eng.cost_distribution(r)) for r in rows])

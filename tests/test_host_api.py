@@ -307,3 +307,32 @@ def test_exact_cvar_and_hist():
     assert pr[x] > 0.5 * pr.max()           # the most frequent string is (one of) the most probable
     emp = sum(cnt * fake.diag[sum(1 << i for i, ch in enumerate(k) if ch == "1")] for k, cnt in h.items()) / 4000
     assert emp == pytest.approx(pr @ fake.diag, abs=0.15)
+
+
+def test_xorbit_mixer_shares_betas_within_node_orbits():
+    """XOrbit (reference x_orbit_mixer.py:53-151): one beta per automorphism orbit, RX(-2 beta_orbit(q)) on qubit q.
+    Must equal XMultiAngle with the per-qubit expansion of the orbit angles."""
+    G = nx.path_graph(5)                     # orbits of a path: {ends}, {next to ends}, {centre}
+    mx = mixers.XOrbit(G)
+    assert sorted(sorted(o) for o in mx.node_orbits) == sorted(sorted(o) for o in mixers.x_orbit_mixer.node_orbits(mx._canonical_G))
+    assert mx.get_num_parameters() == 3
+    Gc = mx._canonical_G
+    for orbit in mx.node_orbits:             # nodes of an orbit are structurally equivalent
+        assert len({Gc.degree(v) for v in orbit}) == 1
+    q, fake = make(problems.MaxCut(G), mixer=mx)
+    assert fake.mixer == ("xmulti",)
+    q.createParameterizedCircuit(2)
+    assert (q.n_gamma, q.n_beta) == (1, 3)
+    q.optimization_results[1] = OptResult(1)
+    q.current_depth = 0
+    q.parametrized_circuit_depth = 2
+    ang = np.array([0.3, 0.2, 0.5, 0.1, 0.7, -0.4, 0.25, 0.9])     # (gamma, b0, b1, b2) x 2
+    got = q.loss(ang)
+    expanded = []
+    for d in range(2):
+        layer = ang[4 * d: 4 * d + 4]
+        expanded += [layer[0]] + [layer[1 + mx.node_to_orbit[v]] for v in sorted(Gc.nodes())]
+    spec = orc.Spec(5, fake.diag, mixer=("xmulti",))
+    assert got == pytest.approx(-orc.energy(spec, expanded)[0], rel=1e-12)
+    # a cycle is vertex transitive: a single orbit, i.e. the plain X mixer
+    assert mixers.XOrbit(nx.cycle_graph(6)).get_num_parameters() == 1
