@@ -40,9 +40,13 @@ class B200Backend:
 
     name = "b200_statevector"
 
-    def __init__(self, device=0, dtype="complex128"):
+    def __init__(self, device=0, dtype="complex128", sharded=False):
+        """``sharded=True`` (under ``torch.distributed``, one process per GPU): ONE register split on its top
+        qubits over all ranks (qaoa_b200/sharded.py); every rank then drives the same QAOA object and sees
+        identical results."""
         self.device = device
         self.dtype = dtype
+        self.sharded = sharded
 
     class _Conf:
         local = True
@@ -222,7 +226,11 @@ class QAOA:
                 _reject("problems with more than one gamma per layer")
             if self.initialstate.get_num_parameters() != 0:
                 _reject("parameterised initial states")
-            eng = Engine(self.problem.N_qubits, dtype=self.backend.dtype, device=self.backend.device)
+            if getattr(self.backend, "sharded", False):
+                from qaoa_b200.sharded import DistShardedEngine
+                eng = DistShardedEngine(self.problem.N_qubits, dtype=self.backend.dtype, device=self.backend.device)
+            else:
+                eng = Engine(self.problem.N_qubits, dtype=self.backend.dtype, device=self.backend.device)
             self.problem.lower_cost(eng)
             self.initialstate.lower_initial(eng)
             self.mixer.lower_mixer(eng, trotter=self.number_trottersteps_mixer)
