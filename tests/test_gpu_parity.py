@@ -345,3 +345,97 @@ def test_cost_distribution_and_sampler(n, dtype):
     assert chi2 < 3 * keep.sum() + 20, (chi2, keep.sum())
     # evaluation afterwards is unaffected (keep_state was switched on only for the duration of the call)
     _check(E.energy(ang), spec, ang, dtype, "after sampling")
+
+
+def test_randomised_configurations_against_oracle():
+    """Seeded sweep over the supported combinations (problem x mixer x initial state x precision x depth x size,
+    including arbitrary XY pair lists, trotter steps, weighted graphs, k-cut colour tables and fixed nodes):
+    every one must agree with the numpy oracle within the stated tolerance."""
+    from qaoa_b200 import engine as eng
+    rng = np.random.default_rng(20261019)
+    checked = 0
+    for trial in range(60):
+        n = int(rng.integers(4, 18))
+        dtype = ["complex64", "complex128"][trial % 2]
+        p = int(rng.integers(1, 4))
+        E = eng.Engine(n, dtype=dtype)
+        kind = ["maxcut", "wmaxcut", "qubo", "diag", "kcut"][int(rng.integers(0, 5))]
+        if kind == "kcut" and n % 2:
+            kind = "maxcut"
+        if kind in ("maxcut", "wmaxcut"):
+            G = orc.relabel_graph(__import__("networkx").gnp_random_graph(n, 0.4, seed=int(rng.integers(1 << 30))))
+            edges = [(u, v, (1.0 if kind == "maxcut" else float(rng.uniform(-1, 2)))) for (u, v, _w) in orc.graph_edges(G)]
+            if not edges:
+                edges = [(0, 1, 1.0)]
+            colors, table = orc.colour_table(2)
+            lut, _ = H.lut_from_table(table, 1)
+            E.set_cost_maxkcut(n, edges, 1, lut)
+            diag = orc.maxkcut_diag(edges, n, 1, table, colors)
+        elif kind == "kcut":      # k = 4 colours, two qubits per node
+            nv = n // 2
+            G = orc.relabel_graph(__import__("networkx").gnp_random_graph(nv, 0.6, seed=int(rng.integers(1 << 30))))
+            edges = orc.graph_edges(G) or [(0, 1, 1.0)]
+            colors, table = orc.colour_table(4)
+            lut, _ = H.lut_from_table(table, 2)
+            E.set_cost_maxkcut(nv, edges, 2, lut)
+            diag = orc.maxkcut_diag(edges, nv, 2, table, colors)
+        elif kind == "qubo":
+            Q, c, b = H.random_qubo(n, seed=int(rng.integers(1 << 30)))
+            E.set_cost_qubo(Q, c, b)
+            diag = orc.qubo_diag(Q, c, b)
+        else:
+            diag = np.round(rng.uniform(-3, 9, size=1 << n), 3)
+            E.set_cost_diagonal(diag)
+        got = E.read_cost_diagonal()
+        scale = max(1.0, np.abs(diag).max())
+        assert np.abs(got - diag).max() <= (1e-12 if dtype == "complex128" else 3e-9) * scale, (trial, kind)
+        k = int(rng.integers(1, n))
+        init_kind = ["plus", "dicke", "vec"][int(rng.integers(0, 3))]
+        mixer_kind = ["x", "xmulti", "xy", "grover"][int(rng.integers(0, 4))]
+        if mixer_kind in ("xy",) and init_kind == "plus":
+            init_kind = "dicke"
+        if init_kind == "plus":
+            init = orc.plus_state(n)
+            E.set_initial(eng.INIT_PLUS)
+        elif init_kind == "dicke":
+            init = orc.dicke_state(n, k)
+            E.set_initial(eng.INIT_DICKE, k)
+        else:
+            init = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
+            init /= np.linalg.norm(init)
+            E.set_initial(eng.INIT_STATEVECTOR, vec=init)
+        trotter, nb = 1, 1
+        if mixer_kind == "x":
+            mixer = ("x",)
+            E.set_mixer(eng.MIXER_X)
+        elif mixer_kind == "xmulti":
+            mixer, nb = ("xmulti",), n
+            E.set_mixer(eng.MIXER_XMULTI)
+        elif mixer_kind == "xy":
+            trotter = int(rng.integers(1, 3))
+            if rng.random() < 0.5:
+                pairs = orc.xy_pairs(n, ["ring", "chain"][int(rng.integers(0, 2))])
+            else:       # arbitrary ordered pair list
+                pairs = [list(rng.choice(n, size=2, replace=False)) for _ in range(int(rng.integers(1, 2 * n)))]
+                pairs = [[int(a), int(b)] for a, b in pairs]
+            mixer = ("xy", pairs)
+            E.set_mixer(eng.MIXER_XY, pairs=pairs, trotter=trotter)
+        else:
+            s = orc.dicke_state(n, k) if init_kind != "plus" else orc.plus_state(n)
+            mixer = ("grover", s)
+            E.set_mixer(eng.MIXER_GROVER, sub_kind=eng.INIT_DICKE if init_kind != "plus" else eng.INIT_PLUS, sub_k=k)
+        spec = orc.Spec(n, diag, mixer=mixer, init=init, trotter=trotter)
+        ang = rng.uniform(-np.pi, np.pi, size=p * (1 + nb))
+        ang[0::(1 + nb)] *= 0.3 / max(1.0, np.abs(diag).max() / 10)
+        out = E.energy(ang)
+        e, e2, mn, mx = orc.energy(spec, ang)
+        tol = TOL[dtype]
+        ref_scale = max(abs(e), 1e-2 * scale)
+        assert abs(out[0] - e) < tol * ref_scale, (trial, n, dtype, kind, init_kind, mixer_kind, p, out, e)
+        assert abs(out[1] - e2) < 2 * tol * max(abs(e2), 1e-2 * scale * scale), (trial, out, e2)
+        assert abs(out[4] - 1.0) < (2e-4 if dtype == "complex64" else 1e-10), (trial, out)
+        if dtype == "complex128":
+            assert abs(out[2] - mn) < 1e-9 * scale and abs(out[3] - mx) < 1e-9 * scale, (trial, out, mn, mx)
+        E.close()
+        checked += 1
+    assert checked == 60
