@@ -58,6 +58,13 @@ double qaoa_get_counter(qaoa_engine_t* h, const char* key); /* "launches", "byte
 int qaoa_set_cost_maxkcut(qaoa_engine_t* h, int n_nodes, int n_edges, const int32_t* u,
                           const int32_t* v, const double* w, int bits_per_node, const uint8_t* lut,
                           int fixed_node, int fixed_colour);
+/* Same cost, but the phase separator takes ONE GAMMA PER TERM: edge e belongs to term term_of_edge[e]
+ * (MaxCutFree: one term per edge, qaoa/problems/maxcut_free_problem.py:31-99; MaxCutOrbit: one per edge orbit,
+ * qaoa/problems/maxcut_orbit_problem.py:51-181) and layer d multiplies by exp(i sum_k gamma_{d,k} term_k(x)).
+ * Angle layout per layer: n_terms gammas, then the betas.  Registers that fit one CTA only (n <= 14 / 13). */
+int qaoa_set_cost_maxkcut_terms(qaoa_engine_t* h, int n_nodes, int n_edges, const int32_t* u, const int32_t* v,
+                                const double* w, const int32_t* term_of_edge, int n_terms, int bits_per_node,
+                                const uint8_t* lut, int fixed_node, int fixed_colour);
 /* cost(x) = -(x^T Q x + c^T x + b)  (qaoa/problems/qubo_problem.py:101-108); Q row-major n*n. */
 int qaoa_set_cost_qubo(qaoa_engine_t* h, int n, const double* Q, const double* c, double b);
 /* Escape hatch for an arbitrary Problem.cost: host array of 2^n doubles. */

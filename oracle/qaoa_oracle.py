@@ -365,8 +365,12 @@ class Spec:
     n_init is always 0 here (Plus / Dicke / StateVector carry no parameters).
     """
 
-    def __init__(self, n, diag, mixer=("x",), init=None, trotter=1):
+    def __init__(self, n, diag, mixer=("x",), init=None, trotter=1, terms=None):
+        """terms: optional list of K diagonals with sum(terms) == diag; the phase separator then takes one
+        gamma per term, exp(i sum_k gamma_k terms_k) (MaxCutFree: one term per edge, maxcut_free_problem.py:31-99;
+        MaxCutOrbit: one per edge orbit, maxcut_orbit_problem.py:51-181)."""
         self.n = n
+        self.terms = None if terms is None else [np.asarray(t, dtype=np.float64) for t in terms]
         self.diag = np.asarray(diag, dtype=np.float64)
         self.mixer = mixer
         self.init = plus_state(n) if init is None else np.asarray(init, dtype=np.complex128)
@@ -374,7 +378,7 @@ class Spec:
 
     @property
     def n_gamma(self):
-        return 1
+        return 1 if self.terms is None else len(self.terms)
 
     @property
     def n_beta(self):
@@ -390,9 +394,12 @@ def evolve(spec, angles, dtype=np.complex128):
     p = angles.size // per
     psi = spec.init.astype(np.complex128).copy()
     for d in range(p):
-        gamma = angles[d * per]
-        betas = angles[d * per + 1:(d + 1) * per]
-        psi *= np.exp(1j * gamma * spec.diag)  # validation.py:43 sign
+        gammas = angles[d * per:d * per + spec.n_gamma]
+        betas = angles[d * per + spec.n_gamma:(d + 1) * per]
+        if spec.terms is None:
+            psi *= np.exp(1j * gammas[0] * spec.diag)  # validation.py:43 sign
+        else:
+            psi *= np.exp(1j * sum(g * t for g, t in zip(gammas, spec.terms)))
         for _ in range(spec.trotter):
             bt = betas / spec.trotter  # qaoa.py:494-503
             kind = spec.mixer[0]
@@ -518,3 +525,48 @@ def exact_cvar(diag, prob, alpha):
     cum = np.cumsum(p)
     take = np.clip(alpha - (cum - p), 0.0, p)
     return float(take @ c) / alpha
+
+
+def edge_terms(edges, num_V, term_of_edge, n_terms, fix_one_node=False):
+    """Per-term MaxCut diagonals: terms[k](x) = sum over edges e with term_of_edge[e] == k of w_e [x_u != x_v]
+    (the fixed node, if any, is node num_V-1 with bit 0).  maxcut_free_problem.py:66-73 / maxcut_orbit_problem.py:139-144."""
+    n = num_V - (1 if fix_one_node else 0)
+    x = np.arange(1 << n, dtype=np.int64)
+    terms = [np.zeros(1 << n) for _ in range(n_terms)]
+    for (u, v, w), k in zip(edges, term_of_edge):
+        bu = (x >> u) & 1 if u < n else 0
+        bv = (x >> v) & 1 if v < n else 0
+        terms[k] += w * (bu ^ bv)
+    return terms
+
+
+def edge_orbits(G):
+    """Orbits of the edges of G (in G.edges() order) under Aut(G), ordered by their first edge
+    (maxcut_orbit_problem.py:61-107).  Returns term_of_edge."""
+    from networkx.algorithms.isomorphism import GraphMatcher
+    edges = list(G.edges())
+    idx = {}
+    for i, (u, v) in enumerate(edges):
+        idx[(u, v)] = i
+        idx[(v, u)] = i
+    parent = list(range(len(edges)))
+
+    def find(a):
+        while parent[a] != a:
+            parent[a] = parent[parent[a]]
+            a = parent[a]
+        return a
+
+    for auto in GraphMatcher(G, G).isomorphisms_iter():
+        for i, (u, v) in enumerate(edges):
+            j = idx.get((auto[u], auto[v]))
+            if j is not None:
+                ri, rj = find(i), find(j)
+                if ri != rj:
+                    parent[ri] = rj
+        if len({find(i) for i in range(len(edges))}) == 1:
+            break
+    order = {}
+    for i in range(len(edges)):
+        order.setdefault(find(i), len(order))
+    return [order[find(i)] for i in range(len(edges))]

@@ -96,6 +96,10 @@ struct Engine {
   void* diag = nullptr;
   std::map<std::pair<int, int>, void*> streams;  // (shape, frame) -> permuted diagonal
 
+  // per-term gammas (MaxCutFree / MaxCutOrbit): n_gamma term diagonals, single-CTA path only
+  int n_gamma = 1;
+  double* d_terms = nullptr;
+
   // mixer / init
   int mixer = MIXER_X;
   std::vector<int> pairs;
@@ -952,6 +956,8 @@ void run_small_chunk(Engine* h, int p, const double* angles, int n_angles, int B
   SmallDesc D;
   D.n = h->n; D.p = p; D.mixer = h->mixer;
   D.n_beta = h->mixer == MIXER_XMULTI ? h->n : 1;
+  D.n_gamma = h->n_gamma;
+  D.terms = h->d_terms;
   D.n_pairs = (int)h->pairs.size() / 2;
   D.trotter = h->trotter;
   D.write_state = h->keep_state;
@@ -1096,11 +1102,14 @@ void check_ready(Engine* h, int p, int n_angles) {
   if (h->dinfo.kind == DIAG_NONE) fail("no cost function set");
   if (p < 1) fail("depth p must be >= 1");
   const int nb = h->mixer == MIXER_XMULTI ? h->n : 1;
-  if (n_angles != p * (1 + nb)) {
-    char b[160];
-    snprintf(b, sizeof(b), "expected %d angles for p=%d (n_beta=%d), got %d", p * (1 + nb), p, nb, n_angles);
+  if (n_angles != p * (h->n_gamma + nb)) {
+    char b[200];
+    snprintf(b, sizeof(b), "expected %d angles for p=%d (n_gamma=%d, n_beta=%d), got %d", p * (h->n_gamma + nb), p,
+             h->n_gamma, nb, n_angles);
     fail(b);
   }
+  if (h->n_gamma > 1 && h->n > h->small_max())
+    fail("per-term gammas (MaxCutFree / MaxCutOrbit) are supported on registers that fit one CTA only");
   if ((h->mixer == MIXER_XY) && h->pairs.empty()) fail("XY mixer without pairs");
 }
 
@@ -1174,6 +1183,8 @@ void energy_batch_body(Engine* h, int p, const double* angles, int n_angles, int
 
 void set_diag_common(Engine* h, int kind, double c0, double delta) {
   close_peers(h, 1);
+  if (h->d_terms) { cudaFree(h->d_terms); h->d_terms = nullptr; }
+  h->n_gamma = 1;
   if (h->diag) { cudaFree(h->diag); h->diag = nullptr; }
   free_streams(h);
   invalidate(h);
@@ -1298,7 +1309,7 @@ int qaoa_destroy(qaoa_engine_t* h) {
   close_peers(h, 0);
   close_peers(h, 1);
   free_streams(h);
-  void* bufs[] = {h->state, h->diag, h->d_pairs, h->init_vec, h->sub_vec, h->d_params, h->d_partials, h->d_out,
+  void* bufs[] = {h->state, h->diag, h->d_terms, h->d_pairs, h->init_vec, h->sub_vec, h->d_params, h->d_partials, h->d_out,
                   h->d_tables, h->d_gamsig, h->d_coefdot, h->d_angles};
   for (void* b : bufs) if (b) cudaFree(b);
   if (h->h_params) cudaFreeHost(h->h_params);
@@ -1389,6 +1400,54 @@ int qaoa_set_cost_maxkcut(qaoa_engine_t* h, int n_nodes, int n_edges, const int3
   CUDA_OK(cudaStreamSynchronize(h->stream));
   h->launches += 1;
   cudaFree(du); cudaFree(dv); cudaFree(dwi); cudaFree(dw);
+  API_END(h)
+}
+
+int qaoa_set_cost_maxkcut_terms(qaoa_engine_t* h, int n_nodes, int n_edges, const int32_t* u, const int32_t* v,
+                                const double* w, const int32_t* term_of_edge, int n_terms, int bits_per_node,
+                                const uint8_t* lut, int fixed_node, int fixed_colour) {
+  if (!h) return 1;
+  // the total cost first (diagonal, bounds, representation), then one double-precision diagonal per term
+  int rc = qaoa_set_cost_maxkcut(h, n_nodes, n_edges, u, v, w, bits_per_node, lut, fixed_node, fixed_colour);
+  if (rc) return rc;
+  API_BEGIN(h)
+  if (h->world > 1) fail("sharded engine: per-term gammas are not supported");
+  if (n_terms < 1 || !term_of_edge) fail("term_of_edge is null / n_terms < 1");
+  if (h->n > (h->dtype == QAOA_DTYPE_C64 ? 14 : 13)) fail("per-term gammas are supported on registers that fit one CTA only");
+  for (int e = 0; e < n_edges; e++) if (term_of_edge[e] < 0 || term_of_edge[e] >= n_terms) fail("term index out of range");
+  if (n_terms > 1) {
+  CUDA_OK(cudaMalloc((void**)&h->d_terms, (size_t)n_terms * h->N * sizeof(double)));
+  MaxKCutDev D;
+  memset(&D, 0, sizeof(D));
+  D.bits = bits_per_node; D.n_free = n_nodes - (fixed_node ? 1 : 0); D.fixed_colour = fixed_colour;
+  for (int i = 0; i < (1 << bits_per_node); i++) D.lut[i] = lut[i];
+  int *du, *dv, *dwi; double* dw;
+  CUDA_OK(cudaMalloc((void**)&du, std::max(n_edges, 1) * 4));
+  CUDA_OK(cudaMalloc((void**)&dv, std::max(n_edges, 1) * 4));
+  CUDA_OK(cudaMalloc((void**)&dwi, std::max(n_edges, 1) * 4));
+  CUDA_OK(cudaMalloc((void**)&dw, std::max(n_edges, 1) * 8));
+  DiagInfo gi{DIAG_F64, 0.0, 1.0};
+  for (int k = 0; k < n_terms; k++) {
+    std::vector<int> su, sv, swi;
+    std::vector<double> sw;
+    for (int e = 0; e < n_edges; e++) if (term_of_edge[e] == k) { su.push_back(u[e]); sv.push_back(v[e]); sw.push_back(w[e]); swi.push_back(0); }
+    const int ne = (int)su.size();
+    if (ne) {
+      CUDA_OK(cudaMemcpy(du, su.data(), ne * 4, cudaMemcpyHostToDevice));
+      CUDA_OK(cudaMemcpy(dv, sv.data(), ne * 4, cudaMemcpyHostToDevice));
+      CUDA_OK(cudaMemcpy(dwi, swi.data(), ne * 4, cudaMemcpyHostToDevice));
+      CUDA_OK(cudaMemcpy(dw, sw.data(), ne * 8, cudaMemcpyHostToDevice));
+    }
+    D.n_edges = ne; D.eu = du; D.ev = dv; D.ewi = dwi; D.ew = dw;
+    gen_maxkcut_kernel<<<grid_for(h->N, 256), 256, 0, h->stream>>>(D, h->N, h->x0, gi, h->d_terms + (size_t)k * h->N);
+    CUDA_OK(cudaGetLastError());
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    h->launches += 1;
+  }
+  cudaFree(du); cudaFree(dv); cudaFree(dwi); cudaFree(dw);
+  h->n_gamma = n_terms;
+  invalidate(h);
+  }
   API_END(h)
 }
 

@@ -224,6 +224,8 @@ struct SmallDesc {
   int p;
   int mixer;       // MixerKind
   int n_beta;      // parameters per layer for the mixer (1 or n)
+  int n_gamma;     // parameters per layer of the phase separator: 1, or the number of cost terms
+  const double* terms;   // n_gamma > 1: term diagonals [n_gamma][2^n]; the phase is exp(i sum_k gamma_k terms_k)
   int n_pairs;     // XY
   int trotter;     // XY only (X and Grover are invariant under trotterisation)
   int write_state; // store the final S-frame state to global memory
@@ -244,7 +246,7 @@ small_fused_kernel(SmallDesc D, const int* __restrict__ pairs, const double* __r
   const size_t N = (size_t)1 << n;
   const int tid = threadIdx.x, nt = blockDim.x;
   const double* ang = angles + (size_t)blockIdx.x * angles_stride;
-  const int per = 1 + D.n_beta;
+  const int ng = D.n_gamma, per = ng + D.n_beta;
 
   for (size_t x = tid; x < N; x += nt) {
     real re, im;
@@ -256,10 +258,17 @@ small_fused_kernel(SmallDesc D, const int* __restrict__ pairs, const double* __r
 
   for (int d = 0; d < D.p; d++) {
     const double gamma = ang[d * per];
-    // phase separator  e^{+i gamma cost(x)}   (sign: qaoa/utils/validation.py:43)
+    // phase separator  e^{+i gamma cost(x)}   (sign: qaoa/utils/validation.py:43); with several cost terms
+    // (one gamma per edge / edge orbit, maxcut_free_problem.py:66-73, maxcut_orbit_problem.py:139-144)
+    // the angle is sum_k gamma_k term_k(x)
     for (size_t x = tid; x < N; x += nt) {
       double s, c;
-      sincos(gamma * diag_decode(info, diag, x), &s, &c);
+      double theta;
+      if (ng > 1) {
+        theta = 0.0;
+        for (int k = 0; k < ng; k++) theta += ang[d * per + k] * D.terms[(size_t)k * N + x];
+      } else theta = gamma * diag_decode(info, diag, x);
+      sincos(theta, &s, &c);
       real re = ps[2 * x], im = ps[2 * x + 1];
       ps[2 * x] = re * (real)c - im * (real)s;
       ps[2 * x + 1] = re * (real)s + im * (real)c;
@@ -267,7 +276,7 @@ small_fused_kernel(SmallDesc D, const int* __restrict__ pairs, const double* __r
     __syncthreads();
     if (D.mixer == MIXER_X || D.mixer == MIXER_XMULTI) {
       for (int q = 0; q < n; q++) {
-        const double beta = ang[d * per + 1 + (D.n_beta == 1 ? 0 : q)];
+        const double beta = ang[d * per + ng + (D.n_beta == 1 ? 0 : q)];
         double sd, cd;
         sincos(beta, &sd, &cd);
         const real c = (real)cd, s = (real)sd;
@@ -285,7 +294,7 @@ small_fused_kernel(SmallDesc D, const int* __restrict__ pairs, const double* __r
       }
     } else if (D.mixer == MIXER_XY) {
       // XXPlusYYGate(0.5 beta): rotation by beta/4 on span{|01>,|10>} (xy_mixer.py:54-56), in order
-      const double beta = ang[d * per + 1] / D.trotter;
+      const double beta = ang[d * per + ng] / D.trotter;
       double sd, cd;
       sincos(0.25 * beta, &sd, &cd);
       const real c = (real)cd, s = (real)sd;
@@ -308,7 +317,7 @@ small_fused_kernel(SmallDesc D, const int* __restrict__ pairs, const double* __r
         }
       }
     } else {  // MIXER_GROVER:  psi += (e^{-i beta} - 1) <s|psi> s   (grover_mixer.py:43-82)
-      const double beta = ang[d * per + 1];
+      const double beta = ang[d * per + ng];
       double v[5] = {0, 0, 0, 1e300, -1e300};
       for (size_t x = tid; x < N; x += nt) {
         real sr, si;

@@ -60,6 +60,11 @@ def load_library():
             [H, ctypes.c_int, ctypes.c_int, _c_int32_p, _c_int32_p, _c_double_p, ctypes.c_int, _c_uint8_p,
              ctypes.c_int, ctypes.c_int],
         ),
+        "qaoa_set_cost_maxkcut_terms": (
+            ctypes.c_int,
+            [H, ctypes.c_int, ctypes.c_int, _c_int32_p, _c_int32_p, _c_double_p, _c_int32_p, ctypes.c_int, ctypes.c_int,
+             _c_uint8_p, ctypes.c_int, ctypes.c_int],
+        ),
         "qaoa_set_cost_qubo": (ctypes.c_int, [H, ctypes.c_int, _c_double_p, _c_double_p, ctypes.c_double]),
         "qaoa_set_cost_diagonal": (ctypes.c_int, [H, _c_double_p]),
         "qaoa_read_cost_diagonal": (ctypes.c_int, [H, ctypes.c_size_t, ctypes.c_size_t, _c_double_p]),
@@ -118,6 +123,7 @@ class Engine:
         self.dtype = {"complex64": DTYPE_C64, "complex128": DTYPE_C128, DTYPE_C64: DTYPE_C64,
                       DTYPE_C128: DTYPE_C128}[dtype]
         self.n_beta = 1
+        self.n_gamma = 1
         self.rank, self.world = int(rank), int(world)
         rc = self._lib.qaoa_create_sharded(self.n_qubits, self.dtype, int(device), self.rank, self.world,
                                            ctypes.byref(self._h))
@@ -149,6 +155,7 @@ class Engine:
 
     # -- cost -------------------------------------------------------------
     def set_cost_maxkcut(self, n_nodes, edges, bits_per_node, lut, fixed_node=False, fixed_colour=0):
+        self.n_gamma = 1
         u = np.ascontiguousarray([e[0] for e in edges], dtype=np.int32)
         v = np.ascontiguousarray([e[1] for e in edges], dtype=np.int32)
         w = np.ascontiguousarray([e[2] for e in edges], dtype=np.float64)
@@ -158,13 +165,30 @@ class Engine:
             self._h, int(n_nodes), len(edges), u.ctypes.data_as(_c_int32_p), v.ctypes.data_as(_c_int32_p),
             _dptr(w), int(bits_per_node), lut.ctypes.data_as(_c_uint8_p), int(bool(fixed_node)), int(fixed_colour)))
 
+    def set_cost_maxkcut_terms(self, n_nodes, edges, term_of_edge, n_terms, bits_per_node, lut, fixed_node=False,
+                               fixed_colour=0):
+        """Same cost as set_cost_maxkcut, one gamma per term (MaxCutFree / MaxCutOrbit); n <= 14 / 13 only."""
+        u = np.ascontiguousarray([e[0] for e in edges], dtype=np.int32)
+        v = np.ascontiguousarray([e[1] for e in edges], dtype=np.int32)
+        w = np.ascontiguousarray([e[2] for e in edges], dtype=np.float64)
+        t = np.ascontiguousarray(term_of_edge, dtype=np.int32)
+        lut = np.ascontiguousarray(lut, dtype=np.uint8)
+        assert t.size == len(edges) and lut.size == 1 << bits_per_node
+        self._check(self._lib.qaoa_set_cost_maxkcut_terms(
+            self._h, int(n_nodes), len(edges), u.ctypes.data_as(_c_int32_p), v.ctypes.data_as(_c_int32_p), _dptr(w),
+            t.ctypes.data_as(_c_int32_p), int(n_terms), int(bits_per_node), lut.ctypes.data_as(_c_uint8_p),
+            int(bool(fixed_node)), int(fixed_colour)))
+        self.n_gamma = int(n_terms)
+
     def set_cost_qubo(self, Q, c=None, b=0.0):
+        self.n_gamma = 1
         Q = np.ascontiguousarray(Q, dtype=np.float64)
         n = Q.shape[0]
         c = np.zeros(n) if c is None else np.ascontiguousarray(c, dtype=np.float64)
         self._check(self._lib.qaoa_set_cost_qubo(self._h, n, _dptr(Q), _dptr(c), float(b)))
 
     def set_cost_diagonal(self, diag):
+        self.n_gamma = 1
         diag = np.ascontiguousarray(diag, dtype=np.float64)
         assert diag.size == 1 << self.n_qubits
         self._check(self._lib.qaoa_set_cost_diagonal(self._h, _dptr(diag)))
@@ -206,7 +230,7 @@ class Engine:
     def energy(self, angles):
         """Returns (E[cost], E[cost^2], min, max, norm) for one flat angle vector."""
         angles = np.ascontiguousarray(angles, dtype=np.float64).reshape(-1)
-        per = 1 + self.n_beta
+        per = self.n_gamma + self.n_beta
         if angles.size == 0 or angles.size % per:
             raise ValueError("angle vector length %d is not a multiple of %d" % (angles.size, per))
         out = np.empty(5, dtype=np.float64)
@@ -218,7 +242,7 @@ class Engine:
         angles = np.ascontiguousarray(angles, dtype=np.float64)
         assert angles.ndim == 2
         B, na = angles.shape
-        per = 1 + self.n_beta
+        per = self.n_gamma + self.n_beta
         if na == 0 or na % per:
             raise ValueError("angle vector length %d is not a multiple of %d" % (na, per))
         out = np.empty((B, 5), dtype=np.float64)
@@ -228,7 +252,7 @@ class Engine:
     def energy_batch_resident(self, angles):
         angles = np.ascontiguousarray(angles, dtype=np.float64)
         B, na = angles.shape
-        per = 1 + self.n_beta
+        per = self.n_gamma + self.n_beta
         self._check(self._lib.qaoa_energy_batch_resident(self._h, na // per, _dptr(angles), na, B))
 
     def fetch_results(self, B):
@@ -244,7 +268,7 @@ class Engine:
     # -- sampling / cost distribution of the final state -------------------------------------------------
     def _angles(self, angles):
         angles = np.ascontiguousarray(angles, dtype=np.float64).reshape(-1)
-        per = 1 + self.n_beta
+        per = self.n_gamma + self.n_beta
         if angles.size == 0 or angles.size % per:
             raise ValueError("angle vector length %d is not a multiple of %d" % (angles.size, per))
         return angles, angles.size // per
@@ -291,7 +315,7 @@ class Engine:
 
     def shard_begin(self, angles):
         angles = np.ascontiguousarray(angles, dtype=np.float64).reshape(-1)
-        per = 1 + self.n_beta
+        per = self.n_gamma + self.n_beta
         if angles.size == 0 or angles.size % per:
             raise ValueError("angle vector length %d is not a multiple of %d" % (angles.size, per))
         n_passes = ctypes.c_int()

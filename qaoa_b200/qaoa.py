@@ -222,8 +222,8 @@ class QAOA:
         if self._engine is None:
             from qaoa_b200.engine import Engine
 
-            if self.problem.get_num_parameters() != 1:
-                _reject("problems with more than one gamma per layer")
+            if self.problem.get_num_parameters() != 1 and not hasattr(self.problem, "term_of_edge"):
+                _reject("problems with more than one gamma per layer (other than MaxCutFree / MaxCutOrbit)")
             if self.initialstate.get_num_parameters() != 0:
                 _reject("parameterised initial states")
             if getattr(self.backend, "sharded", False):

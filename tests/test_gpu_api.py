@@ -103,3 +103,31 @@ def test_hist_and_cvar_on_the_device():
     assert sum(h.values()) == 2048 and all(len(k) == 8 for k in h)
     best = max(h, key=h.get)
     assert dev2.problem.cost(best) >= 8          # README graph: max cut 10, <cost> ~ 8 at these angles
+
+
+@pytest.mark.parametrize("dtype,tol", [("complex128", 1e-9), ("complex64", 1e-4)])
+def test_per_term_gammas_free_and_orbit(dtype, tol):
+    """MaxCutFree + XMultiAngle and MaxCutOrbit + XOrbit on the device vs the oracle stand-in (per-term phase
+    separator of the single-CTA kernel), n = 5 (house) and n = 10 (Petersen: one edge orbit, one node orbit)."""
+    house = nx.Graph([(0, 1), (1, 2), (2, 3), (3, 0), (2, 4), (3, 4)])
+    rng = np.random.default_rng(4)
+    for G, mk_p, mk_m in ((house, problems.MaxCutFree, lambda g: mixers.XMultiAngle()),
+                          (house, problems.MaxCutOrbit, lambda g: mixers.XOrbit(g)),
+                          (nx.petersen_graph(), problems.MaxCutOrbit, lambda g: mixers.XOrbit(g)),
+                          (nx.random_regular_graph(3, 12, seed=5), problems.MaxCutFree, lambda g: mixers.X())):
+        dev, ref = both(lambda: mk_p(G), lambda: mk_m(G), initialstates.Plus, dtype)
+        dev.createParameterizedCircuit(2)
+        ref.createParameterizedCircuit(2)
+        per = dev.n_gamma + dev.n_beta
+        assert per == ref.n_gamma + ref.n_beta
+        rows = rng.uniform(-1.5, 1.5, size=(3, 2 * per))
+        a = dev._evaluate(rows)
+        b = ref._evaluate(rows)
+        assert np.allclose(a[:, 0], b[:, 0], rtol=tol, atol=tol), (type(dev.problem).__name__, a[:, 0], b[:, 0])
+        assert np.allclose(a[:, 1], b[:, 1], rtol=2 * tol, atol=2 * tol)
+    # a register that does not fit one CTA is rejected, not mis-evaluated
+    big = QAOA(problem=problems.MaxCutFree(nx.random_regular_graph(3, 16, seed=1)), mixer=mixers.X(),
+               initialstate=initialstates.Plus(), dtype=dtype)
+    from qaoa_b200.engine import EngineError
+    with pytest.raises(EngineError):
+        big.sample_cost_landscape({"gamma": [0, 1, 2], "beta": [0, 1, 2]})

@@ -37,6 +37,11 @@ class OracleEngine:
             return np.asarray(lut)[(x >> (v * bits)) & ((1 << bits) - 1)]
         self.diag = sum(((col(u) != col(v)) * w for u, v, w in edges), np.zeros(x.shape))
 
+    def set_cost_maxkcut_terms(self, n_nodes, edges, term_of_edge, n_terms, bits, lut, fixed_node=False, fixed_colour=0):
+        self.set_cost_maxkcut(n_nodes, edges, bits, lut, fixed_node=fixed_node, fixed_colour=fixed_colour)
+        self.terms = orc.edge_terms(edges, n_nodes, term_of_edge, n_terms, fix_one_node=fixed_node) if n_terms > 1 else None
+        self.n_gamma = n_terms
+
     def set_cost_qubo(self, Q, c=None, b=0.0):
         self.diag = orc.qubo_diag(Q, np.zeros(Q.shape[0]) if c is None else c, b)
 
@@ -66,7 +71,8 @@ class OracleEngine:
             self.mixer = ("grover", s)
 
     def _prob(self, row):
-        spec = orc.Spec(self.n_qubits, self.diag, mixer=self.mixer, init=self.init, trotter=self.trotter)
+        spec = orc.Spec(self.n_qubits, self.diag, mixer=self.mixer, init=self.init, trotter=self.trotter,
+                        terms=getattr(self, "terms", None))
         pr = np.abs(orc.evolve(spec, np.asarray(row, dtype=float))) ** 2
         return pr / pr.sum()
 
@@ -81,7 +87,8 @@ class OracleEngine:
         return np.minimum(np.searchsorted(cum, u * cum[-1], side="right"), len(cum) - 1).astype(np.uint64)
 
     def energy_batch(self, rows):
-        spec = orc.Spec(self.n_qubits, self.diag, mixer=self.mixer, init=self.init, trotter=self.trotter)
+        spec = orc.Spec(self.n_qubits, self.diag, mixer=self.mixer, init=self.init, trotter=self.trotter,
+                        terms=getattr(self, "terms", None))
         out = np.empty((len(rows), 5))
         for i, r in enumerate(rows):
             self.calls += 1
@@ -336,3 +343,35 @@ def test_xorbit_mixer_shares_betas_within_node_orbits():
     assert got == pytest.approx(-orc.energy(spec, expanded)[0], rel=1e-12)
     # a cycle is vertex transitive: a single orbit, i.e. the plain X mixer
     assert mixers.XOrbit(nx.cycle_graph(6)).get_num_parameters() == 1
+
+
+def test_maxcut_free_and_orbit_per_term_gammas():
+    """MaxCutFree (one gamma per edge, maxcut_free_problem.py:31-99) + XMultiAngle and MaxCutOrbit (one per edge orbit,
+    maxcut_orbit_problem.py:51-181) + XOrbit: parameter counts, term assignment and the depth-2 optimisation of the
+    reference's own tests (unittests/test_multiangle_gridsearch.py:138-154, test_qaoa_core.py 'Orbit depth-2')."""
+    house = nx.Graph([(0, 1), (1, 2), (2, 3), (3, 0), (2, 4), (3, 4)])      # the reference's 5-node "house"
+    free = problems.MaxCutFree(house)
+    assert free.get_num_parameters() == 6 and free.term_of_edge() == list(range(6))
+    q, fake = make(free, mixer=mixers.XMultiAngle(), optimizer=[__import__("qaoa_b200").utils.COBYLA, {"maxiter": 40}])
+    assert fake.n_gamma == 6 and len(fake.terms) == 6 and np.allclose(sum(fake.terms), fake.diag)
+    q.optimize(depth=2, angles={"gamma": [0, np.pi, 4], "beta": [0, np.pi, 4]})
+    assert len(q.get_angles(2)) == 2 * (6 + 5)
+    assert q.get_Exp(2) <= q.get_Exp(1) + 1e-9 <= q.Exp_sampled_p1.min() + 2e-9
+    # every recorded iterate carries the oracle's energy for those angles (per-term layout)
+    spec = orc.Spec(5, fake.diag, mixer=("xmulti",), terms=fake.terms)
+    r = q.optimization_results[2]
+    assert np.allclose(r.Exp, [-orc.energy(spec, a)[0] for a in r.angles], rtol=1e-12)
+
+    orbit = problems.MaxCutOrbit(house)
+    t = orbit.term_of_edge()
+    assert t == orc.edge_orbits(orbit.graph_handler.G) and orbit.get_num_parameters() == len(set(t)) < 6
+    for k, group in enumerate(orbit.edge_orbits):
+        assert all(orbit.edge_to_orbit[e] == k for e in group)
+    q2, fake2 = make(orbit, mixer=mixers.XOrbit(house), optimizer=[__import__("qaoa_b200").utils.COBYLA, {"maxiter": 30}])
+    q2.optimize(depth=2, angles={"gamma": [0, np.pi, 4], "beta": [0, np.pi, 4]})
+    assert len(q2.get_angles(2)) == 2 * (orbit.get_num_parameters() + q2.mixer.get_num_parameters())
+    # equal gammas on every term reproduce the plain MaxCut phase separator
+    plain, fp = make(problems.MaxCut(house))
+    e_plain = fp.energy_batch(np.array([[0.37, 0.21]]))[0, 0]
+    e_terms = fake.energy_batch(np.array([[0.37] * 6 + [0.21] * 5]))[0, 0]
+    assert e_terms == pytest.approx(e_plain, rel=1e-12)
