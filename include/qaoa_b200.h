@@ -36,6 +36,8 @@ typedef struct qaoa_engine qaoa_engine_t;
 #define QAOA_INIT_PLUS 0         /* qaoa/initialstates/plus_initialstate.py:19-25        */
 #define QAOA_INIT_DICKE 1        /* qaoa/initialstates/dicke_initialstate.py:23-56       */
 #define QAOA_INIT_STATEVECTOR 2  /* qaoa/initialstates/statevector_initialstate.py:19-33 */
+#define QAOA_INIT_PLUS_PHASES 3  /* qaoa/initialstates/plus_parameterized_initialstate.py:25-64: k phases lead the
+                                    angle vector (n_init = k); registers that fit one CTA only */
 
 /* Creates an engine for n_qubits on CUDA device `device`.  Replaces the construction of the
  * transpiled parameterised circuit + AerSimulator instance (qaoa/qaoa.py:204, 418-520). */
@@ -82,8 +84,9 @@ int qaoa_set_mixer(qaoa_engine_t* h, int kind, const int32_t* pairs, int n_pairs
 int qaoa_set_initial(qaoa_engine_t* h, int kind, int k, const double* vec);
 
 /* One energy evaluation (replaces QAOA.loss / _eval_cost, qaoa/qaoa.py:885-935, 1029-1066).
- * angles: the reference's flat layout [(gamma_d, beta_d[0..n_beta-1]) for d in 0..p-1]
- * (qaoa/qaoa.py:937-990; n_init = 0 for every supported initial state).
+ * angles: the reference's flat layout [init_0..init_{n_init-1}, (gamma_d[0..n_gamma-1], beta_d[0..n_beta-1]) for d < p]
+ * (qaoa/qaoa.py:937-990; n_init = 0 except for QAOA_INIT_PLUS_PHASES, n_gamma = 1 except after
+ * qaoa_set_cost_maxkcut_terms).
  * out[5] = { E[cost], E[cost^2], min cost over support, max cost over support, norm }. */
 int qaoa_energy(qaoa_engine_t* h, int p, const double* angles, int n_angles, double* out);
 /* B evaluations in one call (replaces the batch branch of sample_cost_landscape,

@@ -570,3 +570,16 @@ def edge_orbits(G):
     for i in range(len(edges)):
         order.setdefault(find(i), len(order))
     return [order[find(i)] for i in range(len(edges))]
+
+
+def phased_plus(psi0, phases):
+    """RZ(phi_q) = diag(e^{-i phi/2}, e^{+i phi/2}) on qubit q for q < len(phases), applied to psi0
+    (plus_parameterized_initialstate.py:55-64: H on every qubit, then rz(param_i, q[i]))."""
+    phases = np.asarray(phases, dtype=np.float64)
+    if phases.size == 0:
+        return psi0
+    x = np.arange(psi0.size, dtype=np.int64)
+    theta = np.zeros(psi0.size)
+    for q, phi in enumerate(phases):
+        theta += phi * (((x >> q) & 1) - 0.5)
+    return np.asarray(psi0, dtype=np.complex128) * np.exp(1j * theta)

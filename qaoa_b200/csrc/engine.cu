@@ -99,6 +99,7 @@ struct Engine {
   // per-term gammas (MaxCutFree / MaxCutOrbit): n_gamma term diagonals, single-CTA path only
   int n_gamma = 1;
   double* d_terms = nullptr;
+  int n_init = 0;            // PlusParameterized: leading phase parameters of the angle vector (single-CTA path only)
 
   // mixer / init
   int mixer = MIXER_X;
@@ -957,6 +958,7 @@ void run_small_chunk(Engine* h, int p, const double* angles, int n_angles, int B
   D.n = h->n; D.p = p; D.mixer = h->mixer;
   D.n_beta = h->mixer == MIXER_XMULTI ? h->n : 1;
   D.n_gamma = h->n_gamma;
+  D.n_init = h->n_init;
   D.terms = h->d_terms;
   D.n_pairs = (int)h->pairs.size() / 2;
   D.trotter = h->trotter;
@@ -1102,12 +1104,14 @@ void check_ready(Engine* h, int p, int n_angles) {
   if (h->dinfo.kind == DIAG_NONE) fail("no cost function set");
   if (p < 1) fail("depth p must be >= 1");
   const int nb = h->mixer == MIXER_XMULTI ? h->n : 1;
-  if (n_angles != p * (h->n_gamma + nb)) {
+  if (n_angles != h->n_init + p * (h->n_gamma + nb)) {
     char b[200];
-    snprintf(b, sizeof(b), "expected %d angles for p=%d (n_gamma=%d, n_beta=%d), got %d", p * (h->n_gamma + nb), p,
-             h->n_gamma, nb, n_angles);
+    snprintf(b, sizeof(b), "expected %d angles for p=%d (n_init=%d, n_gamma=%d, n_beta=%d), got %d",
+             h->n_init + p * (h->n_gamma + nb), p, h->n_init, h->n_gamma, nb, n_angles);
     fail(b);
   }
+  if (h->n_init > 0 && h->n > h->small_max())
+    fail("parameterised initial states (PlusParameterized) are supported on registers that fit one CTA only");
   if (h->n_gamma > 1 && h->n > h->small_max())
     fail("per-term gammas (MaxCutFree / MaxCutOrbit) are supported on registers that fit one CTA only");
   if ((h->mixer == MIXER_XY) && h->pairs.empty()) fail("XY mixer without pairs");
@@ -1579,8 +1583,15 @@ int qaoa_set_mixer(qaoa_engine_t* h, int kind, const int32_t* pairs, int n_pairs
 
 int qaoa_set_initial(qaoa_engine_t* h, int kind, int k, const double* vec) {
   API_BEGIN(h)
-  if (h->world > 1 && kind == INIT_STATEVECTOR) fail("sharded engine: StateVector initial states are not supported");
+  if (h->world > 1 && (kind == INIT_STATEVECTOR || kind == 3)) fail("sharded engine: this initial state is not supported");
   invalidate(h);
+  h->n_init = 0;
+  if (kind == 3) {   // QAOA_INIT_PLUS_PHASES: |+>^n followed by RZ(phi_q) on the first k qubits, phi = leading angles
+    if (k < 1 || k > h->n) fail("number of initial-state phases out of range");
+    if (h->n > (h->dtype == QAOA_DTYPE_C64 ? 14 : 13)) fail("PlusParameterized is supported on registers that fit one CTA only");
+    h->init = make_gen(h, INIT_PLUS, 0, nullptr, &h->init_vec);
+    h->n_init = k;
+  } else
   h->init = make_gen(h, kind, k, vec, &h->init_vec);
   API_END(h)
 }

@@ -224,6 +224,7 @@ struct SmallDesc {
   int p;
   int mixer;       // MixerKind
   int n_beta;      // parameters per layer for the mixer (1 or n)
+  int n_init;      // leading initial-state parameters of the angle vector (PlusParameterized phases)
   int n_gamma;     // parameters per layer of the phase separator: 1, or the number of cost terms
   const double* terms;   // n_gamma > 1: term diagonals [n_gamma][2^n]; the phase is exp(i sum_k gamma_k terms_k)
   int n_pairs;     // XY
@@ -245,12 +246,24 @@ small_fused_kernel(SmallDesc D, const int* __restrict__ pairs, const double* __r
   const int n = D.n;
   const size_t N = (size_t)1 << n;
   const int tid = threadIdx.x, nt = blockDim.x;
-  const double* ang = angles + (size_t)blockIdx.x * angles_stride;
+  const double* ang0 = angles + (size_t)blockIdx.x * angles_stride;
+  const double* ang = ang0 + D.n_init;   // flat layout: initial-state parameters first (qaoa/qaoa.py:937-990)
   const int ng = D.n_gamma, per = ng + D.n_beta;
 
   for (size_t x = tid; x < N; x += nt) {
     real re, im;
     gen_amp<real>(D.init, x, re, im);
+    if (D.n_init > 0) {
+      // PlusParameterized (plus_parameterized_initialstate.py:44-64): RZ(phi_q) = diag(e^{-i phi/2}, e^{+i phi/2})
+      // on qubit q < n_init after the Hadamards
+      double theta = 0.0;
+      for (int q = 0; q < D.n_init; q++) theta += ang0[q] * (((x >> q) & 1) ? 0.5 : -0.5);
+      double sn, cs;
+      sincos(theta, &sn, &cs);
+      const real r2 = re * (real)cs - im * (real)sn;
+      im = re * (real)sn + im * (real)cs;
+      re = r2;
+    }
     ps[2 * x] = re;
     ps[2 * x + 1] = im;
   }

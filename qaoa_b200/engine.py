@@ -20,7 +20,7 @@ _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libqaoa_b2
 DTYPE_C64 = 0
 DTYPE_C128 = 1
 MIXER_X, MIXER_XMULTI, MIXER_XY, MIXER_GROVER = 0, 1, 2, 3
-INIT_PLUS, INIT_DICKE, INIT_STATEVECTOR = 0, 1, 2
+INIT_PLUS, INIT_DICKE, INIT_STATEVECTOR, INIT_PLUS_PHASES = 0, 1, 2, 3
 
 _c_double_p = ctypes.POINTER(ctypes.c_double)
 _c_int32_p = ctypes.POINTER(ctypes.c_int32)
@@ -124,6 +124,7 @@ class Engine:
                       DTYPE_C128: DTYPE_C128}[dtype]
         self.n_beta = 1
         self.n_gamma = 1
+        self.n_init = 0
         self.rank, self.world = int(rank), int(world)
         rc = self._lib.qaoa_create_sharded(self.n_qubits, self.dtype, int(device), self.rank, self.world,
                                            ctypes.byref(self._h))
@@ -225,16 +226,18 @@ class Engine:
             sv = np.ascontiguousarray(np.asarray(vec, dtype=np.complex128)).view(np.float64)
             assert sv.size == 2 << self.n_qubits
         self._check(self._lib.qaoa_set_initial(self._h, int(kind), int(k), _dptr(sv) if sv is not None else None))
+        self.n_init = int(k) if kind == INIT_PLUS_PHASES else 0
 
     # -- evaluation ------------------------------------------------------
     def energy(self, angles):
         """Returns (E[cost], E[cost^2], min, max, norm) for one flat angle vector."""
         angles = np.ascontiguousarray(angles, dtype=np.float64).reshape(-1)
         per = self.n_gamma + self.n_beta
-        if angles.size == 0 or angles.size % per:
-            raise ValueError("angle vector length %d is not a multiple of %d" % (angles.size, per))
+        body = angles.size - self.n_init
+        if body <= 0 or body % per:
+            raise ValueError("angle vector length %d is not %d + a multiple of %d" % (angles.size, self.n_init, per))
         out = np.empty(5, dtype=np.float64)
-        self._check(self._lib.qaoa_energy(self._h, angles.size // per, _dptr(angles), angles.size, _dptr(out)))
+        self._check(self._lib.qaoa_energy(self._h, body // per, _dptr(angles), angles.size, _dptr(out)))
         return out
 
     def energy_batch(self, angles):
@@ -243,17 +246,18 @@ class Engine:
         assert angles.ndim == 2
         B, na = angles.shape
         per = self.n_gamma + self.n_beta
-        if na == 0 or na % per:
-            raise ValueError("angle vector length %d is not a multiple of %d" % (na, per))
+        body = na - self.n_init
+        if body <= 0 or body % per:
+            raise ValueError("angle vector length %d is not %d + a multiple of %d" % (na, self.n_init, per))
         out = np.empty((B, 5), dtype=np.float64)
-        self._check(self._lib.qaoa_energy_batch(self._h, na // per, _dptr(angles), na, B, _dptr(out)))
+        self._check(self._lib.qaoa_energy_batch(self._h, body // per, _dptr(angles), na, B, _dptr(out)))
         return out
 
     def energy_batch_resident(self, angles):
         angles = np.ascontiguousarray(angles, dtype=np.float64)
         B, na = angles.shape
         per = self.n_gamma + self.n_beta
-        self._check(self._lib.qaoa_energy_batch_resident(self._h, na // per, _dptr(angles), na, B))
+        self._check(self._lib.qaoa_energy_batch_resident(self._h, (na - self.n_init) // per, _dptr(angles), na, B))
 
     def fetch_results(self, B):
         out = np.empty((B, 5), dtype=np.float64)
@@ -269,9 +273,10 @@ class Engine:
     def _angles(self, angles):
         angles = np.ascontiguousarray(angles, dtype=np.float64).reshape(-1)
         per = self.n_gamma + self.n_beta
-        if angles.size == 0 or angles.size % per:
-            raise ValueError("angle vector length %d is not a multiple of %d" % (angles.size, per))
-        return angles, angles.size // per
+        body = angles.size - self.n_init
+        if body <= 0 or body % per:
+            raise ValueError("angle vector length %d is not %d + a multiple of %d" % (angles.size, self.n_init, per))
+        return angles, body // per
 
     def sample(self, angles, shots, seed=None):
         """``shots`` basis indices drawn from |psi(angles)|^2 (replaces backend.run(shots) + get_counts,

@@ -224,8 +224,8 @@ class QAOA:
 
             if self.problem.get_num_parameters() != 1 and not hasattr(self.problem, "term_of_edge"):
                 _reject("problems with more than one gamma per layer (other than MaxCutFree / MaxCutOrbit)")
-            if self.initialstate.get_num_parameters() != 0:
-                _reject("parameterised initial states")
+            if self.initialstate.get_num_parameters() != 0 and type(self.initialstate).__name__ != "PlusParameterized":
+                _reject("parameterised initial states (other than PlusParameterized)")
             if getattr(self.backend, "sharded", False):
                 from qaoa_b200.sharded import DistShardedEngine
                 eng = DistShardedEngine(self.problem.N_qubits, dtype=self.backend.dtype, device=self.backend.device)
@@ -238,7 +238,7 @@ class QAOA:
         return self._engine
 
     def _evaluate(self, angle_rows):
-        """(B, n_angles) flat angle vectors -> (B, 6) = E, E2, min, max, norm, CVaR.
+        """(B, n_angles) FULL flat angle vectors (initial-state parameters first) -> (B, 6) = E, E2, min, max, norm, CVaR.
 
         CVaR (= E when cvar == 1) is the shots -> infinity limit of the reference's
         ``Statistic.get_CVaR`` (qaoa/utils/statistic.py:132-142): the mean of the best (largest-cost)
@@ -246,13 +246,15 @@ class QAOA:
         rows = np.atleast_2d(np.asarray(angle_rows, dtype=np.float64))
         eng = self._get_engine()
         n_gamma, n_beta = self.problem.get_num_parameters(), self.mixer.get_num_parameters()
+        n_init = self.initialstate.get_num_parameters()
         if type(self.mixer).engine_betas is not Mixer.engine_betas:
             # shared mixer parameters (XOrbit): expand every layer's betas to what the device mixer takes
             per = n_gamma + n_beta
             rows = np.asarray([
-                np.concatenate([np.concatenate([r[d * per: d * per + n_gamma],
-                                                self.mixer.engine_betas(r[d * per + n_gamma: (d + 1) * per])])
-                                for d in range(len(r) // per)]) for r in rows], dtype=np.float64)
+                np.concatenate([r[:n_init]] + [np.concatenate([r[n_init + d * per: n_init + d * per + n_gamma],
+                                                               self.mixer.engine_betas(r[n_init + d * per + n_gamma:
+                                                                                         n_init + (d + 1) * per])])
+                                               for d in range((len(r) - n_init) // per)]) for r in rows], dtype=np.float64)
         res = eng.energy_batch(rows)
         if self.cvar < 1:
             cv = np.array([self._exact_cvar(*eng.cost_distribution(r)) for r in rows])
@@ -424,7 +426,7 @@ class QAOA:
             raise NotImplementedError
         angles = np.asarray(angles, dtype=np.float64)
         assert len(angles) == self.n_init + self.parametrized_circuit_depth * (self.n_gamma + self.n_beta)
-        e, e2, cmin, cmax, _norm, cv = self._evaluate(angles[self.n_init:])[0]
+        e, e2, cmin, cmax, _norm, cv = self._evaluate(angles)[0]
         self.stat.reset()
         self.stat.set_exact(e, e2, cmin, cmax, cvar_value=cv)
         self.optimization_results[self.current_depth + 1].add_iteration(angles.copy(), self.stat, self.shots)
@@ -448,7 +450,7 @@ class QAOA:
         if not self.backend.configuration().local:
             raise NotImplementedError
         angle_array = np.asarray(angle_array, dtype=np.float64)
-        e, e2, cmin, cmax, _, cv = self._evaluate(angle_array[self.n_init:])[0]
+        e, e2, cmin, cmax, _, cv = self._evaluate(angle_array)[0]
         self.stat.reset()
         self.stat.set_exact(e, e2, cmin, cmax, cvar_value=cv)
         return -self.stat.get_CVaR()
@@ -463,7 +465,7 @@ class QAOA:
         gamma_grid, beta_grid = self._grid(angles)
         LOG.info("Layer grid search at depth %d: %dx%d points", new_depth, len(gamma_grid), len(beta_grid))
         rows = self._vanilla_rows(gamma_grid, beta_grid, prefix=list(np.asarray(prev_angles, dtype=np.float64)))
-        res = self._evaluate(rows[:, self.n_init:])
+        res = self._evaluate(rows)
         costs = -res[:, 5]
         k = int(np.argmin(costs))
         LOG.info("Layer grid search done, best cost: %.6f", -costs[k])
@@ -478,7 +480,7 @@ class QAOA:
         depth = int((len(angles) - n_init) / (n_gamma + n_beta))
         self.createParameterizedCircuit(depth)
         eng = self._get_engine()
-        idx = eng.sample(np.asarray(angles, dtype=np.float64)[n_init:], int(shots))
+        idx = eng.sample(np.asarray(angles, dtype=np.float64), int(shots))
         n = self.problem.N_qubits
         out = {}
         values, counts = np.unique(idx, return_counts=True)

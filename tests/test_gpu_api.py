@@ -131,3 +131,17 @@ def test_per_term_gammas_free_and_orbit(dtype, tol):
     from qaoa_b200.engine import EngineError
     with pytest.raises(EngineError):
         big.sample_cost_landscape({"gamma": [0, 1, 2], "beta": [0, 1, 2]})
+
+
+@pytest.mark.parametrize("dtype,tol", [("complex128", 1e-9), ("complex64", 1e-4)])
+def test_plus_parameterized_on_the_device(dtype, tol):
+    """PlusParameterized: the leading init phases of the angle vector reach the single-CTA kernel."""
+    G = nx.random_regular_graph(3, 10, seed=2)
+    dev, ref = both(lambda: problems.MaxCut(G), mixers.X, lambda: initialstates.PlusParameterized(num_phases=7), dtype)
+    dev.createParameterizedCircuit(2)
+    ref.createParameterizedCircuit(2)
+    rows = np.random.default_rng(9).uniform(-2, 2, size=(4, 7 + 4))
+    a, b = dev._evaluate(rows), ref._evaluate(rows)
+    assert np.allclose(a[:, 0], b[:, 0], rtol=tol, atol=tol) and np.allclose(a[:, 1], b[:, 1], rtol=2 * tol, atol=2 * tol)
+    h = dev.hist(rows[0], 512)
+    assert sum(h.values()) == 512

@@ -53,6 +53,10 @@ class OracleEngine:
 
     def set_initial(self, kind, k=0, vec=None):
         n = self.n_qubits
+        self.n_init = k if kind == eng.INIT_PLUS_PHASES else 0
+        if kind == eng.INIT_PLUS_PHASES:
+            self.init = orc.plus_state(n)
+            return
         self.init = {eng.INIT_PLUS: lambda: orc.plus_state(n), eng.INIT_DICKE: lambda: orc.dicke_state(n, k),
                      eng.INIT_STATEVECTOR: lambda: np.asarray(vec, dtype=complex)}[kind]()
 
@@ -71,8 +75,11 @@ class OracleEngine:
             self.mixer = ("grover", s)
 
     def _prob(self, row):
-        spec = orc.Spec(self.n_qubits, self.diag, mixer=self.mixer, init=self.init, trotter=self.trotter,
-                        terms=getattr(self, "terms", None))
+        row = np.asarray(row, dtype=float)
+        ni = getattr(self, "n_init", 0)
+        spec = orc.Spec(self.n_qubits, self.diag, mixer=self.mixer, init=orc.phased_plus(self.init, row[:ni]),
+                        trotter=self.trotter, terms=getattr(self, "terms", None))
+        row = row[ni:]
         pr = np.abs(orc.evolve(spec, np.asarray(row, dtype=float))) ** 2
         return pr / pr.sum()
 
@@ -90,9 +97,13 @@ class OracleEngine:
         spec = orc.Spec(self.n_qubits, self.diag, mixer=self.mixer, init=self.init, trotter=self.trotter,
                         terms=getattr(self, "terms", None))
         out = np.empty((len(rows), 5))
+        ni = getattr(self, "n_init", 0)
         for i, r in enumerate(rows):
             self.calls += 1
-            e, e2, mn, mx = orc.energy(spec, r)
+            if ni:
+                spec = orc.Spec(self.n_qubits, self.diag, mixer=self.mixer, init=orc.phased_plus(self.init, r[:ni]),
+                                trotter=self.trotter, terms=getattr(self, "terms", None))
+            e, e2, mn, mx = orc.energy(spec, r[ni:])
             out[i] = (e, e2, mn, mx, 1.0)
         return out
 
@@ -375,3 +386,19 @@ def test_maxcut_free_and_orbit_per_term_gammas():
     e_plain = fp.energy_batch(np.array([[0.37, 0.21]]))[0, 0]
     e_terms = fake.energy_batch(np.array([[0.37] * 6 + [0.21] * 5]))[0, 0]
     assert e_terms == pytest.approx(e_plain, rel=1e-12)
+
+
+def test_plus_parameterized_initial_state():
+    """PlusParameterized (plus_parameterized_initialstate.py:25-64): n_init phases lead the angle vector; phi = 0 is |+>."""
+    G = nx.random_regular_graph(3, 6, seed=2)
+    q, fake = make(problems.MaxCut(G), init=initialstates.PlusParameterized(num_phases=4))
+    q.createParameterizedCircuit(1)
+    assert (q.n_init, q.n_gamma, q.n_beta) == (4, 1, 1) and fake.n_init == 4
+    q.optimization_results[1] = OptResult(1)
+    plain, fp = make(problems.MaxCut(G))
+    e0 = -fp.energy_batch(np.array([[0.4, 0.3]]))[0, 0]
+    assert q.loss(np.array([0, 0, 0, 0, 0.4, 0.3])) == pytest.approx(e0, rel=1e-12)
+    assert q.loss(np.array([0.3, -0.8, 1.1, 0.2, 0.4, 0.3])) != pytest.approx(e0, rel=1e-6)
+    q.sample_cost_landscape({"gamma": [0, 1, 3], "beta": [0, 1, 3]})      # landscape: init parameters are 0
+    plain.sample_cost_landscape({"gamma": [0, 1, 3], "beta": [0, 1, 3]})
+    assert np.allclose(q.Exp_sampled_p1, plain.Exp_sampled_p1)
