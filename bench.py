@@ -127,23 +127,26 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
-def landscape_leg(device):
+def landscape_leg(device, world=1):
     """BASELINE config 2: MaxCut 3-regular n=24, X mixer, p=1, 100x100 (gamma, beta) grid through the public
-    QAOA.sample_cost_landscape call (host grid in, four host arrays out)."""
+    QAOA.sample_cost_landscape call (host grid in, four host arrays out).  With several GPUs every rank holds a
+    replica and the grid points are dealt out over the ranks (B200Backend(split_batches=True)); all ranks call this."""
     import networkx as nx
     from qaoa_b200 import QAOA, initialstates, mixers, problems
+    from qaoa_b200.qaoa import B200Backend
 
     n, g = 24, 100
     G = nx.random_regular_graph(3, n, seed=42)
-    q = QAOA(problem=problems.MaxCut(G), mixer=mixers.X(), initialstate=initialstates.Plus(), dtype="complex64",
-             device=device)
+    q = QAOA(problem=problems.MaxCut(G), mixer=mixers.X(), initialstate=initialstates.Plus(),
+             backend=B200Backend(device=device, dtype="complex64", split_batches=world > 1))
     q.sample_cost_landscape({"gamma": [0, 2 * np.pi, 8], "beta": [0, 2 * np.pi, 8]})   # warm-up: plan, streams
     grid = {"gamma": [0, 2 * np.pi, g], "beta": [0, 2 * np.pi, g]}
     t0 = time.perf_counter()
     q.sample_cost_landscape(grid)
     dt = time.perf_counter() - t0
     bytes_per_point = 2 * (8.0 + 1.0) * 2.0 ** n    # FIRST writes the state, FINAL reads it, one diagonal byte each
-    return {"workload": "MaxCut 3-regular n=%d seed=42, X, Plus, p=1, %dx%d grid, complex64" % (n, g, g),
+    return {"workload": "MaxCut 3-regular n=%d seed=42, X, Plus, p=1, %dx%d grid, complex64%s" % (
+                n, g, g, "" if world == 1 else ", grid points dealt out over %d GPUs" % world),
             "points_per_s": g * g / dt, "seconds": dt, "min_exp": float(q.Exp_sampled_p1.min()),
             "algorithmic_gb_per_point": bytes_per_point / 1e9,
             "achieved_gbs": bytes_per_point * g * g / dt / 1e9}
@@ -291,6 +294,12 @@ def main():
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
+    landscape = None
+    if not args.no_landscape:
+        barrier()
+        landscape = landscape_leg(local_rank, world)
+        barrier()
+
     ms_dev = float(np.mean(dev_ms))
     ms_e2e = 1e3 * wall_e2e / args.steps
     if world > 1:
@@ -352,8 +361,8 @@ def main():
                          "survey_model_frac_of_8TBps": survey_bytes / (ms_dev * 1e-3) / 8e12},
             "passes": {names[i]: {"ms_total": v[0], "launches": int(v[1])} for i, v in pass_stats.items() if v[1]},
         }
-        if world == 1 and not args.no_landscape:
-            line["landscape"] = landscape_leg(local_rank)
+        if landscape is not None:
+            line["landscape"] = landscape
         if sharded is not None:
             # ONE register of n + log2(N) qubits sharded over the N GPUs (same 2^n amplitudes per GPU):
             # cross passes over NVLink peer memory + scalar all-reduce; its own value / e2e / roofline / nvlink

@@ -40,13 +40,16 @@ class B200Backend:
 
     name = "b200_statevector"
 
-    def __init__(self, device=0, dtype="complex128", sharded=False):
-        """``sharded=True`` (under ``torch.distributed``, one process per GPU): ONE register split on its top
-        qubits over all ranks (qaoa_b200/sharded.py); every rank then drives the same QAOA object and sees
-        identical results."""
+    def __init__(self, device=0, dtype="complex128", sharded=False, split_batches=False):
+        """Multi-GPU modes (under ``torch.distributed``, one process per GPU, every rank driving the same
+        QAOA object and seeing identical results):
+        ``sharded=True``: ONE register split on its top qubits over all ranks (qaoa_b200/sharded.py);
+        ``split_batches=True``: every rank holds a full replica and batched evaluations (landscape grids, layer
+        grid searches) are dealt out round-robin, the results gathered -- no data-path collective."""
         self.device = device
         self.dtype = dtype
         self.sharded = sharded
+        self.split_batches = split_batches
 
     class _Conf:
         local = True
@@ -255,12 +258,26 @@ class QAOA:
                                                                self.mixer.engine_betas(r[n_init + d * per + n_gamma:
                                                                                          n_init + (d + 1) * per])])
                                                for d in range((len(r) - n_init) // per)]) for r in rows], dtype=np.float64)
-        res = eng.energy_batch(rows)
+        world, rank, dist = 1, 0, None
+        if getattr(self.backend, "split_batches", False) and not getattr(self.backend, "sharded", False):
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                world, rank = dist.get_world_size(), dist.get_rank()
+        mine = rows[rank::world] if world > 1 and len(rows) >= world else rows
+        res = eng.energy_batch(mine)
         if self.cvar < 1:
-            cv = np.array([self._exact_cvar(*eng.cost_distribution(r)) for r in rows])
+            cv = np.array([self._exact_cvar(*eng.cost_distribution(r)) for r in mine])
         else:
             cv = res[:, 0]
-        return np.column_stack([res, cv])
+        out = np.column_stack([res, cv])
+        if mine is not rows:      # landscape / grid-search points were dealt out over the ranks: put them back in order
+            parts = [None] * world
+            dist.all_gather_object(parts, out)
+            full = np.empty((len(rows), out.shape[1]))
+            for r, part in enumerate(parts):
+                full[r::world] = part
+            out = full
+        return out
 
     def _exact_cvar(self, costs, probs):
         order = np.argsort(-costs, kind="stable")

@@ -193,3 +193,50 @@ def test_combine_partials_and_barrier_rule():
     assert np.allclose(out, [3.0, 12.0, 0.0, 4.0, 1.0])
     flags = [False, False, True, False, False, True]
     assert [needs_barrier(flags, i) for i in range(6)] == [False, False, True, True, False, True]
+
+
+def _split_worker(rank, world, port, out_dir):
+    import networkx as nx
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from qaoa_b200 import QAOA, initialstates, mixers, problems
+        from qaoa_b200.qaoa import B200Backend
+        from test_host_api import OracleEngine
+
+        G = nx.random_regular_graph(3, 8, seed=42)
+        prob = problems.MaxCut(G)
+        q = QAOA(problem=prob, mixer=mixers.X(), initialstate=initialstates.Plus(),
+                 backend=B200Backend(split_batches=True))
+        fake = OracleEngine(prob.N_qubits)
+        prob.lower_cost(fake)
+        q.initialstate.lower_initial(fake)
+        q.mixer.lower_mixer(fake, trotter=1)
+        q._engine = fake
+        q.sample_cost_landscape({"gamma": [0, 2 * np.pi, 5], "beta": [0, 2 * np.pi, 3]})
+        np.save(os.path.join(out_dir, "land%d.npy" % rank), np.concatenate([q.Exp_sampled_p1.ravel(), [fake.calls]]))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_landscape_split_across_ranks_gloo(tmp_path):
+    """split_batches: the 15 landscape points are dealt out over 2 ranks (8 + 7 evaluations), gathered back in grid
+    order, and both ranks see the landscape a single process computes."""
+    import networkx as nx
+    import torch.multiprocessing as mp
+
+    from qaoa_b200 import initialstates, mixers, problems
+    from test_host_api import make
+
+    mp.spawn(_split_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    ref, _ = make(problems.MaxCut(nx.random_regular_graph(3, 8, seed=42)), mixer=mixers.X(), init=initialstates.Plus())
+    ref.sample_cost_landscape({"gamma": [0, 2 * np.pi, 5], "beta": [0, 2 * np.pi, 3]})
+    calls = []
+    for r in range(2):
+        row = np.load(tmp_path / ("land%d.npy" % r))
+        assert np.allclose(row[:-1], ref.Exp_sampled_p1.ravel(), rtol=1e-13)
+        calls.append(int(row[-1]))
+    assert sorted(calls) == [7, 8]
