@@ -439,3 +439,28 @@ def test_randomised_configurations_against_oracle():
         E.close()
         checked += 1
     assert checked == 60
+
+
+def test_balanced_schedule_batched_points():
+    """Several points per launch on the balanced schedule (n=25): the persistent CTAs reload the per-point residents
+    (round coefficients, phase table) and flush their reduction accumulators whenever they move to another point."""
+    from oracle import c_oracle
+    n, p = 25, 2
+    eng, E = _engine(n, "complex64")
+    edges, colors, table = H.regular_maxcut(n)
+    lut, _ = H.lut_from_table(table, 1)
+    E.set_cost_maxkcut(n, edges, 1, lut)
+    diag = c_oracle.maxcut_diag(n, edges)
+    rng = np.random.default_rng(99)
+    rows = rng.uniform(-1.2, 1.2, size=(5, 2 * p))
+    E.set_option("batch_points", 3)          # 5 points = one chunk of 3 and one of 2
+    E.counter("reset")
+    got = E.energy_batch(rows)
+    assert E.counter("prog_launches") >= 2
+    for i in (0, 2, 4):
+        ref = c_oracle.energy(n, diag, rows[i], "complex128")
+        _check(got[i], None, rows[i], "complex64", "point %d" % i, ref=ref)
+    E.set_option("batch_points", 1)
+    one = np.stack([E.energy(r) for r in rows])
+    assert np.allclose(got[:, :2], one[:, :2], rtol=2e-6)
+    assert np.array_equal(got[:, 2:4], one[:, 2:4])
