@@ -88,6 +88,24 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm)}
 
 
+def pick_cpu_n(c_oracle, p, n_target, budget_s, evals, requested):
+    """Largest sample size whose `evals` evaluations fit the CPU time budget: calibrate at n=22, work ~ 2^n * n."""
+    if requested > 0:
+        return requested
+    ns = 22
+    diag = c_oracle.maxcut_diag(ns, workload(ns))
+    ang = angles_for(p, 1234)
+    c_oracle.energy(ns, diag, ang, "complex64")
+    t0 = time.perf_counter()
+    c_oracle.energy(ns, diag, ang, "complex64")
+    t = time.perf_counter() - t0
+    best = ns
+    for cand in range(ns + 1, min(n_target, 30) + 1):       # n = 30: 8 GiB state + 8 GiB diagonal on the host
+        if t * (2.0 ** cand * cand) / (2.0 ** ns * ns) * evals <= budget_s:
+            best = cand
+    return best
+
+
 def run_reference(args, rank):
     """CPU arm: oracle/c/qaoa_ref.c on the host cores, bounded sample, scaled to the workload."""
     if rank != 0:
@@ -96,7 +114,7 @@ def run_reference(args, rank):
 
     c_oracle.build()
     c_oracle.use_all_cores()
-    ns = args.cpu_n
+    ns = pick_cpu_n(c_oracle, args.p, args.n, 60.0, args.steps + 1, args.cpu_n)
     edges = workload(ns)
     diag = c_oracle.maxcut_diag(ns, edges)
     ang = angles_for(args.p, 1234)
@@ -227,7 +245,8 @@ def main():
     ap.add_argument("--n", type=int, default=32)
     ap.add_argument("--p", type=int, default=5)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--cpu-n", type=int, default=26, dest="cpu_n")
+    ap.add_argument("--cpu-n", type=int, default=0, dest="cpu_n",
+                    help="sample size of the CPU legs (0: the largest that fits the time budget)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-landscape", action="store_true")
     args = ap.parse_args()
@@ -372,7 +391,7 @@ def main():
             try:
                 c_oracle.build()
                 c_oracle.use_all_cores()
-                ns = args.cpu_n
+                ns = pick_cpu_n(c_oracle, p, n, 20.0, 4, args.cpu_n)
                 cdiag = c_oracle.maxcut_diag(ns, workload(ns))
                 c_oracle.energy(ns, cdiag, ang, "complex64")
                 t0 = time.perf_counter()
