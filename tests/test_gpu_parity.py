@@ -464,3 +464,35 @@ def test_balanced_schedule_batched_points():
     one = np.stack([E.energy(r) for r in rows])
     assert np.allclose(got[:, :2], one[:, :2], rtol=2e-6)
     assert np.array_equal(got[:, 2:4], one[:, 2:4])
+
+
+def test_full_size_properties_n32():
+    """BASELINE size (MaxCut 3-regular n=32, complex64, 32 GiB state) through size-independent properties:
+    the closed-form p=1 energy, the (gamma, beta) -> (-gamma, -beta) symmetry of the energy,
+    unit norm after p=5, extremes of the cost over the support, and bit-exact samples of the cost diagonal."""
+    import torch
+    if torch.cuda.mem_get_info()[0] < 60 * 2 ** 30:
+        pytest.skip("needs 60 GiB of free device memory")
+    n = 32
+    eng, E = _engine(n, "complex64")
+    edges, colors, table = H.regular_maxcut(n)
+    lut, _ = H.lut_from_table(table, 1)
+    E.set_cost_maxkcut(n, edges, 1, lut)
+    rng = np.random.default_rng(3)
+    for off in (0, (1 << 31) + 12345, (1 << 32) - 4096):       # diagonal spot checks against cost(x)
+        got = E.read_cost_diagonal(off, 4096)
+        x = off + np.arange(4096, dtype=np.int64)
+        ref = np.zeros(4096)
+        for (u, v, w) in edges:
+            ref += (((x >> u) ^ (x >> v)) & 1) * w
+        assert np.array_equal(got, ref)
+    for _ in range(2):
+        g, b = rng.uniform(0.1, 1.2), rng.uniform(0.1, 1.2)
+        out = E.energy([g, b])
+        assert out[0] == pytest.approx(orc.maxcut_p1_closed_form(edges, n, g, b), rel=1e-4)
+        assert abs(out[4] - 1) < 1e-4 and out[2] == 0 and 0 < out[3] <= len(edges)
+    ang = rng.uniform(-1.0, 1.0, size=10)
+    a, b2 = E.energy(ang), E.energy(-ang)
+    assert a[0] == pytest.approx(b2[0], rel=1e-5) and abs(a[4] - 1) < 1e-4
+    lo, hi = E.cost_minmax()
+    assert a[2] >= lo and a[3] <= hi and lo == 0
