@@ -107,6 +107,12 @@ int qaoa_read_statevector(qaoa_engine_t* h, double* out);
  * generator (inverse-CDF sampling, deterministic for given u); out_idx[i] = basis index of shot i. */
 int qaoa_sample(qaoa_engine_t* h, int p, const double* angles, int n_angles, int shots, const double* u,
                 uint64_t* out_idx);
+/* Basis indices of the support of |psi(angles)> that attain the maximum (want_max != 0) or minimum cost over that
+ * support: the shots -> infinity limit of Statistic.get_max_sols / get_min_sols (statistic.py:69-82), which feed
+ * OptResult.BestSols and QAOA.get_optimal_solutions (qaoa/qaoa.py:89-91, 1193-1212).  At most `cap` indices are
+ * returned (ascending); *out_count is the true number. */
+int qaoa_extreme_solutions(qaoa_engine_t* h, int p, const double* angles, int n_angles, int want_max, int cap,
+                           uint64_t* out_idx, int* out_count, double* out_cost);
 /* P(cost = *c0 + *delta * k), k < 256, over the final state (integer-valued costs with range <= 255).
  * The shots -> infinity limit of the sorted sample list behind Statistic.get_CVaR (statistic.py:132-142). */
 int qaoa_cost_distribution(qaoa_engine_t* h, int p, const double* angles, int n_angles, double* probs256,

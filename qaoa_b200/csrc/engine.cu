@@ -1718,6 +1718,35 @@ int qaoa_sample(qaoa_engine_t* h, int p, const double* angles, int n_angles, int
   API_END(h)
 }
 
+int qaoa_extreme_solutions(qaoa_engine_t* h, int p, const double* angles, int n_angles, int want_max, int cap,
+                           uint64_t* out_idx, int* out_count, double* out_cost) {
+  API_BEGIN(h)
+  if (cap < 1 || !out_idx || !out_count) fail("empty request");
+  eval_keeping_state(h, p, angles, n_angles);
+  double res[5];
+  CUDA_OK(cudaMemcpy(res, h->d_out, sizeof(res), cudaMemcpyDeviceToHost));
+  const double target = want_max ? res[3] : res[2];
+  unsigned long long* d_idx; unsigned* d_cnt;
+  CUDA_OK(cudaMalloc((void**)&d_idx, (size_t)cap * 8));
+  CUDA_OK(cudaMalloc((void**)&d_cnt, 4));
+  CUDA_OK(cudaMemsetAsync(d_cnt, 0, 4, h->stream));
+  const int grid = grid_for(h->N, 256);
+  if (h->dtype == QAOA_DTYPE_C64) collect_cost_equal_kernel<float><<<grid, 256, 0, h->stream>>>((const float*)h->state, h->diag, h->dinfo, h->N, target, (unsigned)cap, d_idx, d_cnt);
+  else collect_cost_equal_kernel<double><<<grid, 256, 0, h->stream>>>((const double*)h->state, h->diag, h->dinfo, h->N, target, (unsigned)cap, d_idx, d_cnt);
+  CUDA_OK(cudaGetLastError());
+  unsigned cnt = 0;
+  CUDA_OK(cudaMemcpyAsync(&cnt, d_cnt, 4, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  const unsigned got = std::min<unsigned>(cnt, (unsigned)cap);
+  CUDA_OK(cudaMemcpy(out_idx, d_idx, (size_t)got * 8, cudaMemcpyDeviceToHost));
+  std::sort(out_idx, out_idx + got);
+  *out_count = (int)cnt;
+  if (out_cost) *out_cost = target;
+  h->launches += 1;
+  cudaFree(d_idx); cudaFree(d_cnt);
+  API_END(h)
+}
+
 int qaoa_cost_distribution(qaoa_engine_t* h, int p, const double* angles, int n_angles, double* probs256,
                            double* c0, double* delta) {
   API_BEGIN(h)

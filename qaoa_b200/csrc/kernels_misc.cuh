@@ -747,3 +747,19 @@ cost_hist_kernel(const real* __restrict__ st, const uint8_t* __restrict__ diag, 
   __syncthreads();
   partial[(size_t)blockIdx.x * 256 + threadIdx.x] = bins[threadIdx.x];
 }
+
+// Basis indices of the support of the kept state whose cost equals `target` (the extreme the reduction
+// reported): the shots -> infinity limit of Statistic.get_max_sols / get_min_sols (statistic.py:69-82).
+template <typename real>
+__global__ void __launch_bounds__(256)
+collect_cost_equal_kernel(const real* __restrict__ st, const void* __restrict__ diag, DiagInfo info, size_t N,
+                          double target, unsigned cap, unsigned long long* __restrict__ out, unsigned* __restrict__ count) {
+  for (size_t x = blockIdx.x * (size_t)blockDim.x + threadIdx.x; x < N; x += (size_t)gridDim.x * blockDim.x) {
+    if (diag_decode(info, diag, x) != target) continue;
+    const double re = st[2 * x], im = st[2 * x + 1];
+    if (re * re + im * im > 0.0) {
+      const unsigned i = atomicAdd(count, 1u);
+      if (i < cap) out[i] = (unsigned long long)x;
+    }
+  }
+}

@@ -84,6 +84,8 @@ def load_library():
         "qaoa_debug_tile_program": (
             ctypes.c_int, [H, ctypes.c_int, _c_int32_p, ctypes.c_int, ctypes.c_int, ctypes.c_double, _c_double_p]),
         "qaoa_sample": (ctypes.c_int, [H, ctypes.c_int, _c_double_p, ctypes.c_int, ctypes.c_int, _c_double_p, _c_uint64_p]),
+        "qaoa_extreme_solutions": (ctypes.c_int, [H, ctypes.c_int, _c_double_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                  _c_uint64_p, ctypes.POINTER(ctypes.c_int), _c_double_p]),
         "qaoa_cost_distribution": (ctypes.c_int, [H, ctypes.c_int, _c_double_p, ctypes.c_int, _c_double_p,
                                                   _c_double_p, _c_double_p]),
         # sharded registers (one engine per GPU)
@@ -287,6 +289,15 @@ class Engine:
         self._check(self._lib.qaoa_sample(self._h, p, _dptr(angles), angles.size, int(shots), _dptr(u),
                                           out.ctypes.data_as(_c_uint64_p)))
         return out
+
+    def extreme_solutions(self, angles, want_max=True, cap=4096):
+        """(indices, cost): the basis states of the support of |psi(angles)> with the largest (smallest) cost."""
+        angles, p = self._angles(angles)
+        out = np.empty(int(cap), dtype=np.uint64)
+        cnt, cost = ctypes.c_int(), ctypes.c_double()
+        self._check(self._lib.qaoa_extreme_solutions(self._h, p, _dptr(angles), angles.size, int(bool(want_max)), int(cap),
+                                                     out.ctypes.data_as(_c_uint64_p), ctypes.byref(cnt), ctypes.byref(cost)))
+        return out[: min(cnt.value, int(cap))].copy(), cost.value
 
     def cost_distribution(self, angles):
         """(cost values, probabilities) of the final state; integer-valued costs with range <= 255 only."""

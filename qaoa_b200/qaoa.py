@@ -248,16 +248,9 @@ class QAOA:
         ``cvar`` fraction of the distribution, computed from the device's cost-value distribution."""
         rows = np.atleast_2d(np.asarray(angle_rows, dtype=np.float64))
         eng = self._get_engine()
-        n_gamma, n_beta = self.problem.get_num_parameters(), self.mixer.get_num_parameters()
-        n_init = self.initialstate.get_num_parameters()
         if type(self.mixer).engine_betas is not Mixer.engine_betas:
             # shared mixer parameters (XOrbit): expand every layer's betas to what the device mixer takes
-            per = n_gamma + n_beta
-            rows = np.asarray([
-                np.concatenate([r[:n_init]] + [np.concatenate([r[n_init + d * per: n_init + d * per + n_gamma],
-                                                               self.mixer.engine_betas(r[n_init + d * per + n_gamma:
-                                                                                         n_init + (d + 1) * per])])
-                                               for d in range((len(r) - n_init) // per)]) for r in rows], dtype=np.float64)
+            rows = np.asarray([self._engine_row(r) for r in rows], dtype=np.float64)
         world, rank, dist = 1, 0, None
         if getattr(self.backend, "split_batches", False) and not getattr(self.backend, "sharded", False):
             import torch.distributed as dist
@@ -497,7 +490,7 @@ class QAOA:
         depth = int((len(angles) - n_init) / (n_gamma + n_beta))
         self.createParameterizedCircuit(depth)
         eng = self._get_engine()
-        idx = eng.sample(np.asarray(angles, dtype=np.float64), int(shots))
+        idx = eng.sample(self._engine_row(angles), int(shots))
         n = self.problem.N_qubits
         out = {}
         values, counts = np.unique(idx, return_counts=True)
@@ -512,9 +505,37 @@ class QAOA:
         out[0::2], out[1::2] = gam, bet
         return out
 
+    def _fill_best_sols(self, result):
+        """OptResult.BestSols is filled lazily: the exact engine reports the extreme COSTS with every evaluation, the
+        bit-strings attaining them (Statistic.get_max_sols in the reference, qaoa/qaoa.py:89-91) cost one more
+        evaluation with the state kept, so they are fetched only for the iterations that matter."""
+        if not result.BestCost:
+            return
+        lowest = np.min(result.BestCost)
+        n = self.problem.N_qubits
+        eng = self._get_engine()
+        for i in np.where(np.asarray(result.BestCost) == lowest)[0][:1]:
+            if not result.BestSols[i] and hasattr(eng, "extreme_solutions"):
+                idx, _cost = eng.extreme_solutions(self._engine_row(result.angles[i]), want_max=True)
+                result.BestSols[i] = ["".join("1" if (int(x) >> q) & 1 else "0" for q in range(n)) for x in idx]
+
+    def _engine_row(self, angles):
+        """full flat angle vector -> what the device takes (shared mixer parameters expanded)"""
+        row = np.asarray(angles, dtype=np.float64)
+        if type(self.mixer).engine_betas is Mixer.engine_betas:
+            return row
+        n_gamma, n_beta = self.problem.get_num_parameters(), self.mixer.get_num_parameters()
+        n_init, per = self.initialstate.get_num_parameters(), n_gamma + n_beta
+        parts = [row[:n_init]]
+        for d in range((len(row) - n_init) // per):
+            at = n_init + d * per
+            parts += [row[at: at + n_gamma], self.mixer.engine_betas(row[at + n_gamma: at + per])]
+        return np.concatenate(parts)
+
     def get_optimal_solutions(self):
         sols, costs = [], []
         for d in self.optimization_results:
+            self._fill_best_sols(self.optimization_results[d])
             s, c = self.optimization_results[d].get_best_solution()
             sols.append(s)
             costs.append(c)

@@ -145,3 +145,24 @@ def test_plus_parameterized_on_the_device(dtype, tol):
     assert np.allclose(a[:, 0], b[:, 0], rtol=tol, atol=tol) and np.allclose(a[:, 1], b[:, 1], rtol=2 * tol, atol=2 * tol)
     h = dev.hist(rows[0], 512)
     assert sum(h.values()) == 512
+
+
+def test_get_optimal_solutions_on_the_device():
+    """qaoa_extreme_solutions behind QAOA.get_optimal_solutions: the optimal cuts of the README graph."""
+    G = nx.random_regular_graph(3, 8, seed=42)
+    dev = QAOA(problem=problems.MaxCut(G), mixer=mixers.X(), initialstate=initialstates.Plus(), dtype="complex128",
+               optimizer=[COBYLA, {"maxiter": 15}])
+    dev.optimize(depth=1, angles={"gamma": [0, np.pi, 4], "beta": [0, np.pi, 4]})
+    sols = list(dev.get_optimal_solutions())
+    strings = [format(x, "08b")[::-1] for x in range(256)]
+    best = max(dev.problem.cost(s) for s in strings)
+    assert sorted(sols) == sorted(s for s in strings if dev.problem.cost(s) == best)
+    # a Dicke + XY state only has weight-k strings in its support
+    q = QAOA(problem=problems.QUBO(Q=np.random.RandomState(1).rand(10, 10)), mixer=mixers.XY(case="ring"),
+             initialstate=initialstates.Dicke(3), dtype="complex128")
+    eng = q._get_engine()
+    idx, cost = eng.extreme_solutions([0.02, 0.7], want_max=True)
+    assert len(idx) >= 1 and all(bin(int(x)).count("1") == 3 for x in idx)
+    feas = [x for x in range(1 << 10) if bin(x).count("1") == 3]
+    d = eng.read_cost_diagonal()
+    assert cost == pytest.approx(max(d[x] for x in feas))

@@ -88,6 +88,12 @@ class OracleEngine:
         vals = np.unique(self.diag)
         return vals, np.array([pr[self.diag == v].sum() for v in vals])
 
+    def extreme_solutions(self, row, want_max=True, cap=4096):
+        pr = self._prob(row)
+        d = np.where(pr > 0, self.diag, -np.inf if want_max else np.inf)
+        target = d.max() if want_max else d.min()
+        return np.flatnonzero(d == target).astype(np.uint64)[:cap], float(target)
+
     def sample(self, row, shots, seed=None):
         cum = np.cumsum(self._prob(row))
         u = np.random.default_rng(seed).random(int(shots))
@@ -402,3 +408,15 @@ def test_plus_parameterized_initial_state():
     q.sample_cost_landscape({"gamma": [0, 1, 3], "beta": [0, 1, 3]})      # landscape: init parameters are 0
     plain.sample_cost_landscape({"gamma": [0, 1, 3], "beta": [0, 1, 3]})
     assert np.allclose(q.Exp_sampled_p1, plain.Exp_sampled_p1)
+
+
+def test_get_optimal_solutions_returns_the_maximum_cuts():
+    """get_optimal_solutions (qaoa.py:1193-1212): with exact statistics the best strings over the support of a
+    Plus + X state are the optimal cuts of the README graph (max cut 10, found by brute force over cost())."""
+    q, fake = readme_qaoa(optimizer=[__import__("qaoa_b200").utils.COBYLA, {"maxiter": 15}])
+    q.optimize(depth=1, angles={"gamma": [0, np.pi, 4], "beta": [0, np.pi, 4]})
+    sols = list(q.get_optimal_solutions())
+    best = max(q.problem.cost(format(x, "08b")[::-1]) for x in range(256))
+    assert best == 10 and len(sols) >= 2
+    assert all(q.problem.cost(s) == best for s in sols)
+    assert sorted(sols) == sorted(format(x, "08b")[::-1] for x in range(256) if q.problem.cost(format(x, "08b")[::-1]) == best)
