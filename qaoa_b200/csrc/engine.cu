@@ -460,7 +460,8 @@ Plan build_plan(Engine* h, int p) {
     pl.shapes.push_back(s);
   }
   const int m = (int)pl.shapes.size();
-  if (h->schedule != 1 && h->dtype == QAOA_DTYPE_C64 && m >= 3 && !h->keep_state) {
+  // balanced schedule: complex64 with 4 or 5 low bits, complex128 with 5 (no A4 / C4 frames there)
+  if (h->schedule != 1 && (h->dtype == QAOA_DTYPE_C64 || clow == 5) && m >= 3 && !h->keep_state) {
     build_balanced(h, p, pl);
     return pl;
   }
@@ -644,7 +645,9 @@ void* get_stream(Engine* h, const Plan& pl, int shape, int frame) {
   if (it != h->streams.end()) return it->second;
   const int vb = diag_value_bytes(h->dinfo.kind);
   void* s = nullptr;
-  CUDA_OK(cudaMalloc(&s, h->N * vb));
+  // complex128 in frame C: one value per REGISTER (the re / im halves of an amplitude sit in neighbouring lanes)
+  const bool per_reg = h->dtype == QAOA_DTYPE_C128 && frame == 2;
+  CUDA_OK(cudaMalloc(&s, h->N * vb * (per_reg ? 2 : 1)));
   TilePass tp;
   memset(&tp, 0, sizeof(tp));
   const Shape& sh = pl.shapes[shape];
@@ -657,8 +660,8 @@ void* get_stream(Engine* h, const Plan& pl, int shape, int frame) {
   if (cross && !h->peers_diag_set) fail("sharded engine: peer cost-diagonal pointers have not been set");
   shard_fill(h, tp, sh.cross);
   const unsigned ntiles = 1u << (h->El - TILE_BITS);
-  const int namp = h->dtype == QAOA_DTYPE_C64 ? 32 : 16;
-  if (frame >= 2 && namp != 32) fail("frame C / C4 streams exist for complex64 only");
+  const int namp = (h->dtype == QAOA_DTYPE_C64 || per_reg) ? 32 : 16;
+  if (frame >= 3 && namp != 32) fail("frame A4 / C4 streams exist for complex64 only");
   if (vb == 1) make_stream_kernel<1><<<ntiles, TILE_THREADS, 0, h->stream>>>(tp, frame, namp, cross, (const unsigned char*)h->diag, (unsigned char*)s);
   else if (vb == 4) make_stream_kernel<4><<<ntiles, TILE_THREADS, 0, h->stream>>>(tp, frame, namp, cross, (const unsigned char*)h->diag, (unsigned char*)s);
   else make_stream_kernel<8><<<ntiles, TILE_THREADS, 0, h->stream>>>(tp, frame, namp, cross, (const unsigned char*)h->diag, (unsigned char*)s);

@@ -808,6 +808,82 @@ __device__ __forceinline__ void flush_acc(const Ctx<Elem>& c, double (&acc)[5], 
   acc[0] = 0.0; acc[1] = 0.0; acc[2] = 0.0; acc[3] = 1e300; acc[4] = -1e300;
 }
 
+// ---- complex128 in frame C ----------------------------------------------------------------------
+// There the re/im bit (t0) is a LANE bit: register r of an even lane is the real part, of the odd neighbour
+// the imaginary part of the same amplitude; the streams of frame C carry one value per REGISTER (32 per thread,
+// both lanes of a pair see the same value).  The phase multiply fetches the partner with one shuffle; the
+// statistics need no pairing at all (|psi|^2 c = re^2 c + im^2 c).
+// Visits the thread's 32 diagonal values: from the prefetched words (U8, compiled programs) or from the stream.
+template <typename F>
+__device__ __forceinline__ void c128c_each(const Ctx<double>& c, int slot, int kind, const uint4* dq, F&& f) {
+  if (dq) {
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+      const unsigned ww[4] = {dq[j].x, dq[j].y, dq[j].z, dq[j].w};
+#pragma unroll
+      for (int b = 0; b < 16; b++) f(j * 16 + b, (ww[b >> 2] >> (8 * (b & 3))) & 0xffu, 0.0);
+    }
+  } else {
+    for_each_diag<32>(c.P->streams[slot], kind, c.tile, c.warp, c.lane, f);
+  }
+}
+
+// TABLE_READY: the phase table of this slot is resident in shared memory (compiled programs)
+template <bool TABLE_READY>
+__device__ __forceinline__ void op_phase_c128c(const Ctx<double>& c, double (&v)[32], int slot, const uint4* dq) {
+  const TilePass& P = *c.P;
+  const int kind = c.dinfo.kind;
+  const double sgn = (c.lane & 1) ? 1.0 : -1.0;   // re' = re c - im s ; im' = im c + re s
+  if (kind == DIAG_U8) {
+    double2* tab = reinterpret_cast<double2*>(c.tab);
+    if (!TABLE_READY) {
+      __syncthreads();
+      if (threadIdx.x < 256) {
+        const double2* t = reinterpret_cast<const double2*>(c.tables) +
+                           ((size_t)c.point * c.tables_per_point + P.table_id[slot]) * 256;
+        tab[threadIdx.x] = t[threadIdx.x];
+      }
+      __syncthreads();
+    }
+    c128c_each(c, slot, kind, dq, [&](int r, unsigned k, double) {
+      const double2 ph = tab[k];
+      const double other = __shfl_xor_sync(0xffffffffu, v[r], 1);
+      v[r] = fma(sgn * other, ph.y, v[r] * ph.x);
+    });
+  } else {
+    const double gamma = __ldg(c.phs + 2 * slot), mult = __ldg(c.phs + 2 * slot + 1);
+    const double inv2pi = 0.15915494309189533576888;
+    const double g0 = gamma * c.dinfo.c0 * inv2pi, gd = gamma * c.dinfo.delta * inv2pi;
+    c128c_each(c, slot, kind, nullptr, [&](int r, unsigned k, double cd) {
+      const double turns = kind == DIAG_U32FX ? fma((double)k, gd, g0) : fma(cd, gd, g0);
+      double sn, co;
+      phase_sincos(turns, sn, co);
+      const double other = __shfl_xor_sync(0xffffffffu, v[r], 1);
+      v[r] = mult * fma(sgn * other, sn, v[r] * co);
+    });
+  }
+}
+
+__device__ __forceinline__ void op_reduce_c128c(const Ctx<double>& c, double (&v)[32], int slot, const uint4* dq,
+                                                double post, double (&acc)[5]) {
+  const int kind = c.dinfo.kind;
+  double s0 = 0, s1 = 0, s2 = 0, kmin = 1e300, kmax = -1e300;
+  c128c_each(c, slot, kind, dq, [&](int r, unsigned k, double cd) {
+    const double p = v[r] * v[r];
+    const double kv = kind == DIAG_F64 ? cd : (double)k;
+    s0 += p;
+    s1 = fma(p, kv, s1);
+    s2 = fma(p * kv, kv, s2);
+    if (p > 0.0) { kmin = fmin(kmin, kv); kmax = fmax(kmax, kv); }
+  });
+  const double sc = post * post;
+  acc[0] += sc * s0;
+  acc[1] += sc * s1;
+  acc[2] += sc * s2;
+  acc[3] = fmin(acc[3], kmin);
+  acc[4] = fmax(acc[4], kmax);
+}
+
 template <typename Elem>
 __device__ __forceinline__ void ctx_set_tile(Ctx<Elem>& c, unsigned long long id) {
   const TilePass& P = *c.P;
@@ -970,13 +1046,32 @@ tile_pass_kernel(const __grid_constant__ TilePass P, Elem* __restrict__ state, s
         if (cur.frame == 3) op_store8<Elem, CROSS>(c, v); else op_store<Elem, CROSS>(c, v, cur.frame);
         break;
       case TOP_INIT: op_init<Elem>(c, v, cur.frame); break;
-      case TOP_PHASE: op_phase<Elem, 0>(c, v, cur.arg); break;
+      case TOP_PHASE:
+        if constexpr (!ElemTraits<Elem>::IS_C64) {
+          if (cur.frame == 2) { op_phase_c128c<false>(c, v, cur.arg, nullptr); break; }
+        }
+        op_phase<Elem, 0>(c, v, cur.arg);
+        break;
       case TOP_ROUND: round_dynamic<Elem>(c, v, cur.arg); break;
       case TOP_WT: warp_transpose<Elem>(c, v); break;
       case TOP_BT: block_transpose<Elem>(c, v); break;
       case TOP_XT: xt_a_to_c<Elem>(c, v); break;
       case TOP_XTI: xt_c_to_a<Elem>(c, v); break;
-      case TOP_REDUCE: op_reduce<Elem, 0>(c, v, cur.arg); break;
+      case TOP_REDUCE:
+        if constexpr (!ElemTraits<Elem>::IS_C64) {
+          if (cur.frame == 2) {   // per-tile partials, like op_reduce
+            double acc[5] = {0.0, 0.0, 0.0, 1e300, -1e300};
+            op_reduce_c128c(c, v, cur.arg, nullptr, __ldg(c.phs + 2 * P.nphases), acc);
+            block_reduce5(acc, c.scratch);
+            if (threadIdx.x == 0) {
+              double* o = c.partials + ((size_t)c.point * c.ntiles + c.tile) * 5;
+              for (int i = 0; i < 5; i++) o[i] = acc[i];
+            }
+            break;
+          }
+        }
+        op_reduce<Elem, 0>(c, v, cur.arg);
+        break;
       default: break;
     }
   }
@@ -1192,6 +1287,9 @@ struct ProgExec {
           else op_init<Elem>(c, v, op.frame);
         } else op_init<Elem>(c, v, op.frame);
       }
+      else if constexpr (op.type == TOP_PHASE && !ElemTraits<Elem>::IS_C64 && op.frame == 2) {
+        op_phase_c128c<DK == DIAG_U8>(c, v, op.arg, REGS ? dq : nullptr);
+      }
       else if constexpr (op.type == TOP_PHASE) {
         if constexpr (REGS) {
           constexpr bool after_init = I > 0 && Prog::op(I > 0 ? I - 1 : 0).type == TOP_INIT;
@@ -1210,6 +1308,9 @@ struct ProgExec {
           if constexpr (Prog::op(0).frame == 3) stage_issue8<Elem, TileSmem<Elem>::STAGE_PAIRS, 16, false, CROSS>(c, c.id + c.stride);
           else stage_issue<Elem, TileSmem<Elem>::STAGE_PAIRS, 16, false, CROSS>(c, c.id + c.stride, Prog::op(0).frame);
         }
+      }
+      else if constexpr (op.type == TOP_REDUCE && !ElemTraits<Elem>::IS_C64 && op.frame == 2) {
+        op_reduce_c128c(c, v, op.arg, REGS ? dq : nullptr, (double)tau_s[11], acc);
       }
       else if constexpr (op.type == TOP_REDUCE) {
         if constexpr (REGS) op_reduce_u8_regs<Elem>(c, v, dq, tau_s[11], acc);
@@ -1291,9 +1392,11 @@ tile_prog_kernel(const __grid_constant__ TilePass P, Elem* __restrict__ state, s
       dq_issue(id + gridDim.x, it ^ 1);
     } else if constexpr (DK == DIAG_U8 && Prog::n_stream_ops() == 1) {
       // this tile's slice of the permuted diagonal: fetched now, consumed by the PHASE / REDUCE step
+      // (frame C streams carry one value per register, also for complex128)
+      constexpr int SAMP = Prog::op(so >= 0 ? so : 0).frame == 2 ? 32 : NAMP;
       const uint4* s4 = reinterpret_cast<const uint4*>(P.streams[Prog::op(so >= 0 ? so : 0).arg]);
 #pragma unroll
-      for (int j = 0; j < NAMP / 16; j++) dq[j] = __ldg(s4 + stream_chunk(c.tile, c.warp, c.lane, NAMP / 16, j));
+      for (int j = 0; j < SAMP / 16; j++) dq[j] = __ldg(s4 + stream_chunk(c.tile, c.warp, c.lane, SAMP / 16, j));
     }
     ProgExec<Elem, Prog, DK, CROSS, 0>::run(c, v, dq, acc);
   }

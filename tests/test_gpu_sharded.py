@@ -29,7 +29,7 @@ def _setup(n, world, dtype):
 
 
 @pytest.mark.parametrize("n,world,dtype", [(24, 2, "complex64"), (25, 4, "complex64"), (26, 8, "complex64"),
-                                           (23, 2, "complex128"), (20, 4, "complex64")])
+                                           (23, 2, "complex128"), (20, 4, "complex64"), (26, 2, "complex128")])
 def test_sharded_energy_matches_oracle_and_single_engine(n, world, dtype):
     eng, grp, c_oracle, diag, edges, lut = _setup(n, world, dtype)
     assert np.array_equal(grp.read_cost_diagonal(), diag), "sharded cost diagonal is not bit-exact"
