@@ -186,6 +186,20 @@ void ensure(T*& p, size_t& cap, size_t need_bytes, bool pinned_host = false) {
   cap = nb;
 }
 
+// Host <-> device copies of the set-up paths, ordered on the ENGINE's stream.  (The stream is non-blocking: a
+// plain cudaMemcpy from pageable memory may return while its DMA is still in flight, and a kernel launched on
+// the engine's stream right after it would not wait for it.)
+void h2d(Engine* h, void* dst, const void* src, size_t bytes) {
+  if (!bytes) return;
+  CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->stream));
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+}
+void d2h(Engine* h, void* dst, const void* src, size_t bytes) {
+  if (!bytes) return;
+  CUDA_OK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+}
+
 void ensure_state(Engine* h, size_t points) {
   if (h->state && h->state_points >= points) return;
   if (h->state) { cudaFree(h->state); h->state = nullptr; }
@@ -1224,12 +1238,12 @@ StateGen make_gen(Engine* h, int kind, int k, const double* vec, void** devvec) 
     if (!vec) fail("statevector pointer is null");
     CUDA_OK(cudaMalloc(devvec, h->N * h->amp_bytes));
     if (h->dtype == QAOA_DTYPE_C128) {
-      CUDA_OK(cudaMemcpy(*devvec, vec, h->N * 16, cudaMemcpyHostToDevice));
+      h2d(h, *devvec, vec, h->N * 16);
       to_sframe_kernel<double><<<grid_for(h->N, 256), 256, 0, h->stream>>>((double*)*devvec, h->N);
     } else {
       std::vector<float> tmp(h->N * 2);
       for (size_t i = 0; i < h->N * 2; i++) tmp[i] = (float)vec[i];
-      CUDA_OK(cudaMemcpy(*devvec, tmp.data(), h->N * 8, cudaMemcpyHostToDevice));
+      h2d(h, *devvec, tmp.data(), h->N * 8);
       to_sframe_kernel<float><<<grid_for(h->N, 256), 256, 0, h->stream>>>((float*)*devvec, h->N);
     }
     CUDA_OK(cudaGetLastError());
@@ -1396,10 +1410,10 @@ int qaoa_set_cost_maxkcut(qaoa_engine_t* h, int n_nodes, int n_edges, const int3
   CUDA_OK(cudaMalloc((void**)&dv, std::max(n_edges, 1) * 4));
   CUDA_OK(cudaMalloc((void**)&dwi, std::max(n_edges, 1) * 4));
   CUDA_OK(cudaMalloc((void**)&dw, std::max(n_edges, 1) * 8));
-  CUDA_OK(cudaMemcpy(du, u, n_edges * 4, cudaMemcpyHostToDevice));
-  CUDA_OK(cudaMemcpy(dv, v, n_edges * 4, cudaMemcpyHostToDevice));
-  CUDA_OK(cudaMemcpy(dwi, wi.data(), n_edges * 4, cudaMemcpyHostToDevice));
-  CUDA_OK(cudaMemcpy(dw, w, n_edges * 8, cudaMemcpyHostToDevice));
+  h2d(h, du, u, n_edges * 4);
+  h2d(h, dv, v, n_edges * 4);
+  h2d(h, dwi, wi.data(), n_edges * 4);
+  h2d(h, dw, w, n_edges * 8);
   D.eu = du; D.ev = dv; D.ewi = dwi; D.ew = dw;
   DiagInfo gi = h->dinfo;
   gen_maxkcut_kernel<<<grid_for(h->N, 256), 256, 0, h->stream>>>(D, h->N, h->x0, gi, h->diag);
@@ -1440,10 +1454,10 @@ int qaoa_set_cost_maxkcut_terms(qaoa_engine_t* h, int n_nodes, int n_edges, cons
     for (int e = 0; e < n_edges; e++) if (term_of_edge[e] == k) { su.push_back(u[e]); sv.push_back(v[e]); sw.push_back(w[e]); swi.push_back(0); }
     const int ne = (int)su.size();
     if (ne) {
-      CUDA_OK(cudaMemcpy(du, su.data(), ne * 4, cudaMemcpyHostToDevice));
-      CUDA_OK(cudaMemcpy(dv, sv.data(), ne * 4, cudaMemcpyHostToDevice));
-      CUDA_OK(cudaMemcpy(dwi, swi.data(), ne * 4, cudaMemcpyHostToDevice));
-      CUDA_OK(cudaMemcpy(dw, sw.data(), ne * 8, cudaMemcpyHostToDevice));
+      h2d(h, du, su.data(), ne * 4);
+      h2d(h, dv, sv.data(), ne * 4);
+      h2d(h, dwi, swi.data(), ne * 4);
+      h2d(h, dw, sw.data(), ne * 8);
     }
     D.n_edges = ne; D.eu = du; D.ev = dv; D.ewi = dwi; D.ew = dw;
     gen_maxkcut_kernel<<<grid_for(h->N, 256), 256, 0, h->stream>>>(D, h->N, h->x0, gi, h->d_terms + (size_t)k * h->N);
@@ -1483,8 +1497,8 @@ int qaoa_set_cost_qubo(qaoa_engine_t* h, int n, const double* Q, const double* c
   double *dd, *dM;
   CUDA_OK(cudaMalloc((void**)&dd, n * 8));
   CUDA_OK(cudaMalloc((void**)&dM, (size_t)n * n * 8));
-  CUDA_OK(cudaMemcpy(dd, d.data(), n * 8, cudaMemcpyHostToDevice));
-  CUDA_OK(cudaMemcpy(dM, M.data(), (size_t)n * n * 8, cudaMemcpyHostToDevice));
+  h2d(h, dd, d.data(), n * 8);
+  h2d(h, dM, M.data(), (size_t)n * n * 8);
   const int smem = (n + n * n) * 8;
   gen_qubo_kernel<<<grid_for(h->N, 256), 256, smem, h->stream>>>(n, dd, dM, b, h->N, h->x0, h->dinfo, h->diag);
   CUDA_OK(cudaGetLastError());
@@ -1512,7 +1526,7 @@ int qaoa_set_cost_diagonal(qaoa_engine_t* h, const double* diag) {
   CUDA_OK(cudaMalloc((void**)&tmp, std::min(chunk, h->N) * 8));
   for (size_t off = 0; off < h->N; off += chunk) {
     size_t cnt = std::min(chunk, h->N - off);
-    CUDA_OK(cudaMemcpy(tmp, diag + off, cnt * 8, cudaMemcpyHostToDevice));
+    h2d(h, tmp, diag + off, cnt * 8);
     quantise_diag_kernel<<<grid_for(cnt, 256), 256, 0, h->stream>>>(tmp, cnt, off, h->dinfo, h->diag);
     CUDA_OK(cudaGetLastError());
     CUDA_OK(cudaStreamSynchronize(h->stream));
@@ -1578,7 +1592,7 @@ int qaoa_set_mixer(qaoa_engine_t* h, int kind, const int32_t* pairs, int n_pairs
     }
     for (int i = 0; i < n_pairs; i++) if (pairs[2 * i] == pairs[2 * i + 1]) fail("XY pair with identical qubits");
     CUDA_OK(cudaMalloc((void**)&h->d_pairs, h->pairs.size() * 4));
-    CUDA_OK(cudaMemcpy(h->d_pairs, h->pairs.data(), h->pairs.size() * 4, cudaMemcpyHostToDevice));
+    h2d(h, h->d_pairs, h->pairs.data(), h->pairs.size() * 4);
   }
   if (kind == MIXER_GROVER) h->sub = make_gen(h, sub_kind, sub_k, sub_vec, &h->sub_vec);
   API_END(h)
@@ -1637,11 +1651,11 @@ int qaoa_read_statevector(qaoa_engine_t* h, double* out) {
   std::vector<double> re(N), im(N);
   if (h->dtype == QAOA_DTYPE_C128) {
     std::vector<double> tmp(2 * N);
-    CUDA_OK(cudaMemcpy(tmp.data(), h->state, N * 16, cudaMemcpyDeviceToHost));
+    d2h(h, tmp.data(), h->state, N * 16);
     for (size_t x = 0; x < N; x++) { re[x] = tmp[2 * x]; im[x] = tmp[2 * x + 1]; }
   } else {
     std::vector<float> tmp(2 * N);
-    CUDA_OK(cudaMemcpy(tmp.data(), h->state, N * 8, cudaMemcpyDeviceToHost));
+    d2h(h, tmp.data(), h->state, N * 8);
     for (size_t x = 0; x < N; x++) { re[x] = tmp[2 * x]; im[x] = tmp[2 * x + 1]; }
   }
   unsigned long long zm = 0;
@@ -1727,7 +1741,7 @@ int qaoa_extreme_solutions(qaoa_engine_t* h, int p, const double* angles, int n_
   if (cap < 1 || !out_idx || !out_count) fail("empty request");
   eval_keeping_state(h, p, angles, n_angles);
   double res[5];
-  CUDA_OK(cudaMemcpy(res, h->d_out, sizeof(res), cudaMemcpyDeviceToHost));
+  d2h(h, res, h->d_out, sizeof(res));
   const double target = want_max ? res[3] : res[2];
   unsigned long long* d_idx; unsigned* d_cnt;
   CUDA_OK(cudaMalloc((void**)&d_idx, (size_t)cap * 8));
@@ -1741,7 +1755,7 @@ int qaoa_extreme_solutions(qaoa_engine_t* h, int p, const double* angles, int n_
   CUDA_OK(cudaMemcpyAsync(&cnt, d_cnt, 4, cudaMemcpyDeviceToHost, h->stream));
   CUDA_OK(cudaStreamSynchronize(h->stream));
   const unsigned got = std::min<unsigned>(cnt, (unsigned)cap);
-  CUDA_OK(cudaMemcpy(out_idx, d_idx, (size_t)got * 8, cudaMemcpyDeviceToHost));
+  d2h(h, out_idx, d_idx, (size_t)got * 8);
   std::sort(out_idx, out_idx + got);
   *out_count = (int)cnt;
   if (out_cost) *out_cost = target;
@@ -1954,9 +1968,9 @@ int qaoa_debug_tile_program(qaoa_engine_t* h, int hb, const int32_t* ops, int no
       else { ((double*)hb_.data())[r * TILE_ROUND_REALS + s2] = k1; ((double*)hb_.data())[r * TILE_ROUND_REALS + 5 + s2] = -k1; }
     }
   ensure(h->d_params, h->params_cap, hb_.size() + 64);
-  CUDA_OK(cudaMemcpy(h->d_params, hb_.data(), hb_.size(), cudaMemcpyHostToDevice));
+  h2d(h, h->d_params, hb_.data(), hb_.size());
   double one = 1.0;
-  CUDA_OK(cudaMemcpy((char*)h->d_params + hb_.size(), &one, 8, cudaMemcpyHostToDevice));
+  h2d(h, (char*)h->d_params + hb_.size(), &one, 8);
   ensure(h->d_partials, h->partials_cap, 4096);
   const unsigned ntiles = 1u << (h->El - TILE_BITS);
   PlanPass pp;

@@ -499,3 +499,28 @@ def test_full_size_properties_n32():
     assert a[0] == pytest.approx(b2[0], rel=1e-5) and abs(a[4] - 1) < 1e-4
     lo, hi = E.cost_minmax()
     assert a[2] >= lo and a[3] <= hi and lo == 0
+
+
+@pytest.mark.parametrize("dtype", ["complex64", "complex128"])
+def test_uploads_are_ordered_before_the_kernels_that_use_them(dtype):
+    """Regression: host buffers (StateVector amplitudes, host diagonals) are uploaded on the engine's own stream.
+    A plain cudaMemcpy from pageable memory may return with its DMA in flight, and the engine's non-blocking stream
+    does not wait for it -- fresh engines, large vectors, results must be reproducible and match the oracle."""
+    n = 18
+    rng = np.random.default_rng(5)
+    diag = np.round(rng.uniform(0, 40, size=1 << n))
+    vec = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
+    vec /= np.linalg.norm(vec)
+    s = orc.dicke_state(n, 6)
+    spec = orc.Spec(n, diag, mixer=("grover", s), init=vec)
+    ang = np.array([0.05, 0.8, 0.03, -0.4])
+    ref = orc.energy(spec, ang)
+    for _ in range(4):
+        eng, E = _engine(n, dtype)
+        E.set_cost_diagonal(diag)
+        E.set_initial(eng.INIT_STATEVECTOR, vec=vec)
+        E.set_mixer(eng.MIXER_GROVER, sub_kind=eng.INIT_DICKE, sub_k=6)
+        out = E.energy(ang)
+        assert H.rel_err(out[0], ref[0]) < TOL[dtype], (out, ref)
+        assert np.array_equal(E.read_cost_diagonal(), diag)
+        E.close()
