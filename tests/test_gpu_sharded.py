@@ -89,3 +89,51 @@ def test_sharded_multiangle_dicke_and_cot_form():
     assert H.rel_err(got[0], ref[0]) < 1e-9, (got, ref)
     assert got[2] == ref[2] and got[3] == ref[3]
     grp.close()
+
+
+def test_randomised_sharded_configurations_against_the_single_engine():
+    """Seeded sweep: size, number of ranks, precision, cost kind, X / multi-angle X, Plus / Dicke, depth -- the
+    sharded register must reproduce the single-engine result (itself pinned to the oracle by test_gpu_parity)."""
+    from qaoa_b200 import engine as eng
+    from qaoa_b200.sharded import LocalShardGroup
+
+    rng = np.random.default_rng(4242)
+    for trial in range(14):
+        world = int(rng.choice([2, 4, 8]))
+        g = world.bit_length() - 1
+        dtype = ["complex64", "complex128"][trial % 2]
+        n = int(rng.integers(16 + g, 25))
+        p = int(rng.integers(1, 4))
+        grp = LocalShardGroup(n, world, dtype=dtype)
+        one = eng.Engine(n, dtype=dtype)
+        if rng.random() < 0.5:
+            edges, colors, table = H.regular_maxcut(n, seed=int(rng.integers(1 << 20)))
+            lut, _ = H.lut_from_table(table, 1)
+            for e in (grp, one):
+                e.set_cost_maxkcut(n, edges, 1, lut)
+        else:
+            Q, c, b = H.random_qubo(n, seed=int(rng.integers(1 << 20)))
+            for e in (grp, one):
+                e.set_cost_qubo(Q, c, b)
+        assert np.array_equal(grp.read_cost_diagonal(), one.read_cost_diagonal())
+        nb = 1
+        if rng.random() < 0.5:
+            nb = n
+            for e in (grp, one):
+                e.set_mixer(eng.MIXER_XMULTI)
+        if rng.random() < 0.4:
+            k = int(rng.integers(1, n))
+            for e in (grp, one):
+                e.set_initial(eng.INIT_DICKE, k)
+        lo, hi = one.cost_minmax()
+        ang = rng.uniform(-np.pi, np.pi, size=p * (1 + nb))
+        ang[0::(1 + nb)] *= 3.0 / max(1.0, hi - lo)
+        a, b = grp.energy(ang), one.energy(ang)
+        tol = TOL[dtype]
+        scale = max(abs(b[0]), 1e-2 * max(abs(lo), abs(hi), 1.0))
+        assert abs(a[0] - b[0]) < tol * scale, (trial, n, world, dtype, nb, a, b)
+        assert abs(a[4] - 1) < (2e-4 if dtype == "complex64" else 1e-10)
+        if dtype == "complex128":
+            assert a[2] == b[2] and a[3] == b[3]
+        grp.close()
+        one.close()
