@@ -143,6 +143,9 @@ int qaoa_shard_local_ptr(qaoa_engine_t* h, int which, void** out);
 int qaoa_shard_set_peers(qaoa_engine_t* h, int which, void* const* ptrs);
 int qaoa_shard_export(qaoa_engine_t* h, int which, unsigned char* handle64);
 int qaoa_shard_import(qaoa_engine_t* h, int which, const unsigned char* handles);
+/* Unmaps every peer buffer (call on all ranks, with a barrier before and after, before any rank destroys its
+ * engine: an exporter must not free memory that a peer still has mapped). */
+int qaoa_shard_close_peers(qaoa_engine_t* h);
 int qaoa_shard_begin(qaoa_engine_t* h, int p, const double* angles, int n_angles, int* n_passes);
 int qaoa_shard_pass_is_cross(qaoa_engine_t* h, int pass); /* 1 / 0, -1 on error */
 int qaoa_shard_run_pass(qaoa_engine_t* h, int pass);

@@ -1874,6 +1874,16 @@ int qaoa_shard_import(qaoa_engine_t* h, int which, const unsigned char* handles)
   API_END(h)
 }
 
+int qaoa_shard_close_peers(qaoa_engine_t* h) {
+  API_BEGIN(h)
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  close_peers(h, 0);
+  close_peers(h, 1);
+  free_streams(h);
+  invalidate(h);
+  API_END(h)
+}
+
 int qaoa_shard_begin(qaoa_engine_t* h, int p, const double* angles, int n_angles, int* n_passes) {
   API_BEGIN(h)
   if (h->world < 2) fail("not a sharded engine");

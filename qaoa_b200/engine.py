@@ -97,6 +97,7 @@ def load_library():
         "qaoa_shard_set_peers": (ctypes.c_int, [H, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]),
         "qaoa_shard_export": (ctypes.c_int, [H, ctypes.c_int, ctypes.c_char_p]),
         "qaoa_shard_import": (ctypes.c_int, [H, ctypes.c_int, ctypes.c_char_p]),
+        "qaoa_shard_close_peers": (ctypes.c_int, [H]),
         "qaoa_shard_begin": (ctypes.c_int, [H, ctypes.c_int, _c_double_p, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]),
         "qaoa_shard_pass_is_cross": (ctypes.c_int, [H, ctypes.c_int]),
         "qaoa_shard_run_pass": (ctypes.c_int, [H, ctypes.c_int]),
@@ -328,6 +329,9 @@ class Engine:
         blob = b"".join(handles)
         assert len(blob) == 64 * self.world
         self._check(self._lib.qaoa_shard_import(self._h, int(which), blob))
+
+    def shard_close_peers(self):
+        self._check(self._lib.qaoa_shard_close_peers(self._h))
 
     def shard_begin(self, angles):
         angles = np.ascontiguousarray(angles, dtype=np.float64).reshape(-1)

@@ -119,6 +119,8 @@ class LocalShardGroup(_ShardedSurface):
 
     def close(self):
         for e in self.engines:
+            e.shard_close_peers()
+        for e in self.engines:
             e.close()
 
 
@@ -192,4 +194,9 @@ class DistShardedEngine(_ShardedSurface):
         return self._all_reduce(eng.shard_finish())
 
     def close(self):
+        """collective: every rank unmaps its peers before any rank frees the buffers they map"""
+        self._barrier()
+        if hasattr(self.eng, "shard_close_peers"):
+            self.eng.shard_close_peers()
+        self._barrier()
         self.eng.close()
