@@ -48,7 +48,7 @@ const char* qaoa_last_error(qaoa_engine_t* h);
 const char* qaoa_global_error(void);
 
 /* Tunables / test hooks: "small_max_qubits", "keep_state", "batch_points", "batch_bytes",
- * "force_generic", "prefetch_dist", "persistent_ctas", "low_bits", "schedule", "time_passes". */
+ * "force_generic", "prefetch_dist", "persistent_ctas", "low_bits", "schedule", "feasible_subspace", "time_passes". */
 int qaoa_set_option(qaoa_engine_t* h, const char* key, double value);
 double qaoa_get_counter(qaoa_engine_t* h, const char* key); /* "launches", "bytes_alg", ... */
 

@@ -22,7 +22,7 @@ enum DiagKind : int {
   DIAG_F64 = 3     // cost(x) = f64                  (complex128 runs of real-valued costs)
 };
 
-enum InitKind : int { INIT_PLUS = 0, INIT_DICKE = 1, INIT_STATEVECTOR = 2 };
+enum InitKind : int { INIT_PLUS = 0, INIT_DICKE = 1, INIT_STATEVECTOR = 2, INIT_UNIFORM = 4 /* internal */ };
 enum MixerKind : int { MIXER_X = 0, MIXER_XMULTI = 1, MIXER_XY = 2, MIXER_GROVER = 3 };
 
 struct DiagInfo {

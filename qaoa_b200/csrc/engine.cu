@@ -99,6 +99,12 @@ struct Engine {
   // per-term gammas (MaxCutFree / MaxCutOrbit): n_gamma term diagonals, single-CTA path only
   int n_gamma = 1;
   double* d_terms = nullptr;
+  // feasible-subspace compression (Dicke + Grover over the same Dicke state): compact cost diagonal of the
+  // C(n,k) weight-k strings, built lazily; compact_k < 0: not built
+  void* diag_compact = nullptr;
+  size_t n_compact = 0;
+  int compact_k = -1;
+  int compact_enabled = 1;
   int n_init = 0;            // PlusParameterized: leading phase parameters of the angle vector (single-CTA path only)
 
   // mixer / init
@@ -227,6 +233,45 @@ void free_streams(Engine* h) {
 void invalidate(Engine* h) {
   h->plans.clear();
   h->last_valid = false;
+}
+
+int grid_for(size_t N, int threads);
+
+void drop_compact(Engine* h) {
+  if (h->diag_compact) { cudaFree(h->diag_compact); h->diag_compact = nullptr; }
+  h->compact_k = -1;
+  h->n_compact = 0;
+}
+
+// compact diagonal for weight k (see gather_feasible_kernel); false if compression does not apply / pay off
+bool ensure_compact(Engine* h, int k) {
+  if (!h->compact_enabled || h->keep_state || h->world > 1 || h->n > 62) return false;
+  if (h->compact_k == k) return true;
+  drop_compact(h);
+  std::vector<unsigned long long> binom((size_t)(h->n + 1) * (k + 1), 0ull);
+  for (int b = 0; b <= h->n; b++)
+    for (int j = 0; j <= k; j++) {
+      unsigned long long v = j == 0 ? 1ull : (b == 0 ? 0ull : binom[(size_t)(b - 1) * (k + 1) + j] + binom[(size_t)(b - 1) * (k + 1) + j - 1]);
+      binom[(size_t)b * (k + 1) + j] = v;
+    }
+  const unsigned long long M = binom[(size_t)h->n * (k + 1) + k];
+  if (M == 0 || M > h->N / 4) return false;   // little to gain
+  const int vb = diag_value_bytes(h->dinfo.kind);
+  unsigned long long* d_binom;
+  CUDA_OK(cudaMalloc((void**)&d_binom, binom.size() * 8));
+  h2d(h, d_binom, binom.data(), binom.size() * 8);
+  CUDA_OK(cudaMalloc(&h->diag_compact, (size_t)M * vb));
+  const int grid = grid_for((size_t)M, 256);
+  if (vb == 1) gather_feasible_kernel<1><<<grid, 256, 0, h->stream>>>((const unsigned char*)h->diag, (unsigned char*)h->diag_compact, (size_t)M, h->n, k, d_binom);
+  else if (vb == 4) gather_feasible_kernel<4><<<grid, 256, 0, h->stream>>>((const unsigned char*)h->diag, (unsigned char*)h->diag_compact, (size_t)M, h->n, k, d_binom);
+  else gather_feasible_kernel<8><<<grid, 256, 0, h->stream>>>((const unsigned char*)h->diag, (unsigned char*)h->diag_compact, (size_t)M, h->n, k, d_binom);
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  cudaFree(d_binom);
+  h->launches += 1;
+  h->n_compact = (size_t)M;
+  h->compact_k = k;
+  return true;
 }
 
 // sharding fields of a pass descriptor (see TilePass)
@@ -1009,11 +1054,23 @@ void run_elementwise_point(Engine* h, int p, const double* ang, double* d_out_po
   double* part_red = h->d_partials + (size_t)grid * 5;
   int grid_red = grid;
   real* st = (real*)h->state;
-  const double sweep = (double)h->N * h->amp_bytes;
-  const double dsz = (double)h->N * diag_value_bytes(h->dinfo.kind);
+  // Dicke initial state + Grover mixer over the same Dicke state: the register lives in the C(n,k)-dimensional
+  // feasible subspace (compact index = rank of the weight-k string); every entry of |s> is the same amplitude
+  size_t Nv = h->N;
+  const void* diagv = h->diag;
+  StateGen initv = h->init, subv = h->sub;
+  if (h->mixer == MIXER_GROVER && h->init.kind == INIT_DICKE && h->sub.kind == INIT_DICKE && h->init.k == h->sub.k &&
+      ensure_compact(h, h->init.k)) {
+    Nv = h->n_compact;
+    diagv = h->diag_compact;
+    initv.kind = INIT_UNIFORM;
+    subv.kind = INIT_UNIFORM;
+  }
+  const double sweep = (double)Nv * h->amp_bytes;
+  const double dsz = (double)Nv * diag_value_bytes(h->dinfo.kind);
   auto ew = [&](int flags, double gamma) {
-    elementwise_pass_kernel<real><<<grid, threads, 0, h->stream>>>(st, h->N, flags, h->init, h->sub, h->d_coefdot, gamma,
-                                                                  h->diag, h->dinfo, part_dot, part_red);
+    elementwise_pass_kernel<real><<<grid, threads, 0, h->stream>>>(st, Nv, flags, initv, subv, h->d_coefdot, gamma,
+                                                                  diagv, h->dinfo, part_dot, part_red);
     CUDA_OK(cudaGetLastError());
     h->launches += 1;
     h->bytes_alg += ((flags & EW_INIT) ? 0 : sweep) + ((flags & EW_STORE) ? sweep : 0) +
@@ -1204,6 +1261,7 @@ void energy_batch_body(Engine* h, int p, const double* angles, int n_angles, int
 
 void set_diag_common(Engine* h, int kind, double c0, double delta) {
   close_peers(h, 1);
+  drop_compact(h);
   if (h->d_terms) { cudaFree(h->d_terms); h->d_terms = nullptr; }
   h->n_gamma = 1;
   if (h->diag) { cudaFree(h->diag); h->diag = nullptr; }
@@ -1330,7 +1388,7 @@ int qaoa_destroy(qaoa_engine_t* h) {
   close_peers(h, 0);
   close_peers(h, 1);
   free_streams(h);
-  void* bufs[] = {h->state, h->diag, h->d_terms, h->d_pairs, h->init_vec, h->sub_vec, h->d_params, h->d_partials, h->d_out,
+  void* bufs[] = {h->state, h->diag, h->diag_compact, h->d_terms, h->d_pairs, h->init_vec, h->sub_vec, h->d_params, h->d_partials, h->d_out,
                   h->d_tables, h->d_gamsig, h->d_coefdot, h->d_angles};
   for (void* b : bufs) if (b) cudaFree(b);
   if (h->h_params) cudaFreeHost(h->h_params);
@@ -1357,6 +1415,7 @@ int qaoa_set_option(qaoa_engine_t* h, const char* key, double value) {
   else if (k == "time_passes") h->time_passes = value != 0;
   else if (k == "low_bits") { h->low_bits = (int)value; free_streams(h); invalidate(h); }
   else if (k == "schedule") { h->schedule = (int)value; free_streams(h); invalidate(h); }
+  else if (k == "feasible_subspace") h->compact_enabled = value != 0;
   else fail("unknown option: " + k);
   API_END(h)
 }
@@ -1368,6 +1427,7 @@ double qaoa_get_counter(qaoa_engine_t* h, const char* key) {
   if (k == "prog_launches") return h->prog_launches;
   if (k == "bytes_alg") return h->bytes_alg;
   if (k == "diag_kind") return h->dinfo.kind;
+  if (k == "compact_size") return (double)h->n_compact;
   if (k == "reset") {
     h->launches = 0; h->prog_launches = 0; h->bytes_alg = 0;
     for (int i = 0; i < PROG_COUNT; i++) { h->pass_ms[i] = 0; h->pass_count[i] = 0; h->pass_bytes[i] = 0; }

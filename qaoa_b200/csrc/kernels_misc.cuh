@@ -198,6 +198,11 @@ __device__ __forceinline__ void gen_amp(const StateGen& g, size_t x, real& re, r
     im = ((const real*)g.vec)[2 * x + 1];
     return;
   }
+  if (g.kind == INIT_UNIFORM) {   // compact feasible-subspace register: every entry carries the same amplitude
+    re = (real)g.amp;
+    im = (real)0;
+    return;
+  }
   int pc = __popcll((unsigned long long)x);
   re = (real)g.amp;
   im = (real)0;
@@ -761,5 +766,28 @@ collect_cost_equal_kernel(const real* __restrict__ st, const void* __restrict__ 
       const unsigned i = atomicAdd(count, 1u);
       if (i < cap) out[i] = (unsigned long long)x;
     }
+  }
+}
+
+// ============================================================================================
+// feasible-subspace compression: Dicke initial state + Grover mixer over the same Dicke state
+// ============================================================================================
+// |D^n_k> and the Grover reflection about it never leave the span of the C(n,k) weight-k basis states
+// (dicke_initialstate.py:38-56, grover_mixer.py:43-82), so the register is stored compactly: entry i is the
+// i-th weight-k bit string in the combinatorial number system (rank = sum_j C(b_j, j+1) over its set bits
+// b_0 < b_1 < ...).  This kernel gathers the cost of every feasible string into the compact diagonal
+// (raw representation, same DiagInfo).  binom[b * (k+1) + j] = C(b, j).
+template <int VALBYTES>
+__global__ void gather_feasible_kernel(const unsigned char* __restrict__ diag, unsigned char* __restrict__ out, size_t M,
+                                       int n, int k, const unsigned long long* __restrict__ binom) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < M; i += (size_t)gridDim.x * blockDim.x) {
+    unsigned long long r = i, x = 0;
+    int j = k;
+    for (int b = n - 1; b >= 0 && j > 0; b--) {
+      const unsigned long long cbj = binom[b * (k + 1) + j];
+      if (r >= cbj) { x |= 1ull << b; r -= cbj; j--; }
+    }
+#pragma unroll
+    for (int q = 0; q < VALBYTES; q++) out[i * VALBYTES + q] = diag[x * VALBYTES + q];
   }
 }

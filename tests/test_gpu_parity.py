@@ -128,7 +128,16 @@ def test_grover_dicke(n, k, dtype):
     for p in (1, 3):
         ang = rng.uniform(0, 2 * np.pi, size=2 * p)
         ang[::2] *= 0.05
-        _check(E.energy(ang), spec, ang, dtype, "grover p=%d" % p)
+        out = E.energy(ang)
+        _check(out, spec, ang, dtype, "grover p=%d" % p)
+        if n > 13:
+            # Dicke + Grover(Dicke) runs in the C(n,k)-dimensional feasible subspace; the full register must agree
+            from math import comb
+            assert E.counter("compact_size") == comb(n, k)
+            E.set_option("feasible_subspace", 0)
+            full = E.energy(ang)
+            E.set_option("feasible_subspace", 1)
+            assert H.rel_err(out[0], full[0]) < TOL[dtype] * 0.1 and out[2] == full[2] and out[3] == full[3]
 
 
 @pytest.mark.parametrize("dtype", ["complex64", "complex128"])
