@@ -29,8 +29,19 @@ std::string g_global_error;
     }                                                                                       \
   } while (0)
 
-struct Fail {
-  std::string msg;
+// scratch device allocation of a set-up call: released on every exit path (a failed CUDA call throws)
+struct DevTmp {
+  void* p = nullptr;
+  DevTmp() {}
+  explicit DevTmp(size_t bytes) { alloc(bytes); }
+  void alloc(size_t bytes) {
+    cudaError_t e = cudaMalloc(&p, bytes ? bytes : 16);
+    if (e != cudaSuccess) { p = nullptr; throw std::string("cudaMalloc of a temporary buffer failed: ") + cudaGetErrorString(e); }
+  }
+  ~DevTmp() { if (p) cudaFree(p); }
+  DevTmp(const DevTmp&) = delete;
+  DevTmp& operator=(const DevTmp&) = delete;
+  template <typename T> T* as() const { return (T*)p; }
 };
 [[noreturn]] void fail(const std::string& m) { throw std::string(m); }
 
@@ -257,8 +268,8 @@ bool ensure_compact(Engine* h, int k) {
   const unsigned long long M = binom[(size_t)h->n * (k + 1) + k];
   if (M == 0 || M > h->N / 4) return false;   // little to gain
   const int vb = diag_value_bytes(h->dinfo.kind);
-  unsigned long long* d_binom;
-  CUDA_OK(cudaMalloc((void**)&d_binom, binom.size() * 8));
+  DevTmp t_binom(binom.size() * 8);
+  unsigned long long* d_binom = t_binom.as<unsigned long long>();
   h2d(h, d_binom, binom.data(), binom.size() * 8);
   CUDA_OK(cudaMalloc(&h->diag_compact, (size_t)M * vb));
   const int grid = grid_for((size_t)M, 256);
@@ -267,7 +278,6 @@ bool ensure_compact(Engine* h, int k) {
   else gather_feasible_kernel<8><<<grid, 256, 0, h->stream>>>((const unsigned char*)h->diag, (unsigned char*)h->diag_compact, (size_t)M, h->n, k, d_binom);
   CUDA_OK(cudaGetLastError());
   CUDA_OK(cudaStreamSynchronize(h->stream));
-  cudaFree(d_binom);
   h->launches += 1;
   h->n_compact = (size_t)M;
   h->compact_k = k;
@@ -1466,10 +1476,8 @@ int qaoa_set_cost_maxkcut(qaoa_engine_t* h, int n_nodes, int n_edges, const int3
   std::vector<int> wi(std::max(n_edges, 1));
   // the U8 path stores cost - c0 with c0 = sum of the negative weights
   for (int e = 0; e < n_edges; e++) wi[e] = integer ? (int)w[e] : 0;
-  CUDA_OK(cudaMalloc((void**)&du, std::max(n_edges, 1) * 4));
-  CUDA_OK(cudaMalloc((void**)&dv, std::max(n_edges, 1) * 4));
-  CUDA_OK(cudaMalloc((void**)&dwi, std::max(n_edges, 1) * 4));
-  CUDA_OK(cudaMalloc((void**)&dw, std::max(n_edges, 1) * 8));
+  DevTmp t_u(std::max(n_edges, 1) * 4), t_v(std::max(n_edges, 1) * 4), t_wi(std::max(n_edges, 1) * 4), t_w(std::max(n_edges, 1) * 8);
+  du = t_u.as<int>(); dv = t_v.as<int>(); dwi = t_wi.as<int>(); dw = t_w.as<double>();
   h2d(h, du, u, n_edges * 4);
   h2d(h, dv, v, n_edges * 4);
   h2d(h, dwi, wi.data(), n_edges * 4);
@@ -1480,7 +1488,6 @@ int qaoa_set_cost_maxkcut(qaoa_engine_t* h, int n_nodes, int n_edges, const int3
   CUDA_OK(cudaGetLastError());
   CUDA_OK(cudaStreamSynchronize(h->stream));
   h->launches += 1;
-  cudaFree(du); cudaFree(dv); cudaFree(dwi); cudaFree(dw);
   API_END(h)
 }
 
@@ -1503,10 +1510,8 @@ int qaoa_set_cost_maxkcut_terms(qaoa_engine_t* h, int n_nodes, int n_edges, cons
   D.bits = bits_per_node; D.n_free = n_nodes - (fixed_node ? 1 : 0); D.fixed_colour = fixed_colour;
   for (int i = 0; i < (1 << bits_per_node); i++) D.lut[i] = lut[i];
   int *du, *dv, *dwi; double* dw;
-  CUDA_OK(cudaMalloc((void**)&du, std::max(n_edges, 1) * 4));
-  CUDA_OK(cudaMalloc((void**)&dv, std::max(n_edges, 1) * 4));
-  CUDA_OK(cudaMalloc((void**)&dwi, std::max(n_edges, 1) * 4));
-  CUDA_OK(cudaMalloc((void**)&dw, std::max(n_edges, 1) * 8));
+  DevTmp t_u(std::max(n_edges, 1) * 4), t_v(std::max(n_edges, 1) * 4), t_wi(std::max(n_edges, 1) * 4), t_w(std::max(n_edges, 1) * 8);
+  du = t_u.as<int>(); dv = t_v.as<int>(); dwi = t_wi.as<int>(); dw = t_w.as<double>();
   DiagInfo gi{DIAG_F64, 0.0, 1.0};
   for (int k = 0; k < n_terms; k++) {
     std::vector<int> su, sv, swi;
@@ -1525,7 +1530,6 @@ int qaoa_set_cost_maxkcut_terms(qaoa_engine_t* h, int n_nodes, int n_edges, cons
     CUDA_OK(cudaStreamSynchronize(h->stream));
     h->launches += 1;
   }
-  cudaFree(du); cudaFree(dv); cudaFree(dwi); cudaFree(dw);
   h->n_gamma = n_terms;
   invalidate(h);
   }
@@ -1555,8 +1559,8 @@ int qaoa_set_cost_qubo(qaoa_engine_t* h, int n, const double* Q, const double* c
   choose_kind(h, -hi, -lo, integer, &kind, &c0, &delta);
   set_diag_common(h, kind, c0, delta);
   double *dd, *dM;
-  CUDA_OK(cudaMalloc((void**)&dd, n * 8));
-  CUDA_OK(cudaMalloc((void**)&dM, (size_t)n * n * 8));
+  DevTmp t_d(n * 8), t_M((size_t)n * n * 8);
+  dd = t_d.as<double>(); dM = t_M.as<double>();
   h2d(h, dd, d.data(), n * 8);
   h2d(h, dM, M.data(), (size_t)n * n * 8);
   const int smem = (n + n * n) * 8;
@@ -1564,7 +1568,6 @@ int qaoa_set_cost_qubo(qaoa_engine_t* h, int n, const double* Q, const double* c
   CUDA_OK(cudaGetLastError());
   CUDA_OK(cudaStreamSynchronize(h->stream));
   h->launches += 1;
-  cudaFree(dd); cudaFree(dM);
   API_END(h)
 }
 
@@ -1582,8 +1585,8 @@ int qaoa_set_cost_diagonal(qaoa_engine_t* h, const double* diag) {
   choose_kind(h, lo, hi, integer, &kind, &c0, &delta);
   set_diag_common(h, kind, c0, delta);
   const size_t chunk = (size_t)1 << 24;
-  double* tmp;
-  CUDA_OK(cudaMalloc((void**)&tmp, std::min(chunk, h->N) * 8));
+  DevTmp t_tmp(std::min(chunk, h->N) * 8);
+  double* tmp = t_tmp.as<double>();
   for (size_t off = 0; off < h->N; off += chunk) {
     size_t cnt = std::min(chunk, h->N - off);
     h2d(h, tmp, diag + off, cnt * 8);
@@ -1592,7 +1595,6 @@ int qaoa_set_cost_diagonal(qaoa_engine_t* h, const double* diag) {
     CUDA_OK(cudaStreamSynchronize(h->stream));
     h->launches += 1;
   }
-  cudaFree(tmp);
   API_END(h)
 }
 
@@ -1601,8 +1603,8 @@ int qaoa_read_cost_diagonal(qaoa_engine_t* h, size_t offset, size_t count, doubl
   if (h->dinfo.kind == DIAG_NONE) fail("no cost function set");
   if (offset + count > h->N) fail("range outside the diagonal");
   const size_t chunk = (size_t)1 << 24;
-  double* tmp;
-  CUDA_OK(cudaMalloc((void**)&tmp, std::min(chunk, std::max<size_t>(count, 1)) * 8));
+  DevTmp t_tmp(std::min(chunk, std::max<size_t>(count, 1)) * 8);
+  double* tmp = t_tmp.as<double>();
   for (size_t o = 0; o < count; o += chunk) {
     size_t cnt = std::min(chunk, count - o);
     read_diag_kernel<<<grid_for(cnt, 256), 256, 0, h->stream>>>(h->diag, h->dinfo, offset + o, cnt, tmp);
@@ -1611,7 +1613,6 @@ int qaoa_read_cost_diagonal(qaoa_engine_t* h, size_t offset, size_t count, doubl
     CUDA_OK(cudaStreamSynchronize(h->stream));
     h->launches += 1;
   }
-  cudaFree(tmp);
   API_END(h)
 }
 
@@ -1758,8 +1759,8 @@ int qaoa_sample(qaoa_engine_t* h, int p, const double* angles, int n_angles, int
   eval_keeping_state(h, p, angles, n_angles);
   const int chunk_log2 = std::min(h->n, 16);
   const size_t nchunks = (h->N + ((size_t)1 << chunk_log2) - 1) >> chunk_log2;
-  double* d_sums;
-  CUDA_OK(cudaMalloc((void**)&d_sums, nchunks * 8));
+  DevTmp t_sums(nchunks * 8);
+  double* d_sums = t_sums.as<double>();
   if (h->dtype == QAOA_DTYPE_C64) chunk_prob_kernel<float><<<(unsigned)nchunks, 256, 0, h->stream>>>((const float*)h->state, h->N, chunk_log2, d_sums);
   else chunk_prob_kernel<double><<<(unsigned)nchunks, 256, 0, h->stream>>>((const double*)h->state, h->N, chunk_log2, d_sums);
   CUDA_OK(cudaGetLastError());
@@ -1779,10 +1780,10 @@ int qaoa_sample(qaoa_engine_t* h, int p, const double* angles, int n_angles, int
     chunk_of[i] = (unsigned)c;
     resid[i] = t - (c ? cum[c - 1] : 0.0);
   }
-  unsigned* d_chunk; double* d_resid; unsigned long long* d_out;
-  CUDA_OK(cudaMalloc((void**)&d_chunk, (size_t)shots * 4));
-  CUDA_OK(cudaMalloc((void**)&d_resid, (size_t)shots * 8));
-  CUDA_OK(cudaMalloc((void**)&d_out, (size_t)shots * 8));
+  DevTmp t_chunk((size_t)shots * 4), t_resid((size_t)shots * 8), t_out((size_t)shots * 8);
+  unsigned* d_chunk = t_chunk.as<unsigned>();
+  double* d_resid = t_resid.as<double>();
+  unsigned long long* d_out = t_out.as<unsigned long long>();
   CUDA_OK(cudaMemcpyAsync(d_chunk, chunk_of.data(), (size_t)shots * 4, cudaMemcpyHostToDevice, h->stream));
   CUDA_OK(cudaMemcpyAsync(d_resid, resid.data(), (size_t)shots * 8, cudaMemcpyHostToDevice, h->stream));
   if (h->dtype == QAOA_DTYPE_C64) sample_locate_kernel<float><<<shots, 256, 0, h->stream>>>((const float*)h->state, h->N, chunk_log2, d_chunk, d_resid, d_out);
@@ -1791,7 +1792,6 @@ int qaoa_sample(qaoa_engine_t* h, int p, const double* angles, int n_angles, int
   CUDA_OK(cudaMemcpyAsync(out_idx, d_out, (size_t)shots * 8, cudaMemcpyDeviceToHost, h->stream));
   CUDA_OK(cudaStreamSynchronize(h->stream));
   h->launches += 2;
-  cudaFree(d_sums); cudaFree(d_chunk); cudaFree(d_resid); cudaFree(d_out);
   API_END(h)
 }
 
@@ -1803,9 +1803,9 @@ int qaoa_extreme_solutions(qaoa_engine_t* h, int p, const double* angles, int n_
   double res[5];
   d2h(h, res, h->d_out, sizeof(res));
   const double target = want_max ? res[3] : res[2];
-  unsigned long long* d_idx; unsigned* d_cnt;
-  CUDA_OK(cudaMalloc((void**)&d_idx, (size_t)cap * 8));
-  CUDA_OK(cudaMalloc((void**)&d_cnt, 4));
+  DevTmp t_idx((size_t)cap * 8), t_cnt(4);
+  unsigned long long* d_idx = t_idx.as<unsigned long long>();
+  unsigned* d_cnt = t_cnt.as<unsigned>();
   CUDA_OK(cudaMemsetAsync(d_cnt, 0, 4, h->stream));
   const int grid = grid_for(h->N, 256);
   if (h->dtype == QAOA_DTYPE_C64) collect_cost_equal_kernel<float><<<grid, 256, 0, h->stream>>>((const float*)h->state, h->diag, h->dinfo, h->N, target, (unsigned)cap, d_idx, d_cnt);
@@ -1820,7 +1820,6 @@ int qaoa_extreme_solutions(qaoa_engine_t* h, int p, const double* angles, int n_
   *out_count = (int)cnt;
   if (out_cost) *out_cost = target;
   h->launches += 1;
-  cudaFree(d_idx); cudaFree(d_cnt);
   API_END(h)
 }
 
@@ -1831,8 +1830,8 @@ int qaoa_cost_distribution(qaoa_engine_t* h, int p, const double* angles, int n_
   if (h->dinfo.kind != DIAG_U8) fail("cost distribution needs integer-valued costs with a range <= 255");
   eval_keeping_state(h, p, angles, n_angles);
   const int grid = grid_for(h->N, 256);
-  double* d_part;
-  CUDA_OK(cudaMalloc((void**)&d_part, (size_t)grid * 256 * 8));
+  DevTmp t_part((size_t)grid * 256 * 8);
+  double* d_part = t_part.as<double>();
   if (h->dtype == QAOA_DTYPE_C64) cost_hist_kernel<float><<<grid, 256, 0, h->stream>>>((const float*)h->state, (const uint8_t*)h->diag, h->N, d_part);
   else cost_hist_kernel<double><<<grid, 256, 0, h->stream>>>((const double*)h->state, (const uint8_t*)h->diag, h->N, d_part);
   CUDA_OK(cudaGetLastError());
@@ -1851,7 +1850,6 @@ int qaoa_cost_distribution(qaoa_engine_t* h, int p, const double* angles, int n_
   if (c0) *c0 = h->dinfo.c0;
   if (delta) *delta = h->dinfo.delta;
   h->launches += 1;
-  cudaFree(d_part);
   API_END(h)
 }
 
