@@ -69,11 +69,13 @@ struct PlanPass {
   size_t phs_offset = 0;  // doubles, per point block
   int prog = PROG_GENERIC;
   bool cross = false;
+  bool zshape = false;    // pass over the low tile shape of a symmetric register (virtual tile bit 13)
 };
 struct Shape {
   int pos[TILE_BITS];
   std::vector<int> freepos;
   bool cross = false;   // contains element bits owned by other ranks (sharded registers)
+  bool zshape = false;  // low tile of a symmetric register: pos[13] is the virtual top qubit
 };
 struct Plan {
   int p = 0;
@@ -81,6 +83,7 @@ struct Plan {
   std::vector<PlanPass> passes;
   size_t tau_per_point = 0;  // reals over all passes
   size_t phs_per_point = 0;  // doubles over all passes
+  bool z2 = false;           // symmetric register: 2^(n-1) stored amplitudes (tile_kernel.cuh)
 };
 
 struct Engine {
@@ -145,6 +148,9 @@ struct Engine {
   int persistent_ctas = 148; // CTAs of the persistent pass kernels (one per SM)
   int low_bits = 0;          // 0: automatic choice between 4 and 5 low tile bits
   int schedule = 0;          // 0: automatic, 1: classic (interior + boundary), 2: balanced (mid + bound2)
+  int z2_enabled = 1;        // option "symmetric": store half the register when the problem has the global bit-flip symmetry
+  int cost_symmetric = -1;   // cost(x) == cost(~x) for every x: -1 unknown, 0 no, 1 yes (checked on the device)
+  size_t state_bytes = 0;
   double* d_partials = nullptr; size_t partials_cap = 0;
   double* d_out = nullptr; size_t out_cap = 0;
   double* h_out = nullptr; size_t hout_cap = 0;
@@ -217,10 +223,13 @@ void d2h(Engine* h, void* dst, const void* src, size_t bytes) {
   CUDA_OK(cudaStreamSynchronize(h->stream));
 }
 
-void ensure_state(Engine* h, size_t points) {
-  if (h->state && h->state_points >= points) return;
-  if (h->state) { cudaFree(h->state); h->state = nullptr; }
-  CUDA_OK(cudaMalloc(&h->state, h->N * h->amp_bytes * points));
+void ensure_state(Engine* h, size_t points, size_t amps_per_point = 0) {
+  if (!amps_per_point) amps_per_point = h->N;
+  const size_t need = amps_per_point * h->amp_bytes * points;
+  if (h->state && h->state_bytes >= need) return;
+  if (h->state) { cudaFree(h->state); h->state = nullptr; h->state_bytes = 0; }
+  CUDA_OK(cudaMalloc(&h->state, need));
+  h->state_bytes = need;
   h->state_points = points;
 }
 
@@ -282,6 +291,38 @@ bool ensure_compact(Engine* h, int k) {
   h->n_compact = (size_t)M;
   h->compact_k = k;
   return true;
+}
+
+// Symmetric (Z2) registers (tile_kernel.cuh): MaxCut-like costs with cost(x) = cost(~x), X / multi-angle X
+// mixer, |+> initial state, even n.  The tile path then stores the half register with the top qubit = 0.
+bool cost_is_symmetric(Engine* h);
+bool use_z2(Engine* h) {
+  if (!h->z2_enabled || h->world > 1 || h->keep_state || (h->n & 1)) return false;
+  if (h->mixer != MIXER_X && h->mixer != MIXER_XMULTI) return false;
+  if (h->init.kind != INIT_PLUS || h->n_gamma != 1 || h->n_init != 0) return false;
+  if (h->E - 1 < TILE_BITS + 1) return false;          // the half register still needs a high tile shape
+  return cost_is_symmetric(h);
+}
+inline int plan_el(const Engine* h, const Plan& pl) { return pl.z2 ? h->El - 1 : h->El; }          // stored element bits
+inline size_t plan_amps(const Engine* h, const Plan& pl) { return pl.z2 ? h->N >> 1 : h->N; }      // stored amplitudes
+inline unsigned plan_ntiles(const Engine* h, const Plan& pl) { return 1u << (plan_el(h, pl) - TILE_BITS); }
+
+bool cost_is_symmetric(Engine* h) {
+  if (h->cost_symmetric >= 0) return h->cost_symmetric == 1;
+  if (h->dinfo.kind == DIAG_NONE || !h->diag || h->world > 1) return false;
+  DevTmp t_flag(sizeof(int));
+  int* d_flag = t_flag.as<int>();
+  CUDA_OK(cudaMemsetAsync(d_flag, 0, sizeof(int), h->stream));
+  const int grid = grid_for(h->N / 2, 256);
+  if (h->dinfo.kind == DIAG_U8) diag_symmetry_kernel<uint8_t><<<grid, 256, 0, h->stream>>>((const uint8_t*)h->diag, h->N, d_flag);
+  else if (h->dinfo.kind == DIAG_U32FX) diag_symmetry_kernel<uint32_t><<<grid, 256, 0, h->stream>>>((const uint32_t*)h->diag, h->N, d_flag);
+  else diag_symmetry_kernel<unsigned long long><<<grid, 256, 0, h->stream>>>((const unsigned long long*)h->diag, h->N, d_flag);
+  CUDA_OK(cudaGetLastError());
+  h->launches += 1;
+  int flag = 1;
+  d2h(h, &flag, d_flag, sizeof(int));
+  h->cost_symmetric = flag ? 0 : 1;
+  return h->cost_symmetric == 1;
 }
 
 // sharding fields of a pass descriptor (see TilePass)
@@ -357,7 +398,9 @@ void build_balanced(Engine* h, int p, Plan& pl) {
     tp.qshift = qs;
     tp.init_kind = h->init.kind;
     tp.dicke_k = h->init.k;
-    tp.init_amp = h->init.amp;
+    tp.init_amp = h->init.amp * (pl.z2 ? sqrt(2.0) : 1.0);   // the stored half carries the whole norm
+    b.pp.zshape = b.sh->zshape;
+    if (b.sh->zshape) { tp.zbit = E - 1; tp.zsign = ((h->n - 2) / 2) % 2 ? -1 : 1; }
     return b;
   };
   auto push = [&](Builder& b, int type, int fr, int arg, int mask) {
@@ -378,7 +421,8 @@ void build_balanced(Engine* h, int p, Plan& pl) {
       const int eb = b.sh->pos[reg_tile_bit(kind, s)];
       if (eb >= qs && !done[layer][eb]) { rs.ebit[s] = eb; done[layer][eb] = 1; }
     }
-    push(b, TOP_ROUND, 0, (int)b.pp.rounds.size(), mask);
+    // frame field of a ROUND: 1 = slot 4 is the mirror pairing of a symmetric register (frame A of the low tile)
+    push(b, TOP_ROUND, (b.sh->zshape && kind == 0 && ((mask >> 4) & 1)) ? 1 : 0, (int)b.pp.rounds.size(), mask);
     b.pp.rounds.push_back(rs);
   };
   auto phase = [&](Builder& b, int layer, int shape, int frame) {
@@ -492,13 +536,48 @@ Plan build_plan(Engine* h, int p) {
   // does not cost an extra pass per layer.
   // Sharded registers: the local shapes tile the El bits of the shard exactly like an unsharded
   // register of that size; the rank bits get a shape of their own (appended below).
-  const int EL = h->El;
+  pl.z2 = use_z2(h);
+  const int EL = plan_el(h, pl);
+  if (pl.z2) {
+    // Symmetric register: EL = E - 1 real element bits.  Shape 0 = 13 real low bits + the virtual top qubit
+    // (element bit E - 1); its tiles enumerate the free bits 13 .. EL-2 (the top real bit is 0 in the plain
+    // half of a tile and 1 in its mirror image).  The high shapes tile the real bits 13 .. EL-1.
+    const int nHz = EL - 13;
+    const int m4 = (nHz + 9) / 10, m5 = (nHz + 8) / 9;
+    int clow = (m5 == m4) ? 5 : 4;
+    if (h->low_bits == 4 || h->low_bits == 5) clow = h->low_bits;
+    const int hper = TILE_BITS - clow;
+    Shape s0;
+    for (int j = 0; j < 13; j++) s0.pos[j] = j;
+    s0.pos[13] = E - 1;
+    for (int b = 13; b < EL - 1; b++) s0.freepos.push_back(b);
+    s0.zshape = true;
+    pl.shapes.push_back(s0);
+    const int mh = (nHz + hper - 1) / hper;
+    for (int i = 0; i < mh; i++) {
+      std::vector<int> bits;
+      for (int b = 0; b < clow; b++) bits.push_back(b);
+      int lo = 13 + hper * i, hi = std::min(EL, lo + hper);
+      std::vector<int> own;
+      for (int b = lo; b < hi; b++) own.push_back(b);
+      int padb = lo - 1;
+      while ((int)own.size() < hper) { own.push_back(padb); padb--; }
+      for (int b : own) bits.push_back(b);
+      std::sort(bits.begin(), bits.end());
+      Shape s;
+      for (int j = 0; j < TILE_BITS; j++) s.pos[j] = bits[j];
+      for (int b = 0; b < EL; b++)
+        if (!std::binary_search(bits.begin(), bits.end(), b)) s.freepos.push_back(b);
+      pl.shapes.push_back(s);
+    }
+  }
   const int m4 = std::max(1, (EL - 4 + 9) / 10), m5 = std::max(1, (EL - 5 + 8) / 9);
   int clow = (m5 == m4 && EL >= 15) ? 5 : 4;
   if (h->low_bits == 4 || h->low_bits == 5) clow = h->low_bits;
+  if (pl.z2) clow = pl.shapes[1].pos[4] == 4 ? 5 : 4;
   const int hper = TILE_BITS - clow;
   const int nH = EL - clow;
-  const int m_local = std::max(1, (nH + hper - 1) / hper);
+  const int m_local = pl.z2 ? 0 : std::max(1, (nH + hper - 1) / hper);
   for (int i = 0; i < m_local; i++) {
     std::vector<int> bits;
     for (int b = 0; b < clow; b++) bits.push_back(b);
@@ -569,7 +648,9 @@ Plan build_plan(Engine* h, int p) {
     tp.qshift = qs;
     tp.init_kind = h->init.kind;
     tp.dicke_k = h->init.k;
-    tp.init_amp = h->init.amp;
+    tp.init_amp = h->init.amp * (pl.z2 ? sqrt(2.0) : 1.0);
+    pp.zshape = sh.zshape;
+    if (sh.zshape) { tp.zbit = E - 1; tp.zsign = ((h->n - 2) / 2) % 2 ? -1 : 1; }
     int frame = 0;
     auto push = [&](int type, int fr, int arg, int mask) {
       if (tp.nops >= TILE_MAX_OPS) fail("tile pass program overflow");
@@ -619,7 +700,7 @@ Plan build_plan(Engine* h, int p) {
             done[cur][sh.pos[rb[s]]] = 1;
           }
         }
-        push(TOP_ROUND, 0, (int)pp.rounds.size(), masks[step]);
+        push(TOP_ROUND, (sh.zshape && step != 1 && frame == 0 && ((masks[step] >> 4) & 1)) ? 1 : 0, (int)pp.rounds.size(), masks[step]);
         pp.rounds.push_back(rs);
         if (step == 0) push(TOP_WT, 0, 0, 0);
         if (step == 1) { push(TOP_BT, 0, 0, 0); frame ^= 1; }
@@ -665,8 +746,10 @@ Plan build_plan(Engine* h, int p) {
   }
   // complex64: a last pass of the classic FINAL form (high cover through WT + BT, fused reduction)
   // becomes the one-transpose FINAL2 / FINAL2L4 form (p = 1 landscapes at 2-shape sizes: FIRST + this)
+  // (the mirrored low tile of a symmetric register has no A4 / C4 addressing: with 4 low bits its last pass keeps
+  // the classic FINAL form, whose cover reaches all ten bits t4..t13)
   if (h->dtype == QAOA_DTYPE_C64 && !h->keep_state && !pl.passes.empty() && pl.passes.back().prog == PROG_FINAL &&
-      !pl.passes.back().cross) {
+      !pl.passes.back().cross && !(pl.passes.back().zshape && clow == 4)) {
     PlanPass& pp = pl.passes.back();
     TilePass& tp = pp.tp;
     std::vector<char> want(E, 0);
@@ -689,7 +772,7 @@ Plan build_plan(Engine* h, int p) {
         const int eb = tp.pos[frame_reg_bit(frame, k)];
         if (((mask >> k) & 1) && want[eb]) { rs.ebit[k] = eb; want[eb] = 0; }
       }
-      push(TOP_ROUND, 0, (int)pp.rounds.size(), mask);
+      push(TOP_ROUND, (pp.zshape && frame == 0 && ((mask >> 4) & 1)) ? 1 : 0, (int)pp.rounds.size(), mask);
       pp.rounds.push_back(rs);
     };
     push(TOP_LOAD, fio, 0, 0);
@@ -709,14 +792,14 @@ Plan build_plan(Engine* h, int p) {
 }
 
 void* get_stream(Engine* h, const Plan& pl, int shape, int frame) {
-  auto key = std::make_pair(shape, frame);
+  auto key = std::make_pair(shape + (pl.z2 ? 100 : 0), frame);
   auto it = h->streams.find(key);
   if (it != h->streams.end()) return it->second;
   const int vb = diag_value_bytes(h->dinfo.kind);
   void* s = nullptr;
   // complex128 in frame C: one value per REGISTER (the re / im halves of an amplitude sit in neighbouring lanes)
   const bool per_reg = h->dtype == QAOA_DTYPE_C128 && frame == 2;
-  CUDA_OK(cudaMalloc(&s, h->N * vb * (per_reg ? 2 : 1)));
+  CUDA_OK(cudaMalloc(&s, plan_amps(h, pl) * vb * (per_reg ? 2 : 1)));
   TilePass tp;
   memset(&tp, 0, sizeof(tp));
   const Shape& sh = pl.shapes[shape];
@@ -725,10 +808,11 @@ void* get_stream(Engine* h, const Plan& pl, int shape, int frame) {
   for (int j = 0; j < tp.nfree; j++) tp.freepos[j] = sh.freepos[j];
   if (!tilepass_set_free_runs(tp)) fail("tile shape with more than two runs of free bits");
   tp.qshift = h->qshift;
+  if (sh.zshape) tp.zbit = h->E - 1;
   const int cross = sh.cross ? 1 : 0;
   if (cross && !h->peers_diag_set) fail("sharded engine: peer cost-diagonal pointers have not been set");
   shard_fill(h, tp, sh.cross);
-  const unsigned ntiles = 1u << (h->El - TILE_BITS);
+  const unsigned ntiles = plan_ntiles(h, pl);
   const int namp = (h->dtype == QAOA_DTYPE_C64 || per_reg) ? 32 : 16;
   if (frame >= 3 && namp != 32) fail("frame A4 / C4 streams exist for complex64 only");
   if (vb == 1) make_stream_kernel<1><<<ntiles, TILE_THREADS, 0, h->stream>>>(tp, frame, namp, cross, (const unsigned char*)h->diag, (unsigned char*)s);
@@ -853,10 +937,14 @@ int launch_pass(Engine* h, const PlanPass& pp, bool use_prog, unsigned ntiles, i
   if (cross && prog != PROG_BOUNDX && prog != PROG_FINALX) prog = PROG_GENERIC;
   if (!cross && (prog == PROG_BOUNDX || prog == PROG_FINALX)) prog = PROG_GENERIC;
   const bool u8 = h->dinfo.kind == DIAG_U8;
+  const bool zs = pp.zshape;   // low tile of a symmetric register: mirrored addressing (kernel mode 2)
+  if (zs)
+    for (int i = 0; i < tp.nops; i++)
+      if (tp.ops[i].type != TOP_ROUND && tp.ops[i].frame >= 3) fail("symmetric register: the low tile has no A4 / C4 frames");
   int nparts = (int)ntiles;
   // interpreter: one CTA per (tile, point); programs: persistent CTAs walking the linear index
   auto go_generic = [&]() {
-    auto kernel = cross ? tile_pass_kernel<Elem, true> : tile_pass_kernel<Elem, false>;
+    auto kernel = zs ? tile_pass_kernel<Elem, 2> : (cross ? tile_pass_kernel<Elem, 1> : tile_pass_kernel<Elem, 0>);
     CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES));
     tp.prefetch_dist = 0;
     // interpreter walks tiles of ONE point per launch row; use a flat grid over (point, tile)
@@ -873,6 +961,19 @@ int launch_pass(Engine* h, const PlanPass& pp, bool use_prog, unsigned ntiles, i
                                                                       (const real*)d_tau, d_phs, h->d_tables,
                                                                       tables_per_point, h->dinfo, h->d_partials, (unsigned)B);
   };
+  if (zs) {
+    switch (prog) {
+      case PROG_FIRST_INIT: if (u8) go(tile_prog_kernel<Elem, ProgFirstInit, DIAG_U8, 2>); else go(tile_prog_kernel<Elem, ProgFirstInit, 0, 2>); break;
+      case PROG_INTERIOR: go(tile_prog_kernel<Elem, ProgInterior, DIAG_U8, 2>); break;
+      case PROG_BOUNDARY: if (u8) go(tile_prog_kernel<Elem, ProgBoundary, DIAG_U8, 2>); else go(tile_prog_kernel<Elem, ProgBoundary, 0, 2>); break;
+      case PROG_FINAL: if (u8) go(tile_prog_kernel<Elem, ProgFinal, DIAG_U8, 2>); else go(tile_prog_kernel<Elem, ProgFinal, 0, 2>); break;
+      case PROG_MID: go(tile_prog_kernel<Elem, ProgMid, DIAG_U8, 2>); break;
+      case PROG_FINAL2: if (u8) go(tile_prog_kernel<Elem, ProgFinal2, DIAG_U8, 2>); else go(tile_prog_kernel<Elem, ProgFinal2, 0, 2>); break;
+      default: go_generic(); break;
+    }
+    CUDA_OK(cudaGetLastError());
+    return nparts;
+  }
   switch (prog) {
     case PROG_FIRST_INIT: if (u8) go(tile_prog_kernel<Elem, ProgFirstInit, DIAG_U8, false>); else go(tile_prog_kernel<Elem, ProgFirstInit, 0, false>); break;
     case PROG_FIRST_LOAD: if (u8) go(tile_prog_kernel<Elem, ProgFirstLoad, DIAG_U8, false>); else go(tile_prog_kernel<Elem, ProgFirstLoad, 0, false>); break;
@@ -898,7 +999,7 @@ int launch_pass(Engine* h, const PlanPass& pp, bool use_prog, unsigned ntiles, i
 // launches pass ip; tile_finalize turns the partial sums into {E, E2, min, max, norm} per point.
 void tile_prepare(Engine* h, Plan& pl, const double* angles, int n_angles, int Bc, bool record_last) {
   const int p = pl.p;
-  const unsigned ntiles = 1u << (h->El - TILE_BITS);
+  const unsigned ntiles = plan_ntiles(h, pl);
   const bool c64 = h->dtype == QAOA_DTYPE_C64;
   const size_t rsz = c64 ? 4 : 8;
   const size_t tpp = pl.tau_per_point, ppp = pl.phs_per_point;
@@ -971,18 +1072,19 @@ void tile_launch_pass(Engine* h, size_t ip) {
   if (!ev.pl || ip >= ev.pl->passes.size()) fail("no evaluation in flight / pass index out of range");
   Plan& pl = *ev.pl;
   const int p = pl.p, Bc = ev.Bc;
-  const unsigned ntiles = 1u << (h->El - TILE_BITS);
+  const unsigned ntiles = plan_ntiles(h, pl);
   const bool c64 = h->dtype == QAOA_DTYPE_C64;
   const size_t rsz = c64 ? 4 : 8;
   unsigned char* db = (unsigned char*)h->d_params;
-  const size_t point_stride_elems = h->N << h->qshift;
+  const size_t amps = plan_amps(h, pl);
+  const size_t point_stride_elems = amps << h->qshift;
   auto& pp = pl.passes[ip];
   const bool use_prog = ev.all_normal[ip] && !h->force_generic;
   const void* d_tau = db + ev.tbase[ip] * rsz;
   const double* d_phs = (const double*)(db + ev.tau_bytes) + ev.pbase[ip];
   bool reads = pp.tp.ops[0].type == TOP_LOAD, writes = pp.tp.ops[pp.tp.nops - 1].type == TOP_STORE;
-  const double pass_bytes = (double)Bc * (double)h->N * h->amp_bytes * ((reads ? 1 : 0) + (writes ? 1 : 0)) +
-      (double)Bc * (double)h->N * diag_value_bytes(h->dinfo.kind) * (pp.phases.size() + (pp.has_reduce ? 1 : 0));
+  const double pass_bytes = (double)Bc * (double)amps * h->amp_bytes * ((reads ? 1 : 0) + (writes ? 1 : 0)) +
+      (double)Bc * (double)amps * diag_value_bytes(h->dinfo.kind) * (pp.phases.size() + (pp.has_reduce ? 1 : 0));
   size_t evi = 0;
   if (h->time_passes) {
     evi = h->ev_pending.size();
@@ -1250,10 +1352,10 @@ void energy_batch_body(Engine* h, int p, const double* angles, int n_angles, int
   }
   if (h->mixer == MIXER_X || h->mixer == MIXER_XMULTI) {
     Plan& pl = get_plan(h, p);
-    size_t per_point = h->N * h->amp_bytes;
+    size_t per_point = plan_amps(h, pl) * h->amp_bytes;
     int Bmax = h->batch_points > 0 ? h->batch_points : (int)std::max<size_t>(1, std::min<size_t>(64, h->batch_bytes / per_point));
     Bmax = std::min(Bmax, 65535);
-    ensure_state(h, std::min(B, Bmax));
+    ensure_state(h, std::min(B, Bmax), plan_amps(h, pl));
     int done = 0;
     while (done < B) {
       int Bc = std::min(B - done, Bmax);
@@ -1277,6 +1379,7 @@ void set_diag_common(Engine* h, int kind, double c0, double delta) {
   if (h->diag) { cudaFree(h->diag); h->diag = nullptr; }
   free_streams(h);
   invalidate(h);
+  h->cost_symmetric = -1;
   h->dinfo.kind = kind;
   h->dinfo.c0 = kind == DIAG_F64 ? 0.0 : c0;
   h->dinfo.delta = kind == DIAG_F64 ? 1.0 : delta;
@@ -1426,6 +1529,7 @@ int qaoa_set_option(qaoa_engine_t* h, const char* key, double value) {
   else if (k == "low_bits") { h->low_bits = (int)value; free_streams(h); invalidate(h); }
   else if (k == "schedule") { h->schedule = (int)value; free_streams(h); invalidate(h); }
   else if (k == "feasible_subspace") h->compact_enabled = value != 0;
+  else if (k == "symmetric") { h->z2_enabled = value != 0; invalidate(h); }
   else fail("unknown option: " + k);
   API_END(h)
 }
@@ -1438,6 +1542,8 @@ double qaoa_get_counter(qaoa_engine_t* h, const char* key) {
   if (k == "bytes_alg") return h->bytes_alg;
   if (k == "diag_kind") return h->dinfo.kind;
   if (k == "compact_size") return (double)h->n_compact;
+  if (k == "symmetric_plans") { double s = 0; for (auto& kv : h->plans) s += kv.second.z2 ? 1 : 0; return s; }
+  if (k == "state_bytes") return (double)h->state_bytes;
   if (k == "reset") {
     h->launches = 0; h->prog_launches = 0; h->bytes_alg = 0;
     for (int i = 0; i < PROG_COUNT; i++) { h->pass_ms[i] = 0; h->pass_count[i] = 0; h->pass_bytes[i] = 0; }

@@ -100,6 +100,17 @@ __global__ void read_diag_kernel(const void* diag, DiagInfo info, size_t offset,
 }
 
 // min / max of the diagonal (computeMinMaxCosts, base_problem.py:121-134, without the Python loop)
+// cost(x) == cost(~x) for every x?  (raw stored values; flag |= 1 on the first mismatch) -- decides whether the
+// tile path may store the symmetric half of the register only
+template <typename T>
+__global__ void diag_symmetry_kernel(const T* __restrict__ diag, size_t N, int* flag) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  int bad = 0;
+  for (size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x; x < N / 2; x += stride)
+    if (diag[x] != diag[N - 1 - x]) bad = 1;
+  if (bad) atomicOr(flag, 1);
+}
+
 __global__ void diag_minmax_kernel(const void* diag, DiagInfo info, size_t N, double* partials) {
   __shared__ double red[32 * 5];
   double v[5] = {0, 0, 0, 1e300, -1e300};

@@ -92,6 +92,10 @@ struct TilePass {
   unsigned tile0;
   void* peers[QAOA_MAX_RANKS];          // state base of every rank
   const void* dpeers[QAOA_MAX_RANKS];   // cost-diagonal base of every rank (stream construction)
+  // Symmetric (Z2) registers, see "symmetric registers" below: zbit = element bit of the VIRTUAL top
+  // qubit (0 = off); it is tile bit 13 of the low tile shape and of no other shape.
+  int zbit;
+  int zsign;                            // i^(2-n) = +1 / -1 (n even)
 };
 
 template <typename Elem> struct ElemTraits;
@@ -164,9 +168,9 @@ __device__ __forceinline__ size_t tile_base(const TilePass& P, unsigned tile) {
 }
 
 // element index -> pointer.  CROSS passes translate through the peer table (one point only).
-template <bool CROSS, typename Elem>
+template <int CROSS, typename Elem>
 __device__ __forceinline__ Elem* eptr(const TilePass& P, Elem* point_base, size_t e) {
-  if constexpr (CROSS)
+  if constexpr (CROSS == 1)
     return reinterpret_cast<Elem*>(P.peers[e >> P.shard_bits]) + (e & (((size_t)1 << P.shard_bits) - 1));
   else
     return point_base + e;
@@ -240,6 +244,75 @@ __device__ __forceinline__ size_t stream_chunk(unsigned tile, int warp, int lane
   return (((size_t)tile * 16 + warp) * nchunks + j) * 32 + lane;
 }
 
+// ---- symmetric (Z2) registers ---------------------------------------------------------------
+// When cost(x) = cost(~x), the mixer is a sum of X_q and the initial state is |+>^n (MaxCut), the state
+// keeps psi(x) = psi(~x) through every layer: only the half with the top qubit = 0 is stored
+// (2^(n-1) amplitudes, index x' = low n-1 bits).  The mixer on the top qubit pairs x' with ~x':
+//     psi~'(x') = c * (psi~(x') + t * sigma(x') * psi~(~x')),   sigma(x') = i^(2-n) * (-1)^popc(x')   (n even)
+// (S frame of the stored half; sigma(~x') = -sigma(x'), so the pair (x', ~x') sees the usual lifted rotation
+// with t -> t * sigma).  The LOW tile shape carries this pairing as a VIRTUAL tile bit t13 = element bit
+// `zbit`: its tiles are 13 real low bits, a tile = one contiguous run of 2^13 elements plus its mirror image
+// (the run at the complemented base, walked backwards).  A virtual element index e with bit zbit set means
+// "the stored element at fold(e)", fold = clear zbit, complement every qubit bit below it.  t13 is a register
+// bit of frame A (slot 4) -- the butterfly is register local there -- and a warp bit of frames B and C.
+// Every access of the mirror image is as coalesced as the plain one (lanes run backwards); a 16-byte pair of
+// complex64 elements arrives with its halves swapped.
+// Inside the mirror image a virtual tile bit = 0 is a REAL qubit bit = 1, so the two elements of every ordinary
+// butterfly change roles there: mirrored elements (register bit 4 in frame A, lane bit 4 after its warp
+// transpose, warp bit 3 in frames B and C) take t -> -t in every round of the low tile.
+struct Z2Addr {
+  size_t b0, b1;    // pair base with the register's t13 clear / set (frame A); frame B: b0 only
+  size_t roff[4];   // frame A: offsets of t10..t12; frame B: offsets of t6..t9, negated in mirrored threads
+  bool mirrored;    // frame B: this thread's t13 (a warp bit) is set
+};
+
+__device__ __forceinline__ Z2Addr z2_addr(const TilePass& P, size_t base, int frame, size_t thr) {
+  Z2Addr a;
+  const size_t zpair = (((size_t)1 << P.zbit) - 1) & ~(size_t)1;   // complement mask of a 16-byte pair base
+  if (frame == 0) {
+#pragma unroll
+    for (int j = 0; j < 3; j++) a.roff[j] = (size_t)1 << P.pos[10 + j];
+    a.roff[3] = 0;
+    a.b0 = base + thr;
+    a.b1 = a.b0 ^ zpair;   // the offsets' bits are set here: the mirror image walks DOWN from it
+    a.mirrored = false;
+  } else {
+    const size_t v = base + thr;
+    a.mirrored = ((v >> P.zbit) & 1) != 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const size_t r = (size_t)1 << P.pos[6 + j];
+      a.roff[j] = a.mirrored ? (size_t)0 - r : r;
+    }
+    a.b0 = a.mirrored ? (v ^ (((size_t)1 << P.zbit) | zpair)) : v;
+    a.b1 = a.b0;
+  }
+  return a;
+}
+
+// stored element index of the 16-byte pair q (registers 2q, 2q+1) of this thread
+__device__ __forceinline__ size_t z2_pair_index(const Z2Addr& a, int frame, int q) {
+  if (frame == 0) {
+    const size_t off = ((q & 1) ? a.roff[0] : 0) + ((q & 2) ? a.roff[1] : 0) + ((q & 4) ? a.roff[2] : 0);
+    return (q & 8) ? a.b1 - off : a.b0 + off;
+  }
+  return a.b0 + ((q & 1) ? a.roff[0] : 0) + ((q & 2) ? a.roff[1] : 0) + ((q & 4) ? a.roff[2] : 0) +
+         ((q & 8) ? a.roff[3] : 0);
+}
+
+// complex64 only: the two elements of a mirrored pair sit in reverse order (complex128: bit 0 is re / im)
+template <typename Elem>
+__device__ __forceinline__ bool z2_swapped(const Z2Addr& a, int frame, int q) {
+  if (!ElemTraits<Elem>::IS_C64) return false;
+  return frame == 0 ? (q & 8) != 0 : a.mirrored;
+}
+
+// virtual element index -> stored element index (stream construction; qshift low bits are not qubits)
+__host__ __device__ inline size_t z2_fold(size_t e, int zbit, int qshift) {
+  if (zbit > 0 && ((e >> zbit) & 1)) e ^= (((size_t)2 << zbit) - 1) & ~(((size_t)1 << qshift) - 1);
+  return e;
+}
+
 // ---- per-thread context -------------------------------------------------------------------
 template <typename Elem>
 struct Ctx {
@@ -268,6 +341,7 @@ struct Ctx {
   // hoisted shared-memory byte addresses (see warp_transpose / block_transpose)
   unsigned wt_st, wt_ld, bt_st, bt_ld;
   size_t thr[5];   // hoisted per-thread element offsets for frames A, B, C, A4, C4
+  real zsig;       // symmetric registers: sigma of (this thread, register 0) in frame A, see round_static
 };
 
 template <typename Elem>
@@ -349,35 +423,70 @@ __device__ __forceinline__ void xt_c_to_a(const Ctx<Elem>& c, Elem (&v)[32]) {
 // ---- butterflies --------------------------------------------------------------------------
 // canonical (straight-line) round: normal form only, slots selected at compile time; the
 // coefficients of the current point sit in shared memory (see point_setup)
-template <typename Elem, int MASK>
-__device__ __forceinline__ void round_static(const typename ElemTraits<Elem>::real* tau_s, Elem (&v)[32], int round) {
+template <typename Elem, int MASK, bool ZS = false, bool ZR = false, bool ZT = false>
+__device__ __forceinline__ void round_static(const typename ElemTraits<Elem>::real* tau_s, Elem (&v)[32], int round,
+                                             typename ElemTraits<Elem>::real zsig = 0,
+                                             typename ElemTraits<Elem>::real msign = 1) {
   typedef typename ElemTraits<Elem>::real real;
   const real* rp = tau_s + round * TILE_ROUND_REALS;
 #pragma unroll
   for (int s = 0; s < 5; s++) {
-    if (MASK & (1 << s)) {
-      const real t = rp[s];
+    if (ZS && s == 4 && (MASK & 16)) {
+      // symmetric register, frame A: slot 4 pairs an element with its mirror image, t -> t * sigma(x');
+      // sigma alternates with the parity of the amplitude's index bits held in the register number
+      constexpr int QS = ElemTraits<Elem>::IS_C64 ? 0 : 1;
+      const real tz = rp[4] * zsig;
+#pragma unroll
+      for (int i = 0; i < 16; i++) {
+        const real tt = (__builtin_popcount(i >> QS) & 1) ? -tz : tz;
+        Elem a = v[i], b = v[i | 16];
+        v[i] = efma(tt, b, a);
+        v[i | 16] = efma(-tt, a, b);
+      }
+    } else if (MASK & (1 << s)) {
+      // ZT: this thread holds mirrored elements (msign = -1);  ZR: registers 16..31 do (frame A)
+      const real t = ZT ? rp[s] * msign : rp[s];
 #pragma unroll
       for (int i = 0; i < 32; i++) {
         if (!(i & (1 << s))) {
+          const real tt = (ZR && (i & 16)) ? -t : t;
           Elem a = v[i], b = v[i | (1 << s)];
-          v[i] = efma(t, b, a);
-          v[i | (1 << s)] = efma(-t, a, b);
+          v[i] = efma(tt, b, a);
+          v[i | (1 << s)] = efma(-tt, a, b);
         }
       }
     }
   }
 }
 
-// interpreter round: per-slot form, idle slots skipped
-template <typename Elem>
-__device__ __forceinline__ void round_dynamic(const Ctx<Elem>& c, Elem (&v)[32], int round) {
+__device__ __forceinline__ float2 esign(float s, float2 a) { return make_float2(s * a.x, s * a.y); }
+__device__ __forceinline__ double esign(double s, double a) { return s * a; }
+
+// Symmetric registers (Z): zslot = slot 4 of this round is the mirror pairing (frame A; see round_static): the
+// mirrored partner enters and leaves the butterfly multiplied by sigma = +-1, which covers both forms.  Mirrored
+// elements of ordinary slots (zr: registers 16..31; otherwise the whole thread when msign = -1) have the roles of
+// a and b exchanged, which is the same butterfly with b negated on the way in and out.
+template <typename Elem, bool Z = false>
+__device__ __forceinline__ void round_dynamic(const Ctx<Elem>& c, Elem (&v)[32], int round, bool zslot = false,
+                                              bool zr = false, typename ElemTraits<Elem>::real msign = 1) {
   typedef typename ElemTraits<Elem>::real real;
   const real* rp = c.tau + round * TILE_ROUND_REALS;
   const int forms = (int)__ldg(rp + 10);
+  constexpr int QS = ElemTraits<Elem>::IS_C64 ? 0 : 1;
 #pragma unroll
   for (int s = 0; s < 5; s++) {
     const real k1 = __ldg(rp + s), k2 = __ldg(rp + 5 + s);
+    const bool vslot = Z && s == 4 && zslot;
+    if (Z) {
+#pragma unroll
+      for (int i = 0; i < 32; i++) {
+        if (!(i & (1 << s))) {
+          real sg = vslot ? ((__builtin_popcount(i >> QS) & 1) ? -c.zsig : c.zsig)
+                          : (zr ? ((i & 16) ? (real)-1 : (real)1) : msign);
+          v[i | (1 << s)] = esign(sg, v[i | (1 << s)]);
+        }
+      }
+    }
     if ((forms >> s) & 1) {  // cot form: a' = k1 a + b ; b' = k2 b - a
 #pragma unroll
       for (int i = 0; i < 32; i++) {
@@ -394,6 +503,16 @@ __device__ __forceinline__ void round_dynamic(const Ctx<Elem>& c, Elem (&v)[32],
           Elem a = v[i], b = v[i | (1 << s)];
           v[i] = efma(k1, b, a);
           v[i | (1 << s)] = efma(k2, a, b);
+        }
+      }
+    }
+    if (Z) {
+#pragma unroll
+      for (int i = 0; i < 32; i++) {
+        if (!(i & (1 << s))) {
+          real sg = vslot ? ((__builtin_popcount(i >> QS) & 1) ? -c.zsig : c.zsig)
+                          : (zr ? ((i & 16) ? (real)-1 : (real)1) : msign);
+          v[i | (1 << s)] = esign(sg, v[i | (1 << s)]);
         }
       }
     }
@@ -460,8 +579,20 @@ __device__ __forceinline__ void for_each_diag(const void* stream, int kind, unsi
 }
 
 // ---- the steps ----------------------------------------------------------------------------
-template <typename Elem, bool CROSS>
+template <typename Elem, int CROSS>
 __device__ __forceinline__ void op_load(const Ctx<Elem>& c, Elem (&v)[32], int frame) {
+  if constexpr (CROSS == 2) {
+    const Z2Addr za = z2_addr(*c.P, c.base, frame, c.thr[frame]);
+#pragma unroll
+    for (int q = 0; q < 16; q++) {
+      Elem x, y;
+      load16(c.state + z2_pair_index(za, frame, q), x, y);
+      const bool sw = z2_swapped<Elem>(za, frame, q);
+      v[2 * q] = sw ? y : x;
+      v[2 * q + 1] = sw ? x : y;
+    }
+    return;
+  }
   TileAddr ad = tile_addr_off(*c.P, c.base, frame, c.thr[frame]);
 #pragma unroll
   for (int q = 0; q < 16; q++)
@@ -473,7 +604,7 @@ __device__ __forceinline__ void op_load(const Ctx<Elem>& c, Elem (&v)[32], int f
 template <typename Elem>
 __device__ __forceinline__ void prefetch_later_tile(const Ctx<Elem>& c) {
   const TilePass& P = *c.P;
-  if (P.prefetch_dist <= 0 || P.shard_bits != 0) return;
+  if (P.prefetch_dist <= 0 || P.shard_bits != 0 || P.zbit != 0) return;
   const unsigned long long id = c.id + (unsigned)P.prefetch_dist;
   if (id >= c.total) return;
   const unsigned ntile = (unsigned)(id % c.ntiles), npoint = (unsigned)(id / c.ntiles);
@@ -489,8 +620,17 @@ __device__ __forceinline__ void prefetch_later_tile(const Ctx<Elem>& c) {
   }
 }
 
-template <typename Elem, bool CROSS>
+template <typename Elem, int CROSS>
 __device__ __forceinline__ void op_store(const Ctx<Elem>& c, Elem (&v)[32], int frame) {
+  if constexpr (CROSS == 2) {
+    const Z2Addr za = z2_addr(*c.P, c.base, frame, c.thr[frame]);
+#pragma unroll
+    for (int q = 0; q < 16; q++) {
+      const bool sw = z2_swapped<Elem>(za, frame, q);
+      store16(c.state + z2_pair_index(za, frame, q), sw ? v[2 * q + 1] : v[2 * q], sw ? v[2 * q] : v[2 * q + 1]);
+    }
+    return;
+  }
   TileAddr ad = tile_addr_off(*c.P, c.base, frame, c.thr[frame]);
 #pragma unroll
   for (int q = 0; q < 16; q++)
@@ -498,7 +638,7 @@ __device__ __forceinline__ void op_store(const Ctx<Elem>& c, Elem (&v)[32], int 
 }
 
 // frame A4: every register is one 8-byte element of its own 128-byte row
-template <typename Elem, bool CROSS>
+template <typename Elem, int CROSS>
 __device__ __forceinline__ void op_load8(const Ctx<Elem>& c, Elem (&v)[32]) {
   const TilePass& P = *c.P;
   const size_t e0 = c.base + c.thr[3];
@@ -514,7 +654,7 @@ __device__ __forceinline__ void op_load8(const Ctx<Elem>& c, Elem (&v)[32]) {
   }
 }
 
-template <typename Elem, bool CROSS>
+template <typename Elem, int CROSS>
 __device__ __forceinline__ void op_store8(const Ctx<Elem>& c, Elem (&v)[32]) {
   const TilePass& P = *c.P;
   const size_t e0 = c.base + c.thr[3];
@@ -542,7 +682,10 @@ __device__ __forceinline__ void op_init(const Ctx<Elem>& c, Elem (&v)[32], int f
   for (int a = 0; a < NAMP; a++) {
     // tile bits are distinct element bits: popcount(x) = popcount(thread part) + popcount(reg part)
     const int regbits = ElemTraits<Elem>::IS_C64 ? a : (a << 1);
-    const int pc = pc0 + __popc(regbits >> P.qshift);
+    int pc = pc0 + __popc(regbits >> P.qshift);
+    // symmetric register (INIT runs in frame A): register bit 4 is the virtual bit, the stored index of
+    // such an element is the complement of its n-1 real qubit bits
+    if (P.zbit != 0 && (regbits & 16)) pc = (P.zbit - P.qshift) - (pc0 + __popc((regbits & 15) >> P.qshift));
     real re = A, im = (real)0;
     if (P.init_kind == INIT_DICKE && pc != P.dicke_k) re = (real)0;
     mul_i_pow(re, im, pc);
@@ -618,7 +761,7 @@ __device__ __forceinline__ void op_phase_u8_regs(const Ctx<Elem>& c, Elem (&v)[3
 //   psi~(x) = i^popc(x) * A * m * e^{i gamma c(x)}  =  tab4[popc(x) & 3][k(x)],
 // four rotated copies of the phase table sit in the (otherwise unused) staging area, so an amplitude
 // costs one byte extract and one shared-memory load.
-template <typename Elem>
+template <typename Elem, bool Z2>
 __device__ __forceinline__ void op_init_phase_plus(const Ctx<Elem>& c, Elem (&v)[32], const uint4 (&dq)[2]) {
   typedef typename ElemTraits<Elem>::real real;
   typedef typename ElemTraits<Elem>::cplx cplx;
@@ -630,6 +773,12 @@ __device__ __forceinline__ void op_init_phase_plus(const Ctx<Elem>& c, Elem (&v)
   const cplx* tb[4];
 #pragma unroll
   for (int j = 0; j < 4; j++) tb[j] = tab4 + ((pc0 + j) & 3) * 256;
+  // symmetric register: amplitudes whose top index bit (the virtual tile bit) is set are stored at the
+  // complemented index: popc = (n-1) - popc(thread part) - popc(low register part)
+  constexpr int VB = NAMP / 2;
+  const cplx* tm[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) tm[j] = Z2 ? tab4 + (((P.zbit - P.qshift) - pc0 - j) & 3) * 256 : tab4;
 #pragma unroll
   for (int j = 0; j < NAMP / 16; j++) {
     const unsigned ww[4] = {dq[j].x, dq[j].y, dq[j].z, dq[j].w};
@@ -637,7 +786,8 @@ __device__ __forceinline__ void op_init_phase_plus(const Ctx<Elem>& c, Elem (&v)
     for (int b = 0; b < 16; b++) {
       const int a = j * 16 + b;
       const unsigned k = (ww[b >> 2] >> (8 * (b & 3))) & 0xffu;
-      const cplx ph = tb[__builtin_popcount(a) & 3][k];   // amplitude index bits are distinct element bits
+      const cplx* tsel = (Z2 && (a & VB)) ? tm[__builtin_popcount(a & (VB - 1)) & 3] : tb[__builtin_popcount(a) & 3];
+      const cplx ph = tsel[k];   // amplitude index bits are distinct element bits
       amp_set(v, a, (real)ph.x, (real)ph.y);
     }
   }
@@ -894,6 +1044,11 @@ __device__ __forceinline__ void ctx_set_tile(Ctx<Elem>& c, unsigned long long id
   c.tau = c.tau0 + (size_t)c.point * P.tau_stride;
   c.phs = c.phs0 + (size_t)c.point * P.phs_stride;
   c.base = tile_base(P, c.tile + P.tile0);
+  if (P.zbit != 0) {   // sigma of (this thread, register 0) in frame A
+    typedef typename ElemTraits<Elem>::real real;
+    const int par = __popcll((unsigned long long)((c.base + c.thr[0]) >> P.qshift)) & 1;
+    c.zsig = (real)((par ? -1 : 1) * P.zsign);
+  }
 }
 
 
@@ -936,27 +1091,40 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // current tile has been pulled into registers); the remaining pairs use the start of the exchange
 // buffer ("late" group, issued once the tile's last transpose is done with that buffer).  With
 // L2_REST the lines of the pairs >= Q1 are pulled into L2 so that the late group is an L2 hit.
-template <typename Elem, int Q0, int Q1, bool L2_REST, bool CROSS>
+template <typename Elem, int Q0, int Q1, bool L2_REST, int CROSS>
 __device__ __forceinline__ void stage_issue(const Ctx<Elem>& c, unsigned long long id, int frame) {
   constexpr int SP = TileSmem<Elem>::STAGE_PAIRS;
   if (id < c.total) {
     const TilePass& P = *c.P;
     const unsigned ntile = (unsigned)(id % c.ntiles), npoint = (unsigned)(id / c.ntiles);
-    TileAddr ad = tile_addr_off(P, tile_base(P, ntile + P.tile0), frame, c.thr[frame]);
     Elem* pb = c.state0 + (size_t)npoint * c.point_stride;
     const unsigned sb = (unsigned)__cvta_generic_to_shared(c.smem);
     const unsigned early = sb + TileSmem<Elem>::STAGE_OFF + threadIdx.x * 16u;
     // late slots sit inside the OWNING warp's 8 KB region of the exchange buffer; every block-wide
     // transpose starts with a barrier, so they are consumed before anybody else writes there
     const unsigned late = sb + c.warp * 8192u + c.lane * 16u;
+    if constexpr (CROSS == 2) {   // symmetric register: mirrored pairs land with their halves swapped (op_load_staged)
+      const Z2Addr za = z2_addr(P, tile_base(P, ntile + P.tile0), frame, c.thr[frame]);
+#pragma unroll
+      for (int q = Q0; q < Q1; q++) {
+        const unsigned dst = q < SP ? early + q * (TILE_THREADS * 16) : late + (q - SP) * 512;
+        cp_async16(dst, pb + z2_pair_index(za, frame, q));
+      }
+      if (L2_REST) {
+#pragma unroll
+        for (int q = Q1; q < 16; q++) asm volatile("prefetch.global.L2 [%0];" ::"l"(pb + z2_pair_index(za, frame, q)));
+      }
+    } else {
+    TileAddr ad = tile_addr_off(P, tile_base(P, ntile + P.tile0), frame, c.thr[frame]);
 #pragma unroll
     for (int q = Q0; q < Q1; q++) {
       const unsigned dst = q < SP ? early + q * (TILE_THREADS * 16) : late + (q - SP) * 512;
       cp_async16(dst, eptr<CROSS, Elem>(P, pb, ad.e0 + reg_off(ad, q)));
     }
-    if (L2_REST && !CROSS) {   // (peer lines bypass the local L2)
+    if (L2_REST && CROSS != 1) {   // (peer lines bypass the local L2)
 #pragma unroll
       for (int q = Q1; q < 16; q++) asm volatile("prefetch.global.L2 [%0];" ::"l"(pb + ad.e0 + reg_off(ad, q)));
+    }
     }
   }
   cp_async_commit();
@@ -968,7 +1136,7 @@ __device__ __forceinline__ void cp_async8(unsigned smem_addr, const void* g) {
 
 // frame A4 variant: register pair q = registers (2q, 2q+1) = two 8-byte elements of different rows,
 // staged side by side in the same 16-byte slot the A / B frames use
-template <typename Elem, int Q0, int Q1, bool L2_REST, bool CROSS>
+template <typename Elem, int Q0, int Q1, bool L2_REST, int CROSS>
 __device__ __forceinline__ void stage_issue8(const Ctx<Elem>& c, unsigned long long id) {
   constexpr int SP = TileSmem<Elem>::STAGE_PAIRS;
   if (id < c.total) {
@@ -991,7 +1159,7 @@ __device__ __forceinline__ void stage_issue8(const Ctx<Elem>& c, unsigned long l
       const unsigned dst = (q < SP ? early + q * (TILE_THREADS * 16) : late + (q - SP) * 512) + (r & 1) * 8;
       cp_async8(dst, eptr<CROSS, Elem>(P, pb, e));
     }
-    if (L2_REST && !CROSS) {
+    if (L2_REST && CROSS != 1) {
 #pragma unroll
       for (int r = 2 * Q1; r < 32; r++) {
         size_t e = e0;
@@ -1005,7 +1173,7 @@ __device__ __forceinline__ void stage_issue8(const Ctx<Elem>& c, unsigned long l
 }
 
 // persistent-kernel load: every register pair comes from the slots filled during the previous tile
-template <typename Elem, bool CROSS>
+template <typename Elem, int CROSS>
 __device__ __forceinline__ void op_load_staged(const Ctx<Elem>& c, Elem (&v)[32], int frame) {
   constexpr int SP = TileSmem<Elem>::STAGE_PAIRS;
   cp_async_wait_all();
@@ -1014,7 +1182,15 @@ __device__ __forceinline__ void op_load_staged(const Ctx<Elem>& c, Elem (&v)[32]
 #pragma unroll
   for (int q = 0; q < 16; q++) {
     const unsigned char* src = q < SP ? early + q * (TILE_THREADS * 16) : late + (q - SP) * 512;
-    load16(reinterpret_cast<const Elem*>(src), v[2 * q], v[2 * q + 1]);
+    if constexpr (CROSS == 2 && ElemTraits<Elem>::IS_C64) {
+      const bool sw = frame == 0 ? (q & 8) != 0 : (c.warp & 8) != 0;   // see z2_swapped
+      Elem x, y;
+      load16(reinterpret_cast<const Elem*>(src), x, y);
+      v[2 * q] = sw ? y : x;
+      v[2 * q + 1] = sw ? x : y;
+    } else {
+      load16(reinterpret_cast<const Elem*>(src), v[2 * q], v[2 * q + 1]);
+    }
   }
   __syncwarp();
   if (frame == 3) stage_issue8<Elem, 0, SP, true, CROSS>(c, c.id + c.stride);
@@ -1022,18 +1198,21 @@ __device__ __forceinline__ void op_load_staged(const Ctx<Elem>& c, Elem (&v)[32]
 }
 
 // ---- interpreter kernel -------------------------------------------------------------------
-template <typename Elem, bool CROSS>
+template <typename Elem, int CROSS>
 __global__ void __launch_bounds__(TILE_THREADS, 1)
 tile_pass_kernel(const __grid_constant__ TilePass P, Elem* __restrict__ state, size_t point_stride,
                  const typename ElemTraits<Elem>::real* __restrict__ tau, const double* __restrict__ phs,
                  const void* __restrict__ tables, int tables_per_point, DiagInfo dinfo,
                  double* __restrict__ partials) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
+  typedef typename ElemTraits<Elem>::real real_t;
   Ctx<Elem> c;
   ctx_init<Elem>(c, P, state, point_stride, tau, phs, tables, tables_per_point, dinfo, partials, smem_raw,
                  TILE_EXCH_BYTES, TILE_EXCH_BYTES + 4096, (unsigned long long)gridDim.x);
   Elem v[32];
   TileOp op = P.ops[0];
+  int fcur = op.frame;   // frame tracking (symmetric registers: which elements are mirrored)
+  bool wt = false;
   for (int io = 0; io < P.nops; io++) {
     const TileOp cur = op;
     if (io + 1 < P.nops) op = P.ops[io + 1];  // fetch the next step early (constant-bank latency)
@@ -1052,11 +1231,19 @@ tile_pass_kernel(const __grid_constant__ TilePass P, Elem* __restrict__ state, s
         }
         op_phase<Elem, 0>(c, v, cur.arg);
         break;
-      case TOP_ROUND: round_dynamic<Elem>(c, v, cur.arg); break;
-      case TOP_WT: warp_transpose<Elem>(c, v); break;
-      case TOP_BT: block_transpose<Elem>(c, v); break;
-      case TOP_XT: xt_a_to_c<Elem>(c, v); break;
-      case TOP_XTI: xt_c_to_a<Elem>(c, v); break;
+      case TOP_ROUND:
+        if constexpr (CROSS == 2) {
+          const bool zr = fcur == 0 && !wt;
+          const bool mir = (fcur == 0 ? (c.lane & 16) : (c.warp & 8)) != 0;
+          round_dynamic<Elem, true>(c, v, cur.arg, zr && cur.frame == 1, zr, (!zr && mir) ? (real_t)-1 : (real_t)1);
+        } else {
+          round_dynamic<Elem>(c, v, cur.arg);
+        }
+        break;
+      case TOP_WT: warp_transpose<Elem>(c, v); wt = true; break;
+      case TOP_BT: block_transpose<Elem>(c, v); fcur ^= 1; wt = false; break;
+      case TOP_XT: xt_a_to_c<Elem>(c, v); fcur = 2; wt = false; break;
+      case TOP_XTI: xt_c_to_a<Elem>(c, v); fcur = 0; wt = false; break;
       case TOP_REDUCE:
         if constexpr (!ElemTraits<Elem>::IS_C64) {
           if (cur.frame == 2) {   // per-tile partials, like op_reduce
@@ -1095,6 +1282,19 @@ constexpr int M_ALL = 0x1f, M_HI4 = 0x1e, M_TOP2 = 0x18;
     return k;                                                                                        \
   }                                                                                                  \
   static constexpr int last_transpose() { return find_last(TOP_BT, TOP_XT, TOP_XTI, TOP_BT); }       \
+  /* frame the registers are in right before step I (+8: after a warp transpose) */                                \
+  static constexpr int frame_before(int I) {                                                         \
+    int f = op(0).frame;                                                                             \
+    bool wt = false;                                                                                 \
+    for (int i = 0; i < I && i < N; i++) {                                                           \
+      const int t = op(i).type;                                                                      \
+      if (t == TOP_WT) wt = true;                                                                    \
+      else if (t == TOP_BT) { f ^= 1; wt = false; }                                                  \
+      else if (t == TOP_XT) f = 2;                                                                   \
+      else if (t == TOP_XTI) f = 0;                                                                  \
+    }                                                                                                \
+    return f + (wt ? 8 : 0);                                                                         \
+  }                                                                                                  \
   static constexpr int stream_op() { return find_last(TOP_PHASE, TOP_REDUCE, TOP_PHASE, TOP_PHASE); } \
   static constexpr int n_stream_ops() {                                                              \
     int k = 0;                                                                                       \
@@ -1261,7 +1461,7 @@ __device__ __forceinline__ void point_setup(const Ctx<Elem>& c) {
   __syncthreads();
 }
 
-template <typename Elem, typename Prog, int DK, bool CROSS, int I>
+template <typename Elem, typename Prog, int DK, int CROSS, int I>
 struct ProgExec {
   static __device__ __forceinline__ void run(const Ctx<Elem>& c, Elem (&v)[32], const uint4 (&dq)[2], double (&acc)[5]) {
     typedef typename ElemTraits<Elem>::real real;
@@ -1283,7 +1483,7 @@ struct ProgExec {
       }
       else if constexpr (op.type == TOP_INIT) {
         if constexpr (REGS && Prog::op(I + 1 < Prog::N ? I + 1 : I).type == TOP_PHASE) {
-          if (c.P->init_kind == INIT_PLUS) op_init_phase_plus<Elem>(c, v, dq);   // phase fused in
+          if (c.P->init_kind == INIT_PLUS) op_init_phase_plus<Elem, CROSS == 2>(c, v, dq);   // phase fused in
           else op_init<Elem>(c, v, op.frame);
         } else op_init<Elem>(c, v, op.frame);
       }
@@ -1297,7 +1497,18 @@ struct ProgExec {
         }
         else op_phase<Elem, DK>(c, v, op.arg);
       }
-      else if constexpr (op.type == TOP_ROUND) round_static<Elem, op.mask>(tau_s, v, op.arg);
+      else if constexpr (op.type == TOP_ROUND) {
+        if constexpr (CROSS == 2) {   // low tile of a symmetric register
+          constexpr int fb = Prog::frame_before(I);
+          constexpr bool ZR = fb == 0;                    // frame A: registers 16..31 are mirrored
+          constexpr bool ZS = ZR && (op.mask & 16) != 0;  // ... and slot 4 is the mirror pairing
+          real ms = (real)1;
+          if constexpr (!ZR) ms = ((fb == 8 ? (c.lane & 16) : (c.warp & 8)) != 0) ? (real)-1 : (real)1;
+          round_static<Elem, op.mask, ZS, ZR, !ZR>(tau_s, v, op.arg, c.zsig, ms);
+        } else {
+          round_static<Elem, op.mask>(tau_s, v, op.arg);
+        }
+      }
       else if constexpr (op.type == TOP_WT) warp_transpose<Elem>(c, v);
       else if constexpr (op.type == TOP_BT || op.type == TOP_XT || op.type == TOP_XTI) {
         if constexpr (op.type == TOP_BT) block_transpose<Elem>(c, v);
@@ -1321,7 +1532,7 @@ struct ProgExec {
   }
 };
 
-template <typename Elem, typename Prog, int DK, bool CROSS>
+template <typename Elem, typename Prog, int DK, int CROSS>
 __global__ void __launch_bounds__(TILE_THREADS, 1)
 tile_prog_kernel(const __grid_constant__ TilePass P, Elem* __restrict__ state, size_t point_stride,
                  const typename ElemTraits<Elem>::real* __restrict__ tau, const double* __restrict__ phs,
@@ -1440,7 +1651,7 @@ __global__ void make_stream_kernel(const __grid_constant__ TilePass P, int frame
     __align__(16) unsigned char buf[16];
     for (int i = 0; i < V; i++) {
       const int a = j * V + i;
-      const size_t e = e0 + reg_elem_off(P, frame, namp == 32 ? a : 2 * a);
+      const size_t e = z2_fold(e0 + reg_elem_off(P, frame, namp == 32 ? a : 2 * a), P.zbit, P.qshift);
       const size_t x = e >> P.qshift;   // amplitude index (global in a cross pass)
       const int abits = P.shard_bits - P.qshift;
       const unsigned char* src = cross

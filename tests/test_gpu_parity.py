@@ -276,6 +276,7 @@ def test_balanced_schedule_vs_classic_vs_oracle(n, ps, low_bits, dtype):
     low_bits=4 forces the tile shapes n = 33 / 34 use (BOUND2L4 / FINAL2L4 programs)."""
     from oracle import c_oracle
     eng, E = _engine(n, dtype)
+    E.set_option("symmetric", 0)   # the full register (tests/test_gpu_symmetric.py covers the half register)
     if low_bits:   # 4 low bits (what n = 33, 34 choose): high-tile passes run in frames A4 / C4 with 8-byte accesses
         E.set_option("low_bits", low_bits)
     edges, colors, table = H.regular_maxcut(n)
