@@ -7,7 +7,10 @@ statevector.  One step = one energy evaluation <gamma,beta|H_P|gamma,beta>.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--n 32] [--p 5] [--impl reference]
 
-N = 1 : n = 32 on one B200 (32 GiB state, far larger than the 126 MB L2: nothing to flush).
+N = 1 : n = 32 on one B200.  MaxCut + X mixer + |+> keeps psi(x) = psi(~x), so the engine stores the symmetric
+        half of the register (2^31 amplitudes = 16 GiB, far larger than the 126 MB L2: nothing to flush) and pairs
+        every element with its mirror image for the top qubit (tile_kernel.cuh "symmetric registers"); the same
+        evaluation on the full 32 GiB register (option symmetric=0) is reported under "full_register".
 N > 1 : launched under torchrun, one rank per GPU; WEAK scaling: every rank evaluates its own n = 32
         register (independent units: the landscape / optimizer workloads of the reference shard over
         evaluations with no data-path collective); value = step time / N.  The line also carries
@@ -162,9 +165,12 @@ def landscape_leg(device, world=1):
     t0 = time.perf_counter()
     q.sample_cost_landscape(grid)
     dt = time.perf_counter() - t0
-    bytes_per_point = 2 * (8.0 + 1.0) * 2.0 ** n    # FIRST writes the state, FINAL reads it, one diagonal byte each
+    sym = q._get_engine().counter("symmetric_plans") >= 1
+    # FIRST writes the stored register, FINAL reads it, one diagonal byte per amplitude each
+    bytes_per_point = 2 * (8.0 + 1.0) * 2.0 ** (n - 1 if sym else n)
     return {"workload": "MaxCut 3-regular n=%d seed=42, X, Plus, p=1, %dx%d grid, complex64%s" % (
                 n, g, g, "" if world == 1 else ", grid points dealt out over %d GPUs" % world),
+            "register": "symmetric half (2^%d amplitudes per point)" % (n - 1) if sym else "full",
             "points_per_s": g * g / dt, "seconds": dt, "min_exp": float(q.Exp_sampled_p1.min()),
             "algorithmic_gb_per_point": bytes_per_point / 1e9,
             "achieved_gbs": bytes_per_point * g * g / dt / 1e9}
@@ -249,6 +255,7 @@ def main():
                     help="sample size of the CPU legs (0: the largest that fits the time budget)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-landscape", action="store_true")
+    ap.add_argument("--symmetric", type=int, default=1, help="0: always store the full register")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
 
@@ -275,6 +282,7 @@ def main():
         sharded = run_sharded(args, rank, world, local_rank, dist, torch)
     edges = workload(n)
     E = eng.Engine(n, "complex64", device=local_rank)
+    E.set_option("symmetric", args.symmetric)
     E.set_cost_maxkcut(n, edges, 1, np.array([0, 1], dtype=np.uint8))
     ang = angles_for(p, 1234 + rank)
     E.set_option("time_passes", 1)
@@ -302,6 +310,8 @@ def main():
     pass_stats = {i: (E.counter("pass_ms_%d" % i), E.counter("pass_count_%d" % i), E.counter("pass_bytes_%d" % i))
                   for i in range(13)}
     out = E.fetch_results(1)[0]
+    sym = E.counter("symmetric_plans") >= 1
+    stored_amps = 2.0 ** (n - 1) if sym else 2.0 ** n
 
     # ---- end to end through the public API: host angles in, host result out ----------------------
     barrier()
@@ -312,6 +322,23 @@ def main():
     wall_e2e = time.perf_counter() - t0
     sampler.stop_flag = True
     sampler.join(timeout=2)
+
+    full_register = None
+    if sym and world == 1:
+        E.close()
+        E = eng.Engine(n, "complex64", device=local_rank)
+        E.set_option("symmetric", 0)
+        E.set_cost_maxkcut(n, edges, 1, np.array([0, 1], dtype=np.uint8))
+        for _ in range(2):
+            E.energy(ang)
+        ms_full = []
+        for _ in range(3):
+            E.energy_batch_resident(ang[None, :])
+            out_full = E.fetch_results(1)[0]
+            ms_full.append(E.counter("last_device_ms"))
+        full_register = {"value": float(np.mean(ms_full)), "unit": UNIT, "energy": float(-out_full[0]),
+                         "note": "same evaluation with option symmetric=0: all 2^%d amplitudes stored (%d GiB)" % (n, 8 * 2 ** n >> 30)}
+    E.close()
 
     landscape = None
     if not args.no_landscape:
@@ -343,7 +370,7 @@ def main():
         survey_bytes = 8.0 * 2.0 ** n * (2 * p * P - 2)
         traffic = None
         try:
-            with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            with open(os.path.join(ROOT, "profiles", "r01b_traffic.json" if sym else "r01_traffic.json")) as f:
                 ratios = json.load(f)["traffic_over_algorithmic"]
             key = [k for k in ratios if k in names[dom]]
             if key and d_cnt:
@@ -362,7 +389,10 @@ def main():
                                    "the landscape / optimiser workloads shard over evaluations with no data-path collective); "
                                    "value = step time / %d; the sharded single-register path is reported under 'sharded'"
                                    % (n, p, world, world),
-                       "l2": "state is %d GiB >> 126 MB L2, no flush needed" % (8 * 2 ** n >> 30),
+                       "register": ("symmetric half register: psi(x) = psi(~x) for MaxCut + X + Plus, 2^%d stored amplitudes, "
+                                    "the top qubit's rotation pairs every element with its mirror image" % (n - 1)) if sym
+                                   else "full register, 2^%d stored amplitudes" % n,
+                       "l2": "state is %d GiB >> 126 MB L2, no flush needed" % (int(8 * stored_amps) >> 30),
                        "energy": float(-out[0]), "norm": float(out[4])},
             "e2e": {"value": ms_e2e / world, "unit": UNIT, "h2d_bytes_per_step": int(ang.nbytes) * world,
                     "d2h_bytes_per_step": 40 * world,
@@ -371,15 +401,19 @@ def main():
             "clocks": sampler.summary(),
             "roofline": {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic,
-                         "traffic_source": "profiles/r01_tile_kernels_n28.md ratio x algorithmic bytes",
+                         "traffic_source": "profiles/%s ratio x algorithmic bytes" % ("r01b_symmetric_n28.md" if sym else "r01_tile_kernels_n28.md"),
                          "launches_timed": int(d_cnt), "ms_per_launch": d_ms / d_cnt if d_cnt else None,
                          "kernel_share_of_step": d_ms / total_pass_ms if total_pass_ms else None,
                          "whole_eval_actual_gbs": total_bytes / (total_pass_ms * 1e-3) / 1e9 if total_pass_ms else None,
+                         "algorithmic_bytes_per_eval": total_bytes / args.steps,
+                         "whole_eval_frac_of_peak": total_bytes / (total_pass_ms * 1e-3) / 1e9 / peak if total_pass_ms else None,
                          "survey_model_bytes_per_eval": survey_bytes,
-                         "survey_model_gbs": survey_bytes / (ms_dev * 1e-3) / 1e9,
-                         "survey_model_frac_of_8TBps": survey_bytes / (ms_dev * 1e-3) / 8e12},
+                         "survey_model_note": "SURVEY 8d model: 28 sweeps of the FULL 2^n register; the engine does 20 sweeps "
+                                              "of the stored register (half of it when symmetric)"},
             "passes": {names[i]: {"ms_total": v[0], "launches": int(v[1])} for i, v in pass_stats.items() if v[1]},
         }
+        if full_register is not None:
+            line["full_register"] = full_register
         if landscape is not None:
             line["landscape"] = landscape
         if sharded is not None:
