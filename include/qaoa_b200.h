@@ -48,7 +48,10 @@ const char* qaoa_last_error(qaoa_engine_t* h);
 const char* qaoa_global_error(void);
 
 /* Tunables / test hooks: "small_max_qubits", "keep_state", "batch_points", "batch_bytes",
- * "force_generic", "prefetch_dist", "persistent_ctas", "low_bits", "schedule", "feasible_subspace", "time_passes". */
+ * "force_generic", "prefetch_dist", "persistent_ctas", "low_bits", "schedule", "feasible_subspace", "time_passes",
+ * "symmetric" (default 1: when cost(x) == cost(~x) -- checked on the device --, the mixer is X / multi-angle X, the
+ * initial state |+> and n even, the tile path stores only the 2^(n-1) amplitudes with the top qubit = 0; results are
+ * those of the full register; 0 = always store the full register). */
 int qaoa_set_option(qaoa_engine_t* h, const char* key, double value);
 double qaoa_get_counter(qaoa_engine_t* h, const char* key); /* "launches", "bytes_alg", ... */
 
