@@ -929,6 +929,8 @@ int launch_pass(Engine* h, const PlanPass& pp, bool use_prog, unsigned ntiles, i
   typedef typename ElemTraits<Elem>::real real;
   TilePass tp = pp.tp;
   tp.ntiles = ntiles;
+  if (ntiles & (ntiles - 1)) fail("the number of tiles must be a power of two");
+  tilepass_set_offsets(tp);
   tp.prefetch_dist = h->prefetch_dist;
   shard_fill(h, tp, pp.cross);
   int prog = use_prog ? pp.prog : PROG_GENERIC;

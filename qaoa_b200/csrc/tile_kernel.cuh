@@ -96,6 +96,10 @@ struct TilePass {
   // qubit (0 = off); it is tile bit 13 of the low tile shape and of no other shape.
   int zbit;
   int zsign;                            // i^(2-n) = +1 / -1 (n even)
+  // element offsets of the upper register bits, precomputed by the host (tilepass_set_offsets): frames A / B
+  // (register bits 1..4) and A4 (register bits 0..4) -- constant-bank operands instead of per-tile shifts
+  unsigned long long roffe[2][4];
+  unsigned long long roffe8[5];
 };
 
 template <typename Elem> struct ElemTraits;
@@ -191,6 +195,15 @@ inline bool tilepass_set_free_runs(TilePass& tp) {
 }
 
 // tile-local bit held by each lane / warp / register bit of a frame (see the frame table above)
+__host__ __device__ inline int frame_reg_bit(int frame, int j);
+// host: fill the precomputed register-bit offsets from pos (call whenever pos is final)
+inline void tilepass_set_offsets(TilePass& tp) {
+  for (int j = 0; j < 4; j++) {
+    tp.roffe[0][j] = 1ull << tp.pos[10 + j];
+    tp.roffe[1][j] = 1ull << tp.pos[6 + j];
+  }
+  for (int j = 0; j < 5; j++) tp.roffe8[j] = 1ull << tp.pos[frame_reg_bit(3, j)];
+}
 __host__ __device__ inline int frame_lane_bit(int frame, int j) {
   if (frame == 2 || frame == 3) return j;
   if (frame == 4) return j == 0 ? 9 : j - 1;
@@ -227,9 +240,8 @@ __device__ __forceinline__ size_t reg_elem_off(const TilePass& P, int frame, int
 // frames A and B only (register bit 0 = element bit 0, 16-byte accesses)
 __device__ __forceinline__ TileAddr tile_addr_off(const TilePass& P, size_t base, int frame, size_t thr) {
   TileAddr a;
-  const int rofs = frame == 0 ? 10 : 6;
 #pragma unroll
-  for (int j = 0; j < 4; j++) a.roff[j] = (size_t)1 << P.pos[rofs + j];
+  for (int j = 0; j < 4; j++) a.roff[j] = (size_t)P.roffe[frame == 0 ? 0 : 1][j];
   a.e0 = base + thr;
   return a;
 }
@@ -271,7 +283,7 @@ __device__ __forceinline__ Z2Addr z2_addr(const TilePass& P, size_t base, int fr
   const size_t zpair = (((size_t)1 << P.zbit) - 1) & ~(size_t)1;   // complement mask of a 16-byte pair base
   if (frame == 0) {
 #pragma unroll
-    for (int j = 0; j < 3; j++) a.roff[j] = (size_t)1 << P.pos[10 + j];
+    for (int j = 0; j < 3; j++) a.roff[j] = (size_t)P.roffe[0][j];
     a.roff[3] = 0;
     a.b0 = base + thr;
     a.b1 = a.b0 ^ zpair;   // the offsets' bits are set here: the mirror image walks DOWN from it
@@ -281,7 +293,7 @@ __device__ __forceinline__ Z2Addr z2_addr(const TilePass& P, size_t base, int fr
     a.mirrored = ((v >> P.zbit) & 1) != 0;
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-      const size_t r = (size_t)1 << P.pos[6 + j];
+      const size_t r = (size_t)P.roffe[1][j];
       a.roff[j] = a.mirrored ? (size_t)0 - r : r;
     }
     a.b0 = a.mirrored ? (v ^ (((size_t)1 << P.zbit) | zpair)) : v;
@@ -327,7 +339,8 @@ struct Ctx {
   DiagInfo dinfo;
   double* partials;
   unsigned tile, point;
-  unsigned ntiles;
+  unsigned ntiles, tmask;
+  int tshift;                             // ntiles = 1 << tshift
   unsigned long long id, total, stride;   // persistent kernels: linear (point, tile) index walk
   Elem* state0;
   const real* tau0;
@@ -607,7 +620,7 @@ __device__ __forceinline__ void prefetch_later_tile(const Ctx<Elem>& c) {
   if (P.prefetch_dist <= 0 || P.shard_bits != 0 || P.zbit != 0) return;
   const unsigned long long id = c.id + (unsigned)P.prefetch_dist;
   if (id >= c.total) return;
-  const unsigned ntile = (unsigned)(id % c.ntiles), npoint = (unsigned)(id / c.ntiles);
+  const unsigned ntile = (unsigned)(id & c.tmask), npoint = (unsigned)(id >> c.tshift);
   const size_t nbase = tile_base(P, ntile);
   const Elem* st = c.state0 + (size_t)npoint * c.point_stride;
 #pragma unroll
@@ -644,7 +657,7 @@ __device__ __forceinline__ void op_load8(const Ctx<Elem>& c, Elem (&v)[32]) {
   const size_t e0 = c.base + c.thr[3];
   size_t ro[5];
 #pragma unroll
-  for (int j = 0; j < 5; j++) ro[j] = (size_t)1 << P.pos[frame_reg_bit(3, j)];
+  for (int j = 0; j < 5; j++) ro[j] = (size_t)P.roffe8[j];
 #pragma unroll
   for (int r = 0; r < 32; r++) {
     size_t e = e0;
@@ -660,7 +673,7 @@ __device__ __forceinline__ void op_store8(const Ctx<Elem>& c, Elem (&v)[32]) {
   const size_t e0 = c.base + c.thr[3];
   size_t ro[5];
 #pragma unroll
-  for (int j = 0; j < 5; j++) ro[j] = (size_t)1 << P.pos[frame_reg_bit(3, j)];
+  for (int j = 0; j < 5; j++) ro[j] = (size_t)P.roffe8[j];
 #pragma unroll
   for (int r = 0; r < 32; r++) {
     size_t e = e0;
@@ -1038,8 +1051,8 @@ template <typename Elem>
 __device__ __forceinline__ void ctx_set_tile(Ctx<Elem>& c, unsigned long long id) {
   const TilePass& P = *c.P;
   c.id = id;
-  c.tile = (unsigned)(id % c.ntiles);
-  c.point = (unsigned)(id / c.ntiles);
+  c.tile = (unsigned)(id & c.tmask);   // ntiles is a power of two
+  c.point = (unsigned)(id >> c.tshift);
   c.state = c.state0 + (size_t)c.point * c.point_stride;
   c.tau = c.tau0 + (size_t)c.point * P.tau_stride;
   c.phs = c.phs0 + (size_t)c.point * P.phs_stride;
@@ -1062,6 +1075,8 @@ __device__ __forceinline__ void ctx_init(Ctx<Elem>& c, const TilePass& P, Elem* 
   c.lane = threadIdx.x & 31;
   c.warp = threadIdx.x >> 5;
   c.ntiles = P.ntiles;
+  c.tshift = 31 - __clz((int)P.ntiles);
+  c.tmask = P.ntiles - 1u;
   c.total = total;
   c.stride = gridDim.x;
   c.state0 = state;
@@ -1096,7 +1111,7 @@ __device__ __forceinline__ void stage_issue(const Ctx<Elem>& c, unsigned long lo
   constexpr int SP = TileSmem<Elem>::STAGE_PAIRS;
   if (id < c.total) {
     const TilePass& P = *c.P;
-    const unsigned ntile = (unsigned)(id % c.ntiles), npoint = (unsigned)(id / c.ntiles);
+    const unsigned ntile = (unsigned)(id & c.tmask), npoint = (unsigned)(id >> c.tshift);
     Elem* pb = c.state0 + (size_t)npoint * c.point_stride;
     const unsigned sb = (unsigned)__cvta_generic_to_shared(c.smem);
     const unsigned early = sb + TileSmem<Elem>::STAGE_OFF + threadIdx.x * 16u;
@@ -1141,11 +1156,11 @@ __device__ __forceinline__ void stage_issue8(const Ctx<Elem>& c, unsigned long l
   constexpr int SP = TileSmem<Elem>::STAGE_PAIRS;
   if (id < c.total) {
     const TilePass& P = *c.P;
-    const unsigned ntile = (unsigned)(id % c.ntiles), npoint = (unsigned)(id / c.ntiles);
+    const unsigned ntile = (unsigned)(id & c.tmask), npoint = (unsigned)(id >> c.tshift);
     const size_t e0 = tile_base(P, ntile + P.tile0) + c.thr[3];
     size_t ro[5];
 #pragma unroll
-    for (int j = 0; j < 5; j++) ro[j] = (size_t)1 << P.pos[frame_reg_bit(3, j)];
+    for (int j = 0; j < 5; j++) ro[j] = (size_t)P.roffe8[j];
     Elem* pb = c.state0 + (size_t)npoint * c.point_stride;
     const unsigned sb = (unsigned)__cvta_generic_to_shared(c.smem);
     const unsigned early = sb + TileSmem<Elem>::STAGE_OFF + threadIdx.x * 16u;
@@ -1571,7 +1586,7 @@ tile_prog_kernel(const __grid_constant__ TilePass P, Elem* __restrict__ state, s
   constexpr int DQ_OFF = L::STAGE_OFF + 4 * L::TABLE_BYTES;
   auto dq_issue = [&](unsigned long long id, int buf) {
     if (id < total) {
-      const unsigned t = (unsigned)(id % c.ntiles);
+      const unsigned t = (unsigned)(id & c.tmask);
       const uint4* s4 = reinterpret_cast<const uint4*>(P.streams[Prog::op(Prog::stream_op() >= 0 ? Prog::stream_op() : 0).arg]);
       const unsigned sb = (unsigned)__cvta_generic_to_shared(smem_raw) + DQ_OFF + buf * (TILE_THREADS * 32) + threadIdx.x * 16u;
 #pragma unroll
