@@ -150,6 +150,9 @@ struct Engine {
   int schedule = 0;          // 0: automatic, 1: classic (interior + boundary), 2: balanced (mid + bound2)
   int z2_enabled = 1;        // option "symmetric": store half the register when the problem has the global bit-flip symmetry
   int cost_symmetric = -1;   // cost(x) == cost(~x) for every x: -1 unknown, 0 no, 1 yes (checked on the device)
+  // Sharded symmetric register (option "shard_symmetric", tile_kernel.cuh "twisted coordinates"): the engine holds
+  // 2^(n-1-gbits) STORED amplitudes; N, El and x0 describe that stored shard, E still counts the virtual top qubit.
+  int ztw_mode = 0;
   size_t state_bytes = 0;
   double* d_partials = nullptr; size_t partials_cap = 0;
   double* d_out = nullptr; size_t out_cap = 0;
@@ -297,19 +300,26 @@ bool ensure_compact(Engine* h, int k) {
 // mixer, |+> initial state, even n.  The tile path then stores the half register with the top qubit = 0.
 bool cost_is_symmetric(Engine* h);
 bool use_z2(Engine* h) {
+  if (h->ztw_mode) {   // chosen by the caller at creation: everything else is rejected, never re-routed
+    if (h->mixer != MIXER_X && h->mixer != MIXER_XMULTI) fail("sharded symmetric register: X / multi-angle X mixers only");
+    if (h->init.kind != INIT_PLUS || h->n_gamma != 1 || h->n_init != 0) fail("sharded symmetric register: |+> initial state only");
+    if (h->cost_symmetric != 1) fail("sharded symmetric register: the cost function is not known to be invariant under the global bit flip");
+    if (h->keep_state || h->schedule == 1) fail("sharded symmetric register: keep_state / the classic schedule are not supported");
+    return true;
+  }
   if (!h->z2_enabled || h->world > 1 || h->keep_state || (h->n & 1)) return false;
   if (h->mixer != MIXER_X && h->mixer != MIXER_XMULTI) return false;
   if (h->init.kind != INIT_PLUS || h->n_gamma != 1 || h->n_init != 0) return false;
   if (h->E - 1 < TILE_BITS + 1) return false;          // the half register still needs a high tile shape
   return cost_is_symmetric(h);
 }
-inline int plan_el(const Engine* h, const Plan& pl) { return pl.z2 ? h->El - 1 : h->El; }          // stored element bits
-inline size_t plan_amps(const Engine* h, const Plan& pl) { return pl.z2 ? h->N >> 1 : h->N; }      // stored amplitudes
+inline int plan_el(const Engine* h, const Plan& pl) { return (pl.z2 && !h->ztw_mode) ? h->El - 1 : h->El; }      // stored element bits
+inline size_t plan_amps(const Engine* h, const Plan& pl) { return (pl.z2 && !h->ztw_mode) ? h->N >> 1 : h->N; }  // stored amplitudes
 inline unsigned plan_ntiles(const Engine* h, const Plan& pl) { return 1u << (plan_el(h, pl) - TILE_BITS); }
 
 bool cost_is_symmetric(Engine* h) {
   if (h->cost_symmetric >= 0) return h->cost_symmetric == 1;
-  if (h->dinfo.kind == DIAG_NONE || !h->diag || h->world > 1) return false;
+  if (h->dinfo.kind == DIAG_NONE || !h->diag || h->world > 1) return false;   // (sharded: known by construction only)
   DevTmp t_flag(sizeof(int));
   int* d_flag = t_flag.as<int>();
   CUDA_OK(cudaMemsetAsync(d_flag, 0, sizeof(int), h->stream));
@@ -330,6 +340,12 @@ void shard_fill(const Engine* h, TilePass& tp, bool cross) {
   tp.shard_bits = h->world > 1 ? h->El : 0;
   tp.rank_popc = __builtin_popcount((unsigned)h->rank);
   tp.tile0 = 0;
+  tp.zdelta = 0; tp.ztw = 0; tp.xgbits = 0;
+  if (h->ztw_mode) {
+    tp.zdelta = h->gbits - 2 * tp.rank_popc;
+    tp.ztw = h->gbits & 1;
+    tp.xgbits = cross ? h->gbits : 0;
+  }
   if (h->world > 1) {
     // tiles enumerate LOCAL free bits only (a cross tile has the rank bits among its tile bits, any
     // other tile lives entirely inside the local shard)
@@ -370,6 +386,15 @@ void reg_bits(int frame, int sub, int out[5]) {
 // against the classic INTERIOR (2 transposes) + BOUNDARY (4 transposes) pair.  The last layer ends
 // with FINAL2 (1 transpose, fused reduction).  Same number of HBM sweeps, a third less shared-memory
 // traffic and evenly split arithmetic.
+// pass descriptor fields of the low tile of a symmetric register: the virtual top qubit (logical element bit E - 1
+// in Shape::pos[13]) is addressed as the element bit right above the stored (local) register
+void set_zshape(const Engine* h, const Plan& pl, TilePass& tp) {
+  tp.zbit = plan_el(h, pl);
+  tp.pos[TILE_BITS - 1] = tp.zbit;
+  tp.zsign = ((h->n - 2) / 2) % 2 ? -1 : 1;
+  tp.znreal = h->n - 1;
+}
+
 void build_balanced(Engine* h, int p, Plan& pl) {
   const int E = h->E, qs = h->qshift, m = (int)pl.shapes.size();
   std::vector<std::vector<char>> done(p, std::vector<char>(E, 0));
@@ -400,7 +425,7 @@ void build_balanced(Engine* h, int p, Plan& pl) {
     tp.dicke_k = h->init.k;
     tp.init_amp = h->init.amp * (pl.z2 ? sqrt(2.0) : 1.0);   // the stored half carries the whole norm
     b.pp.zshape = b.sh->zshape;
-    if (b.sh->zshape) { tp.zbit = E - 1; tp.zsign = ((h->n - 2) / 2) % 2 ? -1 : 1; }
+    if (b.sh->zshape) set_zshape(h, pl, tp);
     return b;
   };
   auto push = [&](Builder& b, int type, int fr, int arg, int mask) {
@@ -419,8 +444,10 @@ void build_balanced(Engine* h, int p, Plan& pl) {
       rs.ebit[s] = -1;
       if (!((mask >> s) & 1)) continue;
       const int eb = b.sh->pos[reg_tile_bit(kind, s)];
+      if (h->ztw_mode && eb == qs) continue;   // twisted shards: qubit 0 is mixed in the cross passes only
       if (eb >= qs && !done[layer][eb]) { rs.ebit[s] = eb; done[layer][eb] = 1; }
     }
+    if (h->ztw_mode && b.sh->cross && kind == 0 && !done[layer][qs]) { rs.ebit[0] = qs; done[layer][qs] = 1; }
     // frame field of a ROUND: 1 = slot 4 is the mirror pairing of a symmetric register (frame A of the low tile)
     push(b, TOP_ROUND, (b.sh->zshape && kind == 0 && ((mask >> 4) & 1)) ? 1 : 0, (int)b.pp.rounds.size(), mask);
     b.pp.rounds.push_back(rs);
@@ -650,7 +677,7 @@ Plan build_plan(Engine* h, int p) {
     tp.dicke_k = h->init.k;
     tp.init_amp = h->init.amp * (pl.z2 ? sqrt(2.0) : 1.0);
     pp.zshape = sh.zshape;
-    if (sh.zshape) { tp.zbit = E - 1; tp.zsign = ((h->n - 2) / 2) % 2 ? -1 : 1; }
+    if (sh.zshape) set_zshape(h, pl, tp);
     int frame = 0;
     auto push = [&](int type, int fr, int arg, int mask) {
       if (tp.nops >= TILE_MAX_OPS) fail("tile pass program overflow");
@@ -808,7 +835,7 @@ void* get_stream(Engine* h, const Plan& pl, int shape, int frame) {
   for (int j = 0; j < tp.nfree; j++) tp.freepos[j] = sh.freepos[j];
   if (!tilepass_set_free_runs(tp)) fail("tile shape with more than two runs of free bits");
   tp.qshift = h->qshift;
-  if (sh.zshape) tp.zbit = h->E - 1;
+  if (sh.zshape) set_zshape(h, pl, tp);
   const int cross = sh.cross ? 1 : 0;
   if (cross && !h->peers_diag_set) fail("sharded engine: peer cost-diagonal pointers have not been set");
   shard_fill(h, tp, sh.cross);
@@ -1487,7 +1514,6 @@ int qaoa_create_sharded(int n_qubits, int dtype, int device, int rank, int world
     CUDA_OK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     h->init = make_gen(h, INIT_PLUS, 0, nullptr, &h->init_vec);
     h->sub = h->init;
-    if (world > 1) ensure_state(h, 1);   // peers map it before the first evaluation
     *out = h;
   } catch (const std::string& e) {
     g_global_error = e;
@@ -1532,6 +1558,25 @@ int qaoa_set_option(qaoa_engine_t* h, const char* key, double value) {
   else if (k == "schedule") { h->schedule = (int)value; free_streams(h); invalidate(h); }
   else if (k == "feasible_subspace") h->compact_enabled = value != 0;
   else if (k == "symmetric") { h->z2_enabled = value != 0; invalidate(h); }
+  else if (k == "shard_symmetric") {
+    // Sharded symmetric register: to be set right after qaoa_create_sharded (before the state buffer is exported
+    // and before the cost function is set).  The engine then holds 2^(n-1-gbits) stored amplitudes.
+    if ((value != 0) != (h->ztw_mode != 0)) {
+      if (value == 0) fail("shard_symmetric cannot be switched off again");
+      if (h->world < 2) fail("shard_symmetric applies to sharded engines (unsharded engines choose the symmetric register themselves)");
+      if (h->dtype != QAOA_DTYPE_C64) fail("shard_symmetric: complex64 only");
+      if (h->n & 1) fail("shard_symmetric: the number of qubits must be even");
+      if (h->El - 1 < TILE_BITS + 1) fail("shard_symmetric: every shard of the stored half must hold more than 14 qubits");
+      if (h->peers_state_set || h->peers_diag_set || h->dinfo.kind != DIAG_NONE) fail("shard_symmetric must be set before peers / cost function");
+      if (h->state) { cudaFree(h->state); h->state = nullptr; h->state_bytes = 0; }
+      h->ztw_mode = 1;
+      h->N >>= 1;
+      h->El -= 1;
+      h->x0 = (size_t)h->rank << h->El;
+      ensure_state(h, 1);
+      invalidate(h);
+    }
+  }
   else fail("unknown option: " + k);
   API_END(h)
 }
@@ -1592,10 +1637,18 @@ int qaoa_set_cost_maxkcut(qaoa_engine_t* h, int n_nodes, int n_edges, const int3
   h2d(h, dw, w, n_edges * 8);
   D.eu = du; D.ev = dv; D.ewi = dwi; D.ew = dw;
   DiagInfo gi = h->dinfo;
-  gen_maxkcut_kernel<<<grid_for(h->N, 256), 256, 0, h->stream>>>(D, h->N, h->x0, gi, h->diag);
+  if (h->ztw_mode) {
+    // the stored half (top qubit = 0) in twisted coordinates; MaxCut proper is invariant under the global flip
+    if (bits_per_node != 1 || fixed_node || lut[0] == lut[1])
+      fail("sharded symmetric register: MaxCut (one qubit per node, no fixed node) only");
+    gen_maxkcut_kernel<<<grid_for(h->N, 256), 256, 0, h->stream>>>(D, h->N, h->x0, gi, h->diag, h->El, (1u << h->gbits) - 1u);
+  } else {
+    gen_maxkcut_kernel<<<grid_for(h->N, 256), 256, 0, h->stream>>>(D, h->N, h->x0, gi, h->diag);
+  }
   CUDA_OK(cudaGetLastError());
   CUDA_OK(cudaStreamSynchronize(h->stream));
   h->launches += 1;
+  if (h->ztw_mode) h->cost_symmetric = 1;
   API_END(h)
 }
 
@@ -1647,6 +1700,7 @@ int qaoa_set_cost_maxkcut_terms(qaoa_engine_t* h, int n_nodes, int n_edges, cons
 int qaoa_set_cost_qubo(qaoa_engine_t* h, int n, const double* Q, const double* c, double b) {
   API_BEGIN(h)
   if (n != h->n) fail("QUBO size does not match the engine's qubit count");
+  if (h->ztw_mode) fail("sharded symmetric register: MaxCut cost functions only");
   if (!Q) fail("Q is null");
   std::vector<double> d(n), M((size_t)n * n, 0.0);
   double lo = b, hi = b;  // bounds of f = x^T Q x + c^T x + b
@@ -1966,7 +2020,7 @@ int qaoa_shard_info(qaoa_engine_t* h, int* rank, int* world, int* local_qubits) 
   API_BEGIN(h)
   if (rank) *rank = h->rank;
   if (world) *world = h->world;
-  if (local_qubits) *local_qubits = h->n - h->gbits;
+  if (local_qubits) *local_qubits = h->El - h->qshift;
   API_END(h)
 }
 

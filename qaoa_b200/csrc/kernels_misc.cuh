@@ -28,9 +28,13 @@ __device__ __forceinline__ int node_colour(const MaxKCutDev& D, unsigned long lo
 }
 
 // x0: first basis index of the slice this engine holds (sharded registers; 0 otherwise)
-__global__ void gen_maxkcut_kernel(MaxKCutDev D, size_t N, size_t x0, DiagInfo info, void* out) {
+// tw_mask != 0: twisted shard coordinates (tile_kernel.cuh): local indices with bit 0 set belong to the basis index
+// whose rank bits (at tw_shift) are complemented.
+__global__ void gen_maxkcut_kernel(MaxKCutDev D, size_t N, size_t x0, DiagInfo info, void* out, int tw_shift = 0,
+                                   unsigned tw_mask = 0) {
   for (size_t xl = blockIdx.x * (size_t)blockDim.x + threadIdx.x; xl < N; xl += (size_t)gridDim.x * blockDim.x) {
-    const size_t x = x0 + xl;
+    size_t x = x0 + xl;
+    if (tw_mask != 0 && (xl & 1)) x ^= (size_t)tw_mask << tw_shift;
     if (info.kind == DIAG_U8) {
       int s = 0;
       for (int e = 0; e < D.n_edges; e++) {

@@ -96,6 +96,12 @@ struct TilePass {
   // qubit (0 = off); it is tile bit 13 of the low tile shape and of no other shape.
   int zbit;
   int zsign;                            // i^(2-n) = +1 / -1 (n even)
+  int znreal;                           // stored qubits of the WHOLE register (n - 1)
+  // Sharded symmetric registers ("twisted" coordinates, see below): rank bit j of a stored index is
+  // x'[EL + j] XOR x'[0], so that the mirror image of a shard is the shard itself.
+  int zdelta;                           // g - 2 popc(rank): popcount owed by elements with index bit 0 set (0: untwisted)
+  int ztw;                              // 1: sigma does not alternate with index bit 0 (g odd)
+  int xgbits;                           // cross pass of a twisted register: g (its rounds are twisted rounds), else 0
   // element offsets of the upper register bits, precomputed by the host (tilepass_set_offsets): frames A / B
   // (register bits 1..4) and A4 (register bits 0..4) -- constant-bank operands instead of per-tile shifts
   unsigned long long roffe[2][4];
@@ -272,6 +278,17 @@ __device__ __forceinline__ size_t stream_chunk(unsigned tile, int warp, int lane
 // Inside the mirror image a virtual tile bit = 0 is a REAL qubit bit = 1, so the two elements of every ordinary
 // butterfly change roles there: mirrored elements (register bit 4 in frame A, lane bit 4 after its warp
 // transpose, warp bit 3 in frames B and C) take t -> -t in every round of the low tile.
+//
+// Sharded symmetric registers (complex64): a plain split of the stored half on its top g bits would put the mirror
+// image of rank r's shard on rank ~r.  Instead the shards use TWISTED coordinates: stored index x' <-> (z, r) with
+// z = the EL low bits of x' and rank bit r_j = x'[EL + j] XOR x'[0].  Complementing x' complements z and leaves r
+// alone, so every shard is a symmetric register of its own (virtual bit = local element bit EL) and the low-tile
+// passes never leave the GPU.  What changes (the S frame is still i^popc(x')):
+//   * popc(x') = popc(z) + popc(r) + z_0 * zdelta, zdelta = g - 2 popc(r)   (INIT; sigma loses its z_0 factor for odd g)
+//   * qubit 0 pairs (z_0 = 0, r) with (z_0 = 1, ~r): it is mixed in the CROSS passes, where z_0 and the rank bits
+//     are all register bits of frame A (round_xtw_*), and is idle in the low tile;
+//   * a rank qubit j is 0 where r_j = z_0: its butterflies take t -> -t in registers with z_0 = 1.
+// The cost diagonal is generated in the same coordinates (gen_maxkcut_kernel, tw_mask).
 struct Z2Addr {
   size_t b0, b1;    // pair base with the register's t13 clear / set (frame A); frame B: b0 only
   size_t roff[4];   // frame A: offsets of t10..t12; frame B: offsets of t6..t9, negated in mirrored threads
@@ -355,6 +372,7 @@ struct Ctx {
   unsigned wt_st, wt_ld, bt_st, bt_ld;
   size_t thr[5];   // hoisted per-thread element offsets for frames A, B, C, A4, C4
   real zsig;       // symmetric registers: sigma of (this thread, register 0) in frame A, see round_static
+  real zsigo;      // ... of register 1 (= -zsig unless the shard is twisted with an odd number of rank bits)
 };
 
 template <typename Elem>
@@ -439,7 +457,8 @@ __device__ __forceinline__ void xt_c_to_a(const Ctx<Elem>& c, Elem (&v)[32]) {
 template <typename Elem, int MASK, bool ZS = false, bool ZR = false, bool ZT = false>
 __device__ __forceinline__ void round_static(const typename ElemTraits<Elem>::real* tau_s, Elem (&v)[32], int round,
                                              typename ElemTraits<Elem>::real zsig = 0,
-                                             typename ElemTraits<Elem>::real msign = 1) {
+                                             typename ElemTraits<Elem>::real msign = 1,
+                                             typename ElemTraits<Elem>::real zsigo = 0) {
   typedef typename ElemTraits<Elem>::real real;
   const real* rp = tau_s + round * TILE_ROUND_REALS;
 #pragma unroll
@@ -447,11 +466,12 @@ __device__ __forceinline__ void round_static(const typename ElemTraits<Elem>::re
     if (ZS && s == 4 && (MASK & 16)) {
       // symmetric register, frame A: slot 4 pairs an element with its mirror image, t -> t * sigma(x');
       // sigma alternates with the parity of the amplitude's index bits held in the register number
-      constexpr int QS = ElemTraits<Elem>::IS_C64 ? 0 : 1;
-      const real tz = rp[4] * zsig;
+      // (zsigo: sigma of register 1 = -zsig, except in twisted shards with an odd number of rank bits)
+      const real tz = rp[4] * zsig, tzo = ElemTraits<Elem>::IS_C64 ? rp[4] * zsigo : tz;
 #pragma unroll
       for (int i = 0; i < 16; i++) {
-        const real tt = (__builtin_popcount(i >> QS) & 1) ? -tz : tz;
+        const real tb = (ElemTraits<Elem>::IS_C64 && (i & 1)) ? tzo : tz;
+        const real tt = (__builtin_popcount(i >> 1) & 1) ? -tb : tb;
         Elem a = v[i], b = v[i | 16];
         v[i] = efma(tt, b, a);
         v[i | 16] = efma(-tt, a, b);
@@ -475,6 +495,15 @@ __device__ __forceinline__ void round_static(const typename ElemTraits<Elem>::re
 __device__ __forceinline__ float2 esign(float s, float2 a) { return make_float2(s * a.x, s * a.y); }
 __device__ __forceinline__ double esign(double s, double a) { return s * a; }
 
+// sigma of register i (frame A, i < 16) relative to the thread: alternates with the popcount of the amplitude's index
+// bits held in the register number (twisted shards with odd g: not with index bit 0)
+template <typename Elem>
+__device__ __forceinline__ typename ElemTraits<Elem>::real z2_sigma_reg(const Ctx<Elem>& c, int i) {
+  typedef typename ElemTraits<Elem>::real real;
+  const real b = (ElemTraits<Elem>::IS_C64 && (i & 1)) ? c.zsigo : c.zsig;
+  return (__builtin_popcount(i >> 1) & 1) ? -b : b;
+}
+
 // Symmetric registers (Z): zslot = slot 4 of this round is the mirror pairing (frame A; see round_static): the
 // mirrored partner enters and leaves the butterfly multiplied by sigma = +-1, which covers both forms.  Mirrored
 // elements of ordinary slots (zr: registers 16..31; otherwise the whole thread when msign = -1) have the roles of
@@ -485,7 +514,6 @@ __device__ __forceinline__ void round_dynamic(const Ctx<Elem>& c, Elem (&v)[32],
   typedef typename ElemTraits<Elem>::real real;
   const real* rp = c.tau + round * TILE_ROUND_REALS;
   const int forms = (int)__ldg(rp + 10);
-  constexpr int QS = ElemTraits<Elem>::IS_C64 ? 0 : 1;
 #pragma unroll
   for (int s = 0; s < 5; s++) {
     const real k1 = __ldg(rp + s), k2 = __ldg(rp + 5 + s);
@@ -494,7 +522,7 @@ __device__ __forceinline__ void round_dynamic(const Ctx<Elem>& c, Elem (&v)[32],
 #pragma unroll
       for (int i = 0; i < 32; i++) {
         if (!(i & (1 << s))) {
-          real sg = vslot ? ((__builtin_popcount(i >> QS) & 1) ? -c.zsig : c.zsig)
+          real sg = vslot ? z2_sigma_reg<Elem>(c, i)
                           : (zr ? ((i & 16) ? (real)-1 : (real)1) : msign);
           v[i | (1 << s)] = esign(sg, v[i | (1 << s)]);
         }
@@ -523,11 +551,76 @@ __device__ __forceinline__ void round_dynamic(const Ctx<Elem>& c, Elem (&v)[32],
 #pragma unroll
       for (int i = 0; i < 32; i++) {
         if (!(i & (1 << s))) {
-          real sg = vslot ? ((__builtin_popcount(i >> QS) & 1) ? -c.zsig : c.zsig)
+          real sg = vslot ? z2_sigma_reg<Elem>(c, i)
                           : (zr ? ((i & 16) ? (real)-1 : (real)1) : msign);
           v[i | (1 << s)] = esign(sg, v[i | (1 << s)]);
         }
       }
+    }
+  }
+}
+
+// ---- cross passes of a twisted (sharded symmetric) register, frame A: register bit 0 is z_0, the top G register
+// bits are the rank bits.  Rank qubit butterflies take t -> -t where z_0 = 1; qubit 0 pairs register i (z_0 = 0)
+// with register i ^ (1 | rank bits); the remaining slots are ordinary local qubits.  Coefficients: slot s of the
+// round as usual (slot 0 = qubit 0).
+template <typename Elem, int G>
+__device__ __forceinline__ void round_xtw_static(const typename ElemTraits<Elem>::real* tau_s, Elem (&v)[32], int round) {
+  typedef typename ElemTraits<Elem>::real real;
+  const real* rp = tau_s + round * TILE_ROUND_REALS;
+  constexpr int RM = (0x1f << (5 - G)) & 0x1f;
+#pragma unroll
+  for (int s = 1; s < 5; s++) {   // slots below 5 - G are ordinary local qubits (the planner may place some here)
+    const real t = rp[s];
+#pragma unroll
+    for (int i = 0; i < 32; i++) {
+      if (!(i & (1 << s))) {
+        const real tt = (s >= 5 - G && (i & 1)) ? -t : t;
+        Elem a = v[i], b = v[i | (1 << s)];
+        v[i] = efma(tt, b, a);
+        v[i | (1 << s)] = efma(-tt, a, b);
+      }
+    }
+  }
+  const real t0 = rp[0];
+#pragma unroll
+  for (int i = 0; i < 32; i += 2) {
+    Elem a = v[i], b = v[i ^ (1 | RM)];
+    v[i] = efma(t0, b, a);
+    v[i ^ (1 | RM)] = efma(-t0, a, b);
+  }
+}
+
+template <typename Elem, int G>
+__device__ __forceinline__ void round_xtw_dynamic(const Ctx<Elem>& c, Elem (&v)[32], int round) {
+  typedef typename ElemTraits<Elem>::real real;
+  const real* rp = c.tau + round * TILE_ROUND_REALS;
+  const int forms = (int)__ldg(rp + 10);
+  constexpr int RM = (0x1f << (5 - G)) & 0x1f;
+  auto bfly = [&](Elem& a, Elem& b, real k1, real k2, bool cot) {
+    Elem x = a, y = b;
+    if (cot) { a = efma(k1, x, y); b = efma(k2, y, eneg(x)); }       // a' = k1 a + b ; b' = k2 b - a
+    else { a = efma(k1, y, x); b = efma(k2, x, y); }                 // a' = a + k1 b ; b' = b + k2 a
+  };
+#pragma unroll
+  for (int s = 1; s < 5; s++) {   // slots below 5 - G are ordinary local qubits
+    const real k1 = __ldg(rp + s), k2 = __ldg(rp + 5 + s);
+    const bool cot = (forms >> s) & 1;
+    if (!cot && k1 == (real)0 && k2 == (real)0) continue;
+#pragma unroll
+    for (int i = 0; i < 32; i++) {
+      if (!(i & (1 << s))) {
+        if (s >= 5 - G && (i & 1)) bfly(v[i | (1 << s)], v[i], k1, k2, cot);   // z_0 = 1: the element with the rank bit SET has the qubit = 0
+        else bfly(v[i], v[i | (1 << s)], k1, k2, cot);
+      }
+    }
+  }
+  {
+    const real k1 = __ldg(rp), k2 = __ldg(rp + 5);
+    const bool cot = forms & 1;
+    if (cot || k1 != (real)0 || k2 != (real)0) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) bfly(v[i], v[i ^ (1 | RM)], k1, k2, cot);
     }
   }
 }
@@ -695,10 +788,12 @@ __device__ __forceinline__ void op_init(const Ctx<Elem>& c, Elem (&v)[32], int f
   for (int a = 0; a < NAMP; a++) {
     // tile bits are distinct element bits: popcount(x) = popcount(thread part) + popcount(reg part)
     const int regbits = ElemTraits<Elem>::IS_C64 ? a : (a << 1);
-    int pc = pc0 + __popc(regbits >> P.qshift);
+    // (twisted shards, complex64: elements with index bit 0 set owe zdelta more, see "twisted coordinates")
+    const int tw = (regbits & 1) ? P.zdelta : 0;
+    int pc = pc0 + __popc(regbits >> P.qshift) + tw;
     // symmetric register (INIT runs in frame A): register bit 4 is the virtual bit, the stored index of
     // such an element is the complement of its n-1 real qubit bits
-    if (P.zbit != 0 && (regbits & 16)) pc = (P.zbit - P.qshift) - (pc0 + __popc((regbits & 15) >> P.qshift));
+    if (P.zbit != 0 && (regbits & 16)) pc = P.znreal - (pc0 + __popc((regbits & 15) >> P.qshift)) - tw;
     real re = A, im = (real)0;
     if (P.init_kind == INIT_DICKE && pc != P.dicke_k) re = (real)0;
     mul_i_pow(re, im, pc);
@@ -782,16 +877,25 @@ __device__ __forceinline__ void op_init_phase_plus(const Ctx<Elem>& c, Elem (&v)
   const TilePass& P = *c.P;
   const size_t e0 = c.base + c.thr[0];
   const int pc0 = __popcll((unsigned long long)(e0 >> P.qshift)) + P.rank_popc;
-  const cplx* tab4 = reinterpret_cast<const cplx*>(c.smem + TileSmem<Elem>::STAGE_OFF);
-  const cplx* tb[4];
+  const unsigned char* tab4 = c.smem + TileSmem<Elem>::STAGE_OFF;
+  constexpr unsigned TB = 256 * (unsigned)sizeof(cplx);   // bytes per rotated table; tables are addressed by byte offset
+  unsigned tb[4];
 #pragma unroll
-  for (int j = 0; j < 4; j++) tb[j] = tab4 + ((pc0 + j) & 3) * 256;
+  for (int j = 0; j < 4; j++) tb[j] = ((pc0 + j) & 3) * TB;
   // symmetric register: amplitudes whose top index bit (the virtual tile bit) is set are stored at the
   // complemented index: popc = (n-1) - popc(thread part) - popc(low register part)
   constexpr int VB = NAMP / 2;
-  const cplx* tm[4];
+  unsigned tm[4];
 #pragma unroll
-  for (int j = 0; j < 4; j++) tm[j] = Z2 ? tab4 + (((P.zbit - P.qshift) - pc0 - j) & 3) * 256 : tab4;
+  for (int j = 0; j < 4; j++) tm[j] = Z2 ? ((P.znreal - pc0 - j) & 3) * TB : 0u;
+  // twisted shards (complex64): amplitudes with index bit 0 set owe zdelta more (mirrored ones: less)
+  constexpr bool TW = Z2 && ElemTraits<Elem>::IS_C64;
+  unsigned tbo[4], tmo[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    tbo[j] = TW ? ((pc0 + P.zdelta + j) & 3) * TB : 0u;
+    tmo[j] = TW ? ((P.znreal - pc0 - P.zdelta - j) & 3) * TB : 0u;
+  }
 #pragma unroll
   for (int j = 0; j < NAMP / 16; j++) {
     const unsigned ww[4] = {dq[j].x, dq[j].y, dq[j].z, dq[j].w};
@@ -799,8 +903,10 @@ __device__ __forceinline__ void op_init_phase_plus(const Ctx<Elem>& c, Elem (&v)
     for (int b = 0; b < 16; b++) {
       const int a = j * 16 + b;
       const unsigned k = (ww[b >> 2] >> (8 * (b & 3))) & 0xffu;
-      const cplx* tsel = (Z2 && (a & VB)) ? tm[__builtin_popcount(a & (VB - 1)) & 3] : tb[__builtin_popcount(a) & 3];
-      const cplx ph = tsel[k];   // amplitude index bits are distinct element bits
+      const bool odd = TW && (a & 1);
+      const unsigned tsel = (Z2 && (a & VB)) ? (odd ? tmo : tm)[__builtin_popcount(a & (VB - 1)) & 3]
+                                             : (odd ? tbo : tb)[__builtin_popcount(a) & 3];
+      const cplx ph = *reinterpret_cast<const cplx*>(tab4 + tsel + k * (unsigned)sizeof(cplx));
       amp_set(v, a, (real)ph.x, (real)ph.y);
     }
   }
@@ -1059,8 +1165,9 @@ __device__ __forceinline__ void ctx_set_tile(Ctx<Elem>& c, unsigned long long id
   c.base = tile_base(P, c.tile + P.tile0);
   if (P.zbit != 0) {   // sigma of (this thread, register 0) in frame A
     typedef typename ElemTraits<Elem>::real real;
-    const int par = __popcll((unsigned long long)((c.base + c.thr[0]) >> P.qshift)) & 1;
+    const int par = (__popcll((unsigned long long)((c.base + c.thr[0]) >> P.qshift)) + P.rank_popc) & 1;
     c.zsig = (real)((par ? -1 : 1) * P.zsign);
+    c.zsigo = P.ztw ? c.zsig : -c.zsig;
   }
 }
 
@@ -1251,6 +1358,12 @@ tile_pass_kernel(const __grid_constant__ TilePass P, Elem* __restrict__ state, s
           const bool zr = fcur == 0 && !wt;
           const bool mir = (fcur == 0 ? (c.lane & 16) : (c.warp & 8)) != 0;
           round_dynamic<Elem, true>(c, v, cur.arg, zr && cur.frame == 1, zr, (!zr && mir) ? (real_t)-1 : (real_t)1);
+        } else if constexpr (CROSS == 1) {
+          const int xg = P.xgbits;
+          if (xg == 0) round_dynamic<Elem>(c, v, cur.arg);
+          else if (xg == 1) round_xtw_dynamic<Elem, 1>(c, v, cur.arg);
+          else if (xg == 2) round_xtw_dynamic<Elem, 2>(c, v, cur.arg);
+          else round_xtw_dynamic<Elem, 3>(c, v, cur.arg);
         } else {
           round_dynamic<Elem>(c, v, cur.arg);
         }
@@ -1519,7 +1632,13 @@ struct ProgExec {
           constexpr bool ZS = ZR && (op.mask & 16) != 0;  // ... and slot 4 is the mirror pairing
           real ms = (real)1;
           if constexpr (!ZR) ms = ((fb == 8 ? (c.lane & 16) : (c.warp & 8)) != 0) ? (real)-1 : (real)1;
-          round_static<Elem, op.mask, ZS, ZR, !ZR>(tau_s, v, op.arg, c.zsig, ms);
+          round_static<Elem, op.mask, ZS, ZR, !ZR>(tau_s, v, op.arg, c.zsig, ms, c.zsigo);
+        } else if constexpr (CROSS == 1) {
+          const int xg = c.P->xgbits;   // twisted shards: qubit 0 and sign-twisted rank qubits (uniform branch)
+          if (xg == 0) round_static<Elem, op.mask>(tau_s, v, op.arg);
+          else if (xg == 1) round_xtw_static<Elem, 1>(tau_s, v, op.arg);
+          else if (xg == 2) round_xtw_static<Elem, 2>(tau_s, v, op.arg);
+          else round_xtw_static<Elem, 3>(tau_s, v, op.arg);
         } else {
           round_static<Elem, op.mask>(tau_s, v, op.arg);
         }

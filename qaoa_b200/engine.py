@@ -119,7 +119,7 @@ def _dptr(a):
 class Engine:
     """One device-resident QAOA register of ``n_qubits`` qubits on ``cuda:device``."""
 
-    def __init__(self, n_qubits, dtype="complex64", device=0, rank=0, world=1):
+    def __init__(self, n_qubits, dtype="complex64", device=0, rank=0, world=1, shard_symmetric=False):
         self._lib = load_library()
         self._h = ctypes.c_void_p()
         self.n_qubits = int(n_qubits)
@@ -134,6 +134,12 @@ class Engine:
         if rc != 0:
             raise EngineError(self._lib.qaoa_global_error().decode())
         self.local_qubits = self.n_qubits - (self.world.bit_length() - 1)
+        self.shard_symmetric = bool(shard_symmetric)
+        if self.shard_symmetric:
+            # sharded symmetric register (MaxCut + X / multi-angle X + |+>, n even, complex64): each rank holds
+            # 2^(n-1-log2 world) stored amplitudes in twisted coordinates (csrc/tile_kernel.cuh)
+            self.set_option("shard_symmetric", 1)
+            self.local_qubits -= 1
 
     # -- plumbing ---------------------------------------------------------
     def _check(self, rc):

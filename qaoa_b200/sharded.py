@@ -79,9 +79,11 @@ class _ShardedSurface:
 class LocalShardGroup(_ShardedSurface):
     """All ``world`` ranks inside this process (``devices[r]`` = CUDA device of rank r, default all 0)."""
 
-    def __init__(self, n_qubits, world, dtype="complex64", devices=None, engine_factory=None):
+    def __init__(self, n_qubits, world, dtype="complex64", devices=None, engine_factory=None, symmetric=False):
         devices = [0] * world if devices is None else list(devices)
-        make = engine_factory or (lambda r: _eng.Engine(n_qubits, dtype=dtype, device=devices[r], rank=r, world=world))
+        make = engine_factory or (lambda r: _eng.Engine(n_qubits, dtype=dtype, device=devices[r], rank=r, world=world,
+                                                        shard_symmetric=symmetric))
+        self.symmetric = bool(symmetric)
         self.n_qubits, self.world = int(n_qubits), int(world)
         self.engines = [make(r) for r in range(world)]
         ptrs = [e.shard_local_ptr(0) for e in self.engines]
@@ -127,16 +129,18 @@ class LocalShardGroup(_ShardedSurface):
 class DistShardedEngine(_ShardedSurface):
     """This process' shard of a register spread over ``torch.distributed`` ranks (one process per GPU)."""
 
-    def __init__(self, n_qubits, dtype="complex64", device=None, group=None, engine_factory=None):
+    def __init__(self, n_qubits, dtype="complex64", device=None, group=None, engine_factory=None, symmetric=False):
         import torch.distributed as dist
 
+        self.symmetric = bool(symmetric)
         self._dist = dist
         self.group = group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         if device is None and engine_factory is None:
             import torch
             device = torch.cuda.current_device()
-        make = engine_factory or (lambda r, w: _eng.Engine(n_qubits, dtype=dtype, device=device, rank=r, world=w))
+        make = engine_factory or (lambda r, w: _eng.Engine(n_qubits, dtype=dtype, device=device, rank=r, world=w,
+                                                           shard_symmetric=symmetric))
         self.n_qubits = int(n_qubits)
         self.eng = make(self.rank, self.world)
         self.barriers = 0

@@ -137,3 +137,97 @@ def test_randomised_sharded_configurations_against_the_single_engine():
             assert a[2] == b[2] and a[3] == b[3]
         grp.close()
         one.close()
+
+
+def _twisted_index(z, rank, el, g):
+    """stored basis index x' of local index z on `rank` in twisted coordinates (csrc/tile_kernel.cuh)"""
+    mask = (1 << g) - 1
+    r = np.where(z & 1, rank ^ mask, rank)
+    return z | (r.astype(np.int64) << el)
+
+
+@pytest.mark.parametrize("n,world", [(20, 2), (22, 4), (22, 8), (24, 2), (26, 8), (26, 4)])
+def test_sharded_symmetric_register(n, world):
+    """MaxCut + X + |+>, n even: each rank stores 2^(n-1-g) amplitudes of the half register in twisted coordinates;
+    the mirror pairing stays inside the shard, qubit 0 is mixed in the cross passes.  Checked against the C oracle,
+    the plain sharded register and the single engine; diagonal bit-exact under the coordinate map."""
+    eng, grp_full, c_oracle, diag, edges, lut = _setup(n, world, "complex64")
+    from qaoa_b200.sharded import LocalShardGroup
+
+    g = world.bit_length() - 1
+    grp = LocalShardGroup(n, world, dtype="complex64", symmetric=True)
+    grp.set_cost_maxkcut(n, edges, 1, lut)
+    el = n - 1 - g
+    for r, e in enumerate(grp.engines):
+        assert e.local_qubits == el
+        z = np.arange(1 << el, dtype=np.int64)
+        assert np.array_equal(e.read_cost_diagonal(), diag[_twisted_index(z, r, el, g)]), "twisted diagonal differs"
+    rng = np.random.default_rng(5)
+    for p in (1, 2, 3, 4):
+        ang = rng.uniform(0, 2 * np.pi, size=2 * p)
+        ang[1::2] = rng.uniform(-1.2, 1.2, size=p)
+        ref = c_oracle.energy(n, diag, ang, "complex128")
+        got = grp.energy(ang)
+        full = grp_full.energy(ang)
+        assert any(grp.last_cross_flags)
+        assert H.rel_err(got[0], ref[0]) < 1e-4 and H.rel_err(got[1], ref[1]) < 2e-4, (p, got, ref)
+        assert got[2] == ref[2] and got[3] == ref[3]
+        assert abs(got[4] - 1) < 1e-4
+        assert H.rel_err(got[0], full[0]) < 2e-5, (got, full)
+    assert grp.engines[0].counter("state_bytes") == 8 << el
+    grp.close()
+    grp_full.close()
+
+
+def test_sharded_symmetric_multiangle_cot_form_and_interpreter():
+    """Per-qubit betas (qubit 0 and the rank qubits included), beta = pi/2 on qubit 0 / a rank qubit / the top
+    qubit (cot form -> interpreter kernels), and the interpreter forced for every pass."""
+    from oracle import c_oracle
+    from qaoa_b200 import engine as eng
+    from qaoa_b200.sharded import LocalShardGroup
+
+    n, world = 20, 4
+    edges, colors, table = H.regular_maxcut(n, seed=7)
+    lut, _ = H.lut_from_table(table, 1)
+    diag = c_oracle.maxcut_diag(n, edges)
+    rng = np.random.default_rng(9)
+    for variant in range(4):
+        grp = LocalShardGroup(n, world, dtype="complex64", symmetric=True)
+        grp.set_cost_maxkcut(n, edges, 1, lut)
+        grp.set_mixer(eng.MIXER_XMULTI)
+        p = 3
+        ang = rng.uniform(-1.0, 1.0, size=p * (1 + n))
+        ang[0::(1 + n)] = rng.uniform(0, 2 * np.pi, size=p)
+        if variant == 1:
+            ang[1 + 0] = np.pi / 2                    # qubit 0, layer 0
+            ang[(1 + n) + 1 + (n - 2)] = np.pi / 2    # a rank qubit, layer 1
+        if variant == 2:
+            ang[2 * (1 + n) + 1 + (n - 1)] = np.pi / 2   # the virtual top qubit, layer 2
+        if variant == 3:
+            grp.set_option("force_generic", 1)
+        ref = c_oracle.energy(n, diag, ang, "complex128", n_beta=n)
+        got = grp.energy(ang)
+        assert H.rel_err(got[0], ref[0]) < 1e-4 and H.rel_err(got[1], ref[1]) < 2e-4, (variant, got, ref)
+        assert abs(got[4] - 1) < 1e-4
+        grp.close()
+
+
+def test_sharded_symmetric_rejects_what_it_cannot_hold():
+    from qaoa_b200 import engine as eng
+    from qaoa_b200.sharded import LocalShardGroup
+
+    with pytest.raises(eng.EngineError):
+        LocalShardGroup(21, 2, symmetric=True)                       # odd n
+    with pytest.raises(eng.EngineError):
+        LocalShardGroup(20, 2, dtype="complex128", symmetric=True)   # complex64 only
+    grp = LocalShardGroup(20, 2, symmetric=True)
+    Q, c, b = H.random_qubo(20)
+    with pytest.raises(eng.EngineError):
+        grp.set_cost_qubo(Q, c, b)
+    edges, colors, table = H.regular_maxcut(20)
+    lut, _ = H.lut_from_table(table, 1)
+    grp.set_cost_maxkcut(20, edges, 1, lut)
+    grp.set_initial(eng.INIT_DICKE, 3)
+    with pytest.raises(eng.EngineError):
+        grp.energy([0.3, 0.2])
+    grp.close()
