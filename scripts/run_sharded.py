@@ -27,6 +27,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=1)
     ap.add_argument("--check", action="store_true")
     ap.add_argument("--low-bits", type=int, default=0, dest="low_bits")
+    ap.add_argument("--symmetric", action="store_true",
+                    help="sharded symmetric register (MaxCut + X + |+>, n even): 2^(n-1) stored amplitudes")
     args = ap.parse_args()
 
     import torch
@@ -45,7 +47,7 @@ def main():
     n, p = args.n, args.p
     G = nx.random_regular_graph(3 if n % 2 == 0 else 4, n, seed=42)   # odd n: no 3-regular graph exists
     edges = GraphHandler(G, check_isomorphism=False).edge_list()
-    E = DistShardedEngine(n, dtype=args.dtype, device=local_rank)
+    E = DistShardedEngine(n, dtype=args.dtype, device=local_rank, symmetric=args.symmetric)
     if args.low_bits:
         E.set_option("low_bits", args.low_bits)
     E.set_cost_maxkcut(n, edges, 1, np.array([0, 1], dtype=np.uint8))
@@ -71,7 +73,8 @@ def main():
                           "gb_per_launch": E.eng.counter("pass_bytes_%d" % i) / cnt / 1e9}
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    line = {"n": n, "p": p, "world": world, "dtype": args.dtype, "ms_per_eval": float(t[0]), "energy": float(-out[0]),
+    line = {"n": n, "p": p, "world": world, "dtype": args.dtype, "symmetric": bool(args.symmetric),
+            "stored_amplitudes_per_gpu": 1 << E.eng.local_qubits, "ms_per_eval": float(t[0]), "energy": float(-out[0]),
             "norm": float(out[4]), "min": float(out[2]), "max": float(out[3]), "barriers_per_eval": E.barriers / (args.reps + args.warmup),
             "passes_rank0": passes}
     if args.check and rank == 0:
