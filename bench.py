@@ -182,8 +182,16 @@ def run_sharded(args, rank, world, local_rank, dist, torch):
 
     gb = world.bit_length() - 1
     n, p = args.n + gb, args.p
+    sym = bool(args.symmetric)
+    if sym:
+        # symmetric register (MaxCut + X + |+>, n even): 2^(n-1) stored amplitudes over the N GPUs.  N = 4, 8: BASELINE
+        # config 5 itself (n = 36, p = 3); N = 2: n = 34 (n = 36 needs 128 GiB of state + 64 GiB of diagonal streams per GPU)
+        if args.n == 32:
+            n, p = (34 if world == 2 else 36), 3
+        else:   # reduced sizes (quick checks): the next even n
+            n = n + (n & 1)
     edges = workload(n)
-    E = DistShardedEngine(n, dtype="complex64", device=local_rank)
+    E = DistShardedEngine(n, dtype="complex64", device=local_rank, symmetric=sym)
     E.set_cost_maxkcut(n, edges, 1, np.array([0, 1], dtype=np.uint8))
     E.set_option("time_passes", 1)
     ang = angles_for(p, 1234)
@@ -212,7 +220,8 @@ def run_sharded(args, rank, world, local_rank, dist, torch):
     dom = max(local, key=lambda k: local[k][0])
     d_ms, d_cnt, d_bytes = local[dom]
     achieved = (d_bytes / d_cnt) / (d_ms / d_cnt * 1e-3) / 1e9
-    shard_bytes = 8.0 * 2.0 ** (n - gb)
+    lq = E.eng.local_qubits   # stored qubits per shard
+    shard_bytes = 8.0 * 2.0 ** lq
     cross = {}
     if stats["BoundX"][1]:
         ms = stats["BoundX"][0] / stats["BoundX"][1]
@@ -226,7 +235,10 @@ def run_sharded(args, rank, world, local_rank, dist, torch):
         "value": ms_dev, "ms_per_step": ms_dev, "n_gpus": world, "scaling": "weak",
         "config": {"workload": "MaxCut %d-regular n=%d seed=42, X mixer, Plus, p=%d, complex64, ONE register sharded on its top "
                                "%d qubits over %d GPUs (2^%d amplitudes = %d GiB per GPU); 1 step = 1 energy evaluation"
-                               % (3 if n % 2 == 0 else 4, n, p, gb, world, n - gb, int(shard_bytes) >> 30),
+                               % (3 if n % 2 == 0 else 4, n, p, gb, world, lq, int(shard_bytes) >> 30),
+                   "register": ("symmetric half register in twisted shard coordinates: 2^%d stored amplitudes, the mirror "
+                                "pairing of the top qubit stays on the owning GPU, qubit 0 is mixed in the cross passes" % (n - 1))
+                               if sym else "full register",
                    "l2": "shard is %d GiB >> 126 MB L2, no flush needed" % (int(shard_bytes) >> 30),
                    "energy": float(-out[0]), "norm": float(out[4]),
                    "value_is": "sum of the CUDA-event times of the pass kernels of one evaluation, max over ranks",

@@ -40,15 +40,18 @@ class B200Backend:
 
     name = "b200_statevector"
 
-    def __init__(self, device=0, dtype="complex128", sharded=False, split_batches=False):
+    def __init__(self, device=0, dtype="complex128", sharded=False, split_batches=False, shard_symmetric=True):
         """Multi-GPU modes (under ``torch.distributed``, one process per GPU, every rank driving the same
         QAOA object and seeing identical results):
-        ``sharded=True``: ONE register split on its top qubits over all ranks (qaoa_b200/sharded.py);
+        ``sharded=True``: ONE register split on its top qubits over all ranks (qaoa_b200/sharded.py); with
+        ``shard_symmetric`` (default) MaxCut + X-type mixer + |+> on an even number of qubits in complex64 stores only
+        the half register with the top qubit = 0 (same results, half the memory, HBM and NVLink traffic);
         ``split_batches=True``: every rank holds a full replica and batched evaluations (landscape grids, layer
         grid searches) are dealt out round-robin, the results gathered -- no data-path collective."""
         self.device = device
         self.dtype = dtype
         self.sharded = sharded
+        self.shard_symmetric = shard_symmetric
         self.split_batches = split_batches
 
     class _Conf:
@@ -231,7 +234,8 @@ class QAOA:
                 _reject("parameterised initial states (other than PlusParameterized)")
             if getattr(self.backend, "sharded", False):
                 from qaoa_b200.sharded import DistShardedEngine
-                eng = DistShardedEngine(self.problem.N_qubits, dtype=self.backend.dtype, device=self.backend.device)
+                eng = DistShardedEngine(self.problem.N_qubits, dtype=self.backend.dtype, device=self.backend.device,
+                                        symmetric=self._shard_symmetric())
             else:
                 eng = Engine(self.problem.N_qubits, dtype=self.backend.dtype, device=self.backend.device)
             self.problem.lower_cost(eng)
@@ -239,6 +243,20 @@ class QAOA:
             self.mixer.lower_mixer(eng, trotter=self.number_trottersteps_mixer)
             self._engine = eng
         return self._engine
+
+    def _shard_symmetric(self):
+        """MaxCut proper + X-type mixer + |+>, n even, complex64: cost(x) = cost(~x) and the state keeps that symmetry,
+        so a sharded register stores the half with the top qubit = 0 only (csrc/tile_kernel.cuh, twisted coordinates)."""
+        import torch.distributed as dist
+
+        pr, n = self.problem, self.problem.N_qubits
+        g = dist.get_world_size().bit_length() - 1 if dist.is_available() and dist.is_initialized() else 0
+        return bool(getattr(self.backend, "shard_symmetric", True) and g > 0
+                    and getattr(pr, "N_qubits_per_node", 0) == 1 and getattr(pr, "k_cuts", 0) == 2
+                    and not getattr(pr, "fix_one_node", False) and pr.get_num_parameters() == 1
+                    and type(self.mixer).__name__ in ("X", "XMultiAngle", "XOrbit")
+                    and type(self.initialstate).__name__ == "Plus"
+                    and str(self.backend.dtype) in ("complex64", "0") and n % 2 == 0 and n - 1 - g >= 15)
 
     def _evaluate(self, angle_rows):
         """(B, n_angles) FULL flat angle vectors (initial-state parameters first) -> (B, 6) = E, E2, min, max, norm, CVaR.

@@ -37,6 +37,8 @@ def main():
              backend=B200Backend(device=local_rank, dtype="complex64", sharded=True))
     q.optimize(depth=2, angles=grid)
     if rank == 0:
+        print("sharded register: %s, 2^%d stored amplitudes per GPU" % (
+            "symmetric half (twisted coordinates)" if q._get_engine().symmetric else "full", q._get_engine().eng.local_qubits))
         # same landscape on a single-GPU engine, and every iterate the sharded optimiser visited re-evaluated there
         # (comparing two optimiser RUNS is ill-posed: the seed is a symmetric grid point and rounding noise picks the branch)
         one = QAOA(problem=problems.MaxCut(G), mixer=mixers.X(), initialstate=initialstates.Plus(), optimizer=opt,
