@@ -51,7 +51,11 @@ const char* qaoa_global_error(void);
  * "force_generic", "prefetch_dist", "persistent_ctas", "low_bits", "schedule", "feasible_subspace", "time_passes",
  * "symmetric" (default 1: when cost(x) == cost(~x) -- checked on the device --, the mixer is X / multi-angle X, the
  * initial state |+> and n even, the tile path stores only the 2^(n-1) amplitudes with the top qubit = 0; results are
- * those of the full register; 0 = always store the full register). */
+ * those of the full register; 0 = always store the full register),
+ * "shard_symmetric" (sharded engines, to be set to 1 right after qaoa_create_sharded, before any buffer is exported and
+ * before the cost function is set: the engine holds 2^(n-1-log2 world) STORED amplitudes of the symmetric half register
+ * in twisted shard coordinates -- see "Sharded registers" below; complex64, n even, MaxCut cost, X / multi-angle X mixer
+ * and |+> only, anything else fails). */
 int qaoa_set_option(qaoa_engine_t* h, const char* key, double value);
 double qaoa_get_counter(qaoa_engine_t* h, const char* key); /* "launches", "bytes_alg", ... */
 
@@ -139,7 +143,14 @@ int qaoa_cost_distribution(qaoa_engine_t* h, int p, const double* angles, int n_
  *   for i < n_passes: [barrier if pass i or pass i-1 is cross]  qaoa_shard_run_pass(i); qaoa_shard_sync
  *   qaoa_shard_finish(out5) -> this rank's {sum p, sum p c, sum p c^2, min c, max c};
  *   combine over ranks with (sum, sum, sum, min, max): E[c] = S1/S0, E[c^2] = S2/S0, norm = S0.
- * Supported: X / multi-angle X mixers, Plus / Dicke initial states, every cost generator. */
+ * Supported: X / multi-angle X mixers, Plus / Dicke initial states, every cost generator.
+ *
+ * Symmetric variant (option "shard_symmetric"): for MaxCut (cost(x) = cost(~x)), X-type mixers and |+> the state obeys
+ * psi(x) = psi(~x); only the half with the top qubit = 0 is stored, split over the ranks in TWISTED coordinates: the
+ * stored index x' lives on rank r at local index z, where z = the low n-1-g bits of x' and r_j = x'[n-1-g+j] XOR x'[0].
+ * The mirror image of a shard is then the shard itself (no NVLink traffic for the top qubit's mixer), and qubit 0 is
+ * mixed inside the cross passes.  Same call sequence and results; qaoa_read_cost_diagonal and qaoa_shard_local_ptr
+ * expose the shard in (z) order; qaoa_shard_info reports n-1-g local qubits. */
 int qaoa_create_sharded(int n_qubits, int dtype, int device, int rank, int world, qaoa_engine_t** out);
 int qaoa_shard_info(qaoa_engine_t* h, int* rank, int* world, int* local_qubits);
 int qaoa_shard_local_ptr(qaoa_engine_t* h, int which, void** out);
