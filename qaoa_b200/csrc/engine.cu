@@ -84,6 +84,7 @@ struct Plan {
   size_t tau_per_point = 0;  // reals over all passes
   size_t phs_per_point = 0;  // doubles over all passes
   bool z2 = false;           // symmetric register: 2^(n-1) stored amplitudes (tile_kernel.cuh)
+  int kx = 0;                // sharded registers: local bits carried by the cross tile (build_plan)
 };
 
 struct Engine {
@@ -153,6 +154,7 @@ struct Engine {
   // Sharded symmetric register (option "shard_symmetric", tile_kernel.cuh "twisted coordinates"): the engine holds
   // 2^(n-1-gbits) STORED amplitudes; N, El and x0 describe that stored shard, E still counts the virtual top qubit.
   int ztw_mode = 0;
+  int cross_spare = 1;       // option "cross_spare": let the cross tile carry spare local bits (build_plan)
   size_t state_bytes = 0;
   double* d_partials = nullptr; size_t partials_cap = 0;
   double* d_out = nullptr; size_t out_cap = 0;
@@ -565,11 +567,35 @@ Plan build_plan(Engine* h, int p) {
   // register of that size; the rank bits get a shape of their own (appended below).
   pl.z2 = use_z2(h);
   const int EL = plan_el(h, pl);
+  // Sharded registers, balanced schedule: the cross tile has register slots to spare in frame A (t10 .. t13 minus
+  // the rank bits), and a qubit that lives there is mixed for BOTH layers of every cross pass -- it needs no other
+  // pass.  Move the top kx local bits into the cross tile when that lets the local shapes keep 5 low bits
+  // (256-byte rows) without an extra pass per layer: ELC = the bits the local shapes have to cover.
+  int kx = 0;
+  if (h->world > 1 && h->cross_spare && h->dtype == QAOA_DTYPE_C64 && h->schedule != 1 && h->low_bits == 0) {
+    auto counts = [&](int el, int* m4, int* m5) {
+      if (pl.z2) { *m4 = (el - 13 + 9) / 10; *m5 = (el - 13 + 8) / 9; }
+      else { *m4 = std::max(1, (el - 4 + 9) / 10); *m5 = std::max(1, (el - 5 + 8) / 9); }
+    };
+    int m4, m5;
+    counts(EL, &m4, &m5);
+    if (h->cross_spare >= 10) {   // test hook: force k = cross_spare - 10 spare bits
+      kx = std::min(h->cross_spare - 10, 4 - h->gbits);
+      kx = std::max(0, std::min(kx, EL - TILE_BITS - 1));
+    } else if (m5 != m4)
+      for (int k = 1; k <= 4 - h->gbits; k++) {
+        int a4, a5;
+        counts(EL - k, &a4, &a5);
+        if (a5 == a4 && a5 <= m4 && EL - k >= TILE_BITS + 1) { kx = k; break; }
+      }
+  }
+  const int ELC = EL - kx;
+  pl.kx = kx;
   if (pl.z2) {
     // Symmetric register: EL = E - 1 real element bits.  Shape 0 = 13 real low bits + the virtual top qubit
     // (element bit E - 1); its tiles enumerate the free bits 13 .. EL-2 (the top real bit is 0 in the plain
     // half of a tile and 1 in its mirror image).  The high shapes tile the real bits 13 .. EL-1.
-    const int nHz = EL - 13;
+    const int nHz = ELC - 13;
     const int m4 = (nHz + 9) / 10, m5 = (nHz + 8) / 9;
     int clow = (m5 == m4) ? 5 : 4;
     if (h->low_bits == 4 || h->low_bits == 5) clow = h->low_bits;
@@ -584,7 +610,7 @@ Plan build_plan(Engine* h, int p) {
     for (int i = 0; i < mh; i++) {
       std::vector<int> bits;
       for (int b = 0; b < clow; b++) bits.push_back(b);
-      int lo = 13 + hper * i, hi = std::min(EL, lo + hper);
+      int lo = 13 + hper * i, hi = std::min(ELC, lo + hper);
       std::vector<int> own;
       for (int b = lo; b < hi; b++) own.push_back(b);
       int padb = lo - 1;
@@ -598,17 +624,17 @@ Plan build_plan(Engine* h, int p) {
       pl.shapes.push_back(s);
     }
   }
-  const int m4 = std::max(1, (EL - 4 + 9) / 10), m5 = std::max(1, (EL - 5 + 8) / 9);
-  int clow = (m5 == m4 && EL >= 15) ? 5 : 4;
+  const int m4 = std::max(1, (ELC - 4 + 9) / 10), m5 = std::max(1, (ELC - 5 + 8) / 9);
+  int clow = (m5 == m4 && ELC >= 15) ? 5 : 4;
   if (h->low_bits == 4 || h->low_bits == 5) clow = h->low_bits;
   if (pl.z2) clow = pl.shapes[1].pos[4] == 4 ? 5 : 4;
   const int hper = TILE_BITS - clow;
-  const int nH = EL - clow;
+  const int nH = ELC - clow;
   const int m_local = pl.z2 ? 0 : std::max(1, (nH + hper - 1) / hper);
   for (int i = 0; i < m_local; i++) {
     std::vector<int> bits;
     for (int b = 0; b < clow; b++) bits.push_back(b);
-    int lo = clow + hper * i, hi = std::min(EL, lo + hper);
+    int lo = clow + hper * i, hi = std::min(ELC, lo + hper);
     std::vector<int> own;
     for (int b = lo; b < hi; b++) own.push_back(b);
     int padb = lo - 1;
@@ -627,10 +653,13 @@ Plan build_plan(Engine* h, int p) {
     // ONE contiguous run of 2^(14-gbits) elements (64 KB at 2 ranks, 16 KB at 8): peer traffic is
     // sequential, which is what NVLink and the peer TLBs want (tiles made of 256-byte rows 128 MB
     // apart ran at < 200 GB/s per direction at n = 33).
+    // (+ the top kx local bits, see above: 2^kx runs per rank)
     Shape s;
-    for (int j = 0; j < TILE_BITS - h->gbits; j++) s.pos[j] = j;
+    const int nlow = TILE_BITS - h->gbits - kx;
+    for (int j = 0; j < nlow; j++) s.pos[j] = j;
+    for (int j = 0; j < kx; j++) s.pos[nlow + j] = ELC + j;
     for (int j = 0; j < h->gbits; j++) s.pos[TILE_BITS - h->gbits + j] = EL + j;
-    for (int b = TILE_BITS - h->gbits; b < EL; b++) s.freepos.push_back(b);
+    for (int b = nlow; b < ELC; b++) s.freepos.push_back(b);
     s.cross = true;
     pl.shapes.push_back(s);
   }
@@ -1558,6 +1587,7 @@ int qaoa_set_option(qaoa_engine_t* h, const char* key, double value) {
   else if (k == "schedule") { h->schedule = (int)value; free_streams(h); invalidate(h); }
   else if (k == "feasible_subspace") h->compact_enabled = value != 0;
   else if (k == "symmetric") { h->z2_enabled = value != 0; invalidate(h); }
+  else if (k == "cross_spare") { h->cross_spare = (int)value; free_streams(h); invalidate(h); }   // 0 off, 1 auto, 10 + k: force k
   else if (k == "shard_symmetric") {
     // Sharded symmetric register: to be set right after qaoa_create_sharded (before the state buffer is exported
     // and before the cost function is set).  The engine then holds 2^(n-1-gbits) stored amplitudes.
@@ -1591,6 +1621,7 @@ double qaoa_get_counter(qaoa_engine_t* h, const char* key) {
   if (k == "compact_size") return (double)h->n_compact;
   if (k == "symmetric_plans") { double s = 0; for (auto& kv : h->plans) s += kv.second.z2 ? 1 : 0; return s; }
   if (k == "state_bytes") return (double)h->state_bytes;
+  if (k == "cross_spare_bits") { double s = 0; for (auto& kv : h->plans) s = std::max(s, (double)kv.second.kx); return s; }
   if (k == "reset") {
     h->launches = 0; h->prog_launches = 0; h->bytes_alg = 0;
     for (int i = 0; i < PROG_COUNT; i++) { h->pass_ms[i] = 0; h->pass_count[i] = 0; h->pass_bytes[i] = 0; }

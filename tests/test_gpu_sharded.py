@@ -28,8 +28,10 @@ def _setup(n, world, dtype):
     return eng, grp, c_oracle, diag, edges, lut
 
 
+# (26, 4) and (25, 2): 24 local bits, where the cross tile carries a spare local bit to keep 256-byte rows
 @pytest.mark.parametrize("n,world,dtype", [(24, 2, "complex64"), (25, 4, "complex64"), (26, 8, "complex64"),
-                                           (23, 2, "complex128"), (20, 4, "complex64"), (26, 2, "complex128")])
+                                           (23, 2, "complex128"), (20, 4, "complex64"), (26, 2, "complex128"),
+                                           (26, 4, "complex64"), (25, 2, "complex64")])
 def test_sharded_energy_matches_oracle_and_single_engine(n, world, dtype):
     eng, grp, c_oracle, diag, edges, lut = _setup(n, world, dtype)
     assert np.array_equal(grp.read_cost_diagonal(), diag), "sharded cost diagonal is not bit-exact"
@@ -175,18 +177,21 @@ def test_sharded_symmetric_register(n, world):
         assert abs(got[4] - 1) < 1e-4
         assert H.rel_err(got[0], full[0]) < 2e-5, (got, full)
     assert grp.engines[0].counter("state_bytes") == 8 << el
+    if (n, world) == (26, 4):   # 23 stored local bits: the cross tile carries one of them, the local tiles keep 5 low bits
+        assert grp.engines[0].counter("cross_spare_bits") == 1
+        assert grp_full.engines[0].counter("cross_spare_bits") == 1
     grp.close()
     grp_full.close()
 
 
-def test_sharded_symmetric_multiangle_cot_form_and_interpreter():
+@pytest.mark.parametrize("n,world", [(20, 4), (26, 4)])   # (26, 4): the cross tile carries a spare local bit
+def test_sharded_symmetric_multiangle_cot_form_and_interpreter(n, world):
     """Per-qubit betas (qubit 0 and the rank qubits included), beta = pi/2 on qubit 0 / a rank qubit / the top
     qubit (cot form -> interpreter kernels), and the interpreter forced for every pass."""
     from oracle import c_oracle
     from qaoa_b200 import engine as eng
     from qaoa_b200.sharded import LocalShardGroup
 
-    n, world = 20, 4
     edges, colors, table = H.regular_maxcut(n, seed=7)
     lut, _ = H.lut_from_table(table, 1)
     diag = c_oracle.maxcut_diag(n, edges)
@@ -230,4 +235,33 @@ def test_sharded_symmetric_rejects_what_it_cannot_hold():
     grp.set_initial(eng.INIT_DICKE, 3)
     with pytest.raises(eng.EngineError):
         grp.energy([0.3, 0.2])
+    grp.close()
+
+
+@pytest.mark.parametrize("n,world,symmetric,k", [(24, 2, True, 3), (24, 4, True, 2), (24, 2, False, 2), (23, 4, False, 2),
+                                                 (24, 8, True, 1), (22, 2, True, 0)])
+def test_cross_tile_carries_spare_local_bits(n, world, symmetric, k):
+    """The cross tile mixes the rank qubits in register slots of frame A; its spare slots may carry the top k local
+    qubits (mixed for both layers of every cross pass, needed at 33+ local bits to keep 256-byte rows).  Forced here
+    at small sizes (option cross_spare = 10 + k), multi-angle X so that every qubit's angle is its own."""
+    from oracle import c_oracle
+    from qaoa_b200 import engine as eng
+    from qaoa_b200.sharded import LocalShardGroup
+
+    edges, colors, table = H.regular_maxcut(n)
+    lut, _ = H.lut_from_table(table, 1)
+    diag = c_oracle.maxcut_diag(n, edges)
+    grp = LocalShardGroup(n, world, dtype="complex64", symmetric=symmetric)
+    grp.set_option("cross_spare", 10 + k)
+    grp.set_cost_maxkcut(n, edges, 1, lut)
+    grp.set_mixer(eng.MIXER_XMULTI)
+    rng = np.random.default_rng(17 + k)
+    for p in (1, 2, 3, 4):
+        ang = rng.uniform(-1.0, 1.0, size=p * (1 + n))
+        ang[0::(1 + n)] = rng.uniform(0, 2 * np.pi, size=p)
+        ref = c_oracle.energy(n, diag, ang, "complex128", n_beta=n)
+        got = grp.energy(ang)
+        assert H.rel_err(got[0], ref[0]) < 1e-4 and H.rel_err(got[1], ref[1]) < 2e-4, (p, got, ref)
+        assert abs(got[4] - 1) < 1e-4
+    assert grp.engines[0].counter("cross_spare_bits") == k
     grp.close()
