@@ -933,7 +933,11 @@ void fill_point_params(Engine* h, const Plan& pl, const double* ang, double* tau
       for (int s = 0; s < 5; s++) {
         if (rs.ebit[s] < 0) continue;
         const int q = rs.ebit[s] - h->qshift;
-        const double beta = beta_of(h, ang, rs.layer, q);
+        double beta = beta_of(h, ang, rs.layer, q);
+        // Symmetric register + plain X mixer: U_M(beta + pi/2) = i^n X^(xn) U_M(beta), and the global flip X^(xn) acts
+        // trivially on a state with psi(x) = psi(~x): energies have period pi/2 in beta.  Reduce beta to [-pi/4, pi/4]
+        // (|tan| <= 1: no cot form -- the reference's default grids hit beta = pi/2 exactly --, least scaling).
+        if (pl.z2 && h->mixer == MIXER_X) beta -= 1.5707963267948966 * nearbyint(beta / 1.5707963267948966);
         const double c = cos(beta), sn = sin(beta);
         if (fabs(sn) <= tmax * fabs(c)) {   // normal form: c * [[1, t], [-t, 1]]
           const double t = sn / c;

@@ -83,6 +83,30 @@ def test_symmetric_register_cot_form_and_special_angles(dtype):
         _check(off, ref, dtype, "full %s" % ang)
 
 
+def test_symmetric_register_beta_period_keeps_grids_on_the_compiled_kernels():
+    """X mixer on a symmetric register: energies have period pi/2 in beta, the engine reduces beta to [-pi/4, pi/4].
+    The reference's default landscape grids (endpoint=False, 4 | num) contain beta = pi/2 and 3 pi/2 exactly; those rows
+    must neither need the cot form (interpreter kernel) nor differ from the oracle."""
+    n = 18
+    eng, E = _engine(n, "complex64")
+    edges, colors, table = H.regular_maxcut(n)
+    lut, _ = H.lut_from_table(table, 1)
+    E.set_cost_maxkcut(n, edges, 1, lut)
+    spec = orc.Spec(n, H.maxcut_diag(n, edges, colors, table))
+    betas = np.linspace(0, 2 * np.pi, 8, endpoint=False)
+    rows = np.array([[0.8, b] for b in betas])
+    E.set_option("time_passes", 1)
+    E.counter("reset")
+    got = E.energy_batch(rows)
+    assert E.counter("symmetric_plans") >= 1
+    assert E.counter("pass_count_0") == 0, "some points fell back to the interpreter kernel"
+    for r, g in zip(rows, got):
+        ref = orc.energy(spec, r)
+        _check(g, ref, "complex64", "beta = %.4f" % r[1])
+    # period pi/2: rows 0, 2, 4, 6 (beta = 0, pi/2, pi, 3 pi/2) agree, and so do rows 1, 3, 5, 7
+    assert np.allclose(got[0::2, 0], got[0, 0], rtol=1e-5) and np.allclose(got[1::2, 0], got[1, 0], rtol=1e-5)
+
+
 @pytest.mark.parametrize("dtype", ["complex64", "complex128"])
 @pytest.mark.parametrize("n", [16, 20])
 def test_symmetric_register_multiangle_and_weights(n, dtype):
