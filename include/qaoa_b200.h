@@ -32,6 +32,8 @@ typedef struct qaoa_engine qaoa_engine_t;
 #define QAOA_MIXER_XMULTI 1  /* qaoa/mixers/x_multiangle_mixer.py:24-50 */
 #define QAOA_MIXER_XY 2      /* qaoa/mixers/xy_mixer.py:42-79           */
 #define QAOA_MIXER_GROVER 3  /* qaoa/mixers/grover_mixer.py:43-82       */
+#define QAOA_MIXER_NODE_GROVER 4 /* qaoa/mixers/maxkcut_grover_mixer.py:116-124 (tensorized=True): the Grover mixer of a
+                                    b-qubit node state on every node register, one shared beta */
 
 #define QAOA_INIT_PLUS 0         /* qaoa/initialstates/plus_initialstate.py:19-25        */
 #define QAOA_INIT_DICKE 1        /* qaoa/initialstates/dicke_initialstate.py:23-56       */
@@ -84,7 +86,9 @@ int qaoa_read_cost_diagonal(qaoa_engine_t* h, size_t offset, size_t count, doubl
 int qaoa_cost_minmax(qaoa_engine_t* h, double* out_min, double* out_max);
 
 /* pairs: XY topology as (q0,q1) pairs in application order; trotter_steps: qaoa/qaoa.py:494-503.
- * For GROVER, sub_kind/sub_k/sub_vec describe |s> = U_S|0> like qaoa_set_initial. */
+ * For GROVER, sub_kind/sub_k/sub_vec describe |s> = U_S|0> like qaoa_set_initial.
+ * For NODE_GROVER, sub_k = qubits per node (1..3, dividing n) and sub_vec = the 2^sub_k complex amplitudes of the node
+ * state (re, im interleaved); node v occupies qubits [v * sub_k, (v + 1) * sub_k). */
 int qaoa_set_mixer(qaoa_engine_t* h, int kind, const int32_t* pairs, int n_pairs, int trotter_steps,
                    int sub_kind, int sub_k, const double* sub_vec);
 /* vec: 2^n complex128 amplitudes (re,im interleaved), little-endian index; only for STATEVECTOR. */

@@ -353,6 +353,51 @@ def apply_grover(psi, s_state, beta):
     return psi
 
 
+def apply_node_grover(psi, s_node, beta):
+    """MaxKCutGrover(tensorized=True) (maxkcut_grover_mixer.py:116-124): Tensor(Grover(node state), num_V) -- the
+    Grover mixer of grover_mixer.py:43-82 on every b-qubit node register [v b, (v+1) b), one shared beta."""
+    s_node = np.asarray(s_node, dtype=np.complex128)
+    K = s_node.size
+    b = K.bit_length() - 1
+    n = psi.size.bit_length() - 1
+    U = np.eye(K, dtype=np.complex128) + (np.exp(-1j * beta) - 1.0) * np.outer(s_node, s_node.conj())
+    for v in range(n // b):
+        t = psi.reshape(1 << (n - (v + 1) * b), K, 1 << (v * b))   # axis 1 = the node's bits
+        psi[:] = np.einsum("jk,akc->ajc", U, t).reshape(-1)
+    return psi
+
+
+def feasible_node_state(k_cuts, color_encoding="LessThanK"):
+    """Uniform superposition of the feasible colour strings of one node register in the binary encodings, i.e. what
+    LessThanK (lessthank_initialstate.py:69-152) and Dicke1_2 (dicke1_2_initialstate.py:24-41) are documented to
+    prepare; the feasible set is the complement of MaxKCutFeasible.infeasible (maxkcut_feasible_initialstate.py:53-68;
+    character i of a string = qubit i of the register)."""
+    b = int(np.ceil(np.log2(k_cuts)))
+    if k_cuts == 3:
+        bad = ["11"]
+    elif k_cuts == 5:
+        bad = ["100", "111", "101"] if color_encoding == "max_balanced" else ["101", "110", "111"]
+    elif k_cuts == 6:
+        bad = ["000", "111"] if color_encoding in ("Dicke1_2", "max_balanced") else ["110", "111"]
+    elif k_cuts == 7:
+        bad = ["111"]
+    else:
+        bad = []
+    v = np.zeros(1 << b, dtype=np.complex128)
+    for x in range(1 << b):
+        if "".join("1" if (x >> i) & 1 else "0" for i in range(b)) not in bad:
+            v[x] = 1.0
+    return v / np.linalg.norm(v)
+
+
+def tensor_state(node, num):
+    """Tensor(sub, num) (tensor_initialstate.py:44-57): copy i on qubits [i m, (i+1) m)"""
+    out = np.ones(1, dtype=np.complex128)
+    for _ in range(num):
+        out = np.kron(node, out)
+    return out
+
+
 # --------------------------------------------------------------------------
 # the path:  init -> [phase(gamma_d) -> mixer(beta_d)/trotter x trotter] -> stats
 # --------------------------------------------------------------------------
@@ -361,7 +406,7 @@ def apply_grover(psi, s_state, beta):
 class Spec:
     """Bundle of (cost diagonal, mixer, initial state) — the oracle's 'plan'.
 
-    mixer: ("x",) | ("xmulti",) | ("xy", pairs) | ("grover", s_state)
+    mixer: ("x",) | ("xmulti",) | ("xy", pairs) | ("grover", s_state) | ("nodegrover", node_state)
     n_init is always 0 here (Plus / Dicke / StateVector carry no parameters).
     """
 
@@ -411,6 +456,8 @@ def evolve(spec, angles, dtype=np.complex128):
                 apply_xy_mixer(psi, spec.mixer[1], bt[0])
             elif kind == "grover":
                 apply_grover(psi, spec.mixer[1], bt[0])
+            elif kind == "nodegrover":
+                apply_node_grover(psi, spec.mixer[1], bt[0])
             else:
                 raise ValueError(kind)
         if dtype == np.complex64:

@@ -23,7 +23,14 @@ enum DiagKind : int {
 };
 
 enum InitKind : int { INIT_PLUS = 0, INIT_DICKE = 1, INIT_STATEVECTOR = 2, INIT_UNIFORM = 4 /* internal */ };
-enum MixerKind : int { MIXER_X = 0, MIXER_XMULTI = 1, MIXER_XY = 2, MIXER_GROVER = 3 };
+enum MixerKind : int { MIXER_X = 0, MIXER_XMULTI = 1, MIXER_XY = 2, MIXER_GROVER = 3, MIXER_NODE_GROVER = 4 };
+
+// Tensor product of Grover mixers over b-qubit node registers (MaxKCutGrover(tensorized=True), reference
+// qaoa/mixers/maxkcut_grover_mixer.py:116-124): the node state |s_node>, 2^b <= 8 amplitudes, in the S frame.
+struct NodeVec {
+  int bits;
+  double re[8], im[8];
+};
 
 struct DiagInfo {
   int kind;

@@ -131,6 +131,7 @@ struct Engine {
   StateGen sub{INIT_PLUS, 0, 1.0, nullptr};
   void* init_vec = nullptr;
   void* sub_vec = nullptr;
+  NodeVec node{0, {0}, {0}};   // MIXER_NODE_GROVER
 
   // plans
   std::map<int, Plan> plans;
@@ -1200,6 +1201,7 @@ void run_small_chunk(Engine* h, int p, const double* angles, int n_angles, int B
   D.trotter = h->trotter;
   D.write_state = h->keep_state;
   D.init = h->init; D.sub = h->sub;
+  D.node = h->node;
   if (h->keep_state) ensure_state(h, Bc);
   const int smem = (int)(h->N * h->amp_bytes);
   if (h->dtype == QAOA_DTYPE_C64) {
@@ -1259,6 +1261,20 @@ void run_elementwise_point(Engine* h, int p, const double* ang, double* d_out_po
       h->launches += 1;
     }
     ew(EW_AXPY | EW_REDUCE | (h->keep_state ? EW_STORE : 0), 0.0);
+  } else if (h->mixer == MIXER_NODE_GROVER) {   // tensorised Grover mixer: one sweep per node register
+    const int b = h->node.bits;
+    for (int d = 0; d < p; d++) {
+      ew((d == 0 ? EW_INIT : 0) | EW_PHASE | EW_STORE, ang[2 * d]);
+      const double beta = ang[2 * d + 1];
+      const int gg = grid_for(h->N >> b, threads);
+      for (int v = 0; v < h->n / b; v++) {
+        node_grover_kernel<real><<<gg, threads, 0, h->stream>>>(st, h->N, v * b, h->node, cos(beta) - 1.0, -sin(beta));
+        CUDA_OK(cudaGetLastError());
+        h->launches += 1;
+        h->bytes_alg += 2 * sweep;
+      }
+    }
+    ew(EW_REDUCE, 0.0);
   } else if (h->n < (h->dtype == QAOA_DTYPE_C64 ? 13 : 12)) {  // XY on a register smaller than a tile: one sweep per gate
     const int np = (int)h->pairs.size() / 2;
     for (int d = 0; d < p; d++) {
@@ -1834,7 +1850,7 @@ int qaoa_cost_minmax(qaoa_engine_t* h, double* out_min, double* out_max) {
 int qaoa_set_mixer(qaoa_engine_t* h, int kind, const int32_t* pairs, int n_pairs, int trotter_steps,
                    int sub_kind, int sub_k, const double* sub_vec) {
   API_BEGIN(h)
-  if (kind < MIXER_X || kind > MIXER_GROVER) fail("unknown mixer kind");
+  if (kind < MIXER_X || kind > MIXER_NODE_GROVER) fail("unknown mixer kind");
   if (h->world > 1 && kind != MIXER_X && kind != MIXER_XMULTI) fail("sharded engine: only the X and multi-angle X mixers are supported");
   if (trotter_steps < 1) fail("trotter_steps must be >= 1");
   invalidate(h);
@@ -1853,6 +1869,21 @@ int qaoa_set_mixer(qaoa_engine_t* h, int kind, const int32_t* pairs, int n_pairs
     h2d(h, h->d_pairs, h->pairs.data(), h->pairs.size() * 4);
   }
   if (kind == MIXER_GROVER) h->sub = make_gen(h, sub_kind, sub_k, sub_vec, &h->sub_vec);
+  if (kind == MIXER_NODE_GROVER) {   // sub_k = qubits per node, sub_vec = 2^sub_k complex amplitudes of |s_node>
+    if (sub_k < 1 || sub_k > 3 || h->n % sub_k) fail("node Grover mixer: 1..3 qubits per node, dividing the qubit count");
+    if (!sub_vec) fail("node Grover mixer: node state is null");
+    double nrm = 0.0;
+    for (int j = 0; j < (2 << sub_k); j++) nrm += sub_vec[j] * sub_vec[j];
+    if (fabs(nrm - 1.0) > 1e-8) fail("node Grover mixer: node state is not normalised");
+    h->node.bits = sub_k;
+    for (int j = 0; j < (1 << sub_k); j++) {   // S frame: s~_j = i^popc(j) s_j
+      double re = sub_vec[2 * j], im = sub_vec[2 * j + 1];
+      const int k4 = __builtin_popcount((unsigned)j) & 3;
+      const double r = re, m = im;
+      if (k4 == 1) { re = -m; im = r; } else if (k4 == 2) { re = -r; im = -m; } else if (k4 == 3) { re = m; im = -r; }
+      h->node.re[j] = re; h->node.im[j] = im;
+    }
+  }
   API_END(h)
 }
 

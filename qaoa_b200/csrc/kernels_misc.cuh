@@ -252,7 +252,40 @@ struct SmallDesc {
   int write_state; // store the final S-frame state to global memory
   StateGen init;
   StateGen sub;    // Grover |s>
+  NodeVec node;    // MIXER_NODE_GROVER: |s_node>
 };
+
+// One node register of the tensorised Grover mixer: for every group of 2^b amplitudes that differ only in the bits
+// [shift, shift + b):  psi_j += (e^{-i beta} - 1) <s_node|psi_group> s_node[j]   (k = e^{-i beta} - 1 = kr + i ki).
+// `ps`: interleaved (re, im), S frame; works on shared or global memory.
+template <typename real>
+__device__ __forceinline__ void node_grover_group(real* ps, size_t base, int shift, const NodeVec& nv, double kr, double ki) {
+  const int K = 1 << nv.bits;
+  double dr = 0.0, di = 0.0;
+  for (int j = 0; j < K; j++) {
+    const size_t x = base | ((size_t)j << shift);
+    const double re = ps[2 * x], im = ps[2 * x + 1];
+    dr += nv.re[j] * re + nv.im[j] * im;   // conj(s) * psi
+    di += nv.re[j] * im - nv.im[j] * re;
+  }
+  const double fr = kr * dr - ki * di, fi = kr * di + ki * dr;
+  for (int j = 0; j < K; j++) {
+    const size_t x = base | ((size_t)j << shift);
+    ps[2 * x] += (real)(fr * nv.re[j] - fi * nv.im[j]);
+    ps[2 * x + 1] += (real)(fr * nv.im[j] + fi * nv.re[j]);
+  }
+}
+
+// large registers: one sweep of the state per node register
+template <typename real>
+__global__ void node_grover_kernel(real* __restrict__ state, size_t N, int shift, NodeVec nv, double kr, double ki) {
+  const size_t groups = N >> nv.bits;
+  const size_t low = ((size_t)1 << shift) - 1;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < groups; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t base = ((i & ~low) << nv.bits) | (i & low);
+    node_grover_group<real>(state, base, shift, nv, kr, ki);
+  }
+}
 
 template <typename real>
 __global__ void __launch_bounds__(512, 1)
@@ -348,6 +381,19 @@ small_fused_kernel(SmallDesc D, const int* __restrict__ pairs, const double* __r
           }
           __syncthreads();
         }
+      }
+    } else if (D.mixer == MIXER_NODE_GROVER) {
+      // Grover mixer per node register, all nodes sharing beta (maxkcut_grover_mixer.py:116-124 with grover_mixer.py:43-82)
+      const double beta = ang[d * per + ng];
+      double sb, cb;
+      sincos(beta, &sb, &cb);
+      const int b = D.node.bits;
+      for (int v = 0; v < n / b; v++) {
+        const int shift = v * b;
+        const size_t low = ((size_t)1 << shift) - 1;
+        for (size_t i = tid; i < (N >> b); i += nt)
+          node_grover_group<real>(ps, ((i & ~low) << b) | (i & low), shift, D.node, cb - 1.0, -sb);
+        __syncthreads();
       }
     } else {  // MIXER_GROVER:  psi += (e^{-i beta} - 1) <s|psi> s   (grover_mixer.py:43-82)
       const double beta = ang[d * per + ng];

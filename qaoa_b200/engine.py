@@ -19,7 +19,7 @@ _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libqaoa_b2
 
 DTYPE_C64 = 0
 DTYPE_C128 = 1
-MIXER_X, MIXER_XMULTI, MIXER_XY, MIXER_GROVER = 0, 1, 2, 3
+MIXER_X, MIXER_XMULTI, MIXER_XY, MIXER_GROVER, MIXER_NODE_GROVER = 0, 1, 2, 3, 4
 INIT_PLUS, INIT_DICKE, INIT_STATEVECTOR, INIT_PLUS_PHASES = 0, 1, 2, 3
 
 _c_double_p = ctypes.POINTER(ctypes.c_double)

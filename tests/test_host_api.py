@@ -69,6 +69,9 @@ class OracleEngine:
             self.mixer, self.n_beta = ("xmulti",), n
         elif kind == eng.MIXER_XY:
             self.mixer = ("xy", [list(p) for p in pairs])
+        elif kind == eng.MIXER_NODE_GROVER:
+            assert np.asarray(sub_vec).size == 1 << sub_k and n % sub_k == 0
+            self.mixer = ("nodegrover", np.asarray(sub_vec, dtype=complex))
         else:
             s = {eng.INIT_PLUS: lambda: orc.plus_state(n), eng.INIT_DICKE: lambda: orc.dicke_state(n, sub_k),
                  eng.INIT_STATEVECTOR: lambda: np.asarray(sub_vec, dtype=complex)}[sub_kind]()
@@ -420,3 +423,28 @@ def test_get_optimal_solutions_returns_the_maximum_cuts():
     assert best == 10 and len(sols) >= 2
     assert all(q.problem.cost(s) == best for s in sols)
     assert sorted(sols) == sorted(format(x, "08b")[::-1] for x in range(256) if q.problem.cost(format(x, "08b")[::-1]) == best)
+
+
+@pytest.mark.parametrize("k,enc,tensorized", [(3, "LessThanK", True), (3, "LessThanK", False), (5, "LessThanK", True),
+                                              (6, "Dicke1_2", False), (6, "max_balanced", True), (7, "LessThanK", False)])
+def test_kcut_lego_pipeline(k, enc, tensorized):
+    """MaxKCutBinaryFullH + MaxKCutFeasible + MaxKCutGrover (both forms) through the driver.
+    Like the reference's unittests/test_maxkcut_mixers.py:24-62 the mixer must keep the state inside the feasible
+    strings; here additionally the landscape is finite and the optimiser improves on the initial state."""
+    G = nx.Graph([(0, 1), (1, 2), (0, 2), (2, 3)])
+    prob_enc = "max_balanced" if enc in ("Dicke1_2", "max_balanced") else "LessThanK"
+    problem = problems.MaxKCutBinaryFullH(G, k, prob_enc)
+    init = initialstates.MaxKCutFeasible(k, "binary", color_encoding="Dicke1_2" if prob_enc == "max_balanced" else enc)
+    mixer = mixers.MaxKCutGrover(k, problem_encoding="binary", color_encoding=enc, tensorized=tensorized)
+    q, fake = make(problem, mixer=mixer, init=init, optimizer=[__import__("qaoa_b200").utils.COBYLA, {"maxiter": 25}])
+    b = problem.N_qubits_per_node
+    assert q.problem.N_qubits == 4 * b
+    assert fake.mixer[0] == ("nodegrover" if tensorized else "grover")
+    pr = fake._prob([0.37, 0.5912847])
+    bad = set(init.infeasible)
+    for x in np.flatnonzero(pr > 1e-14):
+        s = orc.index_to_string(int(x), 4 * b)
+        assert not ({s[v * b:(v + 1) * b] for v in range(4)} & bad), s
+    q.optimize(depth=1, angles={"gamma": [0, 2 * np.pi, 6], "beta": [0, 2 * np.pi, 6]})
+    e0 = -fake.energy_batch(np.array([[0.0, 0.0]]))[0, 0]
+    assert np.isfinite(q.Exp_sampled_p1).all() and q.get_Exp(1) <= e0 + 1e-9
