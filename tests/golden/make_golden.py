@@ -89,5 +89,16 @@ def main():
     print("golden vectors written to", OUT)
 
 
+def result_file():
+    """The reference's ExactCover result file (examples/ExactCover/data/exact_cover_path_problem_example.json), a DATA
+    file written by the reference's qaoaIO, trimmed to depths 1-3: the on-disk schema qaoa_b200.utils.qaoaIO must read."""
+    with open(os.path.join(REF, "examples/ExactCover/data/exact_cover_path_problem_example.json")) as f:
+        d = json.load(f)
+    d["qaoa_params"]["depths"] = {k: v for k, v in d["qaoa_params"]["depths"].items() if k in ("1", "2", "3")}
+    with open(os.path.join(OUT, "qaoaio_result_example.json"), "w") as f:
+        json.dump(d, f, indent=1)
+
+
 if __name__ == "__main__":
     main()
+    result_file()
