@@ -5,3 +5,4 @@ from .x_multiangle_mixer import XMultiAngle
 from .grover_mixer import Grover
 from .x_orbit_mixer import XOrbit
 from .maxkcut_grover_mixer import MaxKCutGrover
+from .xy_tensor import XYTensor

@@ -51,6 +51,11 @@ class Problem(BaseProblem):
             diag[x] = self.cost("".join("1" if (x >> i) & 1 else "0" for i in range(n)))
         engine.set_cost_diagonal(diag)
 
+    def engine_gammas(self, gammas):
+        """this layer's cost parameters -> the gammas the device phase separator exp(+i gamma cost) takes (identity
+        unless the reference's phase-separator CIRCUIT realises a different multiple of its cost function)"""
+        return list(gammas)
+
     def isFeasible(self, string):
         return True
 

@@ -266,8 +266,8 @@ class QAOA:
         ``cvar`` fraction of the distribution, computed from the device's cost-value distribution."""
         rows = np.atleast_2d(np.asarray(angle_rows, dtype=np.float64))
         eng = self._get_engine()
-        if type(self.mixer).engine_betas is not Mixer.engine_betas:
-            # shared mixer parameters (XOrbit): expand every layer's betas to what the device mixer takes
+        if self._rows_need_lowering():
+            # shared mixer parameters (XOrbit) / rescaled cost parameters: the angles the device takes
             rows = np.asarray([self._engine_row(r) for r in rows], dtype=np.float64)
         world, rank, dist = 1, 0, None
         if getattr(self.backend, "split_batches", False) and not getattr(self.backend, "sharded", False):
@@ -537,17 +537,26 @@ class QAOA:
                 idx, _cost = eng.extreme_solutions(self._engine_row(result.angles[i]), want_max=True)
                 result.BestSols[i] = ["".join("1" if (int(x) >> q) & 1 else "0" for q in range(n)) for x in idx]
 
+    def _rows_need_lowering(self):
+        from qaoa_b200.problems.base_problem import Problem
+
+        gam = getattr(type(self.problem), "engine_gammas", Problem.engine_gammas)
+        return type(self.mixer).engine_betas is not Mixer.engine_betas or gam is not Problem.engine_gammas
+
     def _engine_row(self, angles):
-        """full flat angle vector -> what the device takes (shared mixer parameters expanded)"""
+        """full flat angle vector -> what the device takes (shared mixer parameters expanded, cost parameters rescaled)"""
         row = np.asarray(angles, dtype=np.float64)
-        if type(self.mixer).engine_betas is Mixer.engine_betas:
+        if not self._rows_need_lowering():
             return row
         n_gamma, n_beta = self.problem.get_num_parameters(), self.mixer.get_num_parameters()
         n_init, per = self.initialstate.get_num_parameters(), n_gamma + n_beta
         parts = [row[:n_init]]
         for d in range((len(row) - n_init) // per):
             at = n_init + d * per
-            parts += [row[at: at + n_gamma], self.mixer.engine_betas(row[at + n_gamma: at + per])]
+            gam = row[at: at + n_gamma]
+            if hasattr(self.problem, "engine_gammas"):
+                gam = np.asarray(self.problem.engine_gammas(gam), dtype=np.float64)
+            parts += [gam, self.mixer.engine_betas(row[at + n_gamma: at + per])]
         return np.concatenate(parts)
 
     def get_optimal_solutions(self):

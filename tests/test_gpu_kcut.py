@@ -110,3 +110,35 @@ def test_kcut_through_the_reference_facing_api():
     bad = set(st.infeasible)
     for s in hist:
         assert not ({s[v * 2:(v + 1) * 2] for v in range(5)} & bad), s
+
+
+@pytest.mark.parametrize("dtype", ["complex128", "complex64"])
+@pytest.mark.parametrize("num_v,k,mixer_kind", [(3, 3, "xytensor"), (4, 3, "xytensor"), (5, 3, "xytensor"), (4, 4, "xytensor"),
+                                                (3, 3, "grover"), (5, 3, "grover_tensorized"), (4, 2, "xytensor")])
+def test_onehot_maxkcut_matches_oracle(num_v, k, mixer_kind, dtype):
+    """MaxKCutOneHot + Dicke(1,k)-per-node initial state + XYTensor / MaxKCutGrover(onehot) through the driver: the
+    device gets 2 gamma (the reference's one-hot phase-separator circuit), all three register sizes of the XY path."""
+    from test_host_api import make
+
+    G = nx.gnp_random_graph(num_v, 0.7, seed=num_v)
+    for i in range(num_v - 1):
+        G.add_edge(i, i + 1)
+    rng = np.random.default_rng(7)
+    for (u, v) in G.edges():
+        G[u][v]["weight"] = float(rng.integers(1, 4))
+    def parts():
+        mixer = {"xytensor": lambda: mixers.XYTensor(k),
+                 "grover": lambda: mixers.MaxKCutGrover(k, "onehot", "max_balanced", False),
+                 "grover_tensorized": lambda: mixers.MaxKCutGrover(k, "onehot", "max_balanced", True)}[mixer_kind]()
+        return problems.MaxKCutOneHot(G, k), mixer, initialstates.MaxKCutFeasible(k, "onehot")
+    pr, mx, st = parts()
+    dev = QAOA(problem=pr, mixer=mx, initialstate=st, dtype=dtype)
+    pr, mx, st = parts()
+    ref, fake = make(pr, mixer=mx, init=st)
+    rows = rng.uniform(-1.5, 1.5, size=(4, 4))
+    got = dev._evaluate(rows)
+    want = ref._evaluate(rows)
+    tol = TOL[dtype]
+    assert np.allclose(got[:, 0], want[:, 0], rtol=tol, atol=tol), (got[:, 0], want[:, 0])
+    assert np.allclose(got[:, 2:4], want[:, 2:4])
+    assert np.array_equal(dev._get_engine().read_cost_diagonal(), pr.cost_diagonal())
