@@ -10,7 +10,8 @@ reps = int(sys.argv[3]) if len(sys.argv) > 3 else 5
 G = nx.random_regular_graph(3, n, seed=42)
 edges = [(u, v, 1.0) for u, v in G.edges()]
 ang = np.random.default_rng(1234).uniform(0, 2 * np.pi, size=2 * p)
-for sym in (1, 0):
+modes = (1,) if len(sys.argv) > 4 and sys.argv[4] == "symonly" else (1, 0)
+for sym in modes:
     E = eng.Engine(n, "complex64")
     E.set_option("symmetric", sym)
     E.set_cost_maxkcut(n, edges, 1, np.array([0, 1], dtype=np.uint8))
