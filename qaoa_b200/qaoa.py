@@ -13,7 +13,7 @@ Semantics in the exact engine:
   * ``Exp = -E[cost]`` (cvar = 1) is the shots -> infinity limit of the reference's estimate;
   * ``Var`` is the population variance (the reference's S/(W-1) is undefined without samples);
   * ``BestCost/WorstCost`` are -max/-min of the cost over the support of |psi|^2;
-  * ``noisemodel``, ``precision``, ``memorysize > 0``, ``flip``, ``post``, QNSPSA and foreign
+  * ``noisemodel``, ``precision``, ``memorysize > 0``, ``flip``, QNSPSA and foreign
     ``backend`` objects cannot be honoured by an exact statevector engine and are REJECTED
     (NotImplementedError) — nothing is ever routed to a CPU simulator.
 """
@@ -157,8 +157,6 @@ class QAOA:
             _reject("memorysize > 0 (per-shot memory)")
         if flip:
             _reject("flip=True (bit-flip boosting needs sampled histograms)")
-        if post:
-            _reject("post=True (classical post-processing of sampled histograms)")
         if getattr(problem, "N_ancilla_qubits", 0):
             _reject("problems with ancilla qubits")
         if not (0 < cvar <= 1):
@@ -207,8 +205,12 @@ class QAOA:
         self.optimization_results = {}
         self.memory_lists = []
         self.flip = False
+        from qaoa_b200.utils.flip import BitFlip
+        self.flipper = BitFlip(self.problem.N_qubits)
         self.bitflips = []
-        self.post = False
+        # classical post-processing of the final histogram (qaoa.py:852-856): K = `post` passes of greedy bit flips per
+        # sampled string; the histogram is drawn by the device sampler at the best angles of the last depth
+        self.post = post
         self.Exp_post_processed = None
         self.Var_post_processed = None
         self.samplecount_hists = {}
@@ -443,6 +445,17 @@ class QAOA:
             self.optimization_results[target].opt_time = time.perf_counter() - t0
             LOG.info("cost(depth %d = %s", target, res.fun)
             self.current_depth += 1
+
+        if self.post:
+            from qaoa_b200.utils.post import post_processing
+
+            best = self.optimization_results[self.current_depth].get_best_angles()
+            # sampler's printing order (qubit 0 last), as the reference stores its raw counts
+            samples = {s[::-1]: c for s, c in self.hist(best, self.shots).items()}
+            self.samplecount_hists[self.current_depth] = samples
+            post_processing(self, samples=samples, K=self.post)
+            self.Exp_post_processed = -self.stat.get_CVaR()
+            self.Var_post_processed = self.stat.get_Variance()
 
     def local_opt(self, angles0):
         opt = self.optimizer[0](**self.optimizer[1])

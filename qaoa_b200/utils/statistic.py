@@ -90,15 +90,28 @@ class ExactStatistic:
         self.cvar_value = None
         self.maxSols = []
         self.minSols = []
+        self._sampled = None
 
     def set_exact(self, e, e2, cmin, cmax, cvar_value=None):
         self.E, self.E2, self.minval, self.maxval = float(e), float(e2), float(cmin), float(cmax)
         self.cvar_value = cvar_value
 
+    def add_sample(self, value, weight, string):
+        """Sampled use of the same object (classical post-processing of histograms, utils/post.py): after reset() the
+        first add_sample switches to the reference's streaming statistics until the next reset()."""
+        if self._sampled is None:
+            self._sampled = Statistic(cvar=self.cvar)
+        sm = self._sampled
+        sm.add_sample(value, weight, string)
+        self.E, self.minval, self.maxval = sm.E, sm.minval, sm.maxval
+        self.maxSols, self.minSols = sm.maxSols, sm.minSols
+
     def get_E(self):
         return self.E
 
     def get_Variance(self):
+        if self._sampled is not None:
+            return self._sampled.get_Variance()
         return max(self.E2 - self.E * self.E, 0.0)
 
     def get_max(self):
@@ -114,6 +127,8 @@ class ExactStatistic:
         return self.minSols
 
     def get_CVaR(self):
+        if self._sampled is not None:
+            return self._sampled.get_CVaR()
         if self.cvar < 1:
             if self.cvar_value is None:
                 raise NotImplementedError("exact CVaR was not computed for this evaluation")

@@ -249,7 +249,7 @@ def test_xy_topology_and_trotter():
 def test_unsupported_features_are_rejected_not_rerouted():
     G = nx.random_regular_graph(3, 4, seed=1)
     P, X, I = problems.MaxCut(G), mixers.X(), initialstates.Plus()
-    for kw in ({"noisemodel": object()}, {"precision": 0.1}, {"memorysize": 10}, {"flip": True}, {"post": True},
+    for kw in ({"noisemodel": object()}, {"precision": 0.1}, {"memorysize": 10}, {"flip": True},
                {"backend": object()}):
         with pytest.raises(NotImplementedError):
             QAOA(problem=P, mixer=X, initialstate=I, **kw)
@@ -448,3 +448,38 @@ def test_kcut_lego_pipeline(k, enc, tensorized):
     q.optimize(depth=1, angles={"gamma": [0, 2 * np.pi, 6], "beta": [0, 2 * np.pi, 6]})
     e0 = -fake.energy_batch(np.array([[0.0, 0.0]]))[0, 0]
     assert np.isfinite(q.Exp_sampled_p1).all() and q.get_Exp(1) <= e0 + 1e-9
+
+
+def test_post_processing_of_the_final_histogram():
+    """post=K (reference qaoa.py:852-856, utils/post.py, utils/flip.py): the final histogram -- drawn by the sampler at
+    the best angles -- is boosted string by string with greedy bit flips; costs can only go up."""
+    from qaoa_b200.utils import BitFlip, post_process_all_depths, post_processing
+
+    np.random.seed(3)
+    q, fake = readme_qaoa(post=3, shots=400, optimizer=[__import__("qaoa_b200").utils.COBYLA, {"maxiter": 25}])
+    q.optimize(depth=1)
+    raw = q.samplecount_hists[1]
+    assert sum(raw.values()) == 400 and all(len(s) == 8 for s in raw)
+    sampled_mean = sum(q.problem.cost(s[::-1]) * c for s, c in raw.items()) / 400
+    assert q.Exp_post_processed <= -sampled_mean + 1e-12          # Exp = -mean cost
+    assert q.Exp_post_processed <= q.get_Exp(1) + 0.5 and q.Var_post_processed >= 0
+    # boosted strings are local maxima under single flips (K = 3 passes over 8 qubits is plenty for this graph)
+    hist = post_processing(q, samples=raw, K=8)
+    assert sum(hist.values()) == 400
+    for s in hist:
+        c = q.problem.cost(s[::-1])
+        for i in range(8):
+            t = s[:i] + ("1" if s[i] == "0" else "0") + s[i + 1:]
+            assert q.problem.cost(t[::-1]) <= c
+    assert -q.stat.get_CVaR() <= -sampled_mean + 1e-12
+    bf = BitFlip(4)
+    assert bf.xor("0110", "0011") == [0, 1, 0, 1]
+    bf.create_circuit([0, 1, 0, 1])
+    assert bf.flip_qubits == [0, 2]                                # position n-1-i <-> qubit i
+    means, variances = post_process_all_depths(q, K=1)
+    assert means.shape == (1,) and variances.shape == (1,) and means[0] <= -sampled_mean + 1e-9
+    # the next evaluations go back to the exact statistics
+    assert q.stat._sampled is not None
+    q.post = False
+    q.optimize(depth=2)
+    assert q.stat._sampled is None and q.get_Exp(2) <= q.get_Exp(1) + 1e-9
