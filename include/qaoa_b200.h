@@ -170,6 +170,14 @@ int qaoa_shard_run_pass(qaoa_engine_t* h, int pass);
 int qaoa_shard_sync(qaoa_engine_t* h);
 int qaoa_shard_finish(qaoa_engine_t* h, double* out5);
 
+/* Planner dump (no device needed): the tile plan the engine would build for this configuration, as JSON -- tile shapes,
+ * passes, their step programs, which qubit of which layer every butterfly round mixes, which layer's phase separator a
+ * pass applies.  options: bits 0-1 schedule (0 automatic, 1 classic, 2 balanced), bits 2-4 low_bits (0, 4, 5), bit 5 =
+ * cross_spare off.  Error text via qaoa_global_error.  Used by tests/test_planner.py (CPU) to check the planner's
+ * invariants at full BASELINE sizes. */
+int qaoa_debug_plan(int n_qubits, int dtype, int rank, int world, int symmetric, int mixer, int p, int options,
+                    char* out, size_t cap);
+
 /* Profiling hook: runs an arbitrary (type, frame, mask) step program of the tiled pass kernel and
  * returns the mean CUDA-event time per launch (scripts/tile_floor.py). */
 int qaoa_debug_tile_program(qaoa_engine_t* h, int hb, const int32_t* ops, int nops, int reps, double tau_val,

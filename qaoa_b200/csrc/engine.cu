@@ -70,6 +70,7 @@ struct PlanPass {
   int prog = PROG_GENERIC;
   bool cross = false;
   bool zshape = false;    // pass over the low tile shape of a symmetric register (virtual tile bit 13)
+  int shape_index = 0;    // Plan::shapes entry this pass tiles over
 };
 struct Shape {
   int pos[TILE_BITS];
@@ -417,6 +418,7 @@ void build_balanced(Engine* h, int p, Plan& pl) {
     Builder b;
     b.sh = &pl.shapes[shape];
     b.pp.cross = b.sh->cross;
+    b.pp.shape_index = shape;
     memset(&b.pp.tp, 0, sizeof(TilePass));
     TilePass& tp = b.pp.tp;
     for (int j = 0; j < TILE_BITS; j++) tp.pos[j] = b.sh->pos[j];
@@ -696,6 +698,7 @@ Plan build_plan(Engine* h, int p) {
     const Shape& sh = pl.shapes[best];
     PlanPass pp;
     pp.cross = sh.cross;
+    pp.shape_index = best;
     memset(&pp.tp, 0, sizeof(TilePass));
     TilePass& tp = pp.tp;
     for (int j = 0; j < TILE_BITS; j++) tp.pos[j] = sh.pos[j];
@@ -2213,6 +2216,86 @@ int qaoa_shard_finish(qaoa_engine_t* h, double* out5) {
   CUDA_OK(cudaStreamSynchronize(h->stream));
   harvest_events(h);
   API_END(h)
+}
+
+// Planner dump: builds the tile plan of a hypothetical engine WITHOUT touching a device (the planner is host code)
+// and writes it as JSON -- lets CPU tests check the planner's invariants at sizes no test can execute.
+int qaoa_debug_plan(int n_qubits, int dtype, int rank, int world, int symmetric, int mixer, int p, int options,
+                    char* out, size_t cap) {
+  if (!out || cap < 2) return 1;
+  out[0] = 0;
+  try {
+    if (n_qubits < 1 || n_qubits > QAOA_MAX_QUBITS - 1) fail("n_qubits out of range");
+    int gbits = 0;
+    while ((1 << gbits) < world) gbits++;
+    if (world < 1 || world > QAOA_MAX_RANKS || (1 << gbits) != world || rank < 0 || rank >= world) fail("bad rank / world");
+    if (mixer != MIXER_X && mixer != MIXER_XMULTI) fail("the tile planner serves the X and multi-angle X mixers");
+    if (world > 1 && n_qubits - gbits + (dtype == QAOA_DTYPE_C128 ? 1 : 0) < TILE_BITS + 1)
+      fail("sharded engine: every shard must hold more than 14 element bits");   // (as qaoa_create_sharded)
+    Engine e;
+    Engine* h = &e;
+    h->n = n_qubits; h->dtype = dtype;
+    h->qshift = dtype == QAOA_DTYPE_C128 ? 1 : 0;
+    h->E = n_qubits + h->qshift;
+    h->rank = rank; h->world = world; h->gbits = gbits;
+    h->El = h->E - gbits;
+    h->N = (size_t)1 << (n_qubits - gbits);
+    h->mixer = mixer;
+    h->init.kind = INIT_PLUS;
+    h->dinfo.kind = DIAG_U8;
+    h->cost_symmetric = symmetric ? 1 : 0;
+    h->z2_enabled = symmetric ? 1 : 0;
+    h->schedule = options & 3;                 // 0 automatic, 1 classic, 2 balanced
+    h->low_bits = (options >> 2) & 7;          // 0 automatic, 4, 5
+    h->cross_spare = (options & 32) ? 0 : 1;
+    if (symmetric && world > 1) {
+      if (dtype != QAOA_DTYPE_C64 || (n_qubits & 1) || h->El - 1 < TILE_BITS + 1) fail("no sharded symmetric register for this configuration");
+      h->ztw_mode = 1; h->N >>= 1; h->El -= 1;
+    }
+    if (world > 1) h->peers_state_set = true;
+    Plan pl = build_plan(h, p);
+    static const char* names[] = {"Generic", "FirstInit", "FirstLoad", "Interior", "Boundary", "Final", "Mid", "Bound2",
+                                  "Final2", "BoundX", "FinalX", "Bound2L4", "Final2L4"};
+    std::string js = "{";
+    js += "\"z2\": " + std::string(pl.z2 ? "true" : "false") + ", \"kx\": " + std::to_string(pl.kx) +
+          ", \"el\": " + std::to_string(plan_el(h, pl)) + ", \"qshift\": " + std::to_string(h->qshift) +
+          ", \"E\": " + std::to_string(h->E) + ", \"shapes\": [";
+    for (size_t i = 0; i < pl.shapes.size(); i++) {
+      const Shape& sh = pl.shapes[i];
+      js += std::string(i ? ", " : "") + "{\"pos\": [";
+      for (int j = 0; j < TILE_BITS; j++) js += std::string(j ? "," : "") + std::to_string(sh.pos[j]);
+      js += "], \"free\": [";
+      for (size_t j = 0; j < sh.freepos.size(); j++) js += std::string(j ? "," : "") + std::to_string(sh.freepos[j]);
+      js += "], \"cross\": " + std::string(sh.cross ? "true" : "false") + ", \"zshape\": " + (sh.zshape ? "true" : "false") + "}";
+    }
+    js += "], \"passes\": [";
+    for (size_t i = 0; i < pl.passes.size(); i++) {
+      const PlanPass& pp = pl.passes[i];
+      js += std::string(i ? ", " : "") + "{\"prog\": \"" + names[pp.prog] + "\", \"shape\": " + std::to_string(pp.shape_index) +
+            ", \"cross\": " + (pp.cross ? "true" : "false") + ", \"ops\": [";
+      for (int k = 0; k < pp.tp.nops; k++) {
+        const TileOp& op = pp.tp.ops[k];
+        js += std::string(k ? ", " : "") + "[" + std::to_string(op.type) + "," + std::to_string(op.frame) + "," +
+              std::to_string(op.arg) + "," + std::to_string(op.mask) + "]";
+      }
+      js += "], \"rounds\": [";
+      for (size_t k = 0; k < pp.rounds.size(); k++) {
+        js += std::string(k ? ", " : "") + "{\"layer\": " + std::to_string(pp.rounds[k].layer) + ", \"ebit\": [";
+        for (int t = 0; t < 5; t++) js += std::string(t ? "," : "") + std::to_string(pp.rounds[k].ebit[t]);
+        js += "]}";
+      }
+      js += "], \"phases\": [";
+      for (size_t k = 0; k < pp.phases.size(); k++) js += std::string(k ? "," : "") + std::to_string(pp.phases[k].layer);
+      js += "], \"reduce\": " + std::string(pp.has_reduce ? "true" : "false") + "}";
+    }
+    js += "]}";
+    if (js.size() + 1 > cap) fail("output buffer too small: need " + std::to_string(js.size() + 1) + " bytes");
+    memcpy(out, js.c_str(), js.size() + 1);
+  } catch (const std::string& e) {
+    g_global_error = e;
+    return 2;
+  }
+  return 0;
 }
 
 // Test / profiling hook: runs an arbitrary step program on tiles over {0..3} U [hb, hb+10) with the

@@ -83,6 +83,9 @@ def load_library():
         "qaoa_read_statevector": (ctypes.c_int, [H, _c_double_p]),
         "qaoa_debug_tile_program": (
             ctypes.c_int, [H, ctypes.c_int, _c_int32_p, ctypes.c_int, ctypes.c_int, ctypes.c_double, _c_double_p]),
+        "qaoa_debug_plan": (
+            ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                           ctypes.c_int, ctypes.c_char_p, ctypes.c_size_t]),
         "qaoa_sample": (ctypes.c_int, [H, ctypes.c_int, _c_double_p, ctypes.c_int, ctypes.c_int, _c_double_p, _c_uint64_p]),
         "qaoa_extreme_solutions": (ctypes.c_int, [H, ctypes.c_int, _c_double_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                                   _c_uint64_p, ctypes.POINTER(ctypes.c_int), _c_double_p]),
@@ -114,6 +117,22 @@ def load_library():
 
 def _dptr(a):
     return a.ctypes.data_as(_c_double_p)
+
+
+def debug_plan(n_qubits, dtype="complex64", rank=0, world=1, symmetric=True, mixer=MIXER_X, p=1, schedule=0, low_bits=0,
+               cross_spare=True):
+    """The tile plan the engine would build for this configuration (dict); needs no GPU -- the planner is host code."""
+    import json
+
+    lib = load_library()
+    dt = {"complex64": DTYPE_C64, "complex128": DTYPE_C128}.get(dtype, dtype)
+    options = (schedule & 3) | ((low_bits & 7) << 2) | (0 if cross_spare else 32)
+    buf = ctypes.create_string_buffer(1 << 20)
+    rc = lib.qaoa_debug_plan(int(n_qubits), int(dt), int(rank), int(world), int(bool(symmetric)), int(mixer), int(p),
+                             int(options), buf, len(buf))
+    if rc != 0:
+        raise EngineError(lib.qaoa_global_error().decode())
+    return json.loads(buf.value.decode())
 
 
 class Engine:
