@@ -51,6 +51,8 @@ const char* qaoa_global_error(void);
 
 /* Tunables / test hooks: "small_max_qubits", "keep_state", "batch_points", "batch_bytes",
  * "force_generic", "prefetch_dist", "persistent_ctas", "low_bits", "schedule", "feasible_subspace", "time_passes",
+ * "cross_spare" (sharded registers: 1 = the cross tile may carry spare local qubits so that the local tiles keep 256-byte
+ * rows, 0 = never, 10 + k = exactly k -- a test hook),
  * "symmetric" (default 1: when cost(x) == cost(~x) -- checked on the device --, the mixer is X / multi-angle X, the
  * initial state |+> and n even, the tile path stores only the 2^(n-1) amplitudes with the top qubit = 0; results are
  * those of the full register; 0 = always store the full register),

@@ -22,6 +22,57 @@ from typing import Dict, List, Type
 import numpy as np
 
 
+class InitMethod(Enum):
+    PLUS = "PLUS"
+    DICKE = "DICKE"
+
+
+class MixerMethod(Enum):
+    X = "X"
+    GROVER = "GROVER"
+    XYCHAIN = "XYCHAIN"
+    XYRING = "XYRING"
+
+
+@dataclass
+class DepthResult:
+    optimal_angles: List[float]
+    histogram: Dict[str, int]
+    opt_time: float  # seconds
+
+
+@dataclass
+class QAOAParameters:
+    cvar: float
+    init_method: InitMethod
+    mixer_method: MixerMethod
+    backend: str
+    optimizer: str
+    N_qubits: int
+    depths: Dict[int, DepthResult] = field(default_factory=dict)
+
+
+def _class_token(obj):
+    """'Dicke' / 'Grover' / ... from an instance: the class name, which is also what the reference derives from str(obj)"""
+    return type(obj).__name__.upper()
+
+
+def run_metadata() -> dict:
+    """when / where / on which commit a result was produced (the reference's metadata keys)"""
+    here = os.path.dirname(os.path.abspath(__file__))
+    try:
+        commit = subprocess.check_output(["git", "rev-parse", "HEAD"], cwd=here, stderr=subprocess.DEVNULL).decode().strip()
+    except Exception:
+        commit = "unknown"
+    return {
+        "timestamp": datetime.now().isoformat(timespec="seconds"),
+        "system": platform.system(), "release": platform.release(), "python_version": platform.python_version(),
+        "machine": platform.machine(), "processor": platform.processor(),
+        "conda_env": os.environ.get("CONDA_DEFAULT_ENV", "unknown"),
+        "qaoa_repo_dir": here, "qaoa_git_commit": commit,
+    }
+
+
 def _plain(obj):
     """numpy arrays / scalars / enums -> what json.dump accepts"""
     if isinstance(obj, np.ndarray):
@@ -92,40 +143,6 @@ problem_registry: Dict[str, Type[ProblemData]] = {
 }
 
 
-class InitMethod(Enum):
-    PLUS = "PLUS"
-    DICKE = "DICKE"
-
-
-class MixerMethod(Enum):
-    X = "X"
-    GROVER = "GROVER"
-    XYCHAIN = "XYCHAIN"
-    XYRING = "XYRING"
-
-
-@dataclass
-class DepthResult:
-    optimal_angles: List[float]
-    histogram: Dict[str, int]
-    opt_time: float  # seconds
-
-
-@dataclass
-class QAOAParameters:
-    cvar: float
-    init_method: InitMethod
-    mixer_method: MixerMethod
-    backend: str
-    optimizer: str
-    N_qubits: int
-    depths: Dict[int, DepthResult] = field(default_factory=dict)
-
-
-def _class_token(obj):
-    """'Dicke' / 'Grover' / ... from an instance: the class name, which is also what the reference derives from str(obj)"""
-    return type(obj).__name__.upper()
-
 
 @dataclass
 class QAOAResult:
@@ -167,20 +184,7 @@ class QAOAResult:
         return cls(problem=ProblemData.from_dict(raw["problem"]), qaoa_params=params, metadata=raw.get("metadata", {}))
 
     def _generate_metadata(self) -> dict:
-        here = os.path.dirname(os.path.abspath(__file__))
-        meta = {
-            "timestamp": datetime.now().isoformat(timespec="seconds"),
-            "system": platform.system(), "release": platform.release(), "python_version": platform.python_version(),
-            "machine": platform.machine(), "processor": platform.processor(),
-            "conda_env": os.environ.get("CONDA_DEFAULT_ENV", "unknown"),
-            "qaoa_repo_dir": here,
-        }
-        try:
-            meta["qaoa_git_commit"] = subprocess.check_output(["git", "rev-parse", "HEAD"], cwd=here,
-                                                              stderr=subprocess.DEVNULL).decode().strip()
-        except Exception:
-            meta["qaoa_git_commit"] = "unknown"
-        return meta
+        return run_metadata()
 
     # ---- from / to live objects ----------------------------------------------------------------------------
     @classmethod
