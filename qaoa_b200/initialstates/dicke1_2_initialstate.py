@@ -23,7 +23,11 @@ class Dicke1_2(InitialState):
         s.x(1)
         s.cz(1, 2)
         s.x(1)
-        return s.v
+        if self.N_qubits == 3:
+            return s.v
+        full = np.zeros(1 << self.N_qubits, dtype=np.complex128)   # qubits beyond the first three stay |0>
+        full[:8] = s.v
+        return full
 
     def state_descriptor(self):
         return _eng.INIT_STATEVECTOR, 0, self.state_vector()

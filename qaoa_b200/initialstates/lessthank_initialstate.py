@@ -21,8 +21,11 @@ class LessThanK(InitialState):
         return bool(2 <= k <= 8 or (k > 0 and (k & (k - 1)) == 0))
 
     def state_vector(self):
-        """amplitudes of the reference's circuit for this k (lessthank_initialstate.py:69-152)"""
-        s = SmallState(self.N_qubits)
+        """amplitudes of the reference's circuit for this k (lessthank_initialstate.py:69-152).  The circuit touches
+        the first ceil(log2 k) qubits only: on a larger register (QAOA sets N_qubits to the problem's) every other
+        qubit stays |0>, exactly as the reference's circuit leaves it."""
+        kb = int(np.ceil(np.log2(self.k)))
+        s = SmallState(kb)
         third = np.arccos(1 / np.sqrt(3)) * 2
         if self.k == 3:        # :79-93
             s.ry(third, 1)
@@ -41,12 +44,13 @@ class LessThanK(InitialState):
             s.ry(np.pi / 2, 2, ctrl=0, ctrl_state=0)
             s.ry(third, 1, ctrl=0, ctrl_state=0)
             s.xx_plus_yy(np.pi / 2, -np.pi / 2, 0, 1)
-        else:                  # powers of two: Hadamards (:69-77)
-            for q in range(self.N_qubits):
-                s.h(q)
-        return s.v
+        else:                  # powers of two: Hadamards on the whole register (:69-77)
+            return np.full(1 << self.N_qubits, 2.0 ** (-0.5 * self.N_qubits), dtype=np.complex128)
+        if self.N_qubits < kb:
+            raise ValueError("LessThanK(%d) needs %d qubits" % (self.k, kb))
+        full = np.zeros(1 << self.N_qubits, dtype=np.complex128)
+        full[: 1 << kb] = s.v
+        return full
 
     def state_descriptor(self):
-        if self.N_qubits != int(np.ceil(np.log2(self.k))):
-            raise ValueError("LessThanK(%d) lives on %d qubits" % (self.k, int(np.ceil(np.log2(self.k)))))
         return _eng.INIT_STATEVECTOR, 0, self.state_vector()

@@ -75,3 +75,20 @@ def test_node_grover_oracle_is_the_tensor_product_of_node_reflections():
     ref = np.kron(U1, U1) @ psi
     got = orc.apply_node_grover(psi.copy(), s, beta)
     assert np.allclose(got, ref)
+
+
+def test_node_states_on_a_larger_register_leave_the_other_qubits_in_zero():
+    """QAOA hands an initial state the problem's qubit count; the reference's LessThanK / Dicke1_2 circuits act on their
+    first qubits only (lessthank_initialstate.py:79-152, dicke1_2_initialstate.py:28-41), powers of two put Hadamards
+    on the whole register (:69-77)."""
+    a = ist.LessThanK(3)
+    a.setNumQubits(6)
+    v = a.state_vector()
+    assert v.size == 64 and np.allclose(v[:4], orc.feasible_node_state(3)) and not v[4:].any()
+    b = ist.LessThanK(4)
+    b.setNumQubits(5)
+    assert np.allclose(b.state_vector(), 2.0 ** -2.5)
+    c = ist.Dicke1_2()
+    c.setNumQubits(5)
+    v = c.state_vector()
+    assert np.allclose(v[:8], orc.feasible_node_state(6, "Dicke1_2")) and not v[8:].any()
