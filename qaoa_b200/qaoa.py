@@ -111,6 +111,39 @@ class OptResult:
         return np.unique(sols), lowest
 
 
+class _DepthHistogram(dict):
+    """QAOA.samplecount_hists[depth]: in the reference the raw counts of the optimiser's last evaluation at that depth
+    (qaoa/qaoa.py:830), consumed by utils.post_process_all_depths and the plot routines.  An exact engine has no such
+    by-product, so the histogram is drawn by the device sampler -- `shots` strings at the depth's best angles, keys in
+    the sampler's printing order (qubit 0 last) -- the first time anybody looks at it."""
+
+    def __init__(self, owner, depth):
+        super().__init__()
+        self._owner, self._depth, self._drawn = owner, depth, False
+
+    def _draw(self):
+        if not self._drawn:
+            self._drawn = True
+            best = self._owner.optimization_results[self._depth].get_best_angles()
+            super().update({s[::-1]: c for s, c in self._owner.hist(best, self._owner.shots).items()})
+
+    def __reduce__(self):      # pickles as a plain dict: what has been drawn so far (never samples as a side effect)
+        return (dict, (dict(dict.items(self)),))
+
+
+def _lazy(name):
+    def method(self, *a, **kw):
+        self._draw()
+        return getattr(dict, name)(self, *a, **kw)
+    method.__name__ = name
+    return method
+
+
+for _name in ("__getitem__", "__iter__", "__len__", "__contains__", "__repr__", "__eq__", "keys", "values", "items", "get",
+              "copy"):
+    setattr(_DepthHistogram, _name, _lazy(_name))
+
+
 def _reject(what):
     raise NotImplementedError(
         what + " cannot be honoured by the exact B200 statevector engine and is rejected "
@@ -440,7 +473,7 @@ class QAOA:
             self.optimization_results[target] = OptResult(target)
             self.createParameterizedCircuit(int((len(angles0) - n_init) / (n_gamma + n_beta)))
             res = self.local_opt(angles0)
-            self.samplecount_hists[target] = self.last_hist
+            self.samplecount_hists[target] = _DepthHistogram(self, target)
             self.optimization_results[target].compute_best_index()
             self.optimization_results[target].opt_time = time.perf_counter() - t0
             LOG.info("cost(depth %d = %s", target, res.fun)

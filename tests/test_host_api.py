@@ -483,3 +483,25 @@ def test_post_processing_of_the_final_histogram():
     q.post = False
     q.optimize(depth=2)
     assert q.stat._sampled is None and q.get_Exp(2) <= q.get_Exp(1) + 1e-9
+
+
+def test_depth_histograms_are_drawn_on_demand_for_post_process_all_depths():
+    """examples/MaxCut/ComparisonPostProcessing.ipynb cell 11: plain instances, then utils.post_process_all_depths(instance, K)"""
+    from qaoa_b200.utils import post_process_all_depths
+
+    np.random.seed(11)
+    q, fake = readme_qaoa(shots=200, optimizer=[__import__("qaoa_b200").utils.COBYLA, {"maxiter": 20}])
+    q.optimize(depth=2)
+    before = fake.calls
+    hists = q.samplecount_hists
+    assert sorted(hists) == [1, 2] and all(isinstance(h, dict) for h in hists.values())
+    exp0, var0 = post_process_all_depths(q, 0)          # K = 0: no boosting, just the sampled means
+    assert fake.calls == before                         # (sampling is not an energy evaluation)
+    assert all(sum(h.values()) == 200 for h in hists.values())
+    exp3, var3 = post_process_all_depths(q, 3)
+    assert exp0.shape == exp3.shape == (2,) and (exp3 <= exp0 + 1e-9).all()
+    for d in (1, 2):
+        assert exp0[d - 1] == pytest.approx(q.get_Exp(d), abs=0.6)      # 200 shots around the exact value
+    assert pickle.loads(pickle.dumps(hists[1])) == dict(hists[1].items())
+    q.optimize(depth=3)
+    assert pickle.loads(pickle.dumps(q)).samplecount_hists[3] == {}      # not looked at yet: nothing is sampled by pickling
