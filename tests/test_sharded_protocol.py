@@ -137,6 +137,119 @@ class ShmShardEngine:
         self.shm.unlink()
 
 
+class TwistedShmShardEngine(ShmShardEngine):
+    """Stand-in for a SHARDED SYMMETRIC register (csrc/tile_kernel.cuh "twisted coordinates"): rank r
+    holds phi~(r, z), z = the n-1-g low bits of the stored index x', r_j = x'[n-1-g+j] XOR x'[0], in the S frame.  Local
+    passes: phase separator, the local qubits 1.., the mirror pairing of the virtual top qubit (same shard!).  Cross
+    passes: qubit 0 -- the pairing (z_0 = 0, r) <-> (z_0 = 1, ~r) -- and the rank qubits with their sign twist, on this
+    rank's slice of every shard.  Same algebra as tests/test_twisted_coordinates.py, spread over processes."""
+
+    def __init__(self, n, rank, world, diag, slow=0.0):
+        super().__init__(n, rank, world, diag, slow)
+        self.nl = n - 1 - self.g                      # stored local qubits (the segment is larger than needed)
+        z = np.arange(1 << self.nl)
+        mask = world - 1
+        self.z = z
+        self.x = [z | (np.where(z & 1, r ^ mask, r) << self.nl) for r in range(world)]   # x'(r, z)
+        pc = np.array([bin(int(v)).count("1") for v in self.x[rank]])
+        self.pc = pc
+        self.cost = [self.diag[x] for x in self.x]
+        self.sigma = np.real((1j) ** ((2 - n) % 4)) * (-1.0) ** pc
+
+    def shard_run_pass(self, i):
+        kind, d = self.passes[i]
+        self._check_barrier(i)
+        if self.slow:
+            time.sleep(self.slow)
+        gamma, beta = self.ang[2 * d], self.ang[2 * d + 1]
+        c, s = np.cos(beta), np.sin(beta)
+        z, el, mask = self.z, self.nl, self.world - 1
+        _, mine = self._view(self.rank)
+        if kind == "local":
+            if d == 0:
+                mine[:] = np.sqrt(2.0) * 2.0 ** (-0.5 * self.n) * (1j) ** (self.pc % 4)
+            mine *= np.exp(1j * gamma * self.cost[self.rank])
+            for q in range(1, el):
+                lo = z[(z >> q) & 1 == 0]
+                a, b = mine[lo].copy(), mine[lo | (1 << q)].copy()
+                mine[lo], mine[lo | (1 << q)] = c * a + s * b, c * b - s * a
+            mine[:] = c * mine + s * self.sigma * mine[z ^ ((1 << el) - 1)]
+        else:
+            w = (1 << (el - 1)) // self.world            # this rank's share of the (z >> 1) values, both z_0
+            rest = np.arange(self.rank * w, (self.rank + 1) * w)
+            ev, od = rest << 1, (rest << 1) | 1
+            shards = [self._view(r)[1] for r in range(self.world)]
+            blk = {(r, z0): shards[r][ev if z0 == 0 else od].copy() for r in range(self.world) for z0 in (0, 1)}
+            new = dict(blk)
+            for r in range(self.world):                   # qubit 0
+                a, b = blk[(r, 0)], blk[(r ^ mask, 1)]
+                new[(r, 0)], new[(r ^ mask, 1)] = c * a + s * b, c * b - s * a
+            blk = new
+            for j in range(self.g):                       # rank qubits: the qubit is 0 where r_j == z_0
+                new = dict(blk)
+                for r in range(self.world):
+                    if (r >> j) & 1:
+                        continue
+                    r1 = r | (1 << j)
+                    for z0, (ra, rb) in ((0, (r, r1)), (1, (r1, r))):
+                        a, b = blk[(ra, z0)], blk[(rb, z0)]
+                        new[(ra, z0)], new[(rb, z0)] = c * a + s * b, c * b - s * a
+                blk = new
+            if i == len(self.passes) - 1:
+                tot = np.zeros(3)
+                lo, hi = np.inf, -np.inf
+                for (r, z0), v in blk.items():
+                    cst = self.cost[r][ev if z0 == 0 else od]
+                    pr = np.abs(v) ** 2
+                    tot += [pr.sum(), (pr * cst).sum(), (pr * cst * cst).sum()]
+                    sup = pr > 0
+                    lo, hi = min(lo, cst[sup].min()), max(hi, cst[sup].max())
+                self.partial = np.array([tot[0], tot[1], tot[2], lo, hi])
+            else:
+                for (r, z0), v in blk.items():
+                    shards[r][ev if z0 == 0 else od] = v
+        self._view(self.rank)[0][0] = i
+
+
+def _twisted_worker(rank, world, port, n, out_dir):
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from qaoa_b200 import sharded
+
+        edges, colors, table = H.regular_maxcut(n)
+        diag = H.maxcut_diag(n, edges, colors, table)
+        eng = sharded.DistShardedEngine(
+            n, symmetric=True,
+            engine_factory=lambda r, w: TwistedShmShardEngine(n, r, w, diag, slow=0.03 if r == 1 else 0.0))
+        assert eng.symmetric
+        ang = np.array([0.3, 0.2, 0.5, 1.1, 1.4, -0.7])
+        got = eng.energy(ang)
+        ref = np.array(orc.energy(orc.Spec(n, diag), ang))
+        np.save(os.path.join(out_dir, "t%d.npy" % rank), np.concatenate([got, ref]))
+        dist.barrier()
+        eng.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_twisted_symmetric_shards_over_processes_gloo(world, tmp_path):
+    """the sharded symmetric register's data flow under torch.distributed (gloo): the mirror pairing never leaves a
+    shard, qubit 0 and the rank qubits are mixed in the cross passes, every rank ends with the oracle's energy"""
+    import torch.multiprocessing as mp
+
+    n = 10
+    mp.spawn(_twisted_worker, args=(world, _free_port(), n, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        row = np.load(tmp_path / ("t%d.npy" % r))
+        got, ref = row[:5], row[5:9]
+        assert np.allclose(got[:4], ref, rtol=1e-12), (r, got, ref)
+        assert abs(got[4] - 1.0) < 1e-12
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
