@@ -1,7 +1,9 @@
 """BASELINE config 3 through the reference-facing API: MaxCut 3-regular n=32 (seed 42), X mixer, |+>, complex64,
 `QAOA.optimize(depth=5)` on one B200 -- landscape seed, COBYLA per depth, INTERP between depths.
 
-  python scripts/config3_optimize.py [n=32] [depth=5] [maxiter=25] [grid=12] [out=gpurun_out/config3_optimize.jsonl]
+  python scripts/config3_optimize.py [n=32] [depth=5] [maxiter=25] [grid=12] [out=gpurun_out/config3_optimize.jsonl] [dtype=complex64]
+
+(n=8 depth=3 maxiter=1000 grid=20 dtype=complex128 is BASELINE config 1, the README quick example.)
 
 One JSON line per stage is appended (and flushed) as soon as the stage ends, so a run cut short by a time limit keeps
 what it measured: the landscape (points, seconds), then per depth the number of energy evaluations COBYLA made, the wall
@@ -27,6 +29,7 @@ def main():
     maxiter = int(arg[2]) if len(arg) > 2 else 25
     grid = int(arg[3]) if len(arg) > 3 else 12
     path = arg[4] if len(arg) > 4 else os.path.join(ROOT, "gpurun_out", "config3_optimize.jsonl")
+    dtype = arg[5] if len(arg) > 5 else "complex64"
     os.makedirs(os.path.dirname(path), exist_ok=True)
     out = open(path, "a")
 
@@ -43,11 +46,11 @@ def main():
 
     G = nx.random_regular_graph(3, n, seed=42)
     q = QAOA(problem=problems.MaxCut(G), mixer=mixers.X(), initialstate=initialstates.Plus(),
-             backend=B200Backend(device=0, dtype="complex64"), optimizer=[COBYLA, {"maxiter": maxiter}])
+             backend=B200Backend(device=0, dtype=dtype), optimizer=[COBYLA, {"maxiter": maxiter}])
     t0 = time.perf_counter()
     q.createParameterizedCircuit(1)          # lowers problem / mixer / state: diagonal generated on the device
     q._evaluate(np.array([[0.3, 0.2]]))      # first evaluation builds the plan and the diagonal streams
-    emit({"stage": "setup", "n": n, "import_s": t0 - t_start, "lower_and_first_eval_s": time.perf_counter() - t0})
+    emit({"stage": "setup", "n": n, "dtype": dtype, "import_s": t0 - t_start, "lower_and_first_eval_s": time.perf_counter() - t0})
 
     spec = {"gamma": [0, 2 * np.pi, grid], "beta": [0, 2 * np.pi, grid]}
     t0 = time.perf_counter()
