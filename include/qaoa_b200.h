@@ -115,6 +115,13 @@ int qaoa_fetch_results(qaoa_engine_t* h, int B, double* out);
  * complex128 interleaved).  Test / debugging aid; 2^n * 16 bytes on the host. */
 int qaoa_read_statevector(qaoa_engine_t* h, double* out);
 
+/* X gates between layers -- the reference's flip=True (qaoa/qaoa.py:505-509, qaoa/utils/flip.py:76-88): the state kept by
+ * the last evaluation (option keep_state=1), with X applied on every qubit of flip_mask (bit q = qubit q), is installed
+ * as the initial state, device to device, exactly as qaoa_set_initial(QAOA_INIT_STATEVECTOR) would install it.  The
+ * caller evaluates the circuit segment by segment: layers up to a flip, this call, the next layers, ...; the last
+ * segment's result is the result of the whole circuit.  Single-GPU engines only. */
+int qaoa_continue_from_kept_state(qaoa_engine_t* h, uint64_t flip_mask);
+
 /* Draws `shots` basis indices from |psi(angles)|^2: replaces backend.run(shots=...) + get_counts of
  * QAOA.hist (qaoa/qaoa.py:1134-1172).  u[shots]: uniform numbers in [0,1) from the caller's seeded
  * generator (inverse-CDF sampling, deterministic for given u); out_idx[i] = basis index of shot i. */

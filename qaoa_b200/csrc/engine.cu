@@ -1964,6 +1964,37 @@ int qaoa_read_statevector(qaoa_engine_t* h, double* out) {
   API_END(h)
 }
 
+// X gates between layers (the reference's flip=True, qaoa/qaoa.py:505-509): the state KEPT by the last evaluation, with X
+// applied on the qubits of flip_mask, becomes the initial state -- device to device, as if qaoa_set_initial had been given
+// that statevector -- so that the next evaluation continues the circuit with its remaining layers.
+int qaoa_continue_from_kept_state(qaoa_engine_t* h, uint64_t flip_mask) {
+  API_BEGIN(h)
+  if (h->world > 1) fail("sharded engine: X gates between layers are not supported");
+  if (!h->keep_state || !h->last_valid || !h->state) fail("no kept state: set option keep_state=1 and evaluate first");
+  if (h->n < 64 && (flip_mask >> h->n)) fail("flip mask names qubits beyond the register");
+  unsigned long long zm = 0;
+  for (int q = 0; q < h->n; q++) if (h->last_z[q]) zm |= 1ull << q;
+  const double scale = h->last_scale * h->last_gsign;
+  const int rot = (4 - (__builtin_popcountll(flip_mask) & 3)) & 3;    // i^(-popc(m))
+  void* dst = nullptr;
+  CUDA_OK(cudaMalloc(&dst, h->N * h->amp_bytes));
+  const int grid = grid_for(h->N, 256);
+  if (h->dtype == QAOA_DTYPE_C64)
+    flip_continue_kernel<float><<<grid, 256, 0, h->stream>>>((const float*)h->state, (float*)dst, h->N, flip_mask, zm, (float)scale, rot);
+  else
+    flip_continue_kernel<double><<<grid, 256, 0, h->stream>>>((const double*)h->state, (double*)dst, h->N, flip_mask, zm, scale, rot);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  if (e != cudaSuccess) { cudaFree(dst); CUDA_OK(e); }
+  h->launches += 1;
+  if (h->init_vec) cudaFree(h->init_vec);
+  h->init_vec = dst;
+  h->init.kind = INIT_STATEVECTOR; h->init.k = 0; h->init.amp = 1.0; h->init.vec = dst;
+  h->n_init = 0;
+  invalidate(h);
+  API_END(h)
+}
+
 // ---- sampling / cost distribution of the final state -------------------------------------------
 // evaluates `angles` with the final state kept in HBM (natural index order, S frame; |psi|^2 is what matters)
 static void eval_keeping_state(Engine* h, int p, const double* angles, int n_angles) {

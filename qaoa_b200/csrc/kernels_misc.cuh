@@ -236,6 +236,25 @@ __global__ void to_sframe_kernel(real* st, size_t N) {
   }
 }
 
+// X gates between two layers (reference qaoa/qaoa.py:505-509, flip=True), natural order, S frame on both sides:
+//   psi'(x) = psi(x ^ m)   <=>   psi~'(x) = i^(popc(x) - popc(x ^ m)) psi~(x ^ m) = (-1)^popc(x & m) i^(-popc(m)) psi~(x ^ m).
+// `src` is a KEPT state: the true amplitude is src(y) * scale * (-1)^popc(y & zmask) (what qaoa_read_statevector undoes).
+template <typename real>
+__global__ void flip_continue_kernel(const real* __restrict__ src, real* __restrict__ dst, size_t N,
+                                     unsigned long long m, unsigned long long zmask, real scale, int rot) {
+  for (size_t x = blockIdx.x * (size_t)blockDim.x + threadIdx.x; x < N; x += (size_t)gridDim.x * blockDim.x) {
+    const size_t y = x ^ (size_t)m;
+    real re = src[2 * y], im = src[2 * y + 1];
+    const int odd = (__popcll((unsigned long long)y & zmask) + __popcll((unsigned long long)x & m)) & 1;
+    const real f = odd ? -scale : scale;
+    re *= f;
+    im *= f;
+    mul_i_pow(re, im, rot);
+    dst[2 * x] = re;
+    dst[2 * x + 1] = im;
+  }
+}
+
 // ============================================================================================
 // single-CTA fused kernel: whole circuit for n <= 14 (complex64) / 13 (complex128) in shared memory
 // ============================================================================================

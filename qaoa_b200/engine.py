@@ -81,6 +81,7 @@ def load_library():
             ctypes.c_int, [H, ctypes.c_int, _c_double_p, ctypes.c_int, ctypes.c_int]),
         "qaoa_fetch_results": (ctypes.c_int, [H, ctypes.c_int, _c_double_p]),
         "qaoa_read_statevector": (ctypes.c_int, [H, _c_double_p]),
+        "qaoa_continue_from_kept_state": (ctypes.c_int, [H, ctypes.c_uint64]),
         "qaoa_debug_tile_program": (
             ctypes.c_int, [H, ctypes.c_int, _c_int32_p, ctypes.c_int, ctypes.c_int, ctypes.c_double, _c_double_p]),
         "qaoa_debug_plan": (
@@ -296,6 +297,13 @@ class Engine:
         out = np.empty(2 << self.n_qubits, dtype=np.float64)
         self._check(self._lib.qaoa_read_statevector(self._h, _dptr(out)))
         return out.view(np.complex128)
+
+    def continue_from_kept_state(self, flip_mask=0):
+        """X gates between layers (the reference's flip=True, qaoa/qaoa.py:505-509): the state kept by the last evaluation
+        (option keep_state=1), with X applied on the qubits of ``flip_mask`` (bit q = qubit q), becomes the initial
+        state, device to device; the next evaluation continues the circuit with its remaining layers."""
+        self._check(self._lib.qaoa_continue_from_kept_state(self._h, int(flip_mask)))
+        self.n_init = 0
 
     # -- sampling / cost distribution of the final state -------------------------------------------------
     def _angles(self, angles):

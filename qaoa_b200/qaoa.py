@@ -13,7 +13,9 @@ Semantics in the exact engine:
   * ``Exp = -E[cost]`` (cvar = 1) is the shots -> infinity limit of the reference's estimate;
   * ``Var`` is the population variance (the reference's S/(W-1) is undefined without samples);
   * ``BestCost/WorstCost`` are -max/-min of the cost over the support of |psi|^2;
-  * ``noisemodel``, ``precision``, ``memorysize > 0``, ``flip``, QNSPSA and foreign
+  * ``flip=True`` (X gates between layers from the boosted most-frequent string, qaoa.py:505-509, 840-848) is
+    honoured on a single GPU: the histogram it needs is sampled on the device at the depth's best angles;
+  * ``noisemodel``, ``precision``, ``memorysize > 0``, QNSPSA and foreign
     ``backend`` objects cannot be honoured by an exact statevector engine and are REJECTED
     (NotImplementedError) — nothing is ever routed to a CPU simulator.
 """
@@ -188,8 +190,8 @@ class QAOA:
             _reject("precision (shot-adaptive estimation)")
         if memorysize is not None and memorysize > 0:
             _reject("memorysize > 0 (per-shot memory)")
-        if flip:
-            _reject("flip=True (bit-flip boosting needs sampled histograms)")
+        if flip and getattr(backend, "sharded", False):
+            _reject("flip=True on a sharded register")
         if getattr(problem, "N_ancilla_qubits", 0):
             _reject("problems with ancilla qubits")
         if not (0 < cvar <= 1):
@@ -237,7 +239,10 @@ class QAOA:
 
         self.optimization_results = {}
         self.memory_lists = []
-        self.flip = False
+        # bit-flip boosting between layers (qaoa.py:505-509, 840-848): after depth d has been optimised, the most frequent
+        # sampled string is improved by greedy classical bit flips and the XOR pattern becomes X gates after layer d of
+        # every deeper circuit.  The device applies them as an index permutation of the kept state (_device_call).
+        self.flip = bool(flip)
         from qaoa_b200.utils.flip import BitFlip
         self.flipper = BitFlip(self.problem.N_qubits)
         self.bitflips = []
@@ -310,9 +315,12 @@ class QAOA:
             if dist.is_available() and dist.is_initialized():
                 world, rank = dist.get_world_size(), dist.get_rank()
         mine = rows[rank::world] if world > 1 and len(rows) >= world else rows
-        res = eng.energy_batch(mine)
+        if self._flips_active(mine[0]):
+            res = np.array([self._device_call("energy", r) for r in mine])
+        else:
+            res = eng.energy_batch(mine)
         if self.cvar < 1:
-            cv = np.array([self._exact_cvar(*eng.cost_distribution(r)) for r in mine])
+            cv = np.array([self._exact_cvar(*self._device_call("cost_distribution", r)) for r in mine])
         else:
             cv = res[:, 0]
         out = np.column_stack([res, cv])
@@ -324,6 +332,49 @@ class QAOA:
                 full[r::world] = part
             out = full
         return out
+
+    def _flip_masks(self):
+        """bit masks (bit q = qubit q) of the X gates that follow layers 0, 1, ... (reference qaoa.py:505-509: layer d of
+        a depth-D circuit, d != D - 1, is followed by flipper.create_circuit(bitflips[d]))"""
+        masks = []
+        for pattern in self.bitflips:
+            self.flipper.create_circuit(pattern)
+            masks.append(self.flipper.flip_mask)
+        return masks
+
+    def _flips_active(self, eng_row):
+        if not self.flip or not self.bitflips:
+            return False
+        eng = self._get_engine()
+        depth = (len(eng_row) - eng.n_init) // (eng.n_gamma + eng.n_beta)
+        return any(self._flip_masks()[: depth - 1])
+
+    def _device_call(self, name, eng_row, *args, **kw):
+        """``engine.<name>(angles, ...)`` on the final state of the circuit at ``eng_row`` (device angle layout).  With
+        X gates between layers the circuit runs segment by segment on the device: layers up to a flip with the state
+        kept in HBM, the flip as an index permutation of that state (Engine.continue_from_kept_state), the next layers
+        from there; ``name`` is called for the last segment, whose result is the whole circuit's."""
+        eng = self._get_engine()
+        row = np.asarray(eng_row, dtype=np.float64)
+        if not self._flips_active(row):
+            return getattr(eng, name)(row, *args, **kw)
+        n_init, per = eng.n_init, eng.n_gamma + eng.n_beta
+        depth = (len(row) - n_init) // per
+        masks = self._flip_masks()[: depth - 1]
+        eng.set_option("keep_state", 1)
+        try:
+            start = 0                                   # first row entry of the segment in flight
+            for d, mask in enumerate(masks):
+                if mask:
+                    stop = n_init + (d + 1) * per
+                    eng.energy(row[start:stop])
+                    eng.continue_from_kept_state(mask)
+                    start = stop
+            eng.set_option("keep_state", 0)
+            return getattr(eng, name)(row[start:], *args, **kw)
+        finally:
+            eng.set_option("keep_state", 0)
+            self.initialstate.lower_initial(eng)        # back to the circuit's own initial state
 
     def _exact_cvar(self, costs, probs):
         order = np.argsort(-costs, kind="stable")
@@ -477,6 +528,13 @@ class QAOA:
             self.optimization_results[target].compute_best_index()
             self.optimization_results[target].opt_time = time.perf_counter() - t0
             LOG.info("cost(depth %d = %s", target, res.fun)
+            if self.flip:
+                # qaoa.py:840-848.  (The reference looks at the raw counts of the optimiser's LAST evaluation; here the
+                # histogram is sampled on the device at the depth's best angles.)
+                counts = self.samplecount_hists[target]
+                string = max(counts, key=counts.get)
+                boosted = self.flipper.boost_samples(problem=self.problem, string=string)
+                self.bitflips.append(self.flipper.xor(string, boosted))
             self.current_depth += 1
 
         if self.post:
@@ -554,7 +612,7 @@ class QAOA:
         depth = int((len(angles) - n_init) / (n_gamma + n_beta))
         self.createParameterizedCircuit(depth)
         eng = self._get_engine()
-        idx = eng.sample(self._engine_row(angles), int(shots))
+        idx = self._device_call("sample", self._engine_row(angles), int(shots))
         n = self.problem.N_qubits
         out = {}
         values, counts = np.unique(idx, return_counts=True)
@@ -580,7 +638,7 @@ class QAOA:
         eng = self._get_engine()
         for i in np.where(np.asarray(result.BestCost) == lowest)[0][:1]:
             if not result.BestSols[i] and hasattr(eng, "extreme_solutions"):
-                idx, _cost = eng.extreme_solutions(self._engine_row(result.angles[i]), want_max=True)
+                idx, _cost = self._device_call("extreme_solutions", self._engine_row(result.angles[i]), want_max=True)
                 result.BestSols[i] = ["".join("1" if (int(x) >> q) & 1 else "0" for q in range(n)) for x in idx]
 
     def _rows_need_lowering(self):

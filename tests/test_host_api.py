@@ -26,6 +26,34 @@ class OracleEngine:
         self.init = None
         self.trotter = 1
         self.calls = 0
+        self.n_gamma = 1
+        self.n_init = 0
+        self.options = {}
+        self.kept = None          # final state of the last energy() call made with keep_state=1
+        self.segments = []        # (number of angles, flip mask) of every continue_from_kept_state call
+
+    def set_option(self, key, value):
+        self.options[key] = value
+
+    def energy(self, row):
+        """one evaluation; with keep_state=1 the final state stays available for continue_from_kept_state"""
+        row = np.asarray(row, dtype=float)
+        if self.options.get("keep_state"):
+            ni = self.n_init
+            spec = orc.Spec(self.n_qubits, self.diag, mixer=self.mixer, init=orc.phased_plus(self.init, row[:ni]),
+                            trotter=self.trotter, terms=getattr(self, "terms", None))
+            self.kept = orc.evolve(spec, row[ni:])
+            self._kept_angles = len(row)
+        return self.energy_batch(row[None, :])[0]
+
+    def continue_from_kept_state(self, flip_mask=0):
+        """X on the qubits of flip_mask: psi'(x) = psi(x ^ mask); the result is the new initial state"""
+        assert self.options.get("keep_state") and self.kept is not None
+        x = np.arange(1 << self.n_qubits)
+        self.init = self.kept[x ^ int(flip_mask)]
+        self.n_init = 0
+        self.kept = None
+        self.segments.append((self._kept_angles, int(flip_mask)))
 
     def set_cost_maxkcut(self, n_nodes, edges, bits, lut, fixed_node=False, fixed_colour=0):
         x = np.arange(1 << self.n_qubits)
@@ -249,7 +277,7 @@ def test_xy_topology_and_trotter():
 def test_unsupported_features_are_rejected_not_rerouted():
     G = nx.random_regular_graph(3, 4, seed=1)
     P, X, I = problems.MaxCut(G), mixers.X(), initialstates.Plus()
-    for kw in ({"noisemodel": object()}, {"precision": 0.1}, {"memorysize": 10}, {"flip": True},
+    for kw in ({"noisemodel": object()}, {"precision": 0.1}, {"memorysize": 10},
                {"backend": object()}):
         with pytest.raises(NotImplementedError):
             QAOA(problem=P, mixer=X, initialstate=I, **kw)
@@ -505,3 +533,68 @@ def test_depth_histograms_are_drawn_on_demand_for_post_process_all_depths():
     assert pickle.loads(pickle.dumps(hists[1])) == dict(hists[1].items())
     q.optimize(depth=3)
     assert pickle.loads(pickle.dumps(q)).samplecount_hists[3] == {}      # not looked at yet: nothing is sampled by pickling
+
+
+def _flipped_circuit_state(q, fake_diag, angles, masks):
+    """oracle: init -> [phase, mixer, X^mask_d] per layer (no X after the last layer), as reference qaoa.py:476-509"""
+    n = q.problem.N_qubits
+    psi = orc.plus_state(n)
+    x = np.arange(1 << n)
+    depth = len(angles) // 2
+    for d in range(depth):
+        psi = orc.evolve(orc.Spec(n, fake_diag, init=psi), angles[2 * d: 2 * d + 2])
+        if d != depth - 1 and d < len(masks) and masks[d]:
+            psi = psi[x ^ masks[d]]
+    return psi
+
+
+def test_flip_puts_x_gates_between_layers():
+    """flip=True (reference qaoa.py:505-509, 840-848; unittests/test_qaoa_core.py flip case): after every optimised depth the
+    most frequent sampled string is boosted classically and the XOR pattern becomes X gates after that layer."""
+    np.random.seed(5)
+    q, fake = readme_qaoa(flip=True, shots=256, optimizer=[__import__("qaoa_b200").utils.COBYLA, {"maxiter": 25}])
+    q.optimize(depth=3)
+    assert q.flip and len(q.bitflips) == 3 and all(len(b) == 8 and set(b) <= {0, 1} for b in q.bitflips)
+    assert len(q.get_Exp()) == 3 and all(np.isfinite(q.get_Exp()))
+    assert fake.init is not None and np.allclose(fake.init, orc.plus_state(8))      # the circuit's own state is back
+    assert not fake.options.get("keep_state")
+
+    # a pattern with X gates: energies, histograms and optimal strings follow the segmented circuit
+    q.bitflips = [[0, 0, 1, 0, 0, 1, 1, 0], [0] * 8, [1, 0, 0, 0, 0, 0, 0, 1]]      # printing order: qubit 0 LAST
+    masks = q._flip_masks()
+    assert masks == [0b00100110, 0, 0b10000001]      # the pattern read as a binary numeral: position n-1-q <-> qubit q
+    ang = np.array([0.4, 0.3, 0.7, 0.2, 0.5, 0.6, 0.3, 0.1])                          # depth 4: X after layers 0 and 2
+    q.createParameterizedCircuit(4)
+    q.current_depth, q.optimization_results[4] = 3, OptResult(4)
+    fake.segments.clear()
+    got = q.loss(ang)
+    psi = _flipped_circuit_state(q, fake.diag, ang, masks)
+    pr = np.abs(psi) ** 2
+    assert got == pytest.approx(-(pr @ fake.diag), abs=1e-12)
+    assert fake.segments == [(2, masks[0]), (4, masks[2])]                           # layers 0 | 1-2 | 3
+    plain = -(np.abs(orc.evolve(orc.Spec(8, fake.diag), ang)) ** 2 @ fake.diag)
+    assert abs(got - plain) > 1e-3                                                   # the X gates do matter
+    h = q.hist(ang, 4000)
+    top = max(h, key=h.get)
+    assert pr[int(top[::-1], 2)] == pytest.approx(pr.max(), rel=0.35)
+    assert np.allclose(fake.init, orc.plus_state(8))
+
+    # depth 1 has no X gate (d != depth - 1), and the reference's quirk: a pattern naming qubit 0 alone flips nothing
+    assert q._eval_cost(ang[:2]) == pytest.approx(-(np.abs(orc.evolve(orc.Spec(8, fake.diag), ang[:2])) ** 2 @ fake.diag))
+    q.bitflips = [[0, 0, 0, 0, 0, 0, 0, 1]]
+    assert q._flip_masks() == [0] and not q._flips_active(ang[:4])
+
+
+def test_flip_with_cvar_and_rejection_on_sharded_backends():
+    from qaoa_b200.qaoa import B200Backend
+
+    with pytest.raises(NotImplementedError):
+        QAOA(problems.MaxCut(nx.random_regular_graph(3, 8, seed=42)), mixers.X(), initialstates.Plus(),
+             backend=B200Backend(sharded=True), flip=True)
+    q, fake = readme_qaoa(flip=True, cvar=0.25)
+    q.bitflips = [[0, 1, 0, 0, 0, 0, 1, 1]]
+    masks = q._flip_masks()
+    ang = np.array([0.4, 0.3, 0.7, 0.2])
+    q.createParameterizedCircuit(2)
+    pr = np.abs(_flipped_circuit_state(q, fake.diag, ang, masks)) ** 2
+    assert q._eval_cost(ang) == pytest.approx(-orc.exact_cvar(fake.diag, pr, 0.25), abs=1e-12)
