@@ -2,7 +2,6 @@
 (reference qaoa/initialstates/maxkcut_feasible_initialstate.py:11-103): a Tensor of LessThanK(k) / Dicke1_2 (binary
 encoding) or Dicke(1, k) (one-hot encoding) node states."""
 
-import numpy as np
 
 from .base_initialstate import InitialState
 from .dicke_initialstate import Dicke
