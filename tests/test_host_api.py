@@ -297,6 +297,14 @@ def test_unsupported_features_are_rejected_not_rerouted():
         q.mixer.lower_mixer(OracleEngine(4))
     with pytest.raises(NotImplementedError):
         GateState().state_descriptor()
+    # MaxKCutLX keeps the reference's constructor checks (maxkcut_lx_mixer.py:29-61) and is rejected at lowering
+    lx = mixers.MaxKCutLX(3, "LessThanK", topology="ring")
+    assert (lx.k_bits, lx.get_num_parameters(), str(lx)) == (2, 1, "MaxKCutLX")
+    for bad in ((4, "LessThanK"), (9, "LessThanK"), (3, ""), (3, "LessThanK", "star"), (5, "Dicke1_2")):
+        with pytest.raises(ValueError):
+            mixers.MaxKCutLX(*bad)
+    with pytest.raises(NotImplementedError):
+        lx.lower_mixer(OracleEngine(4))
 
 
 def test_user_problem_uses_the_diagonal_escape_hatch():
