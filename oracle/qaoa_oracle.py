@@ -12,7 +12,7 @@ PARITY PINNING.  The arithmetic of the reference lives in un-vendored
 third-party code (qiskit >=2.3.0, qiskit-aer >=0.17.0, ``setup.py:22-24``, no
 lock file) that is not installable here, and the reference's own Aer-backed
 tests assert no energies.  **Energies are therefore "parity unpinned" against
-Aer itself.**  What IS pinned (tests/test_oracle_*.py):
+Aer itself.**  What IS pinned (tests/test_oracle.py):
   * cost functions against the reference's unit tables
     (unittests/test_problems.py:30-38,100-123) and against fixtures generated
     by importing the reference's loadable fragments (tests/golden/, script
@@ -22,7 +22,9 @@ Aer itself.**  What IS pinned (tests/test_oracle_*.py):
   * Statistic semantics (unittests/test_statistic_utility.py:24-92);
   * the whole Dicke+Grover+QUBO pipeline against the 8192-shot histograms of
     examples/ExactCover/data/exact_cover_path_problem_example.json (chi^2);
-  * the closed-form p=1 MaxCut energy (independent derivation).
+  * the closed-form p=1 MaxCut energy (independent derivation);
+  * the optimised energies the reference's real pipeline printed into its example notebooks (house graph
+    depth 1-3, ToyExample depth 1: qiskit-aer, 1024 shots) against the oracle's exact optima, within shot noise.
 
 Conventions (SURVEY.md cheat-sheet): bit i of the statevector index x is the
 measured value of qubit i and equals ``string[i]`` of the string handed to
