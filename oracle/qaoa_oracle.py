@@ -24,7 +24,8 @@ Aer itself.**  What IS pinned (tests/test_oracle.py):
     examples/ExactCover/data/exact_cover_path_problem_example.json (chi^2);
   * the closed-form p=1 MaxCut energy (independent derivation);
   * the optimised energies the reference's real pipeline printed into its example notebooks (house graph
-    depth 1-3, ToyExample depth 1: qiskit-aer, 1024 shots) against the oracle's exact optima, within shot noise.
+    depth 1-3, ToyExample depth 1, the three example GML graphs incl. fix_one_node: qiskit-aer, 1024 shots) against
+    the oracle's exact optima within shot noise, and the notebooks' quoted minimum costs bit-exactly.
 
 Conventions (SURVEY.md cheat-sheet): bit i of the statevector index x is the
 measured value of qubit i and equals ``string[i]`` of the string handed to

@@ -99,6 +99,48 @@ def result_file():
         json.dump(d, f, indent=1)
 
 
+def notebook_runs():
+    """The example graphs (DATA files examples/MaxCut/data/*.gml, stored as node / weighted-edge lists in file order) and
+    the numbers the reference's real pipeline (qiskit-aer, 1024 shots) left in its example notebooks' outputs: the
+    `cost(depth d = ...)` log lines of `optimize`, the printed `computeMinMaxCosts()` and the "precalculated" minimum
+    costs quoted in the notebooks' first cells."""
+    import re
+
+    def log_lines(nb, cell):
+        with open(os.path.join(REF, nb)) as f:
+            d = json.load(f)
+        text = "".join("".join(o.get("text", [])) for o in d["cells"][cell].get("outputs", []))
+        runs, cur = [], None
+        for m in re.finditer(r"cost\(depth\s*(\d+)\s*=\s*(-?[0-9.]+)", text):
+            depth, val = int(m.group(1)), float(m.group(2))
+            if depth == 1:
+                cur = []
+                runs.append(cur)
+            cur.append(val)
+        return runs
+
+    out = {"graphs": {}, "runs": {}}
+    for name in ("er_n10_k4_0", "w_ba_n10_k4_0", "w_ba_n21_k4_0"):
+        G = nx.read_gml(os.path.join(REF, "examples/MaxCut/data", name + ".gml"))
+        out["graphs"][name] = {"nodes": [str(x) for x in G.nodes()],
+                               "edges": [[str(u), str(v), G[u][v].get("weight", 1)] for u, v in G.edges()]}
+    out["precalculated_mincost"] = {"w_ba_n10_k4_0": -8.657714089848158,      # ComparisonOptimizers.ipynb cell 4
+                                    "w_ba_n21_k4_0": -25.23404480588015}      # CVaR.ipynb cell 4, WithFlip.ipynb cell 3
+    out["printed_minmax"] = {"er_n10_k4_0": [-12, 0]}                         # FixOneQubit.ipynb cell 6 output
+    # per notebook: the optimise runs in execution order, each a list of cost(depth 1), cost(depth 2), ...
+    out["runs"]["FixOneQubit"] = {"graph": "er_n10_k4_0", "order": ["fix_one_node=False", "fix_one_node=True"],
+                                  "cost": log_lines("examples/MaxCut/FixOneQubit.ipynb", 11)}
+    out["runs"]["ComparisonOptimizers"] = {"graph": "w_ba_n10_k4_0", "order": ["spsa", "qnspsa", "neldermead", "cobyla"],
+                                           "cost": log_lines("examples/MaxCut/ComparisonOptimizers.ipynb", 10)}
+    out["runs"]["CVaR"] = {"graph": "w_ba_n21_k4_0", "order": ["cvar=1", "cvar=0.1"],
+                           "cost": log_lines("examples/MaxCut/CVaR.ipynb", 8)}
+    out["runs"]["MixerComparison"] = {"graph": "house", "order": ["vanilla", "free", "orbit"],
+                                      "cost": log_lines("examples/MaxCut/MixerComparison.ipynb", 15)}
+    with open(os.path.join(OUT, "notebook_runs.json"), "w") as f:
+        json.dump(out, f, indent=1)
+
+
 if __name__ == "__main__":
     main()
     result_file()
+    notebook_runs()

@@ -1,0 +1,76 @@
+"""GPU: the reference's example notebooks replayed through the public API on the device, against the numbers those
+notebooks hold (tests/golden/notebook_runs.json, written by tests/golden/make_golden.py from the reference tree):
+the quoted minimum costs of the real-weighted example graphs and the depth-1 energies qiskit-aer produced (1024 shots),
+which the exact engine must meet within shot noise.  (Runs last among the GPU tests on purpose: file name.)"""
+import json
+import math
+import os
+
+import networkx as nx
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _gold():
+    with open(os.path.join(GOLD, "notebook_runs.json")) as f:
+        return json.load(f)
+
+
+def _graph(gold, name):
+    g = gold["graphs"][name]
+    G = nx.Graph()
+    G.add_nodes_from(g["nodes"])
+    for u, v, w in g["edges"]:
+        G.add_edge(u, v, weight=w)
+    return G
+
+
+def _qaoa(G, dtype, **kw):
+    from qaoa_b200 import QAOA, initialstates, mixers, problems
+
+    fix = kw.pop("fix_one_node", False)
+    return QAOA(problem=problems.MaxKCutBinaryPowerOfTwo(G=G, k_cuts=2, fix_one_node=fix), mixer=mixers.X(),
+                initialstate=initialstates.Plus(), dtype=dtype, **kw)
+
+
+@pytest.mark.parametrize("dtype", ["complex128", "complex64"])
+def test_quoted_minimum_costs(dtype):
+    """ComparisonOptimizers.ipynb cell 4 / CVaR.ipynb cell 4 (`mincost = ...  # precalculated`), FixOneQubit.ipynb cell 6
+    (`computeMinMaxCosts()` printed -12 0): extremes of the device cost diagonal (F64 in complex128, 32-bit fixed point in
+    complex64)."""
+    gold = _gold()
+    rel = 1e-12 if dtype == "complex128" else 1e-8
+    for name, want in gold["precalculated_mincost"].items():
+        q = _qaoa(_graph(gold, name), dtype)
+        lo, hi = q._get_engine().cost_minmax()
+        assert -hi == pytest.approx(want, rel=rel) and abs(lo) <= rel * abs(want), (name, lo, hi)
+    q = _qaoa(_graph(gold, "er_n10_k4_0"), dtype)
+    lo, hi = q._get_engine().cost_minmax()
+    assert [-hi, -lo] == gold["printed_minmax"]["er_n10_k4_0"]            # integer weights: exact
+
+
+def test_depth1_energies_meet_aer_within_shot_noise():
+    """optimize(depth=1) on the device (exact energies, COBYLA from the landscape seed) against the `cost(depth 1 = ...)`
+    values of FixOneQubit.ipynb (both circuits), ComparisonOptimizers.ipynb (four optimisers) and CVaR.ipynb (21 qubits)."""
+    gold = _gold()
+
+    def exact_depth1(name, **kw):
+        q = _qaoa(_graph(gold, name), "complex128", **kw)
+        q.optimize(depth=1, angles={"gamma": [0, np.pi, 24], "beta": [0, np.pi / 2, 12]})
+        return q.get_Exp(1), math.sqrt(q.get_Var(1) / 1024.0)
+
+    run = gold["runs"]["FixOneQubit"]
+    for fix, costs in zip((False, True), run["cost"]):
+        got, sigma = exact_depth1(run["graph"], fix_one_node=fix)
+        assert abs(costs[0] - got) < 4 * sigma, (fix, costs[0], got, sigma)
+    run = gold["runs"]["ComparisonOptimizers"]
+    got, sigma = exact_depth1(run["graph"])
+    for name, costs in zip(run["order"], run["cost"]):
+        assert abs(costs[0] - got) < 4 * sigma, (name, costs[0], got, sigma)
+    run = gold["runs"]["CVaR"]
+    got, sigma = exact_depth1(run["graph"])
+    assert abs(run["cost"][0][0] - got) < 4 * sigma, (run["cost"][0][0], got, sigma)

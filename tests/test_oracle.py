@@ -355,3 +355,71 @@ def test_energies_printed_by_the_reference_notebooks():
     toy.add_weighted_edges_from([(0, 1, 1.0), (0, 2, 1.0), (1, 2, 1.0), (3, 2, 1.0), (3, 4, 1.0), (4, 2, 1.0)])
     opt, sigma = _exact_optimum(toy, 1)
     assert abs(-3.9316406249999996 - opt) < 4 * sigma, (opt, sigma)       # -3.9316 vs -3.9288
+
+
+def _notebook_graph(gold, name):
+    g = gold["graphs"][name]
+    G = nx.Graph()
+    G.add_nodes_from(g["nodes"])
+    for u, v, w in g["edges"]:
+        G.add_edge(u, v, weight=w)
+    return G
+
+
+def _notebook_diag(gold, name, fix_one_node=False):
+    G = _notebook_graph(gold, name)
+    edges = orc.graph_edges(orc.relabel_graph(G))
+    colors, table = orc.colour_table(2)
+    n = G.number_of_nodes()
+    return n - int(fix_one_node), orc.maxkcut_diag(edges, n, 1, table, colors, fix_one_node=fix_one_node)
+
+
+def _p1_optimum(n, diag, starts):
+    """exact depth-1 optimum of Exp = -E[cost] (C oracle, Nelder-Mead) and the sigma of a 1024-shot estimate there"""
+    from scipy.optimize import minimize
+    from oracle import c_oracle
+
+    c_oracle.build()
+    best = None
+    for x0 in starts:
+        r = minimize(lambda a: -c_oracle.energy(n, diag, a, "complex128")[0], np.asarray(x0, dtype=float),
+                     method="Nelder-Mead", options={"xatol": 1e-6, "fatol": 1e-8})
+        if best is None or r.fun < best.fun:
+            best = r
+    e = c_oracle.energy(n, diag, best.x, "complex128")
+    return best.fun, math.sqrt(max(e[1] - e[0] ** 2, 0.0) / 1024.0)
+
+
+def test_notebook_graphs_known_answers_and_aer_energies():
+    """tests/golden/notebook_runs.json (written by make_golden.py from the reference's example data and notebook outputs):
+    (i) the cost diagonal's extremes equal the minimum costs the notebooks quote / print, to the last bit for the
+    real-weighted graphs; (ii) the depth-1 `cost(...)` values qiskit-aer produced (1024 shots) agree with the oracle's
+    exact depth-1 optimum within shot noise -- for plain MaxCut on three graphs and for the `fix_one_node=True` circuit,
+    whatever optimiser the notebook used (SPSA, QNSPSA, Nelder-Mead, COBYLA)."""
+    with open(os.path.join(GOLD, "notebook_runs.json")) as f:
+        gold = json.load(f)
+    grid = [(g, b) for g in (0.5, 0.8) for b in (0.3, 0.45)]
+    # (i) known answers
+    for name, want in gold["precalculated_mincost"].items():
+        _, diag = _notebook_diag(gold, name)
+        assert -diag.max() == want and diag.min() == 0.0, name            # bit-exact: -8.657714089848158, -25.23404480588015
+    _, diag = _notebook_diag(gold, "er_n10_k4_0")
+    assert [-diag.max(), -diag.min()] == gold["printed_minmax"]["er_n10_k4_0"]
+    # (ii) Aer's depth-1 energies
+    run = gold["runs"]["FixOneQubit"]
+    for fix, costs in zip((False, True), run["cost"]):
+        n, diag = _notebook_diag(gold, run["graph"], fix_one_node=fix)
+        assert n == (9 if fix else 10)
+        opt, sigma = _p1_optimum(n, diag, grid)
+        assert abs(costs[0] - opt) < 4 * sigma, (fix, costs[0], opt, sigma)   # -10.447 vs -10.413, -10.339 vs -10.305
+        assert all(c > -diag.max() for c in costs)
+    run = gold["runs"]["ComparisonOptimizers"]
+    n, diag = _notebook_diag(gold, run["graph"])
+    opt, sigma = _p1_optimum(n, diag, grid)
+    for name, costs in zip(run["order"], run["cost"]):
+        assert abs(costs[0] - opt) < 4 * sigma, (name, costs[0], opt, sigma)   # -6.91 ... -7.02 vs -6.945, sigma 0.033
+    run = gold["runs"]["CVaR"]
+    n, diag = _notebook_diag(gold, run["graph"])                               # 21 qubits
+    opt, sigma = _p1_optimum(n, diag, [(0.7, 0.35)])
+    assert abs(run["cost"][0][0] - opt) < 4 * sigma, (run["cost"][0][0], opt, sigma)   # -19.918 vs -19.776, sigma 0.063
+    assert run["cost"][1][0] < run["cost"][0][0]                               # CVaR(0.1) lies below the mean
