@@ -298,6 +298,20 @@ class Engine:
         self._check(self._lib.qaoa_read_statevector(self._h, _dptr(out)))
         return out.view(np.complex128)
 
+    def final_probabilities(self, angles):
+        """|psi(angles)|^2 for every basis state (host array of 2^n doubles): one evaluation with the final state kept in
+        HBM, read back once.  For statistics of the final state that have no device reduction yet (the exact CVaR of
+        real-valued costs); the evolution itself runs on the device."""
+        angles = np.ascontiguousarray(angles, dtype=np.float64).reshape(-1)
+        self.set_option("keep_state", 1)
+        try:
+            self.energy(angles)
+            psi = self.read_statevector()
+        finally:
+            self.set_option("keep_state", 0)
+        pr = psi.real ** 2 + psi.imag ** 2
+        return pr / pr.sum()
+
     def continue_from_kept_state(self, flip_mask=0):
         """X gates between layers (the reference's flip=True, qaoa/qaoa.py:505-509): the state kept by the last evaluation
         (option keep_state=1), with X applied on the qubits of ``flip_mask`` (bit q = qubit q), becomes the initial

@@ -261,6 +261,7 @@ class QAOA:
     def __getstate__(self):
         state = dict(self.__dict__)
         state["_engine"] = None  # device handles are re-created lazily after unpickling
+        state.pop("_cvar_sorted", None)
         return state
 
     def _get_engine(self):
@@ -320,7 +321,7 @@ class QAOA:
         else:
             res = eng.energy_batch(mine)
         if self.cvar < 1:
-            cv = np.array([self._exact_cvar(*self._device_call("cost_distribution", r)) for r in mine])
+            cv = np.array([self._cvar_of(r) for r in mine])
         else:
             cv = res[:, 0]
         out = np.column_stack([res, cv])
@@ -375,6 +376,40 @@ class QAOA:
         finally:
             eng.set_option("keep_state", 0)
             self.initialstate.lower_initial(eng)        # back to the circuit's own initial state
+
+    _CVAR_HOST_MAX_QUBITS = 26
+
+    def _cvar_of(self, eng_row):
+        """exact CVaR of the final state's cost distribution.  Integer-valued costs (range <= 255): the device's cost-value
+        histogram.  Real-valued costs (weighted graphs, scaled ExactCover, Portfolio: the reference's CVaR.ipynb and
+        CompareGroverXY.ipynb cases): |psi|^2 is read back once per evaluation and the tail mean is taken on the host
+        over the cost diagonal sorted once (the reference's Statistic is host code too, statistic.py:132-142); registers
+        beyond 26 qubits are rejected."""
+        from qaoa_b200.engine import EngineError
+
+        eng = self._get_engine()
+        if getattr(self, "_cvar_on_host", None) is None:
+            try:
+                costs, probs = self._device_call("cost_distribution", eng_row)
+                self._cvar_on_host = False
+                return self._exact_cvar(costs, probs)
+            except EngineError as exc:
+                if "integer-valued" not in str(exc):
+                    raise
+                self._cvar_on_host = True
+        if not self._cvar_on_host:
+            return self._exact_cvar(*self._device_call("cost_distribution", eng_row))
+        if self.problem.N_qubits > self._CVAR_HOST_MAX_QUBITS:
+            _reject("cvar < 1 with real-valued costs on more than %d qubits" % self._CVAR_HOST_MAX_QUBITS)
+        if getattr(self, "_cvar_sorted", None) is None:
+            diag = np.asarray(eng.read_cost_diagonal(), dtype=np.float64)
+            order = np.argsort(-diag, kind="stable")
+            self._cvar_sorted = (order, diag[order])
+        order, costs = self._cvar_sorted
+        probs = np.asarray(self._device_call("final_probabilities", eng_row))[order]
+        cum = np.cumsum(probs)
+        take = np.clip(self.cvar - (cum - probs), 0.0, probs)
+        return float(take @ costs) / self.cvar
 
     def _exact_cvar(self, costs, probs):
         order = np.argsort(-costs, kind="stable")

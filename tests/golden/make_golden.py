@@ -136,6 +136,15 @@ def notebook_runs():
                            "cost": log_lines("examples/MaxCut/CVaR.ipynb", 8)}
     out["runs"]["MixerComparison"] = {"graph": "house", "order": ["vanilla", "free", "orbit"],
                                       "cost": log_lines("examples/MaxCut/MixerComparison.ipynb", 15)}
+    # ExactCover/CompareGroverXY.ipynb: the problem of the result file (tests/golden/qaoaio_result_example.json) rebuilt with
+    # TODAY's scale_problem=True, Dicke(2) + Grover(Dicke(2)), cvar = 0.7 (from the file), COBYLA, optimize(depth=10)
+    with open(os.path.join(REF, "examples/ExactCover/CompareGroverXY.ipynb")) as f:
+        cell5 = "".join("".join(o.get("text", [])) for o in json.load(f)["cells"][5].get("outputs", []))
+    m = re.search(r"Optimal solution \(brute force\):\s*([01]+)\s*Cost:\s*(-?[0-9.]+)", cell5)
+    out["runs"]["CompareGroverXY"] = {"problem": "qaoaio_result_example.json", "order": ["grover"], "cvar": 0.7,
+                                      "hamming_weight": 2, "optimal_solution": m.group(1),
+                                      "optimal_cost_printed_6_digits": float(m.group(2)),
+                                      "cost": log_lines("examples/ExactCover/CompareGroverXY.ipynb", 7)}
     with open(os.path.join(OUT, "notebook_runs.json"), "w") as f:
         json.dump(out, f, indent=1)
 

@@ -74,3 +74,37 @@ def test_depth1_energies_meet_aer_within_shot_noise():
     run = gold["runs"]["CVaR"]
     got, sigma = exact_depth1(run["graph"])
     assert abs(run["cost"][0][0] - got) < 4 * sigma, (run["cost"][0][0], got, sigma)
+
+
+@pytest.mark.parametrize("dtype", ["complex128", "complex64"])
+def test_exactcover_grover_cvar_run(dtype):
+    """examples/ExactCover/CompareGroverXY.ipynb cells 5-7 on the device: ExactCover (scale_problem=True), Dicke(2) +
+    Grover(Dicke(2)), cvar = 0.7, default landscape, COBYLA, INTERP; qiskit-aer printed 0.178078, 0.110158, 0.082881, 0.082268
+    for depths 1-4 (1024 shots)."""
+    from qaoa_b200 import QAOA, initialstates, mixers, problems
+
+    gold = _gold()
+    run = gold["runs"]["CompareGroverXY"]
+    with open(os.path.join(GOLD, run["problem"])) as f:
+        pr = json.load(f)["problem"]
+    ec = problems.ExactCover(columns=np.array(pr["columns"]), weights=np.array(pr["weights"]),
+                             hamming_weight=run["hamming_weight"], scale_problem=True)
+    k = run["hamming_weight"]
+    q = QAOA(problem=ec, mixer=mixers.Grover(initialstates.Dicke(k)), initialstate=initialstates.Dicke(k), cvar=run["cvar"],
+             dtype=dtype)
+    q.optimize(depth=4)
+    for d, aer in zip((1, 2, 3, 4), run["cost"][0]):
+        assert q.get_Exp(d) == pytest.approx(aer, abs=1.5e-3), (d, q.get_Exp(d), aer)
+
+
+def test_cvar_of_real_valued_costs_at_21_qubits():
+    """examples/MaxCut/CVaR.ipynb: MaxCut on the real-weighted 21-node graph with cvar = 0.1.  Real-valued costs have no
+    device histogram; the exact CVaR is taken from |psi|^2 read back once per evaluation (QAOA._cvar_of).  qiskit-aer
+    printed cost(depth 1) = -23.080 (the best 102 of 1024 shots); the exact depth-1 optimum of CVaR(0.1) is -23.01."""
+    gold = _gold()
+    run = gold["runs"]["CVaR"]
+    q = _qaoa(_graph(gold, run["graph"]), "complex64", cvar=0.1)
+    q.optimize(depth=1, angles={"gamma": [0, np.pi, 12], "beta": [0, np.pi / 2, 8]})
+    assert q._cvar_on_host
+    assert abs(q.get_Exp(1) - run["cost"][1][0]) < 0.25, (q.get_Exp(1), run["cost"][1][0])
+    assert q.get_Exp(1) > gold["precalculated_mincost"][run["graph"]]
