@@ -145,6 +145,21 @@ def notebook_runs():
                                       "hamming_weight": 2, "optimal_solution": m.group(1),
                                       "optimal_cost_printed_6_digits": float(m.group(2)),
                                       "cost": log_lines("examples/ExactCover/CompareGroverXY.ipynb", 7)}
+    # ExactCover/ExactCover 6 3.ipynb: tail-assignment instance data/FRCR_6_24_3.txt (a DATA file, read with the format
+    # the notebook's loader documents: "weight:row,row,..." per column, then the best state), Plus + X, interpolate=False,
+    # landscape {"gamma": [0, 6 pi, 60], "beta": [0, 2 pi, 20]}; cell 7 printed computeMinMaxCosts() = (6.0, 10.0)
+    rows = [ln.strip() for ln in open(os.path.join(REF, "examples/ExactCover/data/FRCR_6_24_3.txt")) if ln.strip()]
+    R, F = 6, 24
+    cols = [[0] * R for _ in range(F)]
+    weights = []
+    for r in range(R):
+        w, idx = rows[r].split(":")
+        weights.append(float(w))
+        for i in idx.split(","):
+            cols[int(i)][r] = 1
+    out["runs"]["ExactCover_6_3"] = {"columns": cols, "weights": weights, "best": [int(x) for x in rows[R].split(",")],
+                                     "printed_minmax": [6.0, 10.0], "order": ["plus_x_gridsearch"],
+                                     "cost": log_lines("examples/ExactCover/ExactCover 6 3.ipynb", 6)}
     with open(os.path.join(OUT, "notebook_runs.json"), "w") as f:
         json.dump(out, f, indent=1)
 

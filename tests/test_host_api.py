@@ -637,3 +637,24 @@ def test_exactcover_grover_cvar_run_of_the_reference_notebook():
     for d, aer in zip((1, 2, 3), run["cost"][0]):
         assert q.get_Exp(d) == pytest.approx(aer, abs=1.5e-3), (d, q.get_Exp(d), aer)
     assert min(run["cost"][0]) > -ec.cost(run["optimal_solution"])        # no sampled CVaR beats the optimal cover
+
+
+def test_exactcover_tail_assignment_notebook():
+    """examples/ExactCover/"ExactCover 6 3.ipynb": the 6-route / 24-flight instance with Plus + X, interpolate=False and the
+    notebook's landscape grid.  Known answer: computeMinMaxCosts() printed (6.0, 10.0).  qiskit-aer's cost(depth 1) = 296.40
+    sits on a landscape of sampled energies with sigma = 5.8; the exact control flow gives 303.02 (1.1 sigma)."""
+    import json
+    import os
+
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "notebook_runs.json")) as f:
+        run = json.load(f)["runs"]["ExactCover_6_3"]
+    ec = problems.ExactCover(columns=np.array(run["columns"], dtype=float), weights=np.array(run["weights"]))
+    assert list(ec.computeMinMaxCosts()) == run["printed_minmax"]
+    best = "".join(str(b) for b in run["best"])
+    assert ec.isFeasible(best) and -ec.cost(best) == run["printed_minmax"][0]
+    q, fake = make(ec, interpolate=False)
+    q.sample_cost_landscape(angles={"gamma": [0, 6 * np.pi, 60], "beta": [0, 2 * np.pi, 20]})
+    assert q.Exp_sampled_p1.shape == (20, 60)
+    q.optimize(depth=1)
+    sigma = np.sqrt(q.get_Var(1) / 1024.0)
+    assert abs(q.get_Exp(1) - run["cost"][0][0]) < 4 * sigma, (q.get_Exp(1), run["cost"][0][0], sigma)
