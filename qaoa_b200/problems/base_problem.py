@@ -51,6 +51,13 @@ class Problem(BaseProblem):
             diag[x] = self.cost("".join("1" if (x >> i) & 1 else "0" for i in range(n)))
         engine.set_cost_diagonal(diag)
 
+    def validate_circuit(self, t=1, flip=True, atol=1e-8, rtol=1e-8, engine=None):
+        """(ok, report): the device's phase separator exp(+i t c_dev(x)) against exp(+i t cost(string)) for every string, up
+        to a global phase (reference base_problem.py:136-149 -> utils/validation.py:16-79); <= 16 qubits."""
+        from qaoa_b200.utils import validation
+
+        return validation.check_phase_separator_exact_problem(self, t=t, flip=flip, atol=atol, rtol=rtol, engine=engine)
+
     def engine_gammas(self, gammas):
         """this layer's cost parameters -> the gammas the device phase separator exp(+i gamma cost) takes (identity
         unless the reference's phase-separator CIRCUIT realises a different multiple of its cost function)"""

@@ -709,16 +709,9 @@ class QAOA:
         return np.unique([x for i in keep for x in sols[i]])
 
     def validate_circuit(self, t=1, flip=True, atol=1e-8, rtol=1e-8):
-        """The reference compares the circuit's diagonal with exp(i t cost) (validation.py:16-79).
-        Here the phase separator IS that diagonal; what can be validated is that the device
-        diagonal equals ``problem.cost`` for every bit-string."""
-        n = self.problem.N_qubits
-        if n > 16:
-            raise ValueError("validate_circuit is a brute-force check for <= 16 qubits")
-        dev = self._get_engine().read_cost_diagonal()
-        host = np.array([
-            self.problem.cost("".join("1" if (x >> i) & 1 else "0" for i in range(n))) for x in range(1 << n)
-        ], dtype=np.float64)
-        err = float(np.max(np.abs(dev - host)))
-        ok = err <= atol + rtol * float(np.max(np.abs(host)))
-        return ok, {"n_qubits": n, "max_cost_error": err}
+        """The reference compares the circuit's diagonal with exp(i t cost) (qaoa.py:1217-1218 -> validation.py:16-79).
+        Here the phase separator IS the diagonal exp(i t c_dev) of the device's cost diagonal; it is compared with
+        exp(i t problem.cost(string)) for every bit-string, same arguments and report keys (<= 16 qubits)."""
+        from qaoa_b200.utils import validation
+
+        return validation.check_phase_separator_exact_qaoa(self, t=t, flip=flip, atol=atol, rtol=rtol)

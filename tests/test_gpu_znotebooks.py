@@ -108,3 +108,18 @@ def test_cvar_of_real_valued_costs_at_21_qubits():
     assert q._cvar_on_host
     assert abs(q.get_Exp(1) - run["cost"][1][0]) < 0.25, (q.get_Exp(1), run["cost"][1][0])
     assert q.get_Exp(1) > gold["precalculated_mincost"][run["graph"]]
+
+
+@pytest.mark.parametrize("name", sorted(__import__("parity_helpers").reference_validate_cases()))
+def test_validate_circuit_cases_of_the_reference_on_the_device(name):
+    """unittests/test_validate_circuits.py:11-147 with the device's cost diagonal standing where the reference has the
+    phase-separator circuit's unitary: exp(i t c_dev(x)) equals exp(i t cost(string)) up to a global phase."""
+    import parity_helpers as H
+    from qaoa_b200 import QAOA, initialstates, mixers
+
+    make_problem, t = H.reference_validate_cases()[name]
+    q = QAOA(problem=make_problem(), mixer=mixers.X(), initialstate=initialstates.Plus())
+    ok, report = q.validate_circuit(t=t)
+    assert ok, report
+    ok2, report2 = make_problem().validate_circuit(t=t)
+    assert ok2 and report2["max_cost_error"] < 1e-9, report2

@@ -658,3 +658,22 @@ def test_exactcover_tail_assignment_notebook():
     q.optimize(depth=1)
     sigma = np.sqrt(q.get_Var(1) / 1024.0)
     assert abs(q.get_Exp(1) - run["cost"][0][0]) < 4 * sigma, (q.get_Exp(1), run["cost"][0][0], sigma)
+
+
+@pytest.mark.parametrize("name", sorted(__import__("parity_helpers").reference_validate_cases()))
+def test_validate_circuit_cases_of_the_reference(name):
+    """unittests/test_validate_circuits.py:11-147: `qaoa.validate_circuit()` is OK for every problem there, with the
+    reference's report keys; also through `problem.validate_circuit()` and with the bit order un-flipped it is not."""
+    import parity_helpers as H
+
+    make_problem, t = H.reference_validate_cases()[name]
+    q, fake = make(make_problem())
+    ok, report = q.validate_circuit(t=t)
+    assert ok, report
+    assert {"n_qubits", "max_magnitude_error", "max_phase_error_rad_after_global", "global_phase_rad"} <= set(report)
+    pr = make_problem()
+    ok2, report2 = pr.validate_circuit(t=t, engine=OracleEngine(pr.N_qubits))
+    assert ok2 and report2["max_cost_error"] < 1e-9
+    if name in ("qubo_linear_offset", "qubo_large_asymmetric_linear"):      # not invariant under reversing the string
+        bad, rep = q.validate_circuit(t=t, flip=False)
+        assert not bad and rep["examples"]
