@@ -527,6 +527,35 @@ class QAOA:
         self.last_hist = {}
         LOG.info("Calculating Energy landscape done")
 
+    def measurementStatistics(self, job):
+        """Statistics of SAMPLED counts, with the reference's semantics (qaoa.py:669-740): ``job`` is a histogram
+        {string: count} in the sampler's printing order (qubit 0 LAST) -- e.g. ``hist()`` with its keys reversed --, a list of
+        such histograms for a landscape grid in (beta, gamma) order, or any object whose ``result().get_counts()`` returns
+        either.  A single histogram is accumulated into ``self.stat`` (CVaR, Bessel-corrected variance, extremes among the
+        sampled strings); a list fills ``Exp/Var/MaxCost/MinCost_sampled_p1`` on the grid of ``landscape_p1_angles``.
+        The exact engine never calls this itself; it serves code that post-processes sampled histograms."""
+        counts_list = job.result().get_counts() if hasattr(job, "result") else job
+        self.last_hist = counts_list
+
+        def accumulate(counts):
+            for string, weight in counts.items():
+                self.stat.add_sample(self.problem.cost(string[::-1]), weight, string[::-1])
+
+        if isinstance(counts_list, list):
+            rows = []
+            for counts in counts_list:
+                self.stat.reset()
+                accumulate(counts)
+                rows.append((self.stat.get_CVaR(), self.stat.get_Variance(), self.stat.get_max(), self.stat.get_min()))
+            rows = np.asarray(rows, dtype=np.float64)
+            shape = (self.landscape_p1_angles["beta"][2], self.landscape_p1_angles["gamma"][2])
+            self.Exp_sampled_p1 = -rows[:, 0].reshape(shape)
+            self.Var_sampled_p1 = rows[:, 1].reshape(shape)
+            self.MaxCost_sampled_p1 = -rows[:, 2].reshape(shape)
+            self.MinCost_sampled_p1 = -rows[:, 3].reshape(shape)
+        else:
+            accumulate(counts_list)
+
     @staticmethod
     def _argmin_first(values):
         """np.argmin with a deterministic tie-break: landscapes of symmetric problems have exactly

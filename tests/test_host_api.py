@@ -677,3 +677,35 @@ def test_validate_circuit_cases_of_the_reference(name):
     if name in ("qubo_linear_offset", "qubo_large_asymmetric_linear"):      # not invariant under reversing the string
         bad, rep = q.validate_circuit(t=t, flip=False)
         assert not bad and rep["examples"]
+
+
+def test_measurement_statistics_of_sampled_counts():
+    """reference qaoa.py:669-740 with plain histograms standing where the qiskit job was: Statistic semantics (weighted
+    mean, Bessel variance S/(W-1), extremes among the sampled strings), landscape lists on the (beta, gamma) grid."""
+    q, fake = readme_qaoa(shots=500)
+    ang = [0.61, 0.39]
+    counts = {s[::-1]: c for s, c in q.hist(ang, 500).items()}          # printing order, as get_counts() returns them
+    q.stat.reset()
+    q.measurementStatistics(counts)
+    costs = np.array([q.problem.cost(s[::-1]) for s in counts for _ in range(counts[s])])
+    assert q.last_hist is counts
+    assert q.stat.get_CVaR() == pytest.approx(costs.mean()) and q.stat.get_Variance() == pytest.approx(costs.var(ddof=1))
+    assert q.stat.get_max() == costs.max() and q.stat.get_min() == costs.min()
+    assert -q.stat.get_CVaR() == pytest.approx(q._eval_cost(ang), abs=0.5)          # 500 shots around the exact value
+
+    class Job:                                                                       # qiskit-like wrapper
+        def __init__(self, c):
+            self.c = c
+
+        def result(self):
+            return self
+
+        def get_counts(self):
+            return self.c
+
+    q.landscape_p1_angles = {"gamma": [0, 1, 3], "beta": [0, 1, 2]}
+    grid = [{s[::-1]: c for s, c in q.hist([g, b], 64).items()} for b in (0.0, 0.5) for g in (0.0, 1 / 3, 2 / 3)]
+    q.measurementStatistics(Job(grid))
+    assert q.Exp_sampled_p1.shape == q.Var_sampled_p1.shape == (2, 3)
+    assert q.Exp_sampled_p1[0, 0] == pytest.approx(-6.0, abs=1.0)                     # (gamma, beta) = 0: |+>, 12 edges / 2
+    assert (q.MaxCost_sampled_p1 <= q.Exp_sampled_p1).all() and (q.Exp_sampled_p1 <= q.MinCost_sampled_p1).all()
