@@ -13,6 +13,8 @@ from .base_mixer import Mixer
 
 
 class MaxKCutLX(Mixer):
+    not_lowerable = True
+
     def __init__(self, k_cuts: int, color_encoding: str, topology: str = "standard"):
         if (k_cuts < 2) or (k_cuts > 8):
             raise ValueError("k_cuts must be 2 or more, and is not implemented for k_cuts > 8")

@@ -273,6 +273,12 @@ class QAOA:
                 _reject("problems with more than one gamma per layer (other than MaxCutFree / MaxCutOrbit)")
             if self.initialstate.get_num_parameters() != 0 and type(self.initialstate).__name__ != "PlusParameterized":
                 _reject("parameterised initial states (other than PlusParameterized)")
+            # plugins that cannot be lowered are rejected BEFORE a device is touched (same error with or without a GPU)
+            mixer_cls, state_cls = type(self.mixer), type(self.initialstate)
+            if mixer_cls.lower_mixer is Mixer.lower_mixer or getattr(self.mixer, "not_lowerable", False):
+                self.mixer.lower_mixer(None, trotter=self.number_trottersteps_mixer)        # raises NotImplementedError
+            if state_cls.state_descriptor is InitialState.state_descriptor and state_cls.lower_initial is InitialState.lower_initial:
+                self.initialstate.state_descriptor()                                        # raises NotImplementedError
             if getattr(self.backend, "sharded", False):
                 from qaoa_b200.sharded import DistShardedEngine
                 eng = DistShardedEngine(self.problem.N_qubits, dtype=self.backend.dtype, device=self.backend.device,

@@ -310,6 +310,13 @@ def test_unsupported_features_are_rejected_not_rerouted():
             mixers.MaxKCutLX(*bad)
     with pytest.raises(NotImplementedError):
         lx.lower_mixer(OracleEngine(4))
+    # ... and QAOA rejects such plugins before it touches a device (no GPU in this test)
+    Gk = nx.Graph([(0, 1), (1, 2)])
+    for kw in ({"mixer": lx, "initialstate": initialstates.LessThanK(3)}, {"mixer": GateMixer(), "initialstate": I},
+               {"mixer": mixers.X(), "initialstate": GateState()}):
+        qq = QAOA(problem=problems.MaxKCutBinaryPowerOfTwo(Gk, k_cuts=4), **kw)
+        with pytest.raises(NotImplementedError):
+            qq.createParameterizedCircuit(1)
 
 
 def test_user_problem_uses_the_diagonal_escape_hatch():
