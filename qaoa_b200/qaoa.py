@@ -363,6 +363,8 @@ class QAOA:
         from there; ``name`` is called for the last segment, whose result is the whole circuit's."""
         eng = self._get_engine()
         row = np.asarray(eng_row, dtype=np.float64)
+        if not hasattr(eng, name):
+            _reject("%s on a sharded register (single-GPU engines only)" % name)
         if not self._flips_active(row):
             return getattr(eng, name)(row, *args, **kw)
         n_init, per = eng.n_init, eng.n_gamma + eng.n_beta

@@ -716,3 +716,20 @@ def test_measurement_statistics_of_sampled_counts():
     assert q.Exp_sampled_p1.shape == q.Var_sampled_p1.shape == (2, 3)
     assert q.Exp_sampled_p1[0, 0] == pytest.approx(-6.0, abs=1.0)                     # (gamma, beta) = 0: |+>, 12 edges / 2
     assert (q.MaxCost_sampled_p1 <= q.Exp_sampled_p1).all() and (q.Exp_sampled_p1 <= q.MinCost_sampled_p1).all()
+
+
+def test_sampling_and_cvar_are_rejected_cleanly_on_engines_without_them():
+    """a sharded register has no sampler / cost distribution: NotImplementedError, not an AttributeError"""
+    q, fake = readme_qaoa(cvar=0.5)
+
+    class Bare:                                     # the surface DistShardedEngine offers
+        n_init, n_gamma, n_beta = 0, 1, 1
+
+        def energy_batch(self, rows):
+            return fake.energy_batch(rows)
+
+    q._engine = Bare()
+    with pytest.raises(NotImplementedError):
+        q.hist([0.3, 0.2], 10)
+    with pytest.raises(NotImplementedError):
+        q._eval_cost([0.3, 0.2])
