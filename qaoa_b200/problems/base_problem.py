@@ -69,8 +69,21 @@ class Problem(BaseProblem):
     def get_num_parameters(self):
         return 1
 
-    def computeMinMaxCosts(self):
-        """Brute force over all feasible strings, like the reference (base_problem.py:121-134)."""
+    _MINMAX_BRUTE_FORCE_QUBITS = 16
+
+    def computeMinMaxCosts(self, engine=None):
+        """(min, max) of -cost over the feasible strings (reference base_problem.py:121-134, a Python loop over all 2^n
+        strings).  Unconstrained problems beyond 16 qubits -- or whenever an ``engine`` is given -- take the extremes of
+        the cost diagonal from a device reduction instead (qaoa_cost_minmax); constrained problems keep the loop."""
+        unconstrained = type(self).isFeasible is Problem.isFeasible
+        if unconstrained and (engine is not None or self.N_qubits > self._MINMAX_BRUTE_FORCE_QUBITS):
+            if engine is None:
+                from qaoa_b200.engine import Engine
+
+                engine = Engine(self.N_qubits, dtype="complex128")
+            self.lower_cost(engine)
+            cmin, cmax = engine.cost_minmax()
+            return -cmax, -cmin
         lo, hi = float("inf"), float("-inf")
         for bits in itertools.product("01", repeat=self.N_qubits):
             s = "".join(bits)

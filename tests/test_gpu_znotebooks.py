@@ -51,6 +51,11 @@ def test_quoted_minimum_costs(dtype):
     q = _qaoa(_graph(gold, "er_n10_k4_0"), dtype)
     lo, hi = q._get_engine().cost_minmax()
     assert [-hi, -lo] == gold["printed_minmax"]["er_n10_k4_0"]            # integer weights: exact
+    if dtype == "complex128":       # the reference's own call (FixOneQubit.ipynb cell 6), and beyond its brute-force reach
+        assert list(q.problem.computeMinMaxCosts(engine=q._get_engine())) == gold["printed_minmax"]["er_n10_k4_0"]
+        big = _qaoa(_graph(gold, "w_ba_n21_k4_0"), dtype).problem
+        lo21, hi21 = big.computeMinMaxCosts()                              # 21 qubits: device reduction
+        assert lo21 == pytest.approx(gold["precalculated_mincost"]["w_ba_n21_k4_0"], rel=1e-12) and hi21 == 0.0
 
 
 def test_depth1_energies_meet_aer_within_shot_noise():

@@ -117,6 +117,9 @@ class OracleEngine:
     def final_probabilities(self, row):
         return self._prob(row)
 
+    def cost_minmax(self):
+        return float(self.diag.min()), float(self.diag.max())
+
     def cost_distribution(self, row):
         if self.options.get("device_like") and not (np.all(self.diag == np.round(self.diag)) and np.ptp(self.diag) <= 255):
             raise eng.EngineError("cost distribution needs integer-valued costs with a range <= 255")
@@ -733,3 +736,26 @@ def test_sampling_and_cvar_are_rejected_cleanly_on_engines_without_them():
         q.hist([0.3, 0.2], 10)
     with pytest.raises(NotImplementedError):
         q._eval_cost([0.3, 0.2])
+
+
+def test_compute_min_max_costs_uses_the_device_reduction_for_unconstrained_problems():
+    """reference base_problem.py:121-134 (brute force) vs the device reduction over the cost diagonal"""
+    pr = problems.MaxCut(nx.random_regular_graph(3, 8, seed=42))
+    brute = pr.computeMinMaxCosts()
+    assert brute == (-10, 0)                                               # SURVEY 8c K2: max cut 10
+    assert pr.computeMinMaxCosts(engine=OracleEngine(8)) == (-10.0, 0.0)
+    big = problems.MaxCut(nx.random_regular_graph(3, 18, seed=42))          # beyond the brute-force limit: device only
+    from qaoa_b200.engine import EngineError
+    lo, hi = big.computeMinMaxCosts(engine=OracleEngine(18))
+    assert hi == 0.0 and -27 <= lo <= -20
+    try:                                                                    # without a GPU: an error, never a CPU fallback
+        assert big.computeMinMaxCosts() == (lo, hi)
+    except EngineError as exc:
+        assert "CUDA" in str(exc) or "device" in str(exc)
+    # constrained problems keep the reference's loop over feasible strings
+    rng = np.random.RandomState(0)
+    A = rng.randn(6, 20)
+    po = problems.PortfolioOptimization(risk=0.5, budget=2, cov_matrix=np.cov(A), exp_return=A.mean(axis=1), penalty=0)
+    lo, hi = po.computeMinMaxCosts()
+    feas = [-po.cost(format(x, "06b")) for x in range(64) if po.isFeasible(format(x, "06b"))]
+    assert (lo, hi) == (min(feas), max(feas)) and len(feas) == 15
