@@ -22,18 +22,23 @@ _CLASSES = {
 class MaxKCutBinaryFullH(GraphProblem):
     def __init__(self, G, k_cuts: int, color_encoding: str, method: str = "Diffusion",
                  fix_one_node: bool = False) -> None:
-        if k_cuts not in (3, 5, 6, 7):
+        MaxKCutBinaryFullH.validate_parameters(k_cuts, method, fix_one_node)
+        self.k_cuts = k_cuts
+        self.method = method
+        self.color_encoding = color_encoding
+        super().__init__(G, int(np.ceil(np.log2(k_cuts))), fix_one_node)
+        self.construct_colors()
+
+    @staticmethod
+    def validate_parameters(k, method, fix_one_node) -> None:
+        """the reference's checks and messages (maxkcut_binary_fullH.py:90-117)"""
+        if k not in (3, 5, 6, 7):
             raise ValueError("k_cuts must be in " + str([3, 5, 6, 7]))
         if method not in ("PauliBasis", "PowerOfTwo", "Diffusion"):
             raise ValueError("method must be in " + str(["PauliBasis", "PowerOfTwo", "Diffusion"]))
         if method == "PowerOfTwo" and fix_one_node:
             raise ValueError('For the PowerOfTwo method it "fix_one_node" is not implemented. '
                              'Use "PauliBasis" or "Diffusion" instead.')
-        self.k_cuts = k_cuts
-        self.method = method
-        self.color_encoding = color_encoding
-        super().__init__(G, int(np.ceil(np.log2(k_cuts))), fix_one_node)
-        self.construct_colors()
 
     def construct_colors(self):
         groups = _CLASSES.get((self.k_cuts, self.color_encoding))
