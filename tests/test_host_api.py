@@ -759,3 +759,18 @@ def test_compute_min_max_costs_uses_the_device_reduction_for_unconstrained_probl
     lo, hi = po.computeMinMaxCosts()
     feas = [-po.cost(format(x, "06b")) for x in range(64) if po.isFeasible(format(x, "06b"))]
     assert (lo, hi) == (min(feas), max(feas)) and len(feas) == 15
+
+
+def test_orbits_printed_by_the_reference_notebook():
+    """examples/MaxCut/MixerComparison.ipynb cell 8 output (house graph): the node orbits of XOrbit and the edge orbits of
+    MaxCutOrbit, in the order and orientation the reference printed them; cell 11: parameter counts per layer."""
+    G = nx.house_graph()
+    orbit_problem, orbit_mixer = problems.MaxCutOrbit(G), mixers.XOrbit(G)
+    assert [list(o) for o in orbit_mixer.node_orbits] == [[0, 1], [2], [3, 4]]
+    assert [[tuple(e) for e in o] for o in orbit_problem.edge_orbits] == [[(0, 1)], [(0, 4), (1, 3)], [(4, 3)], [(4, 2), (3, 2)]]
+    counts = []
+    for pr, mx in ((problems.MaxCut(G), mixers.X()), (problems.MaxCutFree(G), mixers.XMultiAngle()), (orbit_problem, orbit_mixer)):
+        q, _ = make(pr, mixer=mx)
+        q.createParameterizedCircuit(1)
+        counts.append((q.n_gamma, q.n_beta))
+    assert counts == [(1, 1), (6, 5), (4, 3)]       # "Vanilla 1/1, Free 6 (1 per edge)/5 (1 per node), Orbit 4/3"
