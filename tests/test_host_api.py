@@ -662,6 +662,10 @@ def test_exactcover_tail_assignment_notebook():
     assert list(ec.computeMinMaxCosts()) == run["printed_minmax"]
     best = "".join(str(b) for b in run["best"])
     assert ec.isFeasible(best) and -ec.cost(best) == run["printed_minmax"][0]
+    import itertools
+    # cell 4 output of the notebook: "solutions: 000011 7.0 / 001100 10.0 / 110000 6.0" (all feasible strings, with -cost)
+    feasible = {s: -ec.cost(s) for s in ("".join(b) for b in itertools.product("01", repeat=6)) if ec.isFeasible(s)}
+    assert feasible == {"000011": 7.0, "001100": 10.0, "110000": 6.0}
     q, fake = make(ec, interpolate=False)
     q.sample_cost_landscape(angles={"gamma": [0, 6 * np.pi, 60], "beta": [0, 2 * np.pi, 20]})
     assert q.Exp_sampled_p1.shape == (20, 60)
