@@ -160,6 +160,27 @@ def notebook_runs():
     out["runs"]["ExactCover_6_3"] = {"columns": cols, "weights": weights, "best": [int(x) for x in rows[R].split(",")],
                                      "printed_minmax": [6.0, 10.0], "order": ["plus_x_gridsearch"],
                                      "cost": log_lines("examples/ExactCover/ExactCover 6 3.ipynb", 6)}
+    # PortfolioOptimization/PortOpt.ipynb: 12 assets, budget 4, gamma_scale 50.  The asset data come from qiskit_finance's
+    # RandomDataProvider ([3p], not installable) seeded from data/qiskit_finance_seeds.npz (a DATA file); its published
+    # algorithm -- per ticker cumsum(default_rng(seed).standard_normal(days)) + integers(1, 101), period returns
+    # x[t+1]/x[t] - 1, their mean vector and np.cov -- is restated here and CHECKED against the exp_return vector the
+    # notebook printed (cell 4 output, 9 digits).  Cell 9 printed the brute-force optimum, cell 20 computeMinMaxCosts(),
+    # cell 19 the optimize log of six runs: cvar in (0.1, 1) x (penalty + X, XY ring [interpolate=False], Grover).
+    seeds = np.load(os.path.join(REF, "examples/PortfolioOptimization/data/qiskit_finance_seeds.npz"))
+    n_assets, days = 12, 101
+    rng = np.random.default_rng(int(seeds[str(n_assets)][132]))
+    series = np.array([np.maximum(np.cumsum(rng.standard_normal(days)) + rng.integers(1, 101), 0) for _ in range(n_assets)])
+    returns = series[:, 1:] / series[:, :-1] - 1
+    printed = [2.51714041e-03, -6.60209726e-04, -1.70699934e-03, 7.30592102e-04, -7.68369448e-05, 8.56893545e-04,
+               -6.84333999e-03, -1.94220999e-03, 4.44702531e-03, -4.76239370e-04, -3.90803496e-03, 9.03679818e-04]
+    assert np.abs(returns.mean(axis=1) - np.array(printed)).max() < 5e-12, "RandomDataProvider restatement is off"
+    out["runs"]["PortOpt"] = {
+        "n_assets": n_assets, "budget": 4, "gamma_scale": 50, "penalty_of_the_penalty_runs": 200,
+        "exp_return": returns.mean(axis=1).tolist(), "cov_matrix": np.cov(returns).tolist(),
+        "exp_return_printed": printed, "best_solution_printed": "100001001001",
+        "printed_minmax": [-0.29191609262381646, 0.9214724310800932],
+        "order": ["penalty cvar=0.1", "xy_ring cvar=0.1", "grover cvar=0.1", "penalty cvar=1", "xy_ring cvar=1", "grover cvar=1"],
+        "cost": log_lines("examples/PortfolioOptimization/PortOpt.ipynb", 19)}
     with open(os.path.join(OUT, "notebook_runs.json"), "w") as f:
         json.dump(out, f, indent=1)
 

@@ -778,3 +778,48 @@ def test_orbits_printed_by_the_reference_notebook():
         q.createParameterizedCircuit(1)
         counts.append((q.n_gamma, q.n_beta))
     assert counts == [(1, 1), (6, 5), (4, 3)]       # "Vanilla 1/1, Free 6 (1 per edge)/5 (1 per node), Orbit 4/3"
+
+
+def _portopt(run, penalty=None):
+    kw = dict(risk=0.5 * run["gamma_scale"], budget=run["budget"], cov_matrix=np.array(run["cov_matrix"]),
+              exp_return=np.array(run["exp_return"]) * run["gamma_scale"])
+    if penalty:
+        kw["penalty"] = penalty
+    return problems.PortfolioOptimization(**kw)
+
+
+def test_portfolio_notebook_known_answers_and_aer_energies():
+    """examples/PortfolioOptimization/PortOpt.ipynb (12 assets, budget 4; data rebuilt from the notebook's seed file and
+    checked against the exp_return it printed, tests/golden/make_golden.py).  Known answers: cell 20
+    computeMinMaxCosts() = (-0.29191609262381646, 0.9214724310800932), cell 9 brute-force optimum 100001001001.  Aer's
+    cost(depth 1) of the cvar = 1 runs -- penalty + X 378.09, Dicke + XY ring -0.04414, Dicke + Grover 0.03270 -- against
+    the same control flow on exact energies, within shot noise; the CVaR(0.1) runs of X and Grover within the spread of a
+    102-sample tail estimate."""
+    import json
+    import os
+
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "notebook_runs.json")) as f:
+        run = json.load(f)["runs"]["PortOpt"]
+    po = _portopt(run)
+    lo, hi = po.computeMinMaxCosts()
+    assert lo == pytest.approx(run["printed_minmax"][0], rel=1e-13) and hi == pytest.approx(run["printed_minmax"][1], rel=1e-13)
+    assert po.brute_force_solve() == run["best_solution_printed"]
+    aer = dict(zip(run["order"], run["cost"]))
+    grid = {"gamma": [0, 2 * np.pi, 10], "beta": [0, 2 * np.pi, 10]}
+    k = run["budget"]
+
+    def depth1(problem, cvar, **kw):
+        q, _ = make(problem, cvar=cvar, **kw)
+        q.optimize(depth=1, angles=grid)
+        return q.get_Exp(1), np.sqrt(q.get_Var(1) / 1024.0)
+
+    got, sigma = depth1(_portopt(run), 1, mixer=mixers.XY(case="ring"), init=initialstates.Dicke(k), interpolate=False)
+    assert abs(got - aer["xy_ring cvar=1"][0]) < 4 * sigma, (got, aer["xy_ring cvar=1"][0], sigma)      # -0.0373 vs -0.0441
+    got, sigma = depth1(_portopt(run), 1, mixer=mixers.Grover(initialstates.Dicke(k)), init=initialstates.Dicke(k))
+    assert abs(got - aer["grover cvar=1"][0]) < 4 * sigma, (got, aer["grover cvar=1"][0], sigma)        # 0.0413 vs 0.0327
+    got, sigma = depth1(_portopt(run, run["penalty_of_the_penalty_runs"]), 1)
+    assert abs(got - aer["penalty cvar=1"][0]) < 4 * sigma, (got, aer["penalty cvar=1"][0], sigma)      # 388.0 vs 378.1
+    got, _ = depth1(_portopt(run), 0.1, mixer=mixers.Grover(initialstates.Dicke(k)), init=initialstates.Dicke(k))
+    assert abs(got - aer["grover cvar=0.1"][0]) < 0.02, (got, aer["grover cvar=0.1"][0])                # -0.2249 vs -0.2333
+    got, _ = depth1(_portopt(run, run["penalty_of_the_penalty_runs"]), 0.1)
+    assert abs(got - aer["penalty cvar=0.1"][0]) < 0.02, (got, aer["penalty cvar=0.1"][0])              # -0.2287 vs -0.2357
