@@ -423,3 +423,54 @@ def test_notebook_graphs_known_answers_and_aer_energies():
     opt, sigma = _p1_optimum(n, diag, [(0.7, 0.35)])
     assert abs(run["cost"][0][0] - opt) < 4 * sigma, (run["cost"][0][0], opt, sigma)   # -19.918 vs -19.776, sigma 0.063
     assert run["cost"][1][0] < run["cost"][0][0]                               # CVaR(0.1) lies below the mean
+
+
+def test_xy_gate_matrix_agrees_with_the_gate_decomposition_of_xxplusyy():
+    """[3p] qiskit's XXPlusYYGate is not importable here; two independent recollections of it are checked against each other:
+    its documented matrix (cos(theta/2) on the diagonal, -i sin(theta/2) e^{-+i beta} off the diagonal of span{|01>, |10>})
+    as used by oracle.apply_xy_gate and utils/gatesim.py, and its definition in elementary gates
+    (RZ(beta) q0; RZ(-pi/2), SX, RZ(pi/2) q1; S q0; CX(q1 -> q0); RY(-theta/2) q1; RY(-theta/2) q0; CX(q1 -> q0); Sdg q0;
+    RZ(-pi/2), SXdg, RZ(pi/2) q1; RZ(-beta) q0).  Multiplying the definition out gives exactly that matrix, sign of the
+    hopping term included -- which is what the open question in DESIGN.md section 4 (PortOpt CVaR run) turns on."""
+    from qaoa_b200.utils.gatesim import SmallState
+
+    eye = np.eye(2, dtype=complex)
+
+    def rz(a):
+        return np.diag([np.exp(-0.5j * a), np.exp(0.5j * a)])
+
+    def ry(a):
+        return np.array([[math.cos(a / 2), -math.sin(a / 2)], [math.sin(a / 2), math.cos(a / 2)]], dtype=complex)
+
+    sx = 0.5 * np.array([[1 + 1j, 1 - 1j], [1 - 1j, 1 + 1j]])
+    s_gate = np.diag([1, 1j])
+
+    def on(q, g):                        # little endian: q0 is the least significant bit
+        return np.kron(g, eye) if q == 1 else np.kron(eye, g)
+
+    cx10 = np.zeros((4, 4), dtype=complex)          # control q1, target q0
+    for x in range(4):
+        cx10[x ^ ((x >> 1) & 1), x] = 1
+    for theta, beta in ((0.7, 0.0), (2.9, 0.0), (-1.1, 0.0), (0.7, np.pi / 2), (1.3, -0.4)):
+        seq = [on(0, rz(beta)), on(1, rz(-np.pi / 2)), on(1, sx), on(1, rz(np.pi / 2)), on(0, s_gate), cx10,
+               on(1, ry(-theta / 2)), on(0, ry(-theta / 2)), cx10, on(0, s_gate.conj().T), on(1, rz(-np.pi / 2)),
+               on(1, sx.conj().T), on(1, rz(np.pi / 2)), on(0, rz(-beta))]
+        U = np.eye(4, dtype=complex)
+        for g in seq:
+            U = g @ U
+        U = U / U[0, 0]
+        c, s = math.cos(theta / 2), math.sin(theta / 2)
+        want = np.array([[1, 0, 0, 0], [0, c, -1j * s * np.exp(-1j * beta), 0], [0, -1j * s * np.exp(1j * beta), c, 0],
+                         [0, 0, 0, 1]])
+        assert np.allclose(U, want, atol=1e-12), (theta, beta)
+        for start in range(4):            # the host gate simulator (LessThanK / Dicke1_2 states) applies the same matrix
+            st = SmallState(2)
+            st.v[:] = 0
+            st.v[start] = 1
+            st.xx_plus_yy(theta, beta, 0, 1)
+            assert np.allclose(st.v, want[:, start], atol=1e-12)
+        if beta == 0.0:                   # the oracle's XY mixer gate: XXPlusYYGate(0.5 * beta_mixer)
+            for start in range(4):
+                psi = np.zeros(4, dtype=complex)
+                psi[start] = 1
+                assert np.allclose(orc.apply_xy_gate(psi, 0, 1, 2 * theta), want[:, start], atol=1e-12)
