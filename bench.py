@@ -10,15 +10,16 @@ statevector.  One step = one energy evaluation <gamma,beta|H_P|gamma,beta>.
 N = 1 : n = 32 on one B200.  MaxCut + X mixer + |+> keeps psi(x) = psi(~x), so the engine stores the symmetric
         half of the register (2^31 amplitudes = 16 GiB, far larger than the 126 MB L2: nothing to flush) and pairs
         every element with its mirror image for the top qubit (tile_kernel.cuh "symmetric registers"); the same
-        evaluation on the full 32 GiB register (option symmetric=0) is reported under "full_register".
-N > 1 : launched under torchrun, one rank per GPU; WEAK scaling: every rank evaluates its own n = 32
-        register (independent units: the landscape / optimizer workloads of the reference shard over
-        evaluations with no data-path collective); value = step time / N.  The line also carries
-        "sharded": ONE register of n = 32 + log2(N) qubits sharded on its top qubits (32 GiB per GPU),
-        mixer gates on the global qubits as cross passes over NVLink peer memory, energy by a scalar
-        all-reduce -- the path with a real exchange step.
---impl reference : times the CPU restatement of the reference path (oracle/c/qaoa_ref.c, OpenMP over
-        the host cores) on a bounded sample (smaller n) and scales it to the workload.
+        evaluation on the full 32 GiB register (option symmetric=0) is reported under "full_register".  Side legs:
+        "config4" (BASELINE config 4, n=30 p=3: Grover+Dicke, multi-angle X, XY), "landscape" (config 2), "optimize"
+        (config 3 through the public API), "cpu_baseline".
+N > 1 : launched under torchrun, one rank per GPU; STRONG scaling of the SAME workload: the one n = 32, p = 5 register
+        sharded on its top log2(N) qubits over the N GPUs (qaoa_b200/sharded.py): mixer gates on the global qubits as
+        cross passes over NVLink peer memory, energy by a scalar all-reduce; value = ms per evaluation of that register,
+        max over ranks.  "parity" compares the sharded path with the C oracle (n = 28) in the same job; "config5" is
+        BASELINE config 5 (n = 36, p = 3 on 4 / 8 GPUs; n = 34 on 2) with the closed-form p = 1 energy as its check.
+--impl reference : times the CPU restatement of the reference path (oracle/c/qaoa_ref.c: OpenMP over the host cores,
+        cache-blocked gate groups like a gate-fusing simulator) on a bounded sample (smaller n), scaled to the workload.
 """
 import argparse
 import json

@@ -1641,6 +1641,7 @@ double qaoa_get_counter(qaoa_engine_t* h, const char* key) {
   if (k == "prog_launches") return h->prog_launches;
   if (k == "bytes_alg") return h->bytes_alg;
   if (k == "diag_kind") return h->dinfo.kind;
+  if (k == "device") return h->device;
   if (k == "compact_size") return (double)h->n_compact;
   if (k == "symmetric_plans") { double s = 0; for (auto& kv : h->plans) s += kv.second.z2 ? 1 : 0; return s; }
   if (k == "state_bytes") return (double)h->state_bytes;

@@ -42,7 +42,7 @@ class B200Backend:
 
     name = "b200_statevector"
 
-    def __init__(self, device=0, dtype="complex128", sharded=False, split_batches=False, shard_symmetric=True):
+    def __init__(self, device=None, dtype="complex128", sharded=False, split_batches=False, shard_symmetric=True):
         """Multi-GPU modes (under ``torch.distributed``, one process per GPU, every rank driving the same
         QAOA object and seeing identical results):
         ``sharded=True``: ONE register split on its top qubits over all ranks (qaoa_b200/sharded.py); with
@@ -50,6 +50,8 @@ class B200Backend:
         the half register with the top qubit = 0 (same results, half the memory, HBM and NVLink traffic);
         ``split_batches=True``: every rank holds a full replica and batched evaluations (landscape grids, layer
         grid searches) are dealt out round-robin, the results gathered -- no data-path collective."""
+        # None: resolved when the engine is built -- LOCAL_RANK under torchrun, else torch's current device, else 0
+        # (so that sharded=True / split_batches=True put every rank on its OWN GPU without the caller passing it)
         self.device = device
         self.dtype = dtype
         self.sharded = sharded
@@ -279,12 +281,18 @@ class QAOA:
                 self.mixer.lower_mixer(None, trotter=self.number_trottersteps_mixer)        # raises NotImplementedError
             if state_cls.state_descriptor is InitialState.state_descriptor and state_cls.lower_initial is InitialState.lower_initial:
                 self.initialstate.state_descriptor()                                        # raises NotImplementedError
+            device = getattr(self.backend, "device", None)
+            if device is None:
+                from qaoa_b200.sharded import default_device
+                device = default_device()
             if getattr(self.backend, "sharded", False):
                 from qaoa_b200.sharded import DistShardedEngine
-                eng = DistShardedEngine(self.problem.N_qubits, dtype=self.backend.dtype, device=self.backend.device,
+                if hasattr(self.problem, "term_of_edge") and self.problem.get_num_parameters() != 1:
+                    _reject("per-term gammas (MaxCutFree / MaxCutOrbit) on a sharded register")
+                eng = DistShardedEngine(self.problem.N_qubits, dtype=self.backend.dtype, device=device,
                                         symmetric=self._shard_symmetric())
             else:
-                eng = Engine(self.problem.N_qubits, dtype=self.backend.dtype, device=self.backend.device)
+                eng = Engine(self.problem.N_qubits, dtype=self.backend.dtype, device=device)
             self.problem.lower_cost(eng)
             self.initialstate.lower_initial(eng)
             self.mixer.lower_mixer(eng, trotter=self.number_trottersteps_mixer)

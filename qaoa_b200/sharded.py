@@ -22,6 +22,24 @@ import numpy as np
 from qaoa_b200 import engine as _eng
 
 
+def default_device():
+    """The CUDA device of this process: LOCAL_RANK under a launcher (torchrun exports it), else torch's current device.
+    One process per GPU -- ranks of one node must never share a device (all shards would sit in one GPU's HBM and the
+    'NVLink' cross passes would never leave it)."""
+    import os
+
+    lr = os.environ.get("LOCAL_RANK")
+    if lr is not None:
+        return int(lr)
+    try:
+        import torch
+        if torch.cuda.is_available():
+            return int(torch.cuda.current_device())
+    except Exception:   # noqa: BLE001
+        pass
+    return 0
+
+
 def combine_partials(parts):
     """parts: (world, 5) rows {sum p, sum p c, sum p c^2, min c, max c} -> (E, E2, min, max, norm)."""
     parts = np.asarray(parts, dtype=np.float64).reshape(-1, 5)
@@ -38,6 +56,8 @@ class _ShardedSurface:
     """Engine-like methods shared by the two drivers (fan a call out to the local engine(s))."""
 
     n_beta = 1
+    n_gamma = 1     # one gamma per layer: per-term gammas (MaxCutFree / MaxCutOrbit) are single-GPU only
+    n_init = 0      # no parameterised initial states on sharded registers
 
     def _engines(self):
         raise NotImplementedError
@@ -45,22 +65,38 @@ class _ShardedSurface:
     def _diag_changed(self):
         raise NotImplementedError
 
+    def _before_diag_change(self):
+        """Called before the engines free their cost diagonal (a peer may still have it mapped)."""
+
     def set_option(self, key, value):
         for e in self._engines():
             e.set_option(key, value)
 
     def set_cost_maxkcut(self, *a, **k):
+        self._before_diag_change()
         for e in self._engines():
             e.set_cost_maxkcut(*a, **k)
         self._diag_changed()
 
     def set_cost_qubo(self, *a, **k):
+        self._before_diag_change()
         for e in self._engines():
             e.set_cost_qubo(*a, **k)
         self._diag_changed()
 
     def set_cost_diagonal(self, diag):
-        raise _eng.EngineError("sharded engine: host-provided cost diagonals are not supported")
+        raise NotImplementedError("sharded engine: host-provided cost diagonals are not supported")
+
+    def set_cost_maxkcut_terms(self, *a, **k):
+        raise NotImplementedError("sharded engine: per-term gammas (MaxCutFree / MaxCutOrbit) are single-GPU only")
+
+    def cost_minmax(self):
+        """min / max of the cost over ALL basis states (every shard's device reduction, combined)."""
+        lo, hi = zip(*[e.cost_minmax() for e in self._engines()])
+        return self._combine_minmax(min(lo), max(hi))
+
+    def _combine_minmax(self, lo, hi):
+        return lo, hi
 
     def set_mixer(self, kind, *a, **k):
         for e in self._engines():
@@ -137,13 +173,13 @@ class DistShardedEngine(_ShardedSurface):
         self.group = group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         if device is None and engine_factory is None:
-            import torch
-            device = torch.cuda.current_device()
+            device = default_device()
         make = engine_factory or (lambda r, w: _eng.Engine(n_qubits, dtype=dtype, device=device, rank=r, world=w,
                                                            shard_symmetric=symmetric))
         self.n_qubits = int(n_qubits)
         self.eng = make(self.rank, self.world)
         self.barriers = 0
+        self._diag_exchanged = False
         self._exchange(0)
 
     def _engines(self):
@@ -162,8 +198,30 @@ class DistShardedEngine(_ShardedSurface):
         self.eng.shard_sync()
         self._barrier()
 
+    def _before_diag_change(self):
+        """Replacing the cost function is COLLECTIVE: the old diagonal is IPC-mapped by the peers, and an exporter must
+        not free memory a peer still maps -- every rank unmaps first (barrier, close, barrier), then the engines free."""
+        if self._diag_exchanged:
+            self.eng.shard_sync()
+            self._barrier()
+            self.eng.shard_close_peers()      # unmaps state and diagonal peers
+            self._barrier()
+            self._diag_exchanged = False
+            self._exchange(0)                 # the state buffers are unchanged: map them again
+
     def _diag_changed(self):
         self._exchange(1)
+        self._diag_exchanged = True
+
+    def _combine_minmax(self, lo, hi):
+        import torch
+
+        dist = self._dist
+        dev = "cuda" if dist.get_backend(self.group) == "nccl" else "cpu"
+        t = torch.tensor([-lo, hi], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        t = t.cpu()
+        return -float(t[0]), float(t[1])
 
     def read_cost_diagonal(self):
         return self.eng.read_cost_diagonal()

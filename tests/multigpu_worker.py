@@ -1,0 +1,111 @@
+"""Worker of tests/test_gpu_multigpu.py: one process per GPU under torchrun (NCCL).  Every rank drives
+DistShardedEngine -- the CUDA-IPC / torch.distributed path that bench.py's sharded leg uses -- for the FULL sharded
+register and for the sharded SYMMETRIC register; rank 0 compares each energy with the C oracle (complex128 reference,
+tolerance 1e-4 relative for the complex64 engine, 1e-9 for complex128) and with the closed-form p = 1 MaxCut energy, and
+checks that every rank received identical results.  Exit code 0 = all checks passed on every rank."""
+import argparse
+import json
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+for p in (HERE, ROOT):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+
+def closed_form_p1(n, edges, gamma, beta):
+    """<cost> of p = 1 MaxCut QAOA on any unweighted graph (reference sign conventions)."""
+    adj = [set() for _ in range(n)]
+    for u, v, _ in edges:
+        adj[u].add(v)
+        adj[v].add(u)
+    tot = 0.0
+    for u, v, _ in edges:
+        d, e = len(adj[u]) - 1, len(adj[v]) - 1
+        f = len(adj[u] & adj[v])
+        tot += 0.5 + 0.25 * np.sin(4 * beta) * np.sin(gamma) * (np.cos(gamma) ** d + np.cos(gamma) ** e) \
+            - 0.25 * np.sin(2 * beta) ** 2 * np.cos(gamma) ** (d + e - 2 * f) * (1 - np.cos(2 * gamma) ** f)
+    return tot
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n", type=int, default=26)
+    ap.add_argument("--dtype", default="complex64")
+    args = ap.parse_args()
+
+    import torch
+    import torch.distributed as dist
+
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    assert torch.cuda.device_count() >= world, "one GPU per rank"
+
+    import parity_helpers as H
+    from qaoa_b200.sharded import DistShardedEngine
+
+    n, dtype = args.n, args.dtype
+    tol = 1e-4 if dtype == "complex64" else 1e-9
+    edges, colors, table = H.regular_maxcut(n)
+    lut, _ = H.lut_from_table(table, 1)
+    rng = np.random.default_rng(77)
+    cases = []
+    for p in (1, 2, 3):
+        ang = rng.uniform(0, 2 * np.pi, size=2 * p)
+        cases.append(ang)
+    refs = None
+    if rank == 0:
+        from oracle import c_oracle
+        c_oracle.build()
+        c_oracle.use_all_cores()
+        d8 = c_oracle.maxcut_diag_u8(n, edges)
+        refs = [c_oracle.run(n, d8, ang, "complex128", blocked=True) for ang in cases]
+    report = {"n": n, "world": world, "dtype": dtype, "checks": []}
+    ok = True
+    variants = [False] + ([True] if dtype == "complex64" and n % 2 == 0 else [])
+    for sym in variants:
+        E = DistShardedEngine(n, dtype=dtype, device=local_rank, symmetric=sym)
+        assert int(E.eng.counter("device")) == local_rank, "every rank must open its own GPU"
+        E.set_cost_maxkcut(n, edges, 1, lut)
+        for i, ang in enumerate(cases):
+            got = E.energy(ang)
+            # identical on every rank
+            t = torch.tensor(got, dtype=torch.float64, device="cuda")
+            lo, hi = t.clone(), t.clone()
+            dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+            dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+            same = bool(torch.equal(lo, hi))
+            entry = {"symmetric": sym, "p": len(ang) // 2, "energy": float(got[0]), "same_on_all_ranks": same}
+            if rank == 0:
+                ref = refs[i]
+                entry["oracle"] = float(ref[0])
+                entry["rel_err"] = abs(got[0] - ref[0]) / abs(ref[0])
+                good = entry["rel_err"] < tol and abs(got[1] - ref[1]) < 2 * tol * abs(ref[1]) and \
+                    got[2] == ref[2] and got[3] == ref[3] and abs(got[4] - 1) < (1e-4 if dtype == "complex64" else 1e-11)
+                if len(ang) == 2:
+                    cf = closed_form_p1(n, edges, ang[0], ang[1])
+                    entry["closed_form_rel_err"] = abs(got[0] - cf) / abs(cf)
+                    good = good and entry["closed_form_rel_err"] < tol
+                entry["ok"] = bool(good and same)
+                ok = ok and entry["ok"]
+            else:
+                ok = ok and same
+            report["checks"].append(entry)
+        E.close()
+    flag = torch.tensor([0 if ok else 1], dtype=torch.int32, device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        report["ok"] = int(flag[0]) == 0
+        print("MULTIGPU_REPORT " + json.dumps(report), flush=True)
+    dist.destroy_process_group()
+    sys.exit(int(flag[0]))
+
+
+if __name__ == "__main__":
+    main()

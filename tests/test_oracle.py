@@ -11,6 +11,7 @@ import numpy as np
 import pytest
 
 from oracle import qaoa_oracle as orc
+import parity_helpers as H
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
@@ -474,3 +475,80 @@ def test_xy_gate_matrix_agrees_with_the_gate_decomposition_of_xxplusyy():
                 psi = np.zeros(4, dtype=complex)
                 psi[start] = 1
                 assert np.allclose(orc.apply_xy_gate(psi, 0, 1, 2 * theta), want[:, start], atol=1e-12)
+
+
+# ---- round 2: the general C oracle entry (cache-blocked sweeps, u8 diagonal, Grover / Dicke / XY) is pinned against
+# ---- the numpy oracle at sizes numpy handles, so that it can stand in as the checker at n = 26 ... 32
+def _c_vs_numpy(n, diag, ang, rtol=1e-10, **kw):
+    from oracle import c_oracle
+
+    spec_kw = {}
+    mixer = kw.get("mixer", "x")
+    if mixer == "xmulti":
+        spec_kw["mixer"] = ("xmulti",)
+    elif mixer == "grover":
+        k = kw["sub"][1]
+        spec_kw["mixer"] = ("grover", orc.dicke_state(n, k) if kw["sub"][0] == "dicke" else orc.plus_state(n))
+    elif mixer == "xy":
+        spec_kw["mixer"] = ("xy", kw["pairs"])
+        spec_kw["trotter"] = kw.get("trotter", 1)
+    init = kw.get("init", ("plus", 0))
+    if init[0] == "dicke":
+        spec_kw["init"] = orc.dicke_state(n, init[1])
+    ref = orc.energy(orc.Spec(n, np.asarray(diag, dtype=float), **spec_kw), ang)
+    got = c_oracle.run(n, diag, ang, "complex128", **kw)
+    for g, r in zip(got[:4], ref):
+        assert abs(g - r) <= rtol * max(1.0, abs(r)), (kw, got, ref)
+    assert abs(got[4] - 1.0) < 1e-12
+    got32 = c_oracle.run(n, diag, ang, "complex64", **kw)
+    assert abs(got32[0] - ref[0]) <= 1e-5 * max(1.0, abs(ref[0])), (kw, got32, ref)
+    return got
+
+
+@pytest.mark.parametrize("n", [9, 14, 15, 17])
+def test_c_oracle_blocked_and_plain_sweeps_agree_with_numpy(n):
+    """n < 14: one block; n = 15, 17: one / one high group of 1 and 3 qubits -- every branch of x_layer_blocked."""
+    from oracle import c_oracle
+
+    edges, colors, table = H.regular_maxcut(n)
+    d = H.maxcut_diag(n, edges, colors, table).astype(float)
+    d8 = c_oracle.maxcut_diag_u8(n, edges)
+    assert np.array_equal(d8.astype(float), d)
+    rng = np.random.default_rng(n)
+    ang = rng.uniform(0, 2 * np.pi, 6)
+    a = _c_vs_numpy(n, d, ang, blocked=True)
+    b = _c_vs_numpy(n, d, ang, blocked=False)
+    c = _c_vs_numpy(n, d8, ang, blocked=True)
+    assert np.allclose(a, b, rtol=1e-12) and np.allclose(a, c, rtol=1e-12)
+    angm = rng.uniform(0, 2 * np.pi, 2 * (1 + n))
+    _c_vs_numpy(n, d8, angm, mixer="xmulti", blocked=True)
+    _c_vs_numpy(n, d, angm, mixer="xmulti", blocked=False)
+
+
+def test_c_oracle_high_groups_of_five_qubits():
+    """n = 20, 21: six / seven high qubits = two groups (3 + 3, 4 + 3) above the 14-qubit block"""
+    from oracle import c_oracle
+
+    for n in (20, 21):
+        edges, colors, table = H.regular_maxcut(n)
+        d8 = c_oracle.maxcut_diag_u8(n, edges)
+        ang = np.random.default_rng(n).uniform(0, 2 * np.pi, 4)
+        a = c_oracle.run(n, d8, ang, "complex128", blocked=True)
+        b = c_oracle.run(n, d8, ang, "complex128", blocked=False)
+        assert np.allclose(a, b, rtol=1e-12, atol=1e-12), (n, a, b)
+
+
+def test_c_oracle_grover_dicke_and_xy_match_numpy_oracle():
+    n, k = 12, 4
+    Q, c, b = H.random_qubo(n)
+    from oracle import c_oracle
+
+    d = c_oracle.qubo_diag(Q, c, b)
+    assert np.allclose(d, orc.qubo_diag(Q, c, b), rtol=0, atol=1e-12)
+    df = c_oracle.qubo_diag(Q, c, b, fast=True)
+    assert np.allclose(df, d, rtol=0, atol=1e-11)
+    ang = np.random.default_rng(5).uniform(0, 2 * np.pi, 6)
+    _c_vs_numpy(n, d, ang, mixer="grover", init=("dicke", k), sub=("dicke", k))
+    _c_vs_numpy(n, d, ang, mixer="grover", sub=("plus", 0))
+    _c_vs_numpy(n, d, ang, mixer="xy", init=("dicke", k), pairs=orc.xy_pairs(n, "ring"))
+    _c_vs_numpy(n, d, ang, mixer="xy", init=("dicke", k), pairs=orc.xy_pairs(n, "chain"), trotter=2)
