@@ -58,6 +58,35 @@ __device__ __forceinline__ double diag_decode(const DiagInfo& d, const void* p, 
   return ((const double*)p)[x];
 }
 
+// Phase angle of a raw diagonal integer k in 64-bit FIXED POINT: turns = frac(B + k * A), |error| <= 2^-33 turns for
+// k < 2^32 -- two integer multiply-adds instead of a double-precision multiply, round and subtract per amplitude.
+struct PhaseFx {
+  unsigned long long A, B;   // turns per diagonal unit / turns at k = 0, as 0.64 fixed-point fractions
+};
+__host__ __device__ inline unsigned long long turns_to_fx(double t) {
+  t -= floor(t);                                   // [0, 1)
+  const double v = t * 18446744073709551616.0;     // 2^64: exact scaling
+  return v >= 18446744073709549568.0 ? 0xfffffffffffff800ull : (unsigned long long)v;
+}
+__host__ __device__ inline PhaseFx make_phase_fx(double gamma, const DiagInfo& d) {
+  const double inv2pi = 0.15915494309189533576888;
+  PhaseFx f;
+  f.A = turns_to_fx(gamma * d.delta * inv2pi);
+  f.B = turns_to_fx(gamma * d.c0 * inv2pi);
+  return f;
+}
+__device__ __forceinline__ void phase_fx_sincos(const PhaseFx& f, unsigned k, float& s, float& c) {
+  const unsigned long long t = f.B + f.A * (unsigned long long)k;     // frac(turns) * 2^64, wraps mod 1 turn
+  const float half_turns = (float)(int)(t >> 32) * 4.656612873077392578125e-10f;   // 2 * signed turns in [-1, 1)
+  sincospif(half_turns, &s, &c);
+}
+
+// same reduction, hardware sine / cosine (MUFU; absolute error ~2^-21 on [-pi, pi]): the tile passes
+__device__ __forceinline__ void phase_fx_sincos_fast(const PhaseFx& f, unsigned k, float& s, float& c) {
+  const unsigned long long t = f.B + f.A * (unsigned long long)k;
+  __sincosf((float)(int)(t >> 32) * 1.4629180792671596e-9f, &s, &c);   // 2 pi / 2^32
+}
+
 // deterministic block reduction of NV doubles: sums for the first NS, then one min, one max
 // scratch must hold (blockDim.x/32) * 5 doubles.
 __device__ __forceinline__ void block_reduce5(double v[5], double* scratch) {

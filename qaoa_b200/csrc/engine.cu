@@ -1222,6 +1222,37 @@ void run_small_chunk(Engine* h, int p, const double* angles, int n_angles, int B
   h->last_z.assign(h->n, 0);
 }
 
+// launches grover_pass_c64_kernel<flags, diagonal kind, generator kind>; false if the combination is not instantiated
+template <int FLAGS>
+bool launch_grover_fast_f(Engine* h, int grid, float2* st, size_t Nv, const StateGen& g, double gamma, const void* diagv,
+                          double* part_dot, double* part_red) {
+#define QAOA_GF(DK, GK)                                                                                              \
+  if (h->dinfo.kind == DK && g.kind == GK) {                                                                         \
+    grover_pass_c64_kernel<FLAGS, DK, GK><<<grid, 256, 0, h->stream>>>(st, Nv, g, h->d_coefdot, gamma, diagv, h->dinfo, \
+                                                                       part_dot, part_red);                          \
+    return true;                                                                                                     \
+  }
+  QAOA_GF(DIAG_U8, INIT_PLUS) QAOA_GF(DIAG_U8, INIT_DICKE) QAOA_GF(DIAG_U8, INIT_UNIFORM)
+  QAOA_GF(DIAG_U32FX, INIT_PLUS) QAOA_GF(DIAG_U32FX, INIT_DICKE) QAOA_GF(DIAG_U32FX, INIT_UNIFORM)
+#undef QAOA_GF
+  return false;
+}
+bool launch_grover_fast(Engine* h, int grid, float2* st, size_t Nv, int flags, const StateGen& g, double gamma,
+                        const void* diagv, double* part_dot, double* part_red) {
+  switch (flags) {
+    case EW_INIT | EW_PHASE | EW_DOT | EW_STORE:
+      return launch_grover_fast_f<EW_INIT | EW_PHASE | EW_DOT | EW_STORE>(h, grid, st, Nv, g, gamma, diagv, part_dot, part_red);
+    case EW_AXPY | EW_PHASE | EW_DOT | EW_STORE:
+      return launch_grover_fast_f<EW_AXPY | EW_PHASE | EW_DOT | EW_STORE>(h, grid, st, Nv, g, gamma, diagv, part_dot, part_red);
+    case EW_AXPY | EW_REDUCE:
+      return launch_grover_fast_f<EW_AXPY | EW_REDUCE>(h, grid, st, Nv, g, gamma, diagv, part_dot, part_red);
+    case EW_AXPY | EW_REDUCE | EW_STORE:
+      return launch_grover_fast_f<EW_AXPY | EW_REDUCE | EW_STORE>(h, grid, st, Nv, g, gamma, diagv, part_dot, part_red);
+    default:
+      return false;
+  }
+}
+
 template <typename real>
 void run_elementwise_point(Engine* h, int p, const double* ang, double* d_out_point) {
   ensure_state(h, 1);
@@ -1247,9 +1278,15 @@ void run_elementwise_point(Engine* h, int p, const double* ang, double* d_out_po
   }
   const double sweep = (double)Nv * h->amp_bytes;
   const double dsz = (double)Nv * diag_value_bytes(h->dinfo.kind);
+  // complex64 Grover over its own initial state (|+>, |D^n_k>, compact): the specialised passes (kernels_misc.cuh)
+  const bool fast_grover = sizeof(real) == 4 && h->mixer == MIXER_GROVER && !h->force_generic && initv.kind == subv.kind &&
+      initv.k == subv.k && initv.amp == subv.amp &&
+      (initv.kind == INIT_PLUS || initv.kind == INIT_DICKE || initv.kind == INIT_UNIFORM) &&
+      (h->dinfo.kind == DIAG_U8 || h->dinfo.kind == DIAG_U32FX) && (Nv >= 2);
   auto ew = [&](int flags, double gamma) {
-    elementwise_pass_kernel<real><<<grid, threads, 0, h->stream>>>(st, Nv, flags, initv, subv, h->d_coefdot, gamma,
-                                                                  diagv, h->dinfo, part_dot, part_red);
+    if (!(fast_grover && launch_grover_fast(h, grid, (float2*)st, Nv, flags, initv, gamma, diagv, part_dot, part_red)))
+      elementwise_pass_kernel<real><<<grid, threads, 0, h->stream>>>(st, Nv, flags, initv, subv, h->d_coefdot, gamma,
+                                                                    diagv, h->dinfo, part_dot, part_red);
     CUDA_OK(cudaGetLastError());
     h->launches += 1;
     h->bytes_alg += ((flags & EW_INIT) ? 0 : sweep) + ((flags & EW_STORE) ? sweep : 0) +

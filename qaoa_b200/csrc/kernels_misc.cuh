@@ -555,6 +555,130 @@ elementwise_pass_kernel(real* __restrict__ st, size_t N, int flags, StateGen ini
   }
 }
 
+// ---- complex64 Grover passes, specialised (flags, diagonal kind, |s> generator as template parameters) ----------------
+// The generic kernel above spends its issue slots on double-precision range reduction, per-element kind switches and
+// 8-byte accesses (ncu: 24-36 % of the HBM rate at n = 30).  Here: 16-byte accesses (two amplitudes per thread and
+// access, four accesses in flight), the phase angle reduced in 64-bit FIXED POINT (turns = frac(B + k * A) from the raw
+// diagonal integer k: two integer multiply-adds, |error| <= 2^-33 turns) followed by the single-precision sincospif, the
+// dot product <s|v> accumulated as (-i)^popc(x) v in floats per batch of eight elements and in doubles across batches,
+// |s> = amp * i^popc(x) [popc == k] applied by sign / swap instead of a complex multiply.
+template <int GK>
+__device__ __forceinline__ bool gk_support(const StateGen& g, int pc) {
+  return GK == INIT_DICKE ? pc == g.k : true;
+}
+
+// FLAGS: compile-time EwFlags; DK: DIAG_U8 / DIAG_U32FX; GK: INIT_PLUS / INIT_DICKE / INIT_UNIFORM (|s> AND the initial
+// state: the Grover mixers of the reference are built over their own initial state, grover_mixer.py:43-82).
+template <int FLAGS, int DK, int GK>
+__global__ void __launch_bounds__(256)
+grover_pass_c64_kernel(float2* __restrict__ st, size_t N, StateGen gen, const double* __restrict__ coefdot, double gamma,
+                       const void* __restrict__ diag, DiagInfo info, double* __restrict__ part_dot,
+                       double* __restrict__ part_red) {
+  __shared__ double red[8 * 5];
+  const float amp = (float)gen.amp;
+  float far = 0.f, fai = 0.f;                        // coefdot * amp
+  if (FLAGS & EW_AXPY) { far = (float)(coefdot[0] * gen.amp); fai = (float)(coefdot[1] * gen.amp); }
+  const PhaseFx fx = make_phase_fx(gamma, info);
+  double dv[5] = {0, 0, 0, 1e300, -1e300};
+  double rv[5] = {0, 0, 0, 1e300, -1e300};
+  constexpr int U = 4;
+  const size_t npairs = N >> 1;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  float4* st4 = reinterpret_cast<float4*>(st);
+
+  auto one = [&](size_t x, float& re, float& im, unsigned k, float& dr, float& di) {
+    const int pc = GK == INIT_UNIFORM ? 0 : __popcll((unsigned long long)x);
+    const bool on = gk_support<GK>(gen, pc);
+    if (FLAGS & EW_INIT) {
+      re = on ? amp : 0.f;
+      im = 0.f;
+      if (GK != INIT_UNIFORM) mul_i_pow(re, im, pc);
+    }
+    if ((FLAGS & EW_AXPY) && on) {
+      float ar = far, ai = fai;
+      if (GK != INIT_UNIFORM) mul_i_pow(ar, ai, pc);
+      re += ar;
+      im += ai;
+    }
+    if (FLAGS & EW_PHASE) {
+      float s, c;
+      phase_fx_sincos(fx, k, s, c);
+      const float r2 = re * c - im * s;
+      im = re * s + im * c;
+      re = r2;
+    }
+    if ((FLAGS & EW_DOT) && on) {                    // conj(i^pc) v = (-i)^pc v
+      float tr = re, ti = im;
+      if (GK != INIT_UNIFORM) mul_i_pow(tr, ti, -pc);
+      dr += tr;
+      di += ti;
+    }
+    if (FLAGS & EW_REDUCE) {
+      const double c = info.c0 + info.delta * (double)k;
+      const double pr = (double)re * re + (double)im * im;
+      rv[0] += pr;
+      rv[1] += pr * c;
+      rv[2] += pr * c * c;
+      if (pr > 0.0) { rv[3] = fmin(rv[3], c); rv[4] = fmax(rv[4], c); }
+    }
+  };
+  auto diag_pair = [&](size_t i, unsigned& k0, unsigned& k1) {
+    if (DK == DIAG_U8) {
+      const unsigned short w = __ldg(reinterpret_cast<const unsigned short*>(diag) + i);
+      k0 = w & 0xffu; k1 = w >> 8;
+    } else {
+      const uint2 w = __ldg(reinterpret_cast<const uint2*>(diag) + i);
+      k0 = w.x; k1 = w.y;
+    }
+  };
+
+  for (size_t i0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i0 < npairs; i0 += U * stride) {
+    float4 v[U];
+    unsigned k0[U], k1[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const size_t i = i0 + u * stride;
+      if (i < npairs) {
+        if (!(FLAGS & EW_INIT)) v[u] = st4[i];
+        if (FLAGS & (EW_PHASE | EW_REDUCE)) diag_pair(i, k0[u], k1[u]);
+      }
+    }
+    float dr = 0.f, di = 0.f;
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const size_t i = i0 + u * stride;
+      if (i >= npairs) break;
+      one(2 * i, v[u].x, v[u].y, k0[u], dr, di);
+      one(2 * i + 1, v[u].z, v[u].w, k1[u], dr, di);
+      if (FLAGS & EW_STORE) st4[i] = v[u];
+    }
+    if (FLAGS & EW_DOT) { dv[0] += (double)dr; dv[1] += (double)di; }
+  }
+  if ((N & 1) && blockIdx.x == 0 && threadIdx.x == 0) {   // odd compact registers: the last entry
+    const size_t x = N - 1;
+    float re = 0.f, im = 0.f, dr = 0.f, di = 0.f;
+    unsigned k = 0;
+    if (!(FLAGS & EW_INIT)) { re = st[x].x; im = st[x].y; }
+    if (FLAGS & (EW_PHASE | EW_REDUCE))
+      k = DK == DIAG_U8 ? (unsigned)reinterpret_cast<const unsigned char*>(diag)[x] : reinterpret_cast<const unsigned*>(diag)[x];
+    one(x, re, im, k, dr, di);
+    if (FLAGS & EW_STORE) st[x] = make_float2(re, im);
+    if (FLAGS & EW_DOT) { dv[0] += (double)dr; dv[1] += (double)di; }
+  }
+  if (FLAGS & EW_DOT) {
+    dv[0] *= gen.amp;
+    dv[1] *= gen.amp;
+    block_reduce5(dv, red);
+    if (threadIdx.x == 0) { part_dot[blockIdx.x * 2] = dv[0]; part_dot[blockIdx.x * 2 + 1] = dv[1]; }
+  }
+  if (FLAGS & EW_REDUCE) {
+    if (FLAGS & EW_DOT) __syncthreads();
+    block_reduce5(rv, red);
+    if (threadIdx.x == 0)
+      for (int i = 0; i < 5; i++) part_red[blockIdx.x * 5 + i] = rv[i];
+  }
+}
+
 // coefdot = (e^{-i beta} - 1) * sum(partials)     (single block, fixed order)
 __global__ void grover_dot_finalize_kernel(const double* __restrict__ part, int nparts, double beta, double* coefdot) {
   __shared__ double red[32 * 5];

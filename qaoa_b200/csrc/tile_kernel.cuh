@@ -830,10 +830,17 @@ __device__ __forceinline__ void op_phase(const Ctx<Elem>& c, Elem (&v)[32], int 
     const double g0 = gamma * c.dinfo.c0 * inv2pi, gd = gamma * c.dinfo.delta * inv2pi;
     const real sg = (real)mult;
     const int kind = c.dinfo.kind;
+    const PhaseFx fx = make_phase_fx(gamma, c.dinfo);
     for_each_diag<NAMP>(P.streams[slot], kind, c.tile, c.warp, c.lane, [&](int a, unsigned k, double cd) {
-      double turns = kind == DIAG_U32FX ? fma((double)k, gd, g0) : fma(cd, gd, g0);
       real s, co;
-      phase_sincos(turns, s, co);
+      if (sizeof(real) == 4 && kind == DIAG_U32FX) {     // complex64 + fixed-point diagonal: integer range reduction
+        float sf, cf;
+        phase_fx_sincos_fast(fx, k, sf, cf);
+        s = (real)sf; co = (real)cf;
+      } else {
+        double turns = kind == DIAG_U32FX ? fma((double)k, gd, g0) : fma(cd, gd, g0);
+        phase_sincos(turns, s, co);
+      }
       s *= sg;
       co *= sg;
       real re, im;
