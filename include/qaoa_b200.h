@@ -137,6 +137,11 @@ int qaoa_extreme_solutions(qaoa_engine_t* h, int p, const double* angles, int n_
  * The shots -> infinity limit of the sorted sample list behind Statistic.get_CVaR (statistic.py:132-142). */
 int qaoa_cost_distribution(qaoa_engine_t* h, int p, const double* angles, int n_angles, double* probs256,
                            double* c0, double* delta);
+/* Exact CVaR_alpha of the final state's cost distribution, 0 < alpha <= 1: the mean of the cost over the best alpha of
+ * the probability mass -- the shots -> infinity limit of Statistic.get_CVaR (qaoa/utils/statistic.py:132-142), for every
+ * cost representation (integer, 32-bit fixed point, double): a weighted quantile select on the device, one sweep of the
+ * kept final state per 8-bit digit of the cost key.  out2 = {CVaR, threshold cost}. */
+int qaoa_cvar(qaoa_engine_t* h, int p, const double* angles, int n_angles, double alpha, double* out2);
 
 /* ---- Sharded registers: one engine per GPU (one process per GPU), the register split on its top
  * log2(world) qubits; rank r holds the basis indices [r * 2^(n - log2 world), (r+1) * 2^(n - log2 world)).

@@ -115,9 +115,20 @@ struct Engine {
   // per-term gammas (MaxCutFree / MaxCutOrbit): n_gamma term diagonals, single-CTA path only
   int n_gamma = 1;
   double* d_terms = nullptr;
+  // the same terms as an edge list (layered evaluation of registers beyond one CTA, run_layered_point)
+  std::vector<int> term_u, term_v, term_id;
+  std::vector<double> term_w;
+  int term_bits = 1, term_n_free = 0, term_fixed_colour = 0;
+  unsigned char term_lut[8] = {0};
+  int *d_term_u = nullptr, *d_term_v = nullptr;
+  double* d_layer_w = nullptr;      // g_e of the layer being prepared
+  double* d_init_phi = nullptr;     // PlusParameterized phases of the point being evaluated
+  void* layer_vec = nullptr;        // the segment's initial state (N amplitudes)
   // feasible-subspace compression (Dicke + Grover over the same Dicke state): compact cost diagonal of the
   // C(n,k) weight-k strings, built lazily; compact_k < 0: not built
   void* diag_compact = nullptr;
+  void* strings_compact = nullptr;          // XY in the feasible subspace: the weight-k strings (u32 for n <= 32, else u64)
+  unsigned long long* binom_compact = nullptr;   // C(b, j), (n+1) x (k+1), on the device
   size_t n_compact = 0;
   int compact_k = -1;
   int compact_enabled = 1;
@@ -266,6 +277,8 @@ int grid_for(size_t N, int threads);
 
 void drop_compact(Engine* h) {
   if (h->diag_compact) { cudaFree(h->diag_compact); h->diag_compact = nullptr; }
+  if (h->strings_compact) { cudaFree(h->strings_compact); h->strings_compact = nullptr; }
+  if (h->binom_compact) { cudaFree(h->binom_compact); h->binom_compact = nullptr; }
   h->compact_k = -1;
   h->n_compact = 0;
 }
@@ -284,8 +297,8 @@ bool ensure_compact(Engine* h, int k) {
   const unsigned long long M = binom[(size_t)h->n * (k + 1) + k];
   if (M == 0 || M > h->N / 4) return false;   // little to gain
   const int vb = diag_value_bytes(h->dinfo.kind);
-  DevTmp t_binom(binom.size() * 8);
-  unsigned long long* d_binom = t_binom.as<unsigned long long>();
+  CUDA_OK(cudaMalloc((void**)&h->binom_compact, binom.size() * 8));
+  unsigned long long* d_binom = h->binom_compact;
   h2d(h, d_binom, binom.data(), binom.size() * 8);
   CUDA_OK(cudaMalloc(&h->diag_compact, (size_t)M * vb));
   const int grid = grid_for((size_t)M, 256);
@@ -297,6 +310,26 @@ bool ensure_compact(Engine* h, int k) {
   h->launches += 1;
   h->n_compact = (size_t)M;
   h->compact_k = k;
+  return true;
+}
+
+// the weight-k strings themselves (XY mixer in the feasible subspace), built lazily next to the compact diagonal
+bool ensure_compact_strings(Engine* h) {
+  if (h->compact_k < 0) return false;
+  if (h->strings_compact) return true;
+  const size_t M = h->n_compact;
+  const int grid = grid_for(M, 256);
+  if (h->n <= 32) {
+    CUDA_OK(cudaMalloc(&h->strings_compact, M * 4));
+    unrank_feasible_kernel<unsigned><<<grid, 256, 0, h->stream>>>((unsigned*)h->strings_compact, M, h->n, h->compact_k, h->binom_compact);
+  } else {
+    CUDA_OK(cudaMalloc(&h->strings_compact, M * 8));
+    unrank_feasible_kernel<unsigned long long><<<grid, 256, 0, h->stream>>>((unsigned long long*)h->strings_compact, M, h->n,
+                                                                          h->compact_k, h->binom_compact);
+  }
+  CUDA_OK(cudaGetLastError());
+  CUDA_OK(cudaStreamSynchronize(h->stream));
+  h->launches += 1;
   return true;
 }
 
@@ -1255,7 +1288,12 @@ bool launch_grover_fast(Engine* h, int grid, float2* st, size_t Nv, int flags, c
 
 template <typename real>
 void run_elementwise_point(Engine* h, int p, const double* ang, double* d_out_point) {
-  ensure_state(h, 1);
+  // feasible-subspace registers (Dicke + Grover over the same Dicke state, Dicke + XY) need C(n,k) amplitudes only
+  const bool xy_tiled_size = h->n >= (h->dtype == QAOA_DTYPE_C64 ? 13 : 12);
+  const bool want_compact = h->init.kind == INIT_DICKE &&
+      ((h->mixer == MIXER_GROVER && h->sub.kind == INIT_DICKE && h->init.k == h->sub.k) || (h->mixer == MIXER_XY && xy_tiled_size));
+  const bool compact = want_compact && ensure_compact(h, h->init.k) && (h->mixer != MIXER_XY || ensure_compact_strings(h));
+  ensure_state(h, 1, compact ? h->n_compact : h->N);
   const int threads = 256;
   const int grid = grid_for(h->N, threads);
   ensure(h->d_partials, h->partials_cap, (size_t)grid * 5 * sizeof(double) * 2);
@@ -1269,8 +1307,7 @@ void run_elementwise_point(Engine* h, int p, const double* ang, double* d_out_po
   size_t Nv = h->N;
   const void* diagv = h->diag;
   StateGen initv = h->init, subv = h->sub;
-  if (h->mixer == MIXER_GROVER && h->init.kind == INIT_DICKE && h->sub.kind == INIT_DICKE && h->init.k == h->sub.k &&
-      ensure_compact(h, h->init.k)) {
+  if (h->mixer == MIXER_GROVER && compact) {
     Nv = h->n_compact;
     diagv = h->diag_compact;
     initv.kind = INIT_UNIFORM;
@@ -1330,6 +1367,46 @@ void run_elementwise_point(Engine* h, int p, const double* ang, double* d_out_po
         }
     }
     ew(EW_REDUCE, 0.0);
+  } else if (h->mixer == MIXER_XY && compact) {
+    // XY + Dicke in the feasible subspace: C(n,k) entries instead of 2^n, one sweep per gate over the compact register
+    const size_t M = h->n_compact;
+    const int np = (int)h->pairs.size() / 2;
+    StateGen uni = h->init;
+    uni.kind = INIT_UNIFORM;
+    const int cgrid = grid_for(M, threads);
+    const double csweep = (double)M * h->amp_bytes, cdsz = (double)M * diag_value_bytes(h->dinfo.kind);
+    const double sbytes = h->n <= 32 ? 4.0 : 8.0;
+    auto cew = [&](int flags, double gamma) {
+      elementwise_pass_kernel<real><<<cgrid, threads, 0, h->stream>>>(st, M, flags, uni, uni, h->d_coefdot, gamma,
+                                                                     h->diag_compact, h->dinfo, part_dot, part_red);
+      CUDA_OK(cudaGetLastError());
+      h->launches += 1;
+      h->bytes_alg += ((flags & EW_INIT) ? 0 : csweep) + ((flags & EW_STORE) ? csweep : 0) + cdsz;
+    };
+    // fraction of the entries a gate touches: strings with x[q0] != x[q1]
+    const double touched = h->n > 1 ? 2.0 * h->init.k * (h->n - h->init.k) / ((double)h->n * (h->n - 1)) : 0.0;
+    const int smem = (h->n + 1) * (h->init.k + 1) * 8;
+    typedef typename Real2<real>::type real2;
+    for (int d = 0; d < p; d++) {
+      cew((d == 0 ? EW_INIT : 0) | EW_PHASE | EW_STORE, ang[2 * d]);
+      const double a = 0.25 * ang[2 * d + 1] / h->trotter;
+      for (int rep = 0; rep < h->trotter; rep++)
+        for (int e = 0; e < np; e++) {
+          const int q0 = h->pairs[2 * e], q1 = h->pairs[2 * e + 1];
+          if (h->n <= 32)
+            xy_compact_gate_kernel<real, unsigned><<<cgrid, threads, smem, h->stream>>>(
+                (real2*)st, (const unsigned*)h->strings_compact, M, q0, q1, (real)cos(a), (real)sin(a), h->binom_compact, h->n, h->init.k);
+          else
+            xy_compact_gate_kernel<real, unsigned long long><<<cgrid, threads, smem, h->stream>>>(
+                (real2*)st, (const unsigned long long*)h->strings_compact, M, q0, q1, (real)cos(a), (real)sin(a), h->binom_compact,
+                h->n, h->init.k);
+          CUDA_OK(cudaGetLastError());
+          h->launches += 1;
+          h->bytes_alg += (double)M * sbytes + 2.0 * touched * csweep;
+        }
+    }
+    cew(EW_REDUCE, 0.0);
+    grid_red = cgrid;
   } else {  // XY: ordered gate list, tiled (see xy_tile_kernel)
     const int np = (int)h->pairs.size() / 2;
     const bool c64 = h->dtype == QAOA_DTYPE_C64;
@@ -1414,10 +1491,11 @@ void check_ready(Engine* h, int p, int n_angles) {
              h->n_init + p * (h->n_gamma + nb), p, h->n_init, h->n_gamma, nb, n_angles);
     fail(b);
   }
-  if (h->n_init > 0 && h->n > h->small_max())
-    fail("parameterised initial states (PlusParameterized) are supported on registers that fit one CTA only");
-  if (h->n_gamma > 1 && h->n > h->small_max())
-    fail("per-term gammas (MaxCutFree / MaxCutOrbit) are supported on registers that fit one CTA only");
+  if ((h->n_init > 0 || h->n_gamma > 1) && h->n > h->small_max()) {
+    if (h->mixer != MIXER_X && h->mixer != MIXER_XMULTI)
+      fail("per-term gammas / PlusParameterized on registers beyond one CTA: X and multi-angle X mixers only");
+    if (h->world > 1) fail("sharded engine: per-term gammas / PlusParameterized are not supported");
+  }
   if ((h->mixer == MIXER_XY) && h->pairs.empty()) fail("XY mixer without pairs");
 }
 
@@ -1448,11 +1526,94 @@ void energy_batch_impl(Engine* h, int p, const double* angles, int n_angles, int
   CUDA_OK(cudaSetDevice(h->device));
   if (!h->ev_call0) { CUDA_OK(cudaEventCreate(&h->ev_call0)); CUDA_OK(cudaEventCreate(&h->ev_call1)); }
   // make sure plans / streams exist before the timed region starts
-  if (h->n > h->small_max() && (h->mixer == MIXER_X || h->mixer == MIXER_XMULTI)) get_plan(h, p);
+  if (h->n > h->small_max() && (h->mixer == MIXER_X || h->mixer == MIXER_XMULTI) && h->n_gamma == 1 && h->n_init == 0)
+    get_plan(h, p);
   CUDA_OK(cudaEventRecord(h->ev_call0, h->stream));
   energy_batch_body(h, p, angles, n_angles, B);
   CUDA_OK(cudaEventRecord(h->ev_call1, h->stream));
   h->ev_call_recorded = true;
+}
+
+// Per-term gammas (MaxCutFree / MaxCutOrbit) and PlusParameterized on registers beyond one CTA, X-type mixers: the
+// circuit runs layer by layer.  layer_phase_kernel writes the segment's initial state (kept state of the previous
+// segment x the layer's edge phases; first layer: generated state x RZ phases x edge phases), the tile plan of depth 1
+// applies the mixer with gamma = 0 and keeps its final state; the last segment's statistics are the circuit's.  With
+// one gamma per layer (PlusParameterized alone) the prepared state is followed by the ordinary depth-p plan.
+void run_layered_point(Engine* h, int p, const double* ang, double* d_out_point) {
+  const int ng = h->n_gamma, ni = h->n_init;
+  const int nb = h->mixer == MIXER_XMULTI ? h->n : 1;
+  const int per = ng + nb;
+  const int ne = (int)h->term_u.size();
+  if (ng > 1 && ne == 0) fail("per-term gammas without an edge list");
+  if (!h->layer_vec) CUDA_OK(cudaMalloc(&h->layer_vec, h->N * h->amp_bytes));
+  if (ni > 0) {
+    if (!h->d_init_phi) CUDA_OK(cudaMalloc((void**)&h->d_init_phi, QAOA_MAX_QUBITS * sizeof(double)));
+    h2d(h, h->d_init_phi, ang, ni * sizeof(double));
+  }
+  if (ng > 1 && !h->d_layer_w) {
+    CUDA_OK(cudaMalloc((void**)&h->d_layer_w, ne * sizeof(double)));
+    CUDA_OK(cudaMalloc((void**)&h->d_term_u, ne * sizeof(int)));
+    CUDA_OK(cudaMalloc((void**)&h->d_term_v, ne * sizeof(int)));
+    h2d(h, h->d_term_u, h->term_u.data(), ne * sizeof(int));
+    h2d(h, h->d_term_v, h->term_v.data(), ne * sizeof(int));
+  }
+  MaxKCutDev D;
+  memset(&D, 0, sizeof(D));
+  D.bits = h->term_bits; D.n_free = h->term_n_free; D.fixed_colour = h->term_fixed_colour;
+  for (int i = 0; i < 8; i++) D.lut[i] = h->term_lut[i];
+  D.eu = h->d_term_u; D.ev = h->d_term_v; D.ew = h->d_layer_w; D.ewi = nullptr;
+  const StateGen gen0 = h->init;
+  void* const vec0 = h->init_vec;
+  const int keep0 = h->keep_state;
+  const int grid = grid_for(h->N, 256);
+  const double sweep = (double)h->N * h->amp_bytes;
+  auto prepare = [&](int d) {       // d < 0: initial state + RZ phases only
+    D.n_edges = 0;
+    if (d >= 0 && ng > 1) {
+      std::vector<double> g(ne);
+      for (int e = 0; e < ne; e++) g[e] = ang[ni + d * per + h->term_id[e]] * h->term_w[e];
+      h2d(h, h->d_layer_w, g.data(), ne * sizeof(double));
+      D.n_edges = ne;
+    }
+    const bool first = d <= 0;
+    if (h->dtype == QAOA_DTYPE_C64)
+      layer_phase_kernel<float><<<grid, 256, 0, h->stream>>>(first ? nullptr : (const float*)h->state, (float*)h->layer_vec, h->N, gen0,
+                                                           (float)(h->last_scale * h->last_gsign), D, first ? ni : 0, h->d_init_phi);
+    else
+      layer_phase_kernel<double><<<grid, 256, 0, h->stream>>>(first ? nullptr : (const double*)h->state, (double*)h->layer_vec, h->N, gen0,
+                                                            h->last_scale * h->last_gsign, D, first ? ni : 0, h->d_init_phi);
+    CUDA_OK(cudaGetLastError());
+    h->launches += 1;
+    h->bytes_alg += (first ? 1.0 : 2.0) * sweep;
+  };
+  struct Restore {
+    Engine* h; StateGen g; void* v; int keep, ng, ni;
+    ~Restore() { h->init = g; h->init_vec = v; h->keep_state = keep; h->n_gamma = ng; h->n_init = ni; h->plans.clear(); }
+  } restore{h, gen0, vec0, keep0, ng, ni};
+  h->plans.clear();
+  h->init.kind = INIT_STATEVECTOR; h->init.k = 0; h->init.amp = 1.0; h->init.vec = h->layer_vec;
+  h->init_vec = h->layer_vec;
+  h->n_gamma = 1; h->n_init = 0;
+  if (ng == 1) {   // PlusParameterized with an ordinary cost function: prepared state, then the depth-p plan
+    prepare(-1);
+    Plan& pl = get_plan(h, p);
+    ensure_state(h, 1, plan_amps(h, pl));
+    run_tile_chunk(h, pl, ang + ni, p * per, 1, d_out_point, true);
+    CUDA_OK(cudaStreamSynchronize(h->stream));
+    return;
+  }
+  std::vector<double> a1(1 + nb);
+  for (int d = 0; d < p; d++) {
+    h->keep_state = (d + 1 < p) ? 1 : keep0;
+    h->plans.clear();
+    prepare(d);
+    a1[0] = 0.0;
+    for (int q = 0; q < nb; q++) a1[1 + q] = ang[ni + d * per + ng + q];
+    Plan& pl = get_plan(h, 1);
+    ensure_state(h, 1, plan_amps(h, pl));
+    run_tile_chunk(h, pl, a1.data(), 1 + nb, 1, d_out_point, true);
+    CUDA_OK(cudaStreamSynchronize(h->stream));   // pinned parameter buffer reuse
+  }
 }
 
 void energy_batch_body(Engine* h, int p, const double* angles, int n_angles, int B) {
@@ -1466,6 +1627,10 @@ void energy_batch_body(Engine* h, int p, const double* angles, int n_angles, int
       if (Bc < B - done) CUDA_OK(cudaStreamSynchronize(h->stream));  // d_angles reuse
       done += Bc;
     }
+    return;
+  }
+  if ((h->mixer == MIXER_X || h->mixer == MIXER_XMULTI) && (h->n_gamma > 1 || h->n_init > 0)) {
+    for (int b = 0; b < B; b++) run_layered_point(h, p, angles + (size_t)b * n_angles, h->d_out + (size_t)b * 5);
     return;
   }
   if (h->mixer == MIXER_X || h->mixer == MIXER_XMULTI) {
@@ -1489,10 +1654,18 @@ void energy_batch_body(Engine* h, int p, const double* angles, int n_angles, int
   }
 }
 
+void drop_term_edges(Engine* h) {
+  h->term_u.clear(); h->term_v.clear(); h->term_id.clear(); h->term_w.clear();
+  if (h->d_term_u) { cudaFree(h->d_term_u); h->d_term_u = nullptr; }
+  if (h->d_term_v) { cudaFree(h->d_term_v); h->d_term_v = nullptr; }
+  if (h->d_layer_w) { cudaFree(h->d_layer_w); h->d_layer_w = nullptr; }
+}
+
 void set_diag_common(Engine* h, int kind, double c0, double delta) {
   close_peers(h, 1);
   drop_compact(h);
   if (h->d_terms) { cudaFree(h->d_terms); h->d_terms = nullptr; }
+  drop_term_edges(h);
   h->n_gamma = 1;
   if (h->diag) { cudaFree(h->diag); h->diag = nullptr; }
   free_streams(h);
@@ -1618,7 +1791,8 @@ int qaoa_destroy(qaoa_engine_t* h) {
   close_peers(h, 0);
   close_peers(h, 1);
   free_streams(h);
-  void* bufs[] = {h->state, h->diag, h->diag_compact, h->d_terms, h->d_pairs, h->init_vec, h->sub_vec, h->d_params, h->d_partials, h->d_out,
+  void* bufs[] = {h->state, h->diag, h->diag_compact, h->strings_compact, h->binom_compact, h->d_term_u, h->d_term_v, h->d_layer_w,
+                  h->d_init_phi, h->layer_vec, h->d_terms, h->d_pairs, h->init_vec, h->sub_vec, h->d_params, h->d_partials, h->d_out,
                   h->d_tables, h->d_gamsig, h->d_coefdot, h->d_angles};
   for (void* b : bufs) if (b) cudaFree(b);
   if (h->h_params) cudaFreeHost(h->h_params);
@@ -1754,9 +1928,16 @@ int qaoa_set_cost_maxkcut_terms(qaoa_engine_t* h, int n_nodes, int n_edges, cons
   API_BEGIN(h)
   if (h->world > 1) fail("sharded engine: per-term gammas are not supported");
   if (n_terms < 1 || !term_of_edge) fail("term_of_edge is null / n_terms < 1");
-  if (h->n > (h->dtype == QAOA_DTYPE_C64 ? 14 : 13)) fail("per-term gammas are supported on registers that fit one CTA only");
   for (int e = 0; e < n_edges; e++) if (term_of_edge[e] < 0 || term_of_edge[e] >= n_terms) fail("term index out of range");
-  if (n_terms > 1) {
+  if (n_terms > 1) {   // the edge list itself: registers beyond one CTA evaluate the term phases on the fly (run_layered_point)
+    h->term_u.assign(u, u + n_edges); h->term_v.assign(v, v + n_edges); h->term_w.assign(w, w + n_edges);
+    h->term_id.assign(term_of_edge, term_of_edge + n_edges);
+    h->term_bits = bits_per_node; h->term_n_free = n_nodes - (fixed_node ? 1 : 0); h->term_fixed_colour = fixed_colour;
+    for (int i = 0; i < 8; i++) h->term_lut[i] = i < (1 << bits_per_node) ? lut[i] : 0;
+    h->n_gamma = n_terms;
+    invalidate(h);
+  }
+  if (n_terms > 1 && h->n <= (h->dtype == QAOA_DTYPE_C64 ? 14 : 13)) {
   CUDA_OK(cudaMalloc((void**)&h->d_terms, (size_t)n_terms * h->N * sizeof(double)));
   MaxKCutDev D;
   memset(&D, 0, sizeof(D));
@@ -1935,7 +2116,6 @@ int qaoa_set_initial(qaoa_engine_t* h, int kind, int k, const double* vec) {
   h->n_init = 0;
   if (kind == 3) {   // QAOA_INIT_PLUS_PHASES: |+>^n followed by RZ(phi_q) on the first k qubits, phi = leading angles
     if (k < 1 || k > h->n) fail("number of initial-state phases out of range");
-    if (h->n > (h->dtype == QAOA_DTYPE_C64 ? 14 : 13)) fail("PlusParameterized is supported on registers that fit one CTA only");
     h->init = make_gen(h, INIT_PLUS, 0, nullptr, &h->init_vec);
     h->n_init = k;
   } else
@@ -2150,6 +2330,63 @@ int qaoa_cost_distribution(qaoa_engine_t* h, int p, const double* angles, int n_
   if (c0) *c0 = h->dinfo.c0;
   if (delta) *delta = h->dinfo.delta;
   h->launches += 1;
+  API_END(h)
+}
+
+// exact CVaR_alpha of the final state's cost distribution for every cost representation (cvar_digit_kernel)
+int qaoa_cvar(qaoa_engine_t* h, int p, const double* angles, int n_angles, double alpha, double* out2) {
+  API_BEGIN(h)
+  if (!out2) fail("null output");
+  if (!(alpha > 0.0) || alpha > 1.0) fail("cvar fraction must be in (0, 1]");
+  eval_keeping_state(h, p, angles, n_angles);
+  const int grid = grid_for(h->N, 256);
+  DevTmp t_part((size_t)grid * 512 * 8), t_sum(512 * 8);
+  double* d_part = t_part.as<double>();
+  double* d_sum = t_sum.as<double>();
+  const int keybits = h->dinfo.kind == DIAG_U8 ? 8 : (h->dinfo.kind == DIAG_U32FX ? 32 : 64);
+  unsigned long long prefix = 0;
+  double above_mass = 0.0, above_pc = 0.0, total = 0.0, thr_mass = 0.0;
+  std::vector<double> hist(512);
+  for (int shift = keybits - 8; shift >= 0; shift -= 8) {
+    const int check = shift != keybits - 8;
+    if (h->dtype == QAOA_DTYPE_C64)
+      cvar_digit_kernel<float><<<grid, 256, 0, h->stream>>>((const float*)h->state, h->diag, h->dinfo, h->N, prefix, shift, check, d_part);
+    else
+      cvar_digit_kernel<double><<<grid, 256, 0, h->stream>>>((const double*)h->state, h->diag, h->dinfo, h->N, prefix, shift, check, d_part);
+    CUDA_OK(cudaGetLastError());
+    sum_partials_kernel<<<2, 256, 0, h->stream>>>(d_part, grid, 512, d_sum);
+    CUDA_OK(cudaGetLastError());
+    h->launches += 2;
+    d2h(h, hist.data(), d_sum, 512 * 8);
+    if (!check) {
+      for (int d = 0; d < 256; d++) total += hist[d];
+      if (!(total > 0.0)) fail("state has zero norm");
+    }
+    const double want = alpha * total;
+    // the largest digit d* with  above + mass(digits > d*) < want <= above + mass(digits >= d*)
+    int dstar = 0;
+    double am = above_mass, ap = above_pc;
+    for (int d = 255; d >= 0; d--) {
+      if (am + hist[d] >= want || d == 0) { dstar = d; break; }
+      am += hist[d];
+      ap += hist[256 + d];
+    }
+    // rounding can leave the target unreached at digit 0 with an empty bin: fall to the lowest populated digit
+    if (hist[dstar] <= 0.0) for (int d = 0; d < 256; d++) if (hist[d] > 0.0) { dstar = d; break; }
+    above_mass = am; above_pc = ap;
+    thr_mass = hist[dstar];
+    prefix = (prefix << 8) | (unsigned long long)dstar;
+  }
+  double cthr;
+  if (h->dinfo.kind == DIAG_F64) {
+    const unsigned long long b = (prefix >> 63) ? (prefix & 0x7fffffffffffffffull) : ~prefix;
+    long long ll = (long long)b;
+    memcpy(&cthr, &ll, 8);
+  } else cthr = h->dinfo.c0 + h->dinfo.delta * (double)prefix;
+  const double want = alpha * total;
+  const double take = std::min(std::max(want - above_mass, 0.0), thr_mass);
+  out2[0] = (above_pc + take * cthr) / (above_mass + take);
+  out2[1] = cthr;
   API_END(h)
 }
 

@@ -957,6 +957,54 @@ cost_hist_kernel(const real* __restrict__ st, const uint8_t* __restrict__ diag, 
   partial[(size_t)blockIdx.x * 256 + threadIdx.x] = bins[threadIdx.x];
 }
 
+// ---- exact CVaR of ANY cost representation: weighted quantile select on the device ----------------------------------
+// CVaR_alpha = mean of the cost over the best alpha of the probability mass (statistic.py:132-142 in the shots ->
+// infinity limit: the reference sorts the sampled costs and averages the top round(alpha * shots)).  The threshold
+// cost is found digit by digit over an order-preserving integer key of the cost (U8: the byte, U32FX: the 32-bit
+// integer, F64: the sign-flipped bit pattern), most significant digit first: one sweep per 8-bit digit histograms the
+// probability mass and the mass-weighted cost of the amplitudes whose key matches the prefix found so far.
+__device__ __forceinline__ unsigned long long cost_key(const DiagInfo& info, const void* diag, size_t x, double& c) {
+  if (info.kind == DIAG_U8) { const unsigned k = ((const uint8_t*)diag)[x]; c = info.c0 + info.delta * (double)k; return k; }
+  if (info.kind == DIAG_U32FX) { const unsigned k = ((const uint32_t*)diag)[x]; c = info.c0 + info.delta * (double)k; return k; }
+  c = ((const double*)diag)[x];
+  const unsigned long long b = (unsigned long long)__double_as_longlong(c);
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+
+// partial: [gridDim.x][512] = {mass[256], mass x cost[256]} of the digit at `shift` among keys with (key >> (shift+8)) == prefix
+template <typename real>
+__global__ void __launch_bounds__(256)
+cvar_digit_kernel(const real* __restrict__ st, const void* __restrict__ diag, DiagInfo info, size_t N,
+                  unsigned long long prefix, int shift, int check_prefix, double* __restrict__ partial) {
+  __shared__ double bins[512];
+  bins[threadIdx.x] = 0.0;
+  bins[256 + threadIdx.x] = 0.0;
+  __syncthreads();
+  for (size_t x = blockIdx.x * (size_t)blockDim.x + threadIdx.x; x < N; x += (size_t)gridDim.x * blockDim.x) {
+    const double re = st[2 * x], im = st[2 * x + 1];
+    const double p = re * re + im * im;
+    if (!(p > 0.0)) continue;
+    double c;
+    const unsigned long long key = cost_key(info, diag, x, c);
+    if (check_prefix && ((key >> shift) >> 8) != prefix) continue;
+    const unsigned d = (unsigned)(key >> shift) & 255u;
+    atomicAdd(&bins[d], p);
+    atomicAdd(&bins[256 + d], p * c);
+  }
+  __syncthreads();
+  partial[(size_t)blockIdx.x * 512 + threadIdx.x] = bins[threadIdx.x];
+  partial[(size_t)blockIdx.x * 512 + 256 + threadIdx.x] = bins[256 + threadIdx.x];
+}
+
+// out[j] = sum over blocks of partial[b][j]   (fixed order)
+__global__ void sum_partials_kernel(const double* __restrict__ partial, int nblocks, int width, double* __restrict__ out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= width) return;
+  double s = 0.0;
+  for (int b = 0; b < nblocks; b++) s += partial[(size_t)b * width + j];
+  out[j] = s;
+}
+
 // Basis indices of the support of the kept state whose cost equals `target` (the extreme the reduction
 // reported): the shots -> infinity limit of Statistic.get_max_sols / get_min_sols (statistic.py:69-82).
 template <typename real>
@@ -993,5 +1041,97 @@ __global__ void gather_feasible_kernel(const unsigned char* __restrict__ diag, u
     }
 #pragma unroll
     for (int q = 0; q < VALBYTES; q++) out[i * VALBYTES + q] = diag[x * VALBYTES + q];
+  }
+}
+
+// ---- XY mixer in the feasible subspace ------------------------------------------------------------
+// XY gates conserve the Hamming weight (xy_mixer.py:42-79 on |D^n_k>, dicke_initialstate.py:38-56), so with a Dicke
+// initial state the register never leaves the C(n,k) weight-k strings: it is stored compactly, entry i = the i-th
+// weight-k string in colex order (rank(x) = sum over set bits, the j-th from below at position b, of C(b, j) -- the
+// order gather_feasible_kernel uses).  `strings[i]` holds the string itself.
+template <typename S>
+__global__ void unrank_feasible_kernel(S* __restrict__ strings, size_t M, int n, int k,
+                                       const unsigned long long* __restrict__ binom) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < M; i += (size_t)gridDim.x * blockDim.x) {
+    unsigned long long r = i, x = 0;
+    int j = k;
+    for (int b = n - 1; b >= 0 && j > 0; b--) {
+      const unsigned long long cbj = binom[b * (k + 1) + j];
+      if (r >= cbj) { x |= 1ull << b; r -= cbj; j--; }
+    }
+    strings[i] = (S)x;
+  }
+}
+
+// One XY gate on (q0, q1) over the compact register: the thread of a string with x[q0] = 1, x[q1] = 0 finds the rank of
+// its partner (bits q0, q1 swapped) -- only the set bits between the two positions change their contribution to the
+// rank -- and rotates the pair:  a' = c a - i s b,  b' = c b - i s a  (the S frame leaves XY gates unchanged).
+template <typename real, typename S>
+__global__ void __launch_bounds__(256)
+xy_compact_gate_kernel(typename Real2<real>::type* __restrict__ st, const S* __restrict__ strings, size_t M, int q0, int q1,
+                       real c, real s, const unsigned long long* __restrict__ binom, int n, int k) {
+  extern __shared__ unsigned long long sb[];
+  const int k1 = k + 1;
+  for (int t = threadIdx.x; t < (n + 1) * k1; t += blockDim.x) sb[t] = binom[t];
+  __syncthreads();
+  const int lo = q0 < q1 ? q0 : q1, hi = q0 < q1 ? q1 : q0;
+  const unsigned long long range = ((hi == 63 ? 0ull : (1ull << (hi + 1))) - 1ull) & ~((1ull << lo) - 1ull);
+  typedef typename Real2<real>::type real2;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < M; i += (size_t)gridDim.x * blockDim.x) {
+    const unsigned long long x = (unsigned long long)strings[i];
+    if (!((x >> q0) & 1ull) || ((x >> q1) & 1ull)) continue;
+    const unsigned long long xp = x ^ (1ull << q0) ^ (1ull << q1);
+    const int j0 = __popcll(x & ((1ull << lo) - 1ull));
+    long long delta = 0;
+    unsigned long long m = x & range;
+    int j = j0;
+    while (m) { const int b = __ffsll((long long)m) - 1; m &= m - 1; j++; delta -= (long long)sb[b * k1 + j]; }
+    m = xp & range;
+    j = j0;
+    while (m) { const int b = __ffsll((long long)m) - 1; m &= m - 1; j++; delta += (long long)sb[b * k1 + j]; }
+    const size_t ip = (size_t)((long long)i + delta);
+    const real2 a = st[i], b2 = st[ip];
+    real2 an, bn;
+    an.x = c * a.x + s * b2.y;
+    an.y = c * a.y - s * b2.x;
+    bn.x = c * b2.x + s * a.y;
+    bn.y = c * b2.y - s * a.x;
+    st[i] = an;
+    st[ip] = bn;
+  }
+}
+
+// ---- per-term gammas and parameterised |+> beyond one CTA -----------------------------------------
+// MaxCutFree / MaxCutOrbit give every edge (orbit) its own gamma (maxcut_free_problem.py:31-99,
+// maxcut_orbit_problem.py:51-181): the phase separator of layer d is exp(i sum_e g_e [colour(u_e) != colour(v_e)]) with
+// g_e = gamma_{d, term(e)} * w_e -- no single cost diagonal times a scalar, so no phase table.  Large registers run such
+// circuits LAYER BY LAYER (engine.cu run_layered_point): this sweep turns the state kept by the previous layer's mixer
+// passes (true amplitude = src * scale) -- or, for the first layer, the generated initial state with PlusParameterized's
+// RZ phases (plus_parameterized_initialstate.py:44-64) -- into the next segment's initial state, multiplied by the
+// layer's edge phases evaluated on the fly from the edge list; the mixer passes then run with gamma = 0.
+template <typename real>
+__global__ void __launch_bounds__(256)
+layer_phase_kernel(const real* __restrict__ src, real* __restrict__ dst, size_t N, StateGen init, real scale,
+                   MaxKCutDev D /* ew = g_e of this layer; n_edges = 0: no edge phase */, int n_init,
+                   const double* __restrict__ init_phi) {
+  for (size_t x = blockIdx.x * (size_t)blockDim.x + threadIdx.x; x < N; x += (size_t)gridDim.x * blockDim.x) {
+    real re, im;
+    double theta = 0.0;
+    if (src) { re = src[2 * x] * scale; im = src[2 * x + 1] * scale; }
+    else {
+      gen_amp<real>(init, x, re, im);
+      for (int q = 0; q < n_init; q++) theta += __ldg(init_phi + q) * (((x >> q) & 1) ? 0.5 : -0.5);
+    }
+    for (int e = 0; e < D.n_edges; e++) {
+      const int cu = node_colour(D, x, __ldg(D.eu + e)), cv = node_colour(D, x, __ldg(D.ev + e));
+      theta += (cu != cv) ? __ldg(D.ew + e) : 0.0;
+    }
+    double turns = theta * 0.15915494309189533576888;
+    turns -= rint(turns);
+    real s, c;
+    if (sizeof(real) == 4) { float sf, cf; sincospif(2.0f * (float)turns, &sf, &cf); s = (real)sf; c = (real)cf; }
+    else { double sd, cd; sincospi(2.0 * turns, &sd, &cd); s = (real)sd; c = (real)cd; }
+    dst[2 * x] = re * c - im * s;
+    dst[2 * x + 1] = re * s + im * c;
   }
 }

@@ -90,6 +90,7 @@ def load_library():
         "qaoa_sample": (ctypes.c_int, [H, ctypes.c_int, _c_double_p, ctypes.c_int, ctypes.c_int, _c_double_p, _c_uint64_p]),
         "qaoa_extreme_solutions": (ctypes.c_int, [H, ctypes.c_int, _c_double_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                                   _c_uint64_p, ctypes.POINTER(ctypes.c_int), _c_double_p]),
+        "qaoa_cvar": (ctypes.c_int, [H, ctypes.c_int, _c_double_p, ctypes.c_int, ctypes.c_double, _c_double_p]),
         "qaoa_cost_distribution": (ctypes.c_int, [H, ctypes.c_int, _c_double_p, ctypes.c_int, _c_double_p,
                                                   _c_double_p, _c_double_p]),
         # sharded registers (one engine per GPU)
@@ -356,6 +357,13 @@ class Engine:
                                                      ctypes.byref(c0), ctypes.byref(delta)))
         keep = probs > 0
         return (c0.value + delta.value * np.arange(256))[keep], probs[keep]
+
+    def cvar(self, angles, alpha):
+        """exact CVaR_alpha (mean cost over the best alpha of the probability mass) of the final state, any cost type"""
+        angles, p = self._angles(angles)
+        out = np.empty(2, dtype=np.float64)
+        self._check(self._lib.qaoa_cvar(self._h, p, _dptr(angles), angles.size, float(alpha), _dptr(out)))
+        return float(out[0])
 
     # -- sharded registers: one engine per GPU (include/qaoa_b200.h, "Sharded registers") -------------
     def shard_local_ptr(self, which):

@@ -396,14 +396,18 @@ class QAOA:
     _CVAR_HOST_MAX_QUBITS = 26
 
     def _cvar_of(self, eng_row):
-        """exact CVaR of the final state's cost distribution.  Integer-valued costs (range <= 255): the device's cost-value
-        histogram.  Real-valued costs (weighted graphs, scaled ExactCover, Portfolio: the reference's CVaR.ipynb and
-        CompareGroverXY.ipynb cases): |psi|^2 is read back once per evaluation and the tail mean is taken on the host
-        over the cost diagonal sorted once (the reference's Statistic is host code too, statistic.py:132-142); registers
-        beyond 26 qubits are rejected."""
+        """exact CVaR of the final state's cost distribution (shots -> infinity limit of statistic.py:132-142).  On the
+        device engine: ``qaoa_cvar`` (digit-by-digit weighted quantile select, integer AND real-valued costs -- weighted
+        graphs, scaled ExactCover, Portfolio: the reference's CVaR.ipynb and CompareGroverXY.ipynb cases).  Engines
+        without it (the oracle stand-in of the CPU tests, sharded registers) keep the host evaluation: cost-value
+        histogram for integer costs, else |psi|^2 read back and the tail mean over the sorted diagonal (<= 26 qubits)."""
         from qaoa_b200.engine import EngineError
 
         eng = self._get_engine()
+        if hasattr(eng, "cvar"):
+            # the device engine: weighted quantile select over the kept final state (qaoa_cvar), every cost
+            # representation, no read-back of |psi|^2, no qubit limit
+            return self._device_call("cvar", eng_row, self.cvar)
         if getattr(self, "_cvar_on_host", None) is None:
             try:
                 costs, probs = self._device_call("cost_distribution", eng_row)

@@ -125,12 +125,33 @@ def test_per_term_gammas_free_and_orbit(dtype, tol):
         b = ref._evaluate(rows)
         assert np.allclose(a[:, 0], b[:, 0], rtol=tol, atol=tol), (type(dev.problem).__name__, a[:, 0], b[:, 0])
         assert np.allclose(a[:, 1], b[:, 1], rtol=2 * tol, atol=2 * tol)
-    # a register that does not fit one CTA is rejected, not mis-evaluated
-    big = QAOA(problem=problems.MaxCutFree(nx.random_regular_graph(3, 16, seed=1)), mixer=mixers.X(),
-               initialstate=initialstates.Plus(), dtype=dtype)
-    from qaoa_b200.engine import EngineError
-    with pytest.raises(EngineError):
-        big.sample_cost_landscape({"gamma": [0, 1, 2], "beta": [0, 1, 2]})
+
+
+@pytest.mark.parametrize("dtype,tol", [("complex128", 1e-9), ("complex64", 1e-4)])
+def test_per_term_gammas_and_plus_parameterized_beyond_one_cta(dtype, tol):
+    """Registers that do not fit one CTA (n = 16, 18): per-term gammas and PlusParameterized run layer by layer on the
+    tile passes (engine.cu run_layered_point: on-the-fly edge phases, mixer passes with gamma = 0) -- vs the oracle."""
+    rng = np.random.default_rng(11)
+    G16 = nx.random_regular_graph(3, 16, seed=1)
+    G18 = nx.random_regular_graph(3, 18, seed=3)
+    cases = ((lambda: problems.MaxCutFree(G16), mixers.X, initialstates.Plus, 3),
+             (lambda: problems.MaxCutFree(G16), mixers.XMultiAngle, initialstates.Plus, 2),
+             (lambda: problems.MaxCutOrbit(G18), lambda: mixers.XOrbit(G18), initialstates.Plus, 2),
+             (lambda: problems.MaxCut(G16), mixers.X, lambda: initialstates.PlusParameterized(num_phases=9), 3),
+             (lambda: problems.MaxCutFree(G16), mixers.X, lambda: initialstates.PlusParameterized(num_phases=16), 2))
+    for mk_p, mk_m, mk_i, depth in cases:
+        dev, ref = both(mk_p, mk_m, mk_i, dtype)
+        dev.createParameterizedCircuit(depth)
+        ref.createParameterizedCircuit(depth)
+        per = dev.n_gamma + dev.n_beta
+        rows = rng.uniform(-1.5, 1.5, size=(2, dev.n_init + depth * per))
+        a = dev._evaluate(rows)
+        b = ref._evaluate(rows)
+        assert np.allclose(a[:, 0], b[:, 0], rtol=tol, atol=tol), (type(dev.problem).__name__, a[:, 0], b[:, 0])
+        assert np.allclose(a[:, 1], b[:, 1], rtol=2 * tol, atol=2 * tol)
+    # the sampler follows the layered path too (kept final state)
+    h = dev.hist(rows[0], 256)
+    assert sum(h.values()) == 256
 
 
 @pytest.mark.parametrize("dtype,tol", [("complex128", 1e-9), ("complex64", 1e-4)])

@@ -155,7 +155,94 @@ def test_xy_dicke(n, k, case, dtype):
     for p in (1, 2):
         ang = rng.uniform(0, 2 * np.pi, size=2 * p)
         ang[::2] *= 0.05
-        _check(E.energy(ang), spec, ang, dtype, "xy p=%d" % p)
+        out = E.energy(ang)
+        _check(out, spec, ang, dtype, "xy p=%d" % p)
+        if n > 13:
+            # XY + Dicke runs in the C(n,k)-dimensional feasible subspace (xy_compact_gate_kernel); the tiled
+            # full-register kernel must agree
+            from math import comb
+            assert E.counter("compact_size") == comb(n, k)
+            E.set_option("feasible_subspace", 0)
+            full = E.energy(ang)
+            E.set_option("feasible_subspace", 1)
+            assert H.rel_err(out[0], full[0]) < TOL[dtype] * 0.1 and H.rel_err(out[1], full[1]) < TOL[dtype]
+            assert abs(out[2] - full[2]) <= 1e-9 * abs(full[2]) and abs(out[3] - full[3]) <= 1e-9 * abs(full[3])
+
+
+@pytest.mark.parametrize("n,k,pairs", [(20, 7, "full"), (22, 3, "ring"), (34, 2, "chain")])
+def test_xy_compact_register_arbitrary_pairs(n, k, pairs):
+    """compact XY register: non-adjacent pairs (the rank of the partner changes through the set bits in between),
+    long-range ring closure, and n > 32 (64-bit strings) -- against the oracle where numpy can hold it, else against
+    exact invariants (norm, feasible extremes)"""
+    eng, E = _engine(n, "complex64")
+    if pairs == "full":
+        pr = [[i, j] for i in range(0, n, 3) for j in range(i + 2, n, 5)]
+    else:
+        pr = orc.xy_pairs(n, pairs)
+    rng = np.random.default_rng(n)
+    ang = rng.uniform(0, 2 * np.pi, size=4)
+    if n <= 22:
+        Q, c, b = H.random_qubo(n, seed=3)
+        E.set_cost_qubo(Q, c, b)
+        ang[::2] *= 0.05
+        E.set_initial(eng.INIT_DICKE, k)
+        E.set_mixer(eng.MIXER_XY, pairs=pr)
+        out = E.energy(ang)
+        from math import comb
+        assert E.counter("compact_size") == comb(n, k)
+        spec = orc.Spec(n, orc.qubo_diag(Q, c, b), mixer=("xy", pr), init=orc.dicke_state(n, k))
+        _check(out, spec, ang, "complex64", "compact xy %s" % pairs)
+    else:
+        edges = [(i, (i + 1) % n, 1.0) for i in range(n)]
+        E.set_cost_maxkcut(n, edges, 1, np.array([0, 1], dtype=np.uint8))
+        E.set_initial(eng.INIT_DICKE, k)
+        E.set_mixer(eng.MIXER_XY, pairs=pr)
+        out = E.energy(ang)
+        assert abs(out[4] - 1.0) < 1e-5
+        assert out[2] == 2.0 and out[3] == 4.0      # ring, two ones: adjacent (cut 2) or apart (cut 4)
+    E.close()
+
+
+@pytest.mark.parametrize("kind", ["u8", "u32fx"])
+@pytest.mark.parametrize("n,k", [(16, 0), (17, 6), (18, 5)])
+def test_specialised_grover_passes_vs_generic_kernel(n, k, kind):
+    """grover_pass_c64_kernel (16-byte accesses, fixed-point phase reduction) against the generic element-wise kernel
+    (option force_generic) and the oracle: |+> (k = 0), Dicke on the full register, Dicke in the compact register"""
+    eng, E = _engine(n, "complex64")
+    if kind == "u8":
+        edges, colors, table = H.regular_maxcut(n + (n % 2))
+        edges = [e for e in edges if e[0] < n and e[1] < n]
+        lut, _ = H.lut_from_table(table, 1)
+        E.set_cost_maxkcut(n, edges, 1, lut)
+        diag = E.read_cost_diagonal()
+        gs = 1.0
+    else:
+        Q, c, b = H.random_qubo(n, seed=13)
+        E.set_cost_qubo(Q, c, b)
+        diag = orc.qubo_diag(Q, c, b)
+        gs = 0.05
+    if k:
+        E.set_initial(eng.INIT_DICKE, k)
+        E.set_mixer(eng.MIXER_GROVER, sub_kind=eng.INIT_DICKE, sub_k=k)
+        s = orc.dicke_state(n, k)
+    else:
+        E.set_mixer(eng.MIXER_GROVER, sub_kind=eng.INIT_PLUS)
+        s = orc.plus_state(n)
+    spec = orc.Spec(n, diag, mixer=("grover", s), init=s)
+    rng = np.random.default_rng(n + k)
+    for p in (1, 3):
+        ang = rng.uniform(0, 2 * np.pi, size=2 * p)
+        ang[::2] *= gs
+        for fs in ((1, 0) if k else (1,)):
+            E.set_option("feasible_subspace", fs)
+            fast = E.energy(ang)
+            _check(fast, spec, ang, "complex64", "fast grover p=%d fs=%d" % (p, fs))
+            E.set_option("force_generic", 1)
+            slow = E.energy(ang)
+            E.set_option("force_generic", 0)
+            assert H.rel_err(fast[0], slow[0]) < 1e-5 and H.rel_err(fast[1], slow[1]) < 1e-5, (fast, slow)
+            assert fast[2] == slow[2] and fast[3] == slow[3]
+    E.close()
 
 
 @pytest.mark.parametrize("dtype", ["complex64", "complex128"])
