@@ -422,6 +422,7 @@ def config4_leg(device, n=30, p=3, reps=3):
     out = []
 
     def timed(label, kernel, E, ang):
+        E.set_option("time_passes", 1)
         E.energy(ang)
         E.energy(ang)
         E.counter("reset")
@@ -435,6 +436,11 @@ def config4_leg(device, n=30, p=3, reps=3):
         out.append({"case": label, "kernel": kernel, "ms_per_eval": round(m, 3), "launches": int(E.counter("launches") / reps),
                     "algorithmic_gb": round(gb, 3), "achieved_gbs": round(gb / m * 1e3, 1), "frac": round(gb / m * 1e3 / peak, 4),
                     "energy": float(res[0]), "norm": float(res[4])})
+        ps = {PASS_NAMES[i]: (E.counter("pass_ms_%d" % i), E.counter("pass_count_%d" % i), E.counter("pass_bytes_%d" % i))
+              for i in range(len(PASS_NAMES))}
+        if any(v[1] for v in ps.values()):
+            out[-1]["passes"] = {k: {"ms_per_launch": round(v[0] / v[1], 3), "launches_per_eval": v[1] / reps,
+                                     "frac": round(v[2] / v[0] / 1e6 / peak, 4)} for k, v in ps.items() if v[1]}
         E.close()
 
     Qp, cp, bp, k = portfolio_instance(n)
@@ -449,7 +455,7 @@ def config4_leg(device, n=30, p=3, reps=3):
         a = ang2.copy()
         a[0::2] *= 3.0
         timed("Portfolio + Grover(Dicke %d) + Dicke %d, %s" % (k, k, "compact C(n,k) register" if fs else "full 2^n register"),
-              "elementwise_pass_kernel", E, a)
+              "grover_pass_c64_kernel", E, a)
     Q, c = qubo_instance(n)
     E = eng.Engine(n, "complex64", device=device)
     E.set_cost_qubo(Q, c, 0.0)
@@ -463,7 +469,13 @@ def config4_leg(device, n=30, p=3, reps=3):
     E.set_mixer(eng.MIXER_XY, pairs=[[i, (i + 1) % n] for i in range(n)])
     a = ang2.copy()
     a[0::2] *= 0.02
-    timed("QUBO + XY ring + Dicke %d" % k, "xy_tile_kernel", E, a)
+    timed("QUBO + XY ring + Dicke %d, compact C(n,k) register" % k, "xy_compact_gate_kernel", E, a)
+    E = eng.Engine(n, "complex64", device=device)
+    E.set_option("feasible_subspace", 0)
+    E.set_cost_qubo(Q, c, 0.0)
+    E.set_initial(eng.INIT_DICKE, k)
+    E.set_mixer(eng.MIXER_XY, pairs=[[i, (i + 1) % n] for i in range(n)])
+    timed("QUBO + XY ring + Dicke %d, full 2^n register" % k, "xy_tile_kernel", E, a)
     return out
 
 

@@ -183,6 +183,13 @@ int qaoa_shard_pass_is_cross(qaoa_engine_t* h, int pass); /* 1 / 0, -1 on error 
 int qaoa_shard_run_pass(qaoa_engine_t* h, int pass);
 int qaoa_shard_sync(qaoa_engine_t* h);
 int qaoa_shard_finish(qaoa_engine_t* h, double* out5);
+/* Grover mixer on a sharded register (reference qaoa/mixers/grover_mixer.py:43-82 over |+> / |D^n_k>,
+ * dicke_initialstate.py:23-56): no state exchange, one complex scalar per layer.  step = 0 .. p-1 runs layer `step`'s
+ * sweep over the local shard and returns the LOCAL partial <s|v> in out5[0..1]; the caller sums it over the ranks
+ * (all-reduce) and passes the global value as `dot_global` of the next step; step = p applies the last reflection and
+ * returns the raw local statistics {sum p, sum p c, sum p c^2, min c, max c} (combine as for qaoa_shard_finish). */
+int qaoa_shard_grover_step(qaoa_engine_t* h, int step, int p, const double* angles, int n_angles,
+                           const double* dot_global, double* out5);
 
 /* Planner dump (no device needed): the tile plan the engine would build for this configuration, as JSON -- tile shapes,
  * passes, their step programs, which qubit of which layer every butterfly round mixes, which layer's phase separator a

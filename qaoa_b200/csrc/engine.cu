@@ -1481,6 +1481,57 @@ void run_elementwise_point(Engine* h, int p, const double* ang, double* d_out_po
   h->last_z.assign(h->n, 0);
 }
 
+// Grover mixer on a sharded register (no state exchange at all -- one complex scalar per layer crosses the
+// ranks).  The caller steps through the circuit: step d < p runs layer d's sweep over the local shard
+//   v = (d == 0 ? |s> : v + (e^{-i beta_{d-1}} - 1) <s|v>_global s) ; v *= e^{i gamma_d c} ; partial <s|v>
+// and returns the LOCAL partial dot product in out[0..1]; the caller all-reduces it and hands the GLOBAL value back as
+// `dot_global` of the next step.  Step p applies the last reflection and returns the raw local statistics
+// {sum p, sum p c, sum p c^2, min, max} in out[0..4] (combined like the tile path's, qaoa_shard_finish).
+template <typename real>
+void shard_grover_step(Engine* h, int step, int p, const double* ang, const double* dot_global, double* out) {
+  ensure_state(h, 1);
+  const int threads = 256;
+  const int grid = grid_for(h->N, threads);
+  ensure(h->d_partials, h->partials_cap, (size_t)grid * 5 * sizeof(double) * 2);
+  if (!h->d_coefdot) CUDA_OK(cudaMalloc((void**)&h->d_coefdot, 2 * sizeof(double)));
+  double* part_dot = h->d_partials;
+  double* part_red = h->d_partials + (size_t)grid * 5;
+  real* st = (real*)h->state;
+  if (step > 0) {
+    const double beta = ang[2 * (step - 1) + 1];
+    const double kr = cos(beta) - 1.0, ki = -sin(beta);
+    const double cd[2] = {kr * dot_global[0] - ki * dot_global[1], kr * dot_global[1] + ki * dot_global[0]};
+    h2d(h, h->d_coefdot, cd, sizeof(cd));
+  }
+  const bool last = step == p;
+  const int flags = last ? (EW_AXPY | EW_REDUCE) : ((step == 0 ? EW_INIT : EW_AXPY) | EW_PHASE | EW_DOT | EW_STORE);
+  const double gamma = last ? 0.0 : ang[2 * step];
+  const bool fast = sizeof(real) == 4 && !h->force_generic && h->init.kind == h->sub.kind && h->init.k == h->sub.k &&
+      h->init.amp == h->sub.amp && (h->init.kind == INIT_PLUS || h->init.kind == INIT_DICKE) &&
+      (h->dinfo.kind == DIAG_U8 || h->dinfo.kind == DIAG_U32FX);
+  if (!(fast && launch_grover_fast(h, grid, (float2*)st, h->N, flags, h->init, gamma, h->diag, part_dot, part_red)))
+    elementwise_pass_kernel<real><<<grid, threads, 0, h->stream>>>(st, h->N, flags, h->init, h->sub, h->d_coefdot, gamma,
+                                                                  h->diag, h->dinfo, part_dot, part_red);
+  CUDA_OK(cudaGetLastError());
+  h->launches += 1;
+  const double sweep = (double)h->N * h->amp_bytes;
+  h->bytes_alg += (step == 0 ? 0.0 : sweep) + (last ? 0.0 : sweep) + (double)h->N * diag_value_bytes(h->dinfo.kind);
+  if (!last) {
+    DevTmp t_sum(2 * 8);
+    sum_partials_kernel<<<1, 32, 0, h->stream>>>(part_dot, grid, 2, t_sum.as<double>());
+    CUDA_OK(cudaGetLastError());
+    d2h(h, out, t_sum.as<double>(), 2 * 8);
+  } else {
+    std::vector<double> part((size_t)grid * 5);
+    d2h(h, part.data(), part_red, part.size() * 8);
+    out[0] = out[1] = out[2] = 0.0; out[3] = 1e300; out[4] = -1e300;
+    for (int b = 0; b < grid; b++) {
+      out[0] += part[(size_t)b * 5]; out[1] += part[(size_t)b * 5 + 1]; out[2] += part[(size_t)b * 5 + 2];
+      out[3] = std::min(out[3], part[(size_t)b * 5 + 3]); out[4] = std::max(out[4], part[(size_t)b * 5 + 4]);
+    }
+  }
+}
+
 void check_ready(Engine* h, int p, int n_angles) {
   if (h->dinfo.kind == DIAG_NONE) fail("no cost function set");
   if (p < 1) fail("depth p must be >= 1");
@@ -1690,6 +1741,7 @@ void choose_kind(Engine* h, double lo, double hi, bool integer_valued, int* kind
 StateGen make_gen(Engine* h, int kind, int k, const double* vec, void** devvec) {
   StateGen g;
   g.kind = kind; g.k = k; g.vec = nullptr; g.amp = 1.0;
+  g.pc0 = h->world > 1 ? __builtin_popcountll((unsigned long long)h->x0) : 0;
   if (*devvec) { cudaFree(*devvec); *devvec = nullptr; }
   if (kind == INIT_PLUS) g.amp = pow(2.0, -0.5 * h->n);
   else if (kind == INIT_DICKE) {
@@ -2073,7 +2125,9 @@ int qaoa_set_mixer(qaoa_engine_t* h, int kind, const int32_t* pairs, int n_pairs
                    int sub_kind, int sub_k, const double* sub_vec) {
   API_BEGIN(h)
   if (kind < MIXER_X || kind > MIXER_NODE_GROVER) fail("unknown mixer kind");
-  if (h->world > 1 && kind != MIXER_X && kind != MIXER_XMULTI) fail("sharded engine: only the X and multi-angle X mixers are supported");
+  if (h->world > 1 && kind != MIXER_X && kind != MIXER_XMULTI &&
+      !(kind == MIXER_GROVER && !h->ztw_mode && (sub_kind == INIT_PLUS || sub_kind == INIT_DICKE)))
+    fail("sharded engine: the X and multi-angle X mixers, and (full register) the Grover mixer over |+> / Dicke states, are supported");
   if (trotter_steps < 1) fail("trotter_steps must be >= 1");
   invalidate(h);
   h->mixer = kind;
@@ -2521,6 +2575,22 @@ int qaoa_shard_finish(qaoa_engine_t* h, double* out5) {
   CUDA_OK(cudaMemcpyAsync(out5, h->d_out, 5 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CUDA_OK(cudaStreamSynchronize(h->stream));
   harvest_events(h);
+  API_END(h)
+}
+
+int qaoa_shard_grover_step(qaoa_engine_t* h, int step, int p, const double* angles, int n_angles,
+                           const double* dot_global, double* out5) {
+  API_BEGIN(h)
+  if (h->world < 2) fail("not a sharded engine");
+  if (h->mixer != MIXER_GROVER) fail("qaoa_shard_grover_step: the mixer is not the Grover mixer");
+  if (!angles || !out5) fail("null pointer");
+  check_ready(h, p, n_angles);
+  if (step < 0 || step > p) fail("step out of range");
+  if (step > 0 && !dot_global) fail("the global dot product of the previous step is required");
+  if (h->keep_state) fail("sharded engine: keep_state is not supported");
+  if (h->init.kind == INIT_STATEVECTOR || h->sub.kind == INIT_STATEVECTOR) fail("sharded engine: statevector states are not supported");
+  if (h->dtype == QAOA_DTYPE_C64) shard_grover_step<float>(h, step, p, angles, dot_global, out5);
+  else shard_grover_step<double>(h, step, p, angles, dot_global, out5);
   API_END(h)
 }
 

@@ -204,6 +204,7 @@ struct StateGen {
   int k;          // Dicke weight
   double amp;     // 2^{-n/2} or C(n,k)^{-1/2}
   const void* vec;  // S-frame vector for INIT_STATEVECTOR (same element type as the state)
+  int pc0;        // sharded registers: popcount of the rank bits (the basis index is x0 + local index)
 };
 
 template <typename real>
@@ -218,7 +219,7 @@ __device__ __forceinline__ void gen_amp(const StateGen& g, size_t x, real& re, r
     im = (real)0;
     return;
   }
-  int pc = __popcll((unsigned long long)x);
+  int pc = __popcll((unsigned long long)x) + g.pc0;
   re = (real)g.amp;
   im = (real)0;
   if (g.kind == INIT_DICKE && pc != g.k) re = (real)0;
@@ -587,7 +588,7 @@ grover_pass_c64_kernel(float2* __restrict__ st, size_t N, StateGen gen, const do
   float4* st4 = reinterpret_cast<float4*>(st);
 
   auto one = [&](size_t x, float& re, float& im, unsigned k, float& dr, float& di) {
-    const int pc = GK == INIT_UNIFORM ? 0 : __popcll((unsigned long long)x);
+    const int pc = GK == INIT_UNIFORM ? 0 : __popcll((unsigned long long)x) + gen.pc0;
     const bool on = gk_support<GK>(gen, pc);
     if (FLAGS & EW_INIT) {
       re = on ? amp : 0.f;

@@ -1750,6 +1750,21 @@ tile_prog_kernel(const __grid_constant__ TilePass P, Elem* __restrict__ state, s
 #pragma unroll
       for (int j = 0; j < SAMP / 16; j++) dq[j] = __ldg(s4 + stream_chunk(c.tile, c.warp, c.lane, SAMP / 16, j));
     }
+    if constexpr (DK == 0 && ElemTraits<Elem>::IS_C64) {
+      // wide diagonal values (U32FX: 128 bytes per thread and stream) are read where the PHASE / REDUCE step needs
+      // them: pull the NEXT tile's slices into L2 now (one 128-byte line per lane; a warp's slice is contiguous), so
+      // that those loads cost an L2 hit instead of a DRAM round trip in the middle of the tile
+      const unsigned long long nid = id + gridDim.x;
+      if (nid < total) {
+        const unsigned nt = (unsigned)(nid & c.tmask);
+        const int wbytes = NAMP * diag_value_bytes(c.dinfo.kind) * 32;
+        for (int i = 0; i < P.nops; i++) {
+          if (P.ops[i].type != TOP_PHASE && P.ops[i].type != TOP_REDUCE) continue;
+          const char* base = reinterpret_cast<const char*>(P.streams[P.ops[i].arg]) + ((size_t)nt * 16 + c.warp) * wbytes;
+          for (int off = c.lane * 128; off < wbytes; off += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
+        }
+      }
+    }
     ProgExec<Elem, Prog, DK, CROSS, 0>::run(c, v, dq, acc);
   }
   if constexpr (HAS_RED) {

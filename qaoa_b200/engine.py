@@ -90,6 +90,7 @@ def load_library():
         "qaoa_sample": (ctypes.c_int, [H, ctypes.c_int, _c_double_p, ctypes.c_int, ctypes.c_int, _c_double_p, _c_uint64_p]),
         "qaoa_extreme_solutions": (ctypes.c_int, [H, ctypes.c_int, _c_double_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                                   _c_uint64_p, ctypes.POINTER(ctypes.c_int), _c_double_p]),
+        "qaoa_shard_grover_step": (ctypes.c_int, [H, ctypes.c_int, ctypes.c_int, _c_double_p, ctypes.c_int, _c_double_p, _c_double_p]),
         "qaoa_cvar": (ctypes.c_int, [H, ctypes.c_int, _c_double_p, ctypes.c_int, ctypes.c_double, _c_double_p]),
         "qaoa_cost_distribution": (ctypes.c_int, [H, ctypes.c_int, _c_double_p, ctypes.c_int, _c_double_p,
                                                   _c_double_p, _c_double_p]),
@@ -406,6 +407,15 @@ class Engine:
 
     def shard_run_pass(self, i):
         self._check(self._lib.qaoa_shard_run_pass(self._h, int(i)))
+
+    def shard_grover_step(self, step, angles, dot_global=None):
+        """one step of the sharded Grover circuit: (local partial dot) for step < p, raw local statistics for step = p"""
+        angles, p = self._angles(angles)
+        out = np.zeros(5, dtype=np.float64)
+        dg = None if dot_global is None else np.ascontiguousarray(dot_global, dtype=np.float64)
+        self._check(self._lib.qaoa_shard_grover_step(self._h, int(step), p, _dptr(angles), angles.size,
+                                                     _dptr(dg) if dg is not None else None, _dptr(out)))
+        return out[:2].copy() if step < p else out
 
     def shard_sync(self):
         self._check(self._lib.qaoa_shard_sync(self._h))

@@ -98,10 +98,15 @@ class _ShardedSurface:
     def _combine_minmax(self, lo, hi):
         return lo, hi
 
+    mixer_kind = _eng.MIXER_X
+
     def set_mixer(self, kind, *a, **k):
+        if kind == _eng.MIXER_GROVER and getattr(self, "symmetric", False):
+            raise _eng.EngineError("sharded symmetric register: X-type mixers only (use symmetric=False for the Grover mixer)")
         for e in self._engines():
             e.set_mixer(kind, *a, **k)
         self.n_beta = self._engines()[0].n_beta
+        self.mixer_kind = kind
 
     def set_initial(self, kind, *a, **k):
         for e in self._engines():
@@ -142,7 +147,18 @@ class LocalShardGroup(_ShardedSurface):
     def read_cost_diagonal(self):
         return np.concatenate([e.read_cost_diagonal() for e in self.engines])
 
+    def _energy_grover(self, angles):
+        """Grover mixer: no state exchange -- per layer every shard's partial <s|v> is summed and handed back"""
+        angles = np.ascontiguousarray(angles, dtype=np.float64).reshape(-1)
+        p = angles.size // 2
+        dot = None
+        for step in range(p):
+            dot = np.sum([e.shard_grover_step(step, angles, dot) for e in self.engines], axis=0)
+        return combine_partials([e.shard_grover_step(p, angles, dot) for e in self.engines])
+
     def energy(self, angles):
+        if self.mixer_kind == _eng.MIXER_GROVER:
+            return self._energy_grover(angles)
         counts = [e.shard_begin(angles) for e in self.engines]
         assert len(set(counts)) == 1
         self._sync_all()   # (first call: the diagonal streams of every rank are built from peer memory)
@@ -241,8 +257,26 @@ class DistShardedEngine(_ShardedSurface):
         s = sums.cpu().numpy()
         return np.array([s[1] / s[0], s[2] / s[0], float(lo.cpu()[0]), float(hi.cpu()[0]), s[0]])
 
+    def _energy_grover(self, angles):
+        """Grover mixer (grover_mixer.py:43-82): the state never crosses the ranks; per layer ONE complex scalar, the
+        partial <s|v> of every shard, is all-reduced, and the five statistics at the end."""
+        import torch
+
+        dist = self._dist
+        dev = "cuda" if dist.get_backend(self.group) == "nccl" else "cpu"
+        angles = np.ascontiguousarray(angles, dtype=np.float64).reshape(-1)
+        p = angles.size // 2
+        dot = None
+        for step in range(p):
+            t = torch.tensor(self.eng.shard_grover_step(step, angles, dot), dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+            dot = t.cpu().numpy()
+        return self._all_reduce(self.eng.shard_grover_step(p, angles, dot))
+
     def energy(self, angles):
         """(E[cost], E[cost^2], min, max, norm) of the WHOLE register; identical on every rank."""
+        if self.mixer_kind == _eng.MIXER_GROVER:
+            return self._energy_grover(angles)
         eng = self.eng
         n_passes = eng.shard_begin(angles)
         flags = [eng.shard_pass_is_cross(i) for i in range(n_passes)]

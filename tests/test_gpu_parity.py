@@ -203,6 +203,47 @@ def test_xy_compact_register_arbitrary_pairs(n, k, pairs):
     E.close()
 
 
+@pytest.mark.parametrize("case", ["u8-c64", "u32fx-c64", "f64-c128", "u8-c128", "degenerate"])
+def test_device_cvar_weighted_quantile_select(case):
+    """qaoa_cvar (digit-by-digit weighted quantile select over the kept final state) against the host evaluation of
+    the same definition -- mean cost over the best alpha of the probability mass, statistic.py:132-142 in the
+    shots -> infinity limit -- from the device's own |psi|^2 and cost diagonal, and against the oracle's state."""
+    n = 16
+    dtype = "complex128" if case.endswith("c128") else "complex64"
+    eng, E = _engine(n, dtype)
+    if case.startswith("u8") or case == "degenerate":
+        edges, colors, table = H.regular_maxcut(n)
+        lut, _ = H.lut_from_table(table, 1)
+        E.set_cost_maxkcut(n, edges, 1, lut)
+        gs = 1.0
+    else:
+        Q, c, b = H.random_qubo(n, seed=17)
+        E.set_cost_qubo(Q, c, b)
+        gs = 0.05
+    diag = E.read_cost_diagonal()
+    rng = np.random.default_rng(3)
+    ang = rng.uniform(0, 2 * np.pi, size=4)
+    ang[0::2] *= gs
+    if case == "degenerate":
+        ang[:] = 0.0            # uniform distribution over few cost values: the threshold bin is split
+    probs = np.asarray(E.final_probabilities(ang), dtype=np.float64)
+    probs /= probs.sum()
+    order = np.argsort(-diag, kind="stable")
+    cs, ps = diag[order], probs[order]
+    cum = np.cumsum(ps)
+    psi = orc.evolve(orc.Spec(n, diag), ang)
+    for alpha in (1.0, 0.5, 0.1, 0.013, 1e-4):
+        take = np.clip(alpha - (cum - ps), 0.0, ps)
+        want = float(take @ cs) / alpha
+        got = E.cvar(ang, alpha)
+        tol = 1e-9 if dtype == "complex128" else 2e-5
+        assert abs(got - want) <= tol * max(1.0, abs(want)), (case, alpha, got, want)
+        wo = orc.exact_cvar(diag, np.abs(psi) ** 2, alpha)
+        assert abs(got - wo) <= (1e-8 if dtype == "complex128" else 1e-4) * max(1.0, abs(wo)), (case, alpha, got, wo)
+    assert abs(E.cvar(ang, 1.0) - E.energy(ang)[0]) <= (1e-9 if dtype == "complex128" else 1e-5) * abs(E.energy(ang)[0]) + 1e-9
+    E.close()
+
+
 @pytest.mark.parametrize("kind", ["u8", "u32fx"])
 @pytest.mark.parametrize("n,k", [(16, 0), (17, 6), (18, 5)])
 def test_specialised_grover_passes_vs_generic_kernel(n, k, kind):

@@ -53,6 +53,48 @@ def test_sharded_energy_matches_oracle_and_single_engine(n, world, dtype):
     grp.close()
 
 
+@pytest.mark.parametrize("dtype", ["complex64", "complex128"])
+@pytest.mark.parametrize("n,world,k", [(18, 2, 6), (20, 4, 0), (21, 8, 5)])
+def test_sharded_grover_mixer(n, world, k, dtype):
+    """Grover mixer on a sharded register (qaoa_shard_grover_step): |s> = Dicke(k) (k > 0) or |+>, generated per shard
+    with the global popcount; the only cross-rank traffic is the partial dot product of every layer.  Against the C
+    oracle and the single engine's full-register path."""
+    from oracle import c_oracle
+    from qaoa_b200 import engine as eng
+    from qaoa_b200.sharded import LocalShardGroup
+
+    Q, c, b = H.random_qubo(n, seed=n)
+    grp = LocalShardGroup(n, world, dtype=dtype)
+    grp.set_cost_qubo(Q, c, b)
+    single = eng.Engine(n, dtype=dtype)
+    single.set_option("feasible_subspace", 0)
+    single.set_cost_qubo(Q, c, b)
+    if k:
+        for E in (grp, single):
+            E.set_initial(eng.INIT_DICKE, k)
+            E.set_mixer(eng.MIXER_GROVER, sub_kind=eng.INIT_DICKE, sub_k=k)
+        st = ("dicke", k)
+    else:
+        for E in (grp, single):
+            E.set_mixer(eng.MIXER_GROVER, sub_kind=eng.INIT_PLUS)
+        st = ("plus", 0)
+    diag = c_oracle.qubo_diag(Q, c, b)
+    rng = np.random.default_rng(5)
+    for p in (1, 3):
+        ang = rng.uniform(0, 2 * np.pi, size=2 * p)
+        ang[0::2] *= 0.05
+        ref = c_oracle.run(n, diag, ang, "complex128", mixer="grover", init=st, sub=st)
+        got = grp.energy(ang)
+        one = single.energy(ang)
+        tol = TOL[dtype]
+        assert H.rel_err(got[0], ref[0]) < tol and H.rel_err(got[1], ref[1]) < 2 * tol, (p, got, ref)
+        assert abs(got[2] - ref[2]) <= 1e-6 * abs(ref[2]) and abs(got[3] - ref[3]) <= 1e-6 * abs(ref[3]), (got, ref)
+        assert abs(got[4] - 1) < (1e-4 if dtype == "complex64" else 1e-11)
+        assert H.rel_err(got[0], one[0]) < tol * 0.1, (got, one)
+    grp.close()
+    single.close()
+
+
 def test_sharded_multiangle_dicke_and_cot_form():
     """Per-qubit betas follow the logical qubit across the shard boundary; Dicke initial state generated
     per shard with the global popcount; beta = pi/2 exercises the interpreter's cross variant."""
