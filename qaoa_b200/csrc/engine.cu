@@ -158,6 +158,7 @@ struct Engine {
   double* d_params = nullptr; size_t params_cap = 0;   // [tau block (real)][phs block (double)]
   double* h_params = nullptr; size_t hparams_cap = 0;
   int force_generic = 0;
+  int layer_budget = 1;       // multi-angle mixers: normal form whenever the LAYER's total growth fits (fill_point_params)
   int prefetch_dist = 0;     // extra L2 prefetch distance in tiles (0 = off)
   int persistent_ctas = 148; // CTAs of the persistent pass kernels (one per SM)
   int low_bits = 0;          // 0: automatic choice between 4 and 5 low tile bits
@@ -959,6 +960,22 @@ void fill_point_params(Engine* h, const Plan& pl, const double* ang, double* tau
   std::vector<int> sgnS(p, 1);
   const double tmax = tmax_normal_form(h);
   if (pass_all_normal) pass_all_normal->assign(pl.passes.size(), 1);
+  // The fixed bound tmax assumes EVERY qubit of the layer rotates by the same angle (plain X mixer).  With per-qubit
+  // angles (XMultiAngle / XOrbit) a few angles near pi/2 are common, and what has to stay inside the exponent range is
+  // the layer's TOTAL growth sum_q -log2|cos beta_q|: when that fits the budget every qubit of the layer keeps the
+  // normal (lifted) form -- no cot form, no interpreter passes -- however large a single |tan beta_q| is.
+  std::vector<char> layer_fits(p, 0);
+  if (h->mixer == MIXER_XMULTI && h->layer_budget) {
+    const double budget_bits = 0.5 * (h->dtype == QAOA_DTYPE_C64 ? 340.0 : 1800.0);
+    for (int d = 0; d < p; d++) {
+      double bits = 0.0;
+      for (int q = 0; q < h->n; q++) {
+        const double c = fabs(cos(beta_of(h, ang, d, q)));
+        bits += c > 1e-280 ? -log2(c) : 1e9;
+      }
+      layer_fits[d] = bits <= budget_bits;
+    }
+  }
   for (size_t ip = 0; ip < pl.passes.size(); ip++) {
     const auto& pp = pl.passes[ip];
     double* base = tau + pp.tau_offset;
@@ -976,7 +993,7 @@ void fill_point_params(Engine* h, const Plan& pl, const double* ang, double* tau
         // (|tan| <= 1: no cot form -- the reference's default grids hit beta = pi/2 exactly --, least scaling).
         if (pl.z2 && h->mixer == MIXER_X) beta -= 1.5707963267948966 * nearbyint(beta / 1.5707963267948966);
         const double c = cos(beta), sn = sin(beta);
-        if (fabs(sn) <= tmax * fabs(c)) {   // normal form: c * [[1, t], [-t, 1]]
+        if (layer_fits[rs.layer] || fabs(sn) <= tmax * fabs(c)) {   // normal form: c * [[1, t], [-t, 1]]
           const double t = sn / c;
           rp[s] = t;
           rp[5 + s] = -t;
@@ -1866,6 +1883,7 @@ int qaoa_set_option(qaoa_engine_t* h, const char* key, double value) {
   else if (k == "batch_points") h->batch_points = (int)value;
   else if (k == "batch_bytes") h->batch_bytes = (size_t)value;
   else if (k == "force_generic") h->force_generic = value != 0;
+  else if (k == "layer_budget") h->layer_budget = value != 0;
   else if (k == "prefetch_dist") h->prefetch_dist = (int)value;
   else if (k == "persistent_ctas") h->persistent_ctas = std::max(1, (int)value);
   else if (k == "time_passes") h->time_passes = value != 0;

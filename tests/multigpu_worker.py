@@ -34,7 +34,7 @@ def closed_form_p1(n, edges, gamma, beta):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, default=26)
+    ap.add_argument("--qubits", dest="n", type=int, default=26)   # ("--n" is ambiguous to torchrun's own parser)
     ap.add_argument("--dtype", default="complex64")
     args = ap.parse_args()
 

@@ -22,7 +22,7 @@ def _gpus():
 def _run(world, n, dtype, port):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
            "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(HERE, "multigpu_worker.py"),
-           "--n", str(n), "--dtype", dtype]
+           "--qubits", str(n), "--dtype", dtype]
     proc = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     rep = None
     for line in proc.stdout.splitlines():

@@ -203,6 +203,37 @@ def test_xy_compact_register_arbitrary_pairs(n, k, pairs):
     E.close()
 
 
+@pytest.mark.parametrize("dtype", ["complex64", "complex128"])
+def test_multiangle_angles_near_half_pi_stay_on_the_compiled_programs(dtype):
+    """Multi-angle X mixer with single betas at and next to pi/2 (|tan beta| up to 1e16): the layer's total growth fits the
+    exponent budget, so every qubit keeps the lifted normal form and no pass falls back to the interpreter kernel
+    (option layer_budget, default on); with the option off the same angles take the cot form on the interpreter."""
+    n = 18
+    eng, E = _engine(n, dtype)
+    Q, c, b = H.random_qubo(n, seed=2)
+    E.set_cost_qubo(Q, c, b)
+    E.set_mixer(eng.MIXER_XMULTI)
+    spec = orc.Spec(n, orc.qubo_diag(Q, c, b), mixer=("xmulti",))
+    rng = np.random.default_rng(8)
+    ang = rng.uniform(-1.0, 1.0, size=3 * (1 + n))
+    ang[0::1 + n] *= 0.05
+    ang[1 + 3] = np.pi / 2                 # layer 0, qubit 3: exactly pi/2
+    ang[(1 + n) + 1 + 17] = np.pi / 2 + 1e-9    # layer 1, top qubit
+    ang[2 * (1 + n) + 1 + 9] = -np.pi / 2 + 3e-5
+    ref = orc.energy(spec, ang)
+    E.counter("reset")
+    fast = E.energy(ang)
+    assert E.counter("prog_launches") == E.counter("launches") - 2 or E.counter("prog_launches") >= 3   # compiled programs only
+    all_prog = E.counter("prog_launches")
+    _check(fast, spec, ang, dtype, "layer budget", ref=ref)
+    E.set_option("layer_budget", 0)
+    E.counter("reset")
+    slow = E.energy(ang)
+    assert E.counter("prog_launches") < all_prog       # some passes needed the interpreter (cot form)
+    _check(slow, spec, ang, dtype, "cot form", ref=ref)
+    E.close()
+
+
 @pytest.mark.parametrize("case", ["u8-c64", "u32fx-c64", "f64-c128", "u8-c128", "degenerate"])
 def test_device_cvar_weighted_quantile_select(case):
     """qaoa_cvar (digit-by-digit weighted quantile select over the kept final state) against the host evaluation of
