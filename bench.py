@@ -302,7 +302,7 @@ def sharded_leg(n, p, sym, steps, warmup, local_rank, world, dist, torch, oracle
                   "gbs_per_direction": round(per_dir / (ms * 1e-3) / 1e9, 1), "peer_copy_reference_gbs": 770.0}
     res = {"n": n, "p": p, "gpus": world, "register": "symmetric half, twisted shards" if sym else "full",
            "stored_gib_per_gpu": shard_bytes / 2 ** 30, "ms_per_eval": round(ms_wall, 3), "kernels_ms": round(ms_kernels, 3),
-           "cross_pass_ms": round(cross_ms, 3), "launches": int(launches), "energy": float(-out[0]), "norm": float(out[4]),
+           "cross_pass_ms": round(cross_ms, 3), "launches": int(launches), "pipeline_chunks": int(getattr(E, "last_chunks", 1)), "energy": float(-out[0]), "norm": float(out[4]),
            "p1_check": {"engine": float(got1), "closed_form": float(cf), "rel_err": float(abs(got1 - cf) / abs(cf))},
            "dominant_local_pass": {"kernel": "tile_prog_kernel<Prog%s>" % dom, "ms_per_launch": round(d_ms / d_cnt, 3),
                                    "achieved_gbs": round(achieved, 1), "frac": round(achieved / peak, 4)},
@@ -389,7 +389,7 @@ def run_multi(args, rank, world, local_rank):
                          "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
                          "launches_timed": int(d_cnt), "ms_per_launch": d_ms / d_cnt,
                          "note": "dominant LOCAL (HBM-bound) pass on rank 0; the cross passes are NVLink-bound: see sharded.nvlink"},
-            "sharded": {k: head[k] for k in ("kernels_ms", "cross_pass_ms", "nvlink", "passes_ms")},
+            "sharded": {k: head[k] for k in ("kernels_ms", "cross_pass_ms", "pipeline_chunks", "nvlink", "passes_ms")},
         }
         if config5 is not None:
             line["config5"] = config5

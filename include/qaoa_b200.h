@@ -183,6 +183,19 @@ int qaoa_shard_pass_is_cross(qaoa_engine_t* h, int pass); /* 1 / 0, -1 on error 
 int qaoa_shard_run_pass(qaoa_engine_t* h, int pass);
 int qaoa_shard_sync(qaoa_engine_t* h);
 int qaoa_shard_finish(qaoa_engine_t* h, double* out5);
+/* Stream-ordered variants (no host synchronisation inside an evaluation): qaoa_get_stream returns the engine's
+ * cudaStream_t so that the caller can enqueue its cross-rank barrier (an NCCL collective) between two passes on that
+ * stream; qaoa_shard_finish_device leaves the five raw partial sums in device memory (d_out5: device pointer). */
+int qaoa_get_stream(qaoa_engine_t* h, unsigned long long* stream_out);
+int qaoa_shard_finish_device(qaoa_engine_t* h, double* d_out5);
+/* Chunk pipeline of a sharded evaluation: between qaoa_shard_begin and qaoa_shard_finish a pass flagged
+ * closed[i] may be launched chunk by chunk (chunk = 0 .. n_chunks-1; chunk < 0: the whole pass) on the engine's main
+ * (which_stream 0) or side stream (1) with `ctas` persistent CTAs (0 = one per SM).  Chunks are sets of local indices no
+ * closed pass couples, so the cross pass of chunk c (few SMs, NVLink-bound) can run beside the local passes of chunk
+ * c+1; the caller orders the two streams and the cross-rank barriers (qaoa_get_stream / qaoa_get_stream2). */
+int qaoa_shard_chunk_info(qaoa_engine_t* h, int* n_chunks, int* closed, int cap);
+int qaoa_shard_run_pass_chunk(qaoa_engine_t* h, int pass, int chunk, int which_stream, int ctas);
+int qaoa_get_stream2(qaoa_engine_t* h, unsigned long long* stream_out);
 /* Grover mixer on a sharded register (reference qaoa/mixers/grover_mixer.py:43-82 over |+> / |D^n_k>,
  * dicke_initialstate.py:23-56): no state exchange, one complex scalar per layer.  step = 0 .. p-1 runs layer `step`'s
  * sweep over the local shard and returns the LOCAL partial <s|v> in out5[0..1]; the caller sums it over the ranks

@@ -71,6 +71,7 @@ struct PlanPass {
   bool cross = false;
   bool zshape = false;    // pass over the low tile shape of a symmetric register (virtual tile bit 13)
   int shape_index = 0;    // Plan::shapes entry this pass tiles over
+  bool chunk_closed = false;   // the pass never couples two chunks of the chunk pipeline (plan_chunks)
 };
 struct Shape {
   int pos[TILE_BITS];
@@ -86,6 +87,9 @@ struct Plan {
   size_t phs_per_point = 0;  // doubles over all passes
   bool z2 = false;           // symmetric register: 2^(n-1) stored amplitudes (tile_kernel.cuh)
   int kx = 0;                // sharded registers: local bits carried by the cross tile (build_plan)
+  // chunk pipeline (sharded registers, plan_chunks): 2^ch_m chunks, chunk bits u / v_i (element bits), the one local
+  // shape that mixes them (every pass over another shape is chunk-closed)
+  int ch_m = 0, ch_u = -1, ch_v[2] = {-1, -1}, ch_open_shape = -1;
 };
 
 struct Engine {
@@ -102,6 +106,11 @@ struct Engine {
   bool peers_state_set = false, peers_diag_set = false;
   size_t amp_bytes = 8;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;      // side stream of the chunk pipeline (cross passes)
+  // overrides of the launch in flight (tile_launch_pass_chunk): stream, persistent CTAs, chunk
+  cudaStream_t cur_stream = nullptr;
+  int cur_ctas = 0, cur_ch_c = -1;
+  int chunking = 1;                    // option "chunk_pipeline"
 
   // state storage: `state_points` consecutive registers
   void* state = nullptr;
@@ -918,10 +927,14 @@ void* get_stream(Engine* h, const Plan& pl, int shape, int frame) {
   return s;
 }
 
+void plan_chunks(Engine* h, Plan& pl);
+void set_chunk_fields(const Plan& pl, PlanPass& pp, int c);
+
 Plan& get_plan(Engine* h, int p) {
   auto it = h->plans.find(p);
   if (it != h->plans.end()) return it->second;
   Plan pl = build_plan(h, p);
+  plan_chunks(h, pl);
   // attach the diagonal streams
   for (auto& pp : pl.passes) {
     for (size_t j = 0; j < pp.phases.size(); j++)
@@ -1047,6 +1060,8 @@ int launch_pass(Engine* h, const PlanPass& pp, bool use_prog, unsigned ntiles, i
   tilepass_set_offsets(tp);
   tp.prefetch_dist = h->prefetch_dist;
   shard_fill(h, tp, pp.cross);
+  cudaStream_t lstream = h->cur_stream ? h->cur_stream : h->stream;
+  const int lctas = h->cur_ctas > 0 ? h->cur_ctas : h->persistent_ctas;
   int prog = use_prog ? pp.prog : PROG_GENERIC;
   const bool cross = pp.cross;
   // cross passes have compiled programs for the high-tile passes of the balanced schedule only
@@ -1065,15 +1080,19 @@ int launch_pass(Engine* h, const PlanPass& pp, bool use_prog, unsigned ntiles, i
     tp.prefetch_dist = 0;
     // interpreter walks tiles of ONE point per launch row; use a flat grid over (point, tile)
     dim3 grid((unsigned)std::min<unsigned long long>((unsigned long long)ntiles * B, 0x7fffffffull));
-    kernel<<<grid, TILE_THREADS, TILE_SMEM_BYTES, h->stream>>>(tp, (Elem*)h->state, point_stride_elems, (const real*)d_tau,
-                                                               d_phs, h->d_tables, tables_per_point, h->dinfo, h->d_partials);
+    kernel<<<grid, TILE_THREADS, TILE_SMEM_BYTES, lstream>>>(tp, (Elem*)h->state, point_stride_elems, (const real*)d_tau,
+                                                             d_phs, h->d_tables, tables_per_point, h->dinfo, h->d_partials);
   };
   auto go = [&](auto kernel) {
     CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TileSmem<Elem>::TOTAL));
     const unsigned long long total = (unsigned long long)ntiles * B;
-    dim3 grid((unsigned)std::min<unsigned long long>(total, (unsigned long long)h->persistent_ctas));
+    dim3 grid((unsigned)std::min<unsigned long long>(total, (unsigned long long)lctas));
     nparts = (int)grid.x;
-    kernel<<<grid, TILE_THREADS, TileSmem<Elem>::TOTAL, h->stream>>>(tp, (Elem*)h->state, point_stride_elems,
+    if (tp.ch_m > 0) {   // chunked launch: every chunk owns `grid` consecutive partial-result slots
+      tp.ch_part0 = tp.ch_c * (int)grid.x;
+      nparts = (int)grid.x << tp.ch_m;
+    }
+    kernel<<<grid, TILE_THREADS, TileSmem<Elem>::TOTAL, lstream>>>(tp, (Elem*)h->state, point_stride_elems,
                                                                       (const real*)d_tau, d_phs, h->d_tables,
                                                                       tables_per_point, h->dinfo, h->d_partials, (unsigned)B);
   };
@@ -1183,6 +1202,98 @@ void tile_prepare(Engine* h, Plan& pl, const double* angles, int n_angles, int B
   }
 }
 
+// position of element bit e in the tile index of a shape (tiles enumerate the shape's free bits in ascending order)
+static int tile_index_pos(const Shape& sh, int e) {
+  int k = 0;
+  for (int f : sh.freepos) { if (f == e) return k; if (f < e) k++; }
+  return -1;
+}
+
+// fills the chunk fields of a pass' TilePass for chunk c (plan_chunks chose the bits)
+void set_chunk_fields(const Plan& pl, PlanPass& pp, int c) {
+  const Shape& sh = pl.shapes[pp.shape_index];
+  TilePass& tp = pp.tp;
+  tp.ch_m = pl.ch_m; tp.ch_c = c; tp.ch_part0 = 0;
+  tp.ch_pu = tile_index_pos(sh, pl.ch_u);
+  for (int i = 0; i < pl.ch_m; i++) tp.ch_pv[i] = tile_index_pos(sh, pl.ch_v[i]);
+  if (tp.ch_pu < 0) fail("chunk pipeline: chunk bit is not a free bit of the shape");
+  for (int i = 0; i < pl.ch_m; i++) if (tp.ch_pv[i] < 0) fail("chunk pipeline: chunk bit is not a free bit of the shape");
+}
+
+// Chunk pipeline of sharded registers.  The cross passes are NVLink-bound and need few SMs (24 CTAs keep the links
+// busy, scripts/cross_ctas.py), the local passes are HBM / issue bound; they can run side by side if they touch
+// disjoint data.  Pick three local element bits u, v0, v1 that exactly ONE local shape mixes (the "open" shape), that
+// are free bits of every other shape and below the bits that deal the cross tiles out over the ranks: the four sets
+// {z : z[v0]^z[u] = c0, z[v1]^z[u] = c1} are closed under every other pass -- the low tile's mirror pairing included,
+// which complements all three bits -- so chunk c's cross pass may run while chunk c+1 is still in its local passes.
+void plan_chunks(Engine* h, Plan& pl) {
+  pl.ch_m = 0;
+  if (h->world < 2 || !h->chunking) return;
+  const int EL = plan_el(h, pl);
+  const int m = (int)pl.shapes.size();
+  int cross_shape = -1;
+  for (int i = 0; i < m; i++) if (pl.shapes[i].cross) cross_shape = i;
+  if (cross_shape < 0) return;
+  // bits that deal the cross tiles out over the ranks: the top gbits free bits of the cross shape
+  const auto& xf = pl.shapes[cross_shape].freepos;
+  std::vector<int> owner(EL, -1), count(EL, 0);
+  for (int i = 0; i < m; i++)
+    for (int j = 0; j < TILE_BITS; j++) {
+      const int e = pl.shapes[i].pos[j];
+      if (e >= 0 && e < EL) { count[e]++; owner[e] = i; }
+    }
+  std::vector<std::vector<int>> excl(m);
+  for (int e = h->qshift; e < EL; e++) {
+    if (count[e] != 1) continue;
+    const int o = owner[e];
+    if (pl.shapes[o].cross || pl.shapes[o].zshape) continue;
+    const int px = tile_index_pos(pl.shapes[cross_shape], e);
+    if (px < 0 || px >= (int)xf.size() - h->gbits) continue;
+    bool free_everywhere = true;
+    for (int i = 0; i < m; i++) if (i != o && tile_index_pos(pl.shapes[i], e) < 0) free_everywhere = false;
+    if (free_everywhere) excl[o].push_back(e);
+  }
+  // the open shape: preferably the local BOUNDARY shape (its passes carry a phase step and cannot move inside their
+  // layer anyway; the phase-free passes of the other shapes can be placed next to the cross passes)
+  int best = -1;
+  for (const auto& pp : pl.passes)
+    if (!pp.cross && !pp.zshape && !pp.phases.empty() && pp.tp.ops[0].type == TOP_LOAD && excl[pp.shape_index].size() >= 2) {
+      best = pp.shape_index;
+      break;
+    }
+  if (best < 0)
+    for (int i = 0; i < m; i++) if (excl[i].size() >= 2 && (best < 0 || excl[i].size() > excl[best].size())) best = i;
+  if (best < 0) return;
+  // every pass over another shape must be a compiled-program pass candidate; passes over the open shape stay whole
+  const auto& b = excl[best];
+  pl.ch_open_shape = best;
+  pl.ch_m = b.size() >= 3 ? 2 : 1;
+  pl.ch_u = b[b.size() - 1];
+  pl.ch_v[0] = b[b.size() - 2];
+  pl.ch_v[1] = pl.ch_m == 2 ? b[b.size() - 3] : -1;
+  if (pl.ch_m == 2 && pl.ch_v[0] > pl.ch_v[1]) std::swap(pl.ch_v[0], pl.ch_v[1]);   // ascending tile-index positions
+  // chunked launches exist for the compiled-program kernels only (launch_pass sends a cross pass without a BOUNDX /
+  // FINALX program, or any pass without a program, to the interpreter kernel, which walks whole passes)
+  for (auto& pp : pl.passes) {
+    const bool xprog = pp.prog == PROG_BOUNDX || pp.prog == PROG_FINALX;
+    pp.chunk_closed = pp.shape_index != best && pp.prog != PROG_GENERIC && (pp.cross ? xprog : !xprog);
+  }
+  // layer 0: the open shape's pass goes BEFORE the closed pass that precedes the first cross pass (same layer, no
+  // phase in between: the two commute), so that a closed pass sits right before the cross pass and can be pipelined
+  for (size_t i = 0; i + 2 < pl.passes.size(); i++) {
+    auto &a = pl.passes[i], &o = pl.passes[i + 1], &x = pl.passes[i + 2];
+    if (!x.cross || a.cross || o.cross || !a.chunk_closed || o.chunk_closed) continue;
+    if (!a.phases.empty() || !o.phases.empty() || a.has_reduce || o.has_reduce) continue;
+    if (a.tp.ops[0].type != TOP_LOAD || o.tp.ops[0].type != TOP_LOAD) continue;
+    bool same = true;
+    const int L = a.rounds.empty() ? -1 : a.rounds[0].layer;
+    for (auto& r : a.rounds) if (r.layer != L) same = false;
+    for (auto& r : o.rounds) if (r.layer != L) same = false;
+    if (same && L >= 0) std::swap(pl.passes[i], pl.passes[i + 1]);
+    break;
+  }
+}
+
 void tile_launch_pass(Engine* h, size_t ip) {
   Engine::EvalCtx& ev = h->ev;
   if (!ev.pl || ip >= ev.pl->passes.size()) fail("no evaluation in flight / pass index out of range");
@@ -1199,8 +1310,14 @@ void tile_launch_pass(Engine* h, size_t ip) {
   const void* d_tau = db + ev.tbase[ip] * rsz;
   const double* d_phs = (const double*)(db + ev.tau_bytes) + ev.pbase[ip];
   bool reads = pp.tp.ops[0].type == TOP_LOAD, writes = pp.tp.ops[pp.tp.nops - 1].type == TOP_STORE;
-  const double pass_bytes = (double)Bc * (double)amps * h->amp_bytes * ((reads ? 1 : 0) + (writes ? 1 : 0)) +
-      (double)Bc * (double)amps * diag_value_bytes(h->dinfo.kind) * (pp.phases.size() + (pp.has_reduce ? 1 : 0));
+  const int chm = h->cur_ch_c >= 0 ? pl.ch_m : 0;
+  if (chm > 0) {
+    if (!pp.chunk_closed || !use_prog) fail("chunked launch of a pass that couples chunks / needs the interpreter kernel");
+    set_chunk_fields(pl, pp, h->cur_ch_c);
+  } else pp.tp.ch_m = 0;
+  cudaStream_t lstream = h->cur_stream ? h->cur_stream : h->stream;
+  const double pass_bytes = ((double)Bc * (double)amps * h->amp_bytes * ((reads ? 1 : 0) + (writes ? 1 : 0)) +
+      (double)Bc * (double)amps * diag_value_bytes(h->dinfo.kind) * (pp.phases.size() + (pp.has_reduce ? 1 : 0))) / (double)(1 << chm);
   size_t evi = 0;
   if (h->time_passes) {
     evi = h->ev_pending.size();
@@ -1210,13 +1327,13 @@ void tile_launch_pass(Engine* h, size_t ip) {
       CUDA_OK(cudaEventCreate(&b));
       h->ev_pool.push_back({a, b});
     }
-    CUDA_OK(cudaEventRecord(h->ev_pool[evi].first, h->stream));
+    CUDA_OK(cudaEventRecord(h->ev_pool[evi].first, lstream));
   }
-  const int np = c64 ? launch_pass<float2>(h, pp, use_prog, ntiles, Bc, point_stride_elems, d_tau, d_phs, p)
-                     : launch_pass<double>(h, pp, use_prog, ntiles, Bc, point_stride_elems, d_tau, d_phs, p);
+  const int np = c64 ? launch_pass<float2>(h, pp, use_prog, ntiles >> chm, Bc, point_stride_elems, d_tau, d_phs, p)
+                     : launch_pass<double>(h, pp, use_prog, ntiles >> chm, Bc, point_stride_elems, d_tau, d_phs, p);
   if (pp.has_reduce) ev.nparts = np;
   if (h->time_passes) {
-    CUDA_OK(cudaEventRecord(h->ev_pool[evi].second, h->stream));
+    CUDA_OK(cudaEventRecord(h->ev_pool[evi].second, lstream));
     h->ev_pending.push_back({use_prog ? pp.prog : (int)PROG_GENERIC, evi, pass_bytes});
   }
   h->launches += 1;
@@ -1867,6 +1984,7 @@ int qaoa_destroy(qaoa_engine_t* h) {
   if (h->h_params) cudaFreeHost(h->h_params);
   if (h->h_out) cudaFreeHost(h->h_out);
   cudaStreamDestroy(h->stream);
+  if (h->stream2) cudaStreamDestroy(h->stream2);
   delete h;
   return 0;
 }
@@ -1884,6 +2002,7 @@ int qaoa_set_option(qaoa_engine_t* h, const char* key, double value) {
   else if (k == "batch_bytes") h->batch_bytes = (size_t)value;
   else if (k == "force_generic") h->force_generic = value != 0;
   else if (k == "layer_budget") h->layer_budget = value != 0;
+  else if (k == "chunk_pipeline") { h->chunking = value != 0; invalidate(h); }
   else if (k == "prefetch_dist") h->prefetch_dist = (int)value;
   else if (k == "persistent_ctas") h->persistent_ctas = std::max(1, (int)value);
   else if (k == "time_passes") h->time_passes = value != 0;
@@ -2577,9 +2696,67 @@ int qaoa_shard_run_pass(qaoa_engine_t* h, int pass) {
   API_END(h)
 }
 
+// the CUDA stream every launch of this engine goes to (cudaStream_t as an integer): lets the caller order its own
+// stream work -- e.g. an NCCL collective standing in for a cross-rank barrier -- between two passes without a host sync
+int qaoa_get_stream(qaoa_engine_t* h, unsigned long long* out) {
+  API_BEGIN(h)
+  if (!out) fail("null output");
+  *out = (unsigned long long)(uintptr_t)h->stream;
+  API_END(h)
+}
+
+// qaoa_shard_finish without the device -> host copy: the five raw partial sums stay on the device (d_out5 is a device
+// pointer owned by the caller, e.g. a torch tensor that goes straight into an all-gather)
+int qaoa_shard_finish_device(qaoa_engine_t* h, double* d_out5) {
+  API_BEGIN(h)
+  if (h->world < 2) fail("not a sharded engine");
+  if (!d_out5) fail("null output");
+  tile_finalize(h, d_out5, true);
+  API_END(h)
+}
+
+// ---- chunk pipeline (plan_chunks): the caller overlaps the cross pass of one chunk with the local passes of another
+// n_chunks: 1 = this plan has no chunks; closed[i] = 1 if pass i may be launched chunk by chunk
+int qaoa_shard_chunk_info(qaoa_engine_t* h, int* n_chunks, int* closed, int cap) {
+  API_BEGIN(h)
+  if (!h->ev.pl) fail("no evaluation in flight");
+  const Plan& pl = *h->ev.pl;
+  bool ok = pl.ch_m > 0 && !h->force_generic;
+  for (size_t i = 0; i < pl.passes.size(); i++)
+    if (pl.passes[i].chunk_closed && !h->ev.all_normal[i]) ok = false;   // a cot-form pass needs the interpreter: no chunks
+  if (n_chunks) *n_chunks = ok ? (1 << pl.ch_m) : 1;
+  if (closed)
+    for (int i = 0; i < cap && i < (int)pl.passes.size(); i++) closed[i] = ok && pl.passes[i].chunk_closed ? 1 : 0;
+  API_END(h)
+}
+
+// which_stream: 0 = the engine's main stream, 1 = its side stream; ctas: persistent CTAs of this launch (0 = default)
+int qaoa_shard_run_pass_chunk(qaoa_engine_t* h, int pass, int chunk, int which_stream, int ctas) {
+  API_BEGIN(h)
+  if (h->world < 2) fail("not a sharded engine");
+  if (!h->ev.pl) fail("no evaluation in flight");
+  if (chunk >= (1 << h->ev.pl->ch_m)) fail("chunk index out of range");
+  if (which_stream == 1 && !h->stream2) CUDA_OK(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+  h->cur_stream = which_stream == 1 ? h->stream2 : h->stream;
+  h->cur_ctas = ctas;
+  h->cur_ch_c = chunk;     // < 0: the whole pass
+  try { tile_launch_pass(h, (size_t)pass); } catch (...) { h->cur_stream = nullptr; h->cur_ctas = 0; h->cur_ch_c = -1; throw; }
+  h->cur_stream = nullptr; h->cur_ctas = 0; h->cur_ch_c = -1;
+  API_END(h)
+}
+
+int qaoa_get_stream2(qaoa_engine_t* h, unsigned long long* out) {
+  API_BEGIN(h)
+  if (!out) fail("null output");
+  if (!h->stream2) CUDA_OK(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+  *out = (unsigned long long)(uintptr_t)h->stream2;
+  API_END(h)
+}
+
 int qaoa_shard_sync(qaoa_engine_t* h) {
   API_BEGIN(h)
   CUDA_OK(cudaStreamSynchronize(h->stream));
+  if (h->stream2) CUDA_OK(cudaStreamSynchronize(h->stream2));
   harvest_events(h);
   API_END(h)
 }
@@ -2648,12 +2825,17 @@ int qaoa_debug_plan(int n_qubits, int dtype, int rank, int world, int symmetric,
     }
     if (world > 1) h->peers_state_set = true;
     Plan pl = build_plan(h, p);
+    h->chunking = (options & 64) ? 0 : 1;
+    plan_chunks(h, pl);
     static const char* names[] = {"Generic", "FirstInit", "FirstLoad", "Interior", "Boundary", "Final", "Mid", "Bound2",
                                   "Final2", "BoundX", "FinalX", "Bound2L4", "Final2L4"};
     std::string js = "{";
     js += "\"z2\": " + std::string(pl.z2 ? "true" : "false") + ", \"kx\": " + std::to_string(pl.kx) +
           ", \"el\": " + std::to_string(plan_el(h, pl)) + ", \"qshift\": " + std::to_string(h->qshift) +
-          ", \"E\": " + std::to_string(h->E) + ", \"shapes\": [";
+          ", \"E\": " + std::to_string(h->E) + ", \"gbits\": " + std::to_string(h->gbits) +
+          ", \"chunks\": {\"m\": " + std::to_string(pl.ch_m) + ", \"u\": " + std::to_string(pl.ch_u) + ", \"v\": [" +
+          std::to_string(pl.ch_v[0]) + "," + std::to_string(pl.ch_v[1]) + "], \"open_shape\": " + std::to_string(pl.ch_open_shape) +
+          "}, \"shapes\": [";
     for (size_t i = 0; i < pl.shapes.size(); i++) {
       const Shape& sh = pl.shapes[i];
       js += std::string(i ? ", " : "") + "{\"pos\": [";
@@ -2666,7 +2848,8 @@ int qaoa_debug_plan(int n_qubits, int dtype, int rank, int world, int symmetric,
     for (size_t i = 0; i < pl.passes.size(); i++) {
       const PlanPass& pp = pl.passes[i];
       js += std::string(i ? ", " : "") + "{\"prog\": \"" + names[pp.prog] + "\", \"shape\": " + std::to_string(pp.shape_index) +
-            ", \"cross\": " + (pp.cross ? "true" : "false") + ", \"ops\": [";
+            ", \"cross\": " + (pp.cross ? "true" : "false") + ", \"closed\": " + (pp.chunk_closed ? "true" : "false") +
+            ", \"ops\": [";
       for (int k = 0; k < pp.tp.nops; k++) {
         const TileOp& op = pp.tp.ops[k];
         js += std::string(k ? ", " : "") + "[" + std::to_string(op.type) + "," + std::to_string(op.frame) + "," +

@@ -106,7 +106,31 @@ struct TilePass {
   // (register bits 1..4) and A4 (register bits 0..4) -- constant-bank operands instead of per-tile shifts
   unsigned long long roffe[2][4];
   unsigned long long roffe8[5];
+  // Chunked launches (sharded registers: the cross pass of one chunk overlaps the local passes of another, engine.cu
+  // "chunk pipeline"): this launch walks only the tiles of chunk ch_c of 2^ch_m.  A chunk is the set of local indices
+  // with  z[v_i] XOR z[u] = bit i of ch_c  for ch_m bit pairs -- invariant under the mirror pairing of a symmetric
+  // register, and u, v_i are bits no chunk-closed pass mixes.  The launch enumerates j in [0, ntiles) with ntiles =
+  // (tiles of the shape) >> ch_m; the tile index is j with the v_i bits inserted (positions ch_pv, ascending, in tile-
+  // index coordinates) and set to ch_c XOR the u bit (position ch_pu).  ch_part0: first partial-result slot (REDUCE).
+  int ch_m;
+  int ch_c;
+  int ch_pu;
+  int ch_pv[2];
+  int ch_part0;
 };
+
+__device__ __forceinline__ unsigned chunk_tile(const TilePass& P, unsigned j) {
+  if (P.ch_m == 0) return j;
+  unsigned t = j;
+#pragma unroll
+  for (int i = 0; i < 2; i++)
+    if (i < P.ch_m) { const int pv = P.ch_pv[i]; t = ((t >> pv) << (pv + 1)) | (t & ((1u << pv) - 1u)); }
+  const unsigned ub = (t >> P.ch_pu) & 1u;
+#pragma unroll
+  for (int i = 0; i < 2; i++)
+    if (i < P.ch_m) t |= ((((unsigned)P.ch_c >> i) & 1u) ^ ub) << P.ch_pv[i];
+  return t;
+}
 
 template <typename Elem> struct ElemTraits;
 template <> struct ElemTraits<float2> {
@@ -713,7 +737,7 @@ __device__ __forceinline__ void prefetch_later_tile(const Ctx<Elem>& c) {
   if (P.prefetch_dist <= 0 || P.shard_bits != 0 || P.zbit != 0) return;
   const unsigned long long id = c.id + (unsigned)P.prefetch_dist;
   if (id >= c.total) return;
-  const unsigned ntile = (unsigned)(id & c.tmask), npoint = (unsigned)(id >> c.tshift);
+  const unsigned ntile = chunk_tile(*c.P, (unsigned)(id & c.tmask)), npoint = (unsigned)(id >> c.tshift);
   const size_t nbase = tile_base(P, ntile);
   const Elem* st = c.state0 + (size_t)npoint * c.point_stride;
 #pragma unroll
@@ -1077,7 +1101,7 @@ template <typename Elem>
 __device__ __forceinline__ void flush_acc(const Ctx<Elem>& c, double (&acc)[5], unsigned point) {
   block_reduce5(acc, c.scratch);
   if (threadIdx.x == 0) {
-    double* o = c.partials + ((size_t)point * gridDim.x + blockIdx.x) * 5;
+    double* o = c.partials + ((size_t)point * gridDim.x + blockIdx.x + c.P->ch_part0) * 5;
 #pragma unroll
     for (int i = 0; i < 5; i++) o[i] = acc[i];
   }
@@ -1164,7 +1188,7 @@ template <typename Elem>
 __device__ __forceinline__ void ctx_set_tile(Ctx<Elem>& c, unsigned long long id) {
   const TilePass& P = *c.P;
   c.id = id;
-  c.tile = (unsigned)(id & c.tmask);   // ntiles is a power of two
+  c.tile = chunk_tile(P, (unsigned)(id & c.tmask));   // ntiles is a power of two
   c.point = (unsigned)(id >> c.tshift);
   c.state = c.state0 + (size_t)c.point * c.point_stride;
   c.tau = c.tau0 + (size_t)c.point * P.tau_stride;
@@ -1225,7 +1249,7 @@ __device__ __forceinline__ void stage_issue(const Ctx<Elem>& c, unsigned long lo
   constexpr int SP = TileSmem<Elem>::STAGE_PAIRS;
   if (id < c.total) {
     const TilePass& P = *c.P;
-    const unsigned ntile = (unsigned)(id & c.tmask), npoint = (unsigned)(id >> c.tshift);
+    const unsigned ntile = chunk_tile(*c.P, (unsigned)(id & c.tmask)), npoint = (unsigned)(id >> c.tshift);
     Elem* pb = c.state0 + (size_t)npoint * c.point_stride;
     const unsigned sb = (unsigned)__cvta_generic_to_shared(c.smem);
     const unsigned early = sb + TileSmem<Elem>::STAGE_OFF + threadIdx.x * 16u;
@@ -1270,7 +1294,7 @@ __device__ __forceinline__ void stage_issue8(const Ctx<Elem>& c, unsigned long l
   constexpr int SP = TileSmem<Elem>::STAGE_PAIRS;
   if (id < c.total) {
     const TilePass& P = *c.P;
-    const unsigned ntile = (unsigned)(id & c.tmask), npoint = (unsigned)(id >> c.tshift);
+    const unsigned ntile = chunk_tile(*c.P, (unsigned)(id & c.tmask)), npoint = (unsigned)(id >> c.tshift);
     const size_t e0 = tile_base(P, ntile + P.tile0) + c.thr[3];
     size_t ro[5];
 #pragma unroll
@@ -1701,7 +1725,7 @@ tile_prog_kernel(const __grid_constant__ TilePass P, Elem* __restrict__ state, s
   if constexpr (HAS_RED) {
     // partials[point][cta]: neutral entries for the points this CTA never touches
     for (unsigned pt = threadIdx.x; pt < n_points; pt += TILE_THREADS) {
-      double* o = partials + ((size_t)pt * gridDim.x + blockIdx.x) * 5;
+      double* o = partials + ((size_t)pt * gridDim.x + blockIdx.x + P.ch_part0) * 5;
       o[0] = 0.0; o[1] = 0.0; o[2] = 0.0; o[3] = 1e300; o[4] = -1e300;
     }
   }
@@ -1712,7 +1736,7 @@ tile_prog_kernel(const __grid_constant__ TilePass P, Elem* __restrict__ state, s
   constexpr int DQ_OFF = L::STAGE_OFF + 4 * L::TABLE_BYTES;
   auto dq_issue = [&](unsigned long long id, int buf) {
     if (id < total) {
-      const unsigned t = (unsigned)(id & c.tmask);
+      const unsigned t = chunk_tile(P, (unsigned)(id & c.tmask));
       const uint4* s4 = reinterpret_cast<const uint4*>(P.streams[Prog::op(Prog::stream_op() >= 0 ? Prog::stream_op() : 0).arg]);
       const unsigned sb = (unsigned)__cvta_generic_to_shared(smem_raw) + DQ_OFF + buf * (TILE_THREADS * 32) + threadIdx.x * 16u;
 #pragma unroll
@@ -1756,7 +1780,7 @@ tile_prog_kernel(const __grid_constant__ TilePass P, Elem* __restrict__ state, s
       // that those loads cost an L2 hit instead of a DRAM round trip in the middle of the tile
       const unsigned long long nid = id + gridDim.x;
       if (nid < total) {
-        const unsigned nt = (unsigned)(nid & c.tmask);
+        const unsigned nt = chunk_tile(P, (unsigned)(nid & c.tmask));
         const int wbytes = NAMP * diag_value_bytes(c.dinfo.kind) * 32;
         for (int i = 0; i < P.nops; i++) {
           if (P.ops[i].type != TOP_PHASE && P.ops[i].type != TOP_REDUCE) continue;

@@ -90,6 +90,11 @@ def load_library():
         "qaoa_sample": (ctypes.c_int, [H, ctypes.c_int, _c_double_p, ctypes.c_int, ctypes.c_int, _c_double_p, _c_uint64_p]),
         "qaoa_extreme_solutions": (ctypes.c_int, [H, ctypes.c_int, _c_double_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                                   _c_uint64_p, ctypes.POINTER(ctypes.c_int), _c_double_p]),
+        "qaoa_get_stream": (ctypes.c_int, [H, ctypes.POINTER(ctypes.c_ulonglong)]),
+        "qaoa_get_stream2": (ctypes.c_int, [H, ctypes.POINTER(ctypes.c_ulonglong)]),
+        "qaoa_shard_chunk_info": (ctypes.c_int, [H, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int), ctypes.c_int]),
+        "qaoa_shard_run_pass_chunk": (ctypes.c_int, [H, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+        "qaoa_shard_finish_device": (ctypes.c_int, [H, ctypes.c_void_p]),
         "qaoa_shard_grover_step": (ctypes.c_int, [H, ctypes.c_int, ctypes.c_int, _c_double_p, ctypes.c_int, _c_double_p, _c_double_p]),
         "qaoa_cvar": (ctypes.c_int, [H, ctypes.c_int, _c_double_p, ctypes.c_int, ctypes.c_double, _c_double_p]),
         "qaoa_cost_distribution": (ctypes.c_int, [H, ctypes.c_int, _c_double_p, ctypes.c_int, _c_double_p,
@@ -407,6 +412,31 @@ class Engine:
 
     def shard_run_pass(self, i):
         self._check(self._lib.qaoa_shard_run_pass(self._h, int(i)))
+
+    def stream_handle(self):
+        """the engine's cudaStream_t (integer) -- for torch.cuda.ExternalStream"""
+        out = ctypes.c_ulonglong()
+        self._check(self._lib.qaoa_get_stream(self._h, ctypes.byref(out)))
+        return int(out.value)
+
+    def stream2_handle(self):
+        out = ctypes.c_ulonglong()
+        self._check(self._lib.qaoa_get_stream2(self._h, ctypes.byref(out)))
+        return int(out.value)
+
+    def shard_chunk_info(self, n_passes):
+        """(number of chunks, per-pass flag: may be launched chunk by chunk) of the evaluation in flight"""
+        nch = ctypes.c_int()
+        closed = (ctypes.c_int * max(1, n_passes))()
+        self._check(self._lib.qaoa_shard_chunk_info(self._h, ctypes.byref(nch), closed, n_passes))
+        return int(nch.value), [bool(closed[i]) for i in range(n_passes)]
+
+    def shard_run_pass_chunk(self, i, chunk=-1, stream=0, ctas=0):
+        self._check(self._lib.qaoa_shard_run_pass_chunk(self._h, int(i), int(chunk), int(stream), int(ctas)))
+
+    def shard_finish_device(self, device_ptr):
+        """raw partial sums {sum p, sum p c, sum p c^2, min, max} written to DEVICE memory at device_ptr (5 doubles)"""
+        self._check(self._lib.qaoa_shard_finish_device(self._h, ctypes.c_void_p(int(device_ptr))))
 
     def shard_grover_step(self, step, angles, dot_global=None):
         """one step of the sharded Grover circuit: (local partial dot) for step < p, raw local statistics for step = p"""

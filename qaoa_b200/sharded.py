@@ -52,6 +52,39 @@ def needs_barrier(cross_flags, i):
     return bool(cross_flags[i] or (i > 0 and cross_flags[i - 1]))
 
 
+def pipeline_segments(cross_flags, closed):
+    """Splits the pass list of a sharded evaluation into segments for the chunk pipeline: ("pass", i) = the whole pass,
+    ("window", pre, x, post) = cross pass x with the chunk-closed local passes right before and after it.  Inside a
+    window chunk c runs pre -> x -> post independently of the other chunks (engine.cu plan_chunks), so the cross pass of
+    one chunk can overlap the local passes of another."""
+    n = len(cross_flags)
+    segs, i = [], 0
+    while i < n:
+        # a window starts at i if the closed local passes from i on lead straight to a closed cross pass
+        j = i
+        while j < n and closed[j] and not cross_flags[j]:
+            j += 1
+        if j < n and cross_flags[j] and closed[j]:
+            pre, x = list(range(i, j)), j
+            k = x + 1
+            while k < n and closed[k] and not cross_flags[k]:
+                k += 1
+            post = list(range(x + 1, k))
+            # leave the closed passes that lead to the NEXT cross pass to that window if they are all there is between
+            if k < n and cross_flags[k] and closed[k]:
+                post = []
+                k = x + 1
+            segs.append(("window", pre, x, post))
+            i = k
+        elif j > i and not (j < n and cross_flags[j]):
+            segs.extend(("pass", q) for q in range(i, j))
+            i = j
+        else:
+            segs.append(("pass", i))
+            i += 1
+    return segs
+
+
 class _ShardedSurface:
     """Engine-like methods shared by the two drivers (fan a call out to the local engine(s))."""
 
@@ -156,6 +189,9 @@ class LocalShardGroup(_ShardedSurface):
             dot = np.sum([e.shard_grover_step(step, angles, dot) for e in self.engines], axis=0)
         return combine_partials([e.shard_grover_step(p, angles, dot) for e in self.engines])
 
+    chunk_major = False      # tests: run the windows of the chunk pipeline chunk by chunk (pre -> cross -> post per chunk)
+    last_chunks = 1
+
     def energy(self, angles):
         if self.mixer_kind == _eng.MIXER_GROVER:
             return self._energy_grover(angles)
@@ -164,6 +200,27 @@ class LocalShardGroup(_ShardedSurface):
         self._sync_all()   # (first call: the diagonal streams of every rank are built from peer memory)
         flags = [self.engines[0].shard_pass_is_cross(i) for i in range(counts[0])]
         self.last_cross_flags = flags
+        nch, closed = (1, [False] * counts[0])
+        if self.chunk_major and hasattr(self.engines[0], "shard_chunk_info"):
+            nch, closed = self.engines[0].shard_chunk_info(counts[0])
+        self.last_chunks = nch
+        if nch > 1:
+            # every rank's launches of one step are separated from the next step by a device-wide sync (one process, one
+            # GPU: no overlap here -- this path checks that the chunks really are independent of each other)
+            for seg in pipeline_segments(flags, closed):
+                if seg[0] == "pass":
+                    self._sync_all()
+                    for e in self.engines:
+                        e.shard_run_pass(seg[1])
+                    continue
+                _, pre, x, post = seg
+                for c in range(nch):
+                    for i in pre + [x] + post:
+                        self._sync_all()
+                        for e in self.engines:
+                            e.shard_run_pass_chunk(i, c)
+            self._sync_all()
+            return combine_partials([e.shard_finish() for e in self.engines])
         for i in range(counts[0]):
             if needs_barrier(flags, i):
                 self._sync_all()
@@ -196,6 +253,24 @@ class DistShardedEngine(_ShardedSurface):
         self.eng = make(self.rank, self.world)
         self.barriers = 0
         self._diag_exchanged = False
+        # NCCL + a real engine: cross-rank barriers and the final combination are ordered on the engine's own CUDA
+        # stream (an NCCL collective between two passes), so the host never waits inside an evaluation
+        self._ext = None
+        if engine_factory is None and dist.get_backend(group) == "nccl" and hasattr(self.eng, "stream_handle"):
+            import torch
+            dev = torch.device("cuda", int(device))
+            self._ext = torch.cuda.ExternalStream(self.eng.stream_handle(), device=dev)
+            self._bar = torch.zeros(1, dtype=torch.int32, device=dev)
+            self._part = torch.zeros(5, dtype=torch.float64, device=dev)
+            self._parts_all = torch.zeros(5 * self.world, dtype=torch.float64, device=dev)
+            self._ext2 = torch.cuda.ExternalStream(self.eng.stream2_handle(), device=dev)
+            self._sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        import os
+        # chunk pipeline (cross pass of one chunk beside the local passes of another); QAOA_CHUNK_PIPELINE=0 turns it off
+        self.pipeline = os.environ.get("QAOA_CHUNK_PIPELINE", "1") != "0"
+        # SMs a cross pass gets inside a pipeline window (NVLink-bound: 24 CTAs keep the links busy, scripts/cross_ctas.py)
+        self.cross_ctas = int(os.environ.get("QAOA_CROSS_CTAS", "24"))
+        self.last_chunks = 1
         self._exchange(0)
 
     def _engines(self):
@@ -280,6 +355,8 @@ class DistShardedEngine(_ShardedSurface):
         eng = self.eng
         n_passes = eng.shard_begin(angles)
         flags = [eng.shard_pass_is_cross(i) for i in range(n_passes)]
+        if self._ext is not None:
+            return self._energy_stream_ordered(n_passes, flags)
         for i in range(n_passes):
             if needs_barrier(flags, i):
                 eng.shard_sync()
@@ -288,6 +365,69 @@ class DistShardedEngine(_ShardedSurface):
         # the all-reduce doubles as the barrier that keeps the next evaluation's first pass from
         # overwriting a shard some peer is still reading in its last (cross) pass
         return self._all_reduce(eng.shard_finish())
+
+    def _energy_stream_ordered(self, n_passes, flags):
+        """The same protocol with every cross-rank barrier an NCCL all-reduce of one word ON THE ENGINE'S STREAM: it
+        completes on a rank only after every rank has reached it, i.e. after every rank's earlier passes, and the later
+        passes of this rank queue behind it -- no stream synchronise + host barrier bubbles around the cross passes.  The
+        five partial sums go device to device into ONE all-gather (which also fences the next evaluation)."""
+        import torch
+
+        dist, eng = self._dist, self.eng
+        nch, closed = eng.shard_chunk_info(n_passes) if self.pipeline else (1, [False] * n_passes)
+        self.last_chunks = nch
+        A, B = self._ext, self._ext2
+
+        def barrier():
+            self.barriers += 1
+            dist.all_reduce(self._bar, group=self.group)
+
+        with torch.cuda.stream(A):
+            if nch == 1:
+                for i in range(n_passes):
+                    if needs_barrier(flags, i):
+                        barrier()
+                    eng.shard_run_pass(i)
+            else:
+                # Chunk pipeline.  Main stream A: local passes (inside a window on SMs - cross_ctas CTAs); side stream B:
+                # the window's cross pass, chunk by chunk, on cross_ctas CTAs, every chunk between two barriers.  Events
+                # order the two streams per chunk; all ranks enqueue the same sequence, so the collectives match up.
+                local_ctas = max(1, self._sms - self.cross_ctas)
+                prev_cross = False
+                for seg in pipeline_segments(flags, closed):
+                    if seg[0] == "pass":
+                        i = seg[1]
+                        if flags[i] or prev_cross:
+                            barrier()
+                        eng.shard_run_pass(i)
+                        prev_cross = bool(flags[i])
+                        continue
+                    _, pre, x, post = seg
+                    if prev_cross:
+                        barrier()
+                    ev_a = [torch.cuda.Event() for _ in range(nch)]
+                    ev_b = [torch.cuda.Event() for _ in range(nch)]
+                    for c in range(nch):
+                        for i in pre:
+                            eng.shard_run_pass_chunk(i, c, 0, local_ctas)
+                        ev_a[c].record(A)
+                    with torch.cuda.stream(B):
+                        for c in range(nch):
+                            B.wait_event(ev_a[c])
+                            barrier()                 # every rank has finished chunk c's passes before the cross pass
+                            eng.shard_run_pass_chunk(x, c, 1, self.cross_ctas)
+                            barrier()                 # every rank's cross pass of chunk c is complete
+                            ev_b[c].record(B)
+                    for c in range(nch):
+                        A.wait_event(ev_b[c])
+                        for i in post:
+                            eng.shard_run_pass_chunk(i, c, 0, local_ctas)
+                    prev_cross = False
+            eng.shard_finish_device(self._part.data_ptr())
+            dist.all_gather_into_tensor(self._parts_all, self._part, group=self.group)
+            parts = self._parts_all.cpu().numpy().reshape(self.world, 5)
+        eng.shard_sync()          # stream is idle: collects the per-pass event timings
+        return combine_partials(parts)
 
     def close(self):
         """collective: every rank unmaps its peers before any rank frees the buffers they map"""

@@ -28,7 +28,11 @@ def _run(world, n, dtype, port):
     for line in proc.stdout.splitlines():
         if line.startswith("MULTIGPU_REPORT "):
             rep = json.loads(line[len("MULTIGPU_REPORT "):])
-    assert proc.returncode == 0 and rep is not None and rep["ok"], (proc.stdout[-3000:], proc.stderr[-3000:])
+    if rep is not None:
+        for c in rep["checks"]:
+            print("CHECK", json.dumps(c))
+    print(proc.stderr[-1500:])
+    assert proc.returncode == 0 and rep is not None and rep["ok"], (proc.stdout[-300:], proc.stderr[-300:])
     return rep
 
 

@@ -95,6 +95,43 @@ def test_sharded_grover_mixer(n, world, k, dtype):
     single.close()
 
 
+@pytest.mark.parametrize("n,world,symmetric,dtype", [(28, 2, True, "complex64"), (26, 2, True, "complex64"),
+                                                    (28, 8, True, "complex64"), (28, 4, True, "complex64"),
+                                                    (27, 2, False, "complex64"), (28, 4, False, "complex64"),
+                                                    (26, 2, False, "complex128"), (24, 2, False, "complex128")])
+def test_chunk_pipeline_chunks_are_independent(n, world, symmetric, dtype):
+    """The chunk pipeline (engine.cu plan_chunks, sharded.py pipeline_segments): closed passes launched chunk by chunk,
+    and inside every window chunk c runs pre -> cross -> post BEFORE chunk c+1 starts -- if a closed pass coupled two
+    chunks, or the tile remap / partial-sum slots of a chunked launch were off, the result would differ from the
+    whole-pass evaluation and the oracle.  (One process, one GPU: no overlap here, only the data flow.)"""
+    from oracle import c_oracle
+    from qaoa_b200.sharded import LocalShardGroup, pipeline_segments
+
+    edges, colors, table = H.regular_maxcut(n + (n & 1))
+    edges = [e for e in edges if e[0] < n and e[1] < n]
+    lut, _ = H.lut_from_table(table, 1)
+    grp = LocalShardGroup(n, world, dtype=dtype, symmetric=symmetric)
+    grp.set_cost_maxkcut(n, edges, 1, lut)
+    d8 = c_oracle.maxcut_diag_u8(n, edges)
+    rng = np.random.default_rng(n + world)
+    seen_chunks = 0
+    tol = TOL[dtype]
+    for p in (1, 2, 3, 5):
+        ang = rng.uniform(0, 2 * np.pi, size=2 * p)
+        ang[1::2] = rng.uniform(-1.2, 1.2, size=p)
+        grp.chunk_major = False
+        whole = grp.energy(ang)
+        grp.chunk_major = True
+        got = grp.energy(ang)
+        seen_chunks = max(seen_chunks, grp.last_chunks)
+        ref = c_oracle.run(n, d8, ang, "complex128", blocked=True)
+        assert H.rel_err(got[0], ref[0]) < tol and H.rel_err(got[1], ref[1]) < 2 * tol, (p, got, ref)
+        assert got[2] == ref[2] and got[3] == ref[3] and abs(got[4] - 1) < (1e-4 if dtype == "complex64" else 1e-11)
+        assert H.rel_err(got[0], whole[0]) < tol * 0.01 and H.rel_err(got[1], whole[1]) < tol * 0.01, (p, got, whole)
+    assert seen_chunks >= 2 or (n, dtype) == (24, "complex128"), "no plan of this configuration had chunks"
+    grp.close()
+
+
 def test_sharded_multiangle_dicke_and_cot_form():
     """Per-qubit betas follow the logical qubit across the shard boundary; Dicke initial state generated
     per shard with the global popcount; beta = pi/2 exercises the interpreter's cross variant."""
