@@ -295,14 +295,16 @@ def sharded_leg(n, p, sym, steps, warmup, local_rank, world, dist, torch, oracle
     achieved = (d_bytes / d_cnt) / (d_ms / d_cnt * 1e-3) / 1e9
     cross_ms = (stats["BoundX"][0] + stats["FinalX"][0]) / steps
     nvlink = None
+    chunks = int(getattr(E, "last_chunks", 1))
     if stats["BoundX"][1]:
-        ms = stats["BoundX"][0] / stats["BoundX"][1]
-        per_dir = 2.0 * (1.0 - 1.0 / world) * shard_bytes     # read-modify-write: loads + stores, each (1 - 1/N) remote
-        nvlink = {"kernel": "tile_prog_kernel<ProgBoundX>", "ms_per_launch": round(ms, 3),
+        # a whole BOUNDX pass = `chunks` launches in the chunk pipeline; read-modify-write: loads + stores, each (1 - 1/N) remote
+        ms = stats["BoundX"][0] / stats["BoundX"][1] * chunks
+        per_dir = 2.0 * (1.0 - 1.0 / world) * shard_bytes
+        nvlink = {"kernel": "tile_prog_kernel<ProgBoundX>", "ms_per_pass": round(ms, 3),
                   "gbs_per_direction": round(per_dir / (ms * 1e-3) / 1e9, 1), "peer_copy_reference_gbs": 770.0}
     res = {"n": n, "p": p, "gpus": world, "register": "symmetric half, twisted shards" if sym else "full",
            "stored_gib_per_gpu": shard_bytes / 2 ** 30, "ms_per_eval": round(ms_wall, 3), "kernels_ms": round(ms_kernels, 3),
-           "cross_pass_ms": round(cross_ms, 3), "launches": int(launches), "pipeline_chunks": int(getattr(E, "last_chunks", 1)), "energy": float(-out[0]), "norm": float(out[4]),
+           "cross_pass_ms": round(cross_ms, 3), "launches": int(launches), "pipeline_chunks": chunks, "energy": float(-out[0]), "norm": float(out[4]),
            "p1_check": {"engine": float(got1), "closed_form": float(cf), "rel_err": float(abs(got1 - cf) / abs(cf))},
            "dominant_local_pass": {"kernel": "tile_prog_kernel<Prog%s>" % dom, "ms_per_launch": round(d_ms / d_cnt, 3),
                                    "achieved_gbs": round(achieved, 1), "frac": round(achieved / peak, 4)},
@@ -371,30 +373,32 @@ def run_multi(args, rank, world, local_rank):
             "metric": METRIC, "value": head["ms_per_eval"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": head["ms_per_eval"], "higher_is_better": False, "scaling": "strong",
             "vs_baseline": None, "dtype": "c64", "data": "synthetic",
-            "parity": parity,
-            "config": {"workload": "MaxCut 3-regular n=%d seed=42, X mixer, Plus, p=%d, complex64: the SAME register as the "
-                                   "N=1 line, sharded on its top %d qubits over %d GPUs (cross passes over NVLink peer memory, "
-                                   "scalar all-reduce); 1 step = 1 energy evaluation" % (n, p, gb, world),
+            "config": {"workload": "MaxCut 3-regular n=%d seed=42, X mixer, Plus, p=%d, complex64: the N=1 register sharded on its "
+                                   "top %d qubits over %d GPUs; 1 step = 1 energy evaluation" % (n, p, gb, world),
                        "register": head["register"], "stored_gib_per_gpu": head["stored_gib_per_gpu"],
-                       "l2": "shard is %d MiB >> 126 MB L2, no flush needed" % int(head["stored_gib_per_gpu"] * 1024),
-                       "energy": head["energy"], "norm": head["norm"], "p1_check": head["p1_check"],
-                       "value_is": "wall time per evaluation through DistShardedEngine.energy between barriers, max over ranks"},
+                       "l2": "shard >> 126 MB L2, no flush needed",
+                       "value_is": "wall ms per evaluation through DistShardedEngine.energy between barriers, max over ranks"},
             "e2e": {"value": head["ms_per_eval"], "unit": UNIT, "h2d_bytes_per_step": int(ang.nbytes + 4096) * world,
-                    "d2h_bytes_per_step": 40 * world,
-                    "api": "qaoa_shard_begin / qaoa_shard_run_pass / qaoa_shard_finish (C ABI) under torch.distributed; "
-                           "host angles in, host result out, same call as value"},
+                    "d2h_bytes_per_step": 40 * world, "api": "qaoa_shard_* (C ABI) under torch.distributed; same call as value"},
             "gpu_launches": head["launches"] * world,
             "clocks": sampler.summary(),
-            "roofline": {"bound": "hbm", "kernel": "tile_prog_kernel<Prog%s>" % dom, "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
-                         "launches_timed": int(d_cnt), "ms_per_launch": d_ms / d_cnt,
-                         "note": "dominant LOCAL (HBM-bound) pass on rank 0; the cross passes are NVLink-bound: see sharded.nvlink"},
+            "roofline": {"bound": "hbm", "kernel": "tile_prog_kernel<Prog%s>" % dom, "achieved": round(achieved, 1), "peak": peak,
+                         "unit": "GB/s", "frac": round(achieved / peak, 4), "peak_source": peak_src, "traffic": None,
+                         "launches_timed": int(d_cnt), "ms_per_launch": round(d_ms / d_cnt, 3),
+                         "note": "dominant LOCAL pass on rank 0 (chunk launches share the SMs with a cross pass); cross passes are NVLink-bound"},
             "sharded": {k: head[k] for k in ("kernels_ms", "cross_pass_ms", "pipeline_chunks", "nvlink", "passes_ms")},
         }
-        if config5 is not None:
-            line["config5"] = config5
         if landscape is not None:
-            line["landscape"] = landscape
+            line["landscape"] = {k: landscape[k] for k in ("workload", "points_per_s")}
+        if config5 is not None:
+            line["config5"] = {k: config5[k] for k in ("workload", "ms_per_eval", "kernels_ms", "cross_pass_ms", "pipeline_chunks",
+                                                       "stored_gib_per_gpu", "nvlink", "energy", "norm", "p1_check")}
+        # the checks go LAST so that a tail of the line shows them: energy of this run (equal to the N=1 line's), the
+        # closed-form p=1 energy, and the sharded path against the C oracle in this very job
+        line["energy"] = head["energy"]
+        line["norm"] = head["norm"]
+        line["p1_check"] = head["p1_check"]
+        line["parity"] = parity
         print(json.dumps(line), flush=True)
     dist.destroy_process_group()
 
