@@ -128,8 +128,14 @@ class _DepthHistogram(dict):
     def _draw(self):
         if not self._drawn:
             self._drawn = True
-            best = self._owner.optimization_results[self._depth].get_best_angles()
-            super().update({s[::-1]: c for s, c in self._owner.hist(best, self._owner.shots).items()})
+            own = self._owner
+            best = own.optimization_results[self._depth].get_best_angles()
+            depth_before = own.parametrized_circuit_depth
+            super().update({s[::-1]: c for s, c in own.hist(best, own.shots).items()})
+            # looking at a histogram must not move the circuit depth under the caller (hist() re-parameterises the
+            # circuit like the reference's, qaoa.py:1134-1172): put the depth back where it was
+            if depth_before and depth_before != own.parametrized_circuit_depth:
+                own.createParameterizedCircuit(depth_before)
 
     def __reduce__(self):      # pickles as a plain dict: what has been drawn so far (never samples as a side effect)
         return (dict, (dict(dict.items(self)),))
@@ -696,7 +702,12 @@ class QAOA:
         depth = int((len(angles) - n_init) / (n_gamma + n_beta))
         self.createParameterizedCircuit(depth)
         eng = self._get_engine()
-        idx = self._device_call("sample", self._engine_row(angles), int(shots))
+        seed = getattr(self, "sample_seed", None)       # set QAOA.sample_seed for reproducible histograms
+        if seed is not None:
+            self._sample_calls = getattr(self, "_sample_calls", 0) + 1
+            idx = self._device_call("sample", self._engine_row(angles), int(shots), seed=[int(seed), self._sample_calls])
+        else:
+            idx = self._device_call("sample", self._engine_row(angles), int(shots))
         n = self.problem.N_qubits
         out = {}
         values, counts = np.unique(idx, return_counts=True)

@@ -558,6 +558,26 @@ def test_depth_histograms_are_drawn_on_demand_for_post_process_all_depths():
     assert pickle.loads(pickle.dumps(q)).samplecount_hists[3] == {}      # not looked at yet: nothing is sampled by pickling
 
 
+def test_looking_at_a_histogram_keeps_the_circuit_depth_and_is_reproducible_with_a_seed():
+    """reading samplecount_hists[1] after optimize(3) draws the histogram at depth 1 (hist() re-parameterises the circuit)
+    and must leave the circuit at depth 3, so that loss() on depth-3 angles still works; QAOA.sample_seed makes the
+    sampled histograms reproducible"""
+    np.random.seed(3)
+    opt = [__import__("qaoa_b200").utils.COBYLA, {"maxiter": 15}]
+    q, fake = readme_qaoa(shots=128, optimizer=opt)
+    q.sample_seed = 7
+    q.optimize(depth=3)
+    assert q.parametrized_circuit_depth == 3
+    h1 = dict(q.samplecount_hists[1].items())
+    assert sum(h1.values()) == 128 and q.parametrized_circuit_depth == 3
+    q._eval_cost(np.asarray(q.get_angles(3)))           # depth-3 angles still fit the circuit (length assert)
+    q2, _ = readme_qaoa(shots=128, optimizer=opt)
+    q2.sample_seed = 7
+    np.random.seed(3)
+    q2.optimize(depth=3)
+    assert dict(q2.samplecount_hists[1].items()) == h1
+
+
 def _flipped_circuit_state(q, fake_diag, angles, masks):
     """oracle: init -> [phase, mixer, X^mask_d] per layer (no X after the last layer), as reference qaoa.py:476-509"""
     n = q.problem.N_qubits

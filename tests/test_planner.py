@@ -104,7 +104,51 @@ def check_plan(pl, n, p, world, symmetric, dtype):
                 assert key > phases[d], ("butterfly of layer %d before its phase separator" % d, key, phases[d])
             if layer == d - 1:
                 assert key < phases[d], ("butterfly of layer %d after the next phase separator" % (d - 1), key, phases[d])
+    check_chunks(pl, world)
     return len(pl["passes"]), sum(1 for ps in pl["passes"] if ps["cross"])
+
+
+def check_chunks(pl, world):
+    """Chunk pipeline of sharded registers (engine.cu plan_chunks, sharded.py pipeline_segments): the chunk bits are mixed
+    by exactly one local shape; every pass flagged closed tiles over a shape that has all of them as FREE bits (so a chunk
+    is a set of whole tiles of that shape, and the pass never couples two chunks -- the mirror pairing of the symmetric
+    low tile complements all chunk bits, leaving their XORs alone); in the cross shape they lie below the bits that deal
+    the tiles out over the ranks; the driver's segments replay every pass exactly once, in launch order."""
+    from qaoa_b200.sharded import pipeline_segments
+
+    ch = pl["chunks"]
+    g = world.bit_length() - 1
+    flags = [ps["cross"] for ps in pl["passes"]]
+    closed = [ps["closed"] for ps in pl["passes"]]
+    if ch["m"] == 0:
+        assert not any(closed)
+    else:
+        assert world > 1 and ch["m"] in (1, 2)
+        bits = [ch["u"]] + ch["v"][: ch["m"]]
+        assert len(set(bits)) == len(bits) and all(pl["qshift"] <= b < pl["el"] for b in bits)
+        assert ch["v"][: ch["m"]] == sorted(ch["v"][: ch["m"]])
+        open_shape = pl["shapes"][ch["open_shape"]]
+        assert not open_shape["cross"] and not open_shape["zshape"] and all(b in open_shape["pos"] for b in bits)
+        for ps in pl["passes"]:
+            sh = pl["shapes"][ps["shape"]]
+            if not ps["closed"]:
+                continue
+            assert ps["shape"] != ch["open_shape"] and ps["prog"] != "Generic"
+            assert all(b in sh["free"] for b in bits), "chunk bit is not a free bit of a closed pass' shape"
+            assert not any(eb in bits for r in ps["rounds"] for eb in r["ebit"])
+            if sh["cross"]:
+                assert ps["prog"] in ("BoundX", "FinalX")
+                assert all(sh["free"].index(b) < len(sh["free"]) - g for b in bits), "chunk bit deals cross tiles out over the ranks"
+    segs = pipeline_segments(flags, closed)
+    order = []
+    for seg in segs:
+        if seg[0] == "pass":
+            order.append(seg[1])
+        else:
+            _, pre, x, post = seg
+            assert flags[x] and closed[x] and all(closed[i] and not flags[i] for i in pre + post)
+            order += pre + [x] + post
+    assert order == list(range(len(flags))), "segments must replay the passes once, in launch order"
 
 
 def test_baseline_configurations():
@@ -128,6 +172,15 @@ def test_baseline_configurations():
     pl = eng.debug_plan(36, p=3, world=8, cross_spare=False)
     assert pl["kx"] == 0 and "Bound2L4" in [ps["prog"] for ps in pl["passes"]]
     assert eng.debug_plan(34, p=3, world=2)["kx"] == 1
+    # chunk pipeline: four chunks at every BASELINE multi-GPU configuration, windows around every cross pass
+    from qaoa_b200.sharded import pipeline_segments
+    for n, p, world in ((32, 5, 2), (32, 5, 4), (32, 5, 8), (36, 3, 8), (36, 3, 4), (34, 3, 2)):
+        pl = eng.debug_plan(n, p=p, world=world)
+        assert pl["chunks"]["m"] == 2
+        segs = pipeline_segments([ps["cross"] for ps in pl["passes"]], [ps["closed"] for ps in pl["passes"]])
+        wins = [sg for sg in segs if sg[0] == "window"]
+        assert len(wins) == (p + 1) // 2 and all(len(w[1]) >= 1 for w in wins), segs
+        assert all(len(w[3]) == 2 for w in wins[:-1]) and wins[-1][3] == []
 
 
 @pytest.mark.parametrize("world", [1, 2, 4, 8])
