@@ -166,6 +166,10 @@ struct Engine {
   // scratch
   double* d_params = nullptr; size_t params_cap = 0;   // [tau block (real)][phs block (double)]
   double* h_params = nullptr; size_t hparams_cap = 0;
+  // second pinned parameter block + one event per block: the host lowers the angles of chunk i+1 while chunk i runs
+  double* h_params2 = nullptr; size_t hparams2_cap = 0;
+  cudaEvent_t ev_params[2] = {nullptr, nullptr};
+  int param_slot = 0;
   int force_generic = 0;
   int layer_budget = 1;       // multi-angle mixers: normal form whenever the LAYER's total growth fits (fill_point_params)
   int prefetch_dist = 0;     // extra L2 prefetch distance in tiles (0 = off)
@@ -1142,11 +1146,18 @@ void tile_prepare(Engine* h, Plan& pl, const double* angles, int n_angles, int B
   const size_t tau_bytes = (tpp * Bc * rsz + 15) / 16 * 16;
   const size_t phs_bytes = ppp * Bc * 8;
   const size_t gs_bytes = (size_t)2 * p * Bc * 8;
-  ensure(h->h_params, h->hparams_cap, tau_bytes + phs_bytes + gs_bytes, true);
+  // two pinned blocks used in turn; a block is rewritten only after the upload that last read it has completed
+  h->param_slot ^= 1;
+  const int slot = h->param_slot;
+  if (!h->ev_params[slot]) CUDA_OK(cudaEventCreateWithFlags(&h->ev_params[slot], cudaEventDisableTiming));
+  else CUDA_OK(cudaEventSynchronize(h->ev_params[slot]));
+  double*& hpar = slot ? h->h_params2 : h->h_params;
+  size_t& hcap = slot ? h->hparams2_cap : h->hparams_cap;
+  ensure(hpar, hcap, tau_bytes + phs_bytes + gs_bytes, true);
   ensure(h->d_params, h->params_cap, tau_bytes + phs_bytes);
   ensure(h->d_gamsig, h->gamsig_cap, gs_bytes);
   ensure(h->d_partials, h->partials_cap, ((size_t)ntiles + h->persistent_ctas) * Bc * 5 * sizeof(double));
-  unsigned char* hb = (unsigned char*)h->h_params;
+  unsigned char* hb = (unsigned char*)hpar;
   double* h_phs = (double*)(hb + tau_bytes);
   double* hgs = (double*)(hb + tau_bytes + phs_bytes);
   std::vector<double> tau_tmp(tpp), phs_tmp(ppp);
@@ -1195,6 +1206,7 @@ void tile_prepare(Engine* h, Plan& pl, const double* angles, int n_angles, int B
     CUDA_OK(cudaGetLastError());
     h->launches += 1;
   }
+  CUDA_OK(cudaEventRecord(h->ev_params[slot], h->stream));     // the uploads out of this pinned block are behind us
   if (h->init.kind == INIT_STATEVECTOR) {
     for (int b = 0; b < Bc; b++)
       CUDA_OK(cudaMemcpyAsync((char*)h->state + (size_t)b * h->N * h->amp_bytes, h->init_vec, h->N * h->amp_bytes,
@@ -1821,15 +1833,14 @@ void energy_batch_body(Engine* h, int p, const double* angles, int n_angles, int
   if (h->mixer == MIXER_X || h->mixer == MIXER_XMULTI) {
     Plan& pl = get_plan(h, p);
     size_t per_point = plan_amps(h, pl) * h->amp_bytes;
-    int Bmax = h->batch_points > 0 ? h->batch_points : (int)std::max<size_t>(1, std::min<size_t>(64, h->batch_bytes / per_point));
+    int Bmax = h->batch_points > 0 ? h->batch_points : (int)std::max<size_t>(1, std::min<size_t>(256, h->batch_bytes / per_point));
     Bmax = std::min(Bmax, 65535);
     ensure_state(h, std::min(B, Bmax), plan_amps(h, pl));
     int done = 0;
     while (done < B) {
       int Bc = std::min(B - done, Bmax);
       run_tile_chunk(h, pl, angles + (size_t)done * n_angles, n_angles, Bc, h->d_out + (size_t)done * 5, done + Bc == B);
-      done += Bc;
-      if (done < B) CUDA_OK(cudaStreamSynchronize(h->stream));  // pinned param buffer reuse
+      done += Bc;     // (no synchronise: tile_prepare alternates two pinned parameter blocks guarded by events)
     }
     return;
   }
@@ -1982,6 +1993,8 @@ int qaoa_destroy(qaoa_engine_t* h) {
                   h->d_tables, h->d_gamsig, h->d_coefdot, h->d_angles};
   for (void* b : bufs) if (b) cudaFree(b);
   if (h->h_params) cudaFreeHost(h->h_params);
+  if (h->h_params2) cudaFreeHost(h->h_params2);
+  for (auto& e : h->ev_params) if (e) cudaEventDestroy(e);
   if (h->h_out) cudaFreeHost(h->h_out);
   cudaStreamDestroy(h->stream);
   if (h->stream2) cudaStreamDestroy(h->stream2);

@@ -268,8 +268,8 @@ class DistShardedEngine(_ShardedSurface):
         import os
         # chunk pipeline (cross pass of one chunk beside the local passes of another); QAOA_CHUNK_PIPELINE=0 turns it off
         self.pipeline = os.environ.get("QAOA_CHUNK_PIPELINE", "1") != "0"
-        # SMs a cross pass gets inside a pipeline window (NVLink-bound: 24 CTAs keep the links busy, scripts/cross_ctas.py)
-        self.cross_ctas = int(os.environ.get("QAOA_CROSS_CTAS", "24"))
+        # SMs a cross pass gets inside a pipeline window (NVLink-bound: alone, 24 CTAs keep the links busy, scripts/cross_ctas.py; beside local passes 32 is the measured optimum)
+        self.cross_ctas = int(os.environ.get("QAOA_CROSS_CTAS", "32"))
         self.last_chunks = 1
         self._exchange(0)
 
