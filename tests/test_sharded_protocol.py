@@ -353,3 +353,78 @@ def test_landscape_split_across_ranks_gloo(tmp_path):
         assert np.allclose(row[:-1], ref.Exp_sampled_p1.ravel(), rtol=1e-13)
         calls.append(int(row[-1]))
     assert sorted(calls) == [7, 8]
+
+
+class GroverShmEngine(ShmShardEngine):
+    """Stand-in for the sharded Grover protocol (Engine.shard_grover_step): every rank sweeps its own shard, the only
+    thing that crosses the ranks is the partial dot product <s|v> of every layer (all-reduced by DistShardedEngine)."""
+
+    def __init__(self, n, rank, world, diag, s_state):
+        super().__init__(n, rank, world, diag)
+        lo = rank << self.nl
+        self.s_loc = np.asarray(s_state, dtype=np.complex128)[lo: lo + (1 << self.nl)]
+        self.c_loc = self.diag[lo: lo + (1 << self.nl)]
+        self.v = None
+        self.steps = []
+
+    def set_mixer(self, kind, *a, **k):
+        self.n_beta = 1
+
+    def shard_grover_step(self, step, angles, dot_global=None):
+        ang = np.asarray(angles, dtype=np.float64)
+        p = ang.size // 2
+        self.steps.append(step)
+        if step == 0:
+            assert dot_global is None
+            self.v = self.s_loc.copy()
+        else:
+            dot = complex(dot_global[0], dot_global[1])
+            self.v = self.v + (np.exp(-1j * ang[2 * (step - 1) + 1]) - 1.0) * dot * self.s_loc
+        if step < p:
+            self.v = self.v * np.exp(1j * ang[2 * step] * self.c_loc)
+            d = np.vdot(self.s_loc, self.v)
+            return np.array([d.real, d.imag])
+        pr = np.abs(self.v) ** 2
+        sup = pr > 0
+        lo, hi = (self.c_loc[sup].min(), self.c_loc[sup].max()) if sup.any() else (1e300, -1e300)
+        return np.array([pr.sum(), (pr * self.c_loc).sum(), (pr * self.c_loc ** 2).sum(), lo, hi])
+
+
+def _grover_worker(rank, world, port, n, k, out_dir):
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from qaoa_b200 import engine as eng_mod
+        from qaoa_b200 import sharded
+
+        Q, c, b = H.random_qubo(n, seed=4)
+        diag = orc.qubo_diag(Q, c, b)
+        s_state = orc.dicke_state(n, k)
+        eng = sharded.DistShardedEngine(n, engine_factory=lambda r, w: GroverShmEngine(n, r, w, diag, s_state))
+        eng.set_mixer(eng_mod.MIXER_GROVER, sub_kind=eng_mod.INIT_DICKE, sub_k=k)
+        ang = np.array([0.03, 0.7, 0.05, 1.9, 0.02, -0.4])
+        got = eng.energy(ang)
+        assert eng.eng.steps == [0, 1, 2, 3]
+        ref = np.array(orc.energy(orc.Spec(n, diag, mixer=("grover", s_state), init=s_state), ang))
+        np.save(os.path.join(out_dir, "g%d.npy" % rank), np.concatenate([got, ref]))
+        dist.barrier()
+        eng.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_grover_protocol_gloo(world, tmp_path):
+    """Grover mixer on a sharded register under torch.distributed (gloo): step d's local sweep, ONE all-reduced complex
+    scalar per layer, the statistics combined at the end -- every rank ends with the oracle's energy"""
+    import torch.multiprocessing as mp
+
+    n, k = 10, 4
+    mp.spawn(_grover_worker, args=(world, _free_port(), n, k, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        row = np.load(tmp_path / ("g%d.npy" % r))
+        got, ref = row[:5], row[5:9]
+        assert np.allclose(got[:4], ref, rtol=1e-12), (r, got, ref)
+        assert abs(got[4] - 1.0) < 1e-12
