@@ -98,6 +98,30 @@ def main():
                 ok = ok and same
             report["checks"].append(entry)
         E.close()
+    # Replacing the cost function is collective (peers unmap the old diagonal before its owner frees it): lower a second
+    # graph onto the same sharded engine, then the first one again -- the energies must follow
+    E = DistShardedEngine(n, dtype=dtype, device=local_rank, symmetric=False)
+    E.set_cost_maxkcut(n, edges, 1, lut)
+    first = E.energy(cases[1])
+    edges2 = [e for i, e in enumerate(edges) if i % 5]
+    E.set_cost_maxkcut(n, edges2, 1, lut)
+    other = E.energy(cases[1])
+    E.set_cost_maxkcut(n, edges, 1, lut)
+    again = E.energy(cases[1])
+    entry = {"case": "cost replaced twice", "energy": float(again[0]), "same_on_all_ranks": True}
+    if rank == 0:
+        ref2 = c_oracle.run(n, c_oracle.maxcut_diag_u8(n, edges2), cases[1], "complex128", blocked=True)
+        entry["oracle"] = float(ref2[0])
+        entry["rel_err"] = max(abs(other[0] - ref2[0]) / abs(ref2[0]), abs(again[0] - refs[1][0]) / abs(refs[1][0]))
+        entry["ok"] = bool(entry["rel_err"] < tol and again[0] == first[0])
+        ok = ok and entry["ok"]
+    report["checks"].append(entry)
+    try:
+        E.set_cost_maxkcut_terms(n, edges, list(range(len(edges))), len(edges), 1, lut)
+        ok = False                                        # per-term gammas must be rejected on a sharded register
+    except NotImplementedError:
+        pass
+    E.close()
     # Grover mixer over a Dicke state on the sharded FULL register: no state exchange, one all-reduced scalar per layer
     ng, kg = min(n, 24), 7
     Q, cq, bq = H.random_qubo(ng, seed=ng)
