@@ -89,7 +89,7 @@ struct Plan {
   int kx = 0;                // sharded registers: local bits carried by the cross tile (build_plan)
   // chunk pipeline (sharded registers, plan_chunks): 2^ch_m chunks, chunk bits u / v_i (element bits), the one local
   // shape that mixes them (every pass over another shape is chunk-closed)
-  int ch_m = 0, ch_u = -1, ch_v[2] = {-1, -1}, ch_open_shape = -1;
+  int ch_m = 0, ch_u = -1, ch_v[3] = {-1, -1, -1}, ch_open_shape = -1;
 };
 
 struct Engine {
@@ -111,6 +111,7 @@ struct Engine {
   cudaStream_t cur_stream = nullptr;
   int cur_ctas = 0, cur_ch_c = -1;
   int chunking = 1;                    // option "chunk_pipeline"
+  int chunk_bits = 3;                  // option "chunk_bits": at most 2^chunk_bits chunks
 
   // state storage: `state_points` consecutive registers
   void* state = nullptr;
@@ -1279,11 +1280,12 @@ void plan_chunks(Engine* h, Plan& pl) {
   // every pass over another shape must be a compiled-program pass candidate; passes over the open shape stay whole
   const auto& b = excl[best];
   pl.ch_open_shape = best;
-  pl.ch_m = b.size() >= 3 ? 2 : 1;
+  pl.ch_m = std::min({(int)b.size() - 1, 3, std::max(1, h->chunk_bits)});
+  // (every chunk launch must still give each persistent CTA a few tiles)
+  while (pl.ch_m > 1 && (plan_ntiles(h, pl) >> pl.ch_m) < 4u * (unsigned)h->persistent_ctas) pl.ch_m--;
   pl.ch_u = b[b.size() - 1];
-  pl.ch_v[0] = b[b.size() - 2];
-  pl.ch_v[1] = pl.ch_m == 2 ? b[b.size() - 3] : -1;
-  if (pl.ch_m == 2 && pl.ch_v[0] > pl.ch_v[1]) std::swap(pl.ch_v[0], pl.ch_v[1]);   // ascending tile-index positions
+  for (int i = 0; i < 3; i++) pl.ch_v[i] = -1;
+  for (int i = 0; i < pl.ch_m; i++) pl.ch_v[i] = b[b.size() - 1 - pl.ch_m + i];   // ascending tile-index positions
   // chunked launches exist for the compiled-program kernels only (launch_pass sends a cross pass without a BOUNDX /
   // FINALX program, or any pass without a program, to the interpreter kernel, which walks whole passes)
   for (auto& pp : pl.passes) {
@@ -2016,6 +2018,7 @@ int qaoa_set_option(qaoa_engine_t* h, const char* key, double value) {
   else if (k == "force_generic") h->force_generic = value != 0;
   else if (k == "layer_budget") h->layer_budget = value != 0;
   else if (k == "chunk_pipeline") { h->chunking = value != 0; invalidate(h); }
+  else if (k == "chunk_bits") { h->chunk_bits = std::max(1, std::min(3, (int)value)); invalidate(h); }
   else if (k == "prefetch_dist") h->prefetch_dist = (int)value;
   else if (k == "persistent_ctas") h->persistent_ctas = std::max(1, (int)value);
   else if (k == "time_passes") h->time_passes = value != 0;
@@ -2847,7 +2850,8 @@ int qaoa_debug_plan(int n_qubits, int dtype, int rank, int world, int symmetric,
           ", \"el\": " + std::to_string(plan_el(h, pl)) + ", \"qshift\": " + std::to_string(h->qshift) +
           ", \"E\": " + std::to_string(h->E) + ", \"gbits\": " + std::to_string(h->gbits) +
           ", \"chunks\": {\"m\": " + std::to_string(pl.ch_m) + ", \"u\": " + std::to_string(pl.ch_u) + ", \"v\": [" +
-          std::to_string(pl.ch_v[0]) + "," + std::to_string(pl.ch_v[1]) + "], \"open_shape\": " + std::to_string(pl.ch_open_shape) +
+          std::to_string(pl.ch_v[0]) + "," + std::to_string(pl.ch_v[1]) + "," + std::to_string(pl.ch_v[2]) +
+          "], \"open_shape\": " + std::to_string(pl.ch_open_shape) +
           "}, \"shapes\": [";
     for (size_t i = 0; i < pl.shapes.size(); i++) {
       const Shape& sh = pl.shapes[i];

@@ -107,7 +107,7 @@ struct TilePass {
   unsigned long long roffe[2][4];
   unsigned long long roffe8[5];
   // Chunked launches (sharded registers: the cross pass of one chunk overlaps the local passes of another, engine.cu
-  // "chunk pipeline"): this launch walks only the tiles of chunk ch_c of 2^ch_m.  A chunk is the set of local indices
+  // "chunk pipeline"): this launch walks only the tiles of chunk ch_c of 2^ch_m (ch_m <= 3).  A chunk is the set of local indices
   // with  z[v_i] XOR z[u] = bit i of ch_c  for ch_m bit pairs -- invariant under the mirror pairing of a symmetric
   // register, and u, v_i are bits no chunk-closed pass mixes.  The launch enumerates j in [0, ntiles) with ntiles =
   // (tiles of the shape) >> ch_m; the tile index is j with the v_i bits inserted (positions ch_pv, ascending, in tile-
@@ -115,7 +115,7 @@ struct TilePass {
   int ch_m;
   int ch_c;
   int ch_pu;
-  int ch_pv[2];
+  int ch_pv[3];
   int ch_part0;
 };
 
@@ -123,11 +123,11 @@ __device__ __forceinline__ unsigned chunk_tile(const TilePass& P, unsigned j) {
   if (P.ch_m == 0) return j;
   unsigned t = j;
 #pragma unroll
-  for (int i = 0; i < 2; i++)
+  for (int i = 0; i < 3; i++)
     if (i < P.ch_m) { const int pv = P.ch_pv[i]; t = ((t >> pv) << (pv + 1)) | (t & ((1u << pv) - 1u)); }
   const unsigned ub = (t >> P.ch_pu) & 1u;
 #pragma unroll
-  for (int i = 0; i < 2; i++)
+  for (int i = 0; i < 3; i++)
     if (i < P.ch_m) t |= ((((unsigned)P.ch_c >> i) & 1u) ^ ub) << P.ch_pv[i];
   return t;
 }

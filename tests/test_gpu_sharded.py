@@ -111,6 +111,8 @@ def test_chunk_pipeline_chunks_are_independent(n, world, symmetric, dtype):
     edges = [e for e in edges if e[0] < n and e[1] < n]
     lut, _ = H.lut_from_table(table, 1)
     grp = LocalShardGroup(n, world, dtype=dtype, symmetric=symmetric)
+    if (n, world, symmetric) == (28, 2, True):
+        grp.set_option("persistent_ctas", 32)       # fewer CTAs: the planner may cut the shard into eight chunks
     grp.set_cost_maxkcut(n, edges, 1, lut)
     d8 = c_oracle.maxcut_diag_u8(n, edges)
     rng = np.random.default_rng(n + world)
@@ -129,6 +131,8 @@ def test_chunk_pipeline_chunks_are_independent(n, world, symmetric, dtype):
         assert got[2] == ref[2] and got[3] == ref[3] and abs(got[4] - 1) < (1e-4 if dtype == "complex64" else 1e-11)
         assert H.rel_err(got[0], whole[0]) < tol * 0.01 and H.rel_err(got[1], whole[1]) < tol * 0.01, (p, got, whole)
     assert seen_chunks >= 2 or (n, dtype) == (24, "complex128"), "no plan of this configuration had chunks"
+    if (n, world, symmetric) == (28, 2, True):
+        assert seen_chunks == 8
     grp.close()
 
 
