@@ -17,6 +17,7 @@ import numpy as np  # noqa: E402
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--qubits", type=int, default=26)
+    ap.add_argument("--mixer", default="x", help="x: MaxCut + X + Plus; grover: QUBO + Grover(Dicke) + Dicke (full sharded register)")
     args = ap.parse_args()
     import networkx as nx
     import torch
@@ -33,16 +34,25 @@ def main():
     G = nx.random_regular_graph(3, n, seed=42)
     opt = [COBYLA, {"maxiter": 12, "tol": 1e-3}]
     grid = {"gamma": [0, np.pi, 4], "beta": [0, np.pi, 4]}
-    q = QAOA(problem=problems.MaxCut(G), mixer=mixers.X(), initialstate=initialstates.Plus(), optimizer=opt,
-             backend=B200Backend(device=local_rank, dtype="complex64", sharded=True))
+    if args.mixer == "grover":
+        rs = np.random.RandomState(7)
+        Qm, cv, k = rs.rand(n, n) / n, rs.rand(n) - 0.5, n // 3
+
+        def parts():
+            return dict(problem=problems.QUBO(Q=Qm, c=cv, b=0.0), mixer=mixers.Grover(initialstates.Dicke(k)),
+                        initialstate=initialstates.Dicke(k))
+        grid = {"gamma": [0, 2.0, 4], "beta": [0, np.pi, 4]}
+    else:
+        def parts():
+            return dict(problem=problems.MaxCut(G), mixer=mixers.X(), initialstate=initialstates.Plus())
+    q = QAOA(optimizer=opt, backend=B200Backend(device=local_rank, dtype="complex64", sharded=True), **parts())
     q.optimize(depth=2, angles=grid)
     if rank == 0:
         print("sharded register: %s, 2^%d stored amplitudes per GPU" % (
             "symmetric half (twisted coordinates)" if q._get_engine().symmetric else "full", q._get_engine().eng.local_qubits))
         # same landscape on a single-GPU engine, and every iterate the sharded optimiser visited re-evaluated there
         # (comparing two optimiser RUNS is ill-posed: the seed is a symmetric grid point and rounding noise picks the branch)
-        one = QAOA(problem=problems.MaxCut(G), mixer=mixers.X(), initialstate=initialstates.Plus(), optimizer=opt,
-                   backend=B200Backend(device=local_rank, dtype="complex64"))
+        one = QAOA(optimizer=opt, backend=B200Backend(device=local_rank, dtype="complex64"), **parts())
         one.sample_cost_landscape(grid)
         err = np.abs(q.Exp_sampled_p1 - one.Exp_sampled_p1).max() / np.abs(one.Exp_sampled_p1).max()
         print("landscape max rel diff sharded vs single GPU: %.2e" % err)

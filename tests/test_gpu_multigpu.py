@@ -46,3 +46,19 @@ def test_dist_sharded_engine_against_the_oracle(world, n, dtype):
     assert len(rep["checks"]) >= 3
     for c in rep["checks"]:
         assert c["ok"] and c["rel_err"] < (1e-4 if dtype == "complex64" else 1e-9), c
+
+
+@pytest.mark.parametrize("mixer", ["x", "grover"])
+def test_public_api_on_a_sharded_register(mixer):
+    """QAOA(..., backend=B200Backend(sharded=True)) under torchrun on 2 GPUs (scripts/qaoa_sharded_demo.py): landscape and
+    optimiser iterates of the sharded register equal the single-GPU engine's -- MaxCut + X + Plus on the symmetric
+    sharded register, QUBO + Grover(Dicke) + Dicke on the full one"""
+    if _gpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29641" if mixer == "x" else "29642", os.path.join(os.path.dirname(HERE), "scripts", "qaoa_sharded_demo.py"),
+           "--qubits", "24", "--mixer", mixer]
+    proc = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    print(proc.stdout[-1500:])
+    print(proc.stderr[-1500:])
+    assert proc.returncode == 0 and "OK" in proc.stdout
