@@ -552,6 +552,27 @@ def run_single(args, local_rank):
         except Exception as exc:  # noqa: BLE001  (a side leg must never cost the bench line)
             return {"failed": repr(exc)}
 
+    def parity_leg(n_par=28):
+        """the engine (symmetric and full register) against the C oracle in this very job, same angles, n = 28"""
+        from oracle import c_oracle
+        c_oracle.build()
+        c_oracle.use_all_cores()
+        e28 = workload(n_par)
+        ref = c_oracle.run(n_par, c_oracle.maxcut_diag_u8(n_par, e28), ang, "complex128", blocked=True)
+        res = []
+        for symm in (1, 0):
+            Ep = eng.Engine(n_par, "complex64", device=local_rank)
+            Ep.set_option("symmetric", symm)
+            Ep.set_cost_maxkcut(n_par, e28, 1, np.array([0, 1], dtype=np.uint8))
+            got = Ep.energy(ang)
+            Ep.close()
+            rel = float(abs(got[0] - ref[0]) / abs(ref[0]))
+            res.append({"n": n_par, "p": p, "register": "symmetric" if symm else "full", "energy": float(-got[0]),
+                        "oracle": float(-ref[0]), "rel_err": rel, "extremes_equal": bool(got[2] == ref[2] and got[3] == ref[3]),
+                        "ok": bool(rel < 1e-4 and abs(got[1] - ref[1]) < 2e-4 * abs(ref[1]) and got[2] == ref[2] and got[3] == ref[3])})
+        return res
+
+    parity = None if args.no_cpu_baseline else side(parity_leg)
     landscape = None if args.no_landscape else side(landscape_leg, local_rank, 1)
     config4 = None if args.no_config4 else side(config4_leg, local_rank)
     optimize = None if args.no_optimize else side(optimize_leg, local_rank, n=n)
@@ -625,6 +646,8 @@ def run_single(args, local_rank):
             line["cpu_baseline"] = cpu_sample(c_oracle, ns, p, n, 3, ang)[1]
         except Exception as exc:  # noqa: BLE001
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % exc}
+    if parity is not None:
+        line["parity"] = parity          # last, so that a tail of the line shows it
     print(json.dumps(line), flush=True)
 
 
