@@ -203,6 +203,17 @@ int qaoa_get_stream2(qaoa_engine_t* h, unsigned long long* stream_out);
  * returns the raw local statistics {sum p, sum p c, sum p c^2, min c, max c} (combine as for qaoa_shard_finish). */
 int qaoa_shard_grover_step(qaoa_engine_t* h, int step, int p, const double* angles, int n_angles,
                            const double* dot_global, double* out5);
+/* Sampling (QAOA.hist, qaoa/qaoa.py:1134-1172) and exact CVaR (statistic.py:132-142) on a sharded register: the local
+ * halves of qaoa_sample / qaoa_cvar.  With option keep_state = 1 an evaluation (qaoa_shard_begin ... / the Grover steps)
+ * leaves every rank's shard of the final state in HBM (full sharded register only).  qaoa_shard_chunk_probs: probability
+ * mass of every 2^16-amplitude chunk of the local shard (out = NULL: only their number); qaoa_shard_locate: the LOCAL basis
+ * index of each shot given its chunk and the residual mass inside it; qaoa_shard_cvar_digit: one 8-bit digit of the
+ * weighted quantile select over the local shard (out512 = mass[256], mass x cost[256]; key_bits = 8 / 32 / 64).  The
+ * driver gathers / all-reduces these small arrays (qaoa_b200/sharded.py). */
+int qaoa_shard_chunk_probs(qaoa_engine_t* h, double* out, unsigned long long cap, unsigned long long* n_out);
+int qaoa_shard_locate(qaoa_engine_t* h, int shots, const uint32_t* chunk_of, const double* resid, uint64_t* out_idx);
+int qaoa_shard_cvar_digit(qaoa_engine_t* h, unsigned long long prefix, int shift, int check_prefix, double* out512,
+                          int* key_bits);
 
 /* Planner dump (no device needed): the tile plan the engine would build for this configuration, as JSON -- tile shapes,
  * passes, their step programs, which qubit of which layer every butterfly round mixes, which layer's phase separator a

@@ -1652,7 +1652,9 @@ void shard_grover_step(Engine* h, int step, int p, const double* ang, const doub
     h2d(h, h->d_coefdot, cd, sizeof(cd));
   }
   const bool last = step == p;
-  const int flags = last ? (EW_AXPY | EW_REDUCE) : ((step == 0 ? EW_INIT : EW_AXPY) | EW_PHASE | EW_DOT | EW_STORE);
+  const int flags = last ? (EW_AXPY | EW_REDUCE | (h->keep_state ? EW_STORE : 0))
+                         : ((step == 0 ? EW_INIT : EW_AXPY) | EW_PHASE | EW_DOT | EW_STORE);
+  if (last) { h->last_valid = true; h->last_path = 0; h->last_scale = 1.0; h->last_gsign = 1; h->last_z.assign(h->n, 0); }
   const double gamma = last ? 0.0 : ang[2 * step];
   const bool fast = sizeof(real) == 4 && !h->force_generic && h->init.kind == h->sub.kind && h->init.k == h->sub.k &&
       h->init.amp == h->sub.amp && (h->init.kind == INIT_PLUS || h->init.kind == INIT_DICKE) &&
@@ -2057,6 +2059,8 @@ double qaoa_get_counter(qaoa_engine_t* h, const char* key) {
   if (k == "prog_launches") return h->prog_launches;
   if (k == "bytes_alg") return h->bytes_alg;
   if (k == "diag_kind") return h->dinfo.kind;
+  if (k == "diag_c0") return h->dinfo.c0;
+  if (k == "diag_delta") return h->dinfo.delta;
   if (k == "device") return h->device;
   if (k == "compact_size") return (double)h->n_compact;
   if (k == "symmetric_plans") { double s = 0; for (auto& kv : h->plans) s += kv.second.z2 ? 1 : 0; return s; }
@@ -2691,11 +2695,11 @@ int qaoa_shard_begin(qaoa_engine_t* h, int p, const double* angles, int n_angles
   if (h->world < 2) fail("not a sharded engine");
   if (!angles) fail("null angles");
   check_ready(h, p, n_angles);
-  if (h->keep_state) fail("sharded engine: keep_state is not supported");
+  if (h->keep_state && h->ztw_mode) fail("sharded symmetric register: the final state cannot be kept (use the full sharded register)");
   if (!h->peers_state_set || !h->peers_diag_set) fail("sharded engine: peer pointers have not been set");
   Plan& pl = get_plan(h, p);
   ensure_state(h, 1);
-  tile_prepare(h, pl, angles, n_angles, 1, false);
+  tile_prepare(h, pl, angles, n_angles, 1, h->keep_state != 0);
   if (n_passes) *n_passes = (int)pl.passes.size();
   API_END(h)
 }
@@ -2728,6 +2732,69 @@ int qaoa_shard_finish_device(qaoa_engine_t* h, double* d_out5) {
   if (h->world < 2) fail("not a sharded engine");
   if (!d_out5) fail("null output");
   tile_finalize(h, d_out5, true);
+  API_END(h)
+}
+
+// ---- sampling and exact CVaR on a sharded register: the local halves of qaoa_sample / qaoa_cvar --------------------
+// After an evaluation with option keep_state = 1 every rank holds its shard of the final state.  The caller (sharded.py)
+// gathers the per-chunk probability sums of all ranks, deals the shots out to (rank, chunk, residual), has every rank
+// locate its own shots, and all-reduces the per-digit histograms of the weighted quantile select.
+int qaoa_shard_chunk_probs(qaoa_engine_t* h, double* out, unsigned long long cap, unsigned long long* n_out) {
+  API_BEGIN(h)
+  if (!h->keep_state || !h->last_valid || !h->state) fail("no kept state: set option keep_state=1 and evaluate first");
+  const int chunk_log2 = std::min(h->El - h->qshift, 16);
+  const size_t nchunks = (h->N + ((size_t)1 << chunk_log2) - 1) >> chunk_log2;
+  if (n_out) *n_out = nchunks;
+  if (out) {
+    if (cap < nchunks) fail("chunk buffer too small");
+    DevTmp t_sums(nchunks * 8);
+    double* d_sums = t_sums.as<double>();
+    if (h->dtype == QAOA_DTYPE_C64) chunk_prob_kernel<float><<<(unsigned)nchunks, 256, 0, h->stream>>>((const float*)h->state, h->N, chunk_log2, d_sums);
+    else chunk_prob_kernel<double><<<(unsigned)nchunks, 256, 0, h->stream>>>((const double*)h->state, h->N, chunk_log2, d_sums);
+    CUDA_OK(cudaGetLastError());
+    h->launches += 1;
+    d2h(h, out, d_sums, nchunks * 8);
+  }
+  API_END(h)
+}
+
+// out_idx: LOCAL basis indices (the caller adds the shard's offset)
+int qaoa_shard_locate(qaoa_engine_t* h, int shots, const uint32_t* chunk_of, const double* resid, uint64_t* out_idx) {
+  API_BEGIN(h)
+  if (!h->keep_state || !h->last_valid || !h->state) fail("no kept state: set option keep_state=1 and evaluate first");
+  if (shots < 1) return 0;
+  if (!chunk_of || !resid || !out_idx) fail("null pointer");
+  const int chunk_log2 = std::min(h->El - h->qshift, 16);
+  DevTmp t_chunk((size_t)shots * 4), t_resid((size_t)shots * 8), t_out((size_t)shots * 8);
+  h2d(h, t_chunk.as<unsigned>(), chunk_of, (size_t)shots * 4);
+  h2d(h, t_resid.as<double>(), resid, (size_t)shots * 8);
+  if (h->dtype == QAOA_DTYPE_C64) sample_locate_kernel<float><<<shots, 256, 0, h->stream>>>((const float*)h->state, h->N, chunk_log2, t_chunk.as<unsigned>(), t_resid.as<double>(), t_out.as<unsigned long long>());
+  else sample_locate_kernel<double><<<shots, 256, 0, h->stream>>>((const double*)h->state, h->N, chunk_log2, t_chunk.as<unsigned>(), t_resid.as<double>(), t_out.as<unsigned long long>());
+  CUDA_OK(cudaGetLastError());
+  h->launches += 1;
+  d2h(h, out_idx, t_out.as<unsigned long long>(), (size_t)shots * 8);
+  API_END(h)
+}
+
+// one digit of the weighted quantile select over the LOCAL shard: out512 = {mass[256], mass x cost[256]}
+int qaoa_shard_cvar_digit(qaoa_engine_t* h, unsigned long long prefix, int shift, int check_prefix, double* out512,
+                          int* key_bits) {
+  API_BEGIN(h)
+  if (!h->keep_state || !h->last_valid || !h->state) fail("no kept state: set option keep_state=1 and evaluate first");
+  if (key_bits) *key_bits = h->dinfo.kind == DIAG_U8 ? 8 : (h->dinfo.kind == DIAG_U32FX ? 32 : 64);
+  if (out512) {
+    const int grid = grid_for(h->N, 256);
+    DevTmp t_part((size_t)grid * 512 * 8), t_sum(512 * 8);
+    if (h->dtype == QAOA_DTYPE_C64)
+      cvar_digit_kernel<float><<<grid, 256, 0, h->stream>>>((const float*)h->state, h->diag, h->dinfo, h->N, prefix, shift, check_prefix, t_part.as<double>());
+    else
+      cvar_digit_kernel<double><<<grid, 256, 0, h->stream>>>((const double*)h->state, h->diag, h->dinfo, h->N, prefix, shift, check_prefix, t_part.as<double>());
+    CUDA_OK(cudaGetLastError());
+    sum_partials_kernel<<<2, 256, 0, h->stream>>>(t_part.as<double>(), grid, 512, t_sum.as<double>());
+    CUDA_OK(cudaGetLastError());
+    h->launches += 2;
+    d2h(h, out512, t_sum.as<double>(), 512 * 8);
+  }
   API_END(h)
 }
 
@@ -2798,7 +2865,6 @@ int qaoa_shard_grover_step(qaoa_engine_t* h, int step, int p, const double* angl
   check_ready(h, p, n_angles);
   if (step < 0 || step > p) fail("step out of range");
   if (step > 0 && !dot_global) fail("the global dot product of the previous step is required");
-  if (h->keep_state) fail("sharded engine: keep_state is not supported");
   if (h->init.kind == INIT_STATEVECTOR || h->sub.kind == INIT_STATEVECTOR) fail("sharded engine: statevector states are not supported");
   if (h->dtype == QAOA_DTYPE_C64) shard_grover_step<float>(h, step, p, angles, dot_global, out5);
   else shard_grover_step<double>(h, step, p, angles, dot_global, out5);

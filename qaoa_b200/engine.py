@@ -90,6 +90,10 @@ def load_library():
         "qaoa_sample": (ctypes.c_int, [H, ctypes.c_int, _c_double_p, ctypes.c_int, ctypes.c_int, _c_double_p, _c_uint64_p]),
         "qaoa_extreme_solutions": (ctypes.c_int, [H, ctypes.c_int, _c_double_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                                   _c_uint64_p, ctypes.POINTER(ctypes.c_int), _c_double_p]),
+        "qaoa_shard_chunk_probs": (ctypes.c_int, [H, _c_double_p, ctypes.c_ulonglong, ctypes.POINTER(ctypes.c_ulonglong)]),
+        "qaoa_shard_locate": (ctypes.c_int, [H, ctypes.c_int, ctypes.POINTER(ctypes.c_uint32), _c_double_p, _c_uint64_p]),
+        "qaoa_shard_cvar_digit": (ctypes.c_int, [H, ctypes.c_ulonglong, ctypes.c_int, ctypes.c_int, _c_double_p,
+                                                 ctypes.POINTER(ctypes.c_int)]),
         "qaoa_get_stream": (ctypes.c_int, [H, ctypes.POINTER(ctypes.c_ulonglong)]),
         "qaoa_get_stream2": (ctypes.c_int, [H, ctypes.POINTER(ctypes.c_ulonglong)]),
         "qaoa_shard_chunk_info": (ctypes.c_int, [H, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int), ctypes.c_int]),
@@ -412,6 +416,33 @@ class Engine:
 
     def shard_run_pass(self, i):
         self._check(self._lib.qaoa_shard_run_pass(self._h, int(i)))
+
+    def shard_chunk_probs(self):
+        """probability mass of every 2^16-amplitude chunk of the kept local shard"""
+        n = ctypes.c_ulonglong()
+        self._check(self._lib.qaoa_shard_chunk_probs(self._h, None, 0, ctypes.byref(n)))
+        out = np.empty(int(n.value), dtype=np.float64)
+        self._check(self._lib.qaoa_shard_chunk_probs(self._h, _dptr(out), out.size, ctypes.byref(n)))
+        return out
+
+    def shard_locate(self, chunk_of, resid):
+        chunk_of = np.ascontiguousarray(chunk_of, dtype=np.uint32)
+        resid = np.ascontiguousarray(resid, dtype=np.float64)
+        out = np.empty(chunk_of.size, dtype=np.uint64)
+        if chunk_of.size:
+            self._check(self._lib.qaoa_shard_locate(self._h, int(chunk_of.size), chunk_of.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)),
+                                                    _dptr(resid), out.ctypes.data_as(_c_uint64_p)))
+        return out
+
+    def shard_cvar_key_bits(self):
+        kb = ctypes.c_int()
+        self._check(self._lib.qaoa_shard_cvar_digit(self._h, 0, 0, 0, None, ctypes.byref(kb)))
+        return int(kb.value)
+
+    def shard_cvar_digit(self, prefix, shift, check):
+        out = np.empty(512, dtype=np.float64)
+        self._check(self._lib.qaoa_shard_cvar_digit(self._h, int(prefix), int(shift), int(bool(check)), _dptr(out), None))
+        return out
 
     def stream_handle(self):
         """the engine's cudaStream_t (integer) -- for torch.cuda.ExternalStream"""

@@ -85,6 +85,70 @@ def pipeline_segments(cross_flags, closed):
     return segs
 
 
+def cvar_select(alpha, key_bits, digit_hist, decode):
+    """Weighted quantile select over an order-preserving integer key of the cost, most significant 8-bit digit first
+    (the host half of qaoa_cvar, csrc/engine.cu): digit_hist(prefix, shift, check) returns the GLOBAL 512-entry histogram
+    {mass[256], mass x cost[256]} of that digit among the keys matching the prefix; decode(key) -> cost."""
+    prefix, above_mass, above_pc, total, thr_mass = 0, 0.0, 0.0, None, 0.0
+    for shift in range(key_bits - 8, -1, -8):
+        check = shift != key_bits - 8
+        hist = np.asarray(digit_hist(prefix, shift, check), dtype=np.float64)
+        if not check:
+            total = float(hist[:256].sum())
+            if not total > 0.0:
+                raise _eng.EngineError("state has zero norm")
+        want = alpha * total
+        am, ap, dstar = above_mass, above_pc, 0
+        for d in range(255, -1, -1):
+            if am + hist[d] >= want or d == 0:
+                dstar = d
+                break
+            am += hist[d]
+            ap += hist[256 + d]
+        if hist[dstar] <= 0.0:
+            nz = np.flatnonzero(hist[:256] > 0.0)
+            if nz.size:
+                dstar = int(nz[0])
+        above_mass, above_pc, thr_mass = am, ap, float(hist[dstar])
+        prefix = (prefix << 8) | dstar
+    cthr = decode(prefix)
+    take = min(max(alpha * total - above_mass, 0.0), thr_mass)
+    return (above_pc + take * cthr) / (above_mass + take)
+
+
+def decode_cost_key(kind, c0, delta):
+    """key -> cost for the diagonal kinds of the engine (1: U8, 2: U32FX, 3: F64 sign-flipped bit pattern)"""
+    if int(kind) == 3:
+        def dec(key):
+            bits = (key & 0x7FFFFFFFFFFFFFFF) if key >> 63 else (~key) & 0xFFFFFFFFFFFFFFFF
+            return float(np.array([bits], dtype=np.uint64).view(np.float64)[0])
+        return dec
+    return lambda key: c0 + delta * float(key)
+
+
+def deal_shots(u, chunk_sums):
+    """u: uniform numbers in [0, 1); chunk_sums[r]: probability mass of every chunk of rank r's shard.  Returns per rank
+    (shot indices, local chunk ids, residual mass inside the chunk) -- the host half of qaoa_sample over several shards."""
+    sizes = [len(c) for c in chunk_sums]
+    cum = np.cumsum(np.concatenate(chunk_sums))
+    total = cum[-1]
+    if not total > 0.0:
+        raise _eng.EngineError("state has zero norm")
+    t = np.clip(np.asarray(u, dtype=np.float64), 0.0, 1.0) * total
+    c = np.minimum(np.searchsorted(cum, t, side="right"), len(cum) - 1)
+    mass = np.diff(np.concatenate([[0.0], cum]))
+    for i in range(len(c)):                   # never land in an empty chunk
+        while c[i] > 0 and mass[c[i]] <= 0.0:
+            c[i] -= 1
+    resid = t - np.where(c > 0, cum[np.maximum(c - 1, 0)], 0.0)
+    starts = np.concatenate([[0], np.cumsum(sizes)])
+    out = []
+    for r in range(len(chunk_sums)):
+        mine = np.flatnonzero((c >= starts[r]) & (c < starts[r + 1]))
+        out.append((mine, (c[mine] - starts[r]).astype(np.uint32), resid[mine]))
+    return out
+
+
 class _ShardedSurface:
     """Engine-like methods shared by the two drivers (fan a call out to the local engine(s))."""
 
@@ -227,6 +291,40 @@ class LocalShardGroup(_ShardedSurface):
             for e in self.engines:
                 e.shard_run_pass(i)
         return combine_partials([e.shard_finish() for e in self.engines])
+
+    def _evaluate_keeping_state(self, angles):
+        if self.symmetric:
+            raise NotImplementedError("sharded symmetric register: the final state cannot be kept; use symmetric=False")
+        self.set_option("keep_state", 1)
+        try:
+            return self.energy(angles)
+        except Exception:
+            self.set_option("keep_state", 0)
+            raise
+
+    def sample(self, angles, shots, seed=None):
+        """``shots`` basis indices drawn from |psi(angles)|^2 of the WHOLE register (QAOA.hist, qaoa/qaoa.py:1134-1172)"""
+        self._evaluate_keeping_state(angles)
+        try:
+            u = np.random.default_rng(seed).random(int(shots))
+            deal = deal_shots(u, [e.shard_chunk_probs() for e in self.engines])
+            out = np.zeros(int(shots), dtype=np.uint64)
+            for r, (e, (mine, chunk, resid)) in enumerate(zip(self.engines, deal)):
+                out[mine] = e.shard_locate(chunk, resid) + (np.uint64(r) << np.uint64(e.local_qubits))
+            return out
+        finally:
+            self.set_option("keep_state", 0)
+
+    def cvar(self, angles, alpha):
+        """exact CVaR_alpha of the final state's cost distribution over all shards (statistic.py:132-142)"""
+        self._evaluate_keeping_state(angles)
+        try:
+            e0 = self.engines[0]
+            dec = decode_cost_key(e0.counter("diag_kind"), e0.counter("diag_c0"), e0.counter("diag_delta"))
+            return cvar_select(float(alpha), e0.shard_cvar_key_bits(),
+                               lambda pre, sh, ck: np.sum([e.shard_cvar_digit(pre, sh, ck) for e in self.engines], axis=0), dec)
+        finally:
+            self.set_option("keep_state", 0)
 
     def close(self):
         for e in self.engines:
@@ -428,6 +526,64 @@ class DistShardedEngine(_ShardedSurface):
             parts = self._parts_all.cpu().numpy().reshape(self.world, 5)
         eng.shard_sync()          # stream is idle: collects the per-pass event timings
         return combine_partials(parts)
+
+    def _host_tensor(self, arr, dtype):
+        import torch
+        dev = "cuda" if self._dist.get_backend(self.group) == "nccl" else "cpu"
+        return torch.as_tensor(np.ascontiguousarray(arr), dtype=dtype).to(dev)
+
+    def _evaluate_keeping_state(self, angles):
+        if self.symmetric:
+            raise NotImplementedError("sharded symmetric register: the final state cannot be kept; use symmetric=False")
+        self.eng.set_option("keep_state", 1)
+        try:
+            return self.energy(angles)
+        except Exception:
+            self.eng.set_option("keep_state", 0)
+            raise
+
+    def sample(self, angles, shots, seed=None):
+        """``shots`` basis indices drawn from |psi(angles)|^2 of the WHOLE register (QAOA.hist, qaoa/qaoa.py:1134-1172);
+        collective, identical on every rank: rank 0's uniform numbers are broadcast, the per-chunk masses of all shards
+        gathered, every rank locates the shots that fall into its own shard, one all-reduce assembles the indices."""
+        import torch
+
+        dist = self._dist
+        self._evaluate_keeping_state(angles)
+        try:
+            u = self._host_tensor(np.random.default_rng(seed).random(int(shots)), torch.float64)
+            dist.broadcast(u, src=dist.get_global_rank(self.group, 0) if self.group is not None else 0, group=self.group)
+            mine_sums = self._host_tensor(self.eng.shard_chunk_probs(), torch.float64)
+            sums = [torch.empty_like(mine_sums) for _ in range(self.world)]
+            dist.all_gather(sums, mine_sums, group=self.group)
+            deal = deal_shots(u.cpu().numpy(), [t.cpu().numpy() for t in sums])
+            mine, chunk, resid = deal[self.rank]
+            out = np.zeros(int(shots), dtype=np.int64)
+            out[mine] = (self.eng.shard_locate(chunk, resid) + (np.uint64(self.rank) << np.uint64(self.eng.local_qubits))).astype(np.int64)
+            t = self._host_tensor(out, torch.int64)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+            return t.cpu().numpy().astype(np.uint64)
+        finally:
+            self.eng.set_option("keep_state", 0)
+
+    def cvar(self, angles, alpha):
+        """exact CVaR_alpha over all shards: the per-digit histograms of the weighted quantile select are all-reduced"""
+        import torch
+
+        dist = self._dist
+        self._evaluate_keeping_state(angles)
+        try:
+            eng = self.eng
+
+            def digit(prefix, shift, check):
+                t = self._host_tensor(eng.shard_cvar_digit(prefix, shift, check), torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+                return t.cpu().numpy()
+
+            dec = decode_cost_key(eng.counter("diag_kind"), eng.counter("diag_c0"), eng.counter("diag_delta"))
+            return cvar_select(float(alpha), eng.shard_cvar_key_bits(), digit, dec)
+        finally:
+            self.eng.set_option("keep_state", 0)
 
     def close(self):
         """collective: every rank unmaps its peers before any rank frees the buffers they map"""

@@ -136,6 +136,51 @@ def test_chunk_pipeline_chunks_are_independent(n, world, symmetric, dtype):
     grp.close()
 
 
+@pytest.mark.parametrize("case", ["x-u8-c64", "x-qubo-c128", "grover-qubo-c64"])
+def test_sampling_and_cvar_on_a_sharded_register(case):
+    """QAOA.hist / cvar < 1 on a sharded (full) register: every rank keeps its shard of the final state, the per-chunk
+    masses / per-digit histograms are combined across the shards (sharded.py deal_shots, cvar_select).  Same uniform
+    numbers => the same shots as the single engine's sampler; CVaR equal to the single engine's."""
+    from qaoa_b200 import engine as eng
+    from qaoa_b200.sharded import LocalShardGroup
+
+    n, world = 20, 4
+    dtype = "complex128" if case.endswith("c128") else "complex64"
+    grp = LocalShardGroup(n, world, dtype=dtype)
+    one = eng.Engine(n, dtype=dtype)
+    if "u8" in case:
+        edges, colors, table = H.regular_maxcut(n)
+        lut, _ = H.lut_from_table(table, 1)
+        for E in (grp, one):
+            E.set_cost_maxkcut(n, edges, 1, lut)
+        gs = 1.0
+    else:
+        Q, c, b = H.random_qubo(n, seed=9)
+        for E in (grp, one):
+            E.set_cost_qubo(Q, c, b)
+        gs = 0.05
+    if case.startswith("grover"):
+        one.set_option("feasible_subspace", 0)
+        for E in (grp, one):
+            E.set_initial(eng.INIT_DICKE, 7)
+            E.set_mixer(eng.MIXER_GROVER, sub_kind=eng.INIT_DICKE, sub_k=7)
+    ang = np.random.default_rng(2).uniform(0, 2 * np.pi, size=6)
+    ang[0::2] *= gs
+    a = grp.sample(ang, 4096, seed=123)
+    b_ = one.sample(ang, 4096, seed=123)
+    assert a.shape == b_.shape and (a == b_).mean() > 0.995, (a[:8], b_[:8])
+    if case.startswith("grover"):
+        assert all(bin(int(x)).count("1") == 7 for x in a[:256])      # samples stay in the feasible subspace
+    tol = 1e-9 if dtype == "complex128" else 2e-5
+    for alpha in (1.0, 0.3, 0.02):
+        got, want = grp.cvar(ang, alpha), one.cvar(ang, alpha)
+        assert abs(got - want) <= tol * max(1.0, abs(want)), (case, alpha, got, want)
+    e1, e2 = grp.energy(ang), one.energy(ang)          # back to the ordinary (not kept) evaluation
+    assert H.rel_err(e1[0], e2[0]) < TOL[dtype]
+    grp.close()
+    one.close()
+
+
 def test_sharded_multiangle_dicke_and_cot_form():
     """Per-qubit betas follow the logical qubit across the shard boundary; Dicke initial state generated
     per shard with the global popcount; beta = pi/2 exercises the interpreter's cross variant."""

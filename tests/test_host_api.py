@@ -871,3 +871,45 @@ def test_xy_angle_sign_and_the_portfolio_cvar_run():
     with pytest.raises(ValueError):
         mixers.XY(angle_sign=0)
     assert pickle.loads(pickle.dumps(mixers.XY(angle_sign=-1))).engine_betas([1.0]) == [-1.0]
+
+
+def test_host_halves_of_sharded_sampling_and_cvar():
+    """sharded.py deal_shots / cvar_select (pure host code): shots dealt out over per-shard chunk masses land where a
+    single CDF walk puts them; the digit-by-digit quantile select equals the sorted-tail definition of CVaR"""
+    from qaoa_b200.sharded import cvar_select, deal_shots, decode_cost_key
+
+    rng = np.random.default_rng(0)
+    sums = [rng.random(5) * (r + 1) for r in range(4)]
+    sums[2][1] = 0.0
+    u = rng.random(1000)
+    deal = deal_shots(u, sums)
+    flat = np.concatenate(sums)
+    cum = np.cumsum(flat)
+    seen = np.zeros(1000, dtype=bool)
+    for r, (mine, chunk, resid) in enumerate(deal):
+        g = chunk.astype(int) + 5 * r
+        assert np.all(flat[g] > 0) and np.all(resid >= -1e-15) and np.all(resid <= flat[g] + 1e-12)
+        assert np.allclose(np.where(g > 0, cum[np.maximum(g - 1, 0)], 0.0) + resid, u[mine] * cum[-1])
+        seen[mine] = True
+    assert seen.all()
+    # CVaR: 32-bit keys, random masses
+    keys = rng.integers(0, 2 ** 32, size=3000, dtype=np.uint64)
+    mass = rng.random(3000)
+    c0, delta = -3.0, 1e-7
+    cost = c0 + delta * keys.astype(np.float64)
+
+    def digit(prefix, shift, check):
+        sel = ((keys >> np.uint64(shift + 8)) == np.uint64(prefix)) if check else np.ones(len(keys), dtype=bool)
+        d = ((keys >> np.uint64(shift)) & np.uint64(255)).astype(int)[sel]
+        h = np.zeros(512)
+        np.add.at(h, d, mass[sel])
+        np.add.at(h, 256 + d, (mass * cost)[sel])
+        return h
+
+    for alpha in (1.0, 0.4, 0.01):
+        got = cvar_select(alpha, 32, digit, decode_cost_key(2, c0, delta))
+        assert got == pytest.approx(orc.exact_cvar(cost, mass / mass.sum(), alpha), rel=1e-9)
+    key = np.array([-2.5], dtype=np.float64).view(np.uint64)[0]
+    assert decode_cost_key(3, 0, 1)(int(~key & np.uint64(0xFFFFFFFFFFFFFFFF))) == -2.5      # negative doubles: all bits flipped
+    key = np.array([7.25], dtype=np.float64).view(np.uint64)[0]
+    assert decode_cost_key(3, 0, 1)(int(key | np.uint64(1 << 63))) == 7.25
