@@ -493,6 +493,8 @@ def run_single(args, local_rank):
     edges = workload(n)
     E = eng.Engine(n, "complex64", device=local_rank)
     E.set_option("symmetric", args.symmetric)
+    if args.column >= 0:
+        E.set_option("column_kernels", args.column)
     E.set_cost_maxkcut(n, edges, 1, np.array([0, 1], dtype=np.uint8))
     ang = angles_for(p, 1234)
     E.set_option("time_passes", 1)
@@ -667,6 +669,7 @@ def main():
     ap.add_argument("--no-config4", action="store_true", help="skip the BASELINE config 4 leg (n=30 Grover / multi-angle / XY)")
     ap.add_argument("--no-config5", action="store_true", help="N>1: skip the BASELINE config 5 leg (n=36, p=3)")
     ap.add_argument("--symmetric", type=int, default=1, help="0: always store the full register")
+    ap.add_argument("--column", type=int, default=-1, help="engine option column_kernels (-1: the engine's default)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
 

@@ -1,0 +1,257 @@
+// Column kernels: the high-tile passes of the balanced schedule (BOUND2, FINAL2) with DECOUPLED warps.
+//
+// STATUS (round 2): EXPERIMENT, OFF BY DEFAULT (engine option "column_kernels"), NOT part of the product path and not
+// covered by the parity suite.  First measurements on a B200 (n = 32, p = 5, symmetric register, scripts/col_debug.py,
+// bench.py --column 1): energies equal to the tile kernels' in most runs, but (a) BOUND2 takes 7.94 ms against 7.5-7.7 ms
+// for tile_prog_kernel<ProgBound2> (0.70 against 0.73-0.745 of the copy peak) -- three 64 KB stages are too few to keep
+// the TMA round trip (store, wait for the read, reload) off the critical path -- and (b) about one run in three shows
+// relative deviations of 1e-7 ... 1e-6 or a launch failure at 2^28 amplitudes and above, which a stream synchronise in
+// front of the kernel hides; the cause has not been found (the mbarrier protocol, the in-place transposes and the proxy
+// fences are argued below).  Kept as the record of the design that DESIGN.md section 8 item 1 describes.
+//
+// Why.  In a high tile (5 low element bits + 9 high bits) the low bits are spectators: the tile is 32 independent
+// columns of 2^9 amplitudes.  tile_prog_kernel gives every thread 32 amplitudes of 16 different rows and moves the
+// 9 high qubits through the registers with two BLOCK-wide transposes, i.e. four barriers per tile during which the
+// FMA pipe, the shared-memory pipe and the memory system take turns (BOUND2 = 8.5 us per tile against
+// 6.2 us of HBM time).  Here a WARP owns whole columns -- 2 x 512 amplitudes (element bit 0 and all 9 high bits) in
+// its 32 x 32 registers -- so the only exchanges left are lane <-> register transposes INSIDE the warp, and the sixteen
+// warps of an SM drift apart: one warp's butterflies run under another warp's transposes and a third one's loads.
+//
+// Data movement is the Blackwell way: a half tile (512 rows x 128 bytes) is ONE 5-D tensor-map box pair brought in by
+// the TMA unit (cp.async.bulk.tensor, SWIZZLE_128B, completion on an mbarrier) and written back by it; no thread computes
+// a global address.  Three 64 KB stage buffers rotate over the half tiles of a CTA; two groups of eight warps take the
+// half tiles in turn, so that one group computes while the other group's buffer is in flight.  The store of a half tile
+// is issued by an elected thread of its group, which then waits for the TMA to have READ the buffer and refills it with
+// the half tile three items ahead -- the only cross-group signal is the buffer's "full" mbarrier (one per buffer and
+// consuming group: a parity wait is only safe for a waiter that has seen every earlier phase of its barrier).
+//
+// Frames (t0..t13 = tile bits as in tile_kernel.cuh; rows r = t5..t13, chunk c = t1..t3, half h = t4, e = t0):
+//   FA: reg {e, r5..r8 = t10..t13}   lane {r0..r4 = t5..t9}       -- 16-byte accesses, the registers of frame A
+//   FB: reg {r0..r4 = t5..t9}        lane {e, r5..r8 = t10..t13}  --  8-byte accesses, the registers of frame C
+// so the round coefficients, phase tables and frame-C diagonal streams of the existing BOUND2 / FINAL2 plans are used
+// unchanged.  The transposes go through the warp's own column of the stage buffer, in place: the TMA swizzle
+// (16-byte chunk index XOR row & 7) makes the FA accesses conflict free; while the column is in transit its row r sits
+// in the slot of row rho(r) = r ^ ((r >> 3 ^ r >> 6) & 7), which makes the FB accesses conflict free as well.
+#pragma once
+#include <cuda.h>
+
+#include "tile_kernel.cuh"
+
+constexpr int COL_STAGE_BYTES = 65536;   // 512 rows x 128 bytes
+constexpr int COL_NSTAGE = 3;
+constexpr int COL_TAB_OFF = COL_NSTAGE * COL_STAGE_BYTES;             // 256-entry phase table (float2)
+constexpr int COL_TAU_OFF = COL_TAB_OFF + 2048;                       // round coefficients (floats)
+constexpr int COL_SCRATCH_OFF = COL_TAU_OFF + TILE_CANON_ROUNDS * TILE_ROUND_REALS * 4;
+constexpr int COL_BAR_OFF = COL_SCRATCH_OFF + 16 * 5 * 8;
+constexpr int COL_SMEM_BYTES = COL_BAR_OFF + 64;
+
+struct ColGeom {
+  int mid_bits;              // free element bits between bit 5 and the first high bit (tile index, low run)
+  unsigned long long tiles;  // tiles of this launch
+  unsigned tile0;            // first tile (chunked launches use the generic remap instead; here 0)
+};
+
+__device__ __forceinline__ unsigned col_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void col_mbar_init(unsigned bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void col_mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void col_mbar_wait(unsigned bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "COL_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra COL_DONE;\n"
+      "bra COL_WAIT;\n"
+      "COL_DONE:\n"
+      "}" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void col_tma_load(unsigned dst, const CUtensorMap* map, unsigned bar, int c0, int c1, int c2, int c3,
+                                             int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void col_tma_store(const CUtensorMap* map, unsigned src, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(map), "r"(src),
+               "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+}
+__device__ __forceinline__ void col_group_sync(int g) { asm volatile("bar.sync %0, 256;" ::"r"(1 + g) : "memory"); }
+
+// byte offset (inside a stage buffer) of the 16-byte chunk c of the slot of row r, TMA SWIZZLE_128B layout
+__device__ __forceinline__ unsigned col_slot(unsigned r, unsigned c) { return r * 128u + ((c ^ (r & 7u)) << 4); }
+__device__ __forceinline__ unsigned col_rho(unsigned r) { return r ^ (((r >> 3) ^ (r >> 6)) & 7u); }
+
+// FA -> FB: registers {e, r5..r8} / lanes {r0..r4}  ->  registers {r0..r4} / lanes {e, r5..r8}
+__device__ __forceinline__ void col_fa_to_fb(unsigned char* buf, unsigned c, int lane, float2 (&v)[32]) {
+#pragma unroll
+  for (int q = 0; q < 16; q++) {
+    const unsigned r = ((unsigned)q << 5) | (unsigned)lane;
+    *reinterpret_cast<float4*>(buf + col_slot(col_rho(r), c)) = make_float4(v[2 * q].x, v[2 * q].y, v[2 * q + 1].x, v[2 * q + 1].y);
+  }
+  __syncwarp();
+  const unsigned e = lane & 1u, hi = (unsigned)lane >> 1;
+#pragma unroll
+  for (int i = 0; i < 32; i++) {
+    const unsigned r = (hi << 5) | (unsigned)i;
+    v[i] = *reinterpret_cast<const float2*>(buf + col_slot(col_rho(r), c) + e * 8u);
+  }
+  __syncwarp();
+}
+// FB -> FA
+__device__ __forceinline__ void col_fb_to_fa(unsigned char* buf, unsigned c, int lane, float2 (&v)[32]) {
+  const unsigned e = lane & 1u, hi = (unsigned)lane >> 1;
+#pragma unroll
+  for (int i = 0; i < 32; i++) {
+    const unsigned r = (hi << 5) | (unsigned)i;
+    *reinterpret_cast<float2*>(buf + col_slot(col_rho(r), c) + e * 8u) = v[i];
+  }
+  __syncwarp();
+#pragma unroll
+  for (int q = 0; q < 16; q++) {
+    const unsigned r = ((unsigned)q << 5) | (unsigned)lane;
+    const float4 w = *reinterpret_cast<const float4*>(buf + col_slot(col_rho(r), c));
+    v[2 * q] = make_float2(w.x, w.y);
+    v[2 * q + 1] = make_float2(w.z, w.w);
+  }
+  __syncwarp();
+}
+
+// Prog: ProgBound2 (LOAD R XT R PHASE R XTI R STORE) or ProgFinal2 (LOAD R XT R REDUCE); complex64, U8 diagonal, one point.
+template <typename Prog>
+__global__ void __launch_bounds__(TILE_THREADS, 1)
+column_prog_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ TilePass P, ColGeom G,
+                   const float* __restrict__ tau, const double* __restrict__ phs, const void* __restrict__ tables,
+                   int tables_per_point, double* __restrict__ partials) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  constexpr bool HAS_RED = Prog::op(Prog::N - 1).type == TOP_REDUCE;
+  constexpr int so = Prog::stream_op();
+  const int tid = threadIdx.x, lane = tid & 31, g = tid >> 8, wi = (tid >> 5) & 7;
+  const unsigned c = (unsigned)wi;                 // chunk of the half row: element bits 1..3
+  float* tau_s = reinterpret_cast<float*>(smem_raw + COL_TAU_OFF);
+  const unsigned bar0 = col_smem_u32(smem_raw + COL_BAR_OFF);
+  // residents of the (single) point: round coefficients, reduction scale in pad slot 11, phase table
+  if (tid < P.tau_stride) {
+    float val = __ldg(tau + tid);
+    if (tid == 11) val = (float)__ldg(phs + 2 * P.nphases);
+    tau_s[tid] = val;
+  }
+  if constexpr (so >= 0) {
+    if constexpr (Prog::op(so >= 0 ? so : 0).type == TOP_PHASE) {
+      const float2* t = reinterpret_cast<const float2*>(tables) + (size_t)P.table_id[Prog::op(so).arg] * 256;
+      if (tid >= 256) reinterpret_cast<float2*>(smem_raw + COL_TAB_OFF)[tid - 256] = t[tid - 256];
+    }
+  }
+  if (tid == 0) {
+    for (int b = 0; b < 2 * COL_NSTAGE; b++) col_mbar_init(bar0 + 8 * b, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  Ctx<float2> cx;
+  cx.P = &P;
+  cx.lane = lane;
+  cx.warp = tid >> 5;
+  cx.tab = smem_raw + COL_TAB_OFF;
+  cx.scratch = reinterpret_cast<double*>(smem_raw + COL_SCRATCH_OFF);
+  cx.partials = partials;
+  cx.point = 0;
+  cx.smem = smem_raw;
+
+  const unsigned long long my_tiles = G.tiles > blockIdx.x ? (G.tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const unsigned long long n_items = 2 * my_tiles;
+  const unsigned mid_mask = (1u << G.mid_bits) - 1u;
+  auto tile_of = [&](unsigned long long J) { return chunk_tile(P, (unsigned)(blockIdx.x + (J >> 1) * gridDim.x)); };
+  auto issue_load = [&](unsigned long long J) {   // one thread
+    if (J >= n_items) return;
+    const unsigned t = tile_of(J), b = (unsigned)(J % COL_NSTAGE);
+    const unsigned dst = col_smem_u32(smem_raw) + b * COL_STAGE_BYTES;
+    // one "full" mbarrier per (buffer, consuming group): a buffer serves the two groups alternately, and a parity wait
+    // is only safe for a waiter that has seen every earlier phase of its barrier
+    const unsigned bar = bar0 + 8 * (2 * b + (unsigned)(J & 1));
+    col_mbar_expect_tx(bar, COL_STAGE_BYTES);
+    col_tma_load(dst, &tmap, bar, 0, (int)(J & 1), (int)(t & mid_mask), 0, (int)(t >> G.mid_bits));
+    col_tma_load(dst + 32768u, &tmap, bar, 0, (int)(J & 1), (int)(t & mid_mask), 256, (int)(t >> G.mid_bits));
+  };
+  if (tid == 0) for (int J = 0; J < COL_NSTAGE; J++) issue_load(J);
+
+  double acc[5] = {0.0, 0.0, 0.0, 1e300, -1e300};
+  if constexpr (HAS_RED) {
+    if (tid == 0) {
+      double* o = partials + ((size_t)blockIdx.x + P.ch_part0) * 5;
+      o[0] = 0.0; o[1] = 0.0; o[2] = 0.0; o[3] = 1e300; o[4] = -1e300;
+    }
+  }
+  float2 v[32];
+  for (unsigned long long J = g; J < n_items; J += 2) {
+    const unsigned b = (unsigned)(J % COL_NSTAGE);
+    unsigned char* buf = smem_raw + b * COL_STAGE_BYTES;
+    const unsigned t = tile_of(J);
+    // the tile's slice of the frame-C diagonal stream: the 32 bytes of the OLD kernel's thread (warp = t10..t13, lane =
+    // {e, t1..t3, t4}) are exactly this thread's 32 registers in frame FB
+    uint4 dq[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+    if constexpr (so >= 0) {
+      const uint4* s4 = reinterpret_cast<const uint4*>(P.streams[Prog::op(so).arg]);
+      const int ow = lane >> 1, ol = (lane & 1) | (wi << 1) | ((int)(J & 1) << 4);
+      dq[0] = __ldg(s4 + stream_chunk(t, ow, ol, 2, 0));
+      dq[1] = __ldg(s4 + stream_chunk(t, ow, ol, 2, 1));
+    }
+    col_mbar_wait(bar0 + 8 * (2 * b + (unsigned)g), (unsigned)((J / (2 * COL_NSTAGE)) & 1));
+    // LOAD (frame FA)
+#pragma unroll
+    for (int q = 0; q < 16; q++) {
+      const unsigned r = ((unsigned)q << 5) | (unsigned)lane;
+      const float4 w = *reinterpret_cast<const float4*>(buf + col_slot(r, c));
+      v[2 * q] = make_float2(w.x, w.y);
+      v[2 * q + 1] = make_float2(w.z, w.w);
+    }
+    __syncwarp();
+    // the program (its frames A / C are FA / FB here)
+    constexpr int N = Prog::N;
+#pragma unroll
+    for (int I = 1; I < N; I++) {
+      // (compile-time dispatch: Prog::op is constexpr and the loop is fully unrolled)
+      const COp op = Prog::op(I);
+      if (op.type == TOP_ROUND) {
+        if (op.mask == M_ALL) round_static<float2, M_ALL>(tau_s, v, op.arg);
+        else round_static<float2, M_HI4>(tau_s, v, op.arg);
+      } else if (op.type == TOP_XT) col_fa_to_fb(buf, c, lane, v);
+      else if (op.type == TOP_XTI) col_fb_to_fa(buf, c, lane, v);
+      else if (op.type == TOP_PHASE) op_phase_u8_regs<float2>(cx, v, dq);
+      else if (op.type == TOP_REDUCE) op_reduce_u8_regs<float2>(cx, v, dq, tau_s[11], acc);
+      else if (op.type == TOP_STORE) {
+#pragma unroll
+        for (int q = 0; q < 16; q++) {
+          const unsigned r = ((unsigned)q << 5) | (unsigned)lane;
+          *reinterpret_cast<float4*>(buf + col_slot(r, c)) = make_float4(v[2 * q].x, v[2 * q].y, v[2 * q + 1].x, v[2 * q + 1].y);
+        }
+      }
+    }
+    // hand the buffer on: store it (programs that store), then refill it with the half tile three items ahead
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes (results / transposes) before the TMA touches the buffer
+    col_group_sync(g);
+    if ((tid & 255) == 0) {
+      if constexpr (!HAS_RED) {
+        const unsigned src = col_smem_u32(buf);
+        col_tma_store(&tmap, src, 0, (int)(J & 1), (int)(t & mid_mask), 0, (int)(t >> G.mid_bits));
+        col_tma_store(&tmap, src + 32768u, 0, (int)(J & 1), (int)(t & mid_mask), 256, (int)(t >> G.mid_bits));
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      }
+      issue_load(J + COL_NSTAGE);
+    }
+  }
+  if constexpr (!HAS_RED) {
+    if ((tid & 255) == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+  if constexpr (HAS_RED) {
+    __syncthreads();
+    flush_acc<float2>(cx, acc, 0);
+  }
+}

@@ -12,6 +12,7 @@
 #include "../../include/qaoa_b200.h"
 #include "common.cuh"
 #include "kernels_misc.cuh"
+#include "column_kernel.cuh"
 #include "tile_kernel.cuh"
 
 namespace {
@@ -110,6 +111,9 @@ struct Engine {
   // overrides of the launch in flight (tile_launch_pass_chunk): stream, persistent CTAs, chunk
   cudaStream_t cur_stream = nullptr;
   int cur_ctas = 0, cur_ch_c = -1;
+  int column_kernels = 0;              // option "column_kernels": BOUND2 / FINAL2 on the warp-decoupled TMA kernels
+  int column_sync = 0;                 // debug: 1 = stream sync before a column kernel, 2 = after, 3 = both
+  std::map<std::pair<const void*, int>, CUtensorMap> tmaps;   // (state pointer, first high bit) -> tensor map
   int chunking = 1;                    // option "chunk_pipeline"
   int chunk_bits = 3;                  // option "chunk_bits": at most 2^chunk_bits chunks
 
@@ -1054,6 +1058,53 @@ void fill_point_params(Engine* h, const Plan& pl, const double* ang, double* tau
   if (final_scale_out) *final_scale_out = post[p - 1];
 }
 
+// ---- column kernels (column_kernel.cuh): tensor map of the state for a high tile shape --------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled tensor_map_encoder() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess || !p)
+      fail("cuTensorMapEncodeTiled is not available");
+    fn = (PFN_encodeTiled)p;
+  }
+  return fn;
+}
+
+// high tile shape = element bits 0..4 + nine CONSECUTIVE bits hp..hp+8 (complex64: element = 8 bytes).  The register of
+// `amps` elements is a 5-D tensor [16 (bits 0..3)][2 (bit 4)][2^(hp-5)][512 rows][amps >> (hp+9)]; a half tile is two
+// boxes of 256 rows x 128 bytes, SWIZZLE_128B.
+const CUtensorMap& column_tensor_map(Engine* h, void* state, int hp, size_t amps) {
+  auto key = std::make_pair((const void*)state, hp * 64 + (int)(63 - __builtin_clzll((unsigned long long)amps)));
+  auto it = h->tmaps.find(key);
+  if (it != h->tmaps.end()) return it->second;
+  CUtensorMap m;
+  const cuuint64_t dims[5] = {16, 2, (cuuint64_t)1 << (hp - 5), 512, (cuuint64_t)(amps >> (hp + 9))};
+  const cuuint64_t strides[4] = {128, 256, (cuuint64_t)8 << hp, (cuuint64_t)8 << (hp + 9)};   // bytes, dims 1..4
+  const cuuint32_t box[5] = {16, 1, 1, 256, 1};
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult rc = tensor_map_encoder()(&m, CU_TENSOR_MAP_DATA_TYPE_UINT64, 5, state, dims, strides, box, estr,
+                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS) fail("cuTensorMapEncodeTiled failed (" + std::to_string((int)rc) + ")");
+  h->tmaps[key] = m;
+  return h->tmaps[key];
+}
+
+// can this pass run on the column kernels?
+bool column_pass_ok(const Engine* h, const PlanPass& pp, int prog, int B) {
+  if (!h->column_kernels || h->dtype != QAOA_DTYPE_C64 || h->dinfo.kind != DIAG_U8 || B != 1) return false;
+  if (prog != PROG_BOUND2 && prog != PROG_FINAL2) return false;
+  if (pp.cross || pp.zshape) return false;
+  const TilePass& tp = pp.tp;
+  for (int j = 0; j < 5; j++) if (tp.pos[j] != j) return false;
+  for (int j = 6; j < TILE_BITS; j++) if (tp.pos[j] != tp.pos[5] + (j - 5)) return false;
+  return tp.pos[5] >= 5;
+}
+
 // returns the number of partial-result slots per point a REDUCE pass writes
 template <typename Elem>
 int launch_pass(Engine* h, const PlanPass& pp, bool use_prog, unsigned ntiles, int B, size_t point_stride_elems,
@@ -1101,6 +1152,32 @@ int launch_pass(Engine* h, const PlanPass& pp, bool use_prog, unsigned ntiles, i
                                                                       (const real*)d_tau, d_phs, h->d_tables,
                                                                       tables_per_point, h->dinfo, h->d_partials, (unsigned)B);
   };
+  if constexpr (ElemTraits<Elem>::IS_C64) {
+    if (column_pass_ok(h, pp, prog, B)) {
+      const int hp = tp.pos[5];
+      const CUtensorMap& tm = column_tensor_map(h, h->state, hp, point_stride_elems);
+      ColGeom G;
+      G.mid_bits = hp - 5;
+      G.tiles = ntiles;
+      G.tile0 = 0;
+      dim3 grid((unsigned)std::min<unsigned long long>(ntiles, (unsigned long long)lctas));
+      nparts = (int)grid.x;
+      if (tp.ch_m > 0) { tp.ch_part0 = tp.ch_c * (int)grid.x; nparts = (int)grid.x << tp.ch_m; }
+      if (h->column_sync & 1) CUDA_OK(cudaStreamSynchronize(lstream));
+      if (prog == PROG_BOUND2) {
+        CUDA_OK(cudaFuncSetAttribute(column_prog_kernel<ProgBound2>, cudaFuncAttributeMaxDynamicSharedMemorySize, COL_SMEM_BYTES));
+        column_prog_kernel<ProgBound2><<<grid, TILE_THREADS, COL_SMEM_BYTES, lstream>>>(tm, tp, G, (const float*)d_tau, d_phs, h->d_tables,
+                                                                                       tables_per_point, h->d_partials);
+      } else {
+        CUDA_OK(cudaFuncSetAttribute(column_prog_kernel<ProgFinal2>, cudaFuncAttributeMaxDynamicSharedMemorySize, COL_SMEM_BYTES));
+        column_prog_kernel<ProgFinal2><<<grid, TILE_THREADS, COL_SMEM_BYTES, lstream>>>(tm, tp, G, (const float*)d_tau, d_phs, h->d_tables,
+                                                                                       tables_per_point, h->d_partials);
+      }
+      CUDA_OK(cudaGetLastError());
+      if (h->column_sync & 2) CUDA_OK(cudaStreamSynchronize(lstream));
+      return nparts;
+    }
+  }
   if (zs) {
     switch (prog) {
       case PROG_FIRST_INIT: if (u8) go(tile_prog_kernel<Elem, ProgFirstInit, DIAG_U8, 2>); else go(tile_prog_kernel<Elem, ProgFirstInit, 0, 2>); break;
@@ -2019,6 +2096,8 @@ int qaoa_set_option(qaoa_engine_t* h, const char* key, double value) {
   else if (k == "batch_bytes") h->batch_bytes = (size_t)value;
   else if (k == "force_generic") h->force_generic = value != 0;
   else if (k == "layer_budget") h->layer_budget = value != 0;
+  else if (k == "column_kernels") h->column_kernels = value != 0;
+  else if (k == "column_sync") h->column_sync = (int)value;
   else if (k == "chunk_pipeline") { h->chunking = value != 0; invalidate(h); }
   else if (k == "chunk_bits") { h->chunk_bits = std::max(1, std::min(3, (int)value)); invalidate(h); }
   else if (k == "prefetch_dist") h->prefetch_dist = (int)value;
