@@ -196,6 +196,9 @@ int qaoa_shard_finish_device(qaoa_engine_t* h, double* d_out5);
 int qaoa_shard_chunk_info(qaoa_engine_t* h, int* n_chunks, int* closed, int cap);
 int qaoa_shard_run_pass_chunk(qaoa_engine_t* h, int pass, int chunk, int which_stream, int ctas);
 int qaoa_get_stream2(qaoa_engine_t* h, unsigned long long* stream_out);
+/* Timeline of the last evaluation timed with option time_passes = 1: per launch {program id, chunk (-1: whole pass),
+ * stream (0 main, 1 side), start ms, end ms} relative to the first launch; *n_out = number of launches. */
+int qaoa_get_timeline(qaoa_engine_t* h, double* out, int cap, int* n_out);
 /* Grover mixer on a sharded register (reference qaoa/mixers/grover_mixer.py:43-82 over |+> / |D^n_k>,
  * dicke_initialstate.py:23-56): no state exchange, one complex scalar per layer.  step = 0 .. p-1 runs layer `step`'s
  * sweep over the local shard and returns the LOCAL partial <s|v> in out5[0..1]; the caller sums it over the ranks

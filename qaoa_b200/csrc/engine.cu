@@ -220,8 +220,12 @@ struct Engine {
   int time_passes = 0;
   double pass_ms[PROG_COUNT] = {0}, pass_count[PROG_COUNT] = {0}, pass_bytes[PROG_COUNT] = {0};
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
-  struct PendingEv { int prog; size_t idx; double bytes; };
+  struct PendingEv { int prog; size_t idx; double bytes; int chunk; int side; };
   std::vector<PendingEv> ev_pending;
+  // timeline of the last harvested evaluation (option time_passes): start / end of every launch in ms after the first
+  // launch's start, with its program, chunk (-1: whole pass) and stream (0 main, 1 side) -- see qaoa_get_timeline
+  struct TimelineEntry { int prog, chunk, side; float t0, t1; };
+  std::vector<TimelineEntry> timeline;
   double last_device_ms = 0;
   cudaEvent_t ev_call0 = nullptr, ev_call1 = nullptr;
   bool ev_call_recorded = false;
@@ -1425,7 +1429,8 @@ void tile_launch_pass(Engine* h, size_t ip) {
   if (pp.has_reduce) ev.nparts = np;
   if (h->time_passes) {
     CUDA_OK(cudaEventRecord(h->ev_pool[evi].second, lstream));
-    h->ev_pending.push_back({use_prog ? pp.prog : (int)PROG_GENERIC, evi, pass_bytes});
+    h->ev_pending.push_back({use_prog ? pp.prog : (int)PROG_GENERIC, evi, pass_bytes, h->cur_ch_c,
+                             (h->cur_stream && h->cur_stream == h->stream2) ? 1 : 0});
   }
   h->launches += 1;
   if (use_prog && pp.prog != PROG_GENERIC) h->prog_launches += 1;
@@ -1781,8 +1786,14 @@ void energy_batch_body(Engine* h, int p, const double* angles, int n_angles, int
 
 // collects the per-pass event timings once the stream has drained
 void harvest_events(Engine* h) {
+  if (!h->ev_pending.empty()) h->timeline.clear();
   for (auto& pe : h->ev_pending) {
     float ms = 0;
+    float a = 0, b = 0;
+    const cudaEvent_t origin = h->ev_pool[h->ev_pending[0].idx].first;
+    if (cudaEventElapsedTime(&a, origin, h->ev_pool[pe.idx].first) == cudaSuccess &&
+        cudaEventElapsedTime(&b, origin, h->ev_pool[pe.idx].second) == cudaSuccess)
+      h->timeline.push_back({pe.prog, pe.chunk, pe.side, a, b});
     if (cudaEventElapsedTime(&ms, h->ev_pool[pe.idx].first, h->ev_pool[pe.idx].second) == cudaSuccess) {
       h->pass_ms[pe.prog] += ms;
       h->pass_count[pe.prog] += 1;
@@ -2904,6 +2915,19 @@ int qaoa_shard_run_pass_chunk(qaoa_engine_t* h, int pass, int chunk, int which_s
   h->cur_ch_c = chunk;     // < 0: the whole pass
   try { tile_launch_pass(h, (size_t)pass); } catch (...) { h->cur_stream = nullptr; h->cur_ctas = 0; h->cur_ch_c = -1; throw; }
   h->cur_stream = nullptr; h->cur_ctas = 0; h->cur_ch_c = -1;
+  API_END(h)
+}
+
+// launches of the last timed evaluation (option time_passes = 1): 5 doubles per launch {program id, chunk, stream,
+// start ms, end ms}; returns the number of launches in *n_out (out may be null)
+int qaoa_get_timeline(qaoa_engine_t* h, double* out, int cap, int* n_out) {
+  API_BEGIN(h)
+  if (n_out) *n_out = (int)h->timeline.size();
+  if (out)
+    for (int i = 0; i < cap && i < (int)h->timeline.size(); i++) {
+      const auto& e = h->timeline[i];
+      out[5 * i] = e.prog; out[5 * i + 1] = e.chunk; out[5 * i + 2] = e.side; out[5 * i + 3] = e.t0; out[5 * i + 4] = e.t1;
+    }
   API_END(h)
 }
 

@@ -96,6 +96,7 @@ def load_library():
                                                  ctypes.POINTER(ctypes.c_int)]),
         "qaoa_get_stream": (ctypes.c_int, [H, ctypes.POINTER(ctypes.c_ulonglong)]),
         "qaoa_get_stream2": (ctypes.c_int, [H, ctypes.POINTER(ctypes.c_ulonglong)]),
+        "qaoa_get_timeline": (ctypes.c_int, [H, _c_double_p, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]),
         "qaoa_shard_chunk_info": (ctypes.c_int, [H, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int), ctypes.c_int]),
         "qaoa_shard_run_pass_chunk": (ctypes.c_int, [H, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
         "qaoa_shard_finish_device": (ctypes.c_int, [H, ctypes.c_void_p]),
@@ -449,6 +450,14 @@ class Engine:
         out = ctypes.c_ulonglong()
         self._check(self._lib.qaoa_get_stream(self._h, ctypes.byref(out)))
         return int(out.value)
+
+    def timeline(self):
+        """launches of the last evaluation timed with option time_passes: rows {program id, chunk, stream, start ms, end ms}"""
+        n = ctypes.c_int()
+        self._check(self._lib.qaoa_get_timeline(self._h, None, 0, ctypes.byref(n)))
+        out = np.zeros((max(1, n.value), 5), dtype=np.float64)
+        self._check(self._lib.qaoa_get_timeline(self._h, _dptr(out), int(n.value), ctypes.byref(n)))
+        return out[: n.value]
 
     def stream2_handle(self):
         out = ctypes.c_ulonglong()
