@@ -269,6 +269,7 @@ class QAOA:
     def __getstate__(self):
         state = dict(self.__dict__)
         state["_engine"] = None  # device handles are re-created lazily after unpickling
+        state["_engine_full"] = None
         state.pop("_cvar_sorted", None)
         return state
 
@@ -304,6 +305,20 @@ class QAOA:
             self.mixer.lower_mixer(eng, trotter=self.number_trottersteps_mixer)
             self._engine = eng
         return self._engine
+
+    def _full_sharded_engine(self):
+        """the same circuit on the FULL sharded register (kept final states: hist(), cvar < 1); collective like _get_engine"""
+        if getattr(self, "_engine_full", None) is None:
+            from qaoa_b200.sharded import DistShardedEngine, default_device
+
+            device = getattr(self.backend, "device", None)
+            eng = DistShardedEngine(self.problem.N_qubits, dtype=self.backend.dtype,
+                                    device=default_device() if device is None else device, symmetric=False)
+            self.problem.lower_cost(eng)
+            self.initialstate.lower_initial(eng)
+            self.mixer.lower_mixer(eng, trotter=self.number_trottersteps_mixer)
+            self._engine_full = eng
+        return self._engine_full
 
     def _shard_symmetric(self):
         """MaxCut proper + X-type mixer + |+>, n even, complex64: cost(x) = cost(~x) and the state keeps that symmetry,
@@ -379,6 +394,10 @@ class QAOA:
         row = np.asarray(eng_row, dtype=np.float64)
         if not hasattr(eng, name):
             _reject("%s on a sharded register (single-GPU engines only)" % name)
+        if name in ("sample", "cvar") and getattr(eng, "symmetric", False) and getattr(self.backend, "sharded", False):
+            # the sharded SYMMETRIC register cannot keep its final state; sampling and CVaR of such a run use a second,
+            # full sharded register lowered from the same problem (built on first use; twice the stored amplitudes)
+            eng = self._full_sharded_engine()
         if not self._flips_active(row):
             return getattr(eng, name)(row, *args, **kw)
         n_init, per = eng.n_init, eng.n_gamma + eng.n_beta

@@ -64,6 +64,24 @@ def main():
             print("depth %d: %d iterates, best Exp %.6f" % (d, r.num_fval(), q.get_Exp(d)))
         print("optimiser iterates, max rel diff sharded vs single GPU: %.2e" % worst)
         assert err < 1e-4 and worst < 1e-4
+    # hist() and cvar < 1 on the sharded register (collective calls: every rank takes part; MaxCut runs use a second,
+    # full sharded register for them because the symmetric one cannot keep its final state)
+    best = q.optimization_results[2].get_best_angles()
+    q.sample_seed = 11
+    h = q.hist(best, 2048)
+    q.cvar = 0.25
+    cv = q._cvar_of(q._engine_row(best))
+    q.cvar = 1
+    if rank == 0:
+        assert sum(h.values()) == 2048
+        mean = sum(one.problem.cost(s) * c for s, c in h.items()) / 2048.0
+        e = one._get_engine().energy(np.asarray(one._engine_row(best)))
+        exact, var = e[0], e[1] - e[0] ** 2
+        z = abs(mean - exact) / np.sqrt(max(var, 1e-12) / 2048.0)
+        one.cvar = 0.25
+        cv1 = one._cvar_of(one._engine_row(best))
+        print("hist: sampled mean cost %.4f vs exact %.4f (z = %.2f); CVaR(0.25) sharded %.6f vs single GPU %.6f" % (mean, exact, z, cv, cv1))
+        assert z < 5.0 and abs(cv - cv1) < 1e-4 * max(1.0, abs(cv1))
         print("OK")
     dist.barrier()
     dist.destroy_process_group()
