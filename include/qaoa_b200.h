@@ -59,7 +59,13 @@ const char* qaoa_global_error(void);
  * "shard_symmetric" (sharded engines, to be set to 1 right after qaoa_create_sharded, before any buffer is exported and
  * before the cost function is set: the engine holds 2^(n-1-log2 world) STORED amplitudes of the symmetric half register
  * in twisted shard coordinates -- see "Sharded registers" below; complex64, n even, MaxCut cost, X / multi-angle X mixer
- * and |+> only, anything else fails). */
+ * and |+> only, anything else fails),
+ * "layer_budget" (default 1: multi-angle mixers keep the lifted butterfly form for every qubit of a layer whose TOTAL
+ * growth fits the exponent range, however close a single angle is to pi/2; 0 = the fixed per-angle bound),
+ * "chunk_pipeline" (default 1) / "chunk_bits" (default 3): sharded registers, the plan marks passes that may be launched
+ * chunk by chunk (up to 2^chunk_bits chunks) so that cross passes overlap local passes (qaoa_shard_chunk_info),
+ * "column_kernels" (default 0, EXPERIMENTAL: BOUND2 / FINAL2 passes on the TMA / mbarrier kernels of
+ * csrc/column_kernel.cuh, not validated) and "column_sync" (their debug hook). */
 int qaoa_set_option(qaoa_engine_t* h, const char* key, double value);
 double qaoa_get_counter(qaoa_engine_t* h, const char* key); /* "launches", "bytes_alg", ... */
 
