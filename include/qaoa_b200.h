@@ -39,7 +39,7 @@ typedef struct qaoa_engine qaoa_engine_t;
 #define QAOA_INIT_DICKE 1        /* qaoa/initialstates/dicke_initialstate.py:23-56       */
 #define QAOA_INIT_STATEVECTOR 2  /* qaoa/initialstates/statevector_initialstate.py:19-33 */
 #define QAOA_INIT_PLUS_PHASES 3  /* qaoa/initialstates/plus_parameterized_initialstate.py:25-64: k phases lead the
-                                    angle vector (n_init = k); registers that fit one CTA only */
+                                    angle vector (n_init = k); beyond one CTA: X-type mixers, prepared state + tile plan */
 
 /* Creates an engine for n_qubits on CUDA device `device`.  Replaces the construction of the
  * transpiled parameterised circuit + AerSimulator instance (qaoa/qaoa.py:204, 418-520). */
@@ -80,7 +80,8 @@ int qaoa_set_cost_maxkcut(qaoa_engine_t* h, int n_nodes, int n_edges, const int3
 /* Same cost, but the phase separator takes ONE GAMMA PER TERM: edge e belongs to term term_of_edge[e]
  * (MaxCutFree: one term per edge, qaoa/problems/maxcut_free_problem.py:31-99; MaxCutOrbit: one per edge orbit,
  * qaoa/problems/maxcut_orbit_problem.py:51-181) and layer d multiplies by exp(i sum_k gamma_{d,k} term_k(x)).
- * Angle layout per layer: n_terms gammas, then the betas.  Registers that fit one CTA only (n <= 14 / 13). */
+ * Angle layout per layer: n_terms gammas, then the betas.  Registers that fit one CTA (n <= 14 / 13) use term diagonals
+ * in the single-CTA kernel; larger ones run layer by layer (edge phases on the fly, X-type mixers). */
 int qaoa_set_cost_maxkcut_terms(qaoa_engine_t* h, int n_nodes, int n_edges, const int32_t* u, const int32_t* v,
                                 const double* w, const int32_t* term_of_edge, int n_terms, int bits_per_node,
                                 const uint8_t* lut, int fixed_node, int fixed_colour);

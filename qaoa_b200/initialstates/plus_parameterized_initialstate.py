@@ -1,6 +1,6 @@
 """|+>^n followed by one RZ(phi_q) per qubit (public surface of reference
 qaoa/initialstates/plus_parameterized_initialstate.py:25-64): ``num_phases`` parameters (default N_qubits) that
-lead the flat angle vector (``n_init``, qaoa/qaoa.py:937-990).  Registers that fit one CTA only."""
+lead the flat angle vector (``n_init``, qaoa/qaoa.py:937-990).  Registers beyond one CTA run layer by layer on the tile passes (X-type mixers)."""
 
 from .base_initialstate import InitialState
 from qaoa_b200 import engine as _eng

@@ -2,7 +2,7 @@
 
 Edge e (in ``G.edges()`` order of the canonical graph, the order the reference's zero-padded parameter
 names sort in) gets its own angle: layer d multiplies by ``exp(i sum_e gamma_{d,e} w_e [cut_e])``.  Lowered as
-one cost term per edge (``qaoa_set_cost_maxkcut_terms``); registers that fit one CTA only."""
+one cost term per edge (``qaoa_set_cost_maxkcut_terms``); registers beyond one CTA run layer by layer on the tile passes (X-type mixers)."""
 
 from .maxcut_problem import MaxCut
 
