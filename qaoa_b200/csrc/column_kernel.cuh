@@ -1,13 +1,14 @@
 // Column kernels: the high-tile passes of the balanced schedule (BOUND2, FINAL2) with DECOUPLED warps.
 //
-// STATUS (round 2): EXPERIMENT, OFF BY DEFAULT (engine option "column_kernels"), NOT part of the product path and not
-// covered by the parity suite.  First measurements on a B200 (n = 32, p = 5, symmetric register, scripts/col_debug.py,
-// bench.py --column 1): energies equal to the tile kernels' in most runs, but (a) BOUND2 takes 7.94 ms against 7.5-7.7 ms
-// for tile_prog_kernel<ProgBound2> (0.70 against 0.73-0.745 of the copy peak) -- three 64 KB stages are too few to keep
-// the TMA round trip (store, wait for the read, reload) off the critical path -- and (b) about one run in three shows
-// relative deviations of 1e-7 ... 1e-6 or a launch failure at 2^28 amplitudes and above, which a stream synchronise in
-// front of the kernel hides; the cause has not been found (the mbarrier protocol, the in-place transposes and the proxy
-// fences are argued below).  Kept as the record of the design that DESIGN.md section 8 item 1 describes.
+// STATUS (round 2): OFF BY DEFAULT (engine option "column_kernels").  Parity: tests/test_gpu_parity.py
+// test_column_kernels_match_the_tile_kernels (energies equal to the tile kernels' to 1e-9, repeated, and to the C oracle).
+// Speed on a B200 (n = 32, p = 5, symmetric register, bench.py --column 1): BOUND2 7.74-7.77 ms against 7.63 ms for
+// tile_prog_kernel<ProgBound2> on the same box -- no gain yet: with 227 KB of shared memory there are three 64 KB
+// stages for two groups, so a buffer's TMA round trip (store, wait for the read, reload) has half an item to complete.
+// Lesson kept in the code: the first version produced deviations of 1e-7 ... 1e-6 or a launch failure in about one run in
+// three at 2^28 amplitudes and above.  Cause: the state is written through the GENERIC proxy by the kernel that ran
+// before and read here through the ASYNC proxy (TMA), and vice versa for the kernel that follows -- a kernel boundary
+// does not order the two proxies; fence.proxy.async before the first TMA load and after the last TMA store does.
 //
 // Why.  In a high tile (5 low element bits + 9 high bits) the low bits are spectators: the tile is 32 independent
 // columns of 2^9 amplitudes.  tile_prog_kernel gives every thread 32 amplitudes of 16 different rows and moves the
@@ -179,7 +180,11 @@ column_prog_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     col_tma_load(dst, &tmap, bar, 0, (int)(J & 1), (int)(t & mid_mask), 0, (int)(t >> G.mid_bits));
     col_tma_load(dst + 32768u, &tmap, bar, 0, (int)(J & 1), (int)(t & mid_mask), 256, (int)(t >> G.mid_bits));
   };
-  if (tid == 0) for (int J = 0; J < COL_NSTAGE; J++) issue_load(J);
+  if (tid == 0) {
+    // the state was written through the generic proxy (by the kernel before this one); the TMA reads it through the async proxy
+    asm volatile("fence.proxy.async;" ::: "memory");
+    for (int J = 0; J < COL_NSTAGE; J++) issue_load(J);
+  }
 
   double acc[5] = {0.0, 0.0, 0.0, 1e300, -1e300};
   if constexpr (HAS_RED) {
@@ -248,7 +253,11 @@ column_prog_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     }
   }
   if constexpr (!HAS_RED) {
-    if ((tid & 255) == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if ((tid & 255) == 0) {
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+      asm volatile("fence.proxy.async;" ::: "memory");     // ... and the next kernel reads it through the generic proxy
+      __threadfence();
+    }
   }
   if constexpr (HAS_RED) {
     __syncthreads();
