@@ -226,7 +226,15 @@ column_prog_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
       if (op.type == TOP_ROUND) {
         if (op.mask == M_ALL) round_static<float2, M_ALL>(tau_s, v, op.arg);
         else round_static<float2, M_HI4>(tau_s, v, op.arg);
-      } else if (op.type == TOP_XT) col_fa_to_fb(buf, c, lane, v);
+      } else if (op.type == TOP_XT) {
+        col_fa_to_fb(buf, c, lane, v);
+        if constexpr (HAS_RED) {
+          // a reducing program is done with the buffer here: refill it now, under the rest of the item's arithmetic
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          col_group_sync(g);
+          if ((tid & 255) == 0) issue_load(J + COL_NSTAGE);
+        }
+      }
       else if (op.type == TOP_XTI) col_fb_to_fa(buf, c, lane, v);
       else if (op.type == TOP_PHASE) op_phase_u8_regs<float2>(cx, v, dq);
       else if (op.type == TOP_REDUCE) op_reduce_u8_regs<float2>(cx, v, dq, tau_s[11], acc);
@@ -238,18 +246,18 @@ column_prog_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         }
       }
     }
-    // hand the buffer on: store it (programs that store), then refill it with the half tile three items ahead
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes (results / transposes) before the TMA touches the buffer
-    col_group_sync(g);
-    if ((tid & 255) == 0) {
-      if constexpr (!HAS_RED) {
+    // hand the buffer on: store it, then refill it with the half tile three items ahead
+    if constexpr (!HAS_RED) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes before the TMA reads the buffer
+      col_group_sync(g);
+      if ((tid & 255) == 0) {
         const unsigned src = col_smem_u32(buf);
         col_tma_store(&tmap, src, 0, (int)(J & 1), (int)(t & mid_mask), 0, (int)(t >> G.mid_bits));
         col_tma_store(&tmap, src + 32768u, 0, (int)(J & 1), (int)(t & mid_mask), 256, (int)(t >> G.mid_bits));
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        issue_load(J + COL_NSTAGE);
       }
-      issue_load(J + COL_NSTAGE);
     }
   }
   if constexpr (!HAS_RED) {
