@@ -1,6 +1,6 @@
 // Column kernels: the high-tile passes of the balanced schedule (BOUND2, FINAL2) with DECOUPLED warps.
 //
-// STATUS (round 2): OFF BY DEFAULT (engine option "column_kernels").  Parity: tests/test_gpu_parity.py
+// STATUS (round 2): OFF BY DEFAULT (engine option "column_kernels").  Parity: tests/test_gpu_zzz_column_kernels.py
 // test_column_kernels_match_the_tile_kernels (energies equal to the tile kernels' to 1e-9, repeated, and to the C oracle).
 // Speed on a B200 (n = 32, p = 5, symmetric register, bench.py --column 1): BOUND2 7.74-7.77 ms against 7.63 ms for
 // tile_prog_kernel<ProgBound2> on the same box -- no gain yet: with 227 KB of shared memory there are three 64 KB
