@@ -2,9 +2,11 @@
 //
 // STATUS (round 2): OFF BY DEFAULT (engine option "column_kernels").  Parity: tests/test_gpu_zzz_column_kernels.py
 // test_column_kernels_match_the_tile_kernels (energies equal to the tile kernels' to 1e-9, repeated, and to the C oracle).
-// Speed on a B200 (n = 32, p = 5, symmetric register, bench.py --column 1): BOUND2 7.74-7.77 ms against 7.63 ms for
-// tile_prog_kernel<ProgBound2> on the same box -- no gain yet: with 227 KB of shared memory there are three 64 KB
-// stages for two groups, so a buffer's TMA round trip (store, wait for the read, reload) has half an item to complete.
+// Speed on a B200 (n = 32, p = 5, symmetric register, bench.py --column 1 / 0 on the same box): BOUND2 7.25 ms against
+// 7.33 ms for tile_prog_kernel<ProgBound2>, FINAL2 3.89 against 3.98 ms, but the tile passes that FOLLOW a column kernel
+// run 2 % slower (MID 6.00 against 5.86 ms), so the evaluation is 68.5-68.7 ms either way -- parity, not a gain: both
+// designs keep the shared-memory pipe ~70 % busy (profiles/r03i_column_kernels_n28.md); with 227 KB of shared memory there
+// are three 64 KB stages for two groups, so a buffer's TMA round trip (store, wait for the read, reload) has half an item.
 // Lesson kept in the code: the first version produced deviations of 1e-7 ... 1e-6 or a launch failure in about one run in
 // three at 2^28 amplitudes and above.  Cause: the state is written through the GENERIC proxy by the kernel that ran
 // before and read here through the ASYNC proxy (TMA), and vice versa for the kernel that follows -- a kernel boundary
@@ -89,35 +91,45 @@ __device__ __forceinline__ void col_group_sync(int g) { asm volatile("bar.sync %
 __device__ __forceinline__ unsigned col_slot(unsigned r, unsigned c) { return r * 128u + ((c ^ (r & 7u)) << 4); }
 __device__ __forceinline__ unsigned col_rho(unsigned r) { return r ^ (((r >> 3) ^ (r >> 6)) & 7u); }
 
+// The slot of the in-transit row rho(r) splits into a per-thread part and a compile-time part joined by ONE xor:
+//   FA (r = q << 5 | lane):  rho(r) & 31 = lane ^ fl ^ fq,  fl = (lane >> 3) & 7,  fq = ((q << 2) ^ (q >> 1)) & 7
+//       slot = (q << 12) + (baseA ^ KA(q)),  baseA = (lane ^ fl) << 7 | (c ^ ((lane ^ fl) & 7)) << 4,  KA = fq << 7 | fq << 4
+//   FB (r = hi << 5 | i):    rho(r) & 31 = Ci ^ fh,  Ci = i ^ (i >> 3),  fh = ((hi << 2) ^ (hi >> 1)) & 7
+//       slot = baseB ^ KB(i),  baseB = hi << 12 | fh << 7 | ((c ^ fh) & 7) << 4 | e << 3,  KB = Ci << 7 | (Ci & 7) << 4
+struct ColAddr {
+  unsigned baseA, baseB;
+};
+__device__ __forceinline__ ColAddr col_addr(unsigned c, int lane) {
+  ColAddr a;
+  const unsigned l = (unsigned)lane, fl = (l >> 3) & 7u, lx = l ^ fl;
+  a.baseA = (lx << 7) | ((c ^ (lx & 7u)) << 4);
+  const unsigned e = l & 1u, hi = l >> 1, fh = ((hi << 2) ^ (hi >> 1)) & 7u;
+  a.baseB = (hi << 12) | (fh << 7) | (((c ^ fh) & 7u) << 4) | (e << 3);
+  return a;
+}
+__device__ __forceinline__ constexpr unsigned col_ka(int q) { return ((((unsigned)q << 2) ^ ((unsigned)q >> 1)) & 7u) * 0x90u; }
+__device__ __forceinline__ constexpr unsigned col_kb(int i) {
+  return ((((unsigned)i ^ ((unsigned)i >> 3)) & 31u) << 7) | ((((unsigned)i ^ ((unsigned)i >> 3)) & 7u) << 4);
+}
+
 // FA -> FB: registers {e, r5..r8} / lanes {r0..r4}  ->  registers {r0..r4} / lanes {e, r5..r8}
-__device__ __forceinline__ void col_fa_to_fb(unsigned char* buf, unsigned c, int lane, float2 (&v)[32]) {
+__device__ __forceinline__ void col_fa_to_fb(unsigned char* buf, const ColAddr& A, float2 (&v)[32]) {
 #pragma unroll
-  for (int q = 0; q < 16; q++) {
-    const unsigned r = ((unsigned)q << 5) | (unsigned)lane;
-    *reinterpret_cast<float4*>(buf + col_slot(col_rho(r), c)) = make_float4(v[2 * q].x, v[2 * q].y, v[2 * q + 1].x, v[2 * q + 1].y);
-  }
+  for (int q = 0; q < 16; q++)
+    *reinterpret_cast<float4*>(buf + (q << 12) + (A.baseA ^ col_ka(q))) = make_float4(v[2 * q].x, v[2 * q].y, v[2 * q + 1].x, v[2 * q + 1].y);
   __syncwarp();
-  const unsigned e = lane & 1u, hi = (unsigned)lane >> 1;
 #pragma unroll
-  for (int i = 0; i < 32; i++) {
-    const unsigned r = (hi << 5) | (unsigned)i;
-    v[i] = *reinterpret_cast<const float2*>(buf + col_slot(col_rho(r), c) + e * 8u);
-  }
+  for (int i = 0; i < 32; i++) v[i] = *reinterpret_cast<const float2*>(buf + (A.baseB ^ col_kb(i)));
   __syncwarp();
 }
 // FB -> FA
-__device__ __forceinline__ void col_fb_to_fa(unsigned char* buf, unsigned c, int lane, float2 (&v)[32]) {
-  const unsigned e = lane & 1u, hi = (unsigned)lane >> 1;
+__device__ __forceinline__ void col_fb_to_fa(unsigned char* buf, const ColAddr& A, float2 (&v)[32]) {
 #pragma unroll
-  for (int i = 0; i < 32; i++) {
-    const unsigned r = (hi << 5) | (unsigned)i;
-    *reinterpret_cast<float2*>(buf + col_slot(col_rho(r), c) + e * 8u) = v[i];
-  }
+  for (int i = 0; i < 32; i++) *reinterpret_cast<float2*>(buf + (A.baseB ^ col_kb(i))) = v[i];
   __syncwarp();
 #pragma unroll
   for (int q = 0; q < 16; q++) {
-    const unsigned r = ((unsigned)q << 5) | (unsigned)lane;
-    const float4 w = *reinterpret_cast<const float4*>(buf + col_slot(col_rho(r), c));
+    const float4 w = *reinterpret_cast<const float4*>(buf + (q << 12) + (A.baseA ^ col_ka(q)));
     v[2 * q] = make_float2(w.x, w.y);
     v[2 * q + 1] = make_float2(w.z, w.w);
   }
@@ -194,6 +206,8 @@ column_prog_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     }
   }
   float2 v[32];
+  const ColAddr CA = col_addr(c, lane);
+  const unsigned io_off = col_slot((unsigned)lane, c);     // slot of row (q << 5 | lane) = (q << 12) + io_off
   for (unsigned long long J = g; J < n_items; J += 2) {
     const unsigned b = (unsigned)(J % COL_NSTAGE);
     unsigned char* buf = smem_raw + b * COL_STAGE_BYTES;
@@ -201,18 +215,20 @@ column_prog_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
     // the tile's slice of the frame-C diagonal stream: the 32 bytes of the OLD kernel's thread (warp = t10..t13, lane =
     // {e, t1..t3, t4}) are exactly this thread's 32 registers in frame FB
     uint4 dq[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+    const uint4* dqp = nullptr;
     if constexpr (so >= 0) {
       const uint4* s4 = reinterpret_cast<const uint4*>(P.streams[Prog::op(so).arg]);
       const int ow = lane >> 1, ol = (lane & 1) | (wi << 1) | ((int)(J & 1) << 4);
-      dq[0] = __ldg(s4 + stream_chunk(t, ow, ol, 2, 0));
-      dq[1] = __ldg(s4 + stream_chunk(t, ow, ol, 2, 1));
+      dqp = s4 + stream_chunk(t, ow, ol, 2, 0);      // chunk 1 sits 32 uint4 further on
+      // pulled into L2 now, loaded right before the step that needs it (two registers less across the rounds)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(dqp));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(dqp + 32));
     }
     col_mbar_wait(bar0 + 8 * (2 * b + (unsigned)g), (unsigned)((J / (2 * COL_NSTAGE)) & 1));
     // LOAD (frame FA)
 #pragma unroll
     for (int q = 0; q < 16; q++) {
-      const unsigned r = ((unsigned)q << 5) | (unsigned)lane;
-      const float4 w = *reinterpret_cast<const float4*>(buf + col_slot(r, c));
+      const float4 w = *reinterpret_cast<const float4*>(buf + (q << 12) + io_off);
       v[2 * q] = make_float2(w.x, w.y);
       v[2 * q + 1] = make_float2(w.z, w.w);
     }
@@ -227,7 +243,7 @@ column_prog_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
         if (op.mask == M_ALL) round_static<float2, M_ALL>(tau_s, v, op.arg);
         else round_static<float2, M_HI4>(tau_s, v, op.arg);
       } else if (op.type == TOP_XT) {
-        col_fa_to_fb(buf, c, lane, v);
+        col_fa_to_fb(buf, CA, v);
         if constexpr (HAS_RED) {
           // a reducing program is done with the buffer here: refill it now, under the rest of the item's arithmetic
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -235,15 +251,18 @@ column_prog_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_consta
           if ((tid & 255) == 0) issue_load(J + COL_NSTAGE);
         }
       }
-      else if (op.type == TOP_XTI) col_fb_to_fa(buf, c, lane, v);
-      else if (op.type == TOP_PHASE) op_phase_u8_regs<float2>(cx, v, dq);
-      else if (op.type == TOP_REDUCE) op_reduce_u8_regs<float2>(cx, v, dq, tau_s[11], acc);
+      else if (op.type == TOP_XTI) col_fb_to_fa(buf, CA, v);
+      else if (op.type == TOP_PHASE) {
+        dq[0] = __ldg(dqp); dq[1] = __ldg(dqp + 32);
+        op_phase_u8_regs<float2>(cx, v, dq);
+      } else if (op.type == TOP_REDUCE) {
+        dq[0] = __ldg(dqp); dq[1] = __ldg(dqp + 32);
+        op_reduce_u8_regs<float2>(cx, v, dq, tau_s[11], acc);
+      }
       else if (op.type == TOP_STORE) {
 #pragma unroll
-        for (int q = 0; q < 16; q++) {
-          const unsigned r = ((unsigned)q << 5) | (unsigned)lane;
-          *reinterpret_cast<float4*>(buf + col_slot(r, c)) = make_float4(v[2 * q].x, v[2 * q].y, v[2 * q + 1].x, v[2 * q + 1].y);
-        }
+        for (int q = 0; q < 16; q++)
+          *reinterpret_cast<float4*>(buf + (q << 12) + io_off) = make_float4(v[2 * q].x, v[2 * q].y, v[2 * q + 1].x, v[2 * q + 1].y);
       }
     }
     // hand the buffer on: store it, then refill it with the half tile three items ahead
