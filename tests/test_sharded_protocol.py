@@ -428,3 +428,93 @@ def test_sharded_grover_protocol_gloo(world, tmp_path):
         got, ref = row[:5], row[5:9]
         assert np.allclose(got[:4], ref, rtol=1e-12), (r, got, ref)
         assert abs(got[4] - 1.0) < 1e-12
+
+
+class SamplingShmEngine(GroverShmEngine):
+    """adds the local halves of sampling / CVaR (Engine.shard_chunk_probs / shard_locate / shard_cvar_digit) in numpy:
+    chunks of 16 amplitudes, F64 cost keys (sign-flipped bit pattern, 8 digits)"""
+
+    CH = 4
+
+    def __init__(self, n, rank, world, diag, s_state):
+        super().__init__(n, rank, world, diag, s_state)
+        self.local_qubits = self.nl
+        self.options = {}
+
+    def set_option(self, key, value):
+        self.options[key] = value
+
+    def counter(self, key):
+        return {"diag_kind": 3.0, "diag_c0": 0.0, "diag_delta": 1.0}[key]
+
+    def _probs(self):
+        assert self.options.get("keep_state") == 1, "sampling / CVaR need the kept final state"
+        return np.abs(self.v) ** 2
+
+    def shard_chunk_probs(self):
+        return self._probs().reshape(-1, 1 << self.CH).sum(axis=1)
+
+    def shard_locate(self, chunk_of, resid):
+        p = self._probs().reshape(-1, 1 << self.CH)
+        out = np.zeros(len(chunk_of), dtype=np.uint64)
+        for i, (c, r) in enumerate(zip(chunk_of, resid)):
+            cum = np.cumsum(p[int(c)])
+            out[i] = (int(c) << self.CH) + min(int(np.searchsorted(cum, r, side="right")), (1 << self.CH) - 1)
+        return out
+
+    def shard_cvar_key_bits(self):
+        return 64
+
+    def shard_cvar_digit(self, prefix, shift, check):
+        bits = self.c_loc.view(np.uint64)
+        keys = np.where(bits >> np.uint64(63), ~bits, bits | np.uint64(1 << 63))
+        p = self._probs()
+        sel = ((keys >> np.uint64(shift)) >> np.uint64(8)) == np.uint64(prefix) if check else np.ones(len(keys), dtype=bool)
+        d = ((keys >> np.uint64(shift)) & np.uint64(255)).astype(int)[sel]
+        h = np.zeros(512)
+        np.add.at(h, d, p[sel])
+        np.add.at(h, 256 + d, (p * self.c_loc)[sel])
+        return h
+
+
+def _sampling_worker(rank, world, port, n, k, out_dir):
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from qaoa_b200 import engine as eng_mod
+        from qaoa_b200 import sharded
+
+        Q, c, b = H.random_qubo(n, seed=4)
+        diag = np.ascontiguousarray(orc.qubo_diag(Q, c, b))
+        s_state = orc.dicke_state(n, k)
+        eng = sharded.DistShardedEngine(n, engine_factory=lambda r, w: SamplingShmEngine(n, r, w, diag, s_state))
+        eng.set_mixer(eng_mod.MIXER_GROVER, sub_kind=eng_mod.INIT_DICKE, sub_k=k)
+        ang = np.array([0.03, 0.7, 0.05, 1.9])
+        idx = eng.sample(ang, 512, seed=3 + rank)        # rank 0's uniform numbers are broadcast: identical everywhere
+        cv = eng.cvar(ang, 0.3)
+        assert eng.eng.options.get("keep_state") == 0       # kept states are switched off again
+        psi = orc.evolve(orc.Spec(n, diag, mixer=("grover", s_state), init=s_state), ang)
+        want = orc.exact_cvar(diag, np.abs(psi) ** 2, 0.3)
+        np.save(os.path.join(out_dir, "s%d.npy" % rank), np.concatenate([idx.astype(np.float64), [cv, want]]))
+        dist.barrier()
+        eng.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_sampling_and_cvar_protocol_gloo(world, tmp_path):
+    """hist() / cvar < 1 on a sharded register under torch.distributed (gloo): broadcast uniform numbers, gathered chunk
+    masses, shots located on the owning rank and summed back, all-reduced digit histograms of the quantile select"""
+    import torch.multiprocessing as mp
+
+    n, k = 10, 4
+    mp.spawn(_sampling_worker, args=(world, _free_port(), n, k, str(tmp_path)), nprocs=world, join=True)
+    rows = [np.load(tmp_path / ("s%d.npy" % r)) for r in range(world)]
+    for row in rows:
+        assert np.array_equal(row[:512], rows[0][:512])                 # the same shots on every rank
+        assert abs(row[512] - row[513]) <= 1e-10 * max(1.0, abs(row[513]))   # CVaR = the oracle's
+    idx = rows[0][:512].astype(np.int64)
+    assert all(bin(int(x)).count("1") == k for x in idx)                # Grover over Dicke: samples stay feasible
