@@ -149,6 +149,9 @@ int qaoa_cost_distribution(qaoa_engine_t* h, int p, const double* angles, int n_
  * cost representation (integer, 32-bit fixed point, double): a weighted quantile select on the device, one sweep of the
  * kept final state per 8-bit digit of the cost key.  out2 = {CVaR, threshold cost}. */
 int qaoa_cvar(qaoa_engine_t* h, int p, const double* angles, int n_angles, double alpha, double* out2);
+/* Same, plus the statistics of the same evaluation: out7 = {CVaR, threshold cost, E[cost], E[cost^2], min, max, norm}
+ * (QAOA.loss with cvar < 1 needs both, qaoa/qaoa.py:885-935: one circuit evaluation instead of two). */
+int qaoa_cvar_stats(qaoa_engine_t* h, int p, const double* angles, int n_angles, double alpha, double* out7);
 
 /* ---- Sharded registers: one engine per GPU (one process per GPU), the register split on its top
  * log2(world) qubits; rank r holds the basis indices [r * 2^(n - log2 world), (r+1) * 2^(n - log2 world)).

@@ -2691,6 +2691,18 @@ int qaoa_cvar(qaoa_engine_t* h, int p, const double* angles, int n_angles, doubl
   API_END(h)
 }
 
+// the same call, returning the five statistics of the SAME evaluation as well: out7 = {CVaR, threshold cost, E[cost],
+// E[cost^2], min, max, norm} -- a cvar < 1 run needs one circuit evaluation per angle vector, not two
+int qaoa_cvar_stats(qaoa_engine_t* h, int p, const double* angles, int n_angles, double alpha, double* out7) {
+  if (!h) return 1;
+  if (!out7) { h->err = "null output"; return 2; }
+  const int rc = qaoa_cvar(h, p, angles, n_angles, alpha, out7);
+  if (rc) return rc;
+  API_BEGIN(h)
+  d2h(h, out7 + 2, h->d_out, 5 * sizeof(double));     // eval_keeping_state left the evaluation's statistics here
+  API_END(h)
+}
+
 // ---- sharded registers ----------------------------------------------------------------------
 int qaoa_shard_info(qaoa_engine_t* h, int* rank, int* world, int* local_qubits) {
   API_BEGIN(h)

@@ -102,6 +102,7 @@ def load_library():
         "qaoa_shard_finish_device": (ctypes.c_int, [H, ctypes.c_void_p]),
         "qaoa_shard_grover_step": (ctypes.c_int, [H, ctypes.c_int, ctypes.c_int, _c_double_p, ctypes.c_int, _c_double_p, _c_double_p]),
         "qaoa_cvar": (ctypes.c_int, [H, ctypes.c_int, _c_double_p, ctypes.c_int, ctypes.c_double, _c_double_p]),
+        "qaoa_cvar_stats": (ctypes.c_int, [H, ctypes.c_int, _c_double_p, ctypes.c_int, ctypes.c_double, _c_double_p]),
         "qaoa_cost_distribution": (ctypes.c_int, [H, ctypes.c_int, _c_double_p, ctypes.c_int, _c_double_p,
                                                   _c_double_p, _c_double_p]),
         # sharded registers (one engine per GPU)
@@ -375,6 +376,13 @@ class Engine:
         out = np.empty(2, dtype=np.float64)
         self._check(self._lib.qaoa_cvar(self._h, p, _dptr(angles), angles.size, float(alpha), _dptr(out)))
         return float(out[0])
+
+    def cvar_stats(self, angles, alpha):
+        """(E[cost], E[cost^2], min, max, norm, CVaR_alpha) of ONE evaluation (the kept-state run behind the CVaR)"""
+        angles, p = self._angles(angles)
+        out = np.empty(7, dtype=np.float64)
+        self._check(self._lib.qaoa_cvar_stats(self._h, p, _dptr(angles), angles.size, float(alpha), _dptr(out)))
+        return np.array([out[2], out[3], out[4], out[5], out[6], out[0]])
 
     # -- sharded registers: one engine per GPU (include/qaoa_b200.h, "Sharded registers") -------------
     def shard_local_ptr(self, which):

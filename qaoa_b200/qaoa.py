@@ -351,15 +351,19 @@ class QAOA:
             if dist.is_available() and dist.is_initialized():
                 world, rank = dist.get_world_size(), dist.get_rank()
         mine = rows[rank::world] if world > 1 and len(rows) >= world else rows
-        if self._flips_active(mine[0]):
-            res = np.array([self._device_call("energy", r) for r in mine])
+        if self.cvar < 1 and hasattr(eng, "cvar_stats") and not getattr(self.backend, "sharded", False):
+            # one kept-state evaluation per row gives the statistics AND the CVaR (qaoa_cvar_stats)
+            out = np.array([self._device_call("cvar_stats", r, self.cvar) for r in mine])
         else:
-            res = eng.energy_batch(mine)
-        if self.cvar < 1:
-            cv = np.array([self._cvar_of(r) for r in mine])
-        else:
-            cv = res[:, 0]
-        out = np.column_stack([res, cv])
+            if self._flips_active(mine[0]):
+                res = np.array([self._device_call("energy", r) for r in mine])
+            else:
+                res = eng.energy_batch(mine)
+            if self.cvar < 1:
+                cv = np.array([self._cvar_of(r) for r in mine])
+            else:
+                cv = res[:, 0]
+            out = np.column_stack([res, cv])
         if mine is not rows:      # landscape / grid-search points were dealt out over the ranks: put them back in order
             parts = [None] * world
             dist.all_gather_object(parts, out)

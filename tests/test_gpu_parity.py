@@ -272,6 +272,11 @@ def test_device_cvar_weighted_quantile_select(case):
         wo = orc.exact_cvar(diag, np.abs(psi) ** 2, alpha)
         assert abs(got - wo) <= (1e-8 if dtype == "complex128" else 1e-4) * max(1.0, abs(wo)), (case, alpha, got, wo)
     assert abs(E.cvar(ang, 1.0) - E.energy(ang)[0]) <= (1e-9 if dtype == "complex128" else 1e-5) * abs(E.energy(ang)[0]) + 1e-9
+    # one evaluation for the statistics AND the CVaR (qaoa_cvar_stats: what QAOA.loss uses when cvar < 1)
+    st, en = E.cvar_stats(ang, 0.3), E.energy(ang)
+    # (the kept-state evaluation runs another plan -- full register, storing final pass --: complex64 tolerance)
+    assert np.allclose(st[:5], en, rtol=1e-4 if dtype == "complex64" else 1e-9, atol=1e-9), (st, en)
+    assert st[5] == pytest.approx(E.cvar(ang, 0.3), rel=1e-12)
     E.close()
 
 
